@@ -1,0 +1,21 @@
+"""hd_yolo_b200 -- B200-native (sm_100a) post-processing hot path of impromptuRong/hd_yolo.
+
+Only the path from Detect/Segment head outputs to final nuclei instances lives here
+(decode, filter/compact, NMS, score select, masks, tile merge).  Host code is thin Python over
+the C-ABI in ``include/hd_yolo_b200.h``; there is no CPU fallback.
+"""
+from ._lib import HdyError, LIB_PATH, load  # noqa: F401
+from .ops import (  # noqa: F401
+    DetectBatch,
+    HeadSpec,
+    batched_nms,
+    compute_proposals,
+    decode_concat,
+    detect_postprocess,
+    nms,
+    nms_per_image,
+    non_max_suppression,
+    set_iou_compare,
+)
+
+__version__ = "0.1.0"

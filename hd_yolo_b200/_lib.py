@@ -1,0 +1,103 @@
+"""ctypes binding of the C-ABI in include/hd_yolo_b200.h.
+
+The shared library is built in-tree by ``hd_yolo_b200/csrc/build.sh`` (or
+``__graft_entry__.build()``).  There is no CPU fallback and no alternative
+backend: if the library is missing, or a call fails, this module raises.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+import threading
+
+HDY_MAX_LEVELS = 8
+HDY_MAX_ANCHORS = 8
+HDY_MAX_SCORES = 96
+HDY_STATUS_OVERFLOW = 1
+HDY_STATUS_ROUNDS = 2
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libhdyolo_b200.so")
+
+
+class HdyError(RuntimeError):
+    pass
+
+
+class Level(C.Structure):
+    """hdy_level_t"""
+
+    _fields_ = [
+        ("logits", C.c_void_p),
+        ("ny", C.c_int32),
+        ("nx", C.c_int32),
+        ("stride", C.c_float),
+        ("anchor_w", C.c_float * HDY_MAX_ANCHORS),
+        ("anchor_h", C.c_float * HDY_MAX_ANCHORS),
+    ]
+
+
+_vp, _i, _f, _sz = C.c_void_p, C.c_int, C.c_float, C.c_size_t
+_LP = C.POINTER(Level)
+
+# name -> (restype, argtypes); must list every symbol the header declares
+SIGNATURES = {
+    "hdy_version": (C.c_char_p, []),
+    "hdy_last_error": (C.c_char_p, []),
+    "hdy_device_sm_count": (_i, []),
+    "hdy_zero_i32": (_i, [_vp, _sz, _vp]),
+    "hdy_decode_levels": (_i, [_LP, _i, _i, _i, _i, C.POINTER(_vp), _vp]),
+    "hdy_decode_concat": (_i, [_LP, _i, _i, _i, _i, _i, _vp, _vp]),
+    "hdy_filter_compact_logits": (_i, [_LP, _i, _i, _i, _i, _i, _i, _f, _f, _i, _vp, _vp, _vp, _vp, _vp]),
+    "hdy_filter_compact_preds": (_i, [_vp, _i, _i, _i, _f, _f, _i, _vp, _vp, _vp, _vp, _vp]),
+    "hdy_filter_compact_yolo": (_i, [_vp, _i, _i, _i, _f, _i, _vp, _i, _vp, _vp, _vp, _vp, _vp, _vp]),
+    "hdy_nms_workspace_bytes": (_sz, [_i, _i]),
+    "hdy_nms_tiles": (
+        _i,
+        [_vp, _vp, _vp, _vp, _i, _i, _f, _f, _i, _i, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _sz, _vp],
+    ),
+    "hdy_make_keys": (_i, [_vp, _i, _i, _vp, _vp]),
+    "hdy_gather_preds": (_i, [_vp, _i, _i, _i, _i, _vp, _vp, _i, _vp, _vp, _vp]),
+    "hdy_gather_logits": (_i, [_LP, _i, _i, _i, _i, _i, _i, _vp, _vp, _i, _vp, _vp, _vp, _vp]),
+    "hdy_select_scores": (_i, [_vp, _vp, _i, _i, _i, C.POINTER(C.c_int32), _i, _f, _vp, _vp, _vp]),
+}
+
+_lock = threading.Lock()
+_lib = None
+
+
+def load():
+    """Load (once) and return the ctypes handle; raises HdyError if the library is not built."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    with _lock:
+        if _lib is not None:
+            return _lib
+        if not os.path.exists(LIB_PATH):
+            raise HdyError(
+                f"{LIB_PATH} is missing: build it with `bash hd_yolo_b200/csrc/build.sh` "
+                "(or `python -c 'import __graft_entry__ as g; g.build()'`). "
+                "hd_yolo_b200 has no CPU or PyTorch fallback."
+            )
+        lib = C.CDLL(LIB_PATH)
+        for name, (res, args) in SIGNATURES.items():
+            try:
+                fn = getattr(lib, name)
+            except AttributeError as e:  # pragma: no cover
+                raise HdyError(f"{LIB_PATH} does not export {name}; rebuild it") from e
+            fn.restype = res
+            fn.argtypes = args
+        _lib = lib
+    return _lib
+
+
+def check(rc: int, what: str = "") -> None:
+    if rc != 0:
+        msg = load().hdy_last_error().decode("utf-8", "replace")
+        raise HdyError(f"{what or 'hdy call'} failed (rc={rc}): {msg}")
+
+
+def ptr(t):
+    """Device pointer of a torch tensor (or None)."""
+    return None if t is None else C.c_void_p(t.data_ptr())

@@ -1,0 +1,98 @@
+// Shared device/host helpers for the hd_yolo_b200 kernels (sm_100a only).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <string.h>
+#include "hd_yolo_b200.h"
+
+#if defined(__CUDA_ARCH__) && (__CUDA_ARCH__ < 1000)
+#error "hd_yolo_b200 kernels are written for sm_100a (B200) only"
+#endif
+
+namespace hdy {
+
+// ---- host-side error plumbing ------------------------------------------------
+void set_error(const char* fmt, ...);
+int check_launch(const char* what);
+
+#define HDY_REQUIRE(cond, ...)            \
+  do {                                    \
+    if (!(cond)) {                        \
+      hdy::set_error(__VA_ARGS__);        \
+      return HDY_ERR_INVALID;             \
+    }                                     \
+  } while (0)
+
+// ---- exact fp32 arithmetic (the file is also built with -fmad=false) ---------
+// torch's CUDA sigmoid is 1/(1+exp(-x)) in fp32 with the full-precision expf and an
+// IEEE division; keep the same expression so device results track ATen's.
+__device__ __forceinline__ float sigmoidf_ref(float x) { return __fdiv_rn(1.0f, __fadd_rn(1.0f, expf(-x))); }
+
+// Order-preserving map float -> uint32 (ascending).  -0.0 is canonicalised to +0.0 so that
+// ties compare equal exactly as torch's sort does.
+__device__ __forceinline__ uint32_t orderable_u32(float f) {
+  f = f + 0.0f;  // -0.0 -> +0.0
+  uint32_t u = __float_as_uint(f);
+  return (u & 0x80000000u) ? ~u : (u | 0x80000000u);
+}
+__device__ __forceinline__ float from_orderable_u32(uint32_t o) {
+  uint32_t u = (o & 0x80000000u) ? (o & 0x7fffffffu) : ~o;
+  return __uint_as_float(u);
+}
+// Ascending 64-bit key == descending score, ties by ascending index: the order
+// torchvision.ops.nms visits boxes in (scores.sort(stable=True, descending=True)).
+__device__ __forceinline__ uint64_t make_key(float score, uint32_t idx) {
+  return ((uint64_t)(~orderable_u32(score)) << 32) | (uint64_t)idx;
+}
+__device__ __forceinline__ float key_score(uint64_t k) { return from_orderable_u32(~(uint32_t)(k >> 32)); }
+__device__ __forceinline__ uint32_t key_index(uint64_t k) { return (uint32_t)k; }
+
+// IoU > thr exactly as torchvision's kernels evaluate it:
+//   area = (x2-x1)*(y2-y1); w = max(min(x2)-max(x1),0); inter = w*h; iou = inter/(Sa+Sb-inter)
+__device__ __forceinline__ float box_area(const float4& b) {
+  return __fmul_rn(__fsub_rn(b.z, b.x), __fsub_rn(b.w, b.y));
+}
+__device__ __forceinline__ bool iou_gt(const float4& a, const float4& b, float thr) {
+  float xx1 = fmaxf(a.x, b.x), yy1 = fmaxf(a.y, b.y);
+  float xx2 = fminf(a.z, b.z), yy2 = fminf(a.w, b.w);
+  float w = fmaxf(__fsub_rn(xx2, xx1), 0.0f), h = fmaxf(__fsub_rn(yy2, yy1), 0.0f);
+  float inter = __fmul_rn(w, h);
+  if (!(inter > 0.0f)) return false;  // 0/x is 0 or NaN: never > thr (thr >= 0)
+  float uni = __fsub_rn(__fadd_rn(box_area(a), box_area(b)), inter);
+  return __fdiv_rn(inter, uni) > thr;
+}
+
+// streaming 128-bit load that does not pollute L1
+__device__ __forceinline__ float4 ldg_stream_f4(const float4* p) {
+  float4 v;
+  asm volatile("ld.global.nc.L1::no_allocate.v4.f32 {%0,%1,%2,%3}, [%4];"
+               : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w)
+               : "l"(p));
+  return v;
+}
+__device__ __forceinline__ float ldg_stream_f(const float* p) {
+  float v;
+  asm volatile("ld.global.nc.L1::no_allocate.f32 %0, [%1];" : "=f"(v) : "l"(p));
+  return v;
+}
+
+// Device-side copy of the level table (passed by value as a kernel parameter).
+struct LevelDev {
+  const float* ptr;
+  int ny, nx;
+  int rows;        // na*ny*nx rows per tile on this level
+  int row_offset;  // first row of this level inside the concatenated [N] ordering
+  int chunk_begin; // first chunk index of this level inside a tile
+  float stride;
+  float aw[HDY_MAX_ANCHORS], ah[HDY_MAX_ANCHORS];
+};
+struct LevelTable {
+  LevelDev lv[HDY_MAX_LEVELS];
+  int nl, na, no, nc, N, chunks_per_tile, layout;
+};
+
+int build_level_table(const hdy_level_t* levels_host, int nl, int na, int no, int layout, int rows_per_chunk,
+                      LevelTable* out);
+
+}  // namespace hdy

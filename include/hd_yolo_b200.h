@@ -1,0 +1,173 @@
+/*
+ * hd_yolo_b200 -- C-ABI of the B200 (sm_100a) post-processing hot path.
+ *
+ * This is the drop-in boundary: plain pointers, sizes and scalars, no torch
+ * types.  The reference (impromptuRong/hd_yolo) has no FFI layer of its own --
+ * its boundary is a set of Python functions -- so every entry point below
+ * names the reference function (file:line, relative to the reference root)
+ * whose arithmetic it replaces.  The Python mirror with the reference's
+ * call signatures is hd_yolo_b200/ops.py; INTEGRATION.md shows the ctypes
+ * stub a maintainer of the reference would add.
+ *
+ * Conventions
+ *   - every pointer is a DEVICE pointer unless the name ends in _host;
+ *   - every call enqueues work on `stream` and returns without synchronising,
+ *     never allocates, never throws;
+ *   - return value: HDY_OK, or a negative HDY_ERR_* (argument errors are
+ *     detected on the host before anything is launched);
+ *   - capacity overflow is reported asynchronously: the kernel sets bit
+ *     HDY_STATUS_OVERFLOW in *status (device int32) and `counts` holds the
+ *     size that would have been needed;
+ *   - fp32 arithmetic in the reference's operation order (no FMA contraction,
+ *     IEEE division), int32 indices on device (widened to int64 by the host
+ *     mirror where the reference returns int64).
+ */
+#ifndef HD_YOLO_B200_H_
+#define HD_YOLO_B200_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define HDY_OK 0
+#define HDY_ERR_INVALID (-1)   /* bad argument                                  */
+#define HDY_ERR_CAPACITY (-2)  /* host-detectable capacity / workspace problem  */
+#define HDY_ERR_CUDA (-3)      /* a CUDA runtime call failed (see hdy_last_error) */
+
+#define HDY_STATUS_OVERFLOW 1  /* device status bit: a per-tile candidate list overflowed */
+#define HDY_STATUS_ROUNDS 2    /* device status bit: merge rounds budget exhausted        */
+
+#define HDY_MAX_LEVELS 8
+#define HDY_MAX_ANCHORS 8
+#define HDY_MAX_SCORES 96      /* 1 + nc must not exceed this */
+
+typedef void* hdy_stream_t;    /* a cudaStream_t */
+
+#if defined(__GNUC__)
+#define HDY_API __attribute__((visibility("default")))
+#else
+#define HDY_API
+#endif
+
+/* One pyramid level of raw head output (Detect.forward, yolo_head.py:141-145). */
+typedef struct {
+  const float* logits;  /* layout 0: [bs, na, ny, nx, no]   (the permuted tensor the reference decodes)
+                           layout 1: [bs, na*no, ny, nx]     (the 1x1 conv's native output, D0 skipped)   */
+  int32_t ny, nx;
+  float stride;                      /* buffer.stride            yolo_head.py:61   */
+  float anchor_w[HDY_MAX_ANCHORS];   /* anchor_grid = anchor*stride, pixels  yolo_head.py:427 */
+  float anchor_h[HDY_MAX_ANCHORS];
+} hdy_level_t;
+
+/* Library / build information. */
+HDY_API const char* hdy_version(void);
+HDY_API const char* hdy_last_error(void);
+HDY_API int hdy_device_sm_count(void);
+
+/* ------------------------------------------------------------------ decode */
+
+/* D1: Detect.compute_proposals (yolo_head.py:185-213) + _make_grid (:419-429).
+ * out[l] has the layout and shape of levels[l].logits ([bs,na,ny,nx,no]);
+ * layout must be 0.  y = sigmoid(x); xy = (y*2 - 0.5 + grid)*stride;
+ * wh = (y*2)^2 * anchor_grid; the remaining channels are sigmoid(x). */
+HDY_API int hdy_decode_levels(const hdy_level_t* levels_host, int nl, int bs, int na, int no,
+                      float* const* out_host, hdy_stream_t stream);
+
+/* D1+D2: decode + level-id column + concat over levels (yolo_head.py:311-312).
+ * out: [bs, N, no+1] with N = na * sum(ny*nx); last column = level index. */
+HDY_API int hdy_decode_concat(const hdy_level_t* levels_host, int nl, int bs, int na, int no, int layout,
+                      float* out, hdy_stream_t stream);
+
+/* ------------------------------------------------- filter + stream compaction */
+
+/* D0..D2 + B1 + the front half of nms_per_image (utils_general.py:327-338), fused:
+ * reads raw logits once, keeps rows with sigmoid(obj) > conf_thres whose decoded
+ * xyxy box has (x2-x1) >= min_size and (y2-y1) >= min_size, and appends them to the
+ * tile's candidate list (unordered; the key carries the row index).
+ *   cand_keys  [bs, cap] u64 : (~orderable(score) << 32) | row   -- ascending key == reference order
+ *   cand_boxes [bs, cap] f32x4 : xyxy
+ *   counts     [bs] i32 : number of candidates found (may exceed cap -> HDY_STATUS_OVERFLOW)
+ * Rows have `no` >= 5+nc channels (box 4, obj 1, cls nc, then extra channels such as mask
+ * coefficients, which this call ignores).  counts and status must be zeroed by the caller
+ * (hdy_zero_i32). */
+HDY_API int hdy_filter_compact_logits(const hdy_level_t* levels_host, int nl, int bs, int na, int nc, int no, int layout,
+                              float conf_thres, float min_size, int cap,
+                              uint64_t* cand_keys, float* cand_boxes, int32_t* counts, int32_t* status,
+                              hdy_stream_t stream);
+
+/* Front half of nms_per_image (utils_general.py:325-338) on already decoded rows
+ * preds [bs, N, row_len] = (cx, cy, w, h, obj, cls[nc], extra...). Same outputs as above. */
+HDY_API int hdy_filter_compact_preds(const float* preds, int bs, int N, int row_len,
+                             float conf_thres, float min_size, int cap,
+                             uint64_t* cand_keys, float* cand_boxes, int32_t* counts, int32_t* status,
+                             hdy_stream_t stream);
+
+/* Front half of non_max_suppression (utils_general.py:439-491): obj > conf, conf = obj*cls,
+ * best class (multi_label == 0: one candidate per row, key index = row) or every class with
+ * conf > conf_thres (multi_label != 0: key index = row*nc + cls), optional class filter
+ * (class_mask[c] != 0 keeps class c; NULL keeps all).  cand_cls [bs,cap] receives the class
+ * as float, cand_boxes the un-offset xyxy box. */
+HDY_API int hdy_filter_compact_yolo(const float* prediction, int bs, int N, int nc,
+                            float conf_thres, int multi_label, const uint8_t* class_mask, int cap,
+                            uint64_t* cand_keys, float* cand_boxes, float* cand_cls,
+                            int32_t* counts, int32_t* status, hdy_stream_t stream);
+
+/* ------------------------------------------------------------ per-tile NMS */
+
+/* Scratch bytes hdy_nms_tiles needs for (bs, cap). */
+HDY_API size_t hdy_nms_workspace_bytes(int bs, int cap);
+
+/* torchvision.ops.nms semantics per tile (called at utils_general.py:342 and :507):
+ * stable descending score order (ties -> lower index first), greedy suppression with
+ * iou = inter/(area_a+area_b-inter) > iou_thres in fp32, first max_det survivors.
+ * cand_cls may be NULL; otherwise boxes are shifted by cls*class_offset (fp32) before
+ * the IoU test (utils_general.py:505-506).
+ * max_nms > 0: only the max_nms best-scored candidates enter NMS (utils_general.py:501-502).
+ *   keep_idx   [bs, max_det] i32 : key index (row, or row*nc+cls) of survivors, score-descending
+ *   keep_slot  [bs, max_det] i32 : candidate slot of each survivor (into cand_* arrays)
+ *   keep_box   [bs, max_det] f32x4 : un-offset box of each survivor (may be NULL)
+ *   keep_score [bs, max_det] f32 : NMS score of each survivor (may be NULL)
+ *   keep_cls   [bs, max_det] f32 : cand_cls of each survivor (may be NULL)
+ *   keep_counts[bs] i32 */
+HDY_API int hdy_nms_tiles(const uint64_t* cand_keys, const float* cand_boxes, const float* cand_cls,
+                  const int32_t* counts, int bs, int cap, float iou_thres, float class_offset, int max_nms,
+                  int max_det, int32_t* keep_idx, int32_t* keep_slot, float* keep_box, float* keep_score,
+                  float* keep_cls, int32_t* keep_counts, void* workspace, size_t workspace_bytes,
+                  hdy_stream_t stream);
+
+/* Keys for a plain torchvision.ops.nms(boxes, scores, thr) call: scores [bs, seg_len] ->
+ * keys [bs, seg_len] with index = position inside the segment. */
+HDY_API int hdy_make_keys(const float* scores, int bs, int seg_len, uint64_t* keys, hdy_stream_t stream);
+
+/* ---------------------------------------------------------------- epilogues */
+
+/* Tail of nms_per_image (utils_general.py:343): gather surviving rows of preds.
+ *   out_scores [bs, max_det, 1+nc], out_extra [bs, max_det, row_len-5-nc] (may be NULL if no extra) */
+HDY_API int hdy_gather_preds(const float* preds, int bs, int N, int row_len, int nc,
+                     const int32_t* keep_idx, const int32_t* keep_counts, int max_det,
+                     float* out_scores, float* out_extra, hdy_stream_t stream);
+
+/* Scores of surviving rows recomputed from raw logits (sigmoid), + level id + raw extra channels:
+ *   out_scores [bs, max_det, 1+nc], out_level [bs, max_det] f32 (may be NULL),
+ *   out_extra [bs, max_det, no-5-nc] raw (may be NULL) */
+HDY_API int hdy_gather_logits(const hdy_level_t* levels_host, int nl, int bs, int na, int nc, int no, int layout,
+                      const int32_t* keep_idx, const int32_t* keep_counts, int max_det,
+                      float* out_scores, float* out_level, float* out_extra, hdy_stream_t stream);
+
+/* S1: Detect.hierarchical_scores (yolo_head.py:473-479) + score/label select (:336-345), in place
+ * on scores [bs, max_det, 1+nc].  hier_ops_host = n_ops pairs (dst, src): scores[dst] *= scores[src]
+ * applied in order (default tree: (c,0) for c=1..nc).
+ *   out_score [bs,max_det] f32, out_label [bs,max_det] i64 (cls+1, or -100 if cls_score <= conf) */
+HDY_API int hdy_select_scores(float* scores, const int32_t* keep_counts, int bs, int max_det, int nc,
+                      const int32_t* hier_ops_host, int n_ops, float conf_thres,
+                      float* out_score, int64_t* out_label, hdy_stream_t stream);
+
+/* Utility: zero n int32 words (keeps the host mirror free of extra torch launches). */
+HDY_API int hdy_zero_i32(int32_t* p, size_t n, hdy_stream_t stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* HD_YOLO_B200_H_ */

@@ -1,0 +1,161 @@
+"""CPU tests: the oracle (oracle/port.py, oracle/nms_core.c) against the golden vectors generated from
+the real reference (oracle/make_golden.py) and against known-answer cases."""
+import numpy as np
+import pytest
+import torch
+import torchvision
+
+from conftest import load_golden, unpack_list
+from oracle import nms_c, port, synth
+
+
+def _dets(g):
+    i, dets, preds = 0, [], []
+    while f"det{i}" in g:
+        dets.append(torch.from_numpy(g[f"det{i}"]))
+        preds.append(torch.from_numpy(g[f"pred{i}"]))
+        i += 1
+    return dets, preds
+
+
+@pytest.mark.parametrize("name", ["detect_640_l3", "detect_320_l4"])
+def test_decode_matches_reference(name):
+    g = load_golden(name)
+    dets, preds = _dets(g)
+    mine = port.compute_proposals(dets, g["anchors"].tolist(), g["strides"].tolist())
+    for a, b in zip(mine, preds):
+        assert torch.equal(a, b)
+
+
+@pytest.mark.parametrize("name", ["detect_640_l3", "detect_320_l4"])
+def test_compute_outputs_matches_reference(name):
+    g = load_golden(name)
+    _, preds = _dets(g)
+    params = {'conf_thres': float(g["conf_thres"]), 'iou_thres': float(g["iou_thres"]), 'max_det': int(g["max_det"])}
+    mine = port.compute_outputs([p.clone() for p in preds], int(g["nc"]), params)
+    ref = unpack_list(g, "out", ["boxes", "scores", "labels"])
+    assert len(mine) == len(ref)
+    for a, b in zip(mine, ref):
+        assert len(b["boxes"]) > 0
+        for k in ("boxes", "scores", "labels"):
+            assert torch.equal(a[k], b[k]), k
+
+
+@pytest.mark.parametrize("tag", ["a", "b", "c"])
+def test_nms_per_image_matches_reference(tag):
+    g = load_golden("nms_rows")
+    preds = torch.from_numpy(g["preds"])
+    conf, iou, md = g[f"npi_{tag}_params"].tolist()
+    mine = port.nms_per_image(preds.clone(), int(g["nc"]), conf, iou, int(md))
+    ref = unpack_list(g, f"npi_{tag}", ["boxes", "scores", "extra"])
+    for a, b in zip(mine, ref):
+        for k in ("boxes", "scores", "extra"):
+            assert torch.equal(a[k], b[k])
+    assert len(ref[2]["boxes"]) == 0  # the empty image stays empty
+
+
+YOLO_KW = {"a": dict(conf_thres=0.25, iou_thres=0.45, max_det=300),
+           "b": dict(conf_thres=0.1, iou_thres=0.45, multi_label=True, max_det=1000),
+           "c": dict(conf_thres=0.25, iou_thres=0.5, agnostic=True, max_det=300),
+           "d": dict(conf_thres=0.2, iou_thres=0.45, classes=[1, 3], max_det=300)}
+
+
+@pytest.mark.parametrize("tag", list(YOLO_KW))
+def test_non_max_suppression_matches_reference(tag):
+    g = load_golden("nms_rows")
+    nc = int(g["nc"])
+    pred = torch.from_numpy(g["preds"])[..., :5 + nc].contiguous()
+    mine = port.non_max_suppression(pred.clone(), **YOLO_KW[tag])
+    sizes = g[f"yolo_{tag}_sizes"].tolist()
+    assert [len(m) for m in mine] == sizes
+    assert torch.equal(torch.cat(mine), torch.from_numpy(g[f"yolo_{tag}_out"]))
+
+
+def test_hierarchical_scores_tree():
+    g = load_golden("hier_tree")
+    desc = {}
+    for k, v in zip(g["ops_src"].tolist(), g["ops_dst"].tolist()):
+        desc.setdefault(k, []).append(v)
+    x = torch.from_numpy(g["scores_in"]).clone()
+    assert torch.equal(port.hierarchical_scores(x, desc), torch.from_numpy(g["scores_out"]))
+
+
+def test_tile_merge_matches_reference():
+    g = load_golden("tile_merge")
+    H, W = g["image_size"].tolist()
+    rois = port.sliding_window_scanner((H, W), tuple(g["roi_size"].tolist()), int(g["overlap"]))
+    assert torch.equal(rois, torch.from_numpy(g["rois"]))
+    tiles = unpack_list(g, "tile", ["boxes", "scores", "labels"])
+    for t, r in zip(tiles, rois):
+        t["roi"] = r
+    merged = port.merge_outputs(tiles)
+    for k in ("boxes", "scores", "labels"):
+        assert torch.equal(merged[k], torch.from_numpy(g["merged_" + k]))
+    conf, iou, md = g["params"].tolist()
+    final = port.ensemble_merge([{'det': merged}], {'conf_thres': conf, 'iou_thres': iou, 'max_det': md})['det']
+    for k in ("boxes", "scores", "labels"):
+        assert torch.equal(final[k], torch.from_numpy(g["final_" + k]))
+    assert len(final["boxes"]) < len(merged["boxes"])  # the overlap bands did hold duplicates
+
+
+def test_sliding_window_scanner_cases():
+    g = load_golden("tile_merge")
+    big = port.sliding_window_scanner((100000, 100000), (1024, 1024), 64)
+    assert len(big) == int(g["scan_slide_n"]) == 11025
+    assert torch.equal(big[:3], torch.from_numpy(g["scan_slide_head"]))
+    assert torch.equal(big[-3:], torch.from_numpy(g["scan_slide_tail"]))
+    assert big[-1].tolist() == [99840.0, 99840.0, 100000.0, 100000.0]
+    assert torch.equal(port.sliding_window_scanner((300, 500), (128, 200), 0), torch.from_numpy(g["scan_small"]))
+    assert torch.equal(port.sliding_window_scanner((100, 100), (128, 128), 16), torch.from_numpy(g["scan_fit"]))
+
+
+def test_paste_masks_matches_reference():
+    g = load_golden("paste_masks")
+    H, W = g["shape"].tolist()
+    out = port.paste_masks_in_image(torch.from_numpy(g["masks"]), torch.from_numpy(g["boxes"]), (H, W), padding=1)
+    assert torch.equal(out, torch.from_numpy(g["out"]))
+
+
+# ---------------------------------------------------------------- known answers for the third-party NMS
+def _both(boxes, scores, thr):
+    b = torch.tensor(boxes, dtype=torch.float32)
+    s = torch.tensor(scores, dtype=torch.float32)
+    tv = torchvision.ops.nms(b, s, thr).tolist()
+    c = nms_c.nms(b.numpy(), s.numpy(), thr).tolist()
+    assert tv == c
+    return tv
+
+
+def test_nms_known_answers():
+    assert _both([[0, 0, 10, 10]] * 3, [.5, .5, .5], 0.5) == [0]                     # ties -> lowest index
+    assert _both([[0, 0, 10, 10], [0, 0, 10, 5]], [.9, .8], 0.5) == [0, 1]            # iou == thr is kept
+    assert _both([[0, 0, 10, 10], [0, 0, 10, 5]], [.9, .8], 0.4999) == [0]
+    assert _both([[5, 5, 5, 5], [5, 5, 5, 5]], [.9, .8], 0.1) == [0, 1]               # 0/0 = NaN never suppresses
+    assert _both([[0, 0, 4, 4], [10, 10, 14, 14], [0, 0, 4, 4]], [.1, .9, .5], 0.5) == [1, 2]  # score order
+
+
+def test_nms_c_vs_torchvision_random():
+    g = torch.Generator().manual_seed(11)
+    for n, span, thr in [(1, 50, 0.5), (300, 60, 0.45), (2500, 320, 0.45), (2500, 200, 0.3), (800, 40, 0.6)]:
+        c = torch.rand((n, 2), generator=g) * span
+        wh = torch.rand((n, 2), generator=g) * 30 + 2
+        b = torch.cat([c - wh / 2, c + wh / 2], 1)
+        s = (torch.rand(n, generator=g) * 50).round() / 50
+        assert torchvision.ops.nms(b, s, thr).tolist() == nms_c.nms(b.numpy(), s.numpy(), thr).tolist()
+
+
+def test_conf_threshold_is_fp32():
+    # `tensor_fp32 > 0.15` compares against float32(0.15)
+    x = torch.tensor([np.float32(0.15)])
+    assert not bool((x > 0.15).item())
+    assert float(np.float32(0.15)) > 0.15
+
+
+def test_synth_candidate_count():
+    dets = synth.nuclei_logits(2, 320, 4, 250, seed=7, conf=0.25)
+    preds = port.compute_proposals(dets, synth.ANCHORS_3, synth.STRIDES_3)
+    cat = port.concat_levels(preds)
+    n = (cat[..., 4] > 0.25).sum(1)
+    assert ((n > 170) & (n < 330)).all()
+    boxes = cat[..., 2:4][cat[..., 4] > 0.25]
+    assert boxes.min() > 9 and boxes.max() < 40
