@@ -66,6 +66,47 @@ def _stream():
     return C.c_void_p(torch.cuda.current_stream().cuda_stream)
 
 
+class KernelProfile:
+    """Optional per-call CUDA-event timing of the C-ABI launches (used by bench.py for the roofline
+    numbers) and a launch counter.  Events are recorded on the stream the kernels are launched on."""
+
+    # kernels launched per C-ABI call when it is not 1
+    def __init__(self):
+        self.enabled = False
+        self.records = []   # (name, start_event, end_event)
+        self.launches = 0
+
+    def reset(self):
+        self.records.clear()
+        self.launches = 0
+
+    def summary(self):
+        """name -> (calls, total_ms); synchronises."""
+        torch.cuda.synchronize()
+        out = {}
+        for name, s, e in self.records:
+            c, t = out.get(name, (0, 0.0))
+            out[name] = (c + 1, t + s.elapsed_time(e))
+        return out
+
+
+profile = KernelProfile()
+
+
+def _call(name: str, *args, launches: int = 1) -> None:
+    fn = getattr(_lib.load(), name)
+    if profile.enabled:
+        s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        s.record()
+        rc = fn(*args)
+        e.record()
+        profile.records.append((name, s, e))
+    else:
+        rc = fn(*args)
+    profile.launches += launches
+    check(rc, name)
+
+
 def _need_cuda(t: torch.Tensor, name: str) -> None:
     if not isinstance(t, torch.Tensor) or not t.is_cuda:
         raise HdyError(f"{name} must be a CUDA tensor: hd_yolo_b200 has no CPU fallback")
@@ -168,7 +209,7 @@ def compute_proposals(dets: List[torch.Tensor], spec: HeadSpec) -> List[torch.Te
     levels, bs, _ = spec.levels(dets, 0)
     outs = [torch.empty_like(d) for d in dets]
     out_ptrs = (C.c_void_p * spec.nl)(*[o.data_ptr() for o in outs])
-    check(lib.hdy_decode_levels(levels, spec.nl, bs, spec.na, spec.no, out_ptrs, _stream()), "hdy_decode_levels")
+    _call("hdy_decode_levels", levels, spec.nl, bs, spec.na, spec.no, out_ptrs, _stream(), launches=spec.nl)
     return outs
 
 
@@ -179,8 +220,7 @@ def decode_concat(dets: List[torch.Tensor], spec: HeadSpec, layout: int = 0) -> 
     levels, bs, shapes = spec.levels(dets, layout)
     N = spec.rows_per_tile(shapes)
     out = torch.empty((bs, N, spec.no + 1), dtype=torch.float32, device=dets[0].device)
-    check(lib.hdy_decode_concat(levels, spec.nl, bs, spec.na, spec.no, layout, ptr(out), _stream()),
-          "hdy_decode_concat")
+    _call("hdy_decode_concat", levels, spec.nl, bs, spec.na, spec.no, layout, ptr(out), _stream(), launches=spec.nl)
     return out
 
 
@@ -196,7 +236,7 @@ class _Cand:
         self.cls = _scratch.get(device, tag + "cls", n * 4) if with_cls else None
         # counts[bs] followed by one status word
         self.counts = torch.empty(bs + 1, dtype=torch.int32, device=device)
-        check(_lib.load().hdy_zero_i32(ptr(self.counts), bs + 1, _stream()), "hdy_zero_i32")
+        _call("hdy_zero_i32", ptr(self.counts), bs + 1, _stream())
 
     @property
     def status_ptr(self):
@@ -217,13 +257,10 @@ def _run_nms(cand: _Cand, iou_thres: float, max_det: int, class_offset: float = 
     keep_counts = torch.empty(bs, dtype=torch.int32, device=dev)
     wbytes = lib.hdy_nms_workspace_bytes(bs, cap)
     ws = _scratch.get(dev, "nms_ws", wbytes) if wbytes else None
-    check(
-        lib.hdy_nms_tiles(ptr(cand.keys), ptr(cand.boxes), ptr(cand.cls), ptr(cand.counts), bs, cap,
+    _call("hdy_nms_tiles", ptr(cand.keys), ptr(cand.boxes), ptr(cand.cls), ptr(cand.counts), bs, cap,
                           _iou_thr_f32(iou_thres), float(class_offset), int(max_nms), md, ptr(keep_idx),
                           ptr(keep_slot), ptr(keep_box), ptr(keep_score), ptr(keep_cls), ptr(keep_counts),
-                          ptr(ws), wbytes, _stream()),
-        "hdy_nms_tiles",
-    )
+                          ptr(ws), wbytes, _stream())
     return keep_idx, keep_slot, keep_box, keep_score, keep_cls, keep_counts, md
 
 
@@ -269,20 +306,14 @@ def nms_per_image(preds: torch.Tensor, nc: int, conf_thres: float = 0.25, iou_th
         return [{'boxes': z((0, 4)), 'scores': z((0, 1 + nc)), 'extra': z((0, E))} for _ in range(bs)]
     cap = N
     cand = _Cand(dev, bs, cap)
-    check(
-        lib.hdy_filter_compact_preds(ptr(preds), bs, N, row_len, _conf_thr_f32(conf_thres), 2.0, cap,
+    _call("hdy_filter_compact_preds", ptr(preds), bs, N, row_len, _conf_thr_f32(conf_thres), 2.0, cap,
                                      ptr(cand.keys), ptr(cand.boxes), ptr(cand.counts), cand.status_ptr,
-                                     _stream()),
-        "hdy_filter_compact_preds",
-    )
+                                     _stream())
     keep_idx, _, keep_box, _, _, keep_counts, md = _run_nms(cand, iou_thres, max_det)
     out_scores = torch.empty((bs, md, 1 + nc), dtype=torch.float32, device=dev)
     out_extra = torch.empty((bs, md, E), dtype=torch.float32, device=dev)
-    check(
-        lib.hdy_gather_preds(ptr(preds), bs, N, row_len, nc, ptr(keep_idx), ptr(keep_counts), md,
-                             ptr(out_scores), ptr(out_extra) if E > 0 else None, _stream()),
-        "hdy_gather_preds",
-    )
+    _call("hdy_gather_preds", ptr(preds), bs, N, row_len, nc, ptr(keep_idx), ptr(keep_counts), md,
+                             ptr(out_scores), ptr(out_extra) if E > 0 else None, _stream())
     kc = _counts_to_host(cand, keep_counts)
     return [{'boxes': keep_box[i, :k], 'scores': out_scores[i, :k], 'extra': out_extra[i, :k]}
             for i, k in enumerate(kc)]
@@ -336,12 +367,9 @@ def non_max_suppression(prediction: torch.Tensor, conf_thres: float = 0.25, iou_
             if 0 <= int(c) < nc and float(c) == int(c):
                 cm[int(c)] = 1
         cmask = cm.to(dev)
-    check(
-        lib.hdy_filter_compact_yolo(ptr(prediction), bs, N, nc, _conf_thr_f32(conf_thres), int(multi_label),
+    _call("hdy_filter_compact_yolo", ptr(prediction), bs, N, nc, _conf_thr_f32(conf_thres), int(multi_label),
                                     ptr(cmask), cap, ptr(cand.keys), ptr(cand.boxes), ptr(cand.cls),
-                                    ptr(cand.counts), cand.status_ptr, _stream()),
-        "hdy_filter_compact_yolo",
-    )
+                                    ptr(cand.counts), cand.status_ptr, _stream())
     _, _, keep_box, keep_score, keep_cls, keep_counts, md = _run_nms(
         cand, iou_thres, max_det, class_offset=0.0 if agnostic else float(max_wh), max_nms=max_nms, want_cls=True)
     out = torch.cat([keep_box, keep_score[..., None], keep_cls[..., None]], -1)
@@ -364,7 +392,7 @@ def nms(boxes: torch.Tensor, scores: torch.Tensor, iou_threshold: float) -> torc
     boxes = _aligned16(boxes.contiguous())
     scores = scores.contiguous()
     keys = torch.empty(n, dtype=torch.int64, device=dev)
-    check(lib.hdy_make_keys(ptr(scores), 1, n, ptr(keys), _stream()), "hdy_make_keys")
+    _call("hdy_make_keys", ptr(scores), 1, n, ptr(keys), _stream())
     cand = _Cand.__new__(_Cand)
     cand.bs, cand.cap = 1, n
     cand.keys, cand.boxes, cand.cls = keys, boxes, None
@@ -387,7 +415,7 @@ def batched_nms(boxes: torch.Tensor, scores: torch.Tensor, idxs: torch.Tensor, i
     scores = scores.contiguous()
     off = float((boxes.max() + 1.0).item())  # max_coordinate + 1, fp32
     keys = torch.empty(n, dtype=torch.int64, device=dev)
-    check(lib.hdy_make_keys(ptr(scores), 1, n, ptr(keys), _stream()), "hdy_make_keys")
+    _call("hdy_make_keys", ptr(scores), 1, n, ptr(keys), _stream())
     cand = _Cand.__new__(_Cand)
     cand.bs, cand.cap = 1, n
     cand.keys, cand.boxes = keys, boxes
@@ -462,29 +490,20 @@ def detect_postprocess(dets: List[torch.Tensor], spec: HeadSpec, conf_thres: flo
     nc, no = spec.nc, spec.no
     cand = _Cand(dev, bs, cap)
     cthr = _conf_thr_f32(conf_thres)
-    check(
-        lib.hdy_filter_compact_logits(levels, spec.nl, bs, spec.na, nc, no, layout, cthr, float(min_size), cap,
+    _call("hdy_filter_compact_logits", levels, spec.nl, bs, spec.na, nc, no, layout, cthr, float(min_size), cap,
                                       ptr(cand.keys), ptr(cand.boxes), ptr(cand.counts), cand.status_ptr,
-                                      _stream()),
-        "hdy_filter_compact_logits",
-    )
+                                      _stream())
     keep_idx, _, keep_box, _, _, keep_counts, md = _run_nms(cand, iou_thres, max_det)
     scores_full = torch.empty((bs, md, 1 + nc), dtype=torch.float32, device=dev)
     lvl = torch.empty((bs, md), dtype=torch.float32, device=dev)
     ne = no - 5 - nc
     extra = torch.empty((bs, md, ne), dtype=torch.float32, device=dev) if ne > 0 else None
-    check(
-        lib.hdy_gather_logits(levels, spec.nl, bs, spec.na, nc, no, layout, ptr(keep_idx), ptr(keep_counts), md,
-                              ptr(scores_full), ptr(lvl), ptr(extra), _stream()),
-        "hdy_gather_logits",
-    )
+    _call("hdy_gather_logits", levels, spec.nl, bs, spec.na, nc, no, layout, ptr(keep_idx), ptr(keep_counts), md,
+                              ptr(scores_full), ptr(lvl), ptr(extra), _stream())
     score = torch.empty((bs, md), dtype=torch.float32, device=dev)
     label = torch.empty((bs, md), dtype=torch.int64, device=dev)
     ops = default_hier_ops(nc) if hier_ops is None else hier_ops
     flat = (C.c_int32 * (2 * len(ops)))(*[v for p in ops for v in p])
-    check(
-        lib.hdy_select_scores(ptr(scores_full), ptr(keep_counts), bs, md, nc, flat, len(ops), cthr, ptr(score),
-                              ptr(label), _stream()),
-        "hdy_select_scores",
-    )
+    _call("hdy_select_scores", ptr(scores_full), ptr(keep_counts), bs, md, nc, flat, len(ops), cthr, ptr(score),
+                              ptr(label), _stream())
     return DetectBatch(keep_box, scores_full, score, label, lvl, extra, keep_idx, keep_counts, cand.counts, md)

@@ -1,4 +1,4 @@
-"""ORACLE / benchmark input synthesis (CPU, seeded).  Shared by the golden generator, the tests and
+"""Synthetic head-output generator (seeded).  Shared by bench.py, the tests and the golden generator
 bench.py so that oracle and kernels always see identical bytes."""
 import math
 from typing import List, Sequence, Tuple

@@ -12,7 +12,8 @@ import sys
 import numpy as np
 import torch
 
-from . import ref_shim, synth
+from . import ref_shim
+from hd_yolo_b200 import synth
 
 OUT = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "tests", "golden")
 

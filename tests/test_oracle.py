@@ -6,7 +6,8 @@ import torch
 import torchvision
 
 from conftest import load_golden, unpack_list
-from oracle import nms_c, port, synth
+from oracle import nms_c, port
+from hd_yolo_b200 import synth
 
 
 def _dets(g):
