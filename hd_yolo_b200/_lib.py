@@ -57,9 +57,21 @@ SIGNATURES = {
         [_vp, _vp, _vp, _vp, _i, _i, _f, _f, _i, _i, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _sz, _vp],
     ),
     "hdy_make_keys": (_i, [_vp, _i, _i, _vp, _vp]),
+    "hdy_debug_nms_phases": (_i, [_vp]),
     "hdy_gather_preds": (_i, [_vp, _i, _i, _i, _i, _vp, _vp, _i, _vp, _vp, _vp]),
     "hdy_gather_logits": (_i, [_LP, _i, _i, _i, _i, _i, _i, _vp, _vp, _i, _vp, _vp, _vp, _vp]),
     "hdy_select_scores": (_i, [_vp, _vp, _i, _i, _i, C.POINTER(C.c_int32), _i, _f, _vp, _vp, _vp]),
+    "hdy_mask_select": (_i, [_vp, _vp, _vp, _i, _i, _i, _vp, _vp]),
+    "hdy_paste_masks": (_i, [_vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _i, _vp, _vp]),
+    "hdy_paste_geometry": (_i, [_vp, _i, _i, _i, _i, _i, _vp, _vp, _vp]),
+    "hdy_paste_masks_packed": (_i, [_vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _i, _vp, C.c_int64, _vp, _vp]),
+    "hdy_unpack_masks": (_i, [_vp, _vp, _vp, _i, _i, _i, _vp, _vp]),
+    "hdy_process_mask": (_i, [_vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _i, _i, _vp, _vp]),
+    "hdy_process_mask_geometry": (_i, [_vp, _vp, _i, _i, _i, _i, _i, _i, _i, _vp, _vp, _vp]),
+    "hdy_process_mask_packed": (
+        _i,
+        [_vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _i, _i, _vp, C.c_int64, _vp, _vp],
+    ),
 }
 
 _lock = threading.Lock()

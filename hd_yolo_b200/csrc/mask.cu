@@ -1,0 +1,545 @@
+// Mask post-processing.
+//
+// (A) reference parity  -- M1: sigmoid + per-label channel gather (yolo_head.py:332, 346-353)
+//                          M2: torchvision paste_masks_in_image(masks, boxes, (H,W), padding=1) as called at
+//                              val_nuclei.py:169-176 / evaluation.py:122-123
+//                          M3: > 0.5 (the reference only thresholds for display, image_utils.py:331-340)
+// (B) north-star        -- process_mask (ultralytics/yolov5 v7 utils/segment/general.py): K=32 prototype x
+//                          coefficient contraction in fp32 FFMA, sigmoid, box crop, optional bilinear upsample,
+//                          > 0.5.
+//
+// Output layouts:
+//   dense   : exactly the reference tensors ([K,H,W] fp32), for drop-in parity; the canvas is cleared with
+//             one memset and only the paste window is computed.
+//   packed  : box-cropped bit planes.  geom[i] = {x0, y0, w, h} (window in output pixels), offsets[i] = first
+//             32-bit word of mask i; row r of mask i occupies ceil(w/32) words, bit (x - x0) & 31 of word
+//             (x - x0) >> 5, set iff value > 0.5.  This is the layout the throughput numbers use: a nucleus
+//             costs ~100-300 bytes instead of H*W*4.
+//
+// ATen's bilinear (align_corners=False): scale = in/out (fp32); src = scale*(dst+0.5)-0.5, clamped at 0;
+// i0 = (int)src; i1 = min(i0+1, in-1); l1 = src-i0; l0 = 1-l1; v = l0y*(l0x*v00 + l1x*v01) + l1y*(l0x*v10 + l1x*v11).
+#include "hdy_common.cuh"
+
+namespace hdy {
+
+struct Lerp {
+  int i0, i1;
+  float l0, l1;
+};
+
+__device__ __forceinline__ Lerp lerp_coord(int dst, float scale, int in_size) {
+  float src = __fsub_rn(__fmul_rn(scale, __fadd_rn((float)dst, 0.5f)), 0.5f);
+  if (src < 0.f) src = 0.f;
+  Lerp L;
+  L.i0 = min((int)src, in_size - 1);
+  L.i1 = min(L.i0 + 1, in_size - 1);
+  L.l1 = fminf(fmaxf(__fsub_rn(src, (float)L.i0), 0.f), 1.f);
+  L.l0 = __fsub_rn(1.0f, L.l1);
+  return L;
+}
+
+__device__ __forceinline__ float bilerp(float v00, float v01, float v10, float v11, const Lerp& X, const Lerp& Y) {
+  const float top = __fadd_rn(__fmul_rn(X.l0, v00), __fmul_rn(X.l1, v01));
+  const float bot = __fadd_rn(__fmul_rn(X.l0, v10), __fmul_rn(X.l1, v11));
+  return __fadd_rn(__fmul_rn(Y.l0, top), __fmul_rn(Y.l1, bot));
+}
+
+// ---------------------------------------------------------------------------------------------- M1
+__global__ void mask_select_kernel(const float* __restrict__ logits, const int64_t* __restrict__ labels,
+                                   const int64_t* __restrict__ mask_indices, int K, int C, int MM,
+                                   float* __restrict__ out) {
+  const int i = blockIdx.x;
+  if (i >= K) return;
+  // mask_labels = mask_indices[labels.clamp(min=0)]; masks[mask_labels < 0] = 0       yolo_head.py:348-353
+  const int64_t lab = labels[i] < 0 ? 0 : labels[i];
+  const int64_t ch = mask_indices[lab];
+  const float* src = logits + ((size_t)i * C + (ch < 0 ? 0 : ch)) * MM;
+  float* dst = out + (size_t)i * MM;
+  for (int e = threadIdx.x; e < MM; e += blockDim.x) dst[e] = ch < 0 ? 0.f : sigmoidf_ref(src[e]);
+}
+
+// ------------------------------------------------------------------------------------------ M2 geometry
+struct PasteGeom {
+  int bx0, by0;  // expanded integer box origin (may be negative)
+  int rw, rh;    // resize target (>= 1)
+  int x0, y0;    // paste window origin inside the image
+  int w, h;      // paste window size (0 if nothing lands in the image)
+};
+
+__device__ __forceinline__ PasteGeom paste_geometry(const float4 b, float scale, int H, int W) {
+  // expand_boxes (torchvision roi_heads.py): half extents scaled about the centre, then .to(int64) (truncation)
+  float w_half = __fmul_rn(__fmul_rn(__fsub_rn(b.z, b.x), 0.5f), scale);
+  float h_half = __fmul_rn(__fmul_rn(__fsub_rn(b.w, b.y), 0.5f), scale);
+  const float xc = __fmul_rn(__fadd_rn(b.z, b.x), 0.5f), yc = __fmul_rn(__fadd_rn(b.w, b.y), 0.5f);
+  const long long x0 = (long long)__fsub_rn(xc, w_half), x1 = (long long)__fadd_rn(xc, w_half);
+  const long long y0 = (long long)__fsub_rn(yc, h_half), y1 = (long long)__fadd_rn(yc, h_half);
+  PasteGeom g;
+  long long rw = x1 - x0 + 1, rh = y1 - y0 + 1;  // TO_REMOVE = 1
+  rw = rw < 1 ? 1 : rw;
+  rh = rh < 1 ? 1 : rh;
+  const long long px0 = x0 > 0 ? x0 : 0, px1 = (x1 + 1 < W) ? x1 + 1 : W;
+  const long long py0 = y0 > 0 ? y0 : 0, py1 = (y1 + 1 < H) ? y1 + 1 : H;
+  const long long big = 1ll << 30;
+  g.bx0 = (int)max(-big, min(big, x0));
+  g.by0 = (int)max(-big, min(big, y0));
+  g.rw = (int)min(big, rw);
+  g.rh = (int)min(big, rh);
+  if (px1 > px0 && py1 > py0 && x0 > -big && y0 > -big) {
+    g.x0 = (int)px0;
+    g.y0 = (int)py0;
+    g.w = (int)(px1 - px0);
+    g.h = (int)(py1 - py0);
+  } else {
+    g.x0 = g.y0 = g.w = g.h = 0;
+  }
+  return g;
+}
+
+// words of the cropped bit plane per mask, then an exclusive scan (single CTA, chunked) -> offsets[K+1]
+__global__ void __launch_bounds__(1024) scan_words_kernel(const int32_t* __restrict__ geom4, long long K,
+                                                          int64_t* __restrict__ offsets) {
+  __shared__ long long warp_sum[32];
+  __shared__ long long carry;
+  if (threadIdx.x == 0) carry = 0;
+  __syncthreads();
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  for (long long base = 0; base < K; base += 1024) {
+    const long long i = base + threadIdx.x;
+    long long v = 0;
+    if (i < K) v = (long long)((geom4[4 * i + 2] + 31) >> 5) * geom4[4 * i + 3];
+    long long incl = v;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      long long u = __shfl_up_sync(0xffffffffu, incl, o);
+      if (lane >= o) incl += u;
+    }
+    if (lane == 31) warp_sum[warp] = incl;
+    __syncthreads();
+    if (warp == 0) {
+      long long s = warp_sum[lane], t = s;
+#pragma unroll
+      for (int o = 1; o < 32; o <<= 1) {
+        long long u = __shfl_up_sync(0xffffffffu, t, o);
+        if (lane >= o) t += u;
+      }
+      warp_sum[lane] = t - s;
+    }
+    __syncthreads();
+    const long long excl = carry + warp_sum[warp] + incl - v;
+    if (i < K) offsets[i] = excl;
+    __syncthreads();
+    if (threadIdx.x == 1023) carry = excl + v;
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) offsets[K] = carry;
+}
+
+__global__ void paste_geometry_kernel(const float4* __restrict__ boxes, int K, float scale, int H, int W,
+                                      int32_t* __restrict__ geom4) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= K) return;
+  const PasteGeom g = paste_geometry(boxes[i], scale, H, W);
+  reinterpret_cast<int4*>(geom4)[i] = make_int4(g.x0, g.y0, g.w, g.h);
+}
+
+// One CTA per mask.  The (M+2p)^2 zero-padded mask is staged in shared memory (sigmoid applied on the way if
+// the source holds logits), then the paste window is produced row by row.
+template <bool PACKED>
+__global__ void __launch_bounds__(128) paste_masks_kernel(
+    const float* __restrict__ src, const int32_t* __restrict__ channel, const float4* __restrict__ boxes, int K,
+    int C, int M, int pad, int apply_sigmoid, int H, int W, float scale, float* __restrict__ out_dense,
+    const int64_t* __restrict__ offsets, uint32_t* __restrict__ bits, long long capacity_words,
+    int32_t* __restrict__ status) {
+  extern __shared__ float sm[];
+  const int i = blockIdx.x;
+  const int Mp = M + 2 * pad;
+  const int ch = channel ? channel[i] : 0;
+  for (int e = threadIdx.x; e < Mp * Mp; e += blockDim.x) {
+    const int y = e / Mp - pad, x = e % Mp - pad;
+    float v = 0.f;
+    if (ch >= 0 && x >= 0 && x < M && y >= 0 && y < M) {
+      v = src[((size_t)i * C + ch) * M * M + y * M + x];
+      if (apply_sigmoid) v = sigmoidf_ref(v);
+    }
+    sm[e] = v;
+  }
+  __syncthreads();
+  const PasteGeom g = paste_geometry(boxes[i], scale, H, W);
+  if (g.w <= 0 || g.h <= 0) return;
+  const float sx = __fdiv_rn((float)Mp, (float)g.rw), sy = __fdiv_rn((float)Mp, (float)g.rh);
+  if (!PACKED) {
+    float* o = out_dense + (size_t)i * H * W;
+    for (int e = threadIdx.x; e < g.w * g.h; e += blockDim.x) {
+      const int yy = e / g.w, xx = e - yy * g.w;
+      const Lerp Y = lerp_coord(g.y0 + yy - g.by0, sy, Mp), X = lerp_coord(g.x0 + xx - g.bx0, sx, Mp);
+      o[(size_t)(g.y0 + yy) * W + g.x0 + xx] =
+          bilerp(sm[Y.i0 * Mp + X.i0], sm[Y.i0 * Mp + X.i1], sm[Y.i1 * Mp + X.i0], sm[Y.i1 * Mp + X.i1], X, Y);
+    }
+  } else {
+    const int wpr = (g.w + 31) >> 5;
+    const long long off = offsets[i];
+    if (off + (long long)wpr * g.h > capacity_words) {
+      if (threadIdx.x == 0) atomicOr(status, HDY_STATUS_OVERFLOW);
+      return;
+    }
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = blockDim.x >> 5;
+    for (int wi = warp; wi < wpr * g.h; wi += nw) {
+      const int yy = wi / wpr, xw = wi - yy * wpr;
+      const int xx = (xw << 5) + lane;
+      bool bit = false;
+      if (xx < g.w) {
+        const Lerp Y = lerp_coord(g.y0 + yy - g.by0, sy, Mp), X = lerp_coord(g.x0 + xx - g.bx0, sx, Mp);
+        bit = bilerp(sm[Y.i0 * Mp + X.i0], sm[Y.i0 * Mp + X.i1], sm[Y.i1 * Mp + X.i0], sm[Y.i1 * Mp + X.i1], X, Y) >
+              0.5f;
+      }
+      const unsigned word = __ballot_sync(0xffffffffu, bit);
+      if (lane == 0) bits[off + wi] = word;
+    }
+  }
+}
+
+__global__ void unpack_masks_kernel(const int32_t* __restrict__ geom4, const int64_t* __restrict__ offsets,
+                                    const uint32_t* __restrict__ bits, int H, int W, uint8_t* __restrict__ out) {
+  const int i = blockIdx.x;
+  const int4 g = reinterpret_cast<const int4*>(geom4)[i];
+  const int wpr = (g.z + 31) >> 5;
+  const long long off = offsets[i];
+  uint8_t* o = out + (size_t)i * H * W;
+  for (int e = threadIdx.x; e < g.z * g.w; e += blockDim.x) {
+    const int yy = e / g.z, xx = e - yy * g.z;
+    const uint32_t wd = bits[off + (long long)yy * wpr + (xx >> 5)];
+    o[(size_t)(g.y + yy) * W + g.x + xx] = (wd >> (xx & 31)) & 1u;
+  }
+}
+
+// ------------------------------------------------------------------------------------- (B) process_mask
+// Window of mask i in output pixels.  crop_mask keeps proto pixels with x1d <= col < x2d, y1d <= row < y2d
+// (float compares against arange); with upsample the bilinear taps spread every kept pixel over its
+// neighbours, so the output window is the pre-image of [p0-1, p1) under i0 = floor(src).
+struct PMGeom {
+  float x1d, y1d, x2d, y2d;  // down-scaled box (fp32, as the reference computes it)
+  int px0, py0, px1, py1;    // kept proto pixel range [p0, p1)
+  int x0, y0, w, h;          // output window
+};
+
+__device__ __forceinline__ int ceil_to_int_clamped(float v, int lo, int hi) {
+  if (!(v > (float)lo)) return lo;  // also NaN
+  if (v >= (float)hi) return hi;
+  return (int)ceilf(v);
+}
+
+__device__ __forceinline__ PMGeom pm_geometry(const float4 b, int mh, int mw, int ih, int iw, int upsample,
+                                              float rx, float ry) {
+  PMGeom g;
+  g.x1d = __fmul_rn(b.x, rx);  // downsampled_bboxes[:, 0] *= mw / iw
+  g.x2d = __fmul_rn(b.z, rx);
+  g.y1d = __fmul_rn(b.y, ry);
+  g.y2d = __fmul_rn(b.w, ry);
+  // r >= x1 & r < x2 over integers r: [ceil(x1), ceil(x2))
+  g.px0 = ceil_to_int_clamped(g.x1d, 0, mw);
+  g.px1 = ceil_to_int_clamped(g.x2d, 0, mw);
+  g.py0 = ceil_to_int_clamped(g.y1d, 0, mh);
+  g.py1 = ceil_to_int_clamped(g.y2d, 0, mh);
+  if (g.px1 <= g.px0 || g.py1 <= g.py0) {
+    g.x0 = g.y0 = g.w = g.h = 0;
+    return g;
+  }
+  if (!upsample) {
+    g.x0 = g.px0;
+    g.y0 = g.py0;
+    g.w = g.px1 - g.px0;
+    g.h = g.py1 - g.py0;
+  } else {
+    // conservative superset: src = s*(dst+0.5)-0.5 with s = mw/iw; i0 in [p0-1, p1-1]  <=>  src in [p0-1, p1)
+    const float sx = (float)mw / (float)iw, sy = (float)mh / (float)ih;
+    int ox0 = (int)floorf(((float)g.px0 - 0.5f) / sx - 0.5f) - 1, ox1 = (int)ceilf(((float)g.px1 + 0.5f) / sx - 0.5f) + 1;
+    int oy0 = (int)floorf(((float)g.py0 - 0.5f) / sy - 0.5f) - 1, oy1 = (int)ceilf(((float)g.py1 + 0.5f) / sy - 0.5f) + 1;
+    ox0 = max(ox0, 0);
+    oy0 = max(oy0, 0);
+    ox1 = min(ox1, iw);
+    oy1 = min(oy1, ih);
+    g.x0 = ox0;
+    g.y0 = oy0;
+    g.w = max(ox1 - ox0, 0);
+    g.h = max(oy1 - oy0, 0);
+    if (g.w == 0 || g.h == 0) g.x0 = g.y0 = g.w = g.h = 0;
+  }
+  return g;
+}
+
+__global__ void pm_geometry_kernel(const float4* __restrict__ boxes, const int32_t* __restrict__ counts, int bs,
+                                   int max_det, int mh, int mw, int ih, int iw, int upsample, float rx, float ry,
+                                   int32_t* __restrict__ geom4) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= (long long)bs * max_det) return;
+  const int tile = (int)(i / max_det), d = (int)(i - (long long)tile * max_det);
+  int4 out = make_int4(0, 0, 0, 0);
+  if (d < counts[tile]) {
+    const PMGeom g = pm_geometry(boxes[i], mh, mw, ih, iw, upsample, rx, ry);
+    out = make_int4(g.x0, g.y0, g.w, g.h);
+  }
+  reinterpret_cast<int4*>(geom4)[i] = out;
+}
+
+constexpr int kPmTile = 32;               // proto pixels per staged tile side
+constexpr int kPmStage = kPmTile + 1;     // + 1 halo for the second bilinear tap
+constexpr int kPmThreads = 128;
+
+// One CTA per detection slot.  For every kPmTile^2 block of proto pixels touching the mask's window the
+// cropped sigmoid(coef . proto) values are staged in shared memory (32 FFMA per pixel, channel-strided
+// coalesced reads that hit L2 after the first detection of a tile), then the output pixels whose first tap
+// falls into the block are emitted.
+template <bool PACKED>
+__global__ void __launch_bounds__(kPmThreads) process_mask_kernel(
+    const float* __restrict__ protos, const float* __restrict__ coef, const float4* __restrict__ boxes,
+    const int32_t* __restrict__ counts, int max_det, int nm, int mh, int mw, int ih, int iw, int upsample,
+    float rx, float ry, float* __restrict__ out_dense, const int64_t* __restrict__ offsets,
+    uint32_t* __restrict__ bits, long long capacity_words, int32_t* __restrict__ status) {
+  __shared__ float stage[kPmStage * kPmStage];
+  __shared__ float cf[64];
+  const long long slot = blockIdx.x;
+  const int tile = (int)(slot / max_det), d = (int)(slot - (long long)tile * max_det);
+  if (d >= counts[tile]) return;
+  const PMGeom g = pm_geometry(boxes[slot], mh, mw, ih, iw, upsample, rx, ry);
+  if (g.w <= 0 || g.h <= 0) return;
+  const int oh = upsample ? ih : mh, ow = upsample ? iw : mw;
+  const int wpr = (g.w + 31) >> 5;
+  long long off = 0;
+  if (PACKED) {
+    off = offsets[slot];
+    if (off + (long long)wpr * g.h > capacity_words) {
+      if (threadIdx.x == 0) atomicOr(status, HDY_STATUS_OVERFLOW);
+      return;
+    }
+  }
+  for (int c = threadIdx.x; c < nm; c += kPmThreads) cf[c] = coef[slot * nm + c];
+  const float* P = protos + (size_t)tile * nm * mh * mw;
+  const size_t plane = (size_t)mh * mw;
+  const float sxs = (float)mw / (float)iw, sys = (float)mh / (float)ih;  // ATen: scale = in / out (fp32)
+  // proto range that can contribute: the kept pixels, plus one pixel before (their second-tap neighbours)
+  const int ty_begin = upsample ? max(g.py0 - 1, 0) : g.py0, tx_begin = upsample ? max(g.px0 - 1, 0) : g.px0;
+  for (int ty = ty_begin; ty < g.py1; ty += kPmTile) {
+    for (int tx = tx_begin; tx < g.px1; tx += kPmTile) {
+      __syncthreads();
+      // ---- stage cropped sigmoid values for proto pixels [ty, ty+33) x [tx, tx+33)
+      for (int e = threadIdx.x; e < kPmStage * kPmStage; e += kPmThreads) {
+        const int yy = ty + e / kPmStage, xx = tx + e % kPmStage;
+        float v = 0.f;
+        if (yy < mh && xx < mw && (float)xx >= g.x1d && (float)xx < g.x2d && (float)yy >= g.y1d &&
+            (float)yy < g.y2d) {
+          const float* p = P + (size_t)yy * mw + xx;
+          float acc = 0.f;
+#pragma unroll 8
+          for (int c = 0; c < nm; ++c) acc = fmaf(cf[c], __ldg(p + c * plane), acc);
+          v = sigmoidf_ref(acc);
+        }
+        stage[e] = v;
+      }
+      __syncthreads();
+      if (!upsample) {
+        // output pixel == proto pixel
+        const int y_lo = max(ty, g.y0), y_hi = min(ty + kPmTile, g.y0 + g.h);
+        const int x_lo = max(tx, g.x0), x_hi = min(tx + kPmTile, g.x0 + g.w);
+        const int tw = x_hi - x_lo, th = y_hi - y_lo;
+        for (int e = threadIdx.x; e < tw * th; e += kPmThreads) {
+          const int yy = y_lo + e / tw, xx = x_lo + e % tw;
+          const bool bit = stage[(yy - ty) * kPmStage + (xx - tx)] > 0.5f;
+          if (PACKED) {
+            if (bit) atomicOr(&bits[off + (long long)(yy - g.y0) * wpr + ((xx - g.x0) >> 5)], 1u << ((xx - g.x0) & 31));
+          } else {
+            out_dense[(size_t)slot * oh * ow + (size_t)yy * ow + xx] = bit ? 1.f : 0.f;
+          }
+        }
+      } else {
+        // output pixels of the window whose first taps (i0) fall into [ty, ty+32) x [tx, tx+32)
+        for (int e = threadIdx.x; e < g.w * g.h; e += kPmThreads) {
+          const int oy = g.y0 + e / g.w, ox = g.x0 + e % g.w;
+          const Lerp Y = lerp_coord(oy, sys, mh), X = lerp_coord(ox, sxs, mw);
+          if (Y.i0 < ty || Y.i0 >= ty + kPmTile || X.i0 < tx || X.i0 >= tx + kPmTile) continue;
+          const int sy0 = Y.i0 - ty, sx0 = X.i0 - tx, sy1 = Y.i1 - ty, sx1 = X.i1 - tx;
+          const float v = bilerp(stage[sy0 * kPmStage + sx0], stage[sy0 * kPmStage + sx1],
+                                 stage[sy1 * kPmStage + sx0], stage[sy1 * kPmStage + sx1], X, Y);
+          const bool bit = v > 0.5f;
+          if (PACKED) {
+            if (bit) atomicOr(&bits[off + (long long)(oy - g.y0) * wpr + ((ox - g.x0) >> 5)], 1u << ((ox - g.x0) & 31));
+          } else {
+            out_dense[(size_t)slot * oh * ow + (size_t)oy * ow + ox] = bit ? 1.f : 0.f;
+          }
+        }
+      }
+    }
+  }
+}
+
+static int paste_args_ok(const float* src, const float* boxes, int K, int C, int M, int pad, int H, int W) {
+  HDY_REQUIRE(K >= 0 && C >= 1 && M >= 1 && pad >= 0 && H >= 1 && W >= 1, "paste: bad sizes");
+  HDY_REQUIRE((M + 2 * pad) * (M + 2 * pad) * 4 <= 200 * 1024, "paste: mask too large for shared memory");
+  if (K > 0) HDY_REQUIRE(src && boxes && ((uintptr_t)boxes & 15) == 0, "paste: NULL or misaligned pointer");
+  return HDY_OK;
+}
+
+template <bool PACKED>
+static int launch_paste(const float* src, const int32_t* channel, const float* boxes, int K, int C, int M, int pad,
+                        int apply_sigmoid, int H, int W, float* out, const int64_t* offsets, uint32_t* bits,
+                        long long cap, int32_t* status, cudaStream_t st) {
+  const int Mp = M + 2 * pad;
+  const size_t smem = (size_t)Mp * Mp * 4;
+  if (smem > 48 * 1024) {
+    cudaError_t e = cudaFuncSetAttribute(paste_masks_kernel<PACKED>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                         (int)smem);
+    if (e != cudaSuccess) {
+      set_error("cudaFuncSetAttribute: %s", cudaGetErrorString(e));
+      return HDY_ERR_CUDA;
+    }
+  }
+  const float scale = (float)((double)(M + 2 * pad) / (double)M);  // expand_masks: float(M + 2p) / M
+  paste_masks_kernel<PACKED><<<(unsigned)K, 128, smem, st>>>(src, channel, reinterpret_cast<const float4*>(boxes), K,
+                                                             C, M, pad, apply_sigmoid, H, W, scale, out, offsets,
+                                                             bits, cap, status);
+  return check_launch("hdy_paste_masks");
+}
+
+static int pm_args_ok(const float* protos, const float* coef, const float* boxes, const int32_t* counts, int bs,
+                      int max_det, int nm, int mh, int mw, int ih, int iw) {
+  HDY_REQUIRE(bs >= 0 && max_det >= 1 && nm >= 1 && nm <= 64 && mh >= 1 && mw >= 1 && ih >= 1 && iw >= 1,
+              "process_mask: bad sizes (nm must be <= 64)");
+  if (bs > 0)
+    HDY_REQUIRE(protos && coef && boxes && counts && ((uintptr_t)boxes & 15) == 0,
+                "process_mask: NULL or misaligned pointer");
+  return HDY_OK;
+}
+
+}  // namespace hdy
+
+using namespace hdy;
+
+extern "C" {
+
+int hdy_mask_select(const float* logits, const int64_t* labels, const int64_t* mask_indices, int K, int C, int M,
+                    float* out, hdy_stream_t stream) {
+  HDY_REQUIRE(K >= 0 && C >= 1 && M >= 1, "hdy_mask_select: bad sizes");
+  if (K == 0) return HDY_OK;
+  HDY_REQUIRE(logits && labels && mask_indices && out, "hdy_mask_select: NULL pointer");
+  mask_select_kernel<<<(unsigned)K, 128, 0, (cudaStream_t)stream>>>(logits, labels, mask_indices, K, C, M * M, out);
+  return check_launch("hdy_mask_select");
+}
+
+int hdy_paste_masks(const float* src, const int32_t* channel, const float* boxes, int K, int C, int M, int padding,
+                    int apply_sigmoid, int H, int W, float* out, hdy_stream_t stream) {
+  int rc = paste_args_ok(src, boxes, K, C, M, padding, H, W);
+  if (rc) return rc;
+  if (K == 0) return HDY_OK;
+  HDY_REQUIRE(out != nullptr, "hdy_paste_masks: out is NULL");
+  cudaStream_t st = (cudaStream_t)stream;
+  cudaError_t e = cudaMemsetAsync(out, 0, (size_t)K * H * W * sizeof(float), st);
+  if (e != cudaSuccess) {
+    set_error("cudaMemsetAsync: %s", cudaGetErrorString(e));
+    return HDY_ERR_CUDA;
+  }
+  return launch_paste<false>(src, channel, boxes, K, C, M, padding, apply_sigmoid, H, W, out, nullptr, nullptr, 0,
+                             nullptr, st);
+}
+
+int hdy_paste_geometry(const float* boxes, int K, int M, int padding, int H, int W, int32_t* geom,
+                       int64_t* offsets, hdy_stream_t stream) {
+  HDY_REQUIRE(K >= 0 && M >= 1 && padding >= 0 && H >= 1 && W >= 1, "hdy_paste_geometry: bad sizes");
+  HDY_REQUIRE(offsets != nullptr, "hdy_paste_geometry: offsets is NULL");
+  cudaStream_t st = (cudaStream_t)stream;
+  if (K > 0) {
+    HDY_REQUIRE(boxes && geom && ((uintptr_t)boxes & 15) == 0 && ((uintptr_t)geom & 15) == 0,
+                "hdy_paste_geometry: NULL or misaligned pointer");
+    const float scale = (float)((double)(M + 2 * padding) / (double)M);
+    paste_geometry_kernel<<<(unsigned)((K + 127) / 128), 128, 0, st>>>(reinterpret_cast<const float4*>(boxes), K,
+                                                                       scale, H, W, geom);
+  }
+  scan_words_kernel<<<1, 1024, 0, st>>>(geom, K, offsets);
+  return check_launch("hdy_paste_geometry");
+}
+
+int hdy_paste_masks_packed(const float* src, const int32_t* channel, const float* boxes, const int64_t* offsets,
+                           int K, int C, int M, int padding, int apply_sigmoid, int H, int W, uint32_t* bits,
+                           int64_t capacity_words, int32_t* status, hdy_stream_t stream) {
+  int rc = paste_args_ok(src, boxes, K, C, M, padding, H, W);
+  if (rc) return rc;
+  if (K == 0) return HDY_OK;
+  HDY_REQUIRE(offsets && bits && status && capacity_words >= 0, "hdy_paste_masks_packed: NULL pointer");
+  return launch_paste<true>(src, channel, boxes, K, C, M, padding, apply_sigmoid, H, W, nullptr, offsets, bits,
+                            capacity_words, status, (cudaStream_t)stream);
+}
+
+int hdy_unpack_masks(const int32_t* geom, const int64_t* offsets, const uint32_t* bits, int K, int H, int W,
+                     uint8_t* out, hdy_stream_t stream) {
+  HDY_REQUIRE(K >= 0 && H >= 1 && W >= 1, "hdy_unpack_masks: bad sizes");
+  if (K == 0) return HDY_OK;
+  HDY_REQUIRE(geom && offsets && bits && out && ((uintptr_t)geom & 15) == 0, "hdy_unpack_masks: NULL pointer");
+  cudaStream_t st = (cudaStream_t)stream;
+  cudaError_t e = cudaMemsetAsync(out, 0, (size_t)K * H * W, st);
+  if (e != cudaSuccess) {
+    set_error("cudaMemsetAsync: %s", cudaGetErrorString(e));
+    return HDY_ERR_CUDA;
+  }
+  unpack_masks_kernel<<<(unsigned)K, 128, 0, st>>>(geom, offsets, bits, H, W, out);
+  return check_launch("hdy_unpack_masks");
+}
+
+int hdy_process_mask(const float* protos, const float* coef, const float* boxes, const int32_t* counts, int bs,
+                     int max_det, int nm, int mh, int mw, int ih, int iw, int upsample, float* out,
+                     hdy_stream_t stream) {
+  int rc = pm_args_ok(protos, coef, boxes, counts, bs, max_det, nm, mh, mw, ih, iw);
+  if (rc) return rc;
+  if (bs == 0) return HDY_OK;
+  HDY_REQUIRE(out != nullptr, "hdy_process_mask: out is NULL");
+  cudaStream_t st = (cudaStream_t)stream;
+  const size_t oh = upsample ? ih : mh, ow = upsample ? iw : mw;
+  cudaError_t e = cudaMemsetAsync(out, 0, (size_t)bs * max_det * oh * ow * sizeof(float), st);
+  if (e != cudaSuccess) {
+    set_error("cudaMemsetAsync: %s", cudaGetErrorString(e));
+    return HDY_ERR_CUDA;
+  }
+  const float rx = (float)((double)mw / (double)iw), ry = (float)((double)mh / (double)ih);
+  process_mask_kernel<false><<<(unsigned)((size_t)bs * max_det), kPmThreads, 0, st>>>(
+      protos, coef, reinterpret_cast<const float4*>(boxes), counts, max_det, nm, mh, mw, ih, iw, upsample, rx, ry,
+      out, nullptr, nullptr, 0, nullptr);
+  return check_launch("hdy_process_mask");
+}
+
+int hdy_process_mask_geometry(const float* boxes, const int32_t* counts, int bs, int max_det, int mh, int mw, int ih,
+                              int iw, int upsample, int32_t* geom, int64_t* offsets, hdy_stream_t stream) {
+  HDY_REQUIRE(bs >= 0 && max_det >= 1 && mh >= 1 && mw >= 1 && ih >= 1 && iw >= 1, "process_mask_geometry: bad sizes");
+  HDY_REQUIRE(offsets != nullptr, "process_mask_geometry: offsets is NULL");
+  cudaStream_t st = (cudaStream_t)stream;
+  const long long K = (long long)bs * max_det;
+  if (K > 0) {
+    HDY_REQUIRE(boxes && counts && geom && ((uintptr_t)boxes & 15) == 0 && ((uintptr_t)geom & 15) == 0,
+                "process_mask_geometry: NULL or misaligned pointer");
+    const float rx = (float)((double)mw / (double)iw), ry = (float)((double)mh / (double)ih);
+    pm_geometry_kernel<<<(unsigned)((K + 127) / 128), 128, 0, st>>>(reinterpret_cast<const float4*>(boxes), counts, bs,
+                                                                    max_det, mh, mw, ih, iw, upsample, rx, ry, geom);
+  }
+  scan_words_kernel<<<1, 1024, 0, st>>>(geom, K, offsets);
+  return check_launch("hdy_process_mask_geometry");
+}
+
+int hdy_process_mask_packed(const float* protos, const float* coef, const float* boxes, const int32_t* counts,
+                            const int64_t* offsets, int bs, int max_det, int nm, int mh, int mw, int ih, int iw,
+                            int upsample, uint32_t* bits, int64_t capacity_words, int32_t* status,
+                            hdy_stream_t stream) {
+  int rc = pm_args_ok(protos, coef, boxes, counts, bs, max_det, nm, mh, mw, ih, iw);
+  if (rc) return rc;
+  if (bs == 0) return HDY_OK;
+  HDY_REQUIRE(offsets && bits && status && capacity_words >= 0, "hdy_process_mask_packed: NULL pointer");
+  cudaStream_t st = (cudaStream_t)stream;
+  // bits are OR-ed in: clear the used prefix first (capacity is an upper bound the caller sized)
+  cudaError_t e = cudaMemsetAsync(bits, 0, (size_t)capacity_words * 4, st);
+  if (e != cudaSuccess) {
+    set_error("cudaMemsetAsync: %s", cudaGetErrorString(e));
+    return HDY_ERR_CUDA;
+  }
+  const float rx = (float)((double)mw / (double)iw), ry = (float)((double)mh / (double)ih);
+  process_mask_kernel<true><<<(unsigned)((size_t)bs * max_det), kPmThreads, 0, st>>>(
+      protos, coef, reinterpret_cast<const float4*>(boxes), counts, max_det, nm, mh, mw, ih, iw, upsample, rx, ry,
+      nullptr, offsets, bits, capacity_words, status);
+  return check_launch("hdy_process_mask_packed");
+}
+
+}  // extern "C"

@@ -30,6 +30,27 @@ constexpr float kMaxScaled = 16384.0f;  // |centre|/cell above this -> "large" b
 
 enum : uint8_t { ST_UNKNOWN = 0, ST_KEPT = 1, ST_SUPPRESSED = 2 };
 
+// Optional phase profile (hdy_debug_nms_phases): cycles summed over CTAs for
+// 0 load, 1 sort, 2 gather boxes, 3 binning, 4 rounds, 5 output, 6 #rounds, 7 #CTAs
+__device__ unsigned long long* g_phase_cycles = nullptr;
+struct PhaseClock {
+  unsigned long long* buf;
+  long long t0;
+  __device__ PhaseClock() : buf(g_phase_cycles), t0(0) {
+    if (buf && threadIdx.x == 0) t0 = clock64();
+  }
+  __device__ void mark(int phase) {
+    if (buf && threadIdx.x == 0) {
+      const long long t1 = clock64();
+      atomicAdd(buf + phase, (unsigned long long)(t1 - t0));
+      t0 = t1;
+    }
+  }
+  __device__ void add(int slot, unsigned long long v) {
+    if (buf && threadIdx.x == 0) atomicAdd(buf + slot, v);
+  }
+};
+
 __device__ __forceinline__ uint32_t next_pow2(uint32_t v) {
   if (v <= 1) return 1;
   return 1u << (32 - __clz(v - 1));
@@ -95,6 +116,7 @@ __device__ void nms_tile_body(const int n_in, const int max_nms, uint64_t* keys,
   // (ties at the cut are resolved by lower index here; the reference's unstable argsort leaves
   //  them unspecified)
   const int n = (max_nms > 0 && n_in > max_nms) ? max_nms : n_in;
+  PhaseClock pc;
 
   // ---- 1. load + bitonic sort ------------------------------------------------------------------
   for (uint32_t i = t; i < P; i += T) {
@@ -102,6 +124,7 @@ __device__ void nms_tile_body(const int n_in, const int max_nms, uint64_t* keys,
     slots[i] = (IdxT)i;
   }
   __syncthreads();
+  pc.mark(0);
   for (uint32_t k = 2; k <= P; k <<= 1) {
     for (uint32_t j = k >> 1; j > 0; j >>= 1) {
       for (uint32_t p = t; p < (P >> 1); p += T) {
@@ -121,6 +144,7 @@ __device__ void nms_tile_body(const int n_in, const int max_nms, uint64_t* keys,
     }
   }
 
+  pc.mark(1);
   // ---- 2. boxes into rank order (+ class offset), extent statistics ------------------------------
   float ext_sum = 0.f;
   int ext_cnt = 0;
@@ -179,6 +203,7 @@ __device__ void nms_tile_body(const int n_in, const int max_nms, uint64_t* keys,
     return 2;  // also NaN / inf coordinates
   };
 
+  pc.mark(2);
   // ---- 3. counting sort into the torus grid ------------------------------------------------------
   constexpr int NB = G * G + 1;
   for (int i = t; i < NB; i += T) cell[i] = 0;
@@ -199,9 +224,11 @@ __device__ void nms_tile_body(const int n_in, const int max_nms, uint64_t* keys,
   // now: bucket b occupies items[ (b ? cell[b-1] : 0) .. cell[b] )
   const int large_begin = cell[NB - 2], large_end = cell[NB - 1];
 
+  pc.mark(3);
   // ---- 4. parallel greedy rounds -------------------------------------------------------------------
   volatile uint8_t* vstate = state;
   while (true) {
+    pc.add(6, 1);
     int unknown = 0;
     for (int r = t; r < n; r += T) {
       if (vstate[r] != ST_UNKNOWN) continue;
@@ -251,6 +278,7 @@ __device__ void nms_tile_body(const int n_in, const int max_nms, uint64_t* keys,
     if (!__syncthreads_or(unknown)) break;
   }
 
+  pc.mark(4);
   // ---- 5. rank-ordered compaction of survivors ----------------------------------------------------
   {
     const int items_per = (n + T - 1) / T;
@@ -286,6 +314,8 @@ __device__ void nms_tile_body(const int n_in, const int max_nms, uint64_t* keys,
     }
     if (t == 0) *out.keep_count = min(total, max_det);
   }
+  pc.mark(5);
+  pc.add(7, 1);
 }
 
 struct WorkspaceLayout {
@@ -463,6 +493,16 @@ __global__ void select_scores_kernel(float* __restrict__ scores, const int32_t* 
 using namespace hdy;
 
 extern "C" {
+
+int hdy_debug_nms_phases(uint64_t* device_buf8) {
+  unsigned long long* p = reinterpret_cast<unsigned long long*>(device_buf8);
+  cudaError_t e = cudaMemcpyToSymbol(g_phase_cycles, &p, sizeof(p));
+  if (e != cudaSuccess) {
+    set_error("hdy_debug_nms_phases: %s", cudaGetErrorString(e));
+    return HDY_ERR_CUDA;
+  }
+  return HDY_OK;
+}
 
 size_t hdy_nms_workspace_bytes(int bs, int cap) {
   if (bs <= 0 || cap <= kSmemCap) return 0;

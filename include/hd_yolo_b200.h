@@ -137,6 +137,11 @@ HDY_API int hdy_nms_tiles(const uint64_t* cand_keys, const float* cand_boxes, co
                   float* keep_cls, int32_t* keep_counts, void* workspace, size_t workspace_bytes,
                   hdy_stream_t stream);
 
+/* Debug: when device_buf8 (8 x u64, zeroed by the caller) is non-NULL, hdy_nms_tiles accumulates per-phase
+ * SM cycles into it (0 load, 1 sort, 2 gather, 3 binning, 4 rounds, 5 output, 6 rounds run, 7 CTAs).
+ * Pass NULL to switch it off (the default). Synchronises the device. */
+HDY_API int hdy_debug_nms_phases(uint64_t* device_buf8);
+
 /* Keys for a plain torchvision.ops.nms(boxes, scores, thr) call: scores [bs, seg_len] ->
  * keys [bs, seg_len] with index = position inside the segment. */
 HDY_API int hdy_make_keys(const float* scores, int bs, int seg_len, uint64_t* keys, hdy_stream_t stream);
@@ -163,6 +168,52 @@ HDY_API int hdy_gather_logits(const hdy_level_t* levels_host, int nl, int bs, in
 HDY_API int hdy_select_scores(float* scores, const int32_t* keep_counts, int bs, int max_det, int nc,
                       const int32_t* hier_ops_host, int n_ops, float conf_thres,
                       float* out_score, int64_t* out_label, hdy_stream_t stream);
+
+/* -------------------------------------------------------------------- masks */
+
+/* M1: mask tail of Detect.compute_outputs (yolo_head.py:332, 346-353) for K detections:
+ * out[i] = sigmoid(logits[i, mask_indices[max(labels[i],0)]]), or 0 when that index is < 0.
+ *   logits [K, C, M, M] f32, labels [K] i64, mask_indices [nc+1] i64 -> out [K, 1, M, M] f32 */
+HDY_API int hdy_mask_select(const float* logits, const int64_t* labels, const int64_t* mask_indices, int K, int C,
+                            int M, float* out, hdy_stream_t stream);
+
+/* M2: torchvision paste_masks_in_image(masks, boxes, (H,W), padding) as called at val_nuclei.py:169-176 and
+ * evaluation.py:122-123, dense output identical in layout to the reference ([K,1,H,W] f32).
+ *   src [K, C, M, M] f32; channel [K] i32 picks the channel per mask (NULL: channel 0; < 0: all-zero mask);
+ *   apply_sigmoid != 0 fuses M1's sigmoid (src holds logits). */
+HDY_API int hdy_paste_masks(const float* src, const int32_t* channel, const float* boxes, int K, int C, int M,
+                            int padding, int apply_sigmoid, int H, int W, float* out, hdy_stream_t stream);
+
+/* Cropped bit-packed layout (M2 + M3 "> 0.5"): geom [K,4] i32 = paste window {x0, y0, w, h} in image pixels,
+ * offsets [K+1] i64 = first 32-bit word of each mask (row r of mask i = ceil(w/32) words; bit (x-x0)&31 of
+ * word (x-x0)>>5).  hdy_paste_geometry fills geom/offsets (offsets[K] = total words); the caller sizes `bits`
+ * from it (or passes an upper bound: masks that do not fit set HDY_STATUS_OVERFLOW in *status). */
+HDY_API int hdy_paste_geometry(const float* boxes, int K, int M, int padding, int H, int W, int32_t* geom,
+                               int64_t* offsets, hdy_stream_t stream);
+HDY_API int hdy_paste_masks_packed(const float* src, const int32_t* channel, const float* boxes,
+                                   const int64_t* offsets, int K, int C, int M, int padding, int apply_sigmoid,
+                                   int H, int W, uint32_t* bits, int64_t capacity_words, int32_t* status,
+                                   hdy_stream_t stream);
+/* Expand cropped bit planes to a dense [K, H, W] u8 canvas (verification / visualisation). */
+HDY_API int hdy_unpack_masks(const int32_t* geom, const int64_t* offsets, const uint32_t* bits, int K, int H,
+                             int W, uint8_t* out, hdy_stream_t stream);
+
+/* North-star process_mask (ultralytics/yolov5 v7 utils/segment/general.py::process_mask + crop_mask; the
+ * reference itself has no such function): mask = sigmoid(coef . protos), zero outside the box scaled by
+ * (mw/iw, mh/ih), optional bilinear upsample (align_corners=False) to (ih, iw), > 0.5.  Batched over tiles:
+ *   protos [bs, nm, mh, mw], coef [bs, max_det, nm], boxes [bs, max_det, 4] (image pixels), counts [bs]
+ *   dense out [bs, max_det, oh, ow] f32 in {0,1} with (oh,ow) = upsample ? (ih,iw) : (mh,mw). */
+HDY_API int hdy_process_mask(const float* protos, const float* coef, const float* boxes, const int32_t* counts,
+                             int bs, int max_det, int nm, int mh, int mw, int ih, int iw, int upsample, float* out,
+                             hdy_stream_t stream);
+/* Cropped bit-packed variant; geom [bs*max_det, 4], offsets [bs*max_det + 1] as above (slots >= counts are empty). */
+HDY_API int hdy_process_mask_geometry(const float* boxes, const int32_t* counts, int bs, int max_det, int mh, int mw,
+                                      int ih, int iw, int upsample, int32_t* geom, int64_t* offsets,
+                                      hdy_stream_t stream);
+HDY_API int hdy_process_mask_packed(const float* protos, const float* coef, const float* boxes,
+                                    const int32_t* counts, const int64_t* offsets, int bs, int max_det, int nm,
+                                    int mh, int mw, int ih, int iw, int upsample, uint32_t* bits,
+                                    int64_t capacity_words, int32_t* status, hdy_stream_t stream);
 
 /* Utility: zero n int32 words (keeps the host mirror free of extra torch launches). */
 HDY_API int hdy_zero_i32(int32_t* p, size_t n, hdy_stream_t stream);
