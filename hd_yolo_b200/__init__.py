@@ -18,4 +18,15 @@ from .ops import (  # noqa: F401
     set_iou_compare,
 )
 
+from . import masks  # noqa: F401,E402
+from .masks import (  # noqa: F401,E402
+    PackedMasks,
+    mask_select,
+    paste_masks_in_image,
+    paste_masks_packed,
+    process_mask,
+    process_mask_batch,
+    process_mask_packed,
+)
+
 __version__ = "0.1.0"

@@ -1,0 +1,159 @@
+"""GPU parity tests of the mask stage (pytest -m gpu), through the C-ABI, against the reference golden
+(paste_masks_in_image) and the oracle port.
+
+Bars (BASELINE.json north_star): binary masks agree on >= 99.99 % of pixels; dense fp32 canvases within 2e-6
+absolute of the reference (values are probabilities in [0,1]; ATen's CPU bilinear kernel contracts some products
+into FMAs, the device code rounds every product, so the last bit can differ)."""
+import numpy as np
+import pytest
+import torch
+
+from conftest import load_golden
+import hd_yolo_b200 as hdy
+from hd_yolo_b200 import masks as hm
+from oracle import port
+
+pytestmark = pytest.mark.gpu
+
+AGREE = 0.9999
+ATOL = 2e-6
+
+
+def _agreement(a, b):
+    return float((a == b).double().mean())
+
+
+def _rand_boxes(g, k, H, W, lo, hi):
+    c = torch.rand((k, 2), generator=g) * torch.tensor([W, H], dtype=torch.float32)
+    s = torch.rand((k, 2), generator=g) * (hi - lo) + lo
+    return torch.cat([c - s / 2, c + s / 2], 1)
+
+
+# ------------------------------------------------------------------------------------------------ M1
+def test_mask_select_vs_oracle(cuda_device):
+    g = torch.Generator().manual_seed(1)
+    K, C, M, nc = 37, 3, 28, 4
+    logits = torch.randn((K, C, M, M), generator=g) * 3
+    labels = torch.randint(-1, nc + 1, (K,), generator=g)
+    labels[labels < 0] = -100                                   # the reference's "no class" label
+    mask_indices = torch.tensor([0, 0, 1, -1, 2])               # class 3 has no mask head
+    ref = port.mask_select(logits, labels, mask_indices)
+    out = hm.mask_select(logits.to(cuda_device), labels.to(cuda_device), mask_indices.to(cuda_device))
+    assert out.shape == ref.shape == (K, 1, M, M)
+    assert float((out.cpu() - ref).abs().max()) < ATOL
+    zero = mask_indices[labels.clamp(min=0)] < 0
+    assert zero.any() and bool((out.cpu()[zero] == 0).all())
+
+
+# ------------------------------------------------------------------------------------------------ M2
+def test_paste_masks_vs_reference_golden(cuda_device):
+    g = load_golden("paste_masks")
+    H, W = g["shape"].tolist()
+    masks, boxes, ref = torch.from_numpy(g["masks"]), torch.from_numpy(g["boxes"]), torch.from_numpy(g["out"])
+    out = hm.paste_masks_in_image(masks.to(cuda_device), boxes.to(cuda_device), (H, W), padding=1)
+    assert out.shape == ref.shape and out.dtype == torch.float32
+    assert float((out.cpu() - ref).abs().max()) < ATOL
+    assert bool(((out.cpu() == 0) == (ref == 0)).all())        # identical paste windows
+    packed = hm.paste_masks_packed(masks.to(cuda_device), boxes.to(cuda_device), (H, W), padding=1)
+    packed.check()
+    dense = packed.to_dense().cpu()
+    assert _agreement(dense, (ref[:, 0] > 0.5).to(torch.uint8)) >= AGREE
+    assert torch.equal(dense, (out[:, 0] > 0.5).to(torch.uint8).cpu())   # packed == dense path, bit for bit
+
+
+@pytest.mark.parametrize("k,H,W,lo,hi,pad", [(300, 640, 640, 8, 48, 1), (64, 200, 333, 1, 150, 1), (50, 128, 128, 4, 40, 0),
+                                              (40, 100, 90, 2, 30, 2)])
+def test_paste_masks_vs_oracle_random(cuda_device, k, H, W, lo, hi, pad):
+    g = torch.Generator().manual_seed(k + H)
+    masks = torch.rand((k, 1, 28, 28), generator=g)
+    boxes = _rand_boxes(g, k, H, W, lo, hi)
+    ref = port.paste_masks_in_image(masks, boxes, (H, W), padding=pad)
+    out = hm.paste_masks_in_image(masks.to(cuda_device), boxes.to(cuda_device), (H, W), padding=pad).cpu()
+    assert float((out - ref).abs().max()) < ATOL
+    packed = hm.paste_masks_packed(masks.to(cuda_device), boxes.to(cuda_device), (H, W), padding=pad)
+    assert _agreement(packed.to_dense().cpu(), (ref[:, 0] > 0.5).to(torch.uint8)) >= AGREE
+    # geometry: window == bounding box of the reference's non-zero paste region (masks are > 0 everywhere inside)
+    geom = packed.geom.cpu()
+    for i in range(0, k, max(1, k // 16)):
+        nz = ref[i, 0].nonzero()
+        x0, y0, w, h = geom[i].tolist()
+        if len(nz) == 0:
+            continue
+        assert y0 <= int(nz[:, 0].min()) and int(nz[:, 0].max()) < y0 + h
+        assert x0 <= int(nz[:, 1].min()) and int(nz[:, 1].max()) < x0 + w
+
+
+def test_paste_fused_sigmoid_channel(cuda_device):
+    """M1 + M2 + M3 in one kernel == mask_select -> paste -> > 0.5 done separately."""
+    g = torch.Generator().manual_seed(9)
+    K, C, M, H, W = 80, 2, 28, 320, 320
+    logits = torch.randn((K, C, M, M), generator=g) * 2
+    labels = torch.randint(0, 5, (K,), generator=g)
+    mask_indices = torch.tensor([0, 0, 1, -1, 1])
+    boxes = _rand_boxes(g, K, H, W, 10, 40)
+    ch = mask_indices[labels.clamp(min=0)].to(torch.int32)
+    sel = hm.mask_select(logits.to(cuda_device), labels.to(cuda_device), mask_indices.to(cuda_device))
+    two = hm.paste_masks_packed(sel, boxes.to(cuda_device), (H, W)).to_dense()
+    one = hm.paste_masks_packed(logits.to(cuda_device), boxes.to(cuda_device), (H, W), channel=ch.to(cuda_device),
+                                apply_sigmoid=True).to_dense()
+    assert torch.equal(one, two)
+    ref = port.paste_masks_in_image(port.mask_select(logits, labels, mask_indices), boxes, (H, W))
+    assert _agreement(one.cpu(), (ref[:, 0] > 0.5).to(torch.uint8)) >= AGREE
+
+
+def test_paste_empty_and_capacity(cuda_device):
+    z = hm.paste_masks_in_image(torch.zeros((0, 1, 28, 28), device=cuda_device), torch.zeros((0, 4), device=cuda_device),
+                                (32, 48))
+    assert z.shape == (0, 1, 32, 48)
+    p = hm.paste_masks_packed(torch.zeros((0, 1, 28, 28), device=cuda_device), torch.zeros((0, 4), device=cuda_device),
+                              (32, 48))
+    assert len(p) == 0 and p.to_dense().shape == (0, 32, 48)
+    g = torch.Generator().manual_seed(2)
+    masks = torch.rand((10, 1, 28, 28), generator=g).to(cuda_device)
+    boxes = _rand_boxes(g, 10, 64, 64, 10, 30).to(cuda_device)
+    small = hm.paste_masks_packed(masks, boxes, (64, 64), capacity_words=8)
+    with pytest.raises(hdy.HdyError, match="overflow"):
+        small.check()
+    with pytest.raises(hdy.HdyError):
+        hm.paste_masks_in_image(torch.zeros((1, 1, 28, 28)), torch.zeros((1, 4)), (8, 8))   # CPU tensors
+
+
+# ------------------------------------------------------------------------------- process_mask (variant B)
+@pytest.mark.parametrize("upsample", [False, True])
+@pytest.mark.parametrize("n,mh,mw,ih,iw", [(120, 160, 160, 640, 640), (33, 40, 56, 160, 224), (7, 24, 24, 90, 100)])
+def test_process_mask_vs_oracle(cuda_device, upsample, n, mh, mw, ih, iw):
+    g = torch.Generator().manual_seed(n)
+    protos = torch.randn((32, mh, mw), generator=g)
+    coef = torch.randn((n, 32), generator=g) * 0.5
+    boxes = _rand_boxes(g, n, ih, iw, 6, 60)
+    boxes[0] = torch.tensor([-5.0, -3.0, 20.5, 17.25])          # clipped
+    boxes[1] = torch.tensor([iw - 9.5, ih - 12.0, iw + 8.0, ih + 3.0])
+    ref = port.process_mask(protos, coef, boxes.clone(), (ih, iw), upsample=upsample)
+    out = hm.process_mask(protos.to(cuda_device), coef.to(cuda_device), boxes.to(cuda_device), (ih, iw), upsample=upsample)
+    assert out.shape == ref.shape
+    assert set(out.unique().tolist()) <= {0.0, 1.0}
+    assert _agreement(out.cpu(), ref) >= AGREE
+    assert float(ref.sum()) > 0
+    # bit-packed variant == dense variant, exactly
+    counts = torch.tensor([n], dtype=torch.int32, device=cuda_device)
+    packed = hm.process_mask_packed(protos.to(cuda_device)[None], coef.to(cuda_device)[None], boxes.to(cuda_device)[None],
+                                    counts, (ih, iw), upsample=upsample)
+    packed.check()
+    assert torch.equal(packed.to_dense(), out.to(torch.uint8))
+
+
+def test_process_mask_batch_counts(cuda_device):
+    g = torch.Generator().manual_seed(4)
+    bs, md, mh, mw, ih, iw = 3, 20, 40, 40, 160, 160
+    protos = torch.randn((bs, 32, mh, mw), generator=g)
+    coef = torch.randn((bs, md, 32), generator=g)
+    boxes = torch.stack([_rand_boxes(g, md, ih, iw, 8, 50) for _ in range(bs)])
+    counts = torch.tensor([20, 0, 7], dtype=torch.int32)
+    out = hm.process_mask_batch(protos.to(cuda_device), coef.to(cuda_device), boxes.to(cuda_device), counts.to(cuda_device),
+                                (ih, iw), upsample=True).cpu()
+    for i, k in enumerate(counts.tolist()):
+        assert float(out[i, k:].abs().sum()) == 0
+        if k:
+            ref = port.process_mask(protos[i], coef[i, :k], boxes[i, :k].clone(), (ih, iw), upsample=True)
+            assert _agreement(out[i, :k], ref) >= AGREE
+    assert hm.process_mask(protos[0].to(cuda_device), coef[0, :0].to(cuda_device), boxes[0, :0].to(cuda_device), (ih, iw)).shape == (0, mh, mw)
