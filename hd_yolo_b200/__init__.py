@@ -29,4 +29,19 @@ from .masks import (  # noqa: F401,E402
     process_mask_packed,
 )
 
+from . import slide  # noqa: F401,E402
+from .slide import (  # noqa: F401,E402
+    Ensemble,
+    SlideAccumulator,
+    clip_coords,
+    ensemble_merge,
+    merge_nms,
+    merge_outputs,
+    rescale_outputs,
+    scale_coords,
+    sliding_window_scanner,
+    sort_keys,
+    tile_cores,
+)
+
 __version__ = "0.1.0"

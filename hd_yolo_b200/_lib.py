@@ -37,7 +37,7 @@ class Level(C.Structure):
     ]
 
 
-_vp, _i, _f, _sz = C.c_void_p, C.c_int, C.c_float, C.c_size_t
+_vp, _i, _f, _sz, _i64 = C.c_void_p, C.c_int, C.c_float, C.c_size_t, C.c_int64
 _LP = C.POINTER(Level)
 
 # name -> (restype, argtypes); must list every symbol the header declares
@@ -72,6 +72,20 @@ SIGNATURES = {
         _i,
         [_vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _i, _i, _vp, C.c_int64, _vp, _vp],
     ),
+    "hdy_affine_boxes": (_i, [_vp, _i64, _i, _f, _f, _f, _f, _f, _f, _i, _vp]),
+    "hdy_merge_append": (_i, [_vp, _vp, _vp, _vp, _vp, _i, _i, _i, _f, _i64, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
+    "hdy_merge_overhang": (_i, [_vp, _vp, _vp, _vp, _i64, _vp, _vp]),
+    "hdy_merge_workspace_bytes": (_sz, [_i64]),
+    "hdy_merge_nms": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _i64, _f, _f, _i, _vp, _vp, _vp, _sz, _vp]),
+    "hdy_merge_build": (_i, [_vp, _vp, _vp, C.c_uint32, _vp, _vp, _vp, _vp, _i64, _i64, _f, _f, _vp, _vp, _sz, _vp]),
+    "hdy_merge_rounds": (_i, [_vp, _i64, _f, _i, _i, _vp]),
+    "hdy_merge_export_states": (_i, [_vp, _i64, _vp, _vp, _i64, _vp, _vp]),
+    "hdy_merge_import_states": (_i, [_vp, _i64, _i64, _vp, _i64, _vp]),
+    "hdy_merge_finish": (_i, [_vp, _vp, _i64, _vp, _vp, _vp]),
+    "hdy_merge_select": (_i, [_vp, _vp, _vp, _i64, _vp, _vp, _vp]),
+    "hdy_sort_workspace_bytes": (_sz, [_i64]),
+    "hdy_sort_keys": (_i, [_vp, _vp, _vp, _i64, _vp, _sz, _vp]),
+    "hdy_merge_gather": (_i, [_vp, _vp, _i64, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
 }
 
 _lock = threading.Lock()

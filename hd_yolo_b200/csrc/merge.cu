@@ -1,0 +1,805 @@
+// Whole-slide tile merge: Detect.merge_outputs (T2) + Ensemble.merge (T3), sparse and exact.
+//
+// Reference: metayolo/models/yolo_head.py:450-471 (merge_outputs / rescale_outputs: shift tile-local boxes by the
+// tile origin, concatenate, no NMS) and metayolo/models/yolo.py:165-204 (Ensemble.merge: keep scores > conf, one
+// class-agnostic torchvision.ops.nms over ALL detections of the slide on their final scores, first max_det).
+//
+// torchvision's NMS is dense O(n^2) (338 s on the CPU at 2x10^5 boxes); a 100k x 100k px slide holds ~3x10^7
+// detections.  The same result is produced here without ever forming a pair matrix:
+//   * a detection can only be suppressed by a higher-scored box it intersects.  Boxes that survived the per-tile NMS
+//     never suppress each other again when merge iou_thres >= tile iou_thres, so a detection whose box cannot reach
+//     any other tile's detections ("interior": strictly inside its tile's core shrunk by the largest overhang of any
+//     box over its tile) is KEPT outright; only the overlap-band detections enter the pairwise stage;
+//   * band detections are binned by box centre into a torus hash grid (cell = 2 x mean box extent; boxes larger
+//     than a cell go to one bucket everybody scans) and copied into cell order (box + 64-bit order key), so the 3x3
+//     neighbourhood of a box is three contiguous runs;
+//   * greedy NMS is resolved as a fixed point, in rounds: a box is KEPT once every intersecting (IoU > thr)
+//     higher-ranked box is SUPPRESSED, SUPPRESSED as soon as one of them is KEPT.  Rank = (score desc, global index
+//     asc), the order torchvision's stable sort visits boxes in; no global sort is needed for the verdicts;
+//   * multi-GPU: entries [n_local, n) are replicas of seam detections owned by other ranks; they take part in every
+//     test but their verdicts are imported from the owner between rounds (hdy_merge_export/import_states).
+// The IoU arithmetic is hdy_common.cuh's iou_gt (fp32, torchvision's operation order).  Binning only prunes pairs
+// that cannot intersect, so it never changes a verdict.
+//
+// Also here: an LSD radix sort (8-bit digits, warp-private stable ranking) used to return survivors in the
+// reference's score-descending order, and the small device-wide exclusive scan both need.
+#include "hdy_common.cuh"
+
+namespace hdy {
+
+enum : uint8_t { MS_UNKNOWN = 0, MS_KEPT = 1, MS_SUPPRESSED = 2, MS_DROPPED = 3, MS_REMOTE_UNKNOWN = 4 };
+
+constexpr int kMergeThreads = 256;
+constexpr int kMaxRounds = 64;
+constexpr float kMergeCellMargin = 1.01f;
+constexpr float kMergeMaxScaled = 1.0e6f;
+
+struct MergeStats {
+  float ext_sum;
+  unsigned ext_cnt;
+  int unknown[kMaxRounds + 1];  // unknown[r] = boxes still undecided after round r
+  int rounds_run;
+};
+
+// ------------------------------------------------------------------------------------------------
+// device-wide exclusive scan of int32 (in place), 3 phases, 4096 items per block
+// ------------------------------------------------------------------------------------------------
+constexpr int kScanThreads = 1024;
+constexpr int kScanItems = 4;
+constexpr int kScanTile = kScanThreads * kScanItems;
+
+__device__ __forceinline__ int block_scan_1024(int v, int* warp_tmp, int& total) {
+  // inclusive scan over the block's `v`; returns this thread's exclusive prefix, total = block sum
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  int incl = v;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    int u = __shfl_up_sync(0xffffffffu, incl, o);
+    if (lane >= o) incl += u;
+  }
+  if (lane == 31) warp_tmp[warp] = incl;
+  __syncthreads();
+  if (warp == 0) {
+    int s = warp_tmp[lane], t = s;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      int u = __shfl_up_sync(0xffffffffu, t, o);
+      if (lane >= o) t += u;
+    }
+    warp_tmp[lane] = t - s;
+    if (lane == 31) warp_tmp[32] = t;
+  }
+  __syncthreads();
+  const int excl = warp_tmp[warp] + incl - v;
+  total = warp_tmp[32];
+  __syncthreads();
+  return excl;
+}
+
+__global__ void __launch_bounds__(kScanThreads) scan_reduce_kernel(const int* __restrict__ a, long long n,
+                                                                    int* __restrict__ block_sums) {
+  __shared__ int warp_tmp[33];
+  const long long base = (long long)blockIdx.x * kScanTile + (long long)threadIdx.x * kScanItems;
+  int s = 0;
+#pragma unroll
+  for (int k = 0; k < kScanItems; ++k)
+    if (base + k < n) s += a[base + k];
+  int total;
+  block_scan_1024(s, warp_tmp, total);
+  if (threadIdx.x == 0) block_sums[blockIdx.x] = total;
+}
+
+__global__ void __launch_bounds__(kScanThreads) scan_sums_kernel(int* __restrict__ block_sums, int nblocks,
+                                                                  int* __restrict__ total_out) {
+  __shared__ int warp_tmp[33];
+  __shared__ int carry;
+  if (threadIdx.x == 0) carry = 0;
+  __syncthreads();
+  for (int b0 = 0; b0 < nblocks; b0 += kScanThreads) {
+    const int i = b0 + threadIdx.x;
+    const int v = i < nblocks ? block_sums[i] : 0;
+    int total;
+    const int excl = block_scan_1024(v, warp_tmp, total);
+    if (i < nblocks) block_sums[i] = carry + excl;
+    __syncthreads();
+    if (threadIdx.x == 0) carry += total;
+    __syncthreads();
+  }
+  if (threadIdx.x == 0 && total_out) *total_out = carry;
+}
+
+__global__ void __launch_bounds__(kScanThreads) scan_apply_kernel(int* __restrict__ a, long long n,
+                                                                   const int* __restrict__ block_sums) {
+  __shared__ int warp_tmp[33];
+  const long long base = (long long)blockIdx.x * kScanTile + (long long)threadIdx.x * kScanItems;
+  int v[kScanItems], s = 0;
+#pragma unroll
+  for (int k = 0; k < kScanItems; ++k) {
+    v[k] = (base + k < n) ? a[base + k] : 0;
+    s += v[k];
+  }
+  int total;
+  int run = block_sums[blockIdx.x] + block_scan_1024(s, warp_tmp, total);
+#pragma unroll
+  for (int k = 0; k < kScanItems; ++k) {
+    if (base + k < n) a[base + k] = run;
+    run += v[k];
+  }
+}
+
+static inline size_t scan_scratch_ints(long long n) { return (size_t)((n + kScanTile - 1) / kScanTile) + 1; }
+
+// exclusive scan of a[0..n) in place; *total_out (device, may be NULL) receives the sum
+static int device_exclusive_scan(int* a, long long n, int* scratch, int* total_out, cudaStream_t st) {
+  if (n <= 0) return HDY_OK;
+  const int nblocks = (int)((n + kScanTile - 1) / kScanTile);
+  scan_reduce_kernel<<<nblocks, kScanThreads, 0, st>>>(a, n, scratch);
+  scan_sums_kernel<<<1, kScanThreads, 0, st>>>(scratch, nblocks, total_out);
+  scan_apply_kernel<<<nblocks, kScanThreads, 0, st>>>(a, n, scratch);
+  return check_launch("device_exclusive_scan");
+}
+
+// ------------------------------------------------------------------------------------------------
+// T2: tile-local detections -> slide coordinates, appended to flat arrays
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(1024) append_offsets_kernel(const int32_t* __restrict__ counts, int bs,
+                                                               long long* __restrict__ cursor,
+                                                               long long* __restrict__ tile_offsets) {
+  __shared__ int warp_tmp[33];
+  __shared__ long long carry;
+  if (threadIdx.x == 0) carry = *cursor;
+  __syncthreads();
+  for (int b0 = 0; b0 < bs; b0 += 1024) {
+    const int i = b0 + threadIdx.x;
+    const int v = i < bs ? max(counts[i], 0) : 0;
+    int total;
+    const int excl = block_scan_1024(v, warp_tmp, total);
+    if (i < bs) tile_offsets[i] = carry + excl;
+    __syncthreads();
+    if (threadIdx.x == 0) carry += total;
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) {
+    tile_offsets[bs] = carry;
+    *cursor = carry;
+  }
+}
+
+__global__ void append_tiles_kernel(const float4* __restrict__ boxes, const float* __restrict__ scores,
+                                    const int64_t* __restrict__ labels, const int32_t* __restrict__ counts,
+                                    const float4* __restrict__ rois, int max_det, int tile_base, float scale,
+                                    const long long* __restrict__ tile_offsets, long long capacity,
+                                    float4* __restrict__ out_boxes, float* __restrict__ out_scores,
+                                    int64_t* __restrict__ out_labels, int32_t* __restrict__ out_tile,
+                                    int32_t* __restrict__ status) {
+  const int tile = blockIdx.y;
+  const int k = min(max(counts[tile], 0), max_det);
+  const long long off = tile_offsets[tile];
+  const float4 roi = rois[tile];
+  for (int d = blockIdx.x * blockDim.x + threadIdx.x; d < k; d += gridDim.x * blockDim.x) {
+    const long long o = off + d;
+    if (o >= capacity) {
+      atomicOr(status, HDY_STATUS_OVERFLOW);
+      continue;
+    }
+    const size_t s = (size_t)tile * max_det + d;
+    float4 b = boxes[s];
+    if (scale != 1.0f) {  // rescale_outputs: r['boxes'] *= scale          yolo_head.py:468-469
+      b.x = __fmul_rn(b.x, scale);
+      b.y = __fmul_rn(b.y, scale);
+      b.z = __fmul_rn(b.z, scale);
+      b.w = __fmul_rn(b.w, scale);
+    }
+    // boxes + [roi.x0, roi.y0, roi.x0, roi.y0]                             yolo_head.py:455
+    b.x = __fadd_rn(b.x, roi.x);
+    b.y = __fadd_rn(b.y, roi.y);
+    b.z = __fadd_rn(b.z, roi.x);
+    b.w = __fadd_rn(b.w, roi.y);
+    out_boxes[o] = b;
+    if (out_scores) out_scores[o] = scores[s];
+    if (out_labels) out_labels[o] = labels[s];
+    if (out_tile) out_tile[o] = tile_base + tile;
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// overhang of boxes over their own tile (slide coordinates)
+// ------------------------------------------------------------------------------------------------
+__global__ void overhang_kernel(const float4* __restrict__ boxes, const int32_t* __restrict__ tile_id,
+                                const float4* __restrict__ tile_rois, const long long* __restrict__ n_dev,
+                                long long n_max, float* __restrict__ margin) {
+  const long long n = n_dev ? min(*n_dev, n_max) : n_max;
+  float m = 0.f;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+    const int t = tile_id[i];
+    if (t < 0) continue;
+    const float4 b = boxes[i], r = tile_rois[t];
+    float o = fmaxf(fmaxf(r.x - b.x, r.y - b.y), fmaxf(b.z - r.z, b.w - r.w));
+    if (!(o <= 3.0e38f)) o = 3.0e38f;  // NaN / inf coordinates: nothing is interior
+    m = fmaxf(m, o);
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
+  if ((threadIdx.x & 31) == 0 && m > 0.f) atomicMax(reinterpret_cast<int*>(margin), __float_as_int(m));
+}
+
+// ------------------------------------------------------------------------------------------------
+// merge NMS
+// ------------------------------------------------------------------------------------------------
+struct MergeWs {
+  MergeStats* stats;
+  int* cell;       // [G*G + 2] counts -> begin offsets -> end offsets
+  int* scan_tmp;   // scan scratch
+  float4* cbox;    // [n_max] boxes in cell order
+  uint64_t* ckey;  // [n_max] order keys in cell order
+  uint8_t* cstate; // [n_max]
+  uint32_t* pos;   // [n_max] entry -> cell-order position (0xffffffff: not active)
+  size_t bytes;
+  int G;
+};
+
+static inline size_t align256(size_t v) { return (v + 255) & ~(size_t)255; }
+
+static int merge_grid_side(long long n_max) {
+  int G = 64;
+  while (G < 2048 && (long long)G * G < 2 * n_max) G <<= 1;
+  return G;
+}
+
+static MergeWs merge_layout(void* base, long long n_max) {
+  MergeWs w;
+  w.G = merge_grid_side(n_max);
+  const size_t nb = (size_t)w.G * w.G + 2;
+  size_t o = 0;
+  unsigned char* p = static_cast<unsigned char*>(base);
+  w.stats = reinterpret_cast<MergeStats*>(p + o);
+  o += align256(sizeof(MergeStats));
+  w.cell = reinterpret_cast<int*>(p + o);
+  o += align256(nb * 4);
+  w.scan_tmp = reinterpret_cast<int*>(p + o);
+  o += align256(scan_scratch_ints((long long)nb) * 4);
+  w.cbox = reinterpret_cast<float4*>(p + o);
+  o += align256((size_t)n_max * 16);
+  w.ckey = reinterpret_cast<uint64_t*>(p + o);
+  o += align256((size_t)n_max * 8);
+  w.pos = reinterpret_cast<uint32_t*>(p + o);
+  o += align256((size_t)n_max * 4);
+  w.cstate = reinterpret_cast<uint8_t*>(p + o);
+  o += align256((size_t)n_max);
+  w.bytes = o;
+  return w;
+}
+
+struct CellGeom {
+  float cell_size, inv_cell, max_center;
+};
+
+__device__ __forceinline__ CellGeom cell_geom(const MergeStats* s) {
+  CellGeom g;
+  const unsigned c = s->ext_cnt;
+  float cs = c ? 2.0f * (s->ext_sum / (float)c) : 1.0f;
+  if (!(cs > 1e-20f) || !(cs < 1e30f)) cs = 1.0f;
+  g.cell_size = cs;
+  g.inv_cell = 1.0f / (cs * kMergeCellMargin);
+  g.max_center = cs * kMergeMaxScaled;
+  return g;
+}
+
+// 0: degenerate (never intersects anything), 1: small (bucket = torus cell), 2: large (bucket = G*G)
+__device__ __forceinline__ int merge_classify_box(const float4& b, const CellGeom& g, int G, int& bucket, int& ix,
+                                                  int& iy) {
+  const float w = b.z - b.x, h = b.w - b.y;
+  if (w <= 0.f || h <= 0.f) return 0;
+  const float cx = (b.x + b.z) * 0.5f, cy = (b.y + b.w) * 0.5f;
+  if (w <= g.cell_size && h <= g.cell_size && fabsf(cx) <= g.max_center && fabsf(cy) <= g.max_center) {
+    ix = (int)floorf(cx * g.inv_cell);
+    iy = (int)floorf(cy * g.inv_cell);
+    bucket = (ix & (G - 1)) + (iy & (G - 1)) * G;
+    return 1;
+  }
+  bucket = G * G;
+  return 2;  // also NaN / inf coordinates
+}
+
+__global__ void merge_stats_kernel(const float4* __restrict__ boxes, const float* __restrict__ scores,
+                                   const long long* __restrict__ n_dev, long long n_max, float conf,
+                                   MergeStats* __restrict__ stats) {
+  const long long n = n_dev ? min(*n_dev, n_max) : n_max;
+  float sum = 0.f;
+  unsigned cnt = 0;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+    if (!(scores[i] > conf)) continue;
+    const float4 b = boxes[i];
+    const float w = b.z - b.x, h = b.w - b.y;
+    if (w > 0.f && h > 0.f && w < 3.0e38f && h < 3.0e38f) {
+      sum += fmaxf(w, h);
+      ++cnt;
+    }
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    sum += __shfl_xor_sync(0xffffffffu, sum, o);
+    cnt += __shfl_xor_sync(0xffffffffu, cnt, o);
+  }
+  if ((threadIdx.x & 31) == 0 && cnt) {
+    atomicAdd(&stats->ext_sum, sum);
+    atomicAdd(&stats->ext_cnt, cnt);
+  }
+}
+
+struct MergeIn {
+  const float4* boxes;
+  const float* scores;
+  const uint32_t* gidx;       // optional global index per entry (tie order); NULL: gidx_base + i
+  const int32_t* tile_id;     // optional
+  const float4* tile_cores;   // optional [n_tiles] core rectangles (slide coordinates)
+  const float* margin;        // device float: largest overhang of any box over its tile
+  const long long* n_dev;     // optional device count
+  long long n_max, n_local;   // entries >= n_local are remote replicas
+  uint32_t gidx_base;
+  float conf, thr;
+};
+
+// pass 1: initial verdicts, cell histogram.  state[i]: KEPT (interior / degenerate), DROPPED (<= conf), UNKNOWN (active)
+__global__ void merge_classify_kernel(const MergeIn in, const MergeStats* __restrict__ stats, int G,
+                                      int* __restrict__ cell, uint8_t* __restrict__ state) {
+  const long long n = in.n_dev ? min(*in.n_dev, in.n_max) : in.n_max;
+  const CellGeom g = cell_geom(stats);
+  const float m = (in.tile_cores && in.margin) ? *in.margin : 0.f;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+    uint8_t st = MS_UNKNOWN;
+    const float4 b = in.boxes[i];
+    if (!(in.scores[i] > in.conf)) {  // keep = scores > conf_thres                    yolo.py:189
+      st = MS_DROPPED;
+    } else {
+      int bucket = 0, ix, iy;
+      const int cls = merge_classify_box(b, g, G, bucket, ix, iy);
+      const bool remote = i >= in.n_local;
+      if (cls == 0 && !remote) {
+        st = MS_KEPT;
+      } else {
+        bool interior = false;
+        if (!remote && in.tile_cores && in.tile_id && in.tile_id[i] >= 0) {
+          const float4 c = in.tile_cores[in.tile_id[i]];
+          interior = (b.x > c.x + m) && (b.y > c.y + m) && (b.z < c.z - m) && (b.w < c.w - m);
+        }
+        if (interior)
+          st = MS_KEPT;
+        else
+          atomicAdd(&cell[bucket], 1);
+      }
+    }
+    state[i] = st;
+  }
+}
+
+// pass 2: copy active entries into cell order
+__global__ void merge_fill_kernel(const MergeIn in, const MergeStats* __restrict__ stats, int G,
+                                  int* __restrict__ cell, const uint8_t* __restrict__ state,
+                                  float4* __restrict__ cbox, uint64_t* __restrict__ ckey,
+                                  uint8_t* __restrict__ cstate, uint32_t* __restrict__ pos) {
+  const long long n = in.n_dev ? min(*in.n_dev, in.n_max) : in.n_max;
+  const CellGeom g = cell_geom(stats);
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+    uint32_t p = 0xffffffffu;
+    if (state[i] == MS_UNKNOWN) {
+      const float4 b = in.boxes[i];
+      int bucket = 0, ix, iy;
+      const int cls = merge_classify_box(b, g, G, bucket, ix, iy);
+      p = (uint32_t)atomicAdd(&cell[bucket], 1);
+      cbox[p] = b;
+      ckey[p] = make_key(in.scores[i], in.gidx ? in.gidx[i] : in.gidx_base + (uint32_t)i);
+      const bool remote = i >= in.n_local;
+      cstate[p] = remote ? (uint8_t)MS_REMOTE_UNKNOWN : (cls == 0 ? (uint8_t)MS_KEPT : (uint8_t)MS_UNKNOWN);
+    }
+    pos[i] = p;
+  }
+}
+
+// one round of the fixed point over cell-ordered positions
+__global__ void __launch_bounds__(kMergeThreads) merge_round_kernel(const float4* __restrict__ cbox,
+                                                                    const uint64_t* __restrict__ ckey,
+                                                                    uint8_t* cstate, const int* __restrict__ cell,
+                                                                    MergeStats* stats, int G, float thr, int round) {
+  if (round > 0 && stats->unknown[round - 1] == 0) {
+    if (blockIdx.x == 0 && threadIdx.x == 0) stats->unknown[round] = 0;
+    return;
+  }
+  const int NB = G * G + 1;
+  const int n_active = cell[NB - 1];
+  const int large_begin = cell[NB - 2], large_end = n_active;
+  const CellGeom g = cell_geom(stats);
+  volatile uint8_t* vstate = cstate;
+  int unknown = 0;
+  for (int p = blockIdx.x * blockDim.x + threadIdx.x; p < n_active; p += gridDim.x * blockDim.x) {
+    if (vstate[p] != MS_UNKNOWN) continue;
+    const float4 bi = cbox[p];
+    const uint64_t ki = ckey[p];
+    int decided = MS_KEPT;
+    auto visit = [&](int q) -> bool {
+      if (ckey[q] < ki && iou_gt(cbox[q], bi, thr)) {
+        const uint8_t sq = vstate[q];
+        if (sq == MS_KEPT) {
+          decided = MS_SUPPRESSED;
+          return true;
+        }
+        if (sq == MS_UNKNOWN || sq == MS_REMOTE_UNKNOWN) decided = MS_UNKNOWN;
+      }
+      return false;
+    };
+    bool done = false;
+    if (p < large_begin) {
+      const float cx = (bi.x + bi.z) * 0.5f, cy = (bi.y + bi.w) * 0.5f;
+      const int ix = (int)floorf(cx * g.inv_cell), iy = (int)floorf(cy * g.inv_cell);
+#pragma unroll 1
+      for (int dy = -1; dy <= 1 && !done; ++dy) {
+        const int rowb = ((iy + dy) & (G - 1)) * G;
+#pragma unroll 1
+        for (int dx = -1; dx <= 1 && !done; ++dx) {
+          const int b = ((ix + dx) & (G - 1)) + rowb;
+          const int beg = b ? cell[b - 1] : 0, end = cell[b];
+          for (int q = beg; q < end; ++q)
+            if (visit(q)) {
+              done = true;
+              break;
+            }
+        }
+      }
+      for (int q = large_begin; q < large_end && !done; ++q) done = visit(q);
+    } else {
+      for (int q = 0; q < n_active && !done; ++q) done = visit(q);
+    }
+    if (decided != MS_UNKNOWN)
+      vstate[p] = (uint8_t)decided;
+    else
+      unknown = 1;
+  }
+  unknown = __syncthreads_count(unknown);
+  if (threadIdx.x == 0 && unknown) atomicAdd(&stats->unknown[round], unknown);
+}
+
+__global__ void merge_finish_kernel(const uint32_t* __restrict__ pos, const uint8_t* __restrict__ cstate,
+                                    const long long* __restrict__ n_dev, long long n_max,
+                                    uint8_t* __restrict__ state, int32_t* __restrict__ status) {
+  const long long n = n_dev ? min(*n_dev, n_max) : n_max;
+  bool bad = false;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+    const uint32_t p = pos[i];
+    if (p == 0xffffffffu) continue;
+    uint8_t s = cstate[p];
+    if (s == MS_UNKNOWN || s == MS_REMOTE_UNKNOWN) {
+      s = MS_UNKNOWN;
+      bad = true;
+    }
+    state[i] = s;
+  }
+  if (bad && status) atomicOr(status, HDY_STATUS_ROUNDS);
+}
+
+__global__ void merge_export_kernel(const uint32_t* __restrict__ pos, const uint8_t* __restrict__ cstate,
+                                    const uint8_t* __restrict__ state, const int64_t* __restrict__ sel, long long m,
+                                    uint8_t* __restrict__ out) {
+  for (long long k = (long long)blockIdx.x * blockDim.x + threadIdx.x; k < m; k += (long long)gridDim.x * blockDim.x) {
+    const int64_t i = sel[k];
+    const uint32_t p = pos[i];
+    out[k] = (p == 0xffffffffu) ? state[i] : cstate[p];
+  }
+}
+
+__global__ void merge_import_kernel(const uint32_t* __restrict__ pos, uint8_t* __restrict__ cstate, long long first,
+                                    const uint8_t* __restrict__ states, long long m) {
+  for (long long k = (long long)blockIdx.x * blockDim.x + threadIdx.x; k < m; k += (long long)gridDim.x * blockDim.x) {
+    const uint32_t p = pos[first + k];
+    if (p == 0xffffffffu) continue;
+    const uint8_t s = states[k];
+    cstate[p] = (s == MS_KEPT || s == MS_SUPPRESSED || s == MS_DROPPED) ? s : (uint8_t)MS_REMOTE_UNKNOWN;
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// survivors -> keys (unordered compaction), LSD radix sort, gather
+// ------------------------------------------------------------------------------------------------
+__global__ void keep_keys_kernel(const uint8_t* __restrict__ state, const float* __restrict__ scores,
+                                 const long long* __restrict__ n_dev, long long n_max, uint64_t* __restrict__ keys,
+                                 int* __restrict__ count) {
+  const long long n = n_dev ? min(*n_dev, n_max) : n_max;
+  const long long span = (long long)gridDim.x * blockDim.x;
+  const long long iters = (n + span - 1) / span;
+  const int lane = threadIdx.x & 31;
+  for (long long it = 0; it < iters; ++it) {
+    const long long i = it * span + (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    const bool k = i < n && state[i] == MS_KEPT;
+    const unsigned m = __ballot_sync(0xffffffffu, k);
+    int base = 0;
+    if (lane == 0 && m) base = atomicAdd(count, __popc(m));
+    base = __shfl_sync(0xffffffffu, base, 0);
+    if (k) keys[base + __popc(m & ((1u << lane) - 1u))] = make_key(scores[i], (uint32_t)i);
+  }
+}
+
+constexpr int kSortThreads = 256;                         // 8 warps
+constexpr int kSortPerWarp = 1024;                        // keys per warp sub-tile
+constexpr int kSortWarps = kSortThreads / 32;
+
+// histogram of one digit per warp sub-tile: hist[digit * n_sub + sub]
+__global__ void __launch_bounds__(kSortThreads) sort_hist_kernel(const uint64_t* __restrict__ keys,
+                                                                  const int* __restrict__ n_dev, int n_max, int shift,
+                                                                  int n_sub, int* __restrict__ hist) {
+  __shared__ int h[kSortWarps][256];
+  const int n = n_dev ? min(*n_dev, n_max) : n_max;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int sub = blockIdx.x * kSortWarps + warp;
+  for (int d = lane; d < 256; d += 32) h[warp][d] = 0;
+  __syncwarp();
+  const long long b = (long long)sub * kSortPerWarp;
+  for (int k = lane; k < kSortPerWarp; k += 32)
+    if (b + k < n) atomicAdd(&h[warp][(int)((keys[b + k] >> shift) & 255)], 1);
+  __syncwarp();
+  if (sub < n_sub)
+    for (int d = lane; d < 256; d += 32) hist[(size_t)d * n_sub + sub] = h[warp][d];
+}
+
+__global__ void __launch_bounds__(kSortThreads) sort_scatter_kernel(const uint64_t* __restrict__ keys,
+                                                                     const int* __restrict__ n_dev, int n_max,
+                                                                     int shift, int n_sub, const int* __restrict__ hist,
+                                                                     uint64_t* __restrict__ out) {
+  __shared__ int base[kSortWarps][256];
+  const int n = n_dev ? min(*n_dev, n_max) : n_max;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int sub = blockIdx.x * kSortWarps + warp;
+  if (sub >= n_sub) return;
+  for (int d = lane; d < 256; d += 32) base[warp][d] = hist[(size_t)d * n_sub + sub];
+  __syncwarp();
+  const long long b = (long long)sub * kSortPerWarp;
+  for (int k0 = 0; k0 < kSortPerWarp; k0 += 32) {
+    const long long i = b + k0 + lane;
+    const bool valid = i < n;
+    const uint64_t key = valid ? keys[i] : 0;
+    const int d = valid ? (int)((key >> shift) & 255) : 256 + lane;  // invalid lanes match nobody
+    const unsigned peers = __match_any_sync(0xffffffffu, d);
+    const int rank = __popc(peers & ((1u << lane) - 1u));
+    int dst = 0;
+    if (valid) dst = base[warp][d] + rank;
+    __syncwarp();
+    if (valid && rank == 0) base[warp][d] += __popc(peers);
+    __syncwarp();
+    if (valid) out[dst] = key;
+  }
+}
+
+__global__ void merge_gather_kernel(const uint64_t* __restrict__ keys, const int* __restrict__ count, int max_det,
+                                    const float4* __restrict__ boxes, const float* __restrict__ scores,
+                                    const int64_t* __restrict__ labels, int64_t* __restrict__ out_idx,
+                                    float4* __restrict__ out_boxes, float* __restrict__ out_scores,
+                                    int64_t* __restrict__ out_labels, int* __restrict__ out_count) {
+  const int k = min(*count, max_det);
+  if (blockIdx.x == 0 && threadIdx.x == 0) *out_count = k;
+  for (int j = blockIdx.x * blockDim.x + threadIdx.x; j < k; j += gridDim.x * blockDim.x) {
+    const uint32_t i = key_index(keys[j]);
+    if (out_idx) out_idx[j] = (int64_t)i;
+    if (out_boxes) out_boxes[j] = boxes[i];
+    if (out_scores) out_scores[j] = scores[i];
+    if (out_labels && labels) out_labels[j] = labels[i];
+  }
+}
+
+static inline unsigned blocks_for(long long n, int threads, int max_blocks = 148 * 16) {
+  long long b = (n + threads - 1) / threads;
+  if (b < 1) b = 1;
+  if (b > max_blocks) b = max_blocks;
+  return (unsigned)b;
+}
+
+}  // namespace hdy
+
+using namespace hdy;
+
+extern "C" {
+
+int hdy_merge_append(const float* boxes, const float* scores, const int64_t* labels, const int32_t* counts,
+                     const float* rois, int bs, int max_det, int tile_base, float scale, int64_t capacity,
+                     float* out_boxes, float* out_scores, int64_t* out_labels, int32_t* out_tile, int64_t* cursor,
+                     int64_t* tile_offsets, int32_t* status, hdy_stream_t stream) {
+  HDY_REQUIRE(bs >= 0 && max_det > 0 && capacity >= 0, "hdy_merge_append: bad sizes");
+  if (bs == 0) return HDY_OK;
+  HDY_REQUIRE(bs <= 65535, "hdy_merge_append: bs > 65535 (split the batch)");
+  HDY_REQUIRE(boxes && counts && rois && out_boxes && cursor && tile_offsets && status, "hdy_merge_append: NULL pointer");
+  HDY_REQUIRE((((uintptr_t)boxes | (uintptr_t)rois | (uintptr_t)out_boxes) & 15) == 0,
+              "hdy_merge_append: box arrays must be 16-byte aligned");
+  HDY_REQUIRE(!out_scores || scores, "hdy_merge_append: out_scores without scores");
+  HDY_REQUIRE(!out_labels || labels, "hdy_merge_append: out_labels without labels");
+  cudaStream_t st = (cudaStream_t)stream;
+  append_offsets_kernel<<<1, 1024, 0, st>>>(counts, bs, reinterpret_cast<long long*>(cursor),
+                                            reinterpret_cast<long long*>(tile_offsets));
+  dim3 grid((unsigned)((max_det + 127) / 128), (unsigned)bs);
+  append_tiles_kernel<<<grid, 128, 0, st>>>(reinterpret_cast<const float4*>(boxes), scores, labels, counts,
+                                            reinterpret_cast<const float4*>(rois), max_det, tile_base, scale,
+                                            reinterpret_cast<const long long*>(tile_offsets), capacity,
+                                            reinterpret_cast<float4*>(out_boxes), out_scores, out_labels, out_tile,
+                                            status);
+  return check_launch("hdy_merge_append");
+}
+
+int hdy_merge_overhang(const float* boxes, const int32_t* tile_id, const float* tile_rois, const int64_t* n_dev,
+                       int64_t n_max, float* margin, hdy_stream_t stream) {
+  HDY_REQUIRE(n_max >= 0 && margin, "hdy_merge_overhang: bad arguments");
+  if (n_max == 0) return HDY_OK;
+  HDY_REQUIRE(boxes && tile_id && tile_rois && (((uintptr_t)boxes | (uintptr_t)tile_rois) & 15) == 0,
+              "hdy_merge_overhang: NULL or misaligned pointer");
+  overhang_kernel<<<blocks_for(n_max, 256), 256, 0, (cudaStream_t)stream>>>(
+      reinterpret_cast<const float4*>(boxes), tile_id, reinterpret_cast<const float4*>(tile_rois),
+      reinterpret_cast<const long long*>(n_dev), n_max, margin);
+  return check_launch("hdy_merge_overhang");
+}
+
+size_t hdy_merge_workspace_bytes(int64_t n_max) {
+  if (n_max <= 0) return 256;
+  return merge_layout(nullptr, n_max).bytes;
+}
+
+int hdy_merge_build(const float* boxes, const float* scores, const uint32_t* gidx, uint32_t gidx_base,
+                    const int32_t* tile_id, const float* tile_cores, const float* margin, const int64_t* n_dev,
+                    int64_t n_max, int64_t n_local, float conf_thres, float iou_thres, uint8_t* state,
+                    void* workspace, size_t workspace_bytes, hdy_stream_t stream) {
+  HDY_REQUIRE(n_max >= 0 && n_local >= 0 && n_local <= n_max, "hdy_merge_build: bad sizes");
+  HDY_REQUIRE(n_max < (1ll << 31), "hdy_merge_build: at most 2^31-1 detections per call");
+  HDY_REQUIRE(iou_thres >= 0.f, "hdy_merge_build: iou_thres must be >= 0");
+  HDY_REQUIRE(workspace && workspace_bytes >= hdy_merge_workspace_bytes(n_max), "hdy_merge_build: workspace too small");
+  HDY_REQUIRE(!tile_cores || (tile_id && margin), "hdy_merge_build: tile_cores needs tile_id and margin");
+  cudaStream_t st = (cudaStream_t)stream;
+  MergeWs w = merge_layout(workspace, n_max > 0 ? n_max : 1);
+  const size_t nb = (size_t)w.G * w.G + 2;
+  cudaError_t e = cudaMemsetAsync(w.stats, 0, sizeof(MergeStats), st);
+  if (e == cudaSuccess) e = cudaMemsetAsync(w.cell, 0, nb * 4, st);
+  if (e != cudaSuccess) {
+    set_error("hdy_merge_build: cudaMemsetAsync: %s", cudaGetErrorString(e));
+    return HDY_ERR_CUDA;
+  }
+  if (n_max == 0) return HDY_OK;
+  HDY_REQUIRE(boxes && scores && state && (((uintptr_t)boxes | (uintptr_t)tile_cores) & 15) == 0,
+              "hdy_merge_build: NULL or misaligned pointer");
+  MergeIn in;
+  in.boxes = reinterpret_cast<const float4*>(boxes);
+  in.scores = scores;
+  in.gidx = gidx;
+  in.tile_id = tile_id;
+  in.tile_cores = reinterpret_cast<const float4*>(tile_cores);
+  in.margin = margin;
+  in.n_dev = reinterpret_cast<const long long*>(n_dev);
+  in.n_max = n_max;
+  in.n_local = n_local;
+  in.gidx_base = gidx_base;
+  in.conf = conf_thres;
+  in.thr = iou_thres;
+  const unsigned blocks = blocks_for(n_max, kMergeThreads);
+  merge_stats_kernel<<<blocks, kMergeThreads, 0, st>>>(in.boxes, scores, in.n_dev, n_max, conf_thres, w.stats);
+  merge_classify_kernel<<<blocks, kMergeThreads, 0, st>>>(in, w.stats, w.G, w.cell, state);
+  int rc = device_exclusive_scan(w.cell, (long long)nb - 1, w.scan_tmp, nullptr, st);
+  if (rc) return rc;
+  merge_fill_kernel<<<blocks, kMergeThreads, 0, st>>>(in, w.stats, w.G, w.cell, state, w.cbox, w.ckey, w.cstate,
+                                                      w.pos);
+  return check_launch("hdy_merge_build");
+}
+
+int hdy_merge_rounds(void* workspace, int64_t n_max, float iou_thres, int first_round, int n_rounds,
+                     hdy_stream_t stream) {
+  HDY_REQUIRE(workspace && n_max >= 0, "hdy_merge_rounds: bad arguments");
+  HDY_REQUIRE(first_round >= 0 && n_rounds >= 0 && first_round + n_rounds <= kMaxRounds,
+              "hdy_merge_rounds: at most %d rounds in total", kMaxRounds);
+  if (n_max == 0) return HDY_OK;
+  MergeWs w = merge_layout(workspace, n_max);
+  const unsigned blocks = blocks_for(n_max, kMergeThreads, 148 * 8);
+  for (int r = first_round; r < first_round + n_rounds; ++r)
+    merge_round_kernel<<<blocks, kMergeThreads, 0, (cudaStream_t)stream>>>(w.cbox, w.ckey, w.cstate, w.cell, w.stats,
+                                                                           w.G, iou_thres, r);
+  return check_launch("hdy_merge_rounds");
+}
+
+int hdy_merge_finish(void* workspace, const int64_t* n_dev, int64_t n_max, uint8_t* state, int32_t* status,
+                     hdy_stream_t stream) {
+  HDY_REQUIRE(workspace && n_max >= 0, "hdy_merge_finish: bad arguments");
+  if (n_max == 0) return HDY_OK;
+  HDY_REQUIRE(state != nullptr, "hdy_merge_finish: state is NULL");
+  MergeWs w = merge_layout(workspace, n_max);
+  merge_finish_kernel<<<blocks_for(n_max, 256), 256, 0, (cudaStream_t)stream>>>(
+      w.pos, w.cstate, reinterpret_cast<const long long*>(n_dev), n_max, state, status);
+  return check_launch("hdy_merge_finish");
+}
+
+int hdy_merge_export_states(void* workspace, int64_t n_max, const uint8_t* state, const int64_t* sel, int64_t m,
+                            uint8_t* out, hdy_stream_t stream) {
+  HDY_REQUIRE(workspace && n_max >= 0 && m >= 0, "hdy_merge_export_states: bad arguments");
+  if (m == 0) return HDY_OK;
+  HDY_REQUIRE(state && sel && out, "hdy_merge_export_states: NULL pointer");
+  MergeWs w = merge_layout(workspace, n_max);
+  merge_export_kernel<<<blocks_for(m, 256), 256, 0, (cudaStream_t)stream>>>(w.pos, w.cstate, state, sel, m, out);
+  return check_launch("hdy_merge_export_states");
+}
+
+int hdy_merge_import_states(void* workspace, int64_t n_max, int64_t first, const uint8_t* states, int64_t m,
+                            hdy_stream_t stream) {
+  HDY_REQUIRE(workspace && n_max >= 0 && m >= 0 && first >= 0 && first + m <= n_max,
+              "hdy_merge_import_states: bad arguments");
+  if (m == 0) return HDY_OK;
+  HDY_REQUIRE(states != nullptr, "hdy_merge_import_states: NULL pointer");
+  MergeWs w = merge_layout(workspace, n_max);
+  merge_import_kernel<<<blocks_for(m, 256), 256, 0, (cudaStream_t)stream>>>(w.pos, w.cstate, first, states, m);
+  return check_launch("hdy_merge_import_states");
+}
+
+int hdy_merge_nms(const float* boxes, const float* scores, const int32_t* tile_id, const float* tile_cores,
+                  const float* margin, const int64_t* n_dev, int64_t n_max, float conf_thres, float iou_thres,
+                  int max_rounds, uint8_t* state, int32_t* status, void* workspace, size_t workspace_bytes,
+                  hdy_stream_t stream) {
+  HDY_REQUIRE(max_rounds >= 1 && max_rounds <= kMaxRounds, "hdy_merge_nms: max_rounds out of range [1,%d]", kMaxRounds);
+  int rc = hdy_merge_build(boxes, scores, nullptr, 0, tile_id, tile_cores, margin, n_dev, n_max, n_max, conf_thres,
+                           iou_thres, state, workspace, workspace_bytes, stream);
+  if (rc) return rc;
+  rc = hdy_merge_rounds(workspace, n_max, iou_thres, 0, max_rounds, stream);
+  if (rc) return rc;
+  return hdy_merge_finish(workspace, n_dev, n_max, state, status, stream);
+}
+
+size_t hdy_sort_workspace_bytes(int64_t n_max) {
+  if (n_max <= 0) return 256;
+  const long long n_sub = (n_max + kSortPerWarp - 1) / kSortPerWarp;
+  const long long hist = 256 * n_sub;
+  return align256((size_t)hist * 4) + align256(scan_scratch_ints(hist) * 4);
+}
+
+/* ascending LSD radix sort of 64-bit keys; result in `keys` (tmp is scratch of the same size) */
+int hdy_sort_keys(uint64_t* keys, uint64_t* tmp, const int32_t* n_dev, int64_t n_max, void* workspace,
+                  size_t workspace_bytes, hdy_stream_t stream) {
+  HDY_REQUIRE(n_max >= 0 && n_max < (1ll << 31), "hdy_sort_keys: bad size");
+  if (n_max == 0) return HDY_OK;
+  HDY_REQUIRE(keys && tmp && workspace && workspace_bytes >= hdy_sort_workspace_bytes(n_max),
+              "hdy_sort_keys: NULL pointer or workspace too small");
+  cudaStream_t st = (cudaStream_t)stream;
+  const int n_sub = (int)((n_max + kSortPerWarp - 1) / kSortPerWarp);
+  const long long hist_n = 256ll * n_sub;
+  int* hist = static_cast<int*>(workspace);
+  int* scratch = reinterpret_cast<int*>(static_cast<unsigned char*>(workspace) + align256((size_t)hist_n * 4));
+  const unsigned blocks = (unsigned)((n_sub + kSortWarps - 1) / kSortWarps);
+  uint64_t* src = keys;
+  uint64_t* dst = tmp;
+  for (int pass = 0; pass < 8; ++pass) {
+    sort_hist_kernel<<<blocks, kSortThreads, 0, st>>>(src, n_dev, (int)n_max, pass * 8, n_sub, hist);
+    int rc = device_exclusive_scan(hist, hist_n, scratch, nullptr, st);
+    if (rc) return rc;
+    sort_scatter_kernel<<<blocks, kSortThreads, 0, st>>>(src, n_dev, (int)n_max, pass * 8, n_sub, hist, dst);
+    uint64_t* t = src;
+    src = dst;
+    dst = t;
+  }
+  return check_launch("hdy_sort_keys");  // 8 passes: the result is back in `keys`
+}
+
+int hdy_merge_select(const uint8_t* state, const float* scores, const int64_t* n_dev, int64_t n_max, uint64_t* keys,
+                     int32_t* count, hdy_stream_t stream) {
+  HDY_REQUIRE(n_max >= 0 && n_max < (1ll << 31) && count, "hdy_merge_select: bad arguments");
+  cudaStream_t st = (cudaStream_t)stream;
+  cudaError_t e = cudaMemsetAsync(count, 0, 4, st);
+  if (e != cudaSuccess) {
+    set_error("hdy_merge_select: %s", cudaGetErrorString(e));
+    return HDY_ERR_CUDA;
+  }
+  if (n_max == 0) return HDY_OK;
+  HDY_REQUIRE(state && scores && keys, "hdy_merge_select: NULL pointer");
+  keep_keys_kernel<<<blocks_for(n_max, 256), 256, 0, st>>>(state, scores, reinterpret_cast<const long long*>(n_dev),
+                                                           n_max, keys, count);
+  return check_launch("hdy_merge_select");
+}
+
+int hdy_merge_gather(const uint64_t* keys, const int32_t* count, int64_t max_det, const float* boxes,
+                     const float* scores, const int64_t* labels, int64_t* out_idx, float* out_boxes,
+                     float* out_scores, int64_t* out_labels, int32_t* out_count, hdy_stream_t stream) {
+  HDY_REQUIRE(max_det >= 0 && max_det < (1ll << 31) && keys && count && out_count, "hdy_merge_gather: bad arguments");
+  HDY_REQUIRE((!out_boxes || boxes) && (!out_scores || scores), "hdy_merge_gather: output without its source");
+  HDY_REQUIRE((((uintptr_t)boxes | (uintptr_t)out_boxes) & 15) == 0, "hdy_merge_gather: box arrays must be 16-byte aligned");
+  merge_gather_kernel<<<blocks_for(max_det > 0 ? max_det : 1, 256), 256, 0, (cudaStream_t)stream>>>(
+      keys, count, (int)max_det, reinterpret_cast<const float4*>(boxes), scores, labels, out_idx,
+      reinterpret_cast<float4*>(out_boxes), out_scores, out_labels, out_count);
+  return check_launch("hdy_merge_gather");
+}
+
+}  // extern "C"

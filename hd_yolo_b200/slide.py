@@ -1,0 +1,345 @@
+"""Whole-slide tiling and tile-merge: host-side mirror of the reference functions over csrc/merge.cu, csrc/coords.cu.
+
+* ``sliding_window_scanner``  -- hnet/utils.py:37-62 (== metayolo/models/utils_o.py:37-62)          (T1, host side)
+* ``merge_outputs``           -- Detect.merge_outputs, metayolo/models/yolo_head.py:450-463             (T2)
+* ``rescale_outputs``         -- Detect.rescale_outputs, yolo_head.py:465-471 (in place)               (T2)
+* ``Ensemble.merge`` / ``ensemble_merge`` -- metayolo/models/yolo.py:165-204                           (T3)
+* ``scale_coords`` / ``clip_coords``      -- metayolo/models/utils_general.py:161-190 (in place)       (C1)
+* ``SlideAccumulator``        -- the struct-of-arrays form the slide pipeline uses: DetectBatch results are appended
+                                 in slide coordinates without leaving the device, then merged once.
+
+The merge NMS is sparse (spatial hash + fixed-point rounds) but returns exactly what torchvision.ops.nms returns on
+the concatenated detections.  No CPU fallback.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from typing import Dict, List, Optional, Sequence, Tuple
+
+import torch
+
+from . import _lib
+from ._lib import HdyError, ptr
+from .ops import DetectBatch, _Scratch, _aligned16, _call, _conf_thr_f32, _iou_thr_f32, _need_cuda, _stream
+
+__all__ = ["sliding_window_scanner", "tile_cores", "merge_outputs", "rescale_outputs", "scale_coords", "clip_coords",
+           "merge_nms", "ensemble_merge", "Ensemble", "SlideAccumulator", "sort_keys",
+           "STATE_KEPT", "STATE_SUPPRESSED", "STATE_DROPPED"]
+
+STATE_UNKNOWN, STATE_KEPT, STATE_SUPPRESSED, STATE_DROPPED = 0, 1, 2, 3
+AFFINE_UNPAD, AFFINE_SCALE, AFFINE_CLIP, AFFINE_ROUND = 1, 2, 4, 8
+_ws = _Scratch()
+
+
+def _pair(v):
+    return (v, v) if isinstance(v, (int, float)) else (v[0], v[1])
+
+
+# ------------------------------------------------------------------------------------------------ T1
+def sliding_window_scanner(image_size, roi_size=None, overlap=0) -> torch.Tensor:
+    """hnet/utils.py:37-62: window origins every (roi - overlap) pixels, x fastest; windows are clipped to the
+    image, so the last row / column are slivers.  Returns [n, 4] fp32 (x0, y0, x1, y1) on the host (this is
+    control-plane data: 11 025 rows for a 100k x 100k px slide)."""
+    if roi_size is None:
+        return torch.tensor([[0., 0., image_size[0], image_size[1]]], dtype=torch.float32)
+    h, w = _pair(image_size)
+    roi_h, roi_w = _pair(roi_size)
+    xs = torch.arange(0, w, roi_w - overlap, dtype=torch.float32) if w > roi_w else torch.zeros(1)
+    ys = torch.arange(0, h, roi_h - overlap, dtype=torch.float32) if h > roi_h else torch.zeros(1)
+    x0 = xs.repeat(len(ys))
+    y0 = ys.repeat_interleave(len(xs))
+    out = torch.stack((x0, y0, x0 + roi_w, y0 + roi_h), 1)
+    out[:, 0::2] = out[:, 0::2].clamp(min=0, max=w)   # clip_boxes_to_image
+    out[:, 1::2] = out[:, 1::2].clamp(min=0, max=h)
+    return out
+
+
+def tile_cores(rois: torch.Tensor) -> torch.Tensor:
+    """For every tile the rectangle no OTHER tile of a grid tiling reaches: x from the right edge of the previous
+    column to the left edge of the next one (unbounded at the border), same in y.  Host side, [n, 4] fp32."""
+    r = rois.detach().cpu().to(torch.float64)
+    big = 3.0e38
+    out = torch.empty((len(r), 4), dtype=torch.float64)
+    for lo, hi in ((0, 2), (1, 3)):
+        starts = torch.unique(r[:, lo])                    # sorted column / row origins
+        ends = torch.stack([r[r[:, lo] == s, hi].max() for s in starts])
+        idx = torch.searchsorted(starts, r[:, lo].contiguous())
+        prev_end = torch.cat([torch.tensor([-big], dtype=torch.float64), ends[:-1]])
+        # several columns before this one may reach into it: take the furthest
+        prev_end = torch.cummax(prev_end, 0).values
+        next_start = torch.cat([starts[1:], torch.tensor([big], dtype=torch.float64)])
+        out[:, lo] = prev_end[idx]
+        out[:, hi] = next_start[idx]
+    return out.to(torch.float32)
+
+
+# ------------------------------------------------------------------------------------------------ C1
+def _affine(rows: torch.Tensor, pad_x, pad_y, gain, scale, clip_w, clip_h, flags):
+    _need_cuda(rows, "coords")
+    if rows.dim() != 2 or rows.shape[1] < 4 or rows.stride(1) != 1:
+        raise HdyError("coords must be [n, >=4] with unit stride along columns")
+    if rows.shape[0]:
+        _call("hdy_affine_boxes", ptr(rows), rows.shape[0], rows.stride(0), float(pad_x), float(pad_y), float(gain),
+              float(scale), float(clip_w), float(clip_h), flags, _stream())
+    return rows
+
+
+def clip_coords(boxes: torch.Tensor, shape) -> None:
+    """utils_general.py:181-190 (tensor branch), in place: x to [0, shape[1]], y to [0, shape[0]]."""
+    _affine(boxes, 0, 0, 1, 1, shape[1], shape[0], AFFINE_CLIP)
+
+
+def scale_coords(img1_shape, coords: torch.Tensor, img0_shape, ratio_pad=None, round_: bool = False) -> torch.Tensor:
+    """utils_general.py:161-178, in place on coords [n, >=4]: undo the letterbox (subtract pad, divide by gain),
+    clip to img0_shape.  round_=True fuses the ``.round()`` of evaluation.py:109."""
+    img1_shape, img0_shape = _pair(img1_shape), _pair(img0_shape)
+    if ratio_pad is None:
+        gain = min(img1_shape[0] / img0_shape[0], img1_shape[1] / img0_shape[1])
+        pad = (img1_shape[1] - img0_shape[1] * gain) / 2, (img1_shape[0] - img0_shape[0] * gain) / 2
+    else:
+        gain = ratio_pad[0][0]
+        pad = ratio_pad[1]
+    return _affine(coords, pad[0], pad[1], gain, 1, img0_shape[1], img0_shape[0],
+                   AFFINE_UNPAD | AFFINE_CLIP | (AFFINE_ROUND if round_ else 0))
+
+
+def rescale_outputs(r: Dict[str, torch.Tensor], scale: float = 1.0) -> Dict[str, torch.Tensor]:
+    """Detect.rescale_outputs (yolo_head.py:465-471): r['boxes'] *= scale, in place."""
+    if scale != 1.0:
+        _affine(r['boxes'], 0, 0, 1, scale, 0, 0, AFFINE_SCALE)
+    return r
+
+
+# ------------------------------------------------------------------------------------------------ T3 core
+def merge_nms(boxes: torch.Tensor, scores: torch.Tensor, conf_thres: float, iou_thres: float,
+              tile_id: Optional[torch.Tensor] = None, cores: Optional[torch.Tensor] = None,
+              margin: Optional[torch.Tensor] = None, n_dev: Optional[torch.Tensor] = None,
+              max_rounds: int = 24) -> torch.Tensor:
+    """Verdict per row of the slide-level greedy NMS of Ensemble.merge (yolo.py:189-195):
+    uint8 [n] of STATE_KEPT / STATE_SUPPRESSED / STATE_DROPPED (score <= conf_thres).
+    tile_id + cores + margin enable the interior shortcut (see include/hd_yolo_b200.h)."""
+    _need_cuda(boxes, "boxes")
+    _need_cuda(scores, "scores")
+    n = boxes.shape[0]
+    if boxes.dim() != 2 or boxes.shape[1] != 4 or scores.shape != (n,):
+        raise HdyError("boxes must be [n,4] and scores [n]")
+    dev = boxes.device
+    state = torch.empty((n,), dtype=torch.uint8, device=dev)
+    if n == 0:
+        return state
+    boxes = _aligned16(boxes.contiguous())
+    scores = scores.contiguous()
+    lib = _lib.load()
+    wbytes = lib.hdy_merge_workspace_bytes(n)
+    ws = _ws.get(dev, "merge", wbytes)
+    status = torch.zeros((1,), dtype=torch.int32, device=dev)
+    use_cores = cores is not None
+    if use_cores and (tile_id is None or margin is None):
+        raise HdyError("the interior shortcut needs tile_id, cores and margin")
+    rounds = max_rounds
+    while True:
+        _call("hdy_merge_nms", ptr(boxes), ptr(scores), ptr(tile_id) if use_cores else None,
+              ptr(cores) if use_cores else None, ptr(margin) if use_cores else None, ptr(n_dev), n,
+              _conf_thr_f32(conf_thres), _iou_thr_f32(iou_thres), rounds, ptr(state), ptr(status), ptr(ws), wbytes,
+              _stream(), launches=8 + rounds)
+        if not int(status.item()) & _lib.HDY_STATUS_ROUNDS:
+            return state
+        if rounds >= 64:
+            raise HdyError("merge NMS did not converge in 64 rounds")
+        rounds, _ = min(64, rounds * 2), status.zero_()
+
+
+def sort_keys(keys: torch.Tensor, n_dev: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """Ascending in-place LSD radix sort of int64-typed 64-bit keys (bit pattern treated as unsigned)."""
+    if not keys.is_cuda or keys.dtype != torch.int64 or not keys.is_contiguous():
+        raise HdyError("keys must be a contiguous CUDA int64 tensor")
+    n = keys.numel()
+    if n:
+        lib = _lib.load()
+        wbytes = lib.hdy_sort_workspace_bytes(n)
+        ws = _ws.get(keys.device, "sort", wbytes)
+        tmp = _ws.get(keys.device, "sort_tmp", n * 8)
+        _call("hdy_sort_keys", ptr(keys), ptr(tmp), ptr(n_dev), n, ptr(ws), wbytes, _stream(), launches=8 * 5)
+    return keys
+
+
+def _kept_in_order(state, boxes, scores, labels, max_det: int, n_dev=None):
+    """`keep = nms(...)[:max_det]; boxes[keep] ...` (yolo.py:195-196) from the verdicts."""
+    dev = boxes.device
+    n = boxes.shape[0]
+    keys = torch.empty((n,), dtype=torch.int64, device=dev)
+    count = torch.empty((1,), dtype=torch.int32, device=dev)
+    _call("hdy_merge_select", ptr(state), ptr(scores), ptr(n_dev), n, ptr(keys), ptr(count), _stream())
+    k_all = int(count.item())
+    keys = keys[:k_all]
+    sort_keys(keys)
+    k = min(k_all, int(max_det))
+    idx = torch.empty((k,), dtype=torch.int64, device=dev)
+    ob = torch.empty((k, 4), dtype=torch.float32, device=dev)
+    os_ = torch.empty((k,), dtype=torch.float32, device=dev)
+    ol = torch.empty((k,), dtype=torch.int64, device=dev) if labels is not None else None
+    oc = torch.empty((1,), dtype=torch.int32, device=dev)
+    if k:
+        _call("hdy_merge_gather", ptr(keys), ptr(count), k, ptr(boxes), ptr(scores), ptr(labels), ptr(idx), ptr(ob),
+              ptr(os_), ptr(ol), ptr(oc), _stream())
+    return idx, ob, os_, ol
+
+
+# ------------------------------------------------------------------------------------------------ T2 / T3 drop-ins
+def merge_outputs(r: List[Dict[str, torch.Tensor]]) -> Dict[str, torch.Tensor]:
+    """Detect.merge_outputs (yolo_head.py:450-463): one dict per tile with 'boxes' [k,4] (tile coordinates),
+    'labels', 'scores' and 'roi' (x0, y0, ...) -> one dict in slide coordinates, tiles concatenated in order.
+    No NMS.  'masks' are concatenated as they are."""
+    if not len(r):
+        raise HdyError("merge_outputs needs at least one tile")
+    dev = r[0]['boxes'].device
+    _need_cuda(r[0]['boxes'], "boxes")
+    counts_h = [int(t['boxes'].shape[0]) for t in r]
+    bs, md = len(r), max(max(counts_h), 1)
+    n = sum(counts_h)
+    res = {'labels': torch.cat([t['labels'] for t in r]), 'scores': torch.cat([t['scores'] for t in r])}
+    cat = _aligned16(torch.cat([t['boxes'] for t in r]).contiguous())
+    rois = torch.stack([torch.as_tensor(t['roi'], dtype=torch.float32).reshape(-1)[:4].cpu() for t in r]).to(dev)
+    out = torch.empty((n, 4), dtype=torch.float32, device=dev)
+    if n:
+        # one launch per call: every tile is a "batch row" of its own length, addressed through tile_offsets
+        counts = torch.tensor(counts_h, dtype=torch.int32).to(dev)
+        # pad to [bs, md, 4] without a Python loop
+        offs = torch.tensor([0] + counts_h[:-1], dtype=torch.int64).cumsum(0).to(dev)
+        tile_of = torch.repeat_interleave(torch.arange(bs, device=dev), counts.long())
+        slot = torch.arange(n, device=dev) - offs[tile_of]
+        padded = torch.zeros((bs, md, 4), dtype=torch.float32, device=dev)
+        padded[tile_of, slot] = cat
+        cursor = torch.zeros((1,), dtype=torch.int64, device=dev)
+        tile_offsets = torch.empty((bs + 1,), dtype=torch.int64, device=dev)
+        status = torch.zeros((1,), dtype=torch.int32, device=dev)
+        for b0 in range(0, bs, 65535):
+            b1 = min(bs, b0 + 65535)
+            _call("hdy_merge_append", ptr(padded[b0:b1]), None, None, ptr(counts[b0:b1]), ptr(rois[b0:b1]), b1 - b0, md,
+                  b0, 1.0, n, ptr(out), None, None, None, ptr(cursor), ptr(tile_offsets[b0:]), ptr(status), _stream(),
+                  launches=2)
+    res = {'boxes': out, **res}
+    if 'masks' in r[0]:
+        res['masks'] = torch.cat([t['masks'] for t in r])
+    return res
+
+
+def ensemble_merge(x: List[Dict[str, Dict[str, torch.Tensor]]], nms_params: Dict[str, float]):
+    """Ensemble.merge (yolo.py:165-204): per task id, concatenate the members' detections, keep scores >
+    conf_thres, class-agnostic NMS on the final scores, first max_det, gather boxes / scores / labels / masks."""
+    task_ids = set().union(*x)
+    res: Dict[str, Dict[str, torch.Tensor]] = {}
+    conf, iou, max_det = nms_params['conf_thres'], nms_params['iou_thres'], int(nms_params['max_det'])
+    for task_id in task_ids:
+        parts = [r[task_id] for r in x if task_id in r]
+        boxes = torch.cat([p['boxes'] for p in parts])
+        scores = torch.cat([p['scores'] for p in parts])
+        labels = torch.cat([p['labels'] for p in parts])
+        masks = None
+        if any('masks' in p for p in parts):
+            ref = [p['masks'] for p in parts if 'masks' in p][0]
+            masks = torch.cat([p['masks'] if 'masks' in p else torch.zeros(ref.shape[1:]).to(ref.device, ref.dtype)
+                               for p in parts])
+        if scores.dim() != 1:
+            raise HdyError("Ensemble.merge handles single-label outputs (scores [n]); the reference's multi-label "
+                           "merge is unfinished (yolo.py:145)")
+        lab64 = labels.to(torch.int64).contiguous()
+        boxes = _aligned16(boxes.contiguous().float())
+        state = merge_nms(boxes, scores.contiguous(), conf, iou)
+        idx, ob, os_, ol = _kept_in_order(state, boxes, scores.contiguous(), lab64, max_det)
+        out = {'boxes': ob, 'scores': os_, 'labels': ol.to(labels.dtype)}
+        if masks is not None:
+            out['masks'] = masks[idx]
+        res[task_id] = out
+    return res
+
+
+class Ensemble:
+    """The merge half of metayolo.models.yolo.Ensemble (yolo.py:144-204); the member models stay PyTorch."""
+
+    def __init__(self, models=(), nms_params: Dict[str, float] = {}):
+        self.models = list(models)
+        self.nms_params = self.get_nms_params(nms_params)
+
+    def get_nms_params(self, args={}):
+        default_args = {'conf_thres': 0.15, 'iou_thres': 0.45, 'max_det': 300}
+        return {k: float(args.get(k, v)) for k, v in default_args.items()}
+
+    def merge(self, x):
+        return ensemble_merge(x, self.nms_params)
+
+
+# ------------------------------------------------------------------------------------------------ slide pipeline
+class SlideAccumulator:
+    """Slide-level struct-of-arrays store: DetectBatch results are appended in slide coordinates (T2) as the tile
+    batches finish, entirely on the device; ``merge`` then runs T3 once.  Row order == the order
+    ``merge_outputs`` would concatenate the tiles in, so results are identical to the list-of-dicts route."""
+
+    def __init__(self, capacity: int, device, with_labels: bool = True):
+        self.capacity = int(capacity)
+        self.device = torch.device(device)
+        d = self.device
+        self.boxes = torch.empty((self.capacity, 4), dtype=torch.float32, device=d)
+        self.scores = torch.empty((self.capacity,), dtype=torch.float32, device=d)
+        self.labels = torch.empty((self.capacity,), dtype=torch.int64, device=d) if with_labels else None
+        self.tile = torch.empty((self.capacity,), dtype=torch.int32, device=d)
+        self.cursor = torch.zeros((1,), dtype=torch.int64, device=d)
+        self.status = torch.zeros((1,), dtype=torch.int32, device=d)
+        self.tile_offsets: List[torch.Tensor] = []
+        self.rois: List[torch.Tensor] = []
+        self.n_tiles = 0
+
+    def reset(self):
+        self.cursor.zero_()
+        self.status.zero_()
+        self.tile_offsets.clear()
+        self.rois.clear()
+        self.n_tiles = 0
+
+    def append(self, batch: DetectBatch, rois: torch.Tensor, scale: float = 1.0) -> None:
+        """rois [bs, 4] fp32 on the device: the windows (x0, y0, x1, y1) of the batch's tiles."""
+        bs = batch.counts.shape[0]
+        if rois.shape != (bs, 4) or not rois.is_cuda or rois.dtype != torch.float32:
+            raise HdyError("rois must be a CUDA fp32 tensor [bs, 4]")
+        rois = _aligned16(rois.contiguous())
+        offs = torch.empty((bs + 1,), dtype=torch.int64, device=self.device)
+        _call("hdy_merge_append", ptr(batch.boxes), ptr(batch.scores), ptr(batch.labels) if self.labels is not None else None,
+              ptr(batch.counts), ptr(rois), bs, batch.max_det, self.n_tiles, float(scale), self.capacity,
+              ptr(self.boxes), ptr(self.scores), ptr(self.labels), ptr(self.tile), ptr(self.cursor), ptr(offs),
+              ptr(self.status), _stream(), launches=2)
+        self.tile_offsets.append(offs)
+        self.rois.append(rois)
+        self.n_tiles += bs
+
+    def count(self) -> int:
+        """Rows appended so far (synchronises); raises on capacity overflow."""
+        both = torch.cat([self.cursor, self.status.long()]).cpu()
+        if int(both[1]) & _lib.HDY_STATUS_OVERFLOW:
+            raise HdyError(f"slide accumulator overflow: {int(both[0])} rows, capacity {self.capacity}")
+        return int(both[0])
+
+    def verdicts(self, conf_thres: float, iou_thres: float, interior_shortcut: bool = False) -> torch.Tensor:
+        """uint8 state per appended row (asynchronous except for the round-budget check)."""
+        n = self.capacity
+        kw = {}
+        if interior_shortcut:
+            rois = torch.cat(self.rois)
+            margin = torch.zeros((1,), dtype=torch.float32, device=self.device)
+            _call("hdy_merge_overhang", ptr(self.boxes), ptr(self.tile), ptr(rois), ptr(self.cursor), n, ptr(margin),
+                  _stream())
+            kw = dict(tile_id=self.tile, cores=tile_cores(rois).to(self.device), margin=margin)
+        return merge_nms(self.boxes, self.scores, conf_thres, iou_thres, n_dev=self.cursor, **kw)
+
+    def merge(self, conf_thres: float, iou_thres: float, max_det: Optional[int] = None,
+              interior_shortcut: bool = False) -> Dict[str, torch.Tensor]:
+        """Ensemble.merge over everything appended: {'boxes','scores','labels','index'} score-descending;
+        'index' is the row in the concatenated (merge_outputs) order."""
+        n = self.count()
+        state = self.verdicts(conf_thres, iou_thres, interior_shortcut)
+        idx, ob, os_, ol = _kept_in_order(state[:n], self.boxes[:n], self.scores[:n],
+                                          self.labels[:n] if self.labels is not None else None,
+                                          n if max_det is None else max_det)
+        out = {'boxes': ob, 'scores': os_, 'index': idx}
+        if ol is not None:
+            out['labels'] = ol
+        return out

@@ -215,6 +215,88 @@ HDY_API int hdy_process_mask_packed(const float* protos, const float* coef, cons
                                     int mh, int mw, int ih, int iw, int upsample, uint32_t* bits,
                                     int64_t capacity_words, int32_t* status, hdy_stream_t stream);
 
+/* ------------------------------------------------------------- coordinates */
+
+/* C1: scale_coords + clip_coords (utils_general.py:161-190), Detect.rescale_outputs (yolo_head.py:465-471) and the
+ * `.round()` of evaluation.py:109, IN PLACE on rows [n, row_len] whose first four columns are xyxy.  flags:
+ *   1: x -= pad_x, y -= pad_y, then /= gain      2: *= scale      4: clamp x to [0, clip_w], y to [0, clip_h]
+ *   8: round half to even.   Steps run in that order, each a separate fp32 operation. */
+#define HDY_AFFINE_UNPAD 1
+#define HDY_AFFINE_SCALE 2
+#define HDY_AFFINE_CLIP 4
+#define HDY_AFFINE_ROUND 8
+HDY_API int hdy_affine_boxes(float* rows, int64_t n, int row_len, float pad_x, float pad_y, float gain, float scale,
+                             float clip_w, float clip_h, int flags, hdy_stream_t stream);
+
+/* -------------------------------------------------------- whole-slide merge */
+
+#define HDY_STATE_UNKNOWN 0     /* only after HDY_STATUS_ROUNDS: not resolved within the round budget */
+#define HDY_STATE_KEPT 1
+#define HDY_STATE_SUPPRESSED 2
+#define HDY_STATE_DROPPED 3     /* score <= conf_thres */
+
+/* T2: Detect.merge_outputs (yolo_head.py:450-463) [+ rescale_outputs (:465-471) when scale != 1]: the detections
+ * of a batch of tiles (slot d < counts[t] of tile t) are shifted by the tile origin rois[t] = (x0, y0, x1, y1) and
+ * appended, tile by tile in order, to flat slide-level arrays at *cursor (device int64, advanced by the call).
+ *   boxes [bs,max_det,4] f32, scores [bs,max_det] f32, labels [bs,max_det] i64, counts [bs] i32, rois [bs,4] f32
+ *   out_boxes [capacity,4], out_scores/out_labels/out_tile [capacity] (the last three may be NULL)
+ *   tile_offsets [bs+1] i64: first output row of every tile, total in [bs]; out_tile[i] = tile_base + t.
+ * Rows that do not fit set HDY_STATUS_OVERFLOW in *status. */
+HDY_API int hdy_merge_append(const float* boxes, const float* scores, const int64_t* labels, const int32_t* counts,
+                             const float* rois, int bs, int max_det, int tile_base, float scale, int64_t capacity,
+                             float* out_boxes, float* out_scores, int64_t* out_labels, int32_t* out_tile,
+                             int64_t* cursor, int64_t* tile_offsets, int32_t* status, hdy_stream_t stream);
+
+/* Largest distance by which any box sticks out of its own tile (atomic max into *margin, which the caller zeroes).
+ * n_dev (device int64, may be NULL) holds the live row count; n_max bounds it. */
+HDY_API int hdy_merge_overhang(const float* boxes, const int32_t* tile_id, const float* tile_rois,
+                               const int64_t* n_dev, int64_t n_max, float* margin, hdy_stream_t stream);
+
+/* T3: Ensemble.merge (yolo.py:165-204): keep scores > conf_thres, class-agnostic greedy NMS
+ * (torchvision.ops.nms semantics: score-descending, ties by lower index, IoU > iou_thres in fp32) over all n rows.
+ * Sparse and exact: boxes are binned by centre, verdicts are resolved as a fixed point in at most max_rounds
+ * rounds (HDY_STATUS_ROUNDS in *status if the budget was too small; call again with more).
+ *   state [n] u8 receives HDY_STATE_* per row.
+ * Optional shortcut (tile_id, tile_cores [n_tiles,4], margin all non-NULL): a row whose box lies strictly inside
+ * its tile's core shrunk by *margin is KEPT without any pair test.  That is exact only if survivors of the same
+ * tile never exceed iou_thres against each other in slide coordinates; pass NULL for the
+ * unconditional path. */
+HDY_API size_t hdy_merge_workspace_bytes(int64_t n_max);
+HDY_API int hdy_merge_nms(const float* boxes, const float* scores, const int32_t* tile_id, const float* tile_cores,
+                          const float* margin, const int64_t* n_dev, int64_t n_max, float conf_thres,
+                          float iou_thres, int max_rounds, uint8_t* state, int32_t* status, void* workspace,
+                          size_t workspace_bytes, hdy_stream_t stream);
+
+/* The same in steps, for the multi-GPU seam exchange: rows [n_local, n_max) are replicas of detections owned by
+ * other ranks (their verdicts are imported, never computed); gidx (or gidx_base + row) is the row's index in the
+ * slide-wide concatenation, which breaks score ties exactly as the single-device call does.
+ *   build -> { rounds(first_round, n_rounds) -> export_states(sel) -> [all-gather] -> import_states } ... -> finish */
+HDY_API int hdy_merge_build(const float* boxes, const float* scores, const uint32_t* gidx, uint32_t gidx_base,
+                            const int32_t* tile_id, const float* tile_cores, const float* margin,
+                            const int64_t* n_dev, int64_t n_max, int64_t n_local, float conf_thres, float iou_thres,
+                            uint8_t* state, void* workspace, size_t workspace_bytes, hdy_stream_t stream);
+HDY_API int hdy_merge_rounds(void* workspace, int64_t n_max, float iou_thres, int first_round, int n_rounds,
+                             hdy_stream_t stream);
+HDY_API int hdy_merge_export_states(void* workspace, int64_t n_max, const uint8_t* state, const int64_t* sel,
+                                    int64_t m, uint8_t* out, hdy_stream_t stream);
+HDY_API int hdy_merge_import_states(void* workspace, int64_t n_max, int64_t first, const uint8_t* states, int64_t m,
+                                    hdy_stream_t stream);
+HDY_API int hdy_merge_finish(void* workspace, const int64_t* n_dev, int64_t n_max, uint8_t* state, int32_t* status,
+                             hdy_stream_t stream);
+
+/* Survivors in the reference's order (`nms(...)[:max_det]`, yolo.py:195): select writes one 64-bit order key per
+ * KEPT row (unordered) and their number, sort_keys sorts them ascending (== score-descending, ties by lower row),
+ * gather emits the first max_det rows.  hdy_sort_keys is a plain LSD radix sort (8 passes of 8 bits), result in
+ * `keys`, `tmp` is scratch of the same size. */
+HDY_API int hdy_merge_select(const uint8_t* state, const float* scores, const int64_t* n_dev, int64_t n_max,
+                             uint64_t* keys, int32_t* count, hdy_stream_t stream);
+HDY_API size_t hdy_sort_workspace_bytes(int64_t n_max);
+HDY_API int hdy_sort_keys(uint64_t* keys, uint64_t* tmp, const int32_t* n_dev, int64_t n_max, void* workspace,
+                          size_t workspace_bytes, hdy_stream_t stream);
+HDY_API int hdy_merge_gather(const uint64_t* keys, const int32_t* count, int64_t max_det, const float* boxes,
+                             const float* scores, const int64_t* labels, int64_t* out_idx, float* out_boxes,
+                             float* out_scores, int64_t* out_labels, int32_t* out_count, hdy_stream_t stream);
+
 /* Utility: zero n int32 words (keeps the host mirror free of extra torch launches). */
 HDY_API int hdy_zero_i32(int32_t* p, size_t n, hdy_stream_t stream);
 

@@ -1,0 +1,169 @@
+"""GPU parity tests of the tile merge (T2/T3), coordinates (C1) and the radix sort (pytest -m gpu), through the C-ABI,
+against the reference golden (tests/golden/tile_merge.npz) and the oracle port.  Kept sets, order and labels are
+bit-exact; merged boxes are bit-exact (one fp32 addition per coordinate)."""
+import numpy as np
+import pytest
+import torch
+
+from conftest import load_golden, unpack_list
+import hd_yolo_b200 as hdy
+from hd_yolo_b200 import slide as hs
+from hd_yolo_b200.ops import DetectBatch
+from oracle import nms_c, port
+
+pytestmark = pytest.mark.gpu
+
+
+def _to(d, dev):
+    return {k: (v.to(dev) if isinstance(v, torch.Tensor) and k != 'roi' else v) for k, v in d.items()}
+
+
+def test_merge_outputs_and_ensemble_vs_reference_golden(cuda_device):
+    g = load_golden("tile_merge")
+    rois = torch.from_numpy(g["rois"])
+    tiles = unpack_list(g, "tile", ["boxes", "scores", "labels"])
+    for t, r in zip(tiles, rois):
+        t["roi"] = r
+    merged = hs.merge_outputs([_to(t, cuda_device) for t in tiles])
+    for k in ("boxes", "scores", "labels"):
+        assert torch.equal(merged[k].cpu(), torch.from_numpy(g["merged_" + k])), k
+    conf, iou, md = g["params"].tolist()
+    ens = hs.Ensemble([], nms_params={'conf_thres': conf, 'iou_thres': iou, 'max_det': md})
+    final = ens.merge([{'det': merged}])['det']
+    for k in ("boxes", "scores", "labels"):
+        assert torch.equal(final[k].cpu(), torch.from_numpy(g["final_" + k])), k
+    assert final['labels'].dtype == torch.int64
+    # max_det cap keeps the best-scored prefix
+    ens2 = hs.Ensemble([], nms_params={'conf_thres': conf, 'iou_thres': iou, 'max_det': 37})
+    f2 = ens2.merge([{'det': merged}])['det']
+    assert torch.equal(f2['boxes'].cpu(), torch.from_numpy(g["final_boxes"])[:37])
+
+
+def _synthetic_slide(seed, H, W, roi, overlap, n_nuclei, jitter=1.0, coord_offset=0.0):
+    """Per-tile detection lists from a global nuclei field: neighbouring tiles re-detect the nuclei in their overlap
+    band with <= jitter px box noise and their own scores (SURVEY 8d cfg 4)."""
+    g = torch.Generator().manual_seed(seed)
+    rois = hs.sliding_window_scanner((H, W), (roi, roi), overlap)
+    nuc = torch.rand((n_nuclei, 2), generator=g) * torch.tensor([W, H], dtype=torch.float32)
+    size = torch.rand((n_nuclei, 2), generator=g) * 24 + 12
+    tiles = []
+    for r in rois:
+        x0, y0, x1, y1 = r.tolist()
+        inside = (nuc[:, 0] > x0 + 2) & (nuc[:, 0] < x1 - 2) & (nuc[:, 1] > y0 + 2) & (nuc[:, 1] < y1 - 2)
+        k = int(inside.sum())
+        c = nuc[inside] - torch.tensor([x0, y0]) + (torch.rand((k, 2), generator=g) - 0.5) * jitter
+        s = size[inside] + (torch.rand((k, 2), generator=g) - 0.5) * jitter
+        boxes = torch.cat([c - s / 2, c + s / 2], 1)
+        scores = ((torch.rand(k, generator=g) * 0.85 + 0.1) * 256).round() / 256     # ties across tiles
+        labels = torch.randint(1, 5, (k,), generator=g)
+        roi_shift = r + coord_offset
+        tiles.append({'boxes': boxes, 'scores': scores, 'labels': labels, 'roi': roi_shift})
+    return rois, tiles
+
+
+def _as_batch(tiles, dev):
+    bs, md = len(tiles), max(max(len(t['boxes']) for t in tiles), 1)
+    boxes = torch.zeros((bs, md, 4))
+    scores = torch.zeros((bs, md))
+    labels = torch.zeros((bs, md), dtype=torch.int64)
+    counts = torch.zeros((bs,), dtype=torch.int32)
+    for i, t in enumerate(tiles):
+        k = len(t['boxes'])
+        boxes[i, :k], scores[i, :k], labels[i, :k], counts[i] = t['boxes'], t['scores'], t['labels'], k
+    z = torch.zeros((bs, md), device=dev)
+    return DetectBatch(boxes.to(dev), None, scores.to(dev), labels.to(dev), z, None, z.int(), counts.to(dev),
+                       torch.zeros(bs + 1, dtype=torch.int32, device=dev), md)
+
+
+@pytest.mark.parametrize("seed,H,W,roi,overlap,n,off", [(1, 900, 1300, 256, 64, 2500, 0.0), (2, 2000, 2000, 512, 64, 9000, 0.0),
+                                                        (3, 1500, 1100, 256, 32, 4000, 98304.0), (4, 600, 600, 1024, 64, 500, 0.0)])
+def test_slide_accumulator_vs_oracle(cuda_device, seed, H, W, roi, overlap, n, off):
+    rois, tiles = _synthetic_slide(seed, H, W, roi, overlap, n, coord_offset=off)
+    params = {'conf_thres': 0.2, 'iou_thres': 0.45, 'max_det': 10 ** 9}
+    ref_m = port.merge_outputs(tiles)
+    ref = port.ensemble_merge([{'det': ref_m}], params)['det']
+    acc = hs.SlideAccumulator(capacity=sum(len(t['boxes']) for t in tiles) + 100, device=cuda_device)
+    half = max(1, len(tiles) // 2)
+    for chunk in (tiles[:half], tiles[half:]):           # two batches: offsets carry over on the device
+        if chunk:
+            acc.append(_as_batch(chunk, cuda_device), torch.stack([t['roi'] for t in chunk]).to(cuda_device))
+    assert acc.count() == len(ref_m['boxes'])
+    n_rows = acc.count()
+    assert torch.equal(acc.boxes[:n_rows].cpu(), ref_m['boxes'])
+    out = acc.merge(0.2, 0.45)
+    assert len(ref['boxes']) < n_rows
+    assert torch.equal(out['boxes'].cpu(), ref['boxes'])
+    assert torch.equal(out['scores'].cpu(), ref['scores'])
+    assert torch.equal(out['labels'].cpu(), ref['labels'])
+    # 'index' addresses the concatenated order
+    assert torch.equal(ref_m['boxes'][out['index'].cpu()], ref['boxes'])
+    # the interior shortcut gives the same verdicts whenever no same-tile pair crosses the threshold
+    st_full = acc.verdicts(0.2, 0.45)[:n_rows]
+    st_fast = acc.verdicts(0.2, 0.45, interior_shortcut=True)[:n_rows]
+    same_tile_clean = True
+    for t in tiles:   # survivors of one tile must already be mutually <= thr for the shortcut's premise
+        b = t['boxes'] + torch.cat([t['roi'][:2], t['roi'][:2]])
+        keep = t['scores'] > 0.2
+        if int(keep.sum()) != len(port.nms(b[keep], t['scores'][keep], 0.45)):
+            same_tile_clean = False
+    if same_tile_clean:
+        assert torch.equal(st_full, st_fast)
+
+
+def test_merge_nms_random_dense_vs_oracle(cuda_device):
+    g = torch.Generator().manual_seed(5)
+    for n, span, lo, hi in [(1, 10, 4, 8), (5000, 700, 8, 40), (40000, 3000, 10, 36), (3000, 200, 5, 300)]:
+        c = torch.rand((n, 2), generator=g) * span
+        wh = torch.rand((n, 2), generator=g) * (hi - lo) + lo
+        b = torch.cat([c - wh / 2, c + wh / 2], 1)
+        s = (torch.rand(n, generator=g) * 500).round() / 500
+        keep_ref = nms_c.nms(b[s > 0.1].numpy(), s[s > 0.1].numpy(), 0.45)
+        idx_ref = torch.nonzero(s > 0.1)[:, 0][torch.from_numpy(keep_ref)]
+        st = hs.merge_nms(b.to(cuda_device), s.to(cuda_device), 0.1, 0.45).cpu()
+        assert set(torch.nonzero(st == hs.STATE_KEPT)[:, 0].tolist()) == set(idx_ref.tolist())
+        assert bool(((st == hs.STATE_DROPPED) == (s <= np.float32(0.1))).all())
+        assert not bool((st == 0).any())
+
+
+def test_merge_empty_and_all_dropped(cuda_device):
+    assert hs.merge_nms(torch.zeros((0, 4), device=cuda_device), torch.zeros(0, device=cuda_device), 0.2, 0.45).numel() == 0
+    b = torch.tensor([[0., 0., 10., 10.], [1., 1., 11., 11.]], device=cuda_device)
+    s = torch.tensor([0.1, 0.15], device=cuda_device)
+    assert hs.merge_nms(b, s, 0.2, 0.45).tolist() == [3, 3]
+    out = hs.ensemble_merge([{'t': {'boxes': b, 'scores': s, 'labels': torch.tensor([1, 2], device=cuda_device)}}],
+                            {'conf_thres': 0.2, 'iou_thres': 0.45, 'max_det': 10})['t']
+    assert out['boxes'].shape == (0, 4) and out['labels'].shape == (0,)
+
+
+@pytest.mark.parametrize("n", [1, 31, 1024, 1025, 50000, 1 << 20])
+def test_radix_sort(cuda_device, n):
+    g = torch.Generator().manual_seed(n)
+    k = torch.randint(-2 ** 62, 2 ** 62, (n,), generator=g, dtype=torch.int64)
+    k[::7] = k[0]                                           # duplicates
+    out = hs.sort_keys(k.to(cuda_device).clone()).cpu()
+    as_u = lambda t: t.numpy().view(np.uint64)
+    assert np.array_equal(as_u(out), np.sort(as_u(k)))
+
+
+def test_scale_clip_rescale_vs_oracle(cuda_device):
+    g = torch.Generator().manual_seed(8)
+    coords = torch.rand((500, 6), generator=g) * 700 - 30
+    for img1, img0, rp in [((640, 640), (480, 720), None), (640, (1000, 1000), None), ((384, 640), (1080, 1920), None),
+                           ((640, 640), (480, 720), ((0.8, 0.8), (13.0, 40.0)))]:
+        ref = port.scale_coords(img1, coords.clone(), img0, rp)
+        out = coords.clone().to(cuda_device)
+        ret = hs.scale_coords(img1, out, img0, rp)
+        assert ret is out and torch.equal(out.cpu(), ref)
+        assert torch.equal(hs.scale_coords(img1, coords.clone().to(cuda_device), img0, rp, round_=True).cpu()[:, :4], ref[:, :4].round())
+    b = coords[:, :4].clone()
+    port.clip_coords(b, (300, 500))
+    o = coords[:, :4].clone().to(cuda_device)
+    hs.clip_coords(o, (300, 500))
+    assert torch.equal(o.cpu(), b)
+    r = {'boxes': coords[:, :4].clone().to(cuda_device)}
+    assert hs.rescale_outputs(r, 4.0) is r
+    assert torch.equal(r['boxes'].cpu(), port.rescale_outputs({'boxes': coords[:, :4].clone()}, 4.0)['boxes'])
+    # a column view of a wider tensor is modified in place (callers rely on it)
+    wide = coords.clone().to(cuda_device)
+    hs.clip_coords(wide[:, :4], (300, 500))
+    assert torch.equal(wide[:, :4].cpu(), b) and torch.equal(wide[:, 4:].cpu(), coords[:, 4:])
