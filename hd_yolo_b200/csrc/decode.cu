@@ -447,6 +447,11 @@ int hdy_filter_compact_logits(const hdy_level_t* levels_host, int nl, int bs, in
   if (rc) return rc;
   T.nc = nc;
   if (bs == 0) return HDY_OK;
+  if (layout == 0) {  // TMA-staged persistent kernel whenever the chunks are 16-byte aligned
+    rc = launch_filter_compact_tma(levels_host, nl, bs, na, nc, no, conf_thres, min_size, cap, cand_keys, cand_boxes,
+                                   counts, status, (cudaStream_t)stream);
+    if (rc != 1) return rc;
+  }
   const size_t smem = layout == 0 ? stage_smem_bytes(no) : 0;
   rc = ensure_smem(filter_compact_logits_kernel, smem);
   if (rc) return rc;

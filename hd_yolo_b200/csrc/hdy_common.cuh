@@ -92,6 +92,19 @@ struct LevelTable {
   int nl, na, no, nc, N, chunks_per_tile, layout;
 };
 
+// nms_smem.cu: one CTA per tile, tiles with at most 4096 candidates (others return at once)
+constexpr int kNmsSmemCap = 4096;
+int launch_nms_tiles_smem(const uint64_t* cand_keys, const float4* cand_boxes, const float* cand_cls,
+                          const int32_t* counts, int bs, int cap, float thr, float class_offset, int max_nms,
+                          int max_det, int32_t* keep_idx, int32_t* keep_slot, float4* keep_box, float* keep_score,
+                          float* keep_cls, int32_t* keep_counts, unsigned long long* phase_cycles,
+                          cudaStream_t stream);
+
+// filter_tma.cu: returns 1 when the layout does not meet the bulk-copy alignment rules (use the generic kernel)
+int launch_filter_compact_tma(const hdy_level_t* levels_host, int nl, int bs, int na, int nc, int no, float conf_thres,
+                              float min_size, int cap, uint64_t* cand_keys, float* cand_boxes, int32_t* counts,
+                              int32_t* status, cudaStream_t stream);
+
 int build_level_table(const hdy_level_t* levels_host, int nl, int na, int no, int layout, int rows_per_chunk,
                       LevelTable* out);
 

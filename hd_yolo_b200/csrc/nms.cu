@@ -33,6 +33,7 @@ enum : uint8_t { ST_UNKNOWN = 0, ST_KEPT = 1, ST_SUPPRESSED = 2 };
 // Optional phase profile (hdy_debug_nms_phases): cycles summed over CTAs for
 // 0 load, 1 sort, 2 gather boxes, 3 binning, 4 rounds, 5 output, 6 #rounds, 7 #CTAs
 __device__ unsigned long long* g_phase_cycles = nullptr;
+static unsigned long long* g_phase_host = nullptr;  // same pointer, for kernels that take it as a parameter
 struct PhaseClock {
   unsigned long long* buf;
   long long t0;
@@ -358,12 +359,14 @@ __global__ void __launch_bounds__(kNmsThreads, 2) nms_tiles_kernel(
     const float* __restrict__ cand_cls, const int32_t* __restrict__ counts, int cap, float thr,
     float class_offset, int max_nms, int max_det, int32_t* __restrict__ keep_idx,
     int32_t* __restrict__ keep_slot, float4* __restrict__ keep_box, float* __restrict__ keep_score,
-    float* __restrict__ keep_cls, int32_t* __restrict__ keep_counts, unsigned char* __restrict__ workspace) {
+    float* __restrict__ keep_cls, int32_t* __restrict__ keep_counts, unsigned char* __restrict__ workspace,
+    int min_n) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   __shared__ int warp_tmp[kNmsThreads / 32 + 1];
   __shared__ float red_tmp[kNmsThreads / 32];
   const int tile = blockIdx.x;
   const int n = min(counts[tile], cap);
+  if (n <= min_n) return;  // done by nms_tiles_smem_kernel
   TileOut out;
   out.keep_idx = keep_idx + (size_t)tile * max_det;
   out.keep_slot = keep_slot + (size_t)tile * max_det;
@@ -496,6 +499,7 @@ extern "C" {
 
 int hdy_debug_nms_phases(uint64_t* device_buf8) {
   unsigned long long* p = reinterpret_cast<unsigned long long*>(device_buf8);
+  g_phase_host = p;
   cudaError_t e = cudaMemcpyToSymbol(g_phase_cycles, &p, sizeof(p));
   if (e != cudaSuccess) {
     set_error("hdy_debug_nms_phases: %s", cudaGetErrorString(e));
@@ -526,6 +530,12 @@ int hdy_nms_tiles(const uint64_t* cand_keys, const float* cand_boxes, const floa
     set_error("hdy_nms_tiles: workspace too small (%zu < %zu)", workspace_bytes, need);
     return HDY_ERR_CAPACITY;
   }
+  // tiles with at most 4096 candidates: shared-memory kernel (nms_smem.cu); the rest: workspace kernel below
+  int rc = launch_nms_tiles_smem(cand_keys, reinterpret_cast<const float4*>(cand_boxes), cand_cls, counts, bs, cap,
+                                 iou_thres, class_offset, max_nms, max_det, keep_idx, keep_slot,
+                                 reinterpret_cast<float4*>(keep_box), keep_score, keep_cls, keep_counts,
+                                 g_phase_host, (cudaStream_t)stream);
+  if (rc || cap <= kNmsSmemCap) return rc;
   static bool attr_set = false;
   if (!attr_set) {
     cudaError_t e = cudaFuncSetAttribute(nms_tiles_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
@@ -539,7 +549,7 @@ int hdy_nms_tiles(const uint64_t* cand_keys, const float* cand_boxes, const floa
   nms_tiles_kernel<<<(unsigned)bs, kNmsThreads, kSmemBytes, (cudaStream_t)stream>>>(
       cand_keys, reinterpret_cast<const float4*>(cand_boxes), cand_cls, counts, cap, iou_thres, class_offset,
       max_nms, max_det, keep_idx, keep_slot, reinterpret_cast<float4*>(keep_box), keep_score, keep_cls,
-      keep_counts, static_cast<unsigned char*>(workspace));
+      keep_counts, static_cast<unsigned char*>(workspace), kNmsSmemCap);
   return check_launch("hdy_nms_tiles");
 }
 

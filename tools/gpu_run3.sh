@@ -1,0 +1,5 @@
+python -m pytest tests -m gpu -q -x --timeout 900 2>&1 | tail -15
+python tools/nms_phases.py 640 64 1000 1000 2048
+python tools/nms_phases.py 1024 128 3000 3000 4096
+python bench.py --workload tiles1024 --steps 100 --warmup 5 --no-cpu-baseline --no-e2e | python -c "import sys,json; d=json.loads(sys.stdin.read()); print(d['value'], d['ms_per_step'], d['pipeline']['stage_ms'])"
+python bench.py --workload tiles640 --steps 100 --warmup 5 --no-cpu-baseline --no-e2e | python -c "import sys,json; d=json.loads(sys.stdin.read()); print(d['value'], d['ms_per_step'], d['pipeline']['stage_ms'])"

@@ -21,8 +21,8 @@ torch.cuda.synchronize()
 _lib.check(lib.hdy_debug_nms_phases(None))
 b = buf.tolist()
 ctas = max(b[7], 1)
-names = ["load", "sort", "gather", "binning", "rounds", "output"]
+names = {1: "sort", 3: "binning", 4: "pairs", 5: "resolve", 6: "emit"}
 print(f"tile={tile} bs={bs} cand/tile={float(out.cand_counts[:bs].float().mean()):.0f} kept={float(out.counts.float().mean()):.0f}")
-for i, nm in enumerate(names):
+for i, nm in names.items():
     print(f"  {nm:8s} {b[i] / ctas:10.0f} cycles/CTA")
-print(f"  rounds/CTA {b[6] / ctas:.2f}   total {sum(b[:6]) / ctas:.0f} cycles/CTA")
+print(f"  sweeps/CTA {b[0] / ctas:.2f}   total {sum(b[1:7]) / ctas:.0f} cycles/CTA")
