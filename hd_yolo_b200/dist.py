@@ -1,0 +1,286 @@
+"""Whole-slide merge sharded over ranks (one process per GPU, torch.distributed / NCCL for the plumbing).
+
+Reference semantics: ``Ensemble.merge`` (metayolo/models/yolo.py:165-204) applied to the ``Detect.merge_outputs``
+(metayolo/models/yolo_head.py:450-463) concatenation of ALL tiles of the slide, tiles in ``sliding_window_scanner``
+order (hnet/utils.py:37-62).  The reference runs this on one device; here every rank owns a contiguous range of tiles
+(bands of tile rows), so the slide-wide concatenation is rank 0's rows, then rank 1's, ...
+
+Only detections near a band boundary can interact across ranks.  The exchange is:
+
+  1. all-gather of each rank's detection bounding rectangle (4 floats);
+  2. a rank's SEAM rows = rows whose box intersects another rank's rectangle; one padded all-gather of
+     (box, score, global index) of the seam rows -- ~1 % of the slide, a few MB;
+  3. every rank builds the sparse merge structure (csrc/merge.cu) over its own rows + the other ranks' seam rows
+     ("replicas": they take part in every IoU test, but their verdicts are never computed locally);
+  4. loop: a few fixed-point rounds locally -> export the verdicts of the own seam rows -> all-gather (1 byte per seam
+     row) -> import them into the replica slots; stop when no seam row is undecided anywhere;
+  5. finish: remaining local rounds, verdict per own row.
+
+The result is bit-identical to the single-device merge (and hence to torchvision's dense NMS): a row's verdict depends
+only on higher-ranked rows its box intersects, all of which are local rows or replicas, and rank order uses the global
+index for ties.  No kernel waits on another rank; collectives are ordinary NCCL calls between kernel launches.
+
+``ShardedMerge`` is written as explicit phases so that the same code runs (a) under torch.distributed
+(``merge_sharded``), (b) as W emulated ranks inside one process on one GPU (``merge_emulated``; used by the GPU tests),
+and (c) on CPU tensors with a stand-in backend (the gloo tests of the host logic).
+"""
+from __future__ import annotations
+
+from typing import Callable, Dict, List, Optional, Sequence, Tuple
+
+import torch
+
+STATE_UNKNOWN, STATE_KEPT, STATE_SUPPRESSED, STATE_DROPPED, STATE_REMOTE_UNKNOWN = 0, 1, 2, 3, 4
+ROUNDS_PER_EXCHANGE = 4
+MAX_ROUNDS = 64
+
+__all__ = ["shard_tile_rows", "ShardedMerge", "merge_sharded", "merge_emulated", "DeviceMergeBackend"]
+
+
+# ------------------------------------------------------------------------------------------------ tile sharding
+def shard_tile_rows(rois: torch.Tensor, world: int) -> List[Tuple[int, int]]:
+    """Split the scanner's tiles (row-major, x fastest) into `world` contiguous bands of whole tile rows, as even as
+    possible.  Returns [(first_tile, last_tile_exclusive)] per rank; ranks beyond the number of tile rows get empty
+    ranges."""
+    n = int(rois.shape[0])
+    if n == 0:
+        return [(0, 0)] * world
+    y0 = rois[:, 1].cpu()
+    row_start = torch.nonzero(torch.cat([torch.ones(1, dtype=torch.bool), y0[1:] != y0[:-1]])).flatten().tolist()
+    row_start.append(n)
+    n_rows = len(row_start) - 1
+    out = []
+    for r in range(world):
+        a = (n_rows * r) // world
+        b = (n_rows * (r + 1)) // world
+        out.append((row_start[a], row_start[b]))
+    return out
+
+
+# ------------------------------------------------------------------------------------------------ device backend
+class DeviceMergeBackend:
+    """The C-ABI merge steps (hdy_merge_build / rounds / export_states / import_states / finish) over one rank's rows.
+    boxes [n,4] fp32, scores [n] fp32, gidx [n] int32 (global index, bit pattern of a uint32); rows >= n_local are
+    replicas."""
+
+    def __init__(self, boxes, scores, gidx, n_local: int, conf_thres: float, iou_thres: float):
+        import ctypes as C
+
+        from . import _lib
+        from .ops import _Scratch, _call, _conf_thr_f32, _iou_thr_f32, _need_cuda, _stream
+        from ._lib import ptr
+
+        _need_cuda(boxes, "boxes")
+        self._call, self._ptr, self._stream = _call, ptr, _stream
+        self.n = int(boxes.shape[0])
+        self.n_local = int(n_local)
+        dev = boxes.device
+        self.boxes = boxes.contiguous()
+        if self.boxes.data_ptr() % 16:
+            self.boxes = self.boxes.clone()
+        self.scores = scores.contiguous()
+        self.gidx = gidx.contiguous()
+        self.iou = _iou_thr_f32(iou_thres)
+        self.state = torch.empty((max(self.n, 1),), dtype=torch.uint8, device=dev)
+        self.status = torch.zeros((1,), dtype=torch.int32, device=dev)
+        lib = _lib.load()
+        self.wbytes = lib.hdy_merge_workspace_bytes(max(self.n, 1))
+        self.ws = torch.empty((self.wbytes,), dtype=torch.uint8, device=dev)
+        _call("hdy_merge_build", ptr(self.boxes), ptr(self.scores), ptr(self.gidx), 0, None, None, None, None, self.n,
+              self.n_local, _conf_thr_f32(conf_thres), self.iou, ptr(self.state), ptr(self.ws), self.wbytes, _stream(),
+              launches=7)
+
+    def rounds(self, first: int, n: int) -> None:
+        self._call("hdy_merge_rounds", self._ptr(self.ws), self.n, self.iou, first, n, self._stream(), launches=n)
+
+    def export_states(self, sel: torch.Tensor) -> torch.Tensor:
+        out = torch.empty((sel.numel(),), dtype=torch.uint8, device=sel.device)
+        if sel.numel():
+            self._call("hdy_merge_export_states", self._ptr(self.ws), self.n, self._ptr(self.state), self._ptr(sel),
+                       sel.numel(), self._ptr(out), self._stream())
+        return out
+
+    def import_states(self, first: int, states: torch.Tensor) -> None:
+        if states.numel():
+            states = states.contiguous()
+            self._call("hdy_merge_import_states", self._ptr(self.ws), self.n, first, self._ptr(states), states.numel(),
+                       self._stream())
+
+    def finish(self) -> Tuple[torch.Tensor, bool]:
+        """-> (verdict per own row [n_local] uint8, converged)"""
+        self._call("hdy_merge_finish", self._ptr(self.ws), None, self.n, self._ptr(self.state), self._ptr(self.status),
+                   self._stream())
+        ok = not (int(self.status.item()) & 2)
+        return self.state[:self.n_local], ok
+
+
+# ------------------------------------------------------------------------------------------------ the protocol
+class ShardedMerge:
+    """One rank's side of the sharded Ensemble.merge.  Call the phases in order; what goes between them is a
+    collective over all ranks (see merge_sharded / merge_emulated)."""
+
+    def __init__(self, rank: int, world: int, boxes: torch.Tensor, scores: torch.Tensor, conf_thres: float,
+                 iou_thres: float, backend: Callable = DeviceMergeBackend):
+        self.rank, self.world = rank, world
+        self.boxes, self.scores = boxes, scores
+        self.conf, self.iou = conf_thres, iou_thres
+        self.n_local = int(boxes.shape[0])
+        self.backend_cls = backend
+        self.backend = None
+        self.round = 0
+
+    # phase 1 ------------------------------------------------------------------------------------
+    def local_summary(self) -> torch.Tensor:
+        """[4] fp32: bounding rectangle of the own detections (x1, y1, x2, y2; inverted if there are none)."""
+        b = self.boxes
+        if self.n_local == 0:
+            big = 3.0e38
+            return torch.tensor([big, big, -big, -big], dtype=torch.float32, device=b.device)
+        return torch.cat([b[:, :2].min(0).values, b[:, 2:].max(0).values])
+
+    # phase 2 ------------------------------------------------------------------------------------
+    def select_seam(self, summaries: torch.Tensor, counts: Sequence[int]) -> torch.Tensor:
+        """summaries [world, 4] (all-gathered), counts: rows per rank.  Returns the padded-to-be seam payload
+        [m, 6] int32 = (box bits x4, score bits, global index) of the own seam rows."""
+        self.counts = [int(c) for c in counts]
+        self.base = sum(self.counts[:self.rank])
+        if sum(self.counts) >= 2 ** 32:
+            raise ValueError("more than 2^32 detections in one slide")
+        b, dev = self.boxes, self.boxes.device
+        mask = torch.zeros((self.n_local,), dtype=torch.bool, device=dev)
+        for r in range(self.world):
+            if r == self.rank or self.counts[r] == 0:
+                continue
+            x1, y1, x2, y2 = [float(v) for v in summaries[r, :4]]
+            # closed-interval test: a superset of "boxes intersect", which is all exactness needs
+            mask |= (b[:, 2] >= x1) & (b[:, 0] <= x2) & (b[:, 3] >= y1) & (b[:, 1] <= y2)
+        self.sel = torch.nonzero(mask).flatten()                      # int64 rows, ascending
+        m = int(self.sel.numel())
+        pay = torch.empty((m, 6), dtype=torch.int32, device=dev)
+        if m:
+            pay[:, :4] = b[self.sel].contiguous().view(torch.int32)
+            pay[:, 4] = self.scores[self.sel].contiguous().view(torch.int32)
+            g = self.sel + self.base                                   # < 2^32: keep the low 32 bits' pattern
+            pay[:, 5] = torch.where(g >= 2 ** 31, g - 2 ** 32, g).to(torch.int32)
+        return pay
+
+    # phase 3 ------------------------------------------------------------------------------------
+    def build(self, payloads: Sequence[torch.Tensor]) -> None:
+        """payloads[r] = rank r's seam payload [m_r, 6] int32 (own entry ignored)."""
+        dev = self.boxes.device
+        others = [payloads[r] for r in range(self.world) if r != self.rank and payloads[r].numel()]
+        self.seam_sizes = [int(p.shape[0]) for p in payloads]
+        rep = torch.cat(others) if others else torch.empty((0, 6), dtype=torch.int32, device=dev)
+        self.n_rep = int(rep.shape[0])
+        n = self.n_local + self.n_rep
+        boxes = torch.empty((max(n, 1), 4), dtype=torch.float32, device=dev)
+        scores = torch.empty((max(n, 1),), dtype=torch.float32, device=dev)
+        gidx = torch.empty((max(n, 1),), dtype=torch.int32, device=dev)
+        boxes[:self.n_local] = self.boxes
+        scores[:self.n_local] = self.scores
+        g = torch.arange(self.n_local, device=dev, dtype=torch.int64) + self.base
+        gidx[:self.n_local] = torch.where(g >= 2 ** 31, g - 2 ** 32, g).to(torch.int32)
+        if self.n_rep:
+            boxes[self.n_local:n] = rep[:, :4].contiguous().view(torch.float32)
+            scores[self.n_local:n] = rep[:, 4].contiguous().view(torch.float32)
+            gidx[self.n_local:n] = rep[:, 5]
+        self.backend = self.backend_cls(boxes[:n], scores[:n], gidx[:n], self.n_local, self.conf, self.iou)
+        self.round = 0
+
+    # phase 4 (repeated) -------------------------------------------------------------------------
+    def step_rounds(self) -> torch.Tensor:
+        """Runs a few local rounds; returns the verdicts of the own seam rows [m] uint8."""
+        n = min(ROUNDS_PER_EXCHANGE, MAX_ROUNDS - self.round)
+        if n <= 0:
+            raise RuntimeError("sharded merge did not converge within the round budget")
+        self.backend.rounds(self.round, n)
+        self.round += n
+        return self.backend.export_states(self.sel)
+
+    def step_import(self, states: Sequence[torch.Tensor]) -> bool:
+        """states[r] = rank r's seam verdicts [m_r].  Returns True when no seam row is undecided anywhere."""
+        others = [states[r] for r in range(self.world) if r != self.rank and states[r].numel()]
+        if others:
+            self.backend.import_states(self.n_local, torch.cat(others))
+        allst = torch.cat([s for s in states if s.numel()]) if any(s.numel() for s in states) else None
+        if allst is None:
+            return True
+        return not bool(((allst == STATE_UNKNOWN) | (allst == STATE_REMOTE_UNKNOWN)).any())
+
+    # phase 5 ------------------------------------------------------------------------------------
+    def finish(self) -> torch.Tensor:
+        left = MAX_ROUNDS - self.round
+        if left > 0:
+            self.backend.rounds(self.round, left)     # rounds exit at once when nothing is undecided
+            self.round = MAX_ROUNDS
+        state, ok = self.backend.finish()
+        if not ok:
+            raise RuntimeError("sharded merge: undecided rows left after the round budget")
+        return state
+
+
+# ------------------------------------------------------------------------------------------------ drivers
+def _pad_gather(t: torch.Tensor, sizes: Sequence[int], group) -> List[torch.Tensor]:
+    """all_gather of per-rank tensors whose first dimension differs (sizes known to every rank)."""
+    import torch.distributed as dist
+
+    world = len(sizes)
+    mx = max(max(sizes), 1)
+    buf = torch.zeros((mx,) + tuple(t.shape[1:]), dtype=t.dtype, device=t.device)
+    buf[:t.shape[0]] = t
+    out = [torch.empty_like(buf) for _ in range(world)]
+    dist.all_gather(out, buf, group=group)
+    return [o[:s] for o, s in zip(out, sizes)]
+
+
+def merge_sharded(boxes: torch.Tensor, scores: torch.Tensor, conf_thres: float, iou_thres: float, group=None,
+                  backend: Callable = DeviceMergeBackend) -> Dict[str, torch.Tensor]:
+    """Sharded Ensemble.merge verdicts under torch.distributed.  boxes [n_local, 4] / scores [n_local] are this rank's
+    rows of the slide-wide concatenation (rank order == tile order).  Returns {'state': uint8 [n_local],
+    'base': first global row of this rank, 'exchanges': number of verdict all-gathers, 'seam_rows': [world]}."""
+    import torch.distributed as dist
+
+    rank, world = dist.get_rank(group), dist.get_world_size(group)
+    sm = ShardedMerge(rank, world, boxes, scores, conf_thres, iou_thres, backend)
+    dev = boxes.device
+    # 1. rectangles + row counts
+    summ = [torch.empty((4,), dtype=torch.float32, device=dev) for _ in range(world)]
+    dist.all_gather(summ, sm.local_summary(), group=group)
+    cnt = [torch.empty((1,), dtype=torch.int64, device=dev) for _ in range(world)]
+    dist.all_gather(cnt, torch.tensor([sm.n_local], dtype=torch.int64, device=dev), group=group)
+    counts = [int(c) for c in torch.cat(cnt).tolist()]
+    # 2. seam payloads
+    pay = sm.select_seam(torch.stack(summ).cpu(), counts)
+    msz = [torch.empty((1,), dtype=torch.int64, device=dev) for _ in range(world)]
+    dist.all_gather(msz, torch.tensor([pay.shape[0]], dtype=torch.int64, device=dev), group=group)
+    sizes = [int(c) for c in torch.cat(msz).tolist()]
+    pays = _pad_gather(pay, sizes, group)
+    # 3. build, 4. rounds <-> verdict exchange
+    sm.build(pays)
+    exchanges = 0
+    while True:
+        st = sm.step_rounds()
+        sts = _pad_gather(st, sizes, group)
+        exchanges += 1
+        if sm.step_import(sts):
+            break
+    return {'state': sm.finish(), 'base': sm.base, 'exchanges': exchanges, 'seam_rows': sizes}
+
+
+def merge_emulated(parts: Sequence[Tuple[torch.Tensor, torch.Tensor]], conf_thres: float, iou_thres: float,
+                   backend: Callable = DeviceMergeBackend) -> List[torch.Tensor]:
+    """The same protocol with `len(parts)` ranks emulated inside one process (collectives become list passing).
+    parts[r] = (boxes, scores) of rank r.  Returns the verdicts per rank."""
+    world = len(parts)
+    sms = [ShardedMerge(r, world, b, s, conf_thres, iou_thres, backend) for r, (b, s) in enumerate(parts)]
+    summ = torch.stack([sm.local_summary().cpu() for sm in sms])
+    counts = [sm.n_local for sm in sms]
+    pays = [sm.select_seam(summ, counts) for sm in sms]
+    for sm in sms:
+        sm.build(pays)
+    while True:
+        sts = [sm.step_rounds() for sm in sms]
+        done = [sm.step_import(sts) for sm in sms]
+        if all(done):
+            break
+    return [sm.finish() for sm in sms]
