@@ -1,16 +1,25 @@
 #!/usr/bin/env python
 """Benchmark of the post-processing hot path (BASELINE.json metric: post-proc tiles/s & boxes/s).
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--workload tiles640|tiles1024]
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--workload tiles640|tiles1024|slide] [--masks proto|none]
     python bench.py --impl reference ...      # the reference's CPU path (oracle port) on host cores
 
-One "step" = one pass of the hot path (fused decode+filter+compact -> per-tile NMS -> score/label
-select) over one batch of synthetic head outputs.  Prints ONE JSON line on rank 0.
+tiles640 / tiles1024 (BASELINE.json configs[1] / configs[2]): one "step" = one pass of the hot path over one batch of
+synthetic head outputs: fused decode+filter+compact -> per-tile NMS -> score/label select -> proto masks
+(32-prototype contraction, sigmoid, crop, bilinear upsample, threshold, bit-packed).  Weak scaling over GPUs (every
+rank processes its own batches; the path has no cross-tile dependency).
 
+slide (configs[3]): one "step" = a whole synthetic 100k x 100k px slide (11 025 tiles of 1024 px, 64 px overlap) cut
+from one global nuclei field: per-tile post-processing of this rank's tile rows, append in slide coordinates, exact
+slide-level merge NMS with the seam exchange over NCCL.  Strong scaling.  Unless --no-slide, a short slide run is also
+attached to the tiles line as "slide".
+
+Prints ONE JSON line on rank 0:
   value     : whole-job tiles/s with inputs resident in HBM (CUDA events, max over ranks)
-  e2e       : the same through the public API with HOST (pinned) inputs: H2D of the step's logits and
-              D2H of its detections inside the timed region
-  roofline  : dominant kernel (hdy_filter_compact_logits) algorithmic bytes / its CUDA-event time
+  e2e       : the same through the public API with HOST (pinned) inputs: H2D of the step's inputs and D2H of its
+              results inside the timed region
+  roofline  : the dominant HBM-bound kernel: algorithmic bytes per launch / its CUDA-event time (measured live)
+  stages    : every C-ABI call of the step with its time, algorithmic bytes and achieved GB/s
   cpu_baseline : oracle port (the reference's torch/torchvision CPU path) on a bounded sample
 """
 import argparse
@@ -25,24 +34,35 @@ if ROOT not in sys.path:
     sys.path.insert(0, ROOT)
 
 WORKLOADS = {
-    # BASELINE.json configs[1]: 640x640 tiles, batch 64, 3 anchor levels, ~1k candidates/tile
+    # BASELINE.json configs[1]: 640x640 tiles, batch 64, 3 anchor levels, 32 prototypes, ~1k candidates/tile
     "tiles640": dict(tile=640, bs=64, n_cand=1000, conf=0.25, iou=0.45, max_det=1000, nc=4, cap=2048),
     # BASELINE.json configs[2]: 1024x1024 dense-nuclei tiles, batch 128, ~3k candidates/tile
     "tiles1024": dict(tile=1024, bs=128, n_cand=3000, conf=0.25, iou=0.45, max_det=3000, nc=4, cap=4096),
+    # BASELINE.json configs[3]: whole slide, 1024-px tiles, 64-px overlap, ~3k candidates/tile
+    "slide": dict(tile=1024, bs=128, n_cand=3000, conf=0.25, iou=0.45, max_det=4096, nc=4, cap=4096, overlap=64),
 }
+NM = 32            # prototypes
 L2_BYTES = 126e6
 
 
 def parse():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=300)
-    ap.add_argument("--warmup", type=int, default=10)
+    ap.add_argument("--steps", type=int, default=None)
+    ap.add_argument("--warmup", type=int, default=None)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="tiles640", choices=list(WORKLOADS))
+    ap.add_argument("--masks", default="proto", choices=["proto", "none"])
+    ap.add_argument("--slide-size", type=int, default=100000)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
-    return ap.parse_args()
+    ap.add_argument("--no-slide", action="store_true")
+    a = ap.parse_args()
+    if a.steps is None:
+        a.steps = 5 if a.workload == "slide" else 200
+    if a.warmup is None:
+        a.warmup = 3 if a.workload == "slide" else 10
+    return a
 
 
 class ClockSampler(threading.Thread):
@@ -95,88 +115,107 @@ class ClockSampler(threading.Thread):
                 "samples": len(s)}
 
 
-def cpu_reference_pass(dets_cpu, wl, spec_args):
-    """The reference's CPU path for one batch: compute_proposals -> pad/cat -> nms_per_image -> select."""
+# ------------------------------------------------------------------------------------------------ CPU reference arm
+def cpu_reference_pass(dets_cpu, protos_cpu, wl, spec_args, masks):
+    """The reference's CPU path for one batch: compute_proposals -> pad/cat -> nms_per_image -> select
+    (-> process_mask with upsample per tile)."""
     from oracle import port
     anchors, strides = spec_args
+    nc = wl["nc"]
     preds = port.compute_proposals(dets_cpu, anchors, strides)
     params = {'conf_thres': wl["conf"], 'iou_thres': wl["iou"], 'max_det': wl["max_det"]}
-    return port.compute_outputs(preds, wl["nc"], params)
+    if masks == "none":
+        return port.compute_outputs(preds, nc, params)
+    cat = port.concat_levels(preds)
+    res = port.nms_per_image(cat, nc, wl["conf"], wl["iou"], wl["max_det"])
+    out = []
+    for i, r in enumerate(res):
+        s, l = port.select_scores(r['scores'][:, :1 + nc].clone(), wl["conf"], port.default_descendants(nc))
+        coef = r['extra'][:, :NM]      # extra = raw coefficient channels + level id; the coefficients come first
+        m = port.process_mask(protos_cpu[i], coef, r['boxes'], (wl["tile"], wl["tile"]), upsample=True)
+        out.append((r['boxes'], s, l, m))
+    return out
+
+
+def cpu_sample_inputs(wl, masks, sample, seed=1):
+    import torch
+    from hd_yolo_b200 import synth
+    extra = NM if masks == "proto" else 0
+    dets = synth.nuclei_logits(sample, wl["tile"], wl["nc"], wl["n_cand"], seed=seed, conf=wl["conf"], extra=extra)
+    protos = None
+    if masks == "proto":
+        g = torch.Generator().manual_seed(seed + 7)
+        protos = torch.randn((sample, NM, wl["tile"] // 4, wl["tile"] // 4), generator=g)
+    return dets, protos
+
+
+def time_cpu(wl, masks, budget_s, max_reps):
+    """Bounded CPU timing of the oracle port on all host threads.  Returns (tiles/s, cores, sample text)."""
+    import torch
+    from hd_yolo_b200 import synth
+    torch.set_num_threads(os.cpu_count() or 1)
+    sample = 2 if masks == "proto" else 8
+    dets, protos = cpu_sample_inputs(wl, masks, sample)
+    spec_args = (synth.ANCHORS_3, synth.STRIDES_3)
+    cpu_reference_pass(dets, protos, wl, spec_args, masks)          # warm-up
+    reps, t0 = 0, time.perf_counter()
+    while reps < 2 or (time.perf_counter() - t0 < budget_s and reps < max_reps):
+        cpu_reference_pass(dets, protos, wl, spec_args, masks)
+        reps += 1
+    dt = time.perf_counter() - t0
+    what = "compute_proposals + nms_per_image + score select" + (" + process_mask(upsample)" if masks == "proto" else "")
+    return sample * reps / dt, torch.get_num_threads(), (
+        f"{sample} tiles x {reps} passes of oracle/port.py ({what}; torch {torch.__version__} CPU + torchvision nms)")
 
 
 def run_reference(args, wl):
-    """--impl reference: the reference's own CPU implementation (oracle port: same torch/torchvision
-    calls) on all host threads; each step is a bounded sample of the workload."""
-    import torch
-    from hd_yolo_b200 import synth
+    """--impl reference: the reference's own CPU implementation (oracle port: same torch/torchvision calls) on all
+    host threads; each step is a bounded sample of the workload."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    sample = min(wl["bs"], 8)
-    torch.set_num_threads(os.cpu_count() or 1)
-    dets = synth.nuclei_logits(sample, wl["tile"], wl["nc"], wl["n_cand"], seed=1, conf=wl["conf"])
-    spec_args = (synth.ANCHORS_3, synth.STRIDES_3)
-    for _ in range(max(1, min(args.warmup, 3))):
-        cpu_reference_pass(dets, wl, spec_args)
-    steps = max(1, min(args.steps, 20))
-    t0 = time.perf_counter()
-    for _ in range(steps):
-        cpu_reference_pass(dets, wl, spec_args)
-    dt = time.perf_counter() - t0
-    v = sample * steps / dt
+    masks = args.masks if args.workload != "slide" else "none"
+    v, cores, sample = time_cpu(wl, masks, budget_s=20.0, max_reps=max(2, min(args.steps, 50)))
     line = {
         "impl": "reference", "metric": "postproc_tiles_per_s", "value": v, "unit": "tiles/s", "n_gpus": args.gpus,
-        "steps": steps, "warmup": min(args.warmup, 3), "ms_per_step": 1e3 * dt / steps, "higher_is_better": True,
-        "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": args.workload, "tile": wl["tile"], "sample_tiles_per_step": sample,
-                   "candidates_per_tile": wl["n_cand"], "conf": wl["conf"], "iou": wl["iou"], "max_det": wl["max_det"]},
-        "cpu_baseline": {"value": v, "unit": "tiles/s", "cores": torch.get_num_threads(), "kind": "port",
-                         "sample": f"{sample} tiles/step x {steps} steps, oracle/port.py (torch {torch.__version__} CPU + torchvision nms)"},
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * wl["bs"] / v, "higher_is_better": True,
+        "scaling": "strong" if args.workload == "slide" else "weak", "vs_baseline": None, "dtype": "f32",
+        "data": "synthetic",
+        "config": {"workload": args.workload, "tile": wl["tile"], "candidates_per_tile": wl["n_cand"],
+                   "conf": wl["conf"], "iou": wl["iou"], "max_det": wl["max_det"], "masks": masks,
+                   "note": "ms_per_step is the CPU time for one full batch of the workload, extrapolated from the sample"},
+        "cpu_baseline": {"value": v, "unit": "tiles/s", "cores": cores, "kind": "port", "sample": sample},
         "e2e": {"value": v, "unit": "tiles/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "boxes_per_s": v * wl["n_cand"],
     }
     print(json.dumps(line))
 
 
-def main():
-    args = parse()
-    wl = WORKLOADS[args.workload]
-    if args.impl == "reference":
-        return run_reference(args, wl)
+# ------------------------------------------------------------------------------------------------ helpers
+class Ctx:
+    pass
 
+
+def make_ctx(args):
     import torch
     import torch.distributed as dist
-    import hd_yolo_b200 as hdy
-    from hd_yolo_b200 import ops, synth
-
-    world = int(os.environ.get("WORLD_SIZE", "1"))
-    rank = int(os.environ.get("RANK", "0"))
-    local = int(os.environ.get("LOCAL_RANK", "0"))
-    torch.cuda.set_device(local)
-    dev = torch.device("cuda", local)
-    if world > 1:
-        dist.init_process_group("nccl", device_id=dev)
-    assert world == args.gpus, f"--gpus {args.gpus} but WORLD_SIZE={world}: launch with torch.distributed.run"
-
-    spec = hdy.HeadSpec(synth.ANCHORS_3, synth.STRIDES_3, nc=wl["nc"])
-    bs, K, W = wl["bs"], args.steps, args.warmup
-    shapes = synth.level_shapes(wl["tile"], synth.STRIDES_3)
-    N = spec.rows_per_tile(shapes)
-    in_bytes = bs * N * spec.no * 4
-    R = max(2, int(2.5 * L2_BYTES / in_bytes) + 1)       # rotate input batches so that reads miss L2
-    batches = [synth.nuclei_logits(bs, wl["tile"], wl["nc"], wl["n_cand"], seed=1000 * rank + r, conf=wl["conf"],
-                                   generator_device="cuda") for r in range(R)]
-
-    def step(i, dets=None):
-        return hdy.detect_postprocess(dets if dets is not None else batches[i % R], spec, wl["conf"], wl["iou"],
-                                      wl["max_det"], cap=wl["cap"])
+    c = Ctx()
+    c.world = int(os.environ.get("WORLD_SIZE", "1"))
+    c.rank = int(os.environ.get("RANK", "0"))
+    c.local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(c.local)
+    c.dev = torch.device("cuda", c.local)
+    if c.world > 1:
+        dist.init_process_group("nccl", device_id=c.dev)
+    assert c.world == args.gpus, f"--gpus {args.gpus} but WORLD_SIZE={c.world}: launch with torch.distributed.run"
 
     def barrier():
-        if world > 1:
+        if c.world > 1:
             dist.barrier()
         torch.cuda.synchronize()
 
     def timed(fn, steps):
+        """CUDA events around `steps` calls, barrier + synchronize on both sides, max over ranks (ms)."""
         barrier()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
@@ -185,113 +224,306 @@ def main():
         e1.record()
         barrier()
         ms = e0.elapsed_time(e1)
-        if world > 1:
-            t = torch.tensor([ms], device=dev)
+        if c.world > 1:
+            t = torch.tensor([ms], device=c.dev)
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
             ms = float(t)
         return ms
 
-    sampler = ClockSampler(local)
+    c.barrier, c.timed = barrier, timed
+    return c
+
+
+def load_peak():
+    try:
+        p = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+        return float(p["hbm_gbs"]), "MEASURED_PEAKS.json hbm_gbs (of measured)"
+    except Exception:
+        return 6650.0, "fallback 6650 GB/s (of fallback)"
+
+
+# ------------------------------------------------------------------------------------------------ tiles workloads
+def run_tiles(args, wl, c):
+    import torch
+    import hd_yolo_b200 as hdy
+    from hd_yolo_b200 import masks as hmasks
+    from hd_yolo_b200 import ops, synth
+
+    masks = args.masks
+    extra = NM if masks == "proto" else 0
+    nc, tile, bs, K, W = wl["nc"], wl["tile"], wl["bs"], args.steps, max(args.warmup, 3)
+    spec = hdy.HeadSpec(synth.ANCHORS_3, synth.STRIDES_3, nc=nc, no=5 + nc + extra)
+    shapes = synth.level_shapes(tile, synth.STRIDES_3)
+    N = spec.rows_per_tile(shapes)
+    mh = mw = tile // 4
+    in_bytes = bs * N * spec.no * 4 + (bs * NM * mh * mw * 4 if masks == "proto" else 0)
+    R = max(2, int(2.5 * L2_BYTES / in_bytes) + 1)       # rotate input batches so that reads miss L2
+    batches = [synth.nuclei_logits(bs, tile, nc, wl["n_cand"], seed=1000 * c.rank + r, conf=wl["conf"], extra=extra,
+                                   generator_device="cuda") for r in range(R)]
+    protos = None
+    if masks == "proto":
+        g = torch.Generator(device="cuda").manual_seed(77 + c.rank)
+        protos = [torch.randn((bs, NM, mh, mw), generator=g, device=c.dev) for _ in range(R)]
+    state = {"cap_words": None}
+
+    def step(i, dets=None, pr=None):
+        out = hdy.detect_postprocess(dets if dets is not None else batches[i % R], spec, wl["conf"], wl["iou"],
+                                     wl["max_det"], cap=wl["cap"])
+        pm = None
+        if masks == "proto":
+            pm = hmasks.process_mask_packed(pr if pr is not None else protos[i % R], out.extra, out.boxes, out.counts,
+                                            (tile, tile), upsample=True, capacity_words=state["cap_words"])
+        return out, pm
+
+    # size the packed-mask buffer once (the only call that reads a size back), then never sync inside a step
+    out, pm = step(0)
+    out.to_list()                      # raises on candidate-capacity overflow
+    words = 0
+    if pm is not None:
+        words = int(pm.offsets[-1].item())
+        state["cap_words"] = int(words * 1.2) + 1024
+
+    sampler = ClockSampler(c.local)
     sampler.start()
-
-    # ---- value: inputs resident in HBM ---------------------------------------------------------------
-    for i in range(max(W, 3)):
-        out = step(i)
-    out.to_list()                      # raises on capacity overflow
+    for i in range(W):
+        out, pm = step(i)
+    if pm is not None:
+        pm.check()
     ops.profile.reset()
-    ms = timed(step, K)
+    ms = c.timed(step, K)
     launches = ops.profile.launches
-    tiles_per_s = world * bs * K / (ms * 1e-3)
+    tiles_per_s = c.world * bs * K / (ms * 1e-3)
 
-    # ---- per-kernel CUDA-event times over an identical region (roofline) --------------------------------
+    # ---- per-call CUDA-event times over an identical region --------------------------------------------
     ops.profile.enabled = True
     ops.profile.reset()
-    timed(step, K)
+    c.timed(step, K)
     prof = ops.profile.summary()
     ops.profile.enabled = False
-    cand_mean = float(out.cand_counts[:bs].float().mean())
-    kept_mean = float(out.counts.float().mean())
-    dom = "hdy_filter_compact_logits"
-    dom_calls, dom_ms = prof[dom]
-    alg_bytes = bs * (4 * N * spec.no + 24 * cand_mean)          # read logits once, write key(8)+box(16) per candidate
-    peaks = {}
-    try:
-        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
-    except Exception:
-        pass
-    peak = float(peaks.get("hbm_gbs", 6650.0))
-    achieved = alg_bytes / (dom_ms / dom_calls * 1e-3) / 1e9
-    stage_ms = {k: v[1] / v[0] for k, v in prof.items()}
-    # whole-step algorithmic bytes: decode + nms read/write
-    nc = wl["nc"]
-    step_bytes = alg_bytes + bs * (cand_mean * 24 + kept_mean * (4 * (1 + nc)) + kept_mean * (16 + 4 + 8 + 4 + 4 * (1 + nc) + 4))
+    cand = float(out.cand_counts[:bs].float().mean())
+    kept = float(out.counts.float().mean())
+    ne = spec.no - 5 - nc
+    alg = {   # algorithmic bytes per launch
+        "hdy_filter_compact_logits": bs * (4 * N * spec.no + 24 * cand),
+        "hdy_nms_tiles": bs * (24 * cand + 28 * kept),
+        "hdy_gather_logits": bs * kept * (4 * (1 + nc + ne) * 2 + 4),
+        "hdy_select_scores": bs * kept * (4 * (1 + nc) * 2 + 4 + 8),
+        "hdy_process_mask_geometry": bs * min(wl["max_det"], wl["cap"]) * (16 + 16 + 8),
+        "hdy_process_mask_packed": bs * (4 * NM * mh * mw + kept * (4 * NM + 16 + 8)) + 4 * words,
+        "hdy_zero_i32": 4 * (bs + 1),
+    }
+    peak, peak_src = load_peak()
+    stages = {}
+    for name, (calls, tot) in prof.items():
+        t = tot / calls
+        a = alg.get(name)
+        stages[name] = {"ms": t, "alg_bytes": a, "gbs": (a / (t * 1e-3) / 1e9) if a else None}
+    hbm_bound = [k for k in stages if k in ("hdy_filter_compact_logits", "hdy_process_mask_packed")]
+    dom = max(hbm_bound, key=lambda k: stages[k]["ms"])
+    dom_ms, dom_bytes = stages[dom]["ms"], alg[dom]
+    achieved = dom_bytes / (dom_ms * 1e-3) / 1e9
+    step_bytes = sum(v["alg_bytes"] for v in stages.values() if v["alg_bytes"])
 
     # ---- e2e: host (pinned) inputs, H2D + D2H inside the timed region ---------------------------------------
     e2e = None
     if not args.no_e2e:
         host = [[d.cpu().pin_memory() for d in b] for b in batches[:2]]
+        host_p = [p.cpu().pin_memory() for p in protos[:2]] if protos is not None else None
         stage = [torch.empty_like(d) for d in batches[0]]
-        md = min(wl["max_det"], wl["cap"])
-        h_boxes = torch.empty((bs, md, 4), dtype=torch.float32).pin_memory()
-        h_scores = torch.empty((bs, md), dtype=torch.float32).pin_memory()
-        h_labels = torch.empty((bs, md), dtype=torch.int64).pin_memory()
-        h_counts = torch.empty((bs,), dtype=torch.int32).pin_memory()
+        stage_p = torch.empty_like(protos[0]) if protos is not None else None
+        md = out.max_det
+        h = {"boxes": torch.empty((bs, md, 4), dtype=torch.float32).pin_memory(),
+             "scores": torch.empty((bs, md), dtype=torch.float32).pin_memory(),
+             "labels": torch.empty((bs, md), dtype=torch.int64).pin_memory(),
+             "counts": torch.empty((bs,), dtype=torch.int32).pin_memory()}
+        if pm is not None:
+            h["geom"] = torch.empty(tuple(pm.geom.shape), dtype=torch.int32).pin_memory()
+            h["offsets"] = torch.empty(tuple(pm.offsets.shape), dtype=torch.int64).pin_memory()
+            h["bits"] = torch.empty((state["cap_words"],), dtype=torch.int32).pin_memory()
 
         def e2e_step(i):
-            for s, h in zip(stage, host[i % 2]):
-                s.copy_(h, non_blocking=True)
-            o = step(i, stage)
-            h_boxes.copy_(o.boxes, non_blocking=True)
-            h_scores.copy_(o.scores, non_blocking=True)
-            h_labels.copy_(o.labels, non_blocking=True)
-            h_counts.copy_(o.counts, non_blocking=True)
+            for s, hh in zip(stage, host[i % 2]):
+                s.copy_(hh, non_blocking=True)
+            if stage_p is not None:
+                stage_p.copy_(host_p[i % 2], non_blocking=True)
+            o, p = step(i, stage, stage_p)
+            h["boxes"].copy_(o.boxes, non_blocking=True)
+            h["scores"].copy_(o.scores, non_blocking=True)
+            h["labels"].copy_(o.labels, non_blocking=True)
+            h["counts"].copy_(o.counts, non_blocking=True)
+            if p is not None:
+                h["geom"].copy_(p.geom, non_blocking=True)
+                h["offsets"].copy_(p.offsets, non_blocking=True)
+                h["bits"][:p.bits.numel()].copy_(p.bits, non_blocking=True)
 
-        Ke = max(3, min(K, 100))
+        Ke = max(3, min(K, 50))
         for i in range(3):
             e2e_step(i)
-        ms_e = timed(e2e_step, Ke)
-        e2e = {"value": world * bs * Ke / (ms_e * 1e-3), "unit": "tiles/s", "h2d_bytes_per_step": in_bytes,
-               "d2h_bytes_per_step": h_boxes.numel() * 4 + h_scores.numel() * 4 + h_labels.numel() * 8 + h_counts.numel() * 4,
-               "steps": Ke, "ms_per_step": ms_e / Ke}
-
+        ms_e = c.timed(e2e_step, Ke)
+        d2h = sum(t.numel() * t.element_size() for k, t in h.items() if k != "bits") + (words * 4 if pm is not None else 0)
+        e2e = {"value": c.world * bs * Ke / (ms_e * 1e-3), "unit": "tiles/s", "h2d_bytes_per_step": in_bytes,
+               "d2h_bytes_per_step": d2h, "steps": Ke, "ms_per_step": ms_e / Ke}
+        del host, host_p, stage, stage_p, h
     clocks = sampler.stop()
 
-    # ---- CPU baseline: oracle port on host cores, rank 0, bounded sample -----------------------------------
-    cpu = None
-    if rank == 0 and not args.no_cpu_baseline:
-        torch.set_num_threads(os.cpu_count() or 1)
-        sample = min(bs, 16)
-        dets_cpu = [d[:sample].cpu() for d in batches[0]]
-        spec_args = (synth.ANCHORS_3, synth.STRIDES_3)
-        cpu_reference_pass(dets_cpu, wl, spec_args)
-        reps, t0 = 0, time.perf_counter()
-        while reps < 3 or (time.perf_counter() - t0 < 5.0 and reps < 50):
-            cpu_reference_pass(dets_cpu, wl, spec_args)
-            reps += 1
-        dt = time.perf_counter() - t0
-        cpu = {"value": sample * reps / dt, "unit": "tiles/s", "cores": torch.get_num_threads(), "kind": "port",
-               "sample": f"{sample} tiles x {reps} passes of oracle/port.py (torch CPU + torchvision.ops.nms)"}
+    line = {
+        "metric": "postproc_tiles_per_s", "value": tiles_per_s, "unit": "tiles/s", "n_gpus": c.world, "steps": K,
+        "warmup": W, "ms_per_step": ms / K, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": args.workload, "tile": tile, "tiles_per_step_per_gpu": bs, "levels": 3,
+                   "rows_per_tile": N, "channels": spec.no, "prototypes": NM if masks == "proto" else 0,
+                   "candidates_per_tile": round(cand, 1), "kept_per_tile": round(kept, 1), "conf": wl["conf"],
+                   "iou": wl["iou"], "max_det": wl["max_det"], "cap": wl["cap"],
+                   "stages": "decode+filter+compact, nms, score/label select" +
+                             (", process_mask (proto contraction, sigmoid, crop, upsample, >0.5, bit-packed)" if masks == "proto" else ""),
+                   "l2": f"{R} rotating input batches ({R * in_bytes / 1e6:.0f} MB) > 126 MB L2"},
+        "boxes_per_s": tiles_per_s * cand,
+        "roofline": {"bound": "hbm", "kernel": dom, "achieved": achieved, "peak": peak, "unit": "GB/s",
+                     "frac": achieved / peak, "traffic": None, "peak_source": peak_src,
+                     "algorithmic_bytes_per_launch": dom_bytes, "kernel_ms": dom_ms},
+        "stages": stages,
+        "pipeline": {"algorithmic_bytes_per_step": step_bytes, "achieved_gbs": step_bytes / (ms / K * 1e-3) / 1e9,
+                     "frac_of_peak": step_bytes / (ms / K * 1e-3) / 1e9 / peak},
+        "e2e": e2e, "gpu_launches": launches, "clocks": clocks,
+    }
+    del batches, protos
+    torch.cuda.empty_cache()
+    return line
 
-    if rank == 0:
+
+# ------------------------------------------------------------------------------------------------ slide workload
+def run_slide(args, wl, c, steps, warmup, want_e2e):
+    import torch
+    import hd_yolo_b200 as hdy
+    from hd_yolo_b200 import ops, synth
+    from hd_yolo_b200.pipeline import SlidePostprocessor
+
+    nc, tile, bs = wl["nc"], wl["tile"], wl["bs"]
+    spec = hdy.HeadSpec(synth.ANCHORS_3, synth.STRIDES_3, nc=nc)
+    S = args.slide_size
+    post = SlidePostprocessor(spec, (S, S), (tile, tile), wl["overlap"], wl["conf"], wl["iou"], wl["max_det"],
+                              cap=wl["cap"], batch=bs, rank=c.rank, world=c.world, device=c.dev,
+                              capacity=None)
+    t0, t1 = post.tile_range
+    n_tiles = int(post.rois.shape[0])
+    # this rank's head outputs for the whole slide, resident in HBM (N=1: 11 025 tiles x 2.3 MB = 25.6 GB)
+    store = []
+    for a in range(t0, t1, bs):
+        b = min(a + bs, t1)
+        store.append(synth.slide_tile_logits(post.rois[a:b], tile, nc, seed=a, conf=wl["conf"], device=c.dev))
+    in_bytes = sum(sum(t.numel() * 4 for t in dets) for dets in store)
+
+    def provider(a, b):
+        return store[(a - t0) // bs]
+
+    res = {}
+
+    def step(i):
+        res["r"] = post.run(provider, ordered=True)
+
+    for i in range(max(warmup, 1)):
+        step(i)
+    ops.profile.reset()
+    ms = c.timed(step, steps)
+    launches = ops.profile.launches
+    # merge alone (detections already appended by the last step)
+    ms_merge = c.timed(lambda i: post.merge(ordered=True), max(2, min(steps, 5)))
+    ms_merge /= max(2, min(steps, 5))
+    r = res["r"]
+    n_local = int(r["n"])
+    kept_local = int((r["state"] == 1).sum())
+    tot = torch.tensor([n_local, kept_local, in_bytes], dtype=torch.float64, device=c.dev)
+    if c.world > 1:
+        import torch.distributed as dist
+        dist.all_reduce(tot)
+    out = {"tiles": n_tiles, "tiles_per_s": n_tiles * steps / (ms * 1e-3), "ms_per_slide": ms / steps,
+           "merge_ms": ms_merge, "detections": int(tot[0]), "kept": int(tot[1]),
+           "input_bytes": int(tot[2]), "slide_px": S, "tile": tile, "overlap": wl["overlap"],
+           "seam_rows": r.get("seam_rows"), "exchanges": r.get("exchanges"), "gpu_launches": launches,
+           "boxes_per_s": int(tot[0]) * steps / (ms * 1e-3)}
+    if want_e2e:
+        # host-resident head outputs: every batch is copied H2D inside the timed region (4 pinned host batches are
+        # reused in rotation, bytes are counted for every copy), the slide's survivors are read back D2H
+        nrot = min(4, len(store))
+        host = [[t.cpu().pin_memory() for t in store[k]] for k in range(nrot)]
+        stage = [torch.empty_like(t) for t in store[0]]
+
+        def provider_h(a, b):
+            k = ((a - t0) // bs)
+            src = host[k % nrot]
+            n = b - a
+            for s, h in zip(stage, src):
+                s[:n].copy_(h[:n], non_blocking=True)
+            return [s[:n] for s in stage] if n < bs else stage
+
+        hb = {}
+
+        def e2e_step(i):
+            rr = post.run(provider_h, ordered=True)
+            hb["boxes"] = rr["boxes"].cpu()
+            hb["scores"] = rr["scores"].cpu()
+            hb["labels"] = rr["labels"].cpu()
+
+        e2e_step(0)
+        Ke = max(1, min(steps, 3))
+        ms_e = c.timed(e2e_step, Ke)
+        d2h = sum(t.numel() * t.element_size() for t in hb.values())
+        out["e2e"] = {"value": n_tiles * Ke / (ms_e * 1e-3), "unit": "tiles/s", "h2d_bytes_per_step": in_bytes,
+                      "d2h_bytes_per_step": d2h, "steps": Ke, "ms_per_step": ms_e / Ke}
+        del host, stage
+    del store
+    torch.cuda.empty_cache()
+    return out
+
+
+# ------------------------------------------------------------------------------------------------ main
+def main():
+    args = parse()
+    wl = WORKLOADS[args.workload]
+    if args.impl == "reference":
+        return run_reference(args, wl)
+
+    import torch
+    import torch.distributed as dist
+    c = make_ctx(args)
+    peak, peak_src = load_peak()
+
+    if args.workload == "slide":
+        sampler = ClockSampler(c.local)
+        sampler.start()
+        s = run_slide(args, wl, c, args.steps, args.warmup, want_e2e=not args.no_e2e)
+        clocks = sampler.stop()
+        # roofline of the dominant kernel on this workload's tiles: measured on a tiles1024 batch in the same process
+        targs = argparse.Namespace(**vars(args))
+        targs.workload, targs.masks, targs.steps, targs.warmup, targs.no_e2e = "tiles1024", "none", 50, 5, True
+        t = run_tiles(targs, WORKLOADS["tiles1024"], c)
         line = {
-            "metric": "postproc_tiles_per_s", "value": tiles_per_s, "unit": "tiles/s", "n_gpus": world, "steps": K,
-            "warmup": max(W, 3), "ms_per_step": ms / K, "higher_is_better": True, "scaling": "weak",
-            "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": args.workload, "tile": wl["tile"], "tiles_per_step_per_gpu": bs, "levels": 3,
-                       "rows_per_tile": N, "channels": spec.no, "candidates_per_tile": round(cand_mean, 1),
-                       "kept_per_tile": round(kept_mean, 1), "conf": wl["conf"], "iou": wl["iou"],
-                       "max_det": wl["max_det"], "cap": wl["cap"], "stages": "decode+filter+compact, nms, score/label select",
-                       "l2": f"{R} rotating input batches ({R * in_bytes / 1e6:.0f} MB) > 126 MB L2"},
-            "boxes_per_s": tiles_per_s * cand_mean,
-            "roofline": {"bound": "hbm", "kernel": dom, "achieved": achieved, "peak": peak, "unit": "GB/s",
-                         "frac": achieved / peak, "traffic": None, "peak_source": "MEASURED_PEAKS.json hbm_gbs" if peaks else "fallback 6650",
-                         "algorithmic_bytes_per_launch": alg_bytes, "kernel_ms": dom_ms / dom_calls},
-            "pipeline": {"algorithmic_bytes_per_step": step_bytes, "achieved_gbs": step_bytes / (ms / K * 1e-3) / 1e9 * 1.0,
-                         "frac_of_peak": step_bytes / (ms / K * 1e-3) / 1e9 / peak, "stage_ms": stage_ms},
-            "e2e": e2e, "gpu_launches": launches, "clocks": clocks, "cpu_baseline": cpu,
+            "metric": "postproc_tiles_per_s", "value": s["tiles_per_s"], "unit": "tiles/s", "n_gpus": c.world,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": s["ms_per_slide"], "higher_is_better": True,
+            "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": "slide", "slide_px": s["slide_px"], "tile": s["tile"], "overlap": s["overlap"],
+                       "tiles": s["tiles"], "detections": s["detections"], "kept": s["kept"],
+                       "stages": "per-tile decode+filter+compact, nms, select; append in slide coordinates; exact "
+                                 "slide-level merge NMS (seam all-gather + verdict exchange over NCCL when N>1)",
+                       "l2": f"{s['input_bytes'] / 1e9:.1f} GB of head outputs resident in HBM, each read once per step"},
+            "boxes_per_s": s["boxes_per_s"], "roofline": t["roofline"], "stages": t["stages"],
+            "slide": s, "e2e": s.get("e2e"), "gpu_launches": s["gpu_launches"], "clocks": clocks,
         }
+    else:
+        line = run_tiles(args, wl, c)
+        if not args.no_slide:
+            sargs = argparse.Namespace(**vars(args))
+            line["slide"] = run_slide(sargs, WORKLOADS["slide"], c, steps=2, warmup=1, want_e2e=False)
+
+    cpu = None
+    if c.rank == 0 and not args.no_cpu_baseline:
+        masks = args.masks if args.workload != "slide" else "none"
+        v, cores, sample = time_cpu(wl, masks, budget_s=15.0, max_reps=30)
+        cpu = {"value": v, "unit": "tiles/s", "cores": cores, "kind": "port", "sample": sample}
+    line["cpu_baseline"] = cpu
+    if c.rank == 0:
         print(json.dumps(line))
-    if world > 1:
+    if c.world > 1:
         dist.destroy_process_group()
 
 

@@ -12,6 +12,7 @@ from .ops import (  # noqa: F401
     compute_proposals,
     decode_concat,
     detect_postprocess,
+    flatten_onehot_objects,
     nms,
     nms_per_image,
     non_max_suppression,
@@ -43,5 +44,8 @@ from .slide import (  # noqa: F401,E402
     sort_keys,
     tile_cores,
 )
+
+from . import dist, pipeline  # noqa: F401,E402
+from .pipeline import SlidePostprocessor  # noqa: F401,E402
 
 __version__ = "0.1.0"

@@ -18,31 +18,9 @@
 //
 // ATen's bilinear (align_corners=False): scale = in/out (fp32); src = scale*(dst+0.5)-0.5, clamped at 0;
 // i0 = (int)src; i1 = min(i0+1, in-1); l1 = src-i0; l0 = 1-l1; v = l0y*(l0x*v00 + l1x*v01) + l1y*(l0x*v10 + l1x*v11).
-#include "hdy_common.cuh"
+#include "mask_common.cuh"
 
 namespace hdy {
-
-struct Lerp {
-  int i0, i1;
-  float l0, l1;
-};
-
-__device__ __forceinline__ Lerp lerp_coord(int dst, float scale, int in_size) {
-  float src = __fsub_rn(__fmul_rn(scale, __fadd_rn((float)dst, 0.5f)), 0.5f);
-  if (src < 0.f) src = 0.f;
-  Lerp L;
-  L.i0 = min((int)src, in_size - 1);
-  L.i1 = min(L.i0 + 1, in_size - 1);
-  L.l1 = fminf(fmaxf(__fsub_rn(src, (float)L.i0), 0.f), 1.f);
-  L.l0 = __fsub_rn(1.0f, L.l1);
-  return L;
-}
-
-__device__ __forceinline__ float bilerp(float v00, float v01, float v10, float v11, const Lerp& X, const Lerp& Y) {
-  const float top = __fadd_rn(__fmul_rn(X.l0, v00), __fmul_rn(X.l1, v01));
-  const float bot = __fadd_rn(__fmul_rn(X.l0, v10), __fmul_rn(X.l1, v11));
-  return __fadd_rn(__fmul_rn(Y.l0, top), __fmul_rn(Y.l1, bot));
-}
 
 // ---------------------------------------------------------------------------------------------- M1
 __global__ void mask_select_kernel(const float* __restrict__ logits, const int64_t* __restrict__ labels,
@@ -95,43 +73,88 @@ __device__ __forceinline__ PasteGeom paste_geometry(const float4 b, float scale,
   return g;
 }
 
-// words of the cropped bit plane per mask, then an exclusive scan (single CTA, chunked) -> offsets[K+1]
-__global__ void __launch_bounds__(1024) scan_words_kernel(const int32_t* __restrict__ geom4, long long K,
-                                                          int64_t* __restrict__ offsets) {
-  __shared__ long long warp_sum[32];
-  __shared__ long long carry;
-  if (threadIdx.x == 0) carry = 0;
-  __syncthreads();
+// words of the cropped bit plane per mask, then an exclusive scan -> offsets[K+1], in three launches and no scratch:
+//   1. every CTA scans its 1024 masks; the exclusive prefix of a CTA's first mask is 0 by construction, so that slot
+//      (offsets[(b+1)*1024], or offsets[K] for the last CTA) carries the CTA's TOTAL to the next step instead;
+//   2. one CTA turns those totals into running sums: offsets[b*1024] becomes the base of CTA b (its final value),
+//      offsets[K] the grand total;
+//   3. every CTA b >= 1 adds its base to its other 1023 slots.
+constexpr int kScanChunk = 1024;
+
+__device__ __forceinline__ long long block_incl_scan_ll(long long v, long long* warp_sum) {
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  for (long long base = 0; base < K; base += 1024) {
-    const long long i = base + threadIdx.x;
-    long long v = 0;
-    if (i < K) v = (long long)((geom4[4 * i + 2] + 31) >> 5) * geom4[4 * i + 3];
-    long long incl = v;
+  long long incl = v;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    long long u = __shfl_up_sync(0xffffffffu, incl, o);
+    if (lane >= o) incl += u;
+  }
+  if (lane == 31) warp_sum[warp] = incl;
+  __syncthreads();
+  if (warp == 0) {
+    long long s = warp_sum[lane], t = s;
 #pragma unroll
     for (int o = 1; o < 32; o <<= 1) {
-      long long u = __shfl_up_sync(0xffffffffu, incl, o);
-      if (lane >= o) incl += u;
+      long long u = __shfl_up_sync(0xffffffffu, t, o);
+      if (lane >= o) t += u;
     }
-    if (lane == 31) warp_sum[warp] = incl;
+    warp_sum[lane] = t - s;
+  }
+  __syncthreads();
+  const long long r = warp_sum[warp] + incl;
+  __syncthreads();
+  return r;
+}
+
+__global__ void __launch_bounds__(kScanChunk) scan_words_local_kernel(const int32_t* __restrict__ geom4, long long K,
+                                                                      int64_t* __restrict__ offsets) {
+  __shared__ long long warp_sum[32];
+  const long long i = (long long)blockIdx.x * kScanChunk + threadIdx.x;
+  long long v = 0;
+  if (i < K) v = (long long)((geom4[4 * i + 2] + 31) >> 5) * geom4[4 * i + 3];
+  const long long incl = block_incl_scan_ll(v, warp_sum);
+  if (i < K && threadIdx.x != 0) offsets[i] = incl - v;
+  const long long last = min((long long)(blockIdx.x + 1) * kScanChunk, K) - 1;  // last mask of this CTA
+  if (i == last) offsets[last + 1] = incl;                                       // CTA total -> next CTA's first slot
+  if (i == 0) offsets[0] = 0;
+}
+
+__global__ void __launch_bounds__(kScanChunk) scan_words_bases_kernel(long long K, int64_t* __restrict__ offsets) {
+  __shared__ long long warp_sum[32];
+  __shared__ long long carry;
+  const long long nb = (K + kScanChunk - 1) / kScanChunk;  // totals live at slots min((b+1)*1024, K), b = 0..nb-1
+  if (threadIdx.x == 0) carry = 0;
+  __syncthreads();
+  for (long long b0 = 0; b0 < nb; b0 += kScanChunk) {
+    const long long b = b0 + threadIdx.x;
+    const long long slot = min((b + 1) * kScanChunk, K);
+    const long long v = b < nb ? offsets[slot] : 0;
+    const long long incl = block_incl_scan_ll(v, warp_sum) + carry;
+    if (b < nb) offsets[slot] = incl;
     __syncthreads();
-    if (warp == 0) {
-      long long s = warp_sum[lane], t = s;
-#pragma unroll
-      for (int o = 1; o < 32; o <<= 1) {
-        long long u = __shfl_up_sync(0xffffffffu, t, o);
-        if (lane >= o) t += u;
-      }
-      warp_sum[lane] = t - s;
-    }
-    __syncthreads();
-    const long long excl = carry + warp_sum[warp] + incl - v;
-    if (i < K) offsets[i] = excl;
-    __syncthreads();
-    if (threadIdx.x == 1023) carry = excl + v;
+    if (threadIdx.x == kScanChunk - 1) carry = incl;
     __syncthreads();
   }
-  if (threadIdx.x == 0) offsets[K] = carry;
+}
+
+__global__ void __launch_bounds__(kScanChunk) scan_words_add_kernel(long long K, int64_t* __restrict__ offsets) {
+  const long long first = (long long)(blockIdx.x + 1) * kScanChunk;  // CTA 0 has base 0
+  const long long i = first + threadIdx.x;
+  if (threadIdx.x == 0 || i >= K) return;
+  offsets[i] += offsets[first];
+}
+
+static void launch_scan_words(const int32_t* geom, long long K, int64_t* offsets, cudaStream_t st) {
+  if (K <= 0) {
+    cudaMemsetAsync(offsets, 0, sizeof(int64_t), st);
+    return;
+  }
+  const unsigned nb = (unsigned)((K + kScanChunk - 1) / kScanChunk);
+  scan_words_local_kernel<<<nb, kScanChunk, 0, st>>>(geom, K, offsets);
+  if (nb > 1) {
+    scan_words_bases_kernel<<<1, kScanChunk, 0, st>>>(K, offsets);
+    scan_words_add_kernel<<<nb - 1, kScanChunk, 0, st>>>(K, offsets);
+  }
 }
 
 __global__ void paste_geometry_kernel(const float4* __restrict__ boxes, int K, float scale, int H, int W,
@@ -210,61 +233,6 @@ __global__ void unpack_masks_kernel(const int32_t* __restrict__ geom4, const int
     const uint32_t wd = bits[off + (long long)yy * wpr + (xx >> 5)];
     o[(size_t)(g.y + yy) * W + g.x + xx] = (wd >> (xx & 31)) & 1u;
   }
-}
-
-// ------------------------------------------------------------------------------------- (B) process_mask
-// Window of mask i in output pixels.  crop_mask keeps proto pixels with x1d <= col < x2d, y1d <= row < y2d
-// (float compares against arange); with upsample the bilinear taps spread every kept pixel over its
-// neighbours, so the output window is the pre-image of [p0-1, p1) under i0 = floor(src).
-struct PMGeom {
-  float x1d, y1d, x2d, y2d;  // down-scaled box (fp32, as the reference computes it)
-  int px0, py0, px1, py1;    // kept proto pixel range [p0, p1)
-  int x0, y0, w, h;          // output window
-};
-
-__device__ __forceinline__ int ceil_to_int_clamped(float v, int lo, int hi) {
-  if (!(v > (float)lo)) return lo;  // also NaN
-  if (v >= (float)hi) return hi;
-  return (int)ceilf(v);
-}
-
-__device__ __forceinline__ PMGeom pm_geometry(const float4 b, int mh, int mw, int ih, int iw, int upsample,
-                                              float rx, float ry) {
-  PMGeom g;
-  g.x1d = __fmul_rn(b.x, rx);  // downsampled_bboxes[:, 0] *= mw / iw
-  g.x2d = __fmul_rn(b.z, rx);
-  g.y1d = __fmul_rn(b.y, ry);
-  g.y2d = __fmul_rn(b.w, ry);
-  // r >= x1 & r < x2 over integers r: [ceil(x1), ceil(x2))
-  g.px0 = ceil_to_int_clamped(g.x1d, 0, mw);
-  g.px1 = ceil_to_int_clamped(g.x2d, 0, mw);
-  g.py0 = ceil_to_int_clamped(g.y1d, 0, mh);
-  g.py1 = ceil_to_int_clamped(g.y2d, 0, mh);
-  if (g.px1 <= g.px0 || g.py1 <= g.py0) {
-    g.x0 = g.y0 = g.w = g.h = 0;
-    return g;
-  }
-  if (!upsample) {
-    g.x0 = g.px0;
-    g.y0 = g.py0;
-    g.w = g.px1 - g.px0;
-    g.h = g.py1 - g.py0;
-  } else {
-    // conservative superset: src = s*(dst+0.5)-0.5 with s = mw/iw; i0 in [p0-1, p1-1]  <=>  src in [p0-1, p1)
-    const float sx = (float)mw / (float)iw, sy = (float)mh / (float)ih;
-    int ox0 = (int)floorf(((float)g.px0 - 0.5f) / sx - 0.5f) - 1, ox1 = (int)ceilf(((float)g.px1 + 0.5f) / sx - 0.5f) + 1;
-    int oy0 = (int)floorf(((float)g.py0 - 0.5f) / sy - 0.5f) - 1, oy1 = (int)ceilf(((float)g.py1 + 0.5f) / sy - 0.5f) + 1;
-    ox0 = max(ox0, 0);
-    oy0 = max(oy0, 0);
-    ox1 = min(ox1, iw);
-    oy1 = min(oy1, ih);
-    g.x0 = ox0;
-    g.y0 = oy0;
-    g.w = max(ox1 - ox0, 0);
-    g.h = max(oy1 - oy0, 0);
-    if (g.w == 0 || g.h == 0) g.x0 = g.y0 = g.w = g.h = 0;
-  }
-  return g;
 }
 
 __global__ void pm_geometry_kernel(const float4* __restrict__ boxes, const int32_t* __restrict__ counts, int bs,
@@ -452,7 +420,7 @@ int hdy_paste_geometry(const float* boxes, int K, int M, int padding, int H, int
     paste_geometry_kernel<<<(unsigned)((K + 127) / 128), 128, 0, st>>>(reinterpret_cast<const float4*>(boxes), K,
                                                                        scale, H, W, geom);
   }
-  scan_words_kernel<<<1, 1024, 0, st>>>(geom, K, offsets);
+  launch_scan_words(geom, K, offsets, st);
   return check_launch("hdy_paste_geometry");
 }
 
@@ -497,6 +465,9 @@ int hdy_process_mask(const float* protos, const float* coef, const float* boxes,
     return HDY_ERR_CUDA;
   }
   const float rx = (float)((double)mw / (double)iw), ry = (float)((double)mh / (double)ih);
+  rc = launch_process_mask_regions(protos, coef, boxes, counts, bs, max_det, nm, mh, mw, ih, iw, upsample, rx, ry, out,
+                                   nullptr, nullptr, 0, nullptr, st);
+  if (rc != 1) return rc;
   process_mask_kernel<false><<<(unsigned)((size_t)bs * max_det), kPmThreads, 0, st>>>(
       protos, coef, reinterpret_cast<const float4*>(boxes), counts, max_det, nm, mh, mw, ih, iw, upsample, rx, ry,
       out, nullptr, nullptr, 0, nullptr);
@@ -516,7 +487,7 @@ int hdy_process_mask_geometry(const float* boxes, const int32_t* counts, int bs,
     pm_geometry_kernel<<<(unsigned)((K + 127) / 128), 128, 0, st>>>(reinterpret_cast<const float4*>(boxes), counts, bs,
                                                                     max_det, mh, mw, ih, iw, upsample, rx, ry, geom);
   }
-  scan_words_kernel<<<1, 1024, 0, st>>>(geom, K, offsets);
+  launch_scan_words(geom, K, offsets, st);
   return check_launch("hdy_process_mask_geometry");
 }
 
@@ -536,6 +507,9 @@ int hdy_process_mask_packed(const float* protos, const float* coef, const float*
     return HDY_ERR_CUDA;
   }
   const float rx = (float)((double)mw / (double)iw), ry = (float)((double)mh / (double)ih);
+  rc = launch_process_mask_regions(protos, coef, boxes, counts, bs, max_det, nm, mh, mw, ih, iw, upsample, rx, ry,
+                                   nullptr, offsets, bits, capacity_words, status, st);
+  if (rc != 1) return rc;
   process_mask_kernel<true><<<(unsigned)((size_t)bs * max_det), kPmThreads, 0, st>>>(
       protos, coef, reinterpret_cast<const float4*>(boxes), counts, max_det, nm, mh, mw, ih, iw, upsample, rx, ry,
       nullptr, offsets, bits, capacity_words, status);

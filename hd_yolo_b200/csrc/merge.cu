@@ -242,7 +242,7 @@ static inline size_t align256(size_t v) { return (v + 255) & ~(size_t)255; }
 
 static int merge_grid_side(long long n_max) {
   int G = 64;
-  while (G < 2048 && (long long)G * G < 2 * n_max) G <<= 1;
+  while (G < 8192 && (long long)G * G < 2 * n_max) G <<= 1;
   return G;
 }
 
@@ -411,7 +411,7 @@ __global__ void __launch_bounds__(kMergeThreads) merge_round_kernel(const float4
   const CellGeom g = cell_geom(stats);
   volatile uint8_t* vstate = cstate;
   int unknown = 0;
-  for (int p = blockIdx.x * blockDim.x + threadIdx.x; p < n_active; p += gridDim.x * blockDim.x) {
+  for (int p = blockIdx.x * blockDim.x + threadIdx.x; p < large_begin; p += gridDim.x * blockDim.x) {
     if (vstate[p] != MS_UNKNOWN) continue;
     const float4 bi = cbox[p];
     const uint64_t ki = ckey[p];
@@ -428,7 +428,7 @@ __global__ void __launch_bounds__(kMergeThreads) merge_round_kernel(const float4
       return false;
     };
     bool done = false;
-    if (p < large_begin) {
+    {
       const float cx = (bi.x + bi.z) * 0.5f, cy = (bi.y + bi.w) * 0.5f;
       const int ix = (int)floorf(cx * g.inv_cell), iy = (int)floorf(cy * g.inv_cell);
 #pragma unroll 1
@@ -446,8 +446,6 @@ __global__ void __launch_bounds__(kMergeThreads) merge_round_kernel(const float4
         }
       }
       for (int q = large_begin; q < large_end && !done; ++q) done = visit(q);
-    } else {
-      for (int q = 0; q < n_active && !done; ++q) done = visit(q);
     }
     if (decided != MS_UNKNOWN)
       vstate[p] = (uint8_t)decided;
@@ -456,6 +454,67 @@ __global__ void __launch_bounds__(kMergeThreads) merge_round_kernel(const float4
   }
   unknown = __syncthreads_count(unknown);
   if (threadIdx.x == 0 && unknown) atomicAdd(&stats->unknown[round], unknown);
+}
+
+// Same round for the entries of the "large" bucket (boxes wider than a cell, or numerically awkward ones): ONE WARP
+// per entry.  A large box can intersect small boxes whose centre lies within half a cell of it, i.e. the cells
+// [floor((x1 - c/2) / cell), floor((x2 + c/2) / cell)] x [same in y]; the lanes share those cells (the whole grid if
+// the range wraps around the torus, the whole array if the coordinates are not finite) and the large bucket.
+__global__ void __launch_bounds__(kMergeThreads) merge_round_large_kernel(const float4* __restrict__ cbox,
+                                                                          const uint64_t* __restrict__ ckey,
+                                                                          uint8_t* cstate, const int* __restrict__ cell,
+                                                                          MergeStats* stats, int G, float thr,
+                                                                          int round) {
+  if (round > 0 && stats->unknown[round - 1] == 0) return;
+  const int NB = G * G + 1;
+  const int n_active = cell[NB - 1];
+  const int large_begin = cell[NB - 2];
+  const CellGeom g = cell_geom(stats);
+  volatile uint8_t* vstate = cstate;
+  const int lane = threadIdx.x & 31;
+  const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, n_warps = (gridDim.x * blockDim.x) >> 5;
+  for (int p = large_begin + warp; p < n_active; p += n_warps) {
+    if (vstate[p] != MS_UNKNOWN) continue;  // warp-uniform
+    const float4 bi = cbox[p];
+    const uint64_t ki = ckey[p];
+    int kept_dom = 0, unk_dom = 0;
+    auto visit = [&](int q) {
+      if (ckey[q] < ki && iou_gt(cbox[q], bi, thr)) {
+        const uint8_t sq = vstate[q];
+        if (sq == MS_KEPT) kept_dom = 1;
+        if (sq == MS_UNKNOWN || sq == MS_REMOTE_UNKNOWN) unk_dom = 1;
+      }
+    };
+    const float half = 0.5f * g.cell_size;
+    const float fx0 = floorf((bi.x - half) * g.inv_cell), fx1 = floorf((bi.z + half) * g.inv_cell);
+    const float fy0 = floorf((bi.y - half) * g.inv_cell), fy1 = floorf((bi.w + half) * g.inv_cell);
+    const bool finite = fabsf(fx0) < 1.0e9f && fabsf(fx1) < 1.0e9f && fabsf(fy0) < 1.0e9f && fabsf(fy1) < 1.0e9f &&
+                        fx1 >= fx0 && fy1 >= fy0;
+    if (!finite) {
+      for (int q = lane; q < large_begin; q += 32) visit(q);
+    } else {
+      const int ix0 = (int)fx0, iy0 = (int)fy0;
+      const int nx = (int)fminf(fx1 - fx0 + 1.0f, (float)G), ny = (int)fminf(fy1 - fy0 + 1.0f, (float)G);
+      const long long cells = (long long)nx * ny;
+      for (long long c = lane; c < cells; c += 32) {
+        const int cy = (int)(c / nx), cx = (int)(c - (long long)cy * nx);
+        const int b = ((ix0 + cx) & (G - 1)) + ((iy0 + cy) & (G - 1)) * G;
+        const int beg = b ? cell[b - 1] : 0, end = cell[b];
+        for (int q = beg; q < end; ++q) visit(q);
+      }
+    }
+    for (int q = large_begin + lane; q < n_active; q += 32) visit(q);
+    kept_dom = __any_sync(0xffffffffu, kept_dom);
+    unk_dom = __any_sync(0xffffffffu, unk_dom);
+    if (lane == 0) {
+      if (kept_dom)
+        vstate[p] = (uint8_t)MS_SUPPRESSED;
+      else if (!unk_dom)
+        vstate[p] = (uint8_t)MS_KEPT;
+      else
+        atomicAdd(&stats->unknown[round], 1);
+    }
+  }
 }
 
 __global__ void merge_finish_kernel(const uint32_t* __restrict__ pos, const uint8_t* __restrict__ cstate,
@@ -689,9 +748,12 @@ int hdy_merge_rounds(void* workspace, int64_t n_max, float iou_thres, int first_
   if (n_max == 0) return HDY_OK;
   MergeWs w = merge_layout(workspace, n_max);
   const unsigned blocks = blocks_for(n_max, kMergeThreads, 148 * 8);
-  for (int r = first_round; r < first_round + n_rounds; ++r)
+  for (int r = first_round; r < first_round + n_rounds; ++r) {
     merge_round_kernel<<<blocks, kMergeThreads, 0, (cudaStream_t)stream>>>(w.cbox, w.ckey, w.cstate, w.cell, w.stats,
                                                                            w.G, iou_thres, r);
+    merge_round_large_kernel<<<148 * 2, kMergeThreads, 0, (cudaStream_t)stream>>>(w.cbox, w.ckey, w.cstate, w.cell,
+                                                                                  w.stats, w.G, iou_thres, r);
+  }
   return check_launch("hdy_merge_rounds");
 }
 

@@ -382,44 +382,59 @@ __global__ void __launch_bounds__(THREADS, 1) nms_tiles_smem_kernel(
   // ---- 3. dominators ----------------------------------------------------------------------------------------
   // begin offsets -> the walker wants [cell[b-1], cell[b]) with cell[-1] = 0: shift view by one
   const int* cell_end = S.cell + 1;  // cell_end[b] = end of bucket b; begin = b ? cell_end[b-1] : 0 (== S.cell[b])
-  for (int p = t; p < n_active; p += THREADS) {
+  for (int p = t; p < large_begin; p += THREADS) {
     const float4 bi = S.cbox[p];
     const int ri = S.crank[p];
     int nd = 0;
-    auto record = [&](int q) -> bool {
+    auto record = [&](int q) {
       if (iou_gt(S.cbox[q], bi, thr)) {
         if (nd < kMaxDom) S.dom[p * kMaxDom + nd] = (uint16_t)q;
         ++nd;
       }
-      return false;
     };
-    if (p < large_begin) {
-      const float cx = (bi.x + bi.z) * 0.5f, cy = (bi.y + bi.w) * 0.5f;
-      const int ix = (int)floorf(cx * g.inv_cell), iy = (int)floorf(cy * g.inv_cell);
+    const float cx = (bi.x + bi.z) * 0.5f, cy = (bi.y + bi.w) * 0.5f;
+    const int ix = (int)floorf(cx * g.inv_cell), iy = (int)floorf(cy * g.inv_cell);
 #pragma unroll 1
-      for (int dy = -1; dy <= 1; ++dy) {
-        const int rowb = ((iy + dy) & (kFastG - 1)) * kFastG;
+    for (int dy = -1; dy <= 1; ++dy) {
+      const int rowb = ((iy + dy) & (kFastG - 1)) * kFastG;
 #pragma unroll 1
-        for (int dx = -1; dx <= 1; ++dx) {
-          const int b = ((ix + dx) & (kFastG - 1)) + rowb;
-          const int beg = S.cell[b], end = cell_end[b];
-          for (int q = beg; q < end; ++q) {
-            if ((int)S.crank[q] >= ri) {
-              if (sorted) break;
-              continue;
-            }
-            record(q);
+      for (int dx = -1; dx <= 1; ++dx) {
+        const int b = ((ix + dx) & (kFastG - 1)) + rowb;
+        const int beg = S.cell[b], end = cell_end[b];
+        for (int q = beg; q < end; ++q) {
+          if ((int)S.crank[q] >= ri) {
+            if (sorted) break;
+            continue;
           }
+          record(q);
         }
       }
-      for (int q = large_begin; q < n_active; ++q)
-        if ((int)S.crank[q] < ri) record(q);
-    } else {
-      for (int q = 0; q < n_active; ++q)
-        if ((int)S.crank[q] < ri) record(q);
     }
+    for (int q = large_begin; q < n_active; ++q)
+      if ((int)S.crank[q] < ri) record(q);
     S.ndom[p] = (uint8_t)min(nd, 255);
     S.state[p] = nd ? FS_UNKNOWN : FS_KEPT;
+  }
+  // entries of the "large" bucket can intersect anything: the whole CTA scans the tile for each of them (there are
+  // none for nuclei-sized boxes; a serial scan by one thread would take longer than the rest of the kernel)
+  for (int p = large_begin; p < n_active; ++p) {
+    __syncthreads();
+    if (t == 0) S.flags[1] = 0;
+    __syncthreads();
+    const float4 bi = S.cbox[p];
+    const int ri = S.crank[p];
+    for (int q = t; q < n_active; q += THREADS) {
+      if ((int)S.crank[q] < ri && iou_gt(S.cbox[q], bi, thr)) {
+        const int k = atomicAdd(&S.flags[1], 1);
+        if (k < kMaxDom) S.dom[p * kMaxDom + k] = (uint16_t)q;
+      }
+    }
+    __syncthreads();
+    if (t == 0) {
+      const int nd = S.flags[1];
+      S.ndom[p] = (uint8_t)min(nd, 255);
+      S.state[p] = nd ? FS_UNKNOWN : FS_KEPT;
+    }
   }
   __syncthreads();
   mark(4);
@@ -442,6 +457,8 @@ __global__ void __launch_bounds__(THREADS, 1) nms_tiles_smem_kernel(
           }
           if (sq == FS_UNKNOWN) decided = FS_UNKNOWN;
         }
+      } else if (p >= large_begin) {
+        continue;  // overflowed large entry: resolved by the whole CTA below
       } else {
         // more dominators than slots: walk the neighbourhood again
         const float4 bi = S.cbox[p];
@@ -457,38 +474,55 @@ __global__ void __launch_bounds__(THREADS, 1) nms_tiles_smem_kernel(
           }
           return false;
         };
-        if (p < large_begin) {
-          const float cx = (bi.x + bi.z) * 0.5f, cy = (bi.y + bi.w) * 0.5f;
-          const int ix = (int)floorf(cx * g.inv_cell), iy = (int)floorf(cy * g.inv_cell);
-          bool done = false;
+        const float cx = (bi.x + bi.z) * 0.5f, cy = (bi.y + bi.w) * 0.5f;
+        const int ix = (int)floorf(cx * g.inv_cell), iy = (int)floorf(cy * g.inv_cell);
+        bool done = false;
 #pragma unroll 1
-          for (int dy = -1; dy <= 1 && !done; ++dy) {
-            const int rowb = ((iy + dy) & (kFastG - 1)) * kFastG;
+        for (int dy = -1; dy <= 1 && !done; ++dy) {
+          const int rowb = ((iy + dy) & (kFastG - 1)) * kFastG;
 #pragma unroll 1
-            for (int dx = -1; dx <= 1 && !done; ++dx) {
-              const int b = ((ix + dx) & (kFastG - 1)) + rowb;
-              const int beg = S.cell[b], end = cell_end[b];
-              for (int q = beg; q < end && !done; ++q) {
-                if ((int)S.crank[q] >= ri) {
-                  if (sorted) break;
-                  continue;
-                }
-                done = visit(q);
+          for (int dx = -1; dx <= 1 && !done; ++dx) {
+            const int b = ((ix + dx) & (kFastG - 1)) + rowb;
+            const int beg = S.cell[b], end = cell_end[b];
+            for (int q = beg; q < end && !done; ++q) {
+              if ((int)S.crank[q] >= ri) {
+                if (sorted) break;
+                continue;
               }
+              done = visit(q);
             }
           }
-          for (int q = large_begin; q < n_active && !done; ++q)
-            if ((int)S.crank[q] < ri) done = visit(q);
-        } else {
-          bool done = false;
-          for (int q = 0; q < n_active && !done; ++q)
-            if ((int)S.crank[q] < ri) done = visit(q);
         }
+        for (int q = large_begin; q < n_active && !done; ++q)
+          if ((int)S.crank[q] < ri) done = visit(q);
       }
       if (decided != FS_UNKNOWN)
         vstate[p] = (uint8_t)decided;
       else
         unknown = 1;
+    }
+    for (int p = large_begin; p < n_active; ++p) {  // overflowed large entries, one at a time, all threads
+      __syncthreads();
+      if (S.ndom[p] <= kMaxDom || vstate[p] != FS_UNKNOWN) continue;  // uniform: only thread 0 writes these, below
+      const float4 bi = S.cbox[p];
+      const int ri = S.crank[p];
+      int kept_dom = 0, unk_dom = 0;
+      for (int q = t; q < n_active; q += THREADS) {
+        if ((int)S.crank[q] < ri && iou_gt(S.cbox[q], bi, thr)) {
+          const uint8_t sq = vstate[q];
+          kept_dom |= sq == FS_KEPT;
+          unk_dom |= sq == FS_UNKNOWN;
+        }
+      }
+      kept_dom = __syncthreads_or(kept_dom);
+      unk_dom = __syncthreads_or(unk_dom);
+      if (kept_dom) {
+        if (t == 0) vstate[p] = FS_SUPPRESSED;
+      } else if (!unk_dom) {
+        if (t == 0) vstate[p] = FS_KEPT;
+      } else {
+        unknown = 1;
+      }
     }
     ++rounds;
     if (!__syncthreads_or(unknown)) break;

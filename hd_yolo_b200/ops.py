@@ -29,6 +29,7 @@ __all__ = [
     "batched_nms",
     "detect_postprocess",
     "DetectBatch",
+    "flatten_onehot_objects",
 ]
 
 # ----------------------------------------------------------------------------- thresholds
@@ -507,3 +508,23 @@ def detect_postprocess(dets: List[torch.Tensor], spec: HeadSpec, conf_thres: flo
     _call("hdy_select_scores", ptr(scores_full), ptr(keep_counts), bs, md, nc, flat, len(ops), cthr, ptr(score),
                               ptr(label), _stream())
     return DetectBatch(keep_box, scores_full, score, label, lvl, extra, keep_idx, keep_counts, cand.counts, md)
+
+
+def flatten_onehot_objects(x: Dict[str, torch.Tensor]) -> Dict[str, torch.Tensor]:
+    """flatten_onehot_objects (val_nuclei.py:34-48), caller-side glue for multi_label outputs: one row per set bit
+    of the boolean 'labels' [k, 1+nc]; the row's label is the bit's column (column 0, objectness, becomes -100);
+    boxes / masks are repeated, 'scores' [k, 1+nc] is read at the same (row, column).  Index arithmetic only, so it
+    stays in PyTorch like the reference; no [k*(1+nc), ...] intermediate is materialised."""
+    lab = x['labels']
+    assert lab.dim() == 2, f"labels has shape: {lab.shape}, need an one hot tensor."
+    row, col = torch.nonzero(lab > 0., as_tuple=True)       # row-major order == flatten()[keep] order
+    res = {k: v for k, v in x.items()}
+    labels = col.clone()
+    labels[col == 0] = -100
+    res['labels'] = labels
+    res['boxes'] = x['boxes'][row]
+    if 'scores' in x:
+        res['scores'] = x['scores'][row, col]
+    if 'masks' in x:
+        res['masks'] = x['masks'][row]
+    return res

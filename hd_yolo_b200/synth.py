@@ -44,3 +44,64 @@ def nuclei_logits(bs: int, tile: int, nc: int, n_cand: int, seed: int, anchors=A
         d[..., 2:4] = torch.log(sig / (1 - sig))
         dets.append(d.contiguous())
     return dets
+
+
+# ------------------------------------------------------------------------------------------------ whole slide
+def slide_tile_logits(rois: torch.Tensor, tile: int, nc: int, seed: int, pitch: float = 18.7, extra: int = 0,
+                      conf: float = 0.25, size_range=(12.0, 30.0), strides=STRIDES_3, anchors=ANCHORS_3,
+                      device="cuda", background_mu: float = -6.0):
+    """Raw head logits for a batch of slide tiles (rois [bs,4] = x0,y0,x1,y1 from sliding_window_scanner) cut from
+    ONE global nuclei field (cfg 4): nuclei sit on a jittered grid of `pitch` px over the whole slide
+    (~3 000 per 1024^2 tile); a nucleus is a pure function of its grid index, so the tiles that share an overlap band
+    report the same nucleus with the same box (up to fp32 rounding of the tile-local decode) and a tile-dependent
+    score jitter -- consistent duplicates for the merge NMS.  Every nucleus is written into the stride-8 level at the
+    cell holding its centre, anchor chosen by size; all other rows are background (objectness logit ~ N(mu,1), far
+    below the threshold).  Edge tiles (clipped windows) simply contain fewer nuclei.  Returns the level tensors
+    [bs,na,ny,nx,5+nc+extra]."""
+    bs = rois.shape[0]
+    dev = torch.device(device)
+    g = torch.Generator(device=dev).manual_seed(seed)
+    na = len(anchors[0]) // 2
+    no = 5 + nc + extra
+    shapes = level_shapes(tile, strides)
+    dets = []
+    for (ny, nx) in shapes:
+        d = torch.randn((bs, na, ny, nx, no), generator=g, device=dev)
+        d[..., 4] += background_mu
+        dets.append(d)
+    rois = rois.to(dev, torch.float32)
+    s0 = float(strides[0])
+    a0 = torch.tensor(anchors[0], dtype=torch.float32, device=dev).view(na, 2)
+    ncell = int(math.ceil(tile / pitch)) + 1
+    for b in range(bs):
+        x0, y0, x1, y1 = [float(v) for v in rois[b]]
+        i0, j0 = int(math.floor(x0 / pitch)), int(math.floor(y0 / pitch))
+        ii = torch.arange(i0, i0 + ncell, device=dev, dtype=torch.int64)
+        jj = torch.arange(j0, j0 + ncell, device=dev, dtype=torch.int64)
+        J, I = torch.meshgrid(jj, ii, indexing='ij')
+        # hash (I, J) -> four uniforms in [0,1): pure function of the grid index
+        h = (I * 73856093) ^ (J * 19349663)
+
+        def u(k):
+            v = (h * (2 * k + 1) + 0x9E3779B9 * (k + 1)) & 0x7fffffff
+            v = (v * 1103515245 + 12345) & 0x7fffffff
+            return (v >> 7).to(torch.float32) / float(1 << 24)
+        cx = (I.float() + 0.15 + 0.7 * u(0)) * pitch
+        cy = (J.float() + 0.15 + 0.7 * u(1)) * pitch
+        side = size_range[0] + (size_range[1] - size_range[0]) * u(2)
+        score = 0.3 + 0.65 * u(3)
+        inside = (cx >= x0) & (cx < x1) & (cy >= y0) & (cy < y1)
+        cx, cy, side, score = cx[inside] - x0, cy[inside] - y0, side[inside], score[inside]
+        if cx.numel() == 0:
+            continue
+        gx = torch.clamp((cx / s0).floor().long(), 0, shapes[0][1] - 1)
+        gy = torch.clamp((cy / s0).floor().long(), 0, shapes[0][0] - 1)
+        a = torch.where(side < 14.0, 0, torch.where(side < 23.0, 1, 2)).long()
+        sx = ((cx / s0 - gx.float()) + 0.5) / 2.0
+        sy = ((cy / s0 - gy.float()) + 0.5) / 2.0
+        sw = (side / a0[a, 0]).sqrt() / 2.0
+        sh = (side / a0[a, 1]).sqrt() / 2.0
+        sc = (score + 0.04 * (torch.rand(score.shape, generator=g, device=dev) - 0.5)).clamp(conf + 0.02, 0.99)
+        sig = torch.stack([sx, sy, sw, sh, sc], 1).clamp(0.02, 0.98)
+        dets[0][b, a, gy, gx, :5] = torch.log(sig / (1 - sig))
+    return [d.contiguous() for d in dets]

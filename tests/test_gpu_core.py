@@ -340,3 +340,27 @@ def test_full_size_properties(cuda_device, tile, bs, n_cand, md):
     assert torch.equal(out.boxes[0, :k].cpu(), ref['boxes'])
     assert torch.equal(out.labels[0, :k].cpu(), ref['labels'])
     assert torch.equal(out.scores[0, :k].cpu(), ref['scores'])
+
+
+@pytest.mark.parametrize("n_small,n_large,seed", [(2500, 40, 0), (3500, 6, 1), (800, 200, 2)])
+def test_nms_small_nuclei_with_large_boxes(cuda_device, n_small, n_large, seed):
+    """Nuclei-sized boxes plus clusters of near-identical LARGE boxes (the "large" bucket of the per-tile kernel, which
+    the whole CTA scans; clusters of > 4 make their dominator lists overflow) vs torchvision.ops.nms."""
+    import torchvision
+    g = torch.Generator().manual_seed(seed)
+    c = torch.rand((n_small, 2), generator=g) * 1000
+    s = 12 + 24 * torch.rand((n_small, 2), generator=g)
+    small = torch.cat([c - s / 2, c + s / 2], 1)
+    centers = torch.rand((max(n_large // 8, 1), 2), generator=g) * 600 + 200
+    which = torch.randint(0, len(centers), (n_large,), generator=g)
+    lc = centers[which] + 6 * torch.rand((n_large, 2), generator=g)
+    ls = 250 + 30 * torch.rand((n_large, 2), generator=g)
+    large = torch.cat([lc - ls / 2, lc + ls / 2], 1)
+    boxes = torch.cat([small, large])
+    scores = torch.rand((len(boxes),), generator=g)
+    perm = torch.randperm(len(boxes), generator=g)
+    boxes, scores = boxes[perm].contiguous(), scores[perm].contiguous()
+    for thr in (0.45, 0.7):
+        ref = torchvision.ops.nms(boxes, scores, thr)
+        got = hdy.nms(boxes.to(cuda_device), scores.to(cuda_device), thr).cpu()
+        assert torch.equal(got, ref)

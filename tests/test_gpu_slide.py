@@ -167,3 +167,32 @@ def test_scale_clip_rescale_vs_oracle(cuda_device):
     wide = coords.clone().to(cuda_device)
     hs.clip_coords(wide[:, :4], (300, 500))
     assert torch.equal(wide[:, :4].cpu(), b) and torch.equal(wide[:, 4:].cpu(), coords[:, 4:])
+
+
+@pytest.mark.parametrize("n_small,n_large,seed", [(20000, 60, 0), (5000, 400, 1)])
+def test_merge_nms_with_large_boxes(cuda_device, n_small, n_large, seed):
+    """Slide-level merge with boxes far wider than a hash cell (the warp-per-entry kernel of csrc/merge.cu) vs
+    torchvision.ops.nms on the same rows (Ensemble.merge, yolo.py:189-195)."""
+    import torchvision
+    g = torch.Generator().manual_seed(seed)
+    c = torch.rand((n_small, 2), generator=g) * 4000
+    s = 12 + 24 * torch.rand((n_small, 2), generator=g)
+    small = torch.cat([c - s / 2, c + s / 2], 1)
+    centers = torch.rand((max(n_large // 6, 1), 2), generator=g) * 3000 + 500
+    which = torch.randint(0, len(centers), (n_large,), generator=g)
+    lc = centers[which] + 10 * torch.rand((n_large, 2), generator=g)
+    ls = 100 + 900 * torch.rand((n_large, 1), generator=g) + 20 * torch.rand((n_large, 2), generator=g)
+    large = torch.cat([lc - ls / 2, lc + ls / 2], 1)
+    boxes = torch.cat([small, large])
+    scores = torch.rand((len(boxes),), generator=g)
+    perm = torch.randperm(len(boxes), generator=g)
+    boxes, scores = boxes[perm].contiguous(), scores[perm].contiguous()
+    conf, iou = 0.1, 0.45
+    keep = scores > conf
+    idx = torch.nonzero(keep).flatten()
+    kept = idx[torchvision.ops.nms(boxes[idx], scores[idx], iou)]
+    ref = torch.full((len(scores),), 2, dtype=torch.uint8)
+    ref[~keep] = 3
+    ref[kept] = 1
+    got = hdy.merge_nms(boxes.to(cuda_device), scores.to(cuda_device), conf, iou).cpu()
+    assert torch.equal(got, ref)

@@ -160,3 +160,21 @@ def test_synth_candidate_count():
     assert ((n > 170) & (n < 330)).all()
     boxes = cat[..., 2:4][cat[..., 4] > 0.25]
     assert boxes.min() > 9 and boxes.max() < 40
+
+
+def test_flatten_onehot_objects_matches_reference_formulation():
+    """val_nuclei.py:34-48 restated with tile/repeat_interleave (the reference's formulation) vs the mirror."""
+    import torch
+    from hd_yolo_b200.ops import flatten_onehot_objects
+    g = torch.Generator().manual_seed(3)
+    k, nc1 = 37, 5
+    x = {'labels': torch.rand((k, nc1), generator=g) > 0.6, 'boxes': torch.rand((k, 4), generator=g),
+         'scores': torch.rand((k, nc1), generator=g), 'masks': torch.rand((k, 1, 7, 7), generator=g)}
+    keep = x['labels'].flatten() > 0.
+    ref_labels = torch.tile(torch.arange(nc1), (k,))[keep]
+    ref_labels[ref_labels == 0] = -100
+    got = flatten_onehot_objects(x)
+    assert torch.equal(got['labels'], ref_labels)
+    assert torch.equal(got['boxes'], torch.repeat_interleave(x['boxes'], nc1, 0)[keep])
+    assert torch.equal(got['scores'], x['scores'].flatten()[keep])
+    assert torch.equal(got['masks'], torch.repeat_interleave(x['masks'], nc1, 0)[keep])
