@@ -31,19 +31,32 @@ constexpr int kRegRX = 20;          // first-tap columns owned per region: the T
 constexpr int kRegNm = 32;
 constexpr int kRegThreads = 256;
 constexpr int kRegWarps = kRegThreads / 32;
-constexpr int kRegList = 1024;      // detections examined per pass
-constexpr int kRowTab = 96;         // output rows interpolated per pass
+constexpr int kRegList = 512;       // detections examined per pass
+constexpr int kRegBatch = 64;       // listed detections prepared (records + coefficients) at a time
+constexpr int kRowTab = 48;         // output rows interpolated per pass
 
 struct RowTab {
   int off0, off1;  // patch offsets of the two source rows
   float l0, l1;
 };
 
+// Everything about one (detection, region) piece that is the same for all lanes, computed once by ONE thread of the
+// prepare step instead of redundantly by the 32 lanes of the warp that processes the piece.
+struct PieceRec {
+  int d, gx0, gy0, gw;          // detection slot inside the tile; output window origin and width
+  int px0, px1, py0, py1;       // kept proto pixels [p0, p1)
+  float x1d, x2d, y1d, y2d;     // down-scaled box (crop test)
+  int ox_lo, ox_hi, oy_lo, oy_hi;  // output pixels this region produces
+  long long off;                // first word of the mask's bit plane
+  int live, pad;
+};
+
 struct RegSmem {
   float proto[kRegNm][kRegBox][kRegBox];       // TMA destination (dense, x fastest)
   float patch[kRegWarps][kRegBox * kRegBox];   // cropped sigmoid values, staged coordinates
   RowTab rows[kRegWarps][kRowTab];
-  float coef[kRegWarps][kRegNm];
+  PieceRec rec[kRegBatch];
+  float coef[kRegBatch][kRegNm];
   uint16_t list[kRegList];
   int nlist;
   int pad;
@@ -59,16 +72,15 @@ __device__ __forceinline__ void tma_load_4d(void* dst, const CUtensorMap* map, i
       : "memory");
 }
 
-// smallest o in [lo, hi] whose first tap is >= target (hi if there is none); i0 is non-decreasing in o
+// smallest o in [lo, hi] whose first tap is >= target (hi if there is none); i0 is non-decreasing in o.
+// Closed-form guess from src = scale*(o+0.5)-0.5, then exact fix-up against lerp_coord itself.
 __device__ __forceinline__ int first_tap_ge(int target, int lo, int hi, float scale, int in_size) {
-  while (lo < hi) {
-    const int m = (lo + hi) >> 1;
-    if (lerp_coord(m, scale, in_size).i0 >= target)
-      hi = m;
-    else
-      lo = m + 1;
-  }
-  return lo;
+  if (target <= 0) return lo;
+  int o = (int)ceilf(((float)target + 0.5f) / scale - 0.5f);
+  o = max(lo, min(hi, o));
+  while (o > lo && lerp_coord(o - 1, scale, in_size).i0 >= target) --o;
+  while (o < hi && lerp_coord(o, scale, in_size).i0 < target) ++o;
+  return o;
 }
 
 template <bool PACKED, bool UPSAMPLE>
@@ -117,139 +129,192 @@ __global__ void __launch_bounds__(kRegThreads, 2) process_mask_regions_kernel(
     }
     __syncthreads();
     const int nl = S.nlist;
-    if (!loaded) {
-      while (!mbar_try_wait(&S.bar, 0)) {
+
+    for (int b0 = 0; b0 < nl; b0 += kRegBatch) {
+      const int nb = min(kRegBatch, nl - b0);
+      // ---- prepare: one thread per piece computes its record; everybody fetches the coefficients
+      if (t < nb) {
+        PieceRec R;
+        R.d = base + S.list[b0 + t];
+        const size_t slot = (size_t)tile * max_det + R.d;
+        const PMGeom g = pm_geometry(boxes[slot], mh, mw, ih, iw, UPSAMPLE ? 1 : 0, rx, ry);
+        R.gx0 = g.x0;
+        R.gy0 = g.y0;
+        R.gw = g.w;
+        R.px0 = g.px0;
+        R.px1 = g.px1;
+        R.py0 = g.py0;
+        R.py1 = g.py1;
+        R.x1d = g.x1d;
+        R.x2d = g.x2d;
+        R.y1d = g.y1d;
+        R.y2d = g.y2d;
+        R.live = g.w > 0 && g.h > 0;
+        R.off = 0;
+        R.pad = 0;
+        if (UPSAMPLE) {
+          const int tx_lo = max(g.px0 - 1, X0), tx_hi = min(g.px1, X0 + kRegRX);  // first taps [tx_lo, tx_hi)
+          const int ty_lo = max(g.py0 - 1, Y0), ty_hi = min(g.py1, Y0 + kRegRY);
+          R.ox_lo = first_tap_ge(tx_lo, g.x0, g.x0 + g.w, sxs, mw);
+          R.ox_hi = first_tap_ge(tx_hi, g.x0, g.x0 + g.w, sxs, mw);
+          R.oy_lo = first_tap_ge(ty_lo, g.y0, g.y0 + g.h, sys, mh);
+          R.oy_hi = first_tap_ge(ty_hi, g.y0, g.y0 + g.h, sys, mh);
+        } else {  // output pixel == proto pixel; this region owns [X0, X0+RX) x [Y0, Y0+RY)
+          R.ox_lo = max(g.px0, X0);
+          R.ox_hi = min(g.px1, X0 + kRegRX);
+          R.oy_lo = max(g.py0, Y0);
+          R.oy_hi = min(g.py1, Y0 + kRegRY);
+        }
+        if (R.ox_hi <= R.ox_lo || R.oy_hi <= R.oy_lo) R.live = 0;
+        if (PACKED && R.live) {
+          R.off = offsets[slot];
+          if (R.off + (long long)((g.w + 31) >> 5) * g.h > capacity_words) {
+            atomicOr(status, HDY_STATUS_OVERFLOW);
+            R.live = 0;
+          }
+        }
+        S.rec[t] = R;
       }
-      loaded = true;
-    }
-    // ---- one warp per listed detection
-    for (int e = warp; e < nl; e += kRegWarps) {
-      const int d = base + S.list[e];
-      const size_t slot = (size_t)tile * max_det + d;
-      const PMGeom g = pm_geometry(boxes[slot], mh, mw, ih, iw, UPSAMPLE ? 1 : 0, rx, ry);
-      if (g.w <= 0 || g.h <= 0) continue;
-      const int wpr = (g.w + 31) >> 5;
-      long long off = 0;
-      if (PACKED) {
-        off = offsets[slot];
-        if (off + (long long)wpr * g.h > capacity_words) {
-          if (lane == 0) atomicOr(status, HDY_STATUS_OVERFLOW);
+      for (int i = t; i < nb * kRegNm; i += kRegThreads) {
+        const int e = i / kRegNm, c = i - e * kRegNm;
+        S.coef[e][c] = coef[((size_t)tile * max_det + base + S.list[b0 + e]) * kRegNm + c];
+      }
+      __syncthreads();
+      if (!loaded) {
+        while (!mbar_try_wait(&S.bar, 0)) {
+        }
+        loaded = true;
+      }
+
+      // ---- one warp per piece
+      for (int e = warp; e < nb; e += kRegWarps) {
+        const PieceRec& R = S.rec[e];
+        if (!R.live) continue;
+        const size_t slot = (size_t)tile * max_det + R.d;
+        const int wpr = (R.gw + 31) >> 5;
+        float cf[kRegNm];
+#pragma unroll
+        for (int c = 0; c < kRegNm; c += 4) {
+          const float4 v = *reinterpret_cast<const float4*>(&S.coef[e][c]);
+          cf[c] = v.x;
+          cf[c + 1] = v.y;
+          cf[c + 2] = v.z;
+          cf[c + 3] = v.w;
+        }
+        // ---- cropped sigmoid(coef . proto) on the part of the box (+ halo) inside the staged box; lanes cover
+        //      floor(32 / pw) patch rows at a time
+        const int wx0 = max(R.px0 - HALO, X0), wx1 = min(R.px1 + HALO, X0 + kRegRX + HALO);
+        const int wy0 = max(R.py0 - HALO, Y0), wy1 = min(R.py1 + HALO, Y0 + kRegRY + HALO);
+        const int pw = wx1 - wx0;
+        if (pw <= 0 || wy1 <= wy0) continue;
+        {
+          const int rows_per = 32 / pw;  // pw <= 24
+          const int ly = lane / pw, lx = lane - ly * pw;
+          const int xx = wx0 + lx, sx = xx - X0;
+          const bool col_ok = ly < rows_per;
+          const bool x_in = xx < mw && (float)xx >= R.x1d && (float)xx < R.x2d;
+          __syncwarp();
+          for (int yy = wy0 + ly; yy < wy1; yy += rows_per) {
+            if (!col_ok) break;
+            const int sy = yy - Y0;
+            float v = 0.f;
+            if (x_in && yy < mh && (float)yy >= R.y1d && (float)yy < R.y2d) {
+              float acc = 0.f;
+#pragma unroll
+              for (int c = 0; c < kRegNm; ++c) acc = fmaf(cf[c], S.proto[c][sy][sx], acc);
+              v = sigmoidf_ref(acc);
+            }
+            patch[sy * kRegBox + sx] = v;
+          }
+          __syncwarp();
+        }
+
+        const int w_lo = (R.ox_lo - R.gx0) >> 5, w_hi = (R.ox_hi - 1 - R.gx0) >> 5;
+        if (!UPSAMPLE) {
+          for (int w = w_lo; w <= w_hi; ++w) {
+            const int xx = R.gx0 + (w << 5) + lane;
+            const bool valid = xx >= R.ox_lo && xx < R.ox_hi;
+            const bool full = (R.gx0 + (w << 5) >= R.ox_lo) && (min(R.gx0 + (w << 5) + 32, R.gx0 + R.gw) <= R.ox_hi);
+            for (int yy = R.oy_lo; yy < R.oy_hi; ++yy) {
+              const bool bit = valid && patch[(yy - Y0) * kRegBox + (valid ? xx - X0 : 0)] > 0.5f;
+              if (PACKED) {
+                const unsigned word = __ballot_sync(0xffffffffu, bit);
+                if (lane == 0) {
+                  uint32_t* dst = bits + R.off + (long long)(yy - R.gy0) * wpr + w;
+                  if (full)
+                    *dst = word;
+                  else if (word)
+                    atomicOr(dst, word);
+                }
+              } else if (valid) {
+                out_dense[slot * oh * ow + (size_t)yy * ow + xx] = bit ? 1.f : 0.f;
+              }
+            }
+          }
           continue;
         }
-      }
-      __syncwarp();
-      S.coef[warp][lane] = coef[slot * kRegNm + lane];
-      __syncwarp();
-      float cf[kRegNm];
-#pragma unroll
-      for (int c = 0; c < kRegNm; c += 4) {
-        const float4 v = *reinterpret_cast<const float4*>(&S.coef[warp][c]);
-        cf[c] = v.x;
-        cf[c + 1] = v.y;
-        cf[c + 2] = v.z;
-        cf[c + 3] = v.w;
-      }
-      // ---- cropped sigmoid(coef . proto) on the part of the box (+ halo) inside the staged box
-      const int wx0 = max(g.px0 - HALO, X0), wx1 = min(g.px1 + HALO, X0 + kRegRX + HALO);
-      const int wy0 = max(g.py0 - HALO, Y0), wy1 = min(g.py1 + HALO, Y0 + kRegRY + HALO);
-      const int pw = wx1 - wx0, ph = wy1 - wy0;
-      if (pw <= 0 || ph <= 0) continue;
-      for (int i = lane; i < pw * ph; i += 32) {
-        const int yy = wy0 + i / pw, xx = wx0 + i % pw;
-        const int sy = yy - Y0, sx = xx - X0;
-        float v = 0.f;
-        if (yy < mh && xx < mw && (float)xx >= g.x1d && (float)xx < g.x2d && (float)yy >= g.y1d &&
-            (float)yy < g.y2d) {
-          float acc = 0.f;
-#pragma unroll
-          for (int c = 0; c < kRegNm; ++c) acc = fmaf(cf[c], S.proto[c][sy][sx], acc);
-          v = sigmoidf_ref(acc);
-        }
-        patch[sy * kRegBox + sx] = v;
-      }
-      __syncwarp();
 
-      if (!UPSAMPLE) {
-        // output pixel == proto pixel; this region owns [X0, X0+R) x [Y0, Y0+R)
-        const int x_lo = max(g.px0, X0), x_hi = min(g.px1, X0 + kRegRX);
-        const int y_lo = max(g.py0, Y0), y_hi = min(g.py1, Y0 + kRegRY);
-        if (x_hi <= x_lo || y_hi <= y_lo) continue;
-        const int w_lo = (x_lo - g.x0) >> 5, w_hi = (x_hi - 1 - g.x0) >> 5;
-        for (int w = w_lo; w <= w_hi; ++w) {
-          const int xx = g.x0 + (w << 5) + lane;
-          const bool valid = xx >= x_lo && xx < x_hi;
-          const bool full = (g.x0 + (w << 5) >= x_lo) && (min(g.x0 + (w << 5) + 32, g.x0 + g.w) <= x_hi);
-          for (int yy = y_lo; yy < y_hi; ++yy) {
-            const bool bit = valid && patch[(yy - Y0) * kRegBox + (valid ? xx - X0 : 0)] > 0.5f;
-            if (PACKED) {
-              const unsigned word = __ballot_sync(0xffffffffu, bit);
-              if (lane == 0) {
-                uint32_t* dst = bits + off + (long long)(yy - g.y0) * wpr + w;
-                if (full)
-                  *dst = word;
-                else if (word)
-                  atomicOr(dst, word);
-              }
-            } else if (valid) {
-              out_dense[slot * oh * ow + (size_t)yy * ow + xx] = bit ? 1.f : 0.f;
-            }
+        // ---- upsample: output pixels whose first tap lies in this region and sees the box
+        for (int r0 = R.oy_lo; r0 < R.oy_hi; r0 += kRowTab) {
+          const int nr = min(kRowTab, R.oy_hi - r0);
+          __syncwarp();
+          for (int r = lane; r < nr; r += 32) {
+            const Lerp Y = lerp_coord(r0 + r, sys, mh);
+            RowTab T;
+            T.off0 = (Y.i0 - Y0) * kRegBox;
+            T.off1 = (Y.i1 - Y0) * kRegBox;
+            T.l0 = Y.l0;
+            T.l1 = Y.l1;
+            rowtab[r] = T;
           }
-        }
-        continue;
-      }
-
-      // ---- upsample: output pixels whose first tap lies in this region and sees the box
-      const int tx_lo = max(g.px0 - 1, X0), tx_hi = min(g.px1, X0 + kRegRX);  // first taps [tx_lo, tx_hi)
-      const int ty_lo = max(g.py0 - 1, Y0), ty_hi = min(g.py1, Y0 + kRegRY);
-      const int ox_lo = first_tap_ge(tx_lo, g.x0, g.x0 + g.w, sxs, mw), ox_hi = first_tap_ge(tx_hi, g.x0, g.x0 + g.w, sxs, mw);
-      const int oy_lo = first_tap_ge(ty_lo, g.y0, g.y0 + g.h, sys, mh), oy_hi = first_tap_ge(ty_hi, g.y0, g.y0 + g.h, sys, mh);
-      if (ox_hi <= ox_lo || oy_hi <= oy_lo) continue;
-      const int w_lo = (ox_lo - g.x0) >> 5, w_hi = (ox_hi - 1 - g.x0) >> 5;
-      for (int r0 = oy_lo; r0 < oy_hi; r0 += kRowTab) {
-        const int nr = min(kRowTab, oy_hi - r0);
-        __syncwarp();
-        for (int r = lane; r < nr; r += 32) {
-          const Lerp Y = lerp_coord(r0 + r, sys, mh);
-          RowTab R;
-          R.off0 = (Y.i0 - Y0) * kRegBox;
-          R.off1 = (Y.i1 - Y0) * kRegBox;
-          R.l0 = Y.l0;
-          R.l1 = Y.l1;
-          rowtab[r] = R;
-        }
-        __syncwarp();
-        for (int w = w_lo; w <= w_hi; ++w) {
-          const int ox = g.x0 + (w << 5) + lane;
-          const bool valid = ox >= ox_lo && ox < ox_hi;
-          const bool full = (g.x0 + (w << 5) >= ox_lo) && (min(g.x0 + (w << 5) + 32, g.x0 + g.w) <= ox_hi);
-          const Lerp X = lerp_coord(valid ? ox : ox_lo, sxs, mw);
-          const int xi0 = X.i0 - X0, xi1 = X.i1 - X0;
-          uint32_t* dst = bits + off + (long long)(r0 - g.y0) * wpr + w;
-          float* dd = out_dense + slot * oh * ow + (size_t)r0 * ow + ox;
-#pragma unroll 2
-          for (int r = 0; r < nr; ++r) {
-            const float4 rt = *reinterpret_cast<const float4*>(&rowtab[r]);
-            const int o0 = __float_as_int(rt.x), o1 = __float_as_int(rt.y);
-            Lerp Y;
-            Y.i0 = Y.i1 = 0;
-            Y.l0 = rt.z;
-            Y.l1 = rt.w;
-            const float v = bilerp(patch[o0 + xi0], patch[o0 + xi1], patch[o1 + xi0], patch[o1 + xi1], X, Y);
-            const bool bit = valid && v > 0.5f;
-            if (PACKED) {
-              const unsigned word = __ballot_sync(0xffffffffu, bit);
-              if (lane == 0) {
-                if (full)
-                  dst[(long long)r * wpr] = word;
-                else if (word)
-                  atomicOr(dst + (long long)r * wpr, word);
+          __syncwarp();
+          for (int w = w_lo; w <= w_hi; ++w) {
+            const int ox = R.gx0 + (w << 5) + lane;
+            const bool valid = ox >= R.ox_lo && ox < R.ox_hi;
+            const bool full = (R.gx0 + (w << 5) >= R.ox_lo) && (min(R.gx0 + (w << 5) + 32, R.gx0 + R.gw) <= R.ox_hi);
+            const Lerp X = lerp_coord(valid ? ox : R.ox_lo, sxs, mw);
+            const float* p0 = patch + (X.i0 - X0);
+            const float* p1 = patch + (X.i1 - X0);
+            uint32_t* dst = bits + R.off + (long long)(r0 - R.gy0) * wpr + w;
+            float* dd = out_dense + slot * oh * ow + (size_t)r0 * ow + ox;
+            // An output row needs top = l0x*v00 + l1x*v01 of source row i0 and bot of source row i1; several output
+            // rows share a source row (4 at the usual 4x upsample), so both are kept until the row table moves on.
+            int prev0 = -1, prev1 = -1;
+            float top = 0.f, bot = 0.f;
+            unsigned myword = 0;
+            for (int r = 0; r < nr; ++r) {
+              const float4 rt = *reinterpret_cast<const float4*>(&rowtab[r]);
+              const int o0 = __float_as_int(rt.x), o1 = __float_as_int(rt.y);
+              if (o0 != prev0) {  // warp-uniform
+                top = __fadd_rn(__fmul_rn(X.l0, p0[o0]), __fmul_rn(X.l1, p1[o0]));
+                prev0 = o0;
               }
-            } else if (valid) {
-              dd[(size_t)r * ow] = bit ? 1.f : 0.f;
+              if (o1 != prev1) {
+                bot = __fadd_rn(__fmul_rn(X.l0, p0[o1]), __fmul_rn(X.l1, p1[o1]));
+                prev1 = o1;
+              }
+              const float v = __fadd_rn(__fmul_rn(rt.z, top), __fmul_rn(rt.w, bot));
+              const bool bit = valid && v > 0.5f;
+              if (PACKED) {
+                const unsigned word = __ballot_sync(0xffffffffu, bit);
+                if ((r & 31) == lane) myword = word;
+                if ((r & 31) == 31 || r == nr - 1) {  // lanes write the words of up to 32 rows at once
+                  const int rr = (r & ~31) + lane;
+                  if (rr <= r) {
+                    if (full)
+                      dst[(long long)rr * wpr] = myword;
+                    else if (myword)
+                      atomicOr(dst + (long long)rr * wpr, myword);
+                  }
+                }
+              } else if (valid) {
+                dd[(size_t)r * ow] = bit ? 1.f : 0.f;
+              }
             }
           }
         }
       }
+      __syncthreads();  // records and coefficients are overwritten by the next batch
     }
   }
   if (!loaded) {  // never leave with the bulk copy still in flight

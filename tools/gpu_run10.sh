@@ -7,4 +7,4 @@ python bench.py --workload tiles1024 --steps 50 --warmup 5 --no-cpu-baseline --n
 python -c "
 import json; d=json.load(open('gpurun_out/bench_tiles1024.json'))
 print(d['value'], d['ms_per_step']); print(d['roofline']); print({k:(round(v['ms'],4), v['gbs'] and round(v['gbs'])) for k,v in d['stages'].items()})"
-python tools/slide_profile.py 100000 2>&1 | tail -12
+
