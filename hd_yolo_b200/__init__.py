@@ -45,7 +45,7 @@ from .slide import (  # noqa: F401,E402
     tile_cores,
 )
 
-from . import dist, pipeline  # noqa: F401,E402
+from . import dist, hnet, pipeline  # noqa: F401,E402
 from .pipeline import SlidePostprocessor  # noqa: F401,E402
 
 __version__ = "0.1.0"

@@ -85,6 +85,13 @@ SIGNATURES = {
     "hdy_merge_select": (_i, [_vp, _vp, _vp, _i64, _vp, _vp, _vp]),
     "hdy_sort_workspace_bytes": (_sz, [_i64]),
     "hdy_sort_keys": (_i, [_vp, _vp, _vp, _i64, _vp, _sz, _vp]),
+    "hdy_rcnn_decode": (_i, [_vp, _vp, _i64, _i, _i64, _f, _f, _f, _f, _f, _vp, _vp]),
+    "hdy_softmax_rows": (_i, [_vp, _i64, _i, _vp, _vp]),
+    "hdy_rcnn_filter_compact": (_i, [_vp, _vp, _vp, _vp, _i, _i64, _i, _f, _f, _i, _i, _vp, _vp, _vp, _vp, _vp, _vp]),
+    "hdy_rpn_level_keys": (_i, [_vp, _i, _i, C.POINTER(C.c_int32), _i, _vp, _vp]),
+    "hdy_rpn_topk_compact": (_i, [_vp, _vp, _i, _i, C.POINTER(C.c_int32), _i, _i, _vp, _f, _f, _i, _i, _vp, _vp, _vp,
+                                  _vp, _vp, _vp]),
+    "hdy_regroup_kept": (_i, [_vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _vp, _vp, _vp, _vp, _vp, _vp]),
     "hdy_merge_gather": (_i, [_vp, _vp, _i64, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
 }
 

@@ -297,6 +297,52 @@ HDY_API int hdy_merge_gather(const uint64_t* keys, const int32_t* count, int64_t
                              const float* scores, const int64_t* labels, int64_t* out_idx, float* out_boxes,
                              float* out_scores, int64_t* out_labels, int32_t* out_count, hdy_stream_t stream);
 
+/* ------------------------------------------------- hnet multi-level heads (H1-H3) */
+
+/* H1: torchvision BoxCoder.decode_single, as reached from hnet/detection/mask_rcnn.py:67 (RPN, weights 1,1,1,1) and
+ * :192 (RoIHeads.postprocess_detections, weights 10,10,5,5).  deltas [R, C*4], boxes [boxes_rows, 4] (row r of the
+ * deltas uses boxes[r % boxes_rows]: the anchors are shared by the images of a batch) -> out [R, C, 4] xyxy.
+ * xform_clip = log(1000/16).  All three arrays 16-byte aligned. */
+HDY_API int hdy_rcnn_decode(const float* deltas, const float* boxes, int64_t R, int C, int64_t boxes_rows, float wx,
+                            float wy, float ww, float wh, float xform_clip, float* out, hdy_stream_t stream);
+
+/* F.softmax(class_logits, -1) of RoIHeads.postprocess_detections: [R, C] -> [R, C]. */
+HDY_API int hdy_softmax_rows(const float* logits, int64_t R, int C, float* out, hdy_stream_t stream);
+
+/* H3 front half (torchvision roi_heads.py postprocess_detections): clip to the image, drop the background column,
+ * one candidate per (row, class >= 1) with score > score_thresh whose clipped box has both sides >= min_size.
+ *   pred_boxes [R, C, 4], scores [R, C], row_offsets [bs+1] i32 (rows of image i = [row_offsets[i], row_offsets[i+1])),
+ *   img_wh [bs, 2] f32 (width, height).  Candidate lists as for hdy_nms_tiles; key index = position in torchvision's
+ *   flattened arrays ((row - row0) * (C-1) + class - 1), cand_cls = class.
+ *   per_class_tiles != 0: list of (image i, class c) is tile i*(C-1) + c-1 (class-separated NMS, the "vanilla"
+ *   batched_nms); 0: one list per image (use hdy_nms_tiles' class_offset for the coordinate trick). */
+HDY_API int hdy_rcnn_filter_compact(const float* pred_boxes, const float* scores, const int32_t* row_offsets,
+                                    const float* img_wh, int bs, int64_t R, int C, float score_thresh, float min_size,
+                                    int per_class_tiles, int cap, uint64_t* cand_keys, float* cand_boxes,
+                                    float* cand_cls, int32_t* counts, int32_t* status, hdy_stream_t stream);
+
+/* H2 (torchvision rpn.py filter_proposals), step 1: one 64-bit key per anchor so that ONE ascending sort
+ * (hdy_sort_keys) leaves every (image, level) segment in place, best objectness logit first, ties by lower anchor.
+ *   objectness [N, A] logits, level_sizes_host [nl] anchors per level (sum = A, each <= 262144). */
+HDY_API int hdy_rpn_level_keys(const float* objectness, int N, int A, const int32_t* level_sizes_host, int nl,
+                               uint64_t* keys, hdy_stream_t stream);
+/* step 2: the first pre_nms_top_n keys of every segment -> sigmoid, clip, remove_small_boxes(min_size),
+ * score >= score_thresh -> candidate lists (key index = position in the image's top-k concatenation, cand_cls = level).
+ *   proposals [N, A, 4]; per_level_tiles as above (tile = image*nl + level). */
+HDY_API int hdy_rpn_topk_compact(const uint64_t* sorted_keys, const float* proposals, int N, int A,
+                                 const int32_t* level_sizes_host, int nl, int pre_nms_top_n, const float* img_wh,
+                                 float min_size, float score_thresh, int per_level_tiles, int cap,
+                                 uint64_t* cand_keys, float* cand_boxes, float* cand_cls, int32_t* counts,
+                                 int32_t* status, hdy_stream_t stream);
+
+/* Survivors of `group` consecutive class/level tiles (outputs of hdy_nms_tiles) -> one candidate list per image, for
+ * the final score-ordered cut (`keep[:post_nms_top_n]` / `[:detections_per_img]`): run hdy_nms_tiles on it with
+ * iou_thres = 2, which suppresses nothing and only sorts and caps. */
+HDY_API int hdy_regroup_kept(const int32_t* keep_idx, const float* keep_box, const float* keep_score,
+                             const float* keep_cls, const int32_t* keep_counts, int n_tiles, int group, int max_det,
+                             int cap, uint64_t* cand_keys, float* cand_boxes, float* cand_cls, int32_t* counts,
+                             int32_t* status, hdy_stream_t stream);
+
 /* Utility: zero n int32 words (keeps the host mirror free of extra torch launches). */
 HDY_API int hdy_zero_i32(int32_t* p, size_t n, hdy_stream_t stream);
 

@@ -381,3 +381,34 @@ def project_roi_results_on_image(results, rois, image_shape=None):
         for k, v in r.items():
             out.setdefault(k, []).append(b if k == 'boxes' else v)
     return {k: torch.cat(v) for k, v in out.items()}
+
+
+# --------------------------------------------------------------------------------------- hnet heads (H1-H3)
+# hnet/detection/mask_rcnn.py hands all of this arithmetic to torchvision (mask_rcnn.py:67, :72, :192, :248; thresholds
+# hnet/detection/utils_det.py:16-52).  `import hnet.detection` fails in the reference itself (NameError: tmdet,
+# utils_det.py:220), so the oracle calls the same torchvision (0.26, unpinned) functions directly.
+def rcnn_box_decode(rel_codes: torch.Tensor, boxes: List[torch.Tensor], weights=(1.0, 1.0, 1.0, 1.0)) -> torch.Tensor:
+    from torchvision.models.detection._utils import BoxCoder
+    return BoxCoder(tuple(float(w) for w in weights)).decode(rel_codes, boxes)
+
+
+def rpn_filter_proposals(proposals, objectness, image_shapes, num_anchors_per_level, pre_nms_top_n=1000,
+                         post_nms_top_n=1000, nms_thresh=0.7, score_thresh=0.0):
+    from torchvision.models.detection.rpn import RegionProposalNetwork
+    rpn = RegionProposalNetwork(None, None, 0.7, 0.3, 256, 0.5, dict(training=pre_nms_top_n, testing=pre_nms_top_n),
+                                dict(training=post_nms_top_n, testing=post_nms_top_n), nms_thresh, score_thresh)
+    rpn.eval()
+    return rpn.filter_proposals(proposals, objectness, image_shapes, num_anchors_per_level)
+
+
+def roi_postprocess_detections(class_logits, box_regression, proposals, image_shapes, box_weights=(10., 10., 5., 5.),
+                               score_thresh=0.05, nms_thresh=0.5, detections_per_img=100):
+    from torchvision.models.detection.roi_heads import RoIHeads
+    rh = RoIHeads(None, None, None, 0.5, 0.5, 512, 0.25, box_weights, score_thresh, nms_thresh, detections_per_img)
+    rh.eval()
+    return rh.postprocess_detections(class_logits, box_regression, proposals, image_shapes)
+
+
+def maskrcnn_inference(x: torch.Tensor, labels: List[torch.Tensor]) -> List[torch.Tensor]:
+    from torchvision.models.detection.roi_heads import maskrcnn_inference as f
+    return f(x, labels)
