@@ -6,6 +6,7 @@ the C-ABI in ``include/hd_yolo_b200.h``; there is no CPU fallback.
 """
 from ._lib import HdyError, LIB_PATH, load  # noqa: F401
 from .ops import (  # noqa: F401
+    CapturedStep,
     DetectBatch,
     HeadSpec,
     batched_nms,

@@ -262,14 +262,20 @@ __global__ void __launch_bounds__(kPmThreads) process_mask_kernel(
     const float* __restrict__ protos, const float* __restrict__ coef, const float4* __restrict__ boxes,
     const int32_t* __restrict__ counts, int max_det, int nm, int mh, int mw, int ih, int iw, int upsample,
     float rx, float ry, float* __restrict__ out_dense, const int64_t* __restrict__ offsets,
-    uint32_t* __restrict__ bits, long long capacity_words, int32_t* __restrict__ status) {
+    uint32_t* __restrict__ bits, long long capacity_words, int32_t* __restrict__ status,
+    const int32_t* __restrict__ slot_list, const int32_t* __restrict__ list_count) {
   __shared__ float stage[kPmStage * kPmStage];
   __shared__ float cf[64];
-  const long long slot = blockIdx.x;
+  // slot_list == NULL: CTA b handles slot b.  Otherwise the CTAs share the listed slots (the detections too large for
+  // the two-phase path of mask_regions.cu).
+  const long long n_items = slot_list ? (long long)*list_count : (long long)gridDim.x;
+  for (long long item = blockIdx.x; item < n_items; item += gridDim.x) {
+  const long long slot = slot_list ? (long long)slot_list[item] : item;
   const int tile = (int)(slot / max_det), d = (int)(slot - (long long)tile * max_det);
-  if (d >= counts[tile]) return;
+  __syncthreads();  // cf / stage of the previous item are free
+  if (d >= counts[tile]) continue;
   const PMGeom g = pm_geometry(boxes[slot], mh, mw, ih, iw, upsample, rx, ry);
-  if (g.w <= 0 || g.h <= 0) return;
+  if (g.w <= 0 || g.h <= 0) continue;
   const int oh = upsample ? ih : mh, ow = upsample ? iw : mw;
   const int wpr = (g.w + 31) >> 5;
   long long off = 0;
@@ -277,7 +283,7 @@ __global__ void __launch_bounds__(kPmThreads) process_mask_kernel(
     off = offsets[slot];
     if (off + (long long)wpr * g.h > capacity_words) {
       if (threadIdx.x == 0) atomicOr(status, HDY_STATUS_OVERFLOW);
-      return;
+      continue;
     }
   }
   for (int c = threadIdx.x; c < nm; c += kPmThreads) cf[c] = coef[slot * nm + c];
@@ -337,6 +343,25 @@ __global__ void __launch_bounds__(kPmThreads) process_mask_kernel(
       }
     }
   }
+  }
+}
+
+// used by mask_regions.cu for the detections its two-phase path leaves out
+int launch_process_mask_listed(const float* protos, const float* coef, const float* boxes, const int32_t* counts,
+                               int max_det, int nm, int mh, int mw, int ih, int iw, int upsample, float rx, float ry,
+                               float* out_dense, const int64_t* offsets, uint32_t* bits, long long capacity_words,
+                               int32_t* status, const int32_t* slot_list, const int32_t* list_count,
+                               cudaStream_t st) {
+  const unsigned grid = 148 * 4;
+  if (out_dense)
+    process_mask_kernel<false><<<grid, kPmThreads, 0, st>>>(protos, coef, reinterpret_cast<const float4*>(boxes), counts,
+                                                            max_det, nm, mh, mw, ih, iw, upsample, rx, ry, out_dense,
+                                                            nullptr, nullptr, 0, nullptr, slot_list, list_count);
+  else
+    process_mask_kernel<true><<<grid, kPmThreads, 0, st>>>(protos, coef, reinterpret_cast<const float4*>(boxes), counts,
+                                                           max_det, nm, mh, mw, ih, iw, upsample, rx, ry, nullptr,
+                                                           offsets, bits, capacity_words, status, slot_list, list_count);
+  return check_launch("hdy_process_mask(listed)");
 }
 
 static int paste_args_ok(const float* src, const float* boxes, int K, int C, int M, int pad, int H, int W) {
@@ -450,9 +475,13 @@ int hdy_unpack_masks(const int32_t* geom, const int64_t* offsets, const uint32_t
   return check_launch("hdy_unpack_masks");
 }
 
+size_t hdy_process_mask_workspace_bytes(int bs, int max_det) {
+  return process_mask_workspace_bytes((long long)(bs > 0 ? bs : 0) * (max_det > 0 ? max_det : 0));
+}
+
 int hdy_process_mask(const float* protos, const float* coef, const float* boxes, const int32_t* counts, int bs,
-                     int max_det, int nm, int mh, int mw, int ih, int iw, int upsample, float* out,
-                     hdy_stream_t stream) {
+                     int max_det, int nm, int mh, int mw, int ih, int iw, int upsample, float* out, void* workspace,
+                     size_t workspace_bytes, hdy_stream_t stream) {
   int rc = pm_args_ok(protos, coef, boxes, counts, bs, max_det, nm, mh, mw, ih, iw);
   if (rc) return rc;
   if (bs == 0) return HDY_OK;
@@ -466,11 +495,11 @@ int hdy_process_mask(const float* protos, const float* coef, const float* boxes,
   }
   const float rx = (float)((double)mw / (double)iw), ry = (float)((double)mh / (double)ih);
   rc = launch_process_mask_regions(protos, coef, boxes, counts, bs, max_det, nm, mh, mw, ih, iw, upsample, rx, ry, out,
-                                   nullptr, nullptr, 0, nullptr, st);
+                                   nullptr, nullptr, 0, nullptr, workspace, workspace_bytes, st);
   if (rc != 1) return rc;
   process_mask_kernel<false><<<(unsigned)((size_t)bs * max_det), kPmThreads, 0, st>>>(
       protos, coef, reinterpret_cast<const float4*>(boxes), counts, max_det, nm, mh, mw, ih, iw, upsample, rx, ry,
-      out, nullptr, nullptr, 0, nullptr);
+      out, nullptr, nullptr, 0, nullptr, nullptr, nullptr);
   return check_launch("hdy_process_mask");
 }
 
@@ -493,26 +522,27 @@ int hdy_process_mask_geometry(const float* boxes, const int32_t* counts, int bs,
 
 int hdy_process_mask_packed(const float* protos, const float* coef, const float* boxes, const int32_t* counts,
                             const int64_t* offsets, int bs, int max_det, int nm, int mh, int mw, int ih, int iw,
-                            int upsample, uint32_t* bits, int64_t capacity_words, int32_t* status,
-                            hdy_stream_t stream) {
+                            int upsample, uint32_t* bits, int64_t capacity_words, int32_t* status, void* workspace,
+                            size_t workspace_bytes, hdy_stream_t stream) {
   int rc = pm_args_ok(protos, coef, boxes, counts, bs, max_det, nm, mh, mw, ih, iw);
   if (rc) return rc;
   if (bs == 0) return HDY_OK;
   HDY_REQUIRE(offsets && bits && status && capacity_words >= 0, "hdy_process_mask_packed: NULL pointer");
   cudaStream_t st = (cudaStream_t)stream;
-  // bits are OR-ed in: clear the used prefix first (capacity is an upper bound the caller sized)
+  const float rx = (float)((double)mw / (double)iw), ry = (float)((double)mh / (double)ih);
+  // two-phase path: every word of every mask is written exactly once, nothing to clear
+  rc = launch_process_mask_regions(protos, coef, boxes, counts, bs, max_det, nm, mh, mw, ih, iw, upsample, rx, ry,
+                                   nullptr, offsets, bits, capacity_words, status, workspace, workspace_bytes, st);
+  if (rc != 1) return rc;
+  // per-detection path: bits are OR-ed in, clear first (capacity is an upper bound the caller sized)
   cudaError_t e = cudaMemsetAsync(bits, 0, (size_t)capacity_words * 4, st);
   if (e != cudaSuccess) {
     set_error("cudaMemsetAsync: %s", cudaGetErrorString(e));
     return HDY_ERR_CUDA;
   }
-  const float rx = (float)((double)mw / (double)iw), ry = (float)((double)mh / (double)ih);
-  rc = launch_process_mask_regions(protos, coef, boxes, counts, bs, max_det, nm, mh, mw, ih, iw, upsample, rx, ry,
-                                   nullptr, offsets, bits, capacity_words, status, st);
-  if (rc != 1) return rc;
   process_mask_kernel<true><<<(unsigned)((size_t)bs * max_det), kPmThreads, 0, st>>>(
       protos, coef, reinterpret_cast<const float4*>(boxes), counts, max_det, nm, mh, mw, ih, iw, upsample, rx, ry,
-      nullptr, offsets, bits, capacity_words, status);
+      nullptr, offsets, bits, capacity_words, status, nullptr, nullptr);
   return check_launch("hdy_process_mask_packed");
 }
 

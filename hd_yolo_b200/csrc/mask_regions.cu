@@ -1,67 +1,66 @@
-// Region-centric process_mask: the north-star mask kernel (prototype x coefficient contraction in fp32 FFMA, sigmoid,
-// box crop, bilinear upsample, > 0.5, bit-packed), with the prototypes staged through TMA.
+// Two-phase process_mask: the north-star mask kernel (prototype x coefficient contraction in fp32 FFMA, sigmoid, box
+// crop, bilinear upsample, > 0.5, bit-packed), with the prototypes staged through TMA.
 //
 // Semantics: ultralytics/yolov5 v7 utils/segment/general.py::process_mask + crop_mask (restated in oracle/port.py;
 // the reference repo has no such function), identical to process_mask_kernel in mask.cu.
 //
-// Why regions.  A tile's prototypes are [32, mh, mw] fp32 (8.4 MB at 1024 px) and every detection touches a ~10x10
-// window of all 32 planes.  Letting each detection fetch its own window (mask.cu) moves ~13 KB per detection through
-// L2 in 40-byte row fragments.  Here the proto plane is cut into regions of 20x23 pixels; one CTA owns (tile, region):
-//   * ONE 4-D TMA tile load (cp.async.bulk.tensor.4d, SASS UTMALDG) brings the region's 24x24x32 box (one extra
-//     column/row for the second bilinear tap; out-of-bounds is zero-filled by the TMA unit) into 72 KB of shared
-//     memory, so every proto element is read from L2 (24/20)(24/23) = 1.25 times and from HBM once;
-//   * while the load is in flight the CTA scans the tile's boxes and lists the detections whose taps reach into the
-//     region (a nucleus is split over 1-4 regions; big boxes simply over more);
-//   * one warp per listed detection: coefficients to registers, cropped sigmoid(coef . proto) for the part of the
-//     box inside the region into a per-warp patch (32 LDS + 32 FFMA per pixel), then the output pixels whose FIRST
-//     bilinear tap lies in the region are interpolated from the patch in ATen's operation order, thresholded and
-//     ballot-packed; a 32-pixel word owned entirely by this piece is stored, a word shared with the neighbouring
-//     region is OR-ed in atomically.
+// A tile's prototypes are [32, mh, mw] fp32 (8.4 MB at 1024 px); a nucleus touches a ~10x10 window of all 32 planes
+// and produces a ~36x36 output window.  The two halves of the work want different decompositions:
+//
+//   phase 1  proto_patch_kernel, one CTA per (tile, 24x24 proto REGION).  ONE 4-D TMA tile load
+//            (cp.async.bulk.tensor.4d, SASS UTMALDG; out-of-bounds zero-filled by the TMA unit) brings the region's
+//            24x24x32 box into 72 KB of shared memory, so every proto element leaves HBM/L2 exactly once.  While it is
+//            in flight the CTA lists the tile's detections whose box reaches into the region; then one warp per
+//            (detection, region) piece computes the cropped sigmoid(coef . proto) of the piece's pixels (32 LDS + 32
+//            FFMA each) and writes them into the detection's PATCH (<= 16x16 floats) in the workspace.  Three CTAs
+//            per SM, no halo, no atomics.  The tile origin of a TMA load must be 16-byte aligned in the innermost
+//            dimension (measured: tools/micro/tma4d_test.cu faults otherwise), hence 24-pixel regions.
+//   phase 2  mask_upsample_pack_kernel, one WARP per detection, 48 warps per SM.  The patch (with a ring of zeros: the
+//            crop) goes to shared memory; per 32-pixel output word the lanes first interpolate their column along x
+//            for every source row, then every output row is one 2-tap blend of two of those values, a compare and a
+//            ballot -- ATen's bilinear (align_corners=False) operation by operation.  Every word of every mask is
+//            stored exactly once, so the bit planes need no clearing.
+//   Detections whose kept range exceeds 16x16 proto pixels (64 px boxes at the usual 4x) are listed by phase 2 and
+//   handled by the per-detection kernel of mask.cu.
 #include <stdlib.h>
 #include <cuda.h>  // CUtensorMap types only; the encoder is fetched through cudaGetDriverEntryPoint
 #include "mask_common.cuh"
 
 namespace hdy {
 
-constexpr int kRegBox = 24;         // staged proto pixels per side
-constexpr int kRegRY = kRegBox - 1; // first-tap rows owned per region (one more staged row for the second tap)
-constexpr int kRegRX = 20;          // first-tap columns owned per region: the TMA tile origin must be 16-byte aligned
-                                    // in the innermost dimension (measured: tools/micro/tma4d_test.cu), so the x pitch
-                                    // is a multiple of 4 floats and 3 of the 24 staged columns are slack
+constexpr int kRegBox = 24;  // region side == TMA box side (x origin 16-byte aligned)
 constexpr int kRegNm = 32;
 constexpr int kRegThreads = 256;
 constexpr int kRegWarps = kRegThreads / 32;
-constexpr int kRegList = 512;       // detections examined per pass
-constexpr int kRegBatch = 64;       // listed detections prepared (records + coefficients) at a time
-constexpr int kRowTab = 48;         // output rows interpolated per pass
-
-struct RowTab {
-  int off0, off1;  // patch offsets of the two source rows
-  float l0, l1;
-};
-
-// Everything about one (detection, region) piece that is the same for all lanes, computed once by ONE thread of the
-// prepare step instead of redundantly by the 32 lanes of the warp that processes the piece.
-struct PieceRec {
-  int d, gx0, gy0, gw;          // detection slot inside the tile; output window origin and width
-  int px0, px1, py0, py1;       // kept proto pixels [p0, p1)
-  float x1d, x2d, y1d, y2d;     // down-scaled box (crop test)
-  int ox_lo, ox_hi, oy_lo, oy_hi;  // output pixels this region produces
-  long long off;                // first word of the mask's bit plane
-  int live, pad;
-};
+constexpr int kRegList = 512;  // detections examined per pass
 
 struct RegSmem {
-  float proto[kRegNm][kRegBox][kRegBox];       // TMA destination (dense, x fastest)
-  float patch[kRegWarps][kRegBox * kRegBox];   // cropped sigmoid values, staged coordinates
-  RowTab rows[kRegWarps][kRowTab];
-  PieceRec rec[kRegBatch];
-  float coef[kRegBatch][kRegNm];
+  float proto[kRegNm][kRegBox][kRegBox];  // TMA destination (dense, x fastest)
+  float coef[kRegWarps][kRegNm];
   uint16_t list[kRegList];
   int nlist;
   int pad;
   uint64_t bar;
 };
+
+// workspace: [0] large-detection counter, [64..] large list (int32 per slot), then the patches
+struct PmWorkspace {
+  int32_t* large_count;
+  int32_t* large_list;
+  float* patches;
+};
+static inline size_t align256(size_t v) { return (v + 255) & ~(size_t)255; }
+size_t process_mask_workspace_bytes(long long slots) {
+  return 256 + align256((size_t)slots * 4) + (size_t)slots * kPatchPitch * kPatchPitch * 4;
+}
+static PmWorkspace pm_workspace(void* base, long long slots) {
+  PmWorkspace w;
+  unsigned char* p = static_cast<unsigned char*>(base);
+  w.large_count = reinterpret_cast<int32_t*>(p);
+  w.large_list = reinterpret_cast<int32_t*>(p + 256);
+  w.patches = reinterpret_cast<float*>(p + 256 + align256((size_t)slots * 4));
+  return w;
+}
 
 __device__ __forceinline__ void tma_load_4d(void* dst, const CUtensorMap* map, int c0, int c1, int c2, int c3,
                                             uint64_t* bar) {
@@ -72,30 +71,35 @@ __device__ __forceinline__ void tma_load_4d(void* dst, const CUtensorMap* map, i
       : "memory");
 }
 
-// smallest o in [lo, hi] whose first tap is >= target (hi if there is none); i0 is non-decreasing in o.
-// Closed-form guess from src = scale*(o+0.5)-0.5, then exact fix-up against lerp_coord itself.
-__device__ __forceinline__ int first_tap_ge(int target, int lo, int hi, float scale, int in_size) {
-  if (target <= 0) return lo;
-  int o = (int)ceilf(((float)target + 0.5f) / scale - 0.5f);
-  o = max(lo, min(hi, o));
-  while (o > lo && lerp_coord(o - 1, scale, in_size).i0 >= target) --o;
-  while (o < hi && lerp_coord(o, scale, in_size).i0 < target) ++o;
-  return o;
+struct KeptRange {
+  float x1d, y1d, x2d, y2d;
+  int px0, py0, px1, py1;
+};
+__device__ __forceinline__ KeptRange kept_range(const float4 b, float rx, float ry, int mw, int mh) {
+  KeptRange k;
+  k.x1d = __fmul_rn(b.x, rx);  // downsampled_bboxes[:, 0] *= mw / iw ...
+  k.x2d = __fmul_rn(b.z, rx);
+  k.y1d = __fmul_rn(b.y, ry);
+  k.y2d = __fmul_rn(b.w, ry);
+  k.px0 = ceil_to_int_clamped(k.x1d, 0, mw);
+  k.px1 = ceil_to_int_clamped(k.x2d, 0, mw);
+  k.py0 = ceil_to_int_clamped(k.y1d, 0, mh);
+  k.py1 = ceil_to_int_clamped(k.y2d, 0, mh);
+  return k;
 }
 
-template <bool PACKED, bool UPSAMPLE>
-__global__ void __launch_bounds__(kRegThreads, 2) process_mask_regions_kernel(
+// ------------------------------------------------------------------------------------------------ phase 1
+__global__ void __launch_bounds__(kRegThreads, 3) proto_patch_kernel(
     const __grid_constant__ CUtensorMap tmap, const float* __restrict__ coef, const float4* __restrict__ boxes,
-    const int32_t* __restrict__ counts, int max_det, int mh, int mw, int ih, int iw, int rxn, int ryn, float rx,
-    float ry, float* __restrict__ out_dense, const int64_t* __restrict__ offsets, uint32_t* __restrict__ bits,
-    long long capacity_words, int32_t* __restrict__ status) {
+    const int32_t* __restrict__ counts, int max_det, int mh, int mw, int rxn, int ryn, float rx, float ry,
+    float* __restrict__ patches) {
   extern __shared__ __align__(128) unsigned char smem_raw[];
   RegSmem& S = *reinterpret_cast<RegSmem*>(smem_raw);
   const int t = threadIdx.x, lane = t & 31, warp = t >> 5;
   const int per_tile = rxn * ryn;
   const int tile = blockIdx.x / per_tile, reg = blockIdx.x - tile * per_tile;
   const int RY = reg / rxn, RX = reg - RY * rxn;
-  const int X0 = RX * kRegRX, Y0 = RY * kRegRY;
+  const int X0 = RX * kRegBox, Y0 = RY * kRegBox;
   const int n = min(counts[tile], max_det);
   if (n <= 0) return;
 
@@ -105,220 +109,194 @@ __global__ void __launch_bounds__(kRegThreads, 2) process_mask_regions_kernel(
     mbar_arrive_expect_tx(&S.bar, (uint32_t)sizeof(S.proto));
     tma_load_4d(&S.proto[0][0][0], &tmap, X0, Y0, 0, tile, &S.bar);
   }
-  const float sxs = (float)mw / (float)iw, sys = (float)mh / (float)ih;  // ATen: scale = in / out (fp32)
-  const int oh = UPSAMPLE ? ih : mh, ow = UPSAMPLE ? iw : mw;
-  constexpr int HALO = UPSAMPLE ? 1 : 0;
-  float* patch = S.patch[warp];
-  RowTab* rowtab = S.rows[warp];
   bool loaded = false;
-
   for (int base = 0; base < n; base += kRegList) {
     __syncthreads();
     if (t == 0) S.nlist = 0;
     __syncthreads();
-    // ---- which detections reach into this region?
     const int lim = min(base + kRegList, n);
     for (int d = base + t; d < lim; d += kRegThreads) {
-      const float4 b = boxes[(size_t)tile * max_det + d];
-      const int px0 = ceil_to_int_clamped(__fmul_rn(b.x, rx), 0, mw), px1 = ceil_to_int_clamped(__fmul_rn(b.z, rx), 0, mw);
-      const int py0 = ceil_to_int_clamped(__fmul_rn(b.y, ry), 0, mh), py1 = ceil_to_int_clamped(__fmul_rn(b.w, ry), 0, mh);
-      if (px1 <= px0 || py1 <= py0) continue;
-      // first taps that see a kept pixel: [p0 - HALO, p1 - 1]
-      if (px1 - 1 < X0 || px0 - HALO >= X0 + kRegRX || py1 - 1 < Y0 || py0 - HALO >= Y0 + kRegRY) continue;
+      const KeptRange k = kept_range(boxes[(size_t)tile * max_det + d], rx, ry, mw, mh);
+      if (k.px1 <= k.px0 || k.py1 <= k.py0) continue;
+      if (k.px1 - k.px0 > kPatchPitch || k.py1 - k.py0 > kPatchPitch) continue;  // per-detection kernel
+      if (k.px1 <= X0 || k.px0 >= X0 + kRegBox || k.py1 <= Y0 || k.py0 >= Y0 + kRegBox) continue;
       S.list[atomicAdd(&S.nlist, 1)] = (uint16_t)(d - base);
     }
     __syncthreads();
     const int nl = S.nlist;
-
-    for (int b0 = 0; b0 < nl; b0 += kRegBatch) {
-      const int nb = min(kRegBatch, nl - b0);
-      // ---- prepare: one thread per piece computes its record; everybody fetches the coefficients
-      if (t < nb) {
-        PieceRec R;
-        R.d = base + S.list[b0 + t];
-        const size_t slot = (size_t)tile * max_det + R.d;
-        const PMGeom g = pm_geometry(boxes[slot], mh, mw, ih, iw, UPSAMPLE ? 1 : 0, rx, ry);
-        R.gx0 = g.x0;
-        R.gy0 = g.y0;
-        R.gw = g.w;
-        R.px0 = g.px0;
-        R.px1 = g.px1;
-        R.py0 = g.py0;
-        R.py1 = g.py1;
-        R.x1d = g.x1d;
-        R.x2d = g.x2d;
-        R.y1d = g.y1d;
-        R.y2d = g.y2d;
-        R.live = g.w > 0 && g.h > 0;
-        R.off = 0;
-        R.pad = 0;
-        if (UPSAMPLE) {
-          const int tx_lo = max(g.px0 - 1, X0), tx_hi = min(g.px1, X0 + kRegRX);  // first taps [tx_lo, tx_hi)
-          const int ty_lo = max(g.py0 - 1, Y0), ty_hi = min(g.py1, Y0 + kRegRY);
-          R.ox_lo = first_tap_ge(tx_lo, g.x0, g.x0 + g.w, sxs, mw);
-          R.ox_hi = first_tap_ge(tx_hi, g.x0, g.x0 + g.w, sxs, mw);
-          R.oy_lo = first_tap_ge(ty_lo, g.y0, g.y0 + g.h, sys, mh);
-          R.oy_hi = first_tap_ge(ty_hi, g.y0, g.y0 + g.h, sys, mh);
-        } else {  // output pixel == proto pixel; this region owns [X0, X0+RX) x [Y0, Y0+RY)
-          R.ox_lo = max(g.px0, X0);
-          R.ox_hi = min(g.px1, X0 + kRegRX);
-          R.oy_lo = max(g.py0, Y0);
-          R.oy_hi = min(g.py1, Y0 + kRegRY);
-        }
-        if (R.ox_hi <= R.ox_lo || R.oy_hi <= R.oy_lo) R.live = 0;
-        if (PACKED && R.live) {
-          R.off = offsets[slot];
-          if (R.off + (long long)((g.w + 31) >> 5) * g.h > capacity_words) {
-            atomicOr(status, HDY_STATUS_OVERFLOW);
-            R.live = 0;
-          }
-        }
-        S.rec[t] = R;
+    if (!loaded) {
+      while (!mbar_try_wait(&S.bar, 0)) {
       }
-      for (int i = t; i < nb * kRegNm; i += kRegThreads) {
-        const int e = i / kRegNm, c = i - e * kRegNm;
-        S.coef[e][c] = coef[((size_t)tile * max_det + base + S.list[b0 + e]) * kRegNm + c];
-      }
-      __syncthreads();
-      if (!loaded) {
-        while (!mbar_try_wait(&S.bar, 0)) {
-        }
-        loaded = true;
-      }
-
-      // ---- one warp per piece
-      for (int e = warp; e < nb; e += kRegWarps) {
-        const PieceRec& R = S.rec[e];
-        if (!R.live) continue;
-        const size_t slot = (size_t)tile * max_det + R.d;
-        const int wpr = (R.gw + 31) >> 5;
-        float cf[kRegNm];
+      loaded = true;
+    }
+    for (int e = warp; e < nl; e += kRegWarps) {
+      const size_t slot = (size_t)tile * max_det + base + S.list[e];
+      const KeptRange k = kept_range(boxes[slot], rx, ry, mw, mh);
+      __syncwarp();
+      S.coef[warp][lane] = coef[slot * kRegNm + lane];
+      __syncwarp();
+      float cf[kRegNm];
 #pragma unroll
-        for (int c = 0; c < kRegNm; c += 4) {
-          const float4 v = *reinterpret_cast<const float4*>(&S.coef[e][c]);
-          cf[c] = v.x;
-          cf[c + 1] = v.y;
-          cf[c + 2] = v.z;
-          cf[c + 3] = v.w;
-        }
-        // ---- cropped sigmoid(coef . proto) on the part of the box (+ halo) inside the staged box; lanes cover
-        //      floor(32 / pw) patch rows at a time
-        const int wx0 = max(R.px0 - HALO, X0), wx1 = min(R.px1 + HALO, X0 + kRegRX + HALO);
-        const int wy0 = max(R.py0 - HALO, Y0), wy1 = min(R.py1 + HALO, Y0 + kRegRY + HALO);
-        const int pw = wx1 - wx0;
-        if (pw <= 0 || wy1 <= wy0) continue;
-        {
-          const int rows_per = 32 / pw;  // pw <= 24
-          const int ly = lane / pw, lx = lane - ly * pw;
-          const int xx = wx0 + lx, sx = xx - X0;
-          const bool col_ok = ly < rows_per;
-          const bool x_in = xx < mw && (float)xx >= R.x1d && (float)xx < R.x2d;
-          __syncwarp();
-          for (int yy = wy0 + ly; yy < wy1; yy += rows_per) {
-            if (!col_ok) break;
-            const int sy = yy - Y0;
-            float v = 0.f;
-            if (x_in && yy < mh && (float)yy >= R.y1d && (float)yy < R.y2d) {
-              float acc = 0.f;
-#pragma unroll
-              for (int c = 0; c < kRegNm; ++c) acc = fmaf(cf[c], S.proto[c][sy][sx], acc);
-              v = sigmoidf_ref(acc);
-            }
-            patch[sy * kRegBox + sx] = v;
-          }
-          __syncwarp();
-        }
-
-        const int w_lo = (R.ox_lo - R.gx0) >> 5, w_hi = (R.ox_hi - 1 - R.gx0) >> 5;
-        if (!UPSAMPLE) {
-          for (int w = w_lo; w <= w_hi; ++w) {
-            const int xx = R.gx0 + (w << 5) + lane;
-            const bool valid = xx >= R.ox_lo && xx < R.ox_hi;
-            const bool full = (R.gx0 + (w << 5) >= R.ox_lo) && (min(R.gx0 + (w << 5) + 32, R.gx0 + R.gw) <= R.ox_hi);
-            for (int yy = R.oy_lo; yy < R.oy_hi; ++yy) {
-              const bool bit = valid && patch[(yy - Y0) * kRegBox + (valid ? xx - X0 : 0)] > 0.5f;
-              if (PACKED) {
-                const unsigned word = __ballot_sync(0xffffffffu, bit);
-                if (lane == 0) {
-                  uint32_t* dst = bits + R.off + (long long)(yy - R.gy0) * wpr + w;
-                  if (full)
-                    *dst = word;
-                  else if (word)
-                    atomicOr(dst, word);
-                }
-              } else if (valid) {
-                out_dense[slot * oh * ow + (size_t)yy * ow + xx] = bit ? 1.f : 0.f;
-              }
-            }
-          }
-          continue;
-        }
-
-        // ---- upsample: output pixels whose first tap lies in this region and sees the box
-        for (int r0 = R.oy_lo; r0 < R.oy_hi; r0 += kRowTab) {
-          const int nr = min(kRowTab, R.oy_hi - r0);
-          __syncwarp();
-          for (int r = lane; r < nr; r += 32) {
-            const Lerp Y = lerp_coord(r0 + r, sys, mh);
-            RowTab T;
-            T.off0 = (Y.i0 - Y0) * kRegBox;
-            T.off1 = (Y.i1 - Y0) * kRegBox;
-            T.l0 = Y.l0;
-            T.l1 = Y.l1;
-            rowtab[r] = T;
-          }
-          __syncwarp();
-          for (int w = w_lo; w <= w_hi; ++w) {
-            const int ox = R.gx0 + (w << 5) + lane;
-            const bool valid = ox >= R.ox_lo && ox < R.ox_hi;
-            const bool full = (R.gx0 + (w << 5) >= R.ox_lo) && (min(R.gx0 + (w << 5) + 32, R.gx0 + R.gw) <= R.ox_hi);
-            const Lerp X = lerp_coord(valid ? ox : R.ox_lo, sxs, mw);
-            const float* p0 = patch + (X.i0 - X0);
-            const float* p1 = patch + (X.i1 - X0);
-            uint32_t* dst = bits + R.off + (long long)(r0 - R.gy0) * wpr + w;
-            float* dd = out_dense + slot * oh * ow + (size_t)r0 * ow + ox;
-            // An output row needs top = l0x*v00 + l1x*v01 of source row i0 and bot of source row i1; several output
-            // rows share a source row (4 at the usual 4x upsample), so both are kept until the row table moves on.
-            int prev0 = -1, prev1 = -1;
-            float top = 0.f, bot = 0.f;
-            unsigned myword = 0;
-            for (int r = 0; r < nr; ++r) {
-              const float4 rt = *reinterpret_cast<const float4*>(&rowtab[r]);
-              const int o0 = __float_as_int(rt.x), o1 = __float_as_int(rt.y);
-              if (o0 != prev0) {  // warp-uniform
-                top = __fadd_rn(__fmul_rn(X.l0, p0[o0]), __fmul_rn(X.l1, p1[o0]));
-                prev0 = o0;
-              }
-              if (o1 != prev1) {
-                bot = __fadd_rn(__fmul_rn(X.l0, p0[o1]), __fmul_rn(X.l1, p1[o1]));
-                prev1 = o1;
-              }
-              const float v = __fadd_rn(__fmul_rn(rt.z, top), __fmul_rn(rt.w, bot));
-              const bool bit = valid && v > 0.5f;
-              if (PACKED) {
-                const unsigned word = __ballot_sync(0xffffffffu, bit);
-                if ((r & 31) == lane) myword = word;
-                if ((r & 31) == 31 || r == nr - 1) {  // lanes write the words of up to 32 rows at once
-                  const int rr = (r & ~31) + lane;
-                  if (rr <= r) {
-                    if (full)
-                      dst[(long long)rr * wpr] = myword;
-                    else if (myword)
-                      atomicOr(dst + (long long)rr * wpr, myword);
-                  }
-                }
-              } else if (valid) {
-                dd[(size_t)r * ow] = bit ? 1.f : 0.f;
-              }
-            }
-          }
-        }
+      for (int c = 0; c < kRegNm; c += 4) {
+        const float4 v = *reinterpret_cast<const float4*>(&S.coef[warp][c]);
+        cf[c] = v.x;
+        cf[c + 1] = v.y;
+        cf[c + 2] = v.z;
+        cf[c + 3] = v.w;
       }
-      __syncthreads();  // records and coefficients are overwritten by the next batch
+      // the piece: kept pixels inside this region; lanes cover floor(32 / pw) rows at a time
+      const int qx0 = max(k.px0, X0), qx1 = min(k.px1, X0 + kRegBox);
+      const int qy0 = max(k.py0, Y0), qy1 = min(k.py1, Y0 + kRegBox);
+      const int pw = qx1 - qx0;  // 1..16
+      const int rows_per = 32 / pw;
+      const int ly = lane / pw, lx = lane - ly * pw;
+      if (ly >= rows_per) continue;  // lane-level: the rest of the loop body has no warp-wide operation
+      const int xx = qx0 + lx, sx = xx - X0;
+      const bool x_in = (float)xx >= k.x1d && (float)xx < k.x2d;
+      float* dst = patches + slot * (kPatchPitch * kPatchPitch) + (xx - k.px0);
+      for (int yy = qy0 + ly; yy < qy1; yy += rows_per) {
+        float v = 0.f;
+        if (x_in && (float)yy >= k.y1d && (float)yy < k.y2d) {
+          const int sy = yy - Y0;
+          float acc = 0.f;
+#pragma unroll
+          for (int c = 0; c < kRegNm; ++c) acc = fmaf(cf[c], S.proto[c][sy][sx], acc);
+          v = sigmoidf_ref(acc);
+        }
+        dst[(yy - k.py0) * kPatchPitch] = v;
+      }
     }
   }
   if (!loaded) {  // never leave with the bulk copy still in flight
     while (!mbar_try_wait(&S.bar, 0)) {
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------------ phase 2
+constexpr int kUpWarps = 8;
+constexpr int kPatchRing = kPatchPitch + 2;  // patch with a ring of zeros (the crop)
+constexpr int kRowChunk = 64;
+
+struct RowTab {
+  int i0, i1;  // source rows, relative to the ringed patch
+  float l0, l1;
+};
+
+struct UpSmem {
+  float patch[kUpWarps][kPatchRing * kPatchRing];
+  float col[kUpWarps][kPatchRing][32];  // x-interpolated values of the lanes' columns, per source row
+  RowTab rows[kUpWarps][kRowChunk];
+};
+
+template <bool PACKED, bool UPSAMPLE>
+__global__ void __launch_bounds__(kUpWarps * 32) mask_upsample_pack_kernel(
+    const float* __restrict__ patches, const float4* __restrict__ boxes, const int32_t* __restrict__ counts,
+    long long n_slots, int max_det, int mh, int mw, int ih, int iw, float rx, float ry, float* __restrict__ out_dense,
+    const int64_t* __restrict__ offsets, uint32_t* __restrict__ bits, long long capacity_words,
+    int32_t* __restrict__ status, int32_t* __restrict__ large_count, int32_t* __restrict__ large_list) {
+  __shared__ UpSmem S;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const long long slot = (long long)blockIdx.x * kUpWarps + warp;
+  if (slot >= n_slots) return;
+  const int tile = (int)(slot / max_det), d = (int)(slot - (long long)tile * max_det);
+  if (d >= counts[tile]) return;
+  const PMGeom g = pm_geometry(boxes[slot], mh, mw, ih, iw, UPSAMPLE ? 1 : 0, rx, ry);
+  if (g.w <= 0 || g.h <= 0) return;
+  const int wpr = (g.w + 31) >> 5;
+  const int oh = UPSAMPLE ? ih : mh, ow = UPSAMPLE ? iw : mw;
+  long long off = 0;
+  if (PACKED) {
+    off = offsets[slot];
+    if (off + (long long)wpr * g.h > capacity_words) {
+      if (lane == 0) atomicOr(status, HDY_STATUS_OVERFLOW);
+      return;
+    }
+  }
+  const int pw = g.px1 - g.px0, ph = g.py1 - g.py0;
+  if (pw > kPatchPitch || ph > kPatchPitch) {
+    // too large for the patch path: clear its words (the per-detection kernel ORs into them) and list it
+    if (PACKED)
+      for (long long i = lane; i < (long long)wpr * g.h; i += 32) bits[off + i] = 0u;
+    if (lane == 0) large_list[atomicAdd(large_count, 1)] = (int32_t)slot;
+    return;
+  }
+  // ---- patch with its ring of zeros: element (y, x) of the proto plane sits at [(y - py0 + 1)][(x - px0 + 1)]
+  float* P = S.patch[warp];
+  for (int i = lane; i < kPatchRing * kPatchRing; i += 32) {
+    const int y = i / kPatchRing - 1, x = i - (y + 1) * kPatchRing - 1;
+    float v = 0.f;
+    if (y >= 0 && y < ph && x >= 0 && x < pw) v = patches[slot * (kPatchPitch * kPatchPitch) + y * kPatchPitch + x];
+    P[i] = v;
+  }
+  __syncwarp();
+
+  if (!UPSAMPLE) {
+    // output pixel == proto pixel: the window is the kept range itself
+    for (int w = 0; w < wpr; ++w) {
+      const int c = (w << 5) + lane;
+      const bool valid = c < g.w;
+      for (int r = 0; r < g.h; ++r) {
+        const bool bit = valid && P[(r + 1) * kPatchRing + (valid ? c + 1 : 0)] > 0.5f;
+        if (PACKED) {
+          const unsigned word = __ballot_sync(0xffffffffu, bit);
+          if (lane == 0) bits[off + (long long)r * wpr + w] = word;
+        } else if (valid) {
+          out_dense[slot * oh * ow + (size_t)(g.y0 + r) * ow + g.x0 + c] = bit ? 1.f : 0.f;
+        }
+      }
+    }
+    return;
+  }
+
+  const float sxs = (float)mw / (float)iw, sys = (float)mh / (float)ih;  // ATen: scale = in / out (fp32)
+  RowTab* rowtab = S.rows[warp];
+  float(*col)[32] = S.col[warp];
+  const int src_rows = ph + 2;  // ringed patch rows that can be touched
+  for (int r0 = 0; r0 < g.h; r0 += kRowChunk) {
+    const int nr = min(kRowChunk, g.h - r0);
+    __syncwarp();
+    for (int r = lane; r < nr; r += 32) {
+      const Lerp Y = lerp_coord(g.y0 + r0 + r, sys, mh);
+      RowTab T;
+      // taps outside [py0 - 1, py1] contribute nothing (cropped): clamp them onto the ring of zeros
+      T.i0 = min(max(Y.i0 - g.py0 + 1, 0), ph + 1);
+      T.i1 = min(max(Y.i1 - g.py0 + 1, 0), ph + 1);
+      T.l0 = Y.l0;
+      T.l1 = Y.l1;
+      rowtab[r] = T;
+    }
+    __syncwarp();
+    for (int w = 0; w < wpr; ++w) {
+      const int c = (w << 5) + lane;
+      const bool valid = c < g.w;
+      const Lerp X = lerp_coord(g.x0 + (valid ? c : 0), sxs, mw);
+      const int xi0 = min(max(X.i0 - g.px0 + 1, 0), pw + 1), xi1 = min(max(X.i1 - g.px0 + 1, 0), pw + 1);
+      // x pass: top/bot of ATen's formula for every source row, once per word
+      __syncwarp();
+      for (int s = 0; s < src_rows; ++s)
+        col[s][lane] = __fadd_rn(__fmul_rn(X.l0, P[s * kPatchRing + xi0]), __fmul_rn(X.l1, P[s * kPatchRing + xi1]));
+      __syncwarp();
+      uint32_t* dst = bits + off + (long long)r0 * wpr + w;
+      float* dd = out_dense + slot * oh * ow + (size_t)(g.y0 + r0) * ow + g.x0 + c;
+      unsigned myword = 0;
+#pragma unroll 4
+      for (int r = 0; r < nr; ++r) {
+        const float4 rt = *reinterpret_cast<const float4*>(&rowtab[r]);
+        const float v = __fadd_rn(__fmul_rn(rt.z, col[__float_as_int(rt.x)][lane]),
+                                  __fmul_rn(rt.w, col[__float_as_int(rt.y)][lane]));
+        const bool bit = valid && v > 0.5f;
+        if (PACKED) {
+          const unsigned word = __ballot_sync(0xffffffffu, bit);
+          if ((r & 31) == lane) myword = word;
+          if ((r & 31) == 31 || r == nr - 1) {  // lanes store the words of up to 32 rows at once
+            const int rr = (r & ~31) + lane;
+            if (rr <= r) dst[(long long)rr * wpr] = myword;
+          }
+        } else if (valid) {
+          dd[(size_t)r * ow] = bit ? 1.f : 0.f;
+        }
+      }
     }
   }
 }
@@ -341,32 +319,17 @@ static EncodeTiledFn tensor_map_encoder() {
   return fn;
 }
 
-template <bool PACKED, bool UPSAMPLE>
-static int launch_regions(const CUtensorMap& map, const float* coef, const float* boxes, const int32_t* counts, int bs,
-                          int max_det, int mh, int mw, int ih, int iw, int rxn, int ryn, float rx, float ry,
-                          float* out_dense, const int64_t* offsets, uint32_t* bits, long long capacity_words,
-                          int32_t* status, cudaStream_t st) {
-  cudaError_t e = cudaFuncSetAttribute(process_mask_regions_kernel<PACKED, UPSAMPLE>,
-                                       cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(RegSmem));
-  if (e != cudaSuccess) {
-    set_error("cudaFuncSetAttribute(process_mask_regions_kernel): %s", cudaGetErrorString(e));
-    return HDY_ERR_CUDA;
-  }
-  const unsigned grid = (unsigned)((long long)bs * rxn * ryn);
-  process_mask_regions_kernel<PACKED, UPSAMPLE><<<grid, kRegThreads, sizeof(RegSmem), st>>>(
-      map, coef, reinterpret_cast<const float4*>(boxes), counts, max_det, mh, mw, ih, iw, rxn, ryn, rx, ry, out_dense,
-      offsets, bits, capacity_words, status);
-  return check_launch("hdy_process_mask(regions)");
-}
-
 int launch_process_mask_regions(const float* protos, const float* coef, const float* boxes, const int32_t* counts,
                                 int bs, int max_det, int nm, int mh, int mw, int ih, int iw, int upsample, float rx,
                                 float ry, float* out_dense, const int64_t* offsets, uint32_t* bits,
-                                long long capacity_words, int32_t* status, cudaStream_t stream) {
+                                long long capacity_words, int32_t* status, void* workspace, size_t workspace_bytes,
+                                cudaStream_t stream) {
+  const long long slots = (long long)bs * max_det;
+  if (!workspace || workspace_bytes < process_mask_workspace_bytes(slots)) return 1;
   if (nm != kRegNm || (mw & 3) != 0 || ((uintptr_t)protos & 15) != 0 || max_det > 65535) return 1;
   if (getenv("HDY_MASK_GENERIC")) return 1;  // debugging aid: force the per-detection kernel
-  const int rxn = (mw + kRegRX - 1) / kRegRX, ryn = (mh + kRegRY - 1) / kRegRY;
-  if ((long long)bs * rxn * ryn >= (1ll << 31)) return 1;
+  const int rxn = (mw + kRegBox - 1) / kRegBox, ryn = (mh + kRegBox - 1) / kRegBox;
+  if ((long long)bs * rxn * ryn >= (1ll << 31) || slots >= (1ll << 31)) return 1;
   EncodeTiledFn enc = tensor_map_encoder();
   if (!enc) return 1;
   CUtensorMap map;
@@ -378,16 +341,38 @@ int launch_process_mask_regions(const float* protos, const float* coef, const fl
                          CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
                          CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) return 1;
+  const PmWorkspace W = pm_workspace(workspace, slots);
+  cudaError_t e = cudaMemsetAsync(W.large_count, 0, 4, stream);
+  if (e == cudaSuccess)
+    e = cudaFuncSetAttribute(proto_patch_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(RegSmem));
+  if (e != cudaSuccess) {
+    set_error("process_mask(regions) setup: %s", cudaGetErrorString(e));
+    return HDY_ERR_CUDA;
+  }
+  const float4* b4 = reinterpret_cast<const float4*>(boxes);
+  proto_patch_kernel<<<(unsigned)((long long)bs * rxn * ryn), kRegThreads, sizeof(RegSmem), stream>>>(
+      map, coef, b4, counts, max_det, mh, mw, rxn, ryn, rx, ry, W.patches);
+  const unsigned g2 = (unsigned)((slots + kUpWarps - 1) / kUpWarps);
   const bool packed = out_dense == nullptr;
-  if (packed)
-    return upsample ? launch_regions<true, true>(map, coef, boxes, counts, bs, max_det, mh, mw, ih, iw, rxn, ryn, rx, ry,
-                                                 nullptr, offsets, bits, capacity_words, status, stream)
-                    : launch_regions<true, false>(map, coef, boxes, counts, bs, max_det, mh, mw, ih, iw, rxn, ryn, rx,
-                                                  ry, nullptr, offsets, bits, capacity_words, status, stream);
-  return upsample ? launch_regions<false, true>(map, coef, boxes, counts, bs, max_det, mh, mw, ih, iw, rxn, ryn, rx, ry,
-                                                out_dense, nullptr, nullptr, 0, nullptr, stream)
-                  : launch_regions<false, false>(map, coef, boxes, counts, bs, max_det, mh, mw, ih, iw, rxn, ryn, rx, ry,
-                                                 out_dense, nullptr, nullptr, 0, nullptr, stream);
+#define HDY_UP(P, U)                                                                                              \
+  mask_upsample_pack_kernel<P, U><<<g2, kUpWarps * 32, 0, stream>>>(W.patches, b4, counts, slots, max_det, mh, mw, \
+                                                                    ih, iw, rx, ry, out_dense, offsets, bits,      \
+                                                                    capacity_words, status, W.large_count,         \
+                                                                    W.large_list)
+  if (packed && upsample)
+    HDY_UP(true, true);
+  else if (packed)
+    HDY_UP(true, false);
+  else if (upsample)
+    HDY_UP(false, true);
+  else
+    HDY_UP(false, false);
+#undef HDY_UP
+  int rc = check_launch("hdy_process_mask(regions)");
+  if (rc) return rc;
+  return launch_process_mask_listed(protos, coef, boxes, counts, max_det, nm, mh, mw, ih, iw, upsample, rx, ry,
+                                    out_dense, offsets, bits, capacity_words, status, W.large_list, W.large_count,
+                                    stream);
 }
 
 }  // namespace hdy

@@ -21,7 +21,9 @@ import torch
 
 from . import _lib
 from ._lib import HdyError, ptr
-from .ops import _aligned16, _call, _need_cuda, _stream
+from .ops import _Scratch, _aligned16, _call, _need_cuda, _stream
+
+_pm_scratch = _Scratch()
 
 __all__ = ["PackedMasks", "mask_select", "paste_masks_in_image", "paste_masks_packed", "process_mask",
            "process_mask_batch", "process_mask_packed"]
@@ -167,6 +169,12 @@ def _pm_args(protos, coef, boxes, counts):
     return bs, nm, mh, mw, coef.shape[1]
 
 
+def _pm_workspace(dev, bs: int, md: int):
+    """Grow-only scratch for the two-phase path (sigmoid patches + the list of over-sized detections)."""
+    nbytes = _lib.load().hdy_process_mask_workspace_bytes(bs, md)
+    return _pm_scratch.get(dev, "process_mask", nbytes), nbytes
+
+
 def process_mask_batch(protos: torch.Tensor, coef: torch.Tensor, boxes: torch.Tensor, counts: torch.Tensor, shape,
                        upsample: bool = False) -> torch.Tensor:
     """process_mask for a batch of tiles (struct-of-arrays, as DetectBatch holds them): protos [bs,nm,mh,mw],
@@ -177,8 +185,10 @@ def process_mask_batch(protos: torch.Tensor, coef: torch.Tensor, boxes: torch.Te
     oh, ow = (ih, iw) if upsample else (mh, mw)
     out = torch.empty((bs, md, oh, ow), dtype=torch.float32, device=protos.device)
     if bs and md:
-        _call("hdy_process_mask", ptr(protos.contiguous()), ptr(coef.contiguous()), ptr(_aligned16(boxes.contiguous())),
-              ptr(counts), bs, md, nm, mh, mw, ih, iw, int(bool(upsample)), ptr(out), _stream(), launches=2)
+        ws, wbytes = _pm_workspace(protos.device, bs, md)
+        _call("hdy_process_mask", ptr(_aligned16(protos.contiguous())), ptr(coef.contiguous()),
+              ptr(_aligned16(boxes.contiguous())), ptr(counts), bs, md, nm, mh, mw, ih, iw, int(bool(upsample)),
+              ptr(out), ptr(ws), wbytes, _stream(), launches=4)
     return out
 
 
@@ -216,8 +226,9 @@ def process_mask_packed(protos: torch.Tensor, coef: torch.Tensor, boxes: torch.T
     words = int(offsets[K].item()) if capacity_words is None else int(capacity_words)
     bits = torch.empty((max(words, 1),), dtype=torch.int32, device=dev)
     if K:
-        _call("hdy_process_mask_packed", ptr(protos.contiguous()), ptr(coef.contiguous()), ptr(boxes), ptr(counts),
-              ptr(offsets), bs, md, nm, mh, mw, ih, iw, int(bool(upsample)), ptr(bits), words, ptr(status), _stream(),
-              launches=2)
+        ws, wbytes = _pm_workspace(dev, bs, md)
+        _call("hdy_process_mask_packed", ptr(_aligned16(protos.contiguous())), ptr(coef.contiguous()), ptr(boxes),
+              ptr(counts), ptr(offsets), bs, md, nm, mh, mw, ih, iw, int(bool(upsample)), ptr(bits), words, ptr(status),
+              ptr(ws), wbytes, _stream(), launches=3)
     oh, ow = (ih, iw) if upsample else (mh, mw)
     return PackedMasks(geom, offsets, bits[:words], oh, ow, status)

@@ -30,6 +30,7 @@ __all__ = [
     "detect_postprocess",
     "DetectBatch",
     "flatten_onehot_objects",
+    "CapturedStep",
 ]
 
 # ----------------------------------------------------------------------------- thresholds
@@ -106,6 +107,37 @@ def _call(name: str, *args, launches: int = 1) -> None:
         rc = fn(*args)
     profile.launches += launches
     check(rc, name)
+
+
+class CapturedStep:
+    """A fixed-shape post-processing step captured once into a CUDA graph and replayed.
+
+    ``fn`` is any composition of this package's calls that does not synchronise with the host (candidate / mask
+    capacities given, no ``to_list()``): its ~10 kernel launches and ~25 small allocations cost more host time than the
+    kernels take on a B200 at 640-px batches, so a serving loop replays the graph instead.  ``fn`` must read its inputs
+    from buffers that stay in place (write the next batch into them before calling); the returned object of the capture
+    is handed back by every replay and is overwritten in place."""
+
+    def __init__(self, fn, warmup: int = 3):
+        cur = torch.cuda.current_stream()
+        self.stream = torch.cuda.Stream()
+        self.stream.wait_stream(cur)
+        with torch.cuda.stream(self.stream):
+            for _ in range(max(warmup, 1)):      # grows every scratch buffer and sets kernel attributes
+                fn()
+        cur.wait_stream(self.stream)
+        torch.cuda.synchronize()
+        self.graph = torch.cuda.CUDAGraph()
+        before = profile.launches
+        with torch.cuda.graph(self.graph, stream=self.stream):
+            self.out = fn()
+        self.launches = profile.launches - before
+        profile.launches = before
+
+    def __call__(self):
+        self.graph.replay()
+        profile.launches += self.launches
+        return self.out
 
 
 def _need_cuda(t: torch.Tensor, name: str) -> None:

@@ -202,10 +202,14 @@ HDY_API int hdy_unpack_masks(const int32_t* geom, const int64_t* offsets, const 
  * reference itself has no such function): mask = sigmoid(coef . protos), zero outside the box scaled by
  * (mw/iw, mh/ih), optional bilinear upsample (align_corners=False) to (ih, iw), > 0.5.  Batched over tiles:
  *   protos [bs, nm, mh, mw], coef [bs, max_det, nm], boxes [bs, max_det, 4] (image pixels), counts [bs]
- *   dense out [bs, max_det, oh, ow] f32 in {0,1} with (oh,ow) = upsample ? (ih,iw) : (mh,mw). */
+ *   dense out [bs, max_det, oh, ow] f32 in {0,1} with (oh,ow) = upsample ? (ih,iw) : (mh,mw).
+ * workspace (hdy_process_mask_workspace_bytes(bs, max_det) bytes, may be NULL) enables the two-phase path
+ * (csrc/mask_regions.cu: TMA-staged prototypes -> sigmoid patches -> upsample + pack) when nm == 32, mw % 4 == 0 and
+ * protos is 16-byte aligned; otherwise, and for boxes wider than 16 proto pixels, the per-detection kernel runs. */
+HDY_API size_t hdy_process_mask_workspace_bytes(int bs, int max_det);
 HDY_API int hdy_process_mask(const float* protos, const float* coef, const float* boxes, const int32_t* counts,
                              int bs, int max_det, int nm, int mh, int mw, int ih, int iw, int upsample, float* out,
-                             hdy_stream_t stream);
+                             void* workspace, size_t workspace_bytes, hdy_stream_t stream);
 /* Cropped bit-packed variant; geom [bs*max_det, 4], offsets [bs*max_det + 1] as above (slots >= counts are empty). */
 HDY_API int hdy_process_mask_geometry(const float* boxes, const int32_t* counts, int bs, int max_det, int mh, int mw,
                                       int ih, int iw, int upsample, int32_t* geom, int64_t* offsets,
@@ -213,7 +217,8 @@ HDY_API int hdy_process_mask_geometry(const float* boxes, const int32_t* counts,
 HDY_API int hdy_process_mask_packed(const float* protos, const float* coef, const float* boxes,
                                     const int32_t* counts, const int64_t* offsets, int bs, int max_det, int nm,
                                     int mh, int mw, int ih, int iw, int upsample, uint32_t* bits,
-                                    int64_t capacity_words, int32_t* status, hdy_stream_t stream);
+                                    int64_t capacity_words, int32_t* status, void* workspace, size_t workspace_bytes,
+                                    hdy_stream_t stream);
 
 /* ------------------------------------------------------------- coordinates */
 

@@ -157,3 +157,39 @@ def test_process_mask_batch_counts(cuda_device):
             ref = port.process_mask(protos[i], coef[i, :k], boxes[i, :k].clone(), (ih, iw), upsample=True)
             assert _agreement(out[i, :k], ref) >= AGREE
     assert hm.process_mask(protos[0].to(cuda_device), coef[0, :0].to(cuda_device), boxes[0, :0].to(cuda_device), (ih, iw)).shape == (0, mh, mw)
+
+
+@pytest.mark.parametrize("upsample", [False, True])
+def test_process_mask_mixed_small_and_large_boxes(cuda_device, upsample):
+    """Boxes up to 64 px go through the two-phase path (TMA-staged regions -> patches -> upsample/pack), larger ones
+    through the per-detection kernel; both write into the same bit planes."""
+    g = torch.Generator().manual_seed(11)
+    n, mh, mw, ih, iw = 90, 96, 128, 384, 512
+    protos = torch.randn((32, mh, mw), generator=g)
+    coef = torch.randn((n, 32), generator=g) * 0.5
+    boxes = torch.cat([_rand_boxes(g, 60, ih, iw, 6, 60), _rand_boxes(g, 30, ih, iw, 70, 300)])
+    ref = port.process_mask(protos, coef, boxes.clone(), (ih, iw), upsample=upsample)
+    dev = cuda_device
+    out = hm.process_mask(protos.to(dev), coef.to(dev), boxes.to(dev), (ih, iw), upsample=upsample)
+    assert _agreement(out.cpu(), ref) >= AGREE
+    counts = torch.tensor([n], dtype=torch.int32, device=dev)
+    packed = hm.process_mask_packed(protos.to(dev)[None], coef.to(dev)[None], boxes.to(dev)[None], counts, (ih, iw),
+                                    upsample=upsample)
+    packed.check()
+    assert torch.equal(packed.to_dense(), out.to(torch.uint8))
+    # a second call re-uses the bit planes' storage pattern: stale words must not leak (nothing is memset)
+    packed2 = hm.process_mask_packed(protos.to(dev)[None], coef.to(dev)[None], boxes.to(dev)[None], counts, (ih, iw),
+                                     upsample=upsample)
+    assert torch.equal(packed2.to_dense(), out.to(torch.uint8))
+
+
+def test_process_mask_other_prototype_counts(cuda_device):
+    """nm != 32 takes the per-detection kernel."""
+    g = torch.Generator().manual_seed(12)
+    n, nm, mh, mw, ih, iw = 25, 16, 40, 40, 160, 160
+    protos = torch.randn((nm, mh, mw), generator=g)
+    coef = torch.randn((n, nm), generator=g) * 0.7
+    boxes = _rand_boxes(g, n, ih, iw, 8, 80)
+    ref = port.process_mask(protos, coef, boxes.clone(), (ih, iw), upsample=True)
+    out = hm.process_mask(protos.to(cuda_device), coef.to(cuda_device), boxes.to(cuda_device), (ih, iw), upsample=True)
+    assert _agreement(out.cpu(), ref) >= AGREE
