@@ -32,6 +32,7 @@ import time
 ROOT = os.path.dirname(os.path.abspath(__file__))
 if ROOT not in sys.path:
     sys.path.insert(0, ROOT)
+os.environ.setdefault("NCCL_DEBUG", "WARN")   # keep NCCL's version banner off stdout: rank 0 prints ONE JSON line
 
 WORKLOADS = {
     # BASELINE.json configs[1]: 640x640 tiles, batch 64, 3 anchor levels, 32 prototypes, ~1k candidates/tile

@@ -223,11 +223,20 @@ __global__ void __launch_bounds__(kUpWarps * 32) mask_upsample_pack_kernel(
   }
   // ---- patch with its ring of zeros: element (y, x) of the proto plane sits at [(y - py0 + 1)][(x - px0 + 1)]
   float* P = S.patch[warp];
-  for (int i = lane; i < kPatchRing * kPatchRing; i += 32) {
-    const int y = i / kPatchRing - 1, x = i - (y + 1) * kPatchRing - 1;
-    float v = 0.f;
-    if (y >= 0 && y < ph && x >= 0 && x < pw) v = patches[slot * (kPatchPitch * kPatchPitch) + y * kPatchPitch + x];
-    P[i] = v;
+  {
+    // interior: the 16 x 16 patch, coalesced 128-byte rows (entries outside pw x ph are stale: masked to zero)
+    const float* src = patches + slot * (kPatchPitch * kPatchPitch);
+#pragma unroll
+    for (int i = lane; i < kPatchPitch * kPatchPitch; i += 32) {
+      const int y = i >> 4, x = i & 15;
+      P[(y + 1) * kPatchRing + x + 1] = (y < ph && x < pw) ? src[i] : 0.f;
+    }
+    // ring: rows 0 and 17, columns 0 and 17
+    for (int i = lane; i < 4 * kPatchRing; i += 32) {
+      const int k = i / kPatchRing, j = i - k * kPatchRing;
+      const int idx = k == 0 ? j : (k == 1 ? (kPatchRing - 1) * kPatchRing + j : (k == 2 ? j * kPatchRing : j * kPatchRing + kPatchRing - 1));
+      P[idx] = 0.f;
+    }
   }
   __syncwarp();
 
@@ -268,6 +277,37 @@ __global__ void __launch_bounds__(kUpWarps * 32) mask_upsample_pack_kernel(
     }
     __syncwarp();
     for (int w = 0; w < wpr; ++w) {
+      const int vw = min(32, g.w - (w << 5));  // valid columns of this word
+      if (vw <= 16) {
+        // narrow word (the tail of a 36-px window is 4 columns): lanes cover floor(32 / vw) output rows at a time
+        const int rows_per = 32 / vw;
+        const int lr = lane / vw, lc = lane - lr * vw;
+        const bool active = lr < rows_per;
+        const Lerp X = lerp_coord(g.x0 + (w << 5) + lc, sxs, mw);
+        const int xi0 = min(max(X.i0 - g.px0 + 1, 0), pw + 1), xi1 = min(max(X.i1 - g.px0 + 1, 0), pw + 1);
+        __syncwarp();
+        if (active)
+          for (int s = lr; s < src_rows; s += rows_per)
+            col[s][lc] = __fadd_rn(__fmul_rn(X.l0, P[s * kPatchRing + xi0]), __fmul_rn(X.l1, P[s * kPatchRing + xi1]));
+        __syncwarp();
+        const unsigned row_mask = vw == 32 ? 0xffffffffu : ((1u << vw) - 1u);
+        for (int rb = 0; rb < nr; rb += rows_per) {
+          const int r = rb + lr;
+          bool bit = false;
+          if (active && r < nr) {
+            const float4 rt = *reinterpret_cast<const float4*>(&rowtab[r]);
+            const float v = __fadd_rn(__fmul_rn(rt.z, col[__float_as_int(rt.x)][lc]),
+                                      __fmul_rn(rt.w, col[__float_as_int(rt.y)][lc]));
+            bit = v > 0.5f;
+            if (!PACKED) out_dense[slot * oh * ow + (size_t)(g.y0 + r0 + r) * ow + g.x0 + (w << 5) + lc] = bit ? 1.f : 0.f;
+          }
+          if (PACKED) {
+            const unsigned m = __ballot_sync(0xffffffffu, bit);
+            if (active && lc == 0 && r < nr) bits[off + (long long)(r0 + r) * wpr + w] = (m >> (lr * vw)) & row_mask;
+          }
+        }
+        continue;
+      }
       const int c = (w << 5) + lane;
       const bool valid = c < g.w;
       const Lerp X = lerp_coord(g.x0 + (valid ? c : 0), sxs, mw);
