@@ -26,16 +26,21 @@
 #include <cuda.h>  // CUtensorMap types only; the encoder is fetched through cudaGetDriverEntryPoint
 #include "mask_common.cuh"
 
+#ifndef HDY_REG_BOX_X
+#define HDY_REG_BOX_X 24
+#define HDY_REG_BOX_Y 24
+#endif
+
 namespace hdy {
 
-constexpr int kRegBox = 24;  // region side == TMA box side (x origin 16-byte aligned)
+constexpr int kRegBoxX = HDY_REG_BOX_X, kRegBoxY = HDY_REG_BOX_Y;  // region == TMA box (x origin 16-byte aligned)
 constexpr int kRegNm = 32;
 constexpr int kRegThreads = 256;
 constexpr int kRegWarps = kRegThreads / 32;
 constexpr int kRegList = 512;  // detections examined per pass
 
 struct RegSmem {
-  float proto[kRegNm][kRegBox][kRegBox];  // TMA destination (dense, x fastest)
+  float proto[kRegNm][kRegBoxY][kRegBoxX];  // TMA destination (dense, x fastest)
   float coef[kRegWarps][kRegNm];
   uint16_t list[kRegList];
   int nlist;
@@ -99,7 +104,7 @@ __global__ void __launch_bounds__(kRegThreads, 3) proto_patch_kernel(
   const int per_tile = rxn * ryn;
   const int tile = blockIdx.x / per_tile, reg = blockIdx.x - tile * per_tile;
   const int RY = reg / rxn, RX = reg - RY * rxn;
-  const int X0 = RX * kRegBox, Y0 = RY * kRegBox;
+  const int X0 = RX * kRegBoxX, Y0 = RY * kRegBoxY;
   const int n = min(counts[tile], max_det);
   if (n <= 0) return;
 
@@ -119,7 +124,7 @@ __global__ void __launch_bounds__(kRegThreads, 3) proto_patch_kernel(
       const KeptRange k = kept_range(boxes[(size_t)tile * max_det + d], rx, ry, mw, mh);
       if (k.px1 <= k.px0 || k.py1 <= k.py0) continue;
       if (k.px1 - k.px0 > kPatchPitch || k.py1 - k.py0 > kPatchPitch) continue;  // per-detection kernel
-      if (k.px1 <= X0 || k.px0 >= X0 + kRegBox || k.py1 <= Y0 || k.py0 >= Y0 + kRegBox) continue;
+      if (k.px1 <= X0 || k.px0 >= X0 + kRegBoxX || k.py1 <= Y0 || k.py0 >= Y0 + kRegBoxY) continue;
       S.list[atomicAdd(&S.nlist, 1)] = (uint16_t)(d - base);
     }
     __syncthreads();
@@ -145,8 +150,8 @@ __global__ void __launch_bounds__(kRegThreads, 3) proto_patch_kernel(
         cf[c + 3] = v.w;
       }
       // the piece: kept pixels inside this region; lanes cover floor(32 / pw) rows at a time
-      const int qx0 = max(k.px0, X0), qx1 = min(k.px1, X0 + kRegBox);
-      const int qy0 = max(k.py0, Y0), qy1 = min(k.py1, Y0 + kRegBox);
+      const int qx0 = max(k.px0, X0), qx1 = min(k.px1, X0 + kRegBoxX);
+      const int qy0 = max(k.py0, Y0), qy1 = min(k.py1, Y0 + kRegBoxY);
       const int pw = qx1 - qx0;  // 1..16
       const int rows_per = 32 / pw;
       const int ly = lane / pw, lx = lane - ly * pw;
@@ -368,14 +373,14 @@ int launch_process_mask_regions(const float* protos, const float* coef, const fl
   if (!workspace || workspace_bytes < process_mask_workspace_bytes(slots)) return 1;
   if (nm != kRegNm || (mw & 3) != 0 || ((uintptr_t)protos & 15) != 0 || max_det > 65535) return 1;
   if (getenv("HDY_MASK_GENERIC")) return 1;  // debugging aid: force the per-detection kernel
-  const int rxn = (mw + kRegBox - 1) / kRegBox, ryn = (mh + kRegBox - 1) / kRegBox;
+  const int rxn = (mw + kRegBoxX - 1) / kRegBoxX, ryn = (mh + kRegBoxY - 1) / kRegBoxY;
   if ((long long)bs * rxn * ryn >= (1ll << 31) || slots >= (1ll << 31)) return 1;
   EncodeTiledFn enc = tensor_map_encoder();
   if (!enc) return 1;
   CUtensorMap map;
   const cuuint64_t dims[4] = {(cuuint64_t)mw, (cuuint64_t)mh, (cuuint64_t)nm, (cuuint64_t)bs};
   const cuuint64_t strides[3] = {(cuuint64_t)mw * 4, (cuuint64_t)mw * mh * 4, (cuuint64_t)mw * mh * nm * 4};
-  const cuuint32_t box[4] = {kRegBox, kRegBox, kRegNm, 1};
+  const cuuint32_t box[4] = {kRegBoxX, kRegBoxY, kRegNm, 1};
   const cuuint32_t estr[4] = {1, 1, 1, 1};
   const CUresult r = enc(&map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, const_cast<float*>(protos), dims, strides, box, estr,
                          CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
