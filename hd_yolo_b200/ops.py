@@ -31,6 +31,7 @@ __all__ = [
     "DetectBatch",
     "flatten_onehot_objects",
     "CapturedStep",
+    "scratch_slot",
 ]
 
 # ----------------------------------------------------------------------------- thresholds
@@ -118,24 +119,31 @@ class CapturedStep:
     from buffers that stay in place (write the next batch into them before calling); the returned object of the capture
     is handed back by every replay and is overwritten in place."""
 
-    def __init__(self, fn, warmup: int = 3):
+    def __init__(self, fn, warmup: int = 3, slot: int = 0):
         cur = torch.cuda.current_stream()
         self.stream = torch.cuda.Stream()
         self.stream.wait_stream(cur)
-        with torch.cuda.stream(self.stream):
-            for _ in range(max(warmup, 1)):      # grows every scratch buffer and sets kernel attributes
-                fn()
-        cur.wait_stream(self.stream)
-        torch.cuda.synchronize()
-        self.graph = torch.cuda.CUDAGraph()
-        before = profile.launches
-        with torch.cuda.graph(self.graph, stream=self.stream):
-            self.out = fn()
+        with scratch_slot(slot):
+            with torch.cuda.stream(self.stream):
+                for _ in range(max(warmup, 1)):      # grows every scratch buffer and sets kernel attributes
+                    fn()
+            cur.wait_stream(self.stream)
+            torch.cuda.synchronize()
+            self.graph = torch.cuda.CUDAGraph()
+            before = profile.launches
+            with torch.cuda.graph(self.graph, stream=self.stream):
+                self.out = fn()
         self.launches = profile.launches - before
         profile.launches = before
 
-    def __call__(self):
-        self.graph.replay()
+    def __call__(self, stream: Optional[torch.cuda.Stream] = None):
+        """Replay on the current stream (or `stream`).  Graphs captured with different `slot`s may be in flight at the
+        same time on different streams; replays of one graph are ordered by the stream they are issued on."""
+        if stream is None:
+            self.graph.replay()
+        else:
+            with torch.cuda.stream(stream):
+                self.graph.replay()
         profile.launches += self.launches
         return self.out
 
@@ -151,14 +159,33 @@ def _aligned16(t: torch.Tensor) -> torch.Tensor:
     return t if t.data_ptr() % 16 == 0 else t.clone()
 
 
+_SLOT = 0
+
+
+class scratch_slot:
+    """Context manager: work issued inside uses scratch buffer set `k`.  Steps that run concurrently on different
+    streams (two CapturedStep graphs in flight) must use different slots; the default slot is 0."""
+
+    def __init__(self, k: int):
+        self.k = int(k)
+
+    def __enter__(self):
+        global _SLOT
+        self.prev, _SLOT = _SLOT, self.k
+
+    def __exit__(self, *exc):
+        global _SLOT
+        _SLOT = self.prev
+
+
 class _Scratch:
-    """Grow-only per-device scratch buffers (candidate lists, NMS workspace)."""
+    """Grow-only per-device scratch buffers (candidate lists, NMS workspace), one set per scratch slot."""
 
     def __init__(self):
-        self._buf: Dict[Tuple[int, str], torch.Tensor] = {}
+        self._buf: Dict[Tuple[int, int, str], torch.Tensor] = {}
 
     def get(self, device: torch.device, name: str, nbytes: int) -> torch.Tensor:
-        key = (device.index if device.index is not None else torch.cuda.current_device(), name)
+        key = (device.index if device.index is not None else torch.cuda.current_device(), _SLOT, name)
         b = self._buf.get(key)
         if b is None or b.numel() < nbytes:
             b = torch.empty(max(nbytes, 256), dtype=torch.uint8, device=device)
