@@ -341,6 +341,7 @@ def run_tiles(args, wl, c):
         "hdy_filter_compact_logits": bs * (4 * N * spec.no + 24 * cand),
         "hdy_nms_tiles": bs * (24 * cand + 28 * kept),
         "hdy_gather_logits": bs * kept * (4 * (1 + nc + ne) * 2 + 4),
+        "hdy_gather_select_logits": bs * kept * (4 * (1 + nc + ne) * 2 + 4 + 4 + 8),
         "hdy_select_scores": bs * kept * (4 * (1 + nc) * 2 + 4 + 8),
         "hdy_process_mask_geometry": bs * min(wl["max_det"], wl["cap"]) * (16 + 16 + 8),
         "hdy_process_mask_packed": bs * (4 * NM * mh * mw + kept * (4 * NM + 16 + 8)) + 4 * words,

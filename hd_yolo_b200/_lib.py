@@ -60,6 +60,8 @@ SIGNATURES = {
     "hdy_debug_nms_phases": (_i, [_vp]),
     "hdy_gather_preds": (_i, [_vp, _i, _i, _i, _i, _vp, _vp, _i, _vp, _vp, _vp]),
     "hdy_gather_logits": (_i, [_LP, _i, _i, _i, _i, _i, _i, _vp, _vp, _i, _vp, _vp, _vp, _vp]),
+    "hdy_gather_select_logits": (_i, [_LP, _i, _i, _i, _i, _i, _i, _vp, _vp, _i, C.POINTER(C.c_int32), _i, _f, _vp, _vp,
+                                      _vp, _vp, _vp, _vp]),
     "hdy_select_scores": (_i, [_vp, _vp, _i, _i, _i, C.POINTER(C.c_int32), _i, _f, _vp, _vp, _vp]),
     "hdy_mask_select": (_i, [_vp, _vp, _vp, _i, _i, _i, _vp, _vp]),
     "hdy_paste_masks": (_i, [_vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _i, _vp, _vp]),

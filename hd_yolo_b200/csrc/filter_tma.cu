@@ -52,7 +52,7 @@ template <int WARPS, int NBUF, int RPL>
 __global__ void __launch_bounds__(WARPS * 32) filter_compact_tma_kernel(
     const __grid_constant__ LevelTable T, const __grid_constant__ ItemTable I, int bs, int buf_bytes,
     float t_lo, float conf_thres, float min_size, int cap, uint64_t* __restrict__ cand_keys,
-    float4* __restrict__ cand_boxes, int32_t* __restrict__ counts, int32_t* __restrict__ status) {
+    float4* __restrict__ cand_boxes, int32_t* __restrict__ counts, int32_t* __restrict__ status, int keep_rows_in_l2) {
   extern __shared__ __align__(128) unsigned char smem_raw[];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int no = T.no;
@@ -160,6 +160,14 @@ __global__ void __launch_bounds__(WARPS * 32) filter_compact_tma_kernel(
         // remove_small_boxes(min_size)                                             utils_general.py:332
         cand = (__fsub_rn(box.z, box.x) >= min_size) && (__fsub_rn(box.w, box.y) >= min_size);
         key = make_key(p_obj, (uint32_t)(L.row_offset + B.row));
+        if (cand && keep_rows_in_l2) {
+          // The survivors' score / extra channels are gathered again after NMS (hdy_gather_select_logits); by then
+          // the stream has pushed the row out of L2.  Mark its lines evict_last now, while they are still there.
+          const char* rowp = reinterpret_cast<const char*>(L.ptr + ((size_t)tile * L.rows + B.row) * no);
+          const int row_bytes = no * 4;
+          for (int ofs = 16; ofs < row_bytes + 112; ofs += 128)
+            asm volatile("prefetch.global.L2::evict_last [%0];" ::"l"(rowp + min(ofs, row_bytes - 4)));
+        }
       }
     }
     unsigned todo = __ballot_sync(0xffffffffu, cand);
@@ -267,7 +275,7 @@ static int launch_variant(const LevelTable& T, const ItemTable& I, int bs, int b
   if (grid > need) grid = need;
   filter_compact_tma_kernel<WARPS, NBUF, RPL><<<(unsigned)grid, WARPS * 32, smem, stream>>>(
       T, I, bs, buf_bytes, t_lo, conf_thres, min_size, cap, cand_keys, reinterpret_cast<float4*>(cand_boxes),
-      counts, status);
+      counts, status, getenv("HDY_NO_L2_KEEP") ? 0 : 1);
   return check_launch("hdy_filter_compact_logits(tma)");
 }
 
@@ -277,13 +285,15 @@ int launch_filter_compact_tma(const hdy_level_t* levels_host, int nl, int bs, in
                               float min_size, int cap, uint64_t* cand_keys, float* cand_boxes, int32_t* counts,
                               int32_t* status, cudaStream_t stream) {
   // tuning knobs (defaults measured on B200); HDY_TMA_VARIANT="warps,nbuf,chunk_bytes" overrides
-  static int kWarps = 4, kNbuf = 2, kChunk = 9216;
+  static int kWarps = 4, kNbuf = 2, kChunk = 14336;
   static bool env_read = false;
   if (!env_read) {
     env_read = true;
     if (const char* v = getenv("HDY_TMA_VARIANT")) sscanf(v, "%d,%d,%d", &kWarps, &kNbuf, &kChunk);
   }
-  // rows per lane and chunk: 1, 2, 4 or 8
+  // rows per lane and chunk: 1, 2, 4 or 8, the largest whose chunk stays within kChunk bytes (9 KB chunks at no = 9,
+  // 10.5 KB at no = 41: measured best on B200, smaller chunks pay the per-chunk handshake, larger ones leave too few
+  // warps per SM)
   int rpl = kChunk / (32 * no * 4);
   rpl = rpl >= 8 ? 8 : (rpl >= 4 ? 4 : (rpl >= 2 ? 2 : 1));
   const int chunk_rows = 32 * rpl;

@@ -476,7 +476,7 @@ int hdy_unpack_masks(const int32_t* geom, const int64_t* offsets, const uint32_t
 }
 
 size_t hdy_process_mask_workspace_bytes(int bs, int max_det) {
-  return process_mask_workspace_bytes((long long)(bs > 0 ? bs : 0) * (max_det > 0 ? max_det : 0));
+  return process_mask_workspace_bytes(bs > 0 ? bs : 0, max_det > 0 ? max_det : 0);
 }
 
 int hdy_process_mask(const float* protos, const float* coef, const float* boxes, const int32_t* counts, int bs,

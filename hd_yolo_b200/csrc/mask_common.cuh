@@ -87,7 +87,7 @@ __device__ __forceinline__ PMGeom pm_geometry(const float4 b, int mh, int mw, in
 // mask_regions.cu: two-phase process_mask (TMA-staged prototypes -> sigmoid patches -> upsample + pack).  Returns 1
 // when the shapes / workspace do not meet its requirements (the caller then uses the per-detection kernel in mask.cu).
 constexpr int kPatchPitch = 16;  // sigmoid patches of up to 16 x 16 proto pixels go through the workspace
-size_t process_mask_workspace_bytes(long long slots);
+size_t process_mask_workspace_bytes(long long bs, long long max_det);
 int launch_process_mask_regions(const float* protos, const float* coef, const float* boxes, const int32_t* counts,
                                 int bs, int max_det, int nm, int mh, int mw, int ih, int iw, int upsample, float rx,
                                 float ry, float* out_dense, const int64_t* offsets, uint32_t* bits,

@@ -48,15 +48,26 @@ struct RegSmem {
   uint64_t bar;
 };
 
-// workspace: [0] large-detection counter, [64..] large list (int32 per slot), then the patches
+// workspace: [0] large-detection counter, large list (int32 per slot), the patches, then the per-region detection
+// lists (count + kRegCap uint16 entries per (tile, region); sized for the largest proto plane, see kMaxRegions)
+constexpr int kRegCap = 254;          // detections listed per region; a region with more falls back to scanning
+constexpr int kMaxRegionsPerTile = 512;  // ceil(mw/24) * ceil(mh/24) <= 512 covers planes up to 528 x 528 (2112 px tiles)
+struct RegionList {
+  int32_t count;
+  uint16_t det[kRegCap];
+};
+static_assert(sizeof(RegionList) == 512, "one region list is 512 bytes");
 struct PmWorkspace {
   int32_t* large_count;
   int32_t* large_list;
   float* patches;
+  RegionList* regions;
 };
 static inline size_t align256(size_t v) { return (v + 255) & ~(size_t)255; }
-size_t process_mask_workspace_bytes(long long slots) {
-  return 256 + align256((size_t)slots * 4) + (size_t)slots * kPatchPitch * kPatchPitch * 4;
+size_t process_mask_workspace_bytes(long long bs, long long max_det) {
+  const long long slots = bs * max_det;
+  return 256 + align256((size_t)slots * 4) + (size_t)slots * kPatchPitch * kPatchPitch * 4 +
+         (size_t)bs * kMaxRegionsPerTile * sizeof(RegionList);
 }
 static PmWorkspace pm_workspace(void* base, long long slots) {
   PmWorkspace w;
@@ -64,6 +75,8 @@ static PmWorkspace pm_workspace(void* base, long long slots) {
   w.large_count = reinterpret_cast<int32_t*>(p);
   w.large_list = reinterpret_cast<int32_t*>(p + 256);
   w.patches = reinterpret_cast<float*>(p + 256 + align256((size_t)slots * 4));
+  w.regions = reinterpret_cast<RegionList*>(p + 256 + align256((size_t)slots * 4) +
+                                            (size_t)slots * kPatchPitch * kPatchPitch * 4);
   return w;
 }
 
@@ -93,11 +106,35 @@ __device__ __forceinline__ KeptRange kept_range(const float4 b, float rx, float 
   return k;
 }
 
+// ------------------------------------------------------------------------------------------------ phase 0
+// One thread per detection: append it to the list of every region its kept range touches (1-4 for a nucleus), so that
+// a phase-1 CTA does not have to scan the whole tile (121 regions x 2 650 boxes per 1024-px tile otherwise).
+__global__ void __launch_bounds__(256) proto_bin_kernel(const float4* __restrict__ boxes,
+                                                        const int32_t* __restrict__ counts, long long n_slots,
+                                                        int max_det, int mh, int mw, int rxn, int ryn, float rx,
+                                                        float ry, RegionList* __restrict__ regions) {
+  const long long slot = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (slot >= n_slots) return;
+  const int tile = (int)(slot / max_det), d = (int)(slot - (long long)tile * max_det);
+  if (d >= counts[tile]) return;
+  const KeptRange k = kept_range(boxes[slot], rx, ry, mw, mh);
+  if (k.px1 <= k.px0 || k.py1 <= k.py0) return;
+  if (k.px1 - k.px0 > kPatchPitch || k.py1 - k.py0 > kPatchPitch) return;  // per-detection kernel
+  const int rx0 = k.px0 / kRegBoxX, rx1 = (k.px1 - 1) / kRegBoxX;
+  const int ry0 = k.py0 / kRegBoxY, ry1 = (k.py1 - 1) / kRegBoxY;
+  for (int ryy = ry0; ryy <= ry1; ++ryy)
+    for (int rxx = rx0; rxx <= rx1; ++rxx) {
+      RegionList& R = regions[(size_t)tile * (rxn * ryn) + ryy * rxn + rxx];
+      const int pos = atomicAdd(&R.count, 1);
+      if (pos < kRegCap) R.det[pos] = (uint16_t)d;
+    }
+}
+
 // ------------------------------------------------------------------------------------------------ phase 1
 __global__ void __launch_bounds__(kRegThreads, 3) proto_patch_kernel(
     const __grid_constant__ CUtensorMap tmap, const float* __restrict__ coef, const float4* __restrict__ boxes,
     const int32_t* __restrict__ counts, int max_det, int mh, int mw, int rxn, int ryn, float rx, float ry,
-    float* __restrict__ patches) {
+    float* __restrict__ patches, const RegionList* __restrict__ regions) {
   extern __shared__ __align__(128) unsigned char smem_raw[];
   RegSmem& S = *reinterpret_cast<RegSmem*>(smem_raw);
   const int t = threadIdx.x, lane = t & 31, warp = t >> 5;
@@ -105,8 +142,11 @@ __global__ void __launch_bounds__(kRegThreads, 3) proto_patch_kernel(
   const int tile = blockIdx.x / per_tile, reg = blockIdx.x - tile * per_tile;
   const int RY = reg / rxn, RX = reg - RY * rxn;
   const int X0 = RX * kRegBoxX, Y0 = RY * kRegBoxY;
-  const int n = min(counts[tile], max_det);
-  if (n <= 0) return;
+  const RegionList& RL = regions[blockIdx.x];
+  const int listed = RL.count;
+  if (listed <= 0) return;  // nothing reaches into this region: no load at all
+  const bool use_list = listed <= kRegCap;
+  const int n = use_list ? listed : min(counts[tile], max_det);
 
   if (t == 0) {
     mbar_init(&S.bar, 1);
@@ -120,12 +160,19 @@ __global__ void __launch_bounds__(kRegThreads, 3) proto_patch_kernel(
     if (t == 0) S.nlist = 0;
     __syncthreads();
     const int lim = min(base + kRegList, n);
-    for (int d = base + t; d < lim; d += kRegThreads) {
-      const KeptRange k = kept_range(boxes[(size_t)tile * max_det + d], rx, ry, mw, mh);
-      if (k.px1 <= k.px0 || k.py1 <= k.py0) continue;
-      if (k.px1 - k.px0 > kPatchPitch || k.py1 - k.py0 > kPatchPitch) continue;  // per-detection kernel
-      if (k.px1 <= X0 || k.px0 >= X0 + kRegBoxX || k.py1 <= Y0 || k.py0 >= Y0 + kRegBoxY) continue;
-      S.list[atomicAdd(&S.nlist, 1)] = (uint16_t)(d - base);
+    if (use_list) {
+      // the binning pass already listed the detections of this region
+      for (int i = base + t; i < lim; i += kRegThreads) S.list[i - base] = RL.det[i];
+      if (t == 0) S.nlist = lim - base;
+    } else {
+      // overfull list (more than kRegCap detections in one region): scan the tile
+      for (int d = base + t; d < lim; d += kRegThreads) {
+        const KeptRange k = kept_range(boxes[(size_t)tile * max_det + d], rx, ry, mw, mh);
+        if (k.px1 <= k.px0 || k.py1 <= k.py0) continue;
+        if (k.px1 - k.px0 > kPatchPitch || k.py1 - k.py0 > kPatchPitch) continue;  // per-detection kernel
+        if (k.px1 <= X0 || k.px0 >= X0 + kRegBoxX || k.py1 <= Y0 || k.py0 >= Y0 + kRegBoxY) continue;
+        S.list[atomicAdd(&S.nlist, 1)] = (uint16_t)(d - base);
+      }
     }
     __syncthreads();
     const int nl = S.nlist;
@@ -135,7 +182,7 @@ __global__ void __launch_bounds__(kRegThreads, 3) proto_patch_kernel(
       loaded = true;
     }
     for (int e = warp; e < nl; e += kRegWarps) {
-      const size_t slot = (size_t)tile * max_det + base + S.list[e];
+      const size_t slot = (size_t)tile * max_det + (use_list ? 0 : base) + S.list[e];
       const KeptRange k = kept_range(boxes[slot], rx, ry, mw, mh);
       __syncwarp();
       S.coef[warp][lane] = coef[slot * kRegNm + lane];
@@ -370,11 +417,11 @@ int launch_process_mask_regions(const float* protos, const float* coef, const fl
                                 long long capacity_words, int32_t* status, void* workspace, size_t workspace_bytes,
                                 cudaStream_t stream) {
   const long long slots = (long long)bs * max_det;
-  if (!workspace || workspace_bytes < process_mask_workspace_bytes(slots)) return 1;
+  if (!workspace || workspace_bytes < process_mask_workspace_bytes(bs, max_det)) return 1;
   if (nm != kRegNm || (mw & 3) != 0 || ((uintptr_t)protos & 15) != 0 || max_det > 65535) return 1;
   if (getenv("HDY_MASK_GENERIC")) return 1;  // debugging aid: force the per-detection kernel
   const int rxn = (mw + kRegBoxX - 1) / kRegBoxX, ryn = (mh + kRegBoxY - 1) / kRegBoxY;
-  if ((long long)bs * rxn * ryn >= (1ll << 31) || slots >= (1ll << 31)) return 1;
+  if ((long long)bs * rxn * ryn >= (1ll << 31) || slots >= (1ll << 31) || rxn * ryn > kMaxRegionsPerTile) return 1;
   EncodeTiledFn enc = tensor_map_encoder();
   if (!enc) return 1;
   CUtensorMap map;
@@ -388,6 +435,7 @@ int launch_process_mask_regions(const float* protos, const float* coef, const fl
   if (r != CUDA_SUCCESS) return 1;
   const PmWorkspace W = pm_workspace(workspace, slots);
   cudaError_t e = cudaMemsetAsync(W.large_count, 0, 4, stream);
+  if (e == cudaSuccess) e = cudaMemsetAsync(W.regions, 0, (size_t)bs * rxn * ryn * sizeof(RegionList), stream);
   if (e == cudaSuccess)
     e = cudaFuncSetAttribute(proto_patch_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(RegSmem));
   if (e != cudaSuccess) {
@@ -395,8 +443,10 @@ int launch_process_mask_regions(const float* protos, const float* coef, const fl
     return HDY_ERR_CUDA;
   }
   const float4* b4 = reinterpret_cast<const float4*>(boxes);
+  proto_bin_kernel<<<(unsigned)((slots + 255) / 256), 256, 0, stream>>>(b4, counts, slots, max_det, mh, mw, rxn, ryn, rx,
+                                                                        ry, W.regions);
   proto_patch_kernel<<<(unsigned)((long long)bs * rxn * ryn), kRegThreads, sizeof(RegSmem), stream>>>(
-      map, coef, b4, counts, max_det, mh, mw, rxn, ryn, rx, ry, W.patches);
+      map, coef, b4, counts, max_det, mh, mw, rxn, ryn, rx, ry, W.patches, W.regions);
   const unsigned g2 = (unsigned)((slots + kUpWarps - 1) / kUpWarps);
   const bool packed = out_dense == nullptr;
 #define HDY_UP(P, U)                                                                                              \

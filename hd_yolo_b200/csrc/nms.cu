@@ -491,6 +491,100 @@ __global__ void select_scores_kernel(float* __restrict__ scores, const int32_t* 
   }
 }
 
+// Fused gather + S1 for the survivors of the fused head path: ONE WARP per survivor.  Lane c reads channel 4 + c of
+// the survivor's row (one coalesced 128-byte request for obj + classes + the first extra channels), lanes < 1 + nc
+// apply the sigmoid, hierarchical_scores runs as shuffles (yolo_head.py:473-479), the (score, label) select of
+// :336-345 as a shuffle scan, and the raw extra channels (mask coefficients) are written with coalesced stores.
+// Replaces gather_logits_kernel + select_scores_kernel (one thread per survivor walking 37 strided floats each).
+constexpr int kGatherPerWarp = 4;  // survivors per warp: their row loads are issued together (memory-level parallelism)
+
+__global__ void __launch_bounds__(256) gather_select_logits_kernel(
+    const __grid_constant__ LevelTable T, const int32_t* __restrict__ keep_idx,
+    const int32_t* __restrict__ keep_counts, int max_det, const __grid_constant__ HierOps H, float conf_thres,
+    float* __restrict__ out_scores, float* __restrict__ out_level, float* __restrict__ out_extra,
+    float* __restrict__ out_score, int64_t* __restrict__ out_label) {
+  const int tile = blockIdx.y;
+  const int lane = threadIdx.x & 31;
+  const int d0 = (blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5)) * kGatherPerWarp;
+  const int k = min(keep_counts[tile], max_det);
+  if (d0 >= k) return;
+  const int nc = T.nc, no = T.no, ns = 1 + nc, ne = no - 5 - nc;
+  const int nch = ns + ne;              // channels 4 .. 4 + nch of a row
+  const int passes = (nch + 31) >> 5;   // ns <= 32: the scores sit in pass 0
+  const float* rp[kGatherPerWarp];
+  size_t cstride = 1;
+  int lvl[kGatherPerWarp];
+#pragma unroll
+  for (int j = 0; j < kGatherPerWarp; ++j) {
+    const int d = min(d0 + j, k - 1);
+    const int row = keep_idx[(size_t)tile * max_det + d];
+    int l = 0;
+    for (int i = 1; i < T.nl; ++i)
+      if (row >= T.lv[i].row_offset) l = i;
+    const LevelDev& L = T.lv[l];
+    const int rr = row - L.row_offset;
+    lvl[j] = l;
+    if (T.layout == 0) {
+      rp[j] = L.ptr + ((size_t)tile * L.rows + rr) * no;
+    } else {
+      const int plane = L.ny * L.nx;
+      const int a = rr / plane, p = rr - a * plane;
+      rp[j] = L.ptr + ((size_t)(tile * T.na + a) * no) * plane + p;
+      cstride = (size_t)plane;  // per level; re-read below
+    }
+  }
+  // pass 0 of all survivors first (independent loads in flight), then the remaining passes
+  float s[kGatherPerWarp];
+#pragma unroll
+  for (int j = 0; j < kGatherPerWarp; ++j) {
+    const size_t cs = T.layout == 0 ? 1 : (size_t)T.lv[lvl[j]].ny * T.lv[lvl[j]].nx;
+    s[j] = lane < nch ? rp[j][(size_t)(4 + lane) * cs] : 0.f;
+  }
+  for (int ps = 1; ps < passes; ++ps) {
+    float v[kGatherPerWarp];
+    const int c = ps * 32 + lane;
+#pragma unroll
+    for (int j = 0; j < kGatherPerWarp; ++j) {
+      const size_t cs = T.layout == 0 ? 1 : (size_t)T.lv[lvl[j]].ny * T.lv[lvl[j]].nx;
+      v[j] = c < nch ? rp[j][(size_t)(4 + c) * cs] : 0.f;
+    }
+#pragma unroll
+    for (int j = 0; j < kGatherPerWarp; ++j)
+      if (out_extra && c < nch && d0 + j < k) out_extra[((size_t)tile * max_det + d0 + j) * ne + (c - ns)] = v[j];
+  }
+  (void)cstride;
+#pragma unroll
+  for (int j = 0; j < kGatherPerWarp; ++j) {
+    if (d0 + j >= k) break;  // warp-uniform
+    const size_t o = (size_t)tile * max_det + d0 + j;
+    const float raw = s[j];
+    if (out_extra && lane >= ns && lane < nch) out_extra[o * ne + (lane - ns)] = raw;
+    float sc = lane < ns ? sigmoidf_ref(raw) : 0.f;
+    // hierarchical_scores: x[:, dst] *= x[:, src], in order
+    for (int i = 0; i < H.n; ++i) {
+      const float vs = __shfl_sync(0xffffffffu, sc, H.src[i]);
+      if (lane == H.dst[i]) sc = __fmul_rn(sc, vs);
+    }
+    if (lane < ns) out_scores[o * ns + lane] = sc;
+    // cls_scores, cls_labels = scores[..., 1:].max(1)   (first maximal value)
+    float best = __shfl_sync(0xffffffffu, sc, 1);
+    int arg = 0;
+    for (int c = 1; c < nc; ++c) {
+      const float v = __shfl_sync(0xffffffffu, sc, 1 + c);
+      if (v > best) {
+        best = v;
+        arg = c;
+      }
+    }
+    if (lane == 0) {
+      const bool cls_ok = best > conf_thres;
+      if (out_score) out_score[o] = cls_ok ? best : sc;
+      if (out_label) out_label[o] = cls_ok ? (int64_t)(arg + 1) : (int64_t)-100;
+      if (out_level) out_level[o] = (float)lvl[j];
+    }
+  }
+}
+
 }  // namespace hdy
 
 using namespace hdy;
@@ -590,6 +684,42 @@ int hdy_gather_logits(const hdy_level_t* levels_host, int nl, int bs, int na, in
   gather_logits_kernel<<<grid, 128, 0, (cudaStream_t)stream>>>(T, keep_idx, keep_counts, max_det, out_scores,
                                                                out_level, out_extra);
   return check_launch("hdy_gather_logits");
+}
+
+static int fill_hier_ops(const int32_t* hier_ops_host, int n_ops, int nc, HierOps* H) {
+  HDY_REQUIRE(n_ops >= 0 && n_ops <= 2 * HDY_MAX_SCORES && (n_ops == 0 || hier_ops_host), "bad hier ops");
+  H->n = n_ops;
+  for (int i = 0; i < n_ops; ++i) {
+    const int d = hier_ops_host[2 * i], s = hier_ops_host[2 * i + 1];
+    HDY_REQUIRE(d >= 0 && d <= nc && s >= 0 && s <= nc && d != s, "hier op %d: (%d,%d) out of range", i, d, s);
+    H->dst[i] = (int8_t)d;
+    H->src[i] = (int8_t)s;
+  }
+  return HDY_OK;
+}
+
+int hdy_gather_select_logits(const hdy_level_t* levels_host, int nl, int bs, int na, int nc, int no, int layout,
+                             const int32_t* keep_idx, const int32_t* keep_counts, int max_det,
+                             const int32_t* hier_ops_host, int n_ops, float conf_thres, float* out_scores,
+                             float* out_level, float* out_extra, float* out_score, int64_t* out_label,
+                             hdy_stream_t stream) {
+  HDY_REQUIRE(bs >= 0 && max_det > 0 && nc >= 1 && 1 + nc <= 32 && no >= 5 + nc,
+              "hdy_gather_select_logits: bad sizes (1 + nc must be <= 32; use hdy_gather_logits + hdy_select_scores)");
+  HDY_REQUIRE(keep_idx && keep_counts && out_scores, "hdy_gather_select_logits: NULL pointer");
+  LevelTable T;
+  int rc = build_level_table(levels_host, nl, na, no, layout, 256, &T);
+  if (rc) return rc;
+  T.nc = nc;
+  HierOps H;
+  rc = fill_hier_ops(hier_ops_host, n_ops, nc, &H);
+  if (rc) return rc;
+  if (bs == 0) return HDY_OK;
+  HDY_REQUIRE(bs <= 65535, "hdy_gather_select_logits: bs > 65535");
+  dim3 grid((unsigned)((max_det + 8 * kGatherPerWarp - 1) / (8 * kGatherPerWarp)), (unsigned)bs);
+  gather_select_logits_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(T, keep_idx, keep_counts, max_det, H, conf_thres,
+                                                                      out_scores, out_level, out_extra, out_score,
+                                                                      out_label);
+  return check_launch("hdy_gather_select_logits");
 }
 
 int hdy_select_scores(float* scores, const int32_t* keep_counts, int bs, int max_det, int nc,

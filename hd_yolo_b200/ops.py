@@ -558,14 +558,19 @@ def detect_postprocess(dets: List[torch.Tensor], spec: HeadSpec, conf_thres: flo
     lvl = torch.empty((bs, md), dtype=torch.float32, device=dev)
     ne = no - 5 - nc
     extra = torch.empty((bs, md, ne), dtype=torch.float32, device=dev) if ne > 0 else None
-    _call("hdy_gather_logits", levels, spec.nl, bs, spec.na, nc, no, layout, ptr(keep_idx), ptr(keep_counts), md,
-                              ptr(scores_full), ptr(lvl), ptr(extra), _stream())
     score = torch.empty((bs, md), dtype=torch.float32, device=dev)
     label = torch.empty((bs, md), dtype=torch.int64, device=dev)
     ops = default_hier_ops(nc) if hier_ops is None else hier_ops
     flat = (C.c_int32 * (2 * len(ops)))(*[v for p in ops for v in p])
-    _call("hdy_select_scores", ptr(scores_full), ptr(keep_counts), bs, md, nc, flat, len(ops), cthr, ptr(score),
-                              ptr(label), _stream())
+    if 1 + nc <= 32:
+        _call("hdy_gather_select_logits", levels, spec.nl, bs, spec.na, nc, no, layout, ptr(keep_idx),
+              ptr(keep_counts), md, flat, len(ops), cthr, ptr(scores_full), ptr(lvl), ptr(extra), ptr(score),
+              ptr(label), _stream())
+    else:
+        _call("hdy_gather_logits", levels, spec.nl, bs, spec.na, nc, no, layout, ptr(keep_idx), ptr(keep_counts), md,
+              ptr(scores_full), ptr(lvl), ptr(extra), _stream())
+        _call("hdy_select_scores", ptr(scores_full), ptr(keep_counts), bs, md, nc, flat, len(ops), cthr, ptr(score),
+              ptr(label), _stream())
     return DetectBatch(keep_box, scores_full, score, label, lvl, extra, keep_idx, keep_counts, cand.counts, md)
 
 

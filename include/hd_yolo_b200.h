@@ -169,6 +169,14 @@ HDY_API int hdy_select_scores(float* scores, const int32_t* keep_counts, int bs,
                       const int32_t* hier_ops_host, int n_ops, float conf_thres,
                       float* out_score, int64_t* out_label, hdy_stream_t stream);
 
+/* hdy_gather_logits + hdy_select_scores in one launch (one warp per survivor, coalesced), for 1 + nc <= 32:
+ * out_scores receives the scores AFTER hierarchical_scores, exactly what the two-call sequence leaves there. */
+HDY_API int hdy_gather_select_logits(const hdy_level_t* levels_host, int nl, int bs, int na, int nc, int no,
+                                     int layout, const int32_t* keep_idx, const int32_t* keep_counts, int max_det,
+                                     const int32_t* hier_ops_host, int n_ops, float conf_thres, float* out_scores,
+                                     float* out_level, float* out_extra, float* out_score, int64_t* out_label,
+                                     hdy_stream_t stream);
+
 /* -------------------------------------------------------------------- masks */
 
 /* M1: mask tail of Detect.compute_outputs (yolo_head.py:332, 346-353) for K detections:

@@ -364,3 +364,29 @@ def test_nms_small_nuclei_with_large_boxes(cuda_device, n_small, n_large, seed):
         ref = torchvision.ops.nms(boxes, scores, thr)
         got = hdy.nms(boxes.to(cuda_device), scores.to(cuda_device), thr).cpu()
         assert torch.equal(got, ref)
+
+
+@pytest.mark.parametrize("nc,extra,layout", [(40, 0, 0), (40, 3, 1), (31, 5, 0), (4, 32, 1)])
+def test_detect_postprocess_many_classes_and_extras(cuda_device, nc, extra, layout):
+    """1 + nc > 32 takes hdy_gather_logits + hdy_select_scores, otherwise the fused warp-per-survivor kernel; both
+    must give what the oracle gives on the device-decoded rows, and carry the raw extra channels."""
+    dets = synth.nuclei_logits(2, 160, nc, 150, seed=nc + extra, extra=extra, conf=0.25)
+    spec = hdy.HeadSpec(synth.ANCHORS_3, synth.STRIDES_3, nc=nc, no=5 + nc + extra)
+    d0 = [d.to(cuda_device) for d in dets]
+    cat = hdy.decode_concat(d0, spec)
+    ref = _oracle_on_device_decode(cat, nc, 0.25, 0.45, 300)
+    src = d0
+    if layout == 1:
+        src = [d.permute(0, 1, 4, 2, 3).reshape(d.shape[0], -1, d.shape[2], d.shape[3]).contiguous() for d in d0]
+    out = hdy.detect_postprocess(src, spec, 0.25, 0.45, 300, layout=layout)
+    lst = out.to_list()
+    rawcat = torch.cat([d.reshape(2, -1, spec.no) for d in dets], 1)
+    for i, (a, b) in enumerate(zip(lst, ref)):
+        k = len(b['boxes'])
+        assert k > 0 and len(a['boxes']) == k
+        assert torch.equal(a['boxes'].cpu(), b['boxes'])
+        assert torch.equal(a['scores'].cpu(), b['scores'])
+        assert torch.equal(a['labels'].cpu(), b['labels'])
+        if extra:
+            rows = out.rows[i, :k].cpu().long()
+            assert torch.equal(out.extra[i, :k].cpu(), rawcat[i, rows, 5 + nc:])
