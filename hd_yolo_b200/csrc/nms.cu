@@ -496,91 +496,74 @@ __global__ void select_scores_kernel(float* __restrict__ scores, const int32_t* 
 // apply the sigmoid, hierarchical_scores runs as shuffles (yolo_head.py:473-479), the (score, label) select of
 // :336-345 as a shuffle scan, and the raw extra channels (mask coefficients) are written with coalesced stores.
 // Replaces gather_logits_kernel + select_scores_kernel (one thread per survivor walking 37 strided floats each).
-constexpr int kGatherPerWarp = 4;  // survivors per warp: their row loads are issued together (memory-level parallelism)
-
+// G lanes per survivor (G = 8, 16 or 32 >= 1 + nc), 32 / G survivors per warp: one sigmoid evaluation, one round of
+// hierarchical-score shuffles and one select scan serve all of the warp's survivors, and their scattered row loads
+// are in flight together.
+template <int G>
 __global__ void __launch_bounds__(256) gather_select_logits_kernel(
     const __grid_constant__ LevelTable T, const int32_t* __restrict__ keep_idx,
     const int32_t* __restrict__ keep_counts, int max_det, const __grid_constant__ HierOps H, float conf_thres,
     float* __restrict__ out_scores, float* __restrict__ out_level, float* __restrict__ out_extra,
     float* __restrict__ out_score, int64_t* __restrict__ out_label) {
+  constexpr int SPW = 32 / G;
   const int tile = blockIdx.y;
-  const int lane = threadIdx.x & 31;
-  const int d0 = (blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5)) * kGatherPerWarp;
+  const int lane = threadIdx.x & 31, grp = lane / G, g = lane - grp * G;
+  const int d0 = (blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5)) * SPW;
   const int k = min(keep_counts[tile], max_det);
   if (d0 >= k) return;
   const int nc = T.nc, no = T.no, ns = 1 + nc, ne = no - 5 - nc;
-  const int nch = ns + ne;              // channels 4 .. 4 + nch of a row
-  const int passes = (nch + 31) >> 5;   // ns <= 32: the scores sit in pass 0
-  const float* rp[kGatherPerWarp];
-  size_t cstride = 1;
-  int lvl[kGatherPerWarp];
-#pragma unroll
-  for (int j = 0; j < kGatherPerWarp; ++j) {
-    const int d = min(d0 + j, k - 1);
-    const int row = keep_idx[(size_t)tile * max_det + d];
-    int l = 0;
-    for (int i = 1; i < T.nl; ++i)
-      if (row >= T.lv[i].row_offset) l = i;
-    const LevelDev& L = T.lv[l];
-    const int rr = row - L.row_offset;
-    lvl[j] = l;
-    if (T.layout == 0) {
-      rp[j] = L.ptr + ((size_t)tile * L.rows + rr) * no;
-    } else {
-      const int plane = L.ny * L.nx;
-      const int a = rr / plane, p = rr - a * plane;
-      rp[j] = L.ptr + ((size_t)(tile * T.na + a) * no) * plane + p;
-      cstride = (size_t)plane;  // per level; re-read below
+  const int d = min(d0 + grp, k - 1);
+  const bool live = d0 + grp < k;
+  const size_t o = (size_t)tile * max_det + d;
+  const int row = keep_idx[o];
+  int l = 0;
+  for (int i = 1; i < T.nl; ++i)
+    if (row >= T.lv[i].row_offset) l = i;
+  const LevelDev& L = T.lv[l];
+  const int rr = row - L.row_offset;
+  const float* rp;
+  int cs = 1;
+  if (T.layout == 0) {
+    rp = L.ptr + ((size_t)tile * L.rows + rr) * no;
+  } else {
+    const int plane = L.ny * L.nx;
+    const int a = rr / plane, p = rr - a * plane;
+    rp = L.ptr + ((size_t)(tile * T.na + a) * no) * plane + p;
+    cs = plane;
+  }
+  float sc = g < ns ? sigmoidf_ref(rp[(size_t)(4 + g) * cs]) : 0.f;
+  // hierarchical_scores: x[:, dst] *= x[:, src], in order
+  for (int i = 0; i < H.n; ++i) {
+    const float vs = __shfl_sync(0xffffffffu, sc, H.src[i], G);
+    if (g == H.dst[i]) sc = __fmul_rn(sc, vs);
+  }
+  if (live && g < ns) out_scores[o * ns + g] = sc;
+  // cls_scores, cls_labels = scores[..., 1:].max(1)   (first maximal value)
+  float best = __shfl_sync(0xffffffffu, sc, 1, G);
+  int arg = 0;
+  for (int c = 1; c < nc; ++c) {
+    const float v = __shfl_sync(0xffffffffu, sc, 1 + c, G);
+    if (v > best) {
+      best = v;
+      arg = c;
     }
   }
-  // pass 0 of all survivors first (independent loads in flight), then the remaining passes
-  float s[kGatherPerWarp];
-#pragma unroll
-  for (int j = 0; j < kGatherPerWarp; ++j) {
-    const size_t cs = T.layout == 0 ? 1 : (size_t)T.lv[lvl[j]].ny * T.lv[lvl[j]].nx;
-    s[j] = lane < nch ? rp[j][(size_t)(4 + lane) * cs] : 0.f;
+  if (live && g == 0) {
+    const bool cls_ok = best > conf_thres;
+    if (out_score) out_score[o] = cls_ok ? best : sc;
+    if (out_label) out_label[o] = cls_ok ? (int64_t)(arg + 1) : (int64_t)-100;
+    if (out_level) out_level[o] = (float)l;
   }
-  for (int ps = 1; ps < passes; ++ps) {
-    float v[kGatherPerWarp];
-    const int c = ps * 32 + lane;
+  // raw extra channels (mask coefficients): the whole warp copies one survivor's run at a time, coalesced
+  if (out_extra && ne > 0) {
+    const unsigned long long rp_bits = (unsigned long long)(uintptr_t)rp;
 #pragma unroll
-    for (int j = 0; j < kGatherPerWarp; ++j) {
-      const size_t cs = T.layout == 0 ? 1 : (size_t)T.lv[lvl[j]].ny * T.lv[lvl[j]].nx;
-      v[j] = c < nch ? rp[j][(size_t)(4 + c) * cs] : 0.f;
-    }
-#pragma unroll
-    for (int j = 0; j < kGatherPerWarp; ++j)
-      if (out_extra && c < nch && d0 + j < k) out_extra[((size_t)tile * max_det + d0 + j) * ne + (c - ns)] = v[j];
-  }
-  (void)cstride;
-#pragma unroll
-  for (int j = 0; j < kGatherPerWarp; ++j) {
-    if (d0 + j >= k) break;  // warp-uniform
-    const size_t o = (size_t)tile * max_det + d0 + j;
-    const float raw = s[j];
-    if (out_extra && lane >= ns && lane < nch) out_extra[o * ne + (lane - ns)] = raw;
-    float sc = lane < ns ? sigmoidf_ref(raw) : 0.f;
-    // hierarchical_scores: x[:, dst] *= x[:, src], in order
-    for (int i = 0; i < H.n; ++i) {
-      const float vs = __shfl_sync(0xffffffffu, sc, H.src[i]);
-      if (lane == H.dst[i]) sc = __fmul_rn(sc, vs);
-    }
-    if (lane < ns) out_scores[o * ns + lane] = sc;
-    // cls_scores, cls_labels = scores[..., 1:].max(1)   (first maximal value)
-    float best = __shfl_sync(0xffffffffu, sc, 1);
-    int arg = 0;
-    for (int c = 1; c < nc; ++c) {
-      const float v = __shfl_sync(0xffffffffu, sc, 1 + c);
-      if (v > best) {
-        best = v;
-        arg = c;
-      }
-    }
-    if (lane == 0) {
-      const bool cls_ok = best > conf_thres;
-      if (out_score) out_score[o] = cls_ok ? best : sc;
-      if (out_label) out_label[o] = cls_ok ? (int64_t)(arg + 1) : (int64_t)-100;
-      if (out_level) out_level[o] = (float)lvl[j];
+    for (int j = 0; j < SPW; ++j) {
+      const float* rj = (const float*)(uintptr_t)__shfl_sync(0xffffffffu, rp_bits, j * G);
+      const int csj = __shfl_sync(0xffffffffu, cs, j * G);
+      if (d0 + j >= k) break;  // warp-uniform
+      float* oe = out_extra + ((size_t)tile * max_det + d0 + j) * ne;
+      for (int c = lane; c < ne; c += 32) oe[c] = rj[(size_t)(5 + nc + c) * csj];
     }
   }
 }
@@ -715,10 +698,19 @@ int hdy_gather_select_logits(const hdy_level_t* levels_host, int nl, int bs, int
   if (rc) return rc;
   if (bs == 0) return HDY_OK;
   HDY_REQUIRE(bs <= 65535, "hdy_gather_select_logits: bs > 65535");
-  dim3 grid((unsigned)((max_det + 8 * kGatherPerWarp - 1) / (8 * kGatherPerWarp)), (unsigned)bs);
-  gather_select_logits_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(T, keep_idx, keep_counts, max_det, H, conf_thres,
-                                                                      out_scores, out_level, out_extra, out_score,
-                                                                      out_label);
+  const int G = 1 + nc <= 8 ? 8 : (1 + nc <= 16 ? 16 : 32);
+  const int per_cta = 8 * (32 / G);
+  dim3 grid((unsigned)((max_det + per_cta - 1) / per_cta), (unsigned)bs);
+  cudaStream_t st = (cudaStream_t)stream;
+  if (G == 8)
+    gather_select_logits_kernel<8><<<grid, 256, 0, st>>>(T, keep_idx, keep_counts, max_det, H, conf_thres, out_scores,
+                                                         out_level, out_extra, out_score, out_label);
+  else if (G == 16)
+    gather_select_logits_kernel<16><<<grid, 256, 0, st>>>(T, keep_idx, keep_counts, max_det, H, conf_thres, out_scores,
+                                                          out_level, out_extra, out_score, out_label);
+  else
+    gather_select_logits_kernel<32><<<grid, 256, 0, st>>>(T, keep_idx, keep_counts, max_det, H, conf_thres, out_scores,
+                                                          out_level, out_extra, out_score, out_label);
   return check_launch("hdy_gather_select_logits");
 }
 
