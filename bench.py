@@ -58,6 +58,7 @@ def parse():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-slide", action="store_true")
+    ap.add_argument("--inflight", type=int, default=3, help="steps in flight (CUDA graphs on separate streams)")
     a = ap.parse_args()
     if a.steps is None:
         a.steps = 5 if a.workload == "slide" else 200
@@ -264,7 +265,7 @@ def run_tiles(args, wl, c):
     N = spec.rows_per_tile(shapes)
     mh = mw = tile // 4
     in_bytes = bs * N * spec.no * 4 + (bs * NM * mh * mw * 4 if masks == "proto" else 0)
-    R = max(2, int(2.5 * L2_BYTES / in_bytes) + 1)       # rotate input batches so that reads miss L2
+    R = max(2, args.inflight, int(2.5 * L2_BYTES / in_bytes) + 1)   # rotate input batches so that reads miss L2
     batches = [synth.nuclei_logits(bs, tile, nc, wl["n_cand"], seed=1000 * c.rank + r, conf=wl["conf"], extra=extra,
                                    generator_device="cuda") for r in range(R)]
     protos = None
@@ -301,13 +302,13 @@ def run_tiles(args, wl, c):
     # Every graph has its own scratch slot, so two steps can be in flight on two streams: the per-tile NMS occupies
     # only `bs` of the 148 SMs and the tails of the other kernels leave SMs idle, which the neighbouring step fills.
     graphs = [hdy.CapturedStep(lambda r=r: step(r), slot=r) for r in range(R)]
-    side = [torch.cuda.Stream(), torch.cuda.Stream()]
+    side = [torch.cuda.Stream() for _ in range(max(1, args.inflight))]
 
     def gstep(i):
         return graphs[i % R]()
 
     def gstep2(i):
-        return graphs[i % R](stream=side[(i % R) % 2])
+        return graphs[i % R](stream=side[(i % R) % len(side)])
 
     for i in range(W):
         gstep(i)
@@ -358,6 +359,13 @@ def run_tiles(args, wl, c):
     dom_ms, dom_bytes = stages[dom]["ms"], alg[dom]
     achieved = dom_bytes / (dom_ms * 1e-3) / 1e9
     step_bytes = sum(v["alg_bytes"] for v in stages.values() if v["alg_bytes"])
+    traffic = None
+    try:   # DRAM bytes per launch of the dominant call, from the committed ncu --set full capture of this workload
+        traffic = json.load(open(os.path.join(ROOT, "profiles", "r01_traffic.json")))[args.workload][dom]["bytes"]
+        if masks != "proto" and dom == "hdy_filter_compact_logits":
+            traffic = None if args.workload != "tiles1024" else traffic
+    except Exception:
+        pass
 
     # ---- e2e: host (pinned) inputs, H2D + D2H inside the timed region ---------------------------------------
     e2e = None
@@ -414,12 +422,12 @@ def run_tiles(args, wl, c):
                    "stages": "decode+filter+compact, nms, score/label select" +
                              (", process_mask (proto contraction, sigmoid, crop, upsample, >0.5, bit-packed)" if masks == "proto" else ""),
                    "l2": f"{R} rotating input batches ({R * in_bytes / 1e6:.0f} MB) > 126 MB L2",
-                   "launch": "one CUDA graph per input batch (hdy.CapturedStep), replayed; two steps in flight on "
-                             "two streams (each graph has its own scratch slot)",
+                   "launch": f"one CUDA graph per input batch (hdy.CapturedStep), replayed; {len(side)} steps in "
+                             "flight on as many streams (each graph has its own scratch slot)",
                    "ms_per_step_one_stream": ms_serial / K},
         "boxes_per_s": tiles_per_s * cand,
         "roofline": {"bound": "hbm", "kernel": dom, "achieved": achieved, "peak": peak, "unit": "GB/s",
-                     "frac": achieved / peak, "traffic": None, "peak_source": peak_src,
+                     "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
                      "algorithmic_bytes_per_launch": dom_bytes, "kernel_ms": dom_ms},
         "stages": stages,
         "pipeline": {"algorithmic_bytes_per_step": step_bytes, "achieved_gbs": step_bytes / (ms / K * 1e-3) / 1e9,
@@ -553,7 +561,7 @@ def main():
         line = run_tiles(args, wl, c)
         if not args.no_slide:
             sargs = argparse.Namespace(**vars(args))
-            line["slide"] = run_slide(sargs, WORKLOADS["slide"], c, steps=2, warmup=1, want_e2e=False)
+            line["slide"] = run_slide(sargs, WORKLOADS["slide"], c, steps=3, warmup=2, want_e2e=False)
 
     cpu = None
     if c.rank == 0 and not args.no_cpu_baseline:

@@ -52,7 +52,7 @@ template <int WARPS, int NBUF, int RPL>
 __global__ void __launch_bounds__(WARPS * 32) filter_compact_tma_kernel(
     const __grid_constant__ LevelTable T, const __grid_constant__ ItemTable I, int bs, int buf_bytes,
     float t_lo, float conf_thres, float min_size, int cap, uint64_t* __restrict__ cand_keys,
-    float4* __restrict__ cand_boxes, int32_t* __restrict__ counts, int32_t* __restrict__ status, int keep_rows_in_l2) {
+    float4* __restrict__ cand_boxes, int32_t* __restrict__ counts, int32_t* __restrict__ status) {
   extern __shared__ __align__(128) unsigned char smem_raw[];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int no = T.no;
@@ -160,14 +160,6 @@ __global__ void __launch_bounds__(WARPS * 32) filter_compact_tma_kernel(
         // remove_small_boxes(min_size)                                             utils_general.py:332
         cand = (__fsub_rn(box.z, box.x) >= min_size) && (__fsub_rn(box.w, box.y) >= min_size);
         key = make_key(p_obj, (uint32_t)(L.row_offset + B.row));
-        if (cand && keep_rows_in_l2) {
-          // The survivors' score / extra channels are gathered again after NMS (hdy_gather_select_logits); by then
-          // the stream has pushed the row out of L2.  Mark its lines evict_last now, while they are still there.
-          const char* rowp = reinterpret_cast<const char*>(L.ptr + ((size_t)tile * L.rows + B.row) * no);
-          const int row_bytes = no * 4;
-          for (int ofs = 16; ofs < row_bytes + 112; ofs += 128)
-            asm volatile("prefetch.global.L2::evict_last [%0];" ::"l"(rowp + min(ofs, row_bytes - 4)));
-        }
       }
     }
     unsigned todo = __ballot_sync(0xffffffffu, cand);
@@ -275,7 +267,7 @@ static int launch_variant(const LevelTable& T, const ItemTable& I, int bs, int b
   if (grid > need) grid = need;
   filter_compact_tma_kernel<WARPS, NBUF, RPL><<<(unsigned)grid, WARPS * 32, smem, stream>>>(
       T, I, bs, buf_bytes, t_lo, conf_thres, min_size, cap, cand_keys, reinterpret_cast<float4*>(cand_boxes),
-      counts, status, getenv("HDY_NO_L2_KEEP") ? 0 : 1);
+      counts, status);
   return check_launch("hdy_filter_compact_logits(tma)");
 }
 

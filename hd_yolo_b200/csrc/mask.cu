@@ -249,6 +249,30 @@ __global__ void pm_geometry_kernel(const float4* __restrict__ boxes, const int32
   reinterpret_cast<int4*>(geom4)[i] = out;
 }
 
+// pm_geometry_kernel + scan_words_local_kernel in one launch (the step is a chain of small dependent kernels)
+__global__ void __launch_bounds__(kScanChunk) pm_geometry_scan_kernel(
+    const float4* __restrict__ boxes, const int32_t* __restrict__ counts, long long K, int max_det, int mh, int mw,
+    int ih, int iw, int upsample, float rx, float ry, int32_t* __restrict__ geom4, int64_t* __restrict__ offsets) {
+  __shared__ long long warp_sum[32];
+  const long long i = (long long)blockIdx.x * kScanChunk + threadIdx.x;
+  long long v = 0;
+  if (i < K) {
+    const int tile = (int)(i / max_det), d = (int)(i - (long long)tile * max_det);
+    int4 out = make_int4(0, 0, 0, 0);
+    if (d < counts[tile]) {
+      const PMGeom g = pm_geometry(boxes[i], mh, mw, ih, iw, upsample, rx, ry);
+      out = make_int4(g.x0, g.y0, g.w, g.h);
+    }
+    reinterpret_cast<int4*>(geom4)[i] = out;
+    v = (long long)((out.z + 31) >> 5) * out.w;
+  }
+  const long long incl = block_incl_scan_ll(v, warp_sum);
+  if (i < K && threadIdx.x != 0) offsets[i] = incl - v;
+  const long long last = min((long long)(blockIdx.x + 1) * kScanChunk, K) - 1;
+  if (i == last) offsets[last + 1] = incl;
+  if (i == 0) offsets[0] = 0;
+}
+
 constexpr int kPmTile = 32;               // proto pixels per staged tile side
 constexpr int kPmStage = kPmTile + 1;     // + 1 halo for the second bilinear tap
 constexpr int kPmThreads = 128;
@@ -513,10 +537,16 @@ int hdy_process_mask_geometry(const float* boxes, const int32_t* counts, int bs,
     HDY_REQUIRE(boxes && counts && geom && ((uintptr_t)boxes & 15) == 0 && ((uintptr_t)geom & 15) == 0,
                 "process_mask_geometry: NULL or misaligned pointer");
     const float rx = (float)((double)mw / (double)iw), ry = (float)((double)mh / (double)ih);
-    pm_geometry_kernel<<<(unsigned)((K + 127) / 128), 128, 0, st>>>(reinterpret_cast<const float4*>(boxes), counts, bs,
-                                                                    max_det, mh, mw, ih, iw, upsample, rx, ry, geom);
+    const unsigned nb = (unsigned)((K + kScanChunk - 1) / kScanChunk);
+    pm_geometry_scan_kernel<<<nb, kScanChunk, 0, st>>>(reinterpret_cast<const float4*>(boxes), counts, K, max_det, mh,
+                                                       mw, ih, iw, upsample, rx, ry, geom, offsets);
+    if (nb > 1) {
+      scan_words_bases_kernel<<<1, kScanChunk, 0, st>>>(K, offsets);
+      scan_words_add_kernel<<<nb - 1, kScanChunk, 0, st>>>(K, offsets);
+    }
+  } else {
+    launch_scan_words(geom, K, offsets, st);
   }
-  launch_scan_words(geom, K, offsets, st);
   return check_launch("hdy_process_mask_geometry");
 }
 
