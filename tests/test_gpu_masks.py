@@ -193,3 +193,26 @@ def test_process_mask_other_prototype_counts(cuda_device):
     ref = port.process_mask(protos, coef, boxes.clone(), (ih, iw), upsample=True)
     out = hm.process_mask(protos.to(cuda_device), coef.to(cuda_device), boxes.to(cuda_device), (ih, iw), upsample=True)
     assert _agreement(out.cpu(), ref) >= AGREE
+
+
+def test_process_mask_crowded_region_and_empty_regions(cuda_device):
+    """More than 254 detections in one 24x24 proto region (the region's list overflows and the CTA falls back to
+    scanning the tile) while most regions of the plane are touched by nobody (they load nothing)."""
+    g = torch.Generator().manual_seed(21)
+    n, mh, mw, ih, iw = 600, 128, 128, 512, 512
+    protos = torch.randn((32, mh, mw), generator=g)
+    coef = torch.randn((n, 32), generator=g) * 0.5
+    c = torch.cat([200.0 + 40.0 * torch.rand((500, 2), generator=g),          # 500 boxes inside ~2 regions
+                   torch.rand((100, 2), generator=g) * 500.0])
+    wh = 10.0 + 30.0 * torch.rand((n, 2), generator=g)
+    boxes = torch.cat([c - wh / 2, c + wh / 2], 1)
+    dev = cuda_device
+    for upsample in (False, True):
+        ref = port.process_mask(protos, coef, boxes.clone(), (ih, iw), upsample=upsample)
+        out = hm.process_mask(protos.to(dev), coef.to(dev), boxes.to(dev), (ih, iw), upsample=upsample)
+        assert _agreement(out.cpu(), ref) >= AGREE
+        counts = torch.tensor([n], dtype=torch.int32, device=dev)
+        packed = hm.process_mask_packed(protos.to(dev)[None], coef.to(dev)[None], boxes.to(dev)[None], counts,
+                                        (ih, iw), upsample=upsample)
+        packed.check()
+        assert torch.equal(packed.to_dense(), out.to(torch.uint8))
