@@ -151,11 +151,12 @@ def cpu_sample_inputs(wl, masks, sample, seed=1):
     return dets, protos
 
 
-def time_cpu(wl, masks, budget_s, max_reps):
-    """Bounded CPU timing of the oracle port on all host threads.  Returns (tiles/s, cores, sample text)."""
+def time_cpu(wl, masks, budget_s, max_reps, threads=None):
+    """Bounded CPU timing of the oracle port on `threads` host threads (default: all).  Returns (tiles/s, threads,
+    sample text)."""
     import torch
     from hd_yolo_b200 import synth
-    torch.set_num_threads(os.cpu_count() or 1)
+    torch.set_num_threads(threads or os.cpu_count() or 1)
     sample = 2 if masks == "proto" else 8
     dets, protos = cpu_sample_inputs(wl, masks, sample)
     spec_args = (synth.ANCHORS_3, synth.STRIDES_3)
@@ -427,7 +428,8 @@ def run_tiles(args, wl, c):
                    "ms_per_step_one_stream": ms_serial / K},
         "boxes_per_s": tiles_per_s * cand,
         "roofline": {"bound": "hbm", "kernel": dom, "achieved": achieved, "peak": peak, "unit": "GB/s",
-                     "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
+                     "frac": achieved / peak, "frac_of_nominal_8000": achieved / 8000.0, "traffic": traffic,
+                     "peak_source": peak_src,
                      "algorithmic_bytes_per_launch": dom_bytes, "kernel_ms": dom_ms},
         "stages": stages,
         "pipeline": {"algorithmic_bytes_per_step": step_bytes, "achieved_gbs": step_bytes / (ms / K * 1e-3) / 1e9,
@@ -568,6 +570,10 @@ def main():
         masks = args.masks if args.workload != "slide" else "none"
         v, cores, sample = time_cpu(wl, masks, budget_s=15.0, max_reps=30)
         cpu = {"value": v, "unit": "tiles/s", "cores": cores, "kind": "port", "sample": sample}
+        # the reference caps its own thread pool at min(8, ncpu - 1) (metayolo/__init__.py:21,31): second data point
+        v8, c8, _ = time_cpu(wl, masks, budget_s=6.0, max_reps=10, threads=min(8, max(1, (os.cpu_count() or 2) - 1)))
+        cpu["value_reference_threads"] = v8
+        cpu["reference_threads"] = c8
     line["cpu_baseline"] = cpu
     if c.rank == 0:
         print(json.dumps(line))
