@@ -53,7 +53,7 @@ def parse():
     ap.add_argument("--warmup", type=int, default=None)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="tiles640", choices=list(WORKLOADS))
-    ap.add_argument("--masks", default="proto", choices=["proto", "none"])
+    ap.add_argument("--masks", default="proto", choices=["proto", "paste", "none"])
     ap.add_argument("--slide-size", type=int, default=100000)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
@@ -128,13 +128,19 @@ def cpu_reference_pass(dets_cpu, protos_cpu, wl, spec_args, masks):
     params = {'conf_thres': wl["conf"], 'iou_thres': wl["iou"], 'max_det': wl["max_det"]}
     if masks == "none":
         return port.compute_outputs(preds, nc, params)
+    import torch
     cat = port.concat_levels(preds)
     res = port.nms_per_image(cat, nc, wl["conf"], wl["iou"], wl["max_det"])
     out = []
     for i, r in enumerate(res):
         s, l = port.select_scores(r['scores'][:, :1 + nc].clone(), wl["conf"], port.default_descendants(nc))
-        coef = r['extra'][:, :NM]      # extra = raw coefficient channels + level id; the coefficients come first
-        m = port.process_mask(protos_cpu[i], coef, r['boxes'], (wl["tile"], wl["tile"]), upsample=True)
+        if masks == "proto":
+            coef = r['extra'][:, :NM]      # extra = raw coefficient channels + level id; the coefficients come first
+            m = port.process_mask(protos_cpu[i], coef, r['boxes'], (wl["tile"], wl["tile"]), upsample=True)
+        else:                              # reference variant A: mask select + paste_masks_in_image, > 0.5
+            k = len(r['boxes'])
+            sel = port.mask_select(protos_cpu[i][:k], l, torch.tensor([-1, 0, 0, 1, 1]))
+            m = port.paste_masks_in_image(sel, r['boxes'], (wl["tile"], wl["tile"]), padding=1) > 0.5
         out.append((r['boxes'], s, l, m))
     return out
 
@@ -148,6 +154,9 @@ def cpu_sample_inputs(wl, masks, sample, seed=1):
     if masks == "proto":
         g = torch.Generator().manual_seed(seed + 7)
         protos = torch.randn((sample, NM, wl["tile"] // 4, wl["tile"] // 4), generator=g)
+    elif masks == "paste":
+        g = torch.Generator().manual_seed(seed + 8)
+        protos = torch.randn((sample, min(wl["max_det"], wl["cap"]), 2, 28, 28), generator=g)
     return dets, protos
 
 
@@ -157,7 +166,7 @@ def time_cpu(wl, masks, budget_s, max_reps, threads=None):
     import torch
     from hd_yolo_b200 import synth
     torch.set_num_threads(threads or os.cpu_count() or 1)
-    sample = 2 if masks == "proto" else 8
+    sample = 8 if masks == "none" else 2
     dets, protos = cpu_sample_inputs(wl, masks, sample)
     spec_args = (synth.ANCHORS_3, synth.STRIDES_3)
     cpu_reference_pass(dets, protos, wl, spec_args, masks)          # warm-up
@@ -166,7 +175,8 @@ def time_cpu(wl, masks, budget_s, max_reps, threads=None):
         cpu_reference_pass(dets, protos, wl, spec_args, masks)
         reps += 1
     dt = time.perf_counter() - t0
-    what = "compute_proposals + nms_per_image + score select" + (" + process_mask(upsample)" if masks == "proto" else "")
+    what = "compute_proposals + nms_per_image + score select" + \
+        {"proto": " + process_mask(upsample)", "paste": " + mask_select + paste_masks_in_image", "none": ""}[masks]
     return sample * reps / dt, torch.get_num_threads(), (
         f"{sample} tiles x {reps} passes of oracle/port.py ({what}; torch {torch.__version__} CPU + torchvision nms)")
 
@@ -265,7 +275,8 @@ def run_tiles(args, wl, c):
     shapes = synth.level_shapes(tile, synth.STRIDES_3)
     N = spec.rows_per_tile(shapes)
     mh = mw = tile // 4
-    in_bytes = bs * N * spec.no * 4 + (bs * NM * mh * mw * 4 if masks == "proto" else 0)
+    in_bytes = bs * N * spec.no * 4 + (bs * NM * mh * mw * 4 if masks == "proto" else 0) + \
+        (bs * min(wl["max_det"], wl["cap"]) * 2 * 28 * 28 * 4 if masks == "paste" else 0)
     R = max(2, args.inflight, int(2.5 * L2_BYTES / in_bytes) + 1)   # rotate input batches so that reads miss L2
     batches = [synth.nuclei_logits(bs, tile, nc, wl["n_cand"], seed=1000 * c.rank + r, conf=wl["conf"], extra=extra,
                                    generator_device="cuda") for r in range(R)]
@@ -273,6 +284,15 @@ def run_tiles(args, wl, c):
     if masks == "proto":
         g = torch.Generator(device="cuda").manual_seed(77 + c.rank)
         protos = [torch.randn((bs, NM, mh, mw), generator=g, device=c.dev) for _ in range(R)]
+    md_slots = min(wl["max_det"], wl["cap"])
+    mlogits = None
+    if masks == "paste":
+        # reference variant A (yolo_head.py:321-353 + torchvision paste_masks_in_image): one 2-channel 28x28 mask
+        # logit map per detection slot, as the RoI mask head would produce them
+        g = torch.Generator(device="cuda").manual_seed(78 + c.rank)
+        mlogits = [torch.randn((bs * md_slots, 2, 28, 28), generator=g, device=c.dev) for _ in range(R)]
+        mask_indices = torch.tensor([-1, 0, 0, 1, 1], dtype=torch.int32, device=c.dev)
+        slot_ids = torch.arange(md_slots, device=c.dev)[None, :]
     state = {"cap_words": None}
 
     def step(i, dets=None, pr=None):
@@ -282,6 +302,14 @@ def run_tiles(args, wl, c):
         if masks == "proto":
             pm = hmasks.process_mask_packed(pr if pr is not None else protos[i % R], out.extra, out.boxes, out.counts,
                                             (tile, tile), upsample=True, capacity_words=state["cap_words"])
+        elif masks == "paste":
+            # M1: channel = mask_indices[labels.clamp(min=0)], empty beyond counts; M2+M3 fused and bit-packed
+            live = slot_ids < out.counts[:, None]            # slots beyond counts hold uninitialised labels
+            ch = mask_indices[torch.where(live, out.labels, torch.zeros_like(out.labels)).clamp(min=0)]
+            ch = torch.where(live, ch, torch.full_like(ch, -1)).reshape(-1)
+            pm = hmasks.paste_masks_packed(pr if pr is not None else mlogits[i % R], out.boxes.reshape(-1, 4),
+                                           (tile, tile), padding=1, channel=ch, apply_sigmoid=True,
+                                           capacity_words=state["cap_words"])
         return out, pm
 
     # size the packed-mask buffer once (the only call that reads a size back), then never sync inside a step
@@ -348,6 +376,8 @@ def run_tiles(args, wl, c):
         "hdy_process_mask_geometry": bs * min(wl["max_det"], wl["cap"]) * (16 + 16 + 8),
         "hdy_process_mask_packed": bs * (4 * NM * mh * mw + kept * (4 * NM + 16 + 8)) + 4 * words,
         "hdy_zero_i32": 4 * (bs + 1),
+        "hdy_paste_geometry": bs * md_slots * (16 + 16 + 8 + 4),
+        "hdy_paste_masks_packed": bs * kept * (28 * 28 * 4 + 16 + 8) + 4 * words,
     }
     peak, peak_src = load_peak()
     stages = {}
@@ -355,7 +385,8 @@ def run_tiles(args, wl, c):
         t = tot / calls
         a = alg.get(name)
         stages[name] = {"ms": t, "alg_bytes": a, "gbs": (a / (t * 1e-3) / 1e9) if a else None}
-    hbm_bound = [k for k in stages if k in ("hdy_filter_compact_logits", "hdy_process_mask_packed")]
+    hbm_bound = [k for k in stages if k in ("hdy_filter_compact_logits", "hdy_process_mask_packed",
+                                            "hdy_paste_masks_packed")]
     dom = max(hbm_bound, key=lambda k: stages[k]["ms"])
     dom_ms, dom_bytes = stages[dom]["ms"], alg[dom]
     achieved = dom_bytes / (dom_ms * 1e-3) / 1e9
@@ -372,9 +403,10 @@ def run_tiles(args, wl, c):
     e2e = None
     if not args.no_e2e:
         host = [[d.cpu().pin_memory() for d in b] for b in batches[:2]]
-        host_p = [p.cpu().pin_memory() for p in protos[:2]] if protos is not None else None
+        second = protos if protos is not None else mlogits
+        host_p = [p.cpu().pin_memory() for p in second[:2]] if second is not None else None
         stage = [torch.empty_like(d) for d in batches[0]]
-        stage_p = torch.empty_like(protos[0]) if protos is not None else None
+        stage_p = torch.empty_like(second[0]) if second is not None else None
         md = out.max_det
         h = {"boxes": torch.empty((bs, md, 4), dtype=torch.float32).pin_memory(),
              "scores": torch.empty((bs, md), dtype=torch.float32).pin_memory(),
@@ -421,7 +453,8 @@ def run_tiles(args, wl, c):
                    "candidates_per_tile": round(cand, 1), "kept_per_tile": round(kept, 1), "conf": wl["conf"],
                    "iou": wl["iou"], "max_det": wl["max_det"], "cap": wl["cap"],
                    "stages": "decode+filter+compact, nms, score/label select" +
-                             (", process_mask (proto contraction, sigmoid, crop, upsample, >0.5, bit-packed)" if masks == "proto" else ""),
+                             (", process_mask (proto contraction, sigmoid, crop, upsample, >0.5, bit-packed)" if masks == "proto" else "") +
+                             (", mask select + paste_masks_in_image > 0.5 (28x28 mask logits, bit-packed)" if masks == "paste" else ""),
                    "l2": f"{R} rotating input batches ({R * in_bytes / 1e6:.0f} MB) > 126 MB L2",
                    "launch": f"one CUDA graph per input batch (hdy.CapturedStep), replayed; {len(side)} steps in "
                              "flight on as many streams (each graph has its own scratch slot)",
@@ -436,7 +469,7 @@ def run_tiles(args, wl, c):
                      "frac_of_peak": step_bytes / (ms / K * 1e-3) / 1e9 / peak},
         "e2e": e2e, "gpu_launches": launches, "clocks": clocks,
     }
-    del batches, protos, graphs
+    del batches, protos, mlogits, graphs
     torch.cuda.empty_cache()
     return line
 

@@ -18,6 +18,7 @@
 //
 // ATen's bilinear (align_corners=False): scale = in/out (fp32); src = scale*(dst+0.5)-0.5, clamped at 0;
 // i0 = (int)src; i1 = min(i0+1, in-1); l1 = src-i0; l0 = 1-l1; v = l0y*(l0x*v00 + l1x*v01) + l1y*(l0x*v10 + l1x*v11).
+#include <stdlib.h>
 #include "mask_common.cuh"
 
 namespace hdy {
@@ -157,12 +158,16 @@ static void launch_scan_words(const int32_t* geom, long long K, int64_t* offsets
   }
 }
 
-__global__ void paste_geometry_kernel(const float4* __restrict__ boxes, int K, float scale, int H, int W,
-                                      int32_t* __restrict__ geom4) {
+__global__ void paste_geometry_kernel(const float4* __restrict__ boxes, const int32_t* __restrict__ channel, int K,
+                                      float scale, int H, int W, int32_t* __restrict__ geom4) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= K) return;
-  const PasteGeom g = paste_geometry(boxes[i], scale, H, W);
-  reinterpret_cast<int4*>(geom4)[i] = make_int4(g.x0, g.y0, g.w, g.h);
+  int4 out = make_int4(0, 0, 0, 0);
+  if (!channel || channel[i] >= 0) {  // channel < 0: empty mask (no words)
+    const PasteGeom g = paste_geometry(boxes[i], scale, H, W);
+    out = make_int4(g.x0, g.y0, g.w, g.h);
+  }
+  reinterpret_cast<int4*>(geom4)[i] = out;
 }
 
 // One CTA per mask.  The (M+2p)^2 zero-padded mask is staged in shared memory (sigmoid applied on the way if
@@ -177,6 +182,7 @@ __global__ void __launch_bounds__(128) paste_masks_kernel(
   const int i = blockIdx.x;
   const int Mp = M + 2 * pad;
   const int ch = channel ? channel[i] : 0;
+  if (ch < 0) return;  // empty mask: no words in the packed layout, the dense canvas is already zero
   for (int e = threadIdx.x; e < Mp * Mp; e += blockDim.x) {
     const int y = e / Mp - pad, x = e % Mp - pad;
     float v = 0.f;
@@ -457,8 +463,8 @@ int hdy_paste_masks(const float* src, const int32_t* channel, const float* boxes
                              nullptr, st);
 }
 
-int hdy_paste_geometry(const float* boxes, int K, int M, int padding, int H, int W, int32_t* geom,
-                       int64_t* offsets, hdy_stream_t stream) {
+int hdy_paste_geometry(const float* boxes, const int32_t* channel, int K, int M, int padding, int H, int W,
+                       int32_t* geom, int64_t* offsets, hdy_stream_t stream) {
   HDY_REQUIRE(K >= 0 && M >= 1 && padding >= 0 && H >= 1 && W >= 1, "hdy_paste_geometry: bad sizes");
   HDY_REQUIRE(offsets != nullptr, "hdy_paste_geometry: offsets is NULL");
   cudaStream_t st = (cudaStream_t)stream;
@@ -466,8 +472,8 @@ int hdy_paste_geometry(const float* boxes, int K, int M, int padding, int H, int
     HDY_REQUIRE(boxes && geom && ((uintptr_t)boxes & 15) == 0 && ((uintptr_t)geom & 15) == 0,
                 "hdy_paste_geometry: NULL or misaligned pointer");
     const float scale = (float)((double)(M + 2 * padding) / (double)M);
-    paste_geometry_kernel<<<(unsigned)((K + 127) / 128), 128, 0, st>>>(reinterpret_cast<const float4*>(boxes), K,
-                                                                       scale, H, W, geom);
+    paste_geometry_kernel<<<(unsigned)((K + 127) / 128), 128, 0, st>>>(reinterpret_cast<const float4*>(boxes), channel,
+                                                                       K, scale, H, W, geom);
   }
   launch_scan_words(geom, K, offsets, st);
   return check_launch("hdy_paste_geometry");

@@ -145,7 +145,8 @@ def paste_masks_packed(masks: torch.Tensor, boxes: torch.Tensor, img_shape, padd
     b = _boxes4(boxes, k) if k else None
     if channel is not None:
         channel = channel.to(dev, torch.int32).contiguous()
-    _call("hdy_paste_geometry", ptr(b), k, M, int(padding), H, W, ptr(geom), ptr(offsets), _stream(), launches=2)
+    _call("hdy_paste_geometry", ptr(b), ptr(channel), k, M, int(padding), H, W, ptr(geom), ptr(offsets), _stream(),
+          launches=4)
     words = int(offsets[k].item()) if capacity_words is None else int(capacity_words)
     bits = torch.empty((max(words, 1),), dtype=torch.int32, device=dev)
     if k:

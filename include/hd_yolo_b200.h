@@ -196,8 +196,8 @@ HDY_API int hdy_paste_masks(const float* src, const int32_t* channel, const floa
  * offsets [K+1] i64 = first 32-bit word of each mask (row r of mask i = ceil(w/32) words; bit (x-x0)&31 of
  * word (x-x0)>>5).  hdy_paste_geometry fills geom/offsets (offsets[K] = total words); the caller sizes `bits`
  * from it (or passes an upper bound: masks that do not fit set HDY_STATUS_OVERFLOW in *status). */
-HDY_API int hdy_paste_geometry(const float* boxes, int K, int M, int padding, int H, int W, int32_t* geom,
-                               int64_t* offsets, hdy_stream_t stream);
+HDY_API int hdy_paste_geometry(const float* boxes, const int32_t* channel, int K, int M, int padding, int H, int W,
+                               int32_t* geom, int64_t* offsets, hdy_stream_t stream);
 HDY_API int hdy_paste_masks_packed(const float* src, const int32_t* channel, const float* boxes,
                                    const int64_t* offsets, int K, int C, int M, int padding, int apply_sigmoid,
                                    int H, int W, uint32_t* bits, int64_t capacity_words, int32_t* status,

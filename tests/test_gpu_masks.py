@@ -216,3 +216,17 @@ def test_process_mask_crowded_region_and_empty_regions(cuda_device):
                                         (ih, iw), upsample=upsample)
         packed.check()
         assert torch.equal(packed.to_dense(), out.to(torch.uint8))
+
+
+@pytest.mark.parametrize("M", [14, 56])
+def test_paste_other_mask_sizes(cuda_device, M):
+    """Mask sides other than the reference's 28 (the padded mask is staged in dynamic shared memory)."""
+    g = torch.Generator().manual_seed(M)
+    k, H, W = 40, 300, 260
+    masks = torch.rand((k, 1, M, M), generator=g)
+    boxes = _rand_boxes(g, k, H, W, 5, 120)
+    ref = port.paste_masks_in_image(masks, boxes, (H, W), padding=1)
+    out = hm.paste_masks_in_image(masks.to(cuda_device), boxes.to(cuda_device), (H, W), padding=1).cpu()
+    assert float((out - ref).abs().max()) < ATOL
+    packed = hm.paste_masks_packed(masks.to(cuda_device), boxes.to(cuda_device), (H, W), padding=1)
+    assert _agreement(packed.to_dense().cpu(), (ref[:, 0] > 0.5).to(torch.uint8)) >= AGREE
