@@ -27,7 +27,9 @@ int check_launch(const char* what);
 // ---- exact fp32 arithmetic (the file is also built with -fmad=false) ---------
 // torch's CUDA sigmoid is 1/(1+exp(-x)) in fp32 with the full-precision expf and an
 // IEEE division; keep the same expression so device results track ATen's.
-__device__ __forceinline__ float sigmoidf_ref(float x) { return __fdiv_rn(1.0f, __fadd_rn(1.0f, expf(-x))); }
+// 1/y rounded to nearest is one value whether it is produced by a division or by the correctly rounded reciprocal;
+// __frcp_rn is the cheaper instruction sequence.
+__device__ __forceinline__ float sigmoidf_ref(float x) { return __frcp_rn(__fadd_rn(1.0f, expf(-x))); }
 
 // Order-preserving map float -> uint32 (ascending).  -0.0 is canonicalised to +0.0 so that
 // ties compare equal exactly as torch's sort does.

@@ -170,59 +170,131 @@ __global__ void paste_geometry_kernel(const float4* __restrict__ boxes, const in
   reinterpret_cast<int4*>(geom4)[i] = out;
 }
 
-// One CTA per mask.  The (M+2p)^2 zero-padded mask is staged in shared memory (sigmoid applied on the way if
-// the source holds logits), then the paste window is produced row by row.
+// One CTA (4 warps) per mask.  The (M+2p)^2 zero-padded mask is staged in shared memory (sigmoid applied on the way
+// if the source holds logits).  The paste window is cut into items of (32-pixel word, quarter of the rows); a warp
+// takes an item, interpolates its lanes' columns along x for the source rows the item touches (ATen's `top`/`bot`
+// terms, once per source row instead of once per pixel), then every output row is one 2-tap blend from that column
+// buffer, a compare and a ballot.  Narrow tail words (4 columns of a 36-px window) are processed several rows at a
+// time.  Every word of the mask is stored exactly once.
+constexpr int kPasteThreads = 128;
+constexpr int kPasteWarps = kPasteThreads / 32;
+constexpr int kPasteRows = 64;  // output rows per pass
+struct PasteRow {
+  int i0, i1;
+  float l0, l1;
+};
+static inline size_t paste_smem_bytes(int Mp) {
+  return (size_t)Mp * Mp * 4 + kPasteRows * sizeof(PasteRow) + (size_t)kPasteWarps * Mp * 32 * 4;
+}
+
 template <bool PACKED>
-__global__ void __launch_bounds__(128) paste_masks_kernel(
+__global__ void __launch_bounds__(kPasteThreads) paste_masks_kernel(
     const float* __restrict__ src, const int32_t* __restrict__ channel, const float4* __restrict__ boxes, int K,
     int C, int M, int pad, int apply_sigmoid, int H, int W, float scale, float* __restrict__ out_dense,
     const int64_t* __restrict__ offsets, uint32_t* __restrict__ bits, long long capacity_words,
     int32_t* __restrict__ status) {
-  extern __shared__ float sm[];
+  extern __shared__ __align__(16) float sm[];
   const int i = blockIdx.x;
   const int Mp = M + 2 * pad;
   const int ch = channel ? channel[i] : 0;
   if (ch < 0) return;  // empty mask: no words in the packed layout, the dense canvas is already zero
-  for (int e = threadIdx.x; e < Mp * Mp; e += blockDim.x) {
-    const int y = e / Mp - pad, x = e % Mp - pad;
-    float v = 0.f;
-    if (ch >= 0 && x >= 0 && x < M && y >= 0 && y < M) {
-      v = src[((size_t)i * C + ch) * M * M + y * M + x];
-      if (apply_sigmoid) v = sigmoidf_ref(v);
-    }
-    sm[e] = v;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  float* P = sm;                                                   // [Mp][Mp]
+  PasteRow* rowtab = reinterpret_cast<PasteRow*>(sm + Mp * Mp);    // [kPasteRows]  (Mp*Mp*4 is a multiple of 16)
+  float* col = reinterpret_cast<float*>(rowtab + kPasteRows) + (size_t)warp * Mp * 32;  // [Mp][32] per warp
+  {
+    const float* m = src + ((size_t)i * C + ch) * M * M;
+    for (int y = warp; y < Mp; y += kPasteWarps)
+      for (int x = lane; x < Mp; x += 32) {
+        float v = 0.f;
+        const int yy = y - pad, xx = x - pad;
+        if (xx >= 0 && xx < M && yy >= 0 && yy < M) {
+          v = m[yy * M + xx];
+          if (apply_sigmoid) v = sigmoidf_ref(v);
+        }
+        P[y * Mp + x] = v;
+      }
   }
-  __syncthreads();
   const PasteGeom g = paste_geometry(boxes[i], scale, H, W);
-  if (g.w <= 0 || g.h <= 0) return;
-  const float sx = __fdiv_rn((float)Mp, (float)g.rw), sy = __fdiv_rn((float)Mp, (float)g.rh);
-  if (!PACKED) {
-    float* o = out_dense + (size_t)i * H * W;
-    for (int e = threadIdx.x; e < g.w * g.h; e += blockDim.x) {
-      const int yy = e / g.w, xx = e - yy * g.w;
-      const Lerp Y = lerp_coord(g.y0 + yy - g.by0, sy, Mp), X = lerp_coord(g.x0 + xx - g.bx0, sx, Mp);
-      o[(size_t)(g.y0 + yy) * W + g.x0 + xx] =
-          bilerp(sm[Y.i0 * Mp + X.i0], sm[Y.i0 * Mp + X.i1], sm[Y.i1 * Mp + X.i0], sm[Y.i1 * Mp + X.i1], X, Y);
-    }
-  } else {
-    const int wpr = (g.w + 31) >> 5;
-    const long long off = offsets[i];
+  if (g.w <= 0 || g.h <= 0) return;  // uniform
+  const int wpr = (g.w + 31) >> 5;
+  long long off = 0;
+  if (PACKED) {
+    off = offsets[i];
     if (off + (long long)wpr * g.h > capacity_words) {
       if (threadIdx.x == 0) atomicOr(status, HDY_STATUS_OVERFLOW);
       return;
     }
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = blockDim.x >> 5;
-    for (int wi = warp; wi < wpr * g.h; wi += nw) {
-      const int yy = wi / wpr, xw = wi - yy * wpr;
-      const int xx = (xw << 5) + lane;
-      bool bit = false;
-      if (xx < g.w) {
-        const Lerp Y = lerp_coord(g.y0 + yy - g.by0, sy, Mp), X = lerp_coord(g.x0 + xx - g.bx0, sx, Mp);
-        bit = bilerp(sm[Y.i0 * Mp + X.i0], sm[Y.i0 * Mp + X.i1], sm[Y.i1 * Mp + X.i0], sm[Y.i1 * Mp + X.i1], X, Y) >
-              0.5f;
+  }
+  const float sx = __fdiv_rn((float)Mp, (float)g.rw), sy = __fdiv_rn((float)Mp, (float)g.rh);
+  for (int r0 = 0; r0 < g.h; r0 += kPasteRows) {
+    const int nr = min(kPasteRows, g.h - r0);
+    __syncthreads();  // P is complete / the previous pass is done with rowtab
+    if ((int)threadIdx.x < nr) {
+      const Lerp Y = lerp_coord(g.y0 + r0 + (int)threadIdx.x - g.by0, sy, Mp);
+      PasteRow T;
+      T.i0 = Y.i0;
+      T.i1 = Y.i1;
+      T.l0 = Y.l0;
+      T.l1 = Y.l1;
+      rowtab[threadIdx.x] = T;
+    }
+    __syncthreads();
+    const int quarter = (nr + kPasteWarps - 1) / kPasteWarps;
+    for (int item = warp; item < wpr * kPasteWarps; item += kPasteWarps) {
+      // items of one word go to the four warps: (word, q) -> warp q handles rows [q*quarter, (q+1)*quarter)
+      const int w = item / kPasteWarps;
+      const int ra = min(warp * quarter, nr), rb = min(ra + quarter, nr);
+      if (rb <= ra) continue;
+      const int s_lo = rowtab[ra].i0, s_hi = rowtab[rb - 1].i1;  // source rows touched (lerp is monotone)
+      const int vw = min(32, g.w - (w << 5));
+      __syncwarp();
+      if (vw <= 16) {
+        const int rows_per = 32 / vw;
+        const int lr = lane / vw, lc = lane - lr * vw;
+        const bool active = lr < rows_per;
+        const Lerp X = lerp_coord(g.x0 + (w << 5) + lc - g.bx0, sx, Mp);
+        if (active)
+          for (int s_ = s_lo + lr; s_ <= s_hi; s_ += rows_per)
+            col[s_ * 32 + lc] = __fadd_rn(__fmul_rn(X.l0, P[s_ * Mp + X.i0]), __fmul_rn(X.l1, P[s_ * Mp + X.i1]));
+        __syncwarp();
+        const unsigned row_mask = (1u << vw) - 1u;
+        for (int rbase = ra; rbase < rb; rbase += rows_per) {
+          const int r = rbase + lr;
+          bool bit = false;
+          if (active && r < rb) {
+            const float4 rt = *reinterpret_cast<const float4*>(&rowtab[r]);
+            const float v = __fadd_rn(__fmul_rn(rt.z, col[__float_as_int(rt.x) * 32 + lc]),
+                                      __fmul_rn(rt.w, col[__float_as_int(rt.y) * 32 + lc]));
+            bit = v > 0.5f;
+            if (!PACKED) out_dense[(size_t)i * H * W + (size_t)(g.y0 + r0 + r) * W + g.x0 + (w << 5) + lc] = v;
+          }
+          if (PACKED) {
+            const unsigned mm = __ballot_sync(0xffffffffu, bit);
+            if (active && lc == 0 && r < rb) bits[off + (long long)(r0 + r) * wpr + w] = (mm >> (lr * vw)) & row_mask;
+          }
+        }
+        continue;
       }
-      const unsigned word = __ballot_sync(0xffffffffu, bit);
-      if (lane == 0) bits[off + wi] = word;
+      const int c = (w << 5) + lane;
+      const bool valid = c < g.w;
+      const Lerp X = lerp_coord(g.x0 + (valid ? c : 0) - g.bx0, sx, Mp);
+      for (int s_ = s_lo; s_ <= s_hi; ++s_)
+        col[s_ * 32 + lane] = __fadd_rn(__fmul_rn(X.l0, P[s_ * Mp + X.i0]), __fmul_rn(X.l1, P[s_ * Mp + X.i1]));
+      __syncwarp();
+      unsigned myword = 0;
+      for (int r = ra; r < rb; ++r) {  // rb - ra <= 16
+        const float4 rt = *reinterpret_cast<const float4*>(&rowtab[r]);
+        const float v = __fadd_rn(__fmul_rn(rt.z, col[__float_as_int(rt.x) * 32 + lane]),
+                                  __fmul_rn(rt.w, col[__float_as_int(rt.y) * 32 + lane]));
+        if (PACKED) {
+          const unsigned word = __ballot_sync(0xffffffffu, valid && v > 0.5f);
+          if (r - ra == lane) myword = word;
+        } else if (valid) {
+          out_dense[(size_t)i * H * W + (size_t)(g.y0 + r0 + r) * W + g.x0 + c] = v;
+        }
+      }
+      if (PACKED && lane < rb - ra) bits[off + (long long)(r0 + ra + lane) * wpr + w] = myword;
     }
   }
 }
@@ -396,7 +468,7 @@ int launch_process_mask_listed(const float* protos, const float* coef, const flo
 
 static int paste_args_ok(const float* src, const float* boxes, int K, int C, int M, int pad, int H, int W) {
   HDY_REQUIRE(K >= 0 && C >= 1 && M >= 1 && pad >= 0 && H >= 1 && W >= 1, "paste: bad sizes");
-  HDY_REQUIRE((M + 2 * pad) * (M + 2 * pad) * 4 <= 200 * 1024, "paste: mask too large for shared memory");
+  HDY_REQUIRE(paste_smem_bytes(M + 2 * pad) <= 200 * 1024, "paste: mask too large for shared memory");
   if (K > 0) HDY_REQUIRE(src && boxes && ((uintptr_t)boxes & 15) == 0, "paste: NULL or misaligned pointer");
   return HDY_OK;
 }
@@ -406,7 +478,7 @@ static int launch_paste(const float* src, const int32_t* channel, const float* b
                         int apply_sigmoid, int H, int W, float* out, const int64_t* offsets, uint32_t* bits,
                         long long cap, int32_t* status, cudaStream_t st) {
   const int Mp = M + 2 * pad;
-  const size_t smem = (size_t)Mp * Mp * 4;
+  const size_t smem = paste_smem_bytes(Mp);
   if (smem > 48 * 1024) {
     cudaError_t e = cudaFuncSetAttribute(paste_masks_kernel<PACKED>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                          (int)smem);
@@ -416,9 +488,10 @@ static int launch_paste(const float* src, const int32_t* channel, const float* b
     }
   }
   const float scale = (float)((double)(M + 2 * pad) / (double)M);  // expand_masks: float(M + 2p) / M
-  paste_masks_kernel<PACKED><<<(unsigned)K, 128, smem, st>>>(src, channel, reinterpret_cast<const float4*>(boxes), K,
-                                                             C, M, pad, apply_sigmoid, H, W, scale, out, offsets,
-                                                             bits, cap, status);
+  paste_masks_kernel<PACKED><<<(unsigned)K, kPasteThreads, smem, st>>>(src, channel,
+                                                                       reinterpret_cast<const float4*>(boxes), K, C, M,
+                                                                       pad, apply_sigmoid, H, W, scale, out, offsets,
+                                                                       bits, cap, status);
   return check_launch("hdy_paste_masks");
 }
 
