@@ -203,17 +203,28 @@ __global__ void __launch_bounds__(kPasteThreads) paste_masks_kernel(
   PasteRow* rowtab = reinterpret_cast<PasteRow*>(sm + Mp * Mp);    // [kPasteRows]  (Mp*Mp*4 is a multiple of 16)
   float* col = reinterpret_cast<float*>(rowtab + kPasteRows) + (size_t)warp * Mp * 32;  // [Mp][32] per warp
   {
+    // stage the padded mask: zero everything, then the M x M interior with 8 independent (coalesced) loads in flight
+    // per thread before the first sigmoid needs its operand
+    for (int e = threadIdx.x; e < Mp * Mp; e += kPasteThreads) P[e] = 0.f;
+    __syncthreads();
     const float* m = src + ((size_t)i * C + ch) * M * M;
-    for (int y = warp; y < Mp; y += kPasteWarps)
-      for (int x = lane; x < Mp; x += 32) {
-        float v = 0.f;
-        const int yy = y - pad, xx = x - pad;
-        if (xx >= 0 && xx < M && yy >= 0 && yy < M) {
-          v = m[yy * M + xx];
-          if (apply_sigmoid) v = sigmoidf_ref(v);
-        }
-        P[y * Mp + x] = v;
+    const int MM = M * M;
+    for (int e0 = 0; e0 < MM; e0 += kPasteThreads * 8) {
+      float v[8];
+#pragma unroll
+      for (int k = 0; k < 8; ++k) {
+        const int e = e0 + k * kPasteThreads + (int)threadIdx.x;
+        v[k] = e < MM ? m[e] : 0.f;
       }
+#pragma unroll
+      for (int k = 0; k < 8; ++k) {
+        const int e = e0 + k * kPasteThreads + (int)threadIdx.x;
+        if (e < MM) {
+          const int y = e / M, x = e - y * M;
+          P[(y + pad) * Mp + x + pad] = apply_sigmoid ? sigmoidf_ref(v[k]) : v[k];
+        }
+      }
+    }
   }
   const PasteGeom g = paste_geometry(boxes[i], scale, H, W);
   if (g.w <= 0 || g.h <= 0) return;  // uniform
