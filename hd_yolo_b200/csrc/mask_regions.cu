@@ -176,17 +176,30 @@ __global__ void __launch_bounds__(kRegThreads, 3) proto_patch_kernel(
     }
     __syncthreads();
     const int nl = S.nlist;
+    // software pipeline over this warp's pieces: the box and the coefficients of the NEXT piece are requested before
+    // the current one is computed (and those of the first piece before waiting for the TMA load)
+    int e = warp;
+    size_t nslot = 0;
+    float4 nbox = make_float4(0.f, 0.f, 0.f, 0.f);
+    float ncoef = 0.f;
+    auto fetch = [&](int ee) {
+      nslot = (size_t)tile * max_det + (use_list ? 0 : base) + S.list[ee];
+      nbox = boxes[nslot];
+      ncoef = coef[nslot * kRegNm + lane];
+    };
+    if (e < nl) fetch(e);
     if (!loaded) {
       while (!mbar_try_wait(&S.bar, 0)) {
       }
       loaded = true;
     }
-    for (int e = warp; e < nl; e += kRegWarps) {
-      const size_t slot = (size_t)tile * max_det + (use_list ? 0 : base) + S.list[e];
-      const KeptRange k = kept_range(boxes[slot], rx, ry, mw, mh);
+    for (; e < nl; e += kRegWarps) {
+      const size_t slot = nslot;
+      const KeptRange k = kept_range(nbox, rx, ry, mw, mh);
       __syncwarp();
-      S.coef[warp][lane] = coef[slot * kRegNm + lane];
+      S.coef[warp][lane] = ncoef;
       __syncwarp();
+      if (e + kRegWarps < nl) fetch(e + kRegWarps);
       float cf[kRegNm];
 #pragma unroll
       for (int c = 0; c < kRegNm; c += 4) {
