@@ -54,7 +54,7 @@ SIGNATURES = {
     "hdy_nms_workspace_bytes": (_sz, [_i, _i]),
     "hdy_nms_tiles": (
         _i,
-        [_vp, _vp, _vp, _vp, _i, _i, _f, _f, _i, _i, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _sz, _vp],
+        [_vp, _vp, _vp, _vp, _i, _i, _f, _f, _i, _i, _vp, _vp, _vp, _vp, _vp, _vp, _f, _vp, _vp, _sz, _vp],
     ),
     "hdy_make_keys": (_i, [_vp, _i, _i, _vp, _vp]),
     "hdy_debug_nms_phases": (_i, [_vp]),
@@ -76,11 +76,14 @@ SIGNATURES = {
         [_vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _i, _i, _vp, C.c_int64, _vp, _vp, _sz, _vp],
     ),
     "hdy_affine_boxes": (_i, [_vp, _i64, _i, _f, _f, _f, _f, _f, _f, _i, _vp]),
-    "hdy_merge_append": (_i, [_vp, _vp, _vp, _vp, _vp, _i, _i, _i, _f, _i64, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
-    "hdy_merge_overhang": (_i, [_vp, _vp, _vp, _vp, _i64, _vp, _vp]),
+    "hdy_merge_append": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _f, _i64, _vp, _vp, _vp, _vp, _vp, _vp, _vp,
+                              _vp]),
+    "hdy_merge_overhang": (_i, [_vp, _vp, _vp, _vp, _i64, _f, _vp, _vp, _vp, _vp, _i, _vp]),
+    "hdy_merge_dirty_tiles": (_i, [_vp, _vp, _vp, _i, _vp, _i, _vp, _vp]),
     "hdy_merge_workspace_bytes": (_sz, [_i64]),
-    "hdy_merge_nms": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _i64, _f, _f, _i, _vp, _vp, _vp, _sz, _vp]),
-    "hdy_merge_build": (_i, [_vp, _vp, _vp, C.c_uint32, _vp, _vp, _vp, _vp, _i64, _i64, _f, _f, _vp, _vp, _sz, _vp]),
+    "hdy_merge_nms": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _i64, _f, _f, _i, _vp, _vp, _vp, _sz, _vp]),
+    "hdy_merge_build": (_i, [_vp, _vp, _vp, C.c_uint32, _vp, _vp, _vp, _vp, _vp, _i64, _i64, _f, _f, _vp, _vp, _sz,
+                             _vp]),
     "hdy_merge_rounds": (_i, [_vp, _i64, _f, _i, _i, _vp]),
     "hdy_merge_export_states": (_i, [_vp, _i64, _vp, _vp, _i64, _vp, _vp]),
     "hdy_merge_import_states": (_i, [_vp, _i64, _i64, _vp, _i64, _vp]),

@@ -65,6 +65,22 @@ __device__ __forceinline__ bool iou_gt(const float4& a, const float4& b, float t
   return __fdiv_rn(inter, uni) > thr;
 }
 
+// Can IoU(a', b') exceed thr when every coordinate of a and b moves by at most e (the rounding of `box + tile
+// origin` in slide coordinates, Detect.merge_outputs yolo_head.py:455) and the result is evaluated in fp32?
+// Upper bound: the largest possible intersection over the smallest possible union.  Conservative by construction
+// (false positives only cost work), never optimistic.
+__device__ __forceinline__ bool iou_may_exceed(const float4& a, const float4& b, float thr, float e) {
+  const float e2 = 2.0f * e;
+  const float w = fminf(a.z, b.z) - fmaxf(a.x, b.x) + e2, h = fminf(a.w, b.w) - fmaxf(a.y, b.y) + e2;
+  if (!(w > 0.0f) || !(h > 0.0f)) return false;
+  const float imax = w * h;
+  const float wa = fmaxf(a.z - a.x - e2, 0.0f), ha = fmaxf(a.w - a.y - e2, 0.0f);
+  const float wb = fmaxf(b.z - b.x - e2, 0.0f), hb = fmaxf(b.w - b.y - e2, 0.0f);
+  const float umin = wa * ha + wb * hb - imax;
+  if (!(umin > 0.0f)) return true;
+  return imax * 1.0001f > thr * umin;  // 1e-4: fp32 rounding of this bound and of the IoU it bounds
+}
+
 // streaming 128-bit load that does not pollute L1
 __device__ __forceinline__ float4 ldg_stream_f4(const float4* p) {
   float4 v;
@@ -130,8 +146,8 @@ constexpr int kNmsSmemCap = 4096;
 int launch_nms_tiles_smem(const uint64_t* cand_keys, const float4* cand_boxes, const float* cand_cls,
                           const int32_t* counts, int bs, int cap, float thr, float class_offset, int max_nms,
                           int max_det, int32_t* keep_idx, int32_t* keep_slot, float4* keep_box, float* keep_score,
-                          float* keep_cls, int32_t* keep_counts, unsigned long long* phase_cycles,
-                          cudaStream_t stream);
+                          float* keep_cls, int32_t* keep_counts, float gray_eps, uint8_t* keep_fragile,
+                          unsigned long long* phase_cycles, cudaStream_t stream);
 
 // filter_tma.cu: returns 1 when the layout does not meet the bulk-copy alignment rules (use the generic kernel)
 int launch_filter_compact_tma(const hdy_level_t* levels_host, int nl, int bs, int na, int nc, int no, float conf_thres,

@@ -166,7 +166,8 @@ __global__ void __launch_bounds__(1024) append_offsets_kernel(const int32_t* __r
 }
 
 __global__ void append_tiles_kernel(const float4* __restrict__ boxes, const float* __restrict__ scores,
-                                    const int64_t* __restrict__ labels, const int32_t* __restrict__ counts,
+                                    const int64_t* __restrict__ labels, const uint8_t* __restrict__ fragile,
+                                    const int32_t* __restrict__ counts,
                                     const float4* __restrict__ rois, int max_det, int tile_base, float scale,
                                     const long long* __restrict__ tile_offsets, long long capacity,
                                     float4* __restrict__ out_boxes, float* __restrict__ out_scores,
@@ -198,7 +199,8 @@ __global__ void append_tiles_kernel(const float4* __restrict__ boxes, const floa
     out_boxes[o] = b;
     if (out_scores) out_scores[o] = scores[s];
     if (out_labels) out_labels[o] = labels[s];
-    if (out_tile) out_tile[o] = tile_base + tile;
+    // fragile rows carry ~tile (negative): they still know their tile (overhang), but never take the shortcut
+    if (out_tile) out_tile[o] = (fragile && fragile[s]) ? ~(tile_base + tile) : tile_base + tile;
   }
 }
 
@@ -207,20 +209,51 @@ __global__ void append_tiles_kernel(const float4* __restrict__ boxes, const floa
 // ------------------------------------------------------------------------------------------------
 __global__ void overhang_kernel(const float4* __restrict__ boxes, const int32_t* __restrict__ tile_id,
                                 const float4* __restrict__ tile_rois, const long long* __restrict__ n_dev,
-                                long long n_max, float* __restrict__ margin) {
+                                long long n_max, float far_cap, float* __restrict__ margin,
+                                float4* __restrict__ far_boxes, int32_t* __restrict__ far_tile,
+                                int32_t* __restrict__ far_count, int far_capacity) {
   const long long n = n_dev ? min(*n_dev, n_max) : n_max;
   float m = 0.f;
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
-    const int t = tile_id[i];
-    if (t < 0) continue;
+    int t = tile_id[i];
+    if (t < 0) t = ~t;  // fragile row: ~tile
     const float4 b = boxes[i], r = tile_rois[t];
     float o = fmaxf(fmaxf(r.x - b.x, r.y - b.y), fmaxf(b.z - r.z, b.w - r.w));
     if (!(o <= 3.0e38f)) o = 3.0e38f;  // NaN / inf coordinates: nothing is interior
-    m = fmaxf(m, o);
+    if (far_count && o > far_cap) {
+      // a box that reaches far beyond its tile (a rare, huge false positive) would shrink EVERY core through the
+      // margin: list it instead, the tiles it touches lose the shortcut (dirty_tiles_kernel)
+      const int k = atomicAdd(far_count, 1);
+      if (k < far_capacity) {
+        far_boxes[k] = b;
+        far_tile[k] = t;
+      }
+    } else {
+      m = fmaxf(m, o);
+    }
   }
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
   if ((threadIdx.x & 31) == 0 && m > 0.f) atomicMax(reinterpret_cast<int*>(margin), __float_as_int(m));
+}
+
+// dirty[t] = 1 if a far-reaching box of ANOTHER tile intersects tile t's window (or the far list overflowed, or a far
+// box is not finite): rows of dirty tiles never take the interior shortcut
+__global__ void dirty_tiles_kernel(const float4* __restrict__ far_boxes, const int32_t* __restrict__ far_tile,
+                                   const int32_t* __restrict__ far_count, int far_capacity,
+                                   const float4* __restrict__ tile_rois, int n_tiles, uint8_t* __restrict__ dirty) {
+  const int t = blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= n_tiles) return;
+  const int nf = *far_count;
+  uint8_t d = nf > far_capacity ? 1 : 0;
+  const float4 r = tile_rois[t];
+  for (int k = 0; k < min(nf, far_capacity) && !d; ++k) {
+    if (far_tile[k] == t) continue;
+    const float4 b = far_boxes[k];
+    const bool apart = (b.z < r.x) || (b.x > r.z) || (b.w < r.y) || (b.y > r.w);  // false for NaN: dirty
+    if (!apart) d = 1;
+  }
+  dirty[t] = d;
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -333,7 +366,8 @@ struct MergeIn {
   const uint32_t* gidx;       // optional global index per entry (tie order); NULL: gidx_base + i
   const int32_t* tile_id;     // optional
   const float4* tile_cores;   // optional [n_tiles] core rectangles (slide coordinates)
-  const float* margin;        // device float: largest overhang of any box over its tile
+  const uint8_t* tile_dirty;  // optional [n_tiles]: tiles reached by another tile's far-reaching box (no shortcut)
+  const float* margin;        // device float: largest overhang of any (not far-reaching) box over its tile
   const long long* n_dev;     // optional device count
   long long n_max, n_local;   // entries >= n_local are remote replicas
   uint32_t gidx_base;
@@ -361,7 +395,8 @@ __global__ void merge_classify_kernel(const MergeIn in, const MergeStats* __rest
         bool interior = false;
         if (!remote && in.tile_cores && in.tile_id && in.tile_id[i] >= 0) {
           const float4 c = in.tile_cores[in.tile_id[i]];
-          interior = (b.x > c.x + m) && (b.y > c.y + m) && (b.z < c.z - m) && (b.w < c.w - m);
+          interior = (b.x > c.x + m) && (b.y > c.y + m) && (b.z < c.z - m) && (b.w < c.w - m) &&
+                     !(in.tile_dirty && in.tile_dirty[in.tile_id[i]]);
         }
         if (interior)
           st = MS_KEPT;
@@ -655,8 +690,9 @@ using namespace hdy;
 
 extern "C" {
 
-int hdy_merge_append(const float* boxes, const float* scores, const int64_t* labels, const int32_t* counts,
-                     const float* rois, int bs, int max_det, int tile_base, float scale, int64_t capacity,
+int hdy_merge_append(const float* boxes, const float* scores, const int64_t* labels, const uint8_t* fragile,
+                     const int32_t* counts, const float* rois, int bs, int max_det, int tile_base, float scale,
+                     int64_t capacity,
                      float* out_boxes, float* out_scores, int64_t* out_labels, int32_t* out_tile, int64_t* cursor,
                      int64_t* tile_offsets, int32_t* status, hdy_stream_t stream) {
   HDY_REQUIRE(bs >= 0 && max_det > 0 && capacity >= 0, "hdy_merge_append: bad sizes");
@@ -671,7 +707,7 @@ int hdy_merge_append(const float* boxes, const float* scores, const int64_t* lab
   append_offsets_kernel<<<1, 1024, 0, st>>>(counts, bs, reinterpret_cast<long long*>(cursor),
                                             reinterpret_cast<long long*>(tile_offsets));
   dim3 grid((unsigned)((max_det + 127) / 128), (unsigned)bs);
-  append_tiles_kernel<<<grid, 128, 0, st>>>(reinterpret_cast<const float4*>(boxes), scores, labels, counts,
+  append_tiles_kernel<<<grid, 128, 0, st>>>(reinterpret_cast<const float4*>(boxes), scores, labels, fragile, counts,
                                             reinterpret_cast<const float4*>(rois), max_det, tile_base, scale,
                                             reinterpret_cast<const long long*>(tile_offsets), capacity,
                                             reinterpret_cast<float4*>(out_boxes), out_scores, out_labels, out_tile,
@@ -680,15 +716,32 @@ int hdy_merge_append(const float* boxes, const float* scores, const int64_t* lab
 }
 
 int hdy_merge_overhang(const float* boxes, const int32_t* tile_id, const float* tile_rois, const int64_t* n_dev,
-                       int64_t n_max, float* margin, hdy_stream_t stream) {
+                       int64_t n_max, float far_cap, float* margin, float* far_boxes, int32_t* far_tile,
+                       int32_t* far_count, int far_capacity, hdy_stream_t stream) {
   HDY_REQUIRE(n_max >= 0 && margin, "hdy_merge_overhang: bad arguments");
+  HDY_REQUIRE(!far_count || (far_boxes && far_tile && far_capacity >= 0 && ((uintptr_t)far_boxes & 15) == 0),
+              "hdy_merge_overhang: far_count needs far_boxes (16-byte aligned) and far_tile");
   if (n_max == 0) return HDY_OK;
   HDY_REQUIRE(boxes && tile_id && tile_rois && (((uintptr_t)boxes | (uintptr_t)tile_rois) & 15) == 0,
               "hdy_merge_overhang: NULL or misaligned pointer");
   overhang_kernel<<<blocks_for(n_max, 256), 256, 0, (cudaStream_t)stream>>>(
       reinterpret_cast<const float4*>(boxes), tile_id, reinterpret_cast<const float4*>(tile_rois),
-      reinterpret_cast<const long long*>(n_dev), n_max, margin);
+      reinterpret_cast<const long long*>(n_dev), n_max, far_cap, margin, reinterpret_cast<float4*>(far_boxes), far_tile,
+      far_count, far_capacity);
   return check_launch("hdy_merge_overhang");
+}
+
+int hdy_merge_dirty_tiles(const float* far_boxes, const int32_t* far_tile, const int32_t* far_count, int far_capacity,
+                          const float* tile_rois, int n_tiles, uint8_t* dirty, hdy_stream_t stream) {
+  HDY_REQUIRE(n_tiles >= 0 && far_capacity >= 0, "hdy_merge_dirty_tiles: bad sizes");
+  if (n_tiles == 0) return HDY_OK;
+  HDY_REQUIRE(far_boxes && far_tile && far_count && tile_rois && dirty &&
+                  (((uintptr_t)far_boxes | (uintptr_t)tile_rois) & 15) == 0,
+              "hdy_merge_dirty_tiles: NULL or misaligned pointer");
+  dirty_tiles_kernel<<<(unsigned)((n_tiles + 127) / 128), 128, 0, (cudaStream_t)stream>>>(
+      reinterpret_cast<const float4*>(far_boxes), far_tile, far_count, far_capacity,
+      reinterpret_cast<const float4*>(tile_rois), n_tiles, dirty);
+  return check_launch("hdy_merge_dirty_tiles");
 }
 
 size_t hdy_merge_workspace_bytes(int64_t n_max) {
@@ -697,7 +750,8 @@ size_t hdy_merge_workspace_bytes(int64_t n_max) {
 }
 
 int hdy_merge_build(const float* boxes, const float* scores, const uint32_t* gidx, uint32_t gidx_base,
-                    const int32_t* tile_id, const float* tile_cores, const float* margin, const int64_t* n_dev,
+                    const int32_t* tile_id, const float* tile_cores, const uint8_t* tile_dirty, const float* margin,
+                    const int64_t* n_dev,
                     int64_t n_max, int64_t n_local, float conf_thres, float iou_thres, uint8_t* state,
                     void* workspace, size_t workspace_bytes, hdy_stream_t stream) {
   HDY_REQUIRE(n_max >= 0 && n_local >= 0 && n_local <= n_max, "hdy_merge_build: bad sizes");
@@ -723,6 +777,7 @@ int hdy_merge_build(const float* boxes, const float* scores, const uint32_t* gid
   in.gidx = gidx;
   in.tile_id = tile_id;
   in.tile_cores = reinterpret_cast<const float4*>(tile_cores);
+  in.tile_dirty = tile_dirty;
   in.margin = margin;
   in.n_dev = reinterpret_cast<const long long*>(n_dev);
   in.n_max = n_max;
@@ -790,12 +845,13 @@ int hdy_merge_import_states(void* workspace, int64_t n_max, int64_t first, const
 }
 
 int hdy_merge_nms(const float* boxes, const float* scores, const int32_t* tile_id, const float* tile_cores,
-                  const float* margin, const int64_t* n_dev, int64_t n_max, float conf_thres, float iou_thres,
+                  const uint8_t* tile_dirty, const float* margin, const int64_t* n_dev, int64_t n_max, float conf_thres,
+                  float iou_thres,
                   int max_rounds, uint8_t* state, int32_t* status, void* workspace, size_t workspace_bytes,
                   hdy_stream_t stream) {
   HDY_REQUIRE(max_rounds >= 1 && max_rounds <= kMaxRounds, "hdy_merge_nms: max_rounds out of range [1,%d]", kMaxRounds);
-  int rc = hdy_merge_build(boxes, scores, nullptr, 0, tile_id, tile_cores, margin, n_dev, n_max, n_max, conf_thres,
-                           iou_thres, state, workspace, workspace_bytes, stream);
+  int rc = hdy_merge_build(boxes, scores, nullptr, 0, tile_id, tile_cores, tile_dirty, margin, n_dev, n_max, n_max,
+                           conf_thres, iou_thres, state, workspace, workspace_bytes, stream);
   if (rc) return rc;
   rc = hdy_merge_rounds(workspace, n_max, iou_thres, 0, max_rounds, stream);
   if (rc) return rc;

@@ -103,6 +103,7 @@ struct TileOut {
   float* keep_score;
   float* keep_cls;
   int32_t* keep_count;
+  uint8_t* keep_frag;  // optional: 1 for every survivor (this path does not analyse the gray zone; conservative)
 };
 
 template <typename IdxT, int G>
@@ -310,6 +311,7 @@ __device__ void nms_tile_body(const int n_in, const int max_nms, uint64_t* keys,
         if (out.keep_box) out.keep_box[pos] = gboxes[s];
         if (out.keep_score) out.keep_score[pos] = key_score(k);
         if (out.keep_cls) out.keep_cls[pos] = gcls ? gcls[s] : 0.f;
+        if (out.keep_frag) out.keep_frag[pos] = 1;
         ++pos;
       }
     }
@@ -360,7 +362,7 @@ __global__ void __launch_bounds__(kNmsThreads, 2) nms_tiles_kernel(
     float class_offset, int max_nms, int max_det, int32_t* __restrict__ keep_idx,
     int32_t* __restrict__ keep_slot, float4* __restrict__ keep_box, float* __restrict__ keep_score,
     float* __restrict__ keep_cls, int32_t* __restrict__ keep_counts, unsigned char* __restrict__ workspace,
-    int min_n) {
+    int min_n, uint8_t* __restrict__ keep_fragile) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   __shared__ int warp_tmp[kNmsThreads / 32 + 1];
   __shared__ float red_tmp[kNmsThreads / 32];
@@ -374,6 +376,7 @@ __global__ void __launch_bounds__(kNmsThreads, 2) nms_tiles_kernel(
   out.keep_score = keep_score ? keep_score + (size_t)tile * max_det : nullptr;
   out.keep_cls = keep_cls ? keep_cls + (size_t)tile * max_det : nullptr;
   out.keep_count = keep_counts + tile;
+  out.keep_frag = keep_fragile ? keep_fragile + (size_t)tile * max_det : nullptr;
   if (n <= 0) {
     if (threadIdx.x == 0) *out.keep_count = 0;
     return;
@@ -593,8 +596,8 @@ size_t hdy_nms_workspace_bytes(int bs, int cap) {
 int hdy_nms_tiles(const uint64_t* cand_keys, const float* cand_boxes, const float* cand_cls,
                   const int32_t* counts, int bs, int cap, float iou_thres, float class_offset, int max_nms,
                   int max_det, int32_t* keep_idx, int32_t* keep_slot, float* keep_box, float* keep_score,
-                  float* keep_cls, int32_t* keep_counts, void* workspace, size_t workspace_bytes,
-                  hdy_stream_t stream) {
+                  float* keep_cls, int32_t* keep_counts, float gray_eps, uint8_t* keep_fragile, void* workspace,
+                  size_t workspace_bytes, hdy_stream_t stream) {
   HDY_REQUIRE(bs >= 0 && cap > 0 && max_det > 0, "hdy_nms_tiles: bs=%d cap=%d max_det=%d", bs, cap, max_det);
   HDY_REQUIRE(iou_thres >= 0.f, "hdy_nms_tiles: iou_thres must be >= 0");
   HDY_REQUIRE(cand_keys && cand_boxes && counts && keep_idx && keep_slot && keep_counts,
@@ -610,8 +613,8 @@ int hdy_nms_tiles(const uint64_t* cand_keys, const float* cand_boxes, const floa
   // tiles with at most 4096 candidates: shared-memory kernel (nms_smem.cu); the rest: workspace kernel below
   int rc = launch_nms_tiles_smem(cand_keys, reinterpret_cast<const float4*>(cand_boxes), cand_cls, counts, bs, cap,
                                  iou_thres, class_offset, max_nms, max_det, keep_idx, keep_slot,
-                                 reinterpret_cast<float4*>(keep_box), keep_score, keep_cls, keep_counts,
-                                 g_phase_host, (cudaStream_t)stream);
+                                 reinterpret_cast<float4*>(keep_box), keep_score, keep_cls, keep_counts, gray_eps,
+                                 keep_fragile, g_phase_host, (cudaStream_t)stream);
   if (rc || cap <= kNmsSmemCap) return rc;
   static bool attr_set = false;
   if (!attr_set) {
@@ -626,7 +629,7 @@ int hdy_nms_tiles(const uint64_t* cand_keys, const float* cand_boxes, const floa
   nms_tiles_kernel<<<(unsigned)bs, kNmsThreads, kSmemBytes, (cudaStream_t)stream>>>(
       cand_keys, reinterpret_cast<const float4*>(cand_boxes), cand_cls, counts, cap, iou_thres, class_offset,
       max_nms, max_det, keep_idx, keep_slot, reinterpret_cast<float4*>(keep_box), keep_score, keep_cls,
-      keep_counts, static_cast<unsigned char*>(workspace), kNmsSmemCap);
+      keep_counts, static_cast<unsigned char*>(workspace), kNmsSmemCap, keep_fragile);
   return check_launch("hdy_nms_tiles");
 }
 

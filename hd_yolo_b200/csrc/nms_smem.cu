@@ -43,6 +43,7 @@ struct FastSmem {
   uint16_t dom[kFastCap * kMaxDom];
   uint8_t ndom[kFastCap];
   uint8_t state[kFastCap];
+  uint8_t frag[kFastCap];        // cell-order position -> has a neighbour whose IoU could cross thr after the shift
   int cell[kFastNB + 3];
   int warp_i[33];
   float warp_f[2][32];
@@ -226,9 +227,15 @@ __global__ void __launch_bounds__(THREADS, 1) nms_tiles_smem_kernel(
     const float* __restrict__ cand_cls, const int32_t* __restrict__ counts, int cap, float thr, float class_offset,
     int max_nms, int max_det, int32_t* __restrict__ keep_idx, int32_t* __restrict__ keep_slot,
     float4* __restrict__ keep_box, float* __restrict__ keep_score, float* __restrict__ keep_cls,
-    int32_t* __restrict__ keep_counts, unsigned long long* __restrict__ phase_cycles) {
+    int32_t* __restrict__ keep_counts, float gray_eps, uint8_t* __restrict__ keep_fragile,
+    unsigned long long* __restrict__ phase_cycles) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   FastSmem& S = *reinterpret_cast<FastSmem*>(smem_raw);
+  // gray zone: pairs that this NMS leaves alone (IoU <= thr in tile coordinates) but whose IoU may exceed thr once both
+  // boxes are shifted to slide coordinates and rounded.  Both boxes of such a pair are reported FRAGILE: the slide-level
+  // merge must look at them even if they sit in the interior of their tile (interior shortcut).
+  const bool gray = keep_fragile != nullptr && gray_eps > 0.f;
+  uint8_t* o_frag = keep_fragile ? keep_fragile + (size_t)blockIdx.x * max_det : nullptr;
   constexpr int MAXR = kFastCap / THREADS;  // ranks owned by one thread
   const int tile = blockIdx.x;
   const int t = threadIdx.x;
@@ -308,6 +315,8 @@ __global__ void __launch_bounds__(THREADS, 1) nms_tiles_smem_kernel(
     S.warp_i[t >> 5] = ext_cnt;
   }
   for (int i = t; i < kFastNB + 3; i += THREADS) S.cell[i] = 0;
+  if (gray)
+    for (int i = t; i < kFastCap; i += THREADS) S.frag[i] = 0;
   if (t == 0) S.flags[0] = 1;
   __syncthreads();
   FastGeom g;
@@ -387,9 +396,13 @@ __global__ void __launch_bounds__(THREADS, 1) nms_tiles_smem_kernel(
     const int ri = S.crank[p];
     int nd = 0;
     auto record = [&](int q) {
-      if (iou_gt(S.cbox[q], bi, thr)) {
+      const float4 bq = S.cbox[q];
+      if (iou_gt(bq, bi, thr)) {
         if (nd < kMaxDom) S.dom[p * kMaxDom + nd] = (uint16_t)q;
         ++nd;
+      } else if (gray && iou_may_exceed(bq, bi, thr, gray_eps)) {
+        S.frag[p] = 1;
+        S.frag[q] = 1;
       }
     };
     const float cx = (bi.x + bi.z) * 0.5f, cy = (bi.y + bi.w) * 0.5f;
@@ -424,9 +437,15 @@ __global__ void __launch_bounds__(THREADS, 1) nms_tiles_smem_kernel(
     const float4 bi = S.cbox[p];
     const int ri = S.crank[p];
     for (int q = t; q < n_active; q += THREADS) {
-      if ((int)S.crank[q] < ri && iou_gt(S.cbox[q], bi, thr)) {
-        const int k = atomicAdd(&S.flags[1], 1);
-        if (k < kMaxDom) S.dom[p * kMaxDom + k] = (uint16_t)q;
+      if ((int)S.crank[q] < ri) {
+        const float4 bq = S.cbox[q];
+        if (iou_gt(bq, bi, thr)) {
+          const int k = atomicAdd(&S.flags[1], 1);
+          if (k < kMaxDom) S.dom[p * kMaxDom + k] = (uint16_t)q;
+        } else if (gray && iou_may_exceed(bq, bi, thr, gray_eps)) {
+          S.frag[p] = 1;
+          S.frag[q] = 1;
+        }
       }
     }
     __syncthreads();
@@ -563,6 +582,10 @@ __global__ void __launch_bounds__(THREADS, 1) nms_tiles_smem_kernel(
         if (o_box) o_box[opos] = gboxes[s];
         if (o_score) o_score[opos] = key_score(k);
         if (o_cls) o_cls[opos] = gcls ? gcls[s] : 0.f;
+        if (o_frag) {
+          const uint16_t pp = S.pos[r];
+          o_frag[opos] = (gray && pp != 0xffffu) ? S.frag[pp] : (uint8_t)0;
+        }
         ++opos;
       }
     }
@@ -580,8 +603,8 @@ constexpr int kFastThreads = 1024;
 int launch_nms_tiles_smem(const uint64_t* cand_keys, const float4* cand_boxes, const float* cand_cls,
                           const int32_t* counts, int bs, int cap, float thr, float class_offset, int max_nms,
                           int max_det, int32_t* keep_idx, int32_t* keep_slot, float4* keep_box, float* keep_score,
-                          float* keep_cls, int32_t* keep_counts, unsigned long long* phase_cycles,
-                          cudaStream_t stream) {
+                          float* keep_cls, int32_t* keep_counts, float gray_eps, uint8_t* keep_fragile,
+                          unsigned long long* phase_cycles, cudaStream_t stream) {
   static bool attr_set = false;
   if (!attr_set) {
     cudaError_t e = cudaFuncSetAttribute(nms_tiles_smem_kernel<kFastThreads>,
@@ -594,7 +617,7 @@ int launch_nms_tiles_smem(const uint64_t* cand_keys, const float4* cand_boxes, c
   }
   nms_tiles_smem_kernel<kFastThreads><<<(unsigned)bs, kFastThreads, sizeof(FastSmem), stream>>>(
       cand_keys, cand_boxes, cand_cls, counts, cap, thr, class_offset, max_nms, max_det, keep_idx, keep_slot,
-      keep_box, keep_score, keep_cls, keep_counts, phase_cycles);
+      keep_box, keep_score, keep_cls, keep_counts, gray_eps, keep_fragile, phase_cycles);
   return check_launch("hdy_nms_tiles(smem)");
 }
 

@@ -63,7 +63,8 @@ class DeviceMergeBackend:
     boxes [n,4] fp32, scores [n] fp32, gidx [n] int32 (global index, bit pattern of a uint32); rows >= n_local are
     replicas."""
 
-    def __init__(self, boxes, scores, gidx, n_local: int, conf_thres: float, iou_thres: float):
+    def __init__(self, boxes, scores, gidx, n_local: int, conf_thres: float, iou_thres: float, tile_id=None,
+                 cores=None, margin=None, dirty=None):
         import ctypes as C
 
         from . import _lib
@@ -86,7 +87,14 @@ class DeviceMergeBackend:
         lib = _lib.load()
         self.wbytes = lib.hdy_merge_workspace_bytes(max(self.n, 1))
         self.ws = torch.empty((self.wbytes,), dtype=torch.uint8, device=dev)
-        _call("hdy_merge_build", ptr(self.boxes), ptr(self.scores), ptr(self.gidx), 0, None, None, None, None, self.n,
+        if cores is not None:
+            # interior shortcut (see SlideAccumulator.verdicts): rows beyond n_local are replicas and never take it
+            tid = torch.full((max(self.n, 1),), -1, dtype=torch.int32, device=dev)
+            tid[:self.n_local] = tile_id[:self.n_local]
+            self._keep = (tid, cores.contiguous(), margin.contiguous(), dirty)
+        tile_p, cores_p, margin_p, dirty_p = (ptr(t) for t in self._keep) if cores is not None else (None,) * 4
+        _call("hdy_merge_build", ptr(self.boxes), ptr(self.scores), ptr(self.gidx), 0, tile_p, cores_p, dirty_p, margin_p,
+              None, self.n,
               self.n_local, _conf_thr_f32(conf_thres), self.iou, ptr(self.state), ptr(self.ws), self.wbytes, _stream(),
               launches=7)
 
@@ -120,9 +128,11 @@ class ShardedMerge:
     collective over all ranks (see merge_sharded / merge_emulated)."""
 
     def __init__(self, rank: int, world: int, boxes: torch.Tensor, scores: torch.Tensor, conf_thres: float,
-                 iou_thres: float, backend: Callable = DeviceMergeBackend):
+                 iou_thres: float, backend: Callable = DeviceMergeBackend, tile_id=None, cores=None, margin=None,
+                 dirty=None):
         self.rank, self.world = rank, world
         self.boxes, self.scores = boxes, scores
+        self.tile_id, self.cores, self.margin, self.dirty = tile_id, cores, margin, dirty
         self.conf, self.iou = conf_thres, iou_thres
         self.n_local = int(boxes.shape[0])
         self.backend_cls = backend
@@ -131,19 +141,24 @@ class ShardedMerge:
 
     # phase 1 ------------------------------------------------------------------------------------
     def local_summary(self) -> torch.Tensor:
-        """[4] fp32: bounding rectangle of the own detections (x1, y1, x2, y2; inverted if there are none)."""
+        """[5] fp32: bounding rectangle of the own detections (x1, y1, x2, y2; inverted if there are none) and the
+        largest overhang of an own box over its tile (0 without the interior shortcut)."""
         b = self.boxes
+        m = self.margin.reshape(1).to(torch.float32) if self.margin is not None else \
+            torch.zeros((1,), dtype=torch.float32, device=b.device)
         if self.n_local == 0:
             big = 3.0e38
-            return torch.tensor([big, big, -big, -big], dtype=torch.float32, device=b.device)
-        return torch.cat([b[:, :2].min(0).values, b[:, 2:].max(0).values])
+            return torch.cat([torch.tensor([big, big, -big, -big], dtype=torch.float32, device=b.device), m])
+        return torch.cat([b[:, :2].min(0).values, b[:, 2:].max(0).values, m])
 
     # phase 2 ------------------------------------------------------------------------------------
     def select_seam(self, summaries: torch.Tensor, counts: Sequence[int]) -> torch.Tensor:
-        """summaries [world, 4] (all-gathered), counts: rows per rank.  Returns the padded-to-be seam payload
+        """summaries [world, 5] (all-gathered), counts: rows per rank.  Returns the padded-to-be seam payload
         [m, 6] int32 = (box bits x4, score bits, global index) of the own seam rows."""
         self.counts = [int(c) for c in counts]
         self.base = sum(self.counts[:self.rank])
+        # boxes of any rank may stick out of their tiles: the shortcut needs the largest overhang anywhere
+        self.margin_all = float(summaries[:, 4].max()) if summaries.shape[1] > 4 else 0.0
         if sum(self.counts) >= 2 ** 32:
             raise ValueError("more than 2^32 detections in one slide")
         b, dev = self.boxes, self.boxes.device
@@ -184,7 +199,11 @@ class ShardedMerge:
             boxes[self.n_local:n] = rep[:, :4].contiguous().view(torch.float32)
             scores[self.n_local:n] = rep[:, 4].contiguous().view(torch.float32)
             gidx[self.n_local:n] = rep[:, 5]
-        self.backend = self.backend_cls(boxes[:n], scores[:n], gidx[:n], self.n_local, self.conf, self.iou)
+        kw = {}
+        if self.cores is not None:
+            kw = dict(tile_id=self.tile_id, cores=self.cores, dirty=self.dirty,
+                      margin=torch.tensor([self.margin_all], dtype=torch.float32, device=dev))
+        self.backend = self.backend_cls(boxes[:n], scores[:n], gidx[:n], self.n_local, self.conf, self.iou, **kw)
         self.round = 0
 
     # phase 4 (repeated) -------------------------------------------------------------------------
@@ -234,17 +253,18 @@ def _pad_gather(t: torch.Tensor, sizes: Sequence[int], group) -> List[torch.Tens
 
 
 def merge_sharded(boxes: torch.Tensor, scores: torch.Tensor, conf_thres: float, iou_thres: float, group=None,
-                  backend: Callable = DeviceMergeBackend) -> Dict[str, torch.Tensor]:
+                  backend: Callable = DeviceMergeBackend, tile_id=None, cores=None, margin=None,
+                  dirty=None) -> Dict[str, torch.Tensor]:
     """Sharded Ensemble.merge verdicts under torch.distributed.  boxes [n_local, 4] / scores [n_local] are this rank's
     rows of the slide-wide concatenation (rank order == tile order).  Returns {'state': uint8 [n_local],
     'base': first global row of this rank, 'exchanges': number of verdict all-gathers, 'seam_rows': [world]}."""
     import torch.distributed as dist
 
     rank, world = dist.get_rank(group), dist.get_world_size(group)
-    sm = ShardedMerge(rank, world, boxes, scores, conf_thres, iou_thres, backend)
+    sm = ShardedMerge(rank, world, boxes, scores, conf_thres, iou_thres, backend, tile_id, cores, margin, dirty)
     dev = boxes.device
-    # 1. rectangles + row counts
-    summ = [torch.empty((4,), dtype=torch.float32, device=dev) for _ in range(world)]
+    # 1. rectangles (+ overhang) + row counts
+    summ = [torch.empty((5,), dtype=torch.float32, device=dev) for _ in range(world)]
     dist.all_gather(summ, sm.local_summary(), group=group)
     cnt = [torch.empty((1,), dtype=torch.int64, device=dev) for _ in range(world)]
     dist.all_gather(cnt, torch.tensor([sm.n_local], dtype=torch.int64, device=dev), group=group)

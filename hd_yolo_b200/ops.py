@@ -304,7 +304,7 @@ class _Cand:
 
 
 def _run_nms(cand: _Cand, iou_thres: float, max_det: int, class_offset: float = 0.0, max_nms: int = 0,
-             want_cls: bool = False):
+             want_cls: bool = False, gray_eps: float = 0.0, fragile_out: Optional[list] = None):
     lib = _lib.load()
     dev = cand.counts.device
     bs, cap = cand.bs, cand.cap
@@ -315,12 +315,16 @@ def _run_nms(cand: _Cand, iou_thres: float, max_det: int, class_offset: float = 
     keep_score = torch.empty((bs, md), dtype=torch.float32, device=dev)
     keep_cls = torch.empty((bs, md), dtype=torch.float32, device=dev) if want_cls else None
     keep_counts = torch.empty(bs, dtype=torch.int32, device=dev)
+    keep_frag = None
+    if gray_eps > 0.0 and fragile_out is not None:
+        keep_frag = torch.empty((bs, md), dtype=torch.uint8, device=dev)
+        fragile_out.append(keep_frag)
     wbytes = lib.hdy_nms_workspace_bytes(bs, cap)
     ws = _scratch.get(dev, "nms_ws", wbytes) if wbytes else None
     _call("hdy_nms_tiles", ptr(cand.keys), ptr(cand.boxes), ptr(cand.cls), ptr(cand.counts), bs, cap,
                           _iou_thr_f32(iou_thres), float(class_offset), int(max_nms), md, ptr(keep_idx),
                           ptr(keep_slot), ptr(keep_box), ptr(keep_score), ptr(keep_cls), ptr(keep_counts),
-                          ptr(ws), wbytes, _stream())
+                          float(gray_eps), ptr(keep_frag), ptr(ws), wbytes, _stream())
     return keep_idx, keep_slot, keep_box, keep_score, keep_cls, keep_counts, md
 
 
@@ -502,6 +506,7 @@ class DetectBatch:
     counts: torch.Tensor       # [bs] int32
     cand_counts: torch.Tensor  # [bs+1] int32: candidates per tile after the filter, then status word
     max_det: int
+    fragile: Optional[torch.Tensor] = None  # [bs, max_det] uint8: gray-zone flags (detect_postprocess(gray_eps=...))
 
     def to_list(self, multi_label: bool = False, conf_thres: float = 0.0) -> List[Dict[str, torch.Tensor]]:
         """The reference's List[Dict] (yolo_head.py:335-355); synchronises once."""
@@ -533,13 +538,17 @@ def hier_ops_from_descendants(descendants: Dict[int, List[int]]) -> List[Tuple[i
 def detect_postprocess(dets: List[torch.Tensor], spec: HeadSpec, conf_thres: float = 0.15,
                        iou_thres: float = 0.45, max_det: int = 300, layout: int = 0,
                        cap: Optional[int] = None, hier_ops: Optional[List[Tuple[int, int]]] = None,
-                       min_size: float = 2.0) -> DetectBatch:
+                       min_size: float = 2.0, gray_eps: float = 0.0) -> DetectBatch:
     """Fused Detect.compute_proposals + compute_outputs without masks
     (yolo_head.py:185-213, 301-345 -> utils_general.py:299-356): raw level logits in,
     final boxes / scores / labels out, no host synchronisation.
 
     cap bounds the candidates kept per tile after the confidence filter (default: all rows, which
     can never overflow); overflow is reported by DetectBatch.to_list().
+
+    gray_eps > 0 (whole-slide pipeline): also report, per survivor, whether a neighbour's IoU could cross iou_thres
+    once both boxes are shifted to slide coordinates and rounded by up to gray_eps per coordinate
+    (DetectBatch.fragile; see hdy_nms_tiles in include/hd_yolo_b200.h).
     """
     _check_thresholds(conf_thres, iou_thres)
     lib = _lib.load()
@@ -553,7 +562,9 @@ def detect_postprocess(dets: List[torch.Tensor], spec: HeadSpec, conf_thres: flo
     _call("hdy_filter_compact_logits", levels, spec.nl, bs, spec.na, nc, no, layout, cthr, float(min_size), cap,
                                       ptr(cand.keys), ptr(cand.boxes), ptr(cand.counts), cand.status_ptr,
                                       _stream())
-    keep_idx, _, keep_box, _, _, keep_counts, md = _run_nms(cand, iou_thres, max_det)
+    frag: list = []
+    keep_idx, _, keep_box, _, _, keep_counts, md = _run_nms(cand, iou_thres, max_det, gray_eps=gray_eps,
+                                                            fragile_out=frag)
     scores_full = torch.empty((bs, md, 1 + nc), dtype=torch.float32, device=dev)
     lvl = torch.empty((bs, md), dtype=torch.float32, device=dev)
     ne = no - 5 - nc
@@ -571,7 +582,8 @@ def detect_postprocess(dets: List[torch.Tensor], spec: HeadSpec, conf_thres: flo
               ptr(scores_full), ptr(lvl), ptr(extra), _stream())
         _call("hdy_select_scores", ptr(scores_full), ptr(keep_counts), bs, md, nc, flat, len(ops), cthr, ptr(score),
               ptr(label), _stream())
-    return DetectBatch(keep_box, scores_full, score, label, lvl, extra, keep_idx, keep_counts, cand.counts, md)
+    return DetectBatch(keep_box, scores_full, score, label, lvl, extra, keep_idx, keep_counts, cand.counts, md,
+                       frag[0] if frag else None)
 
 
 def flatten_onehot_objects(x: Dict[str, torch.Tensor]) -> Dict[str, torch.Tensor]:

@@ -10,6 +10,7 @@ from __future__ import annotations
 
 from typing import Callable, Dict, List, Optional, Sequence, Tuple
 
+import numpy as np
 import torch
 
 from . import dist as hdist
@@ -28,7 +29,7 @@ class SlidePostprocessor:
 
     def __init__(self, spec: HeadSpec, image_size, roi_size, overlap: int, conf_thres: float, iou_thres: float,
                  max_det: int, cap: Optional[int] = None, batch: int = 128, rank: int = 0, world: int = 1,
-                 group=None, device=None, capacity: Optional[int] = None):
+                 group=None, device=None, capacity: Optional[int] = None, interior_shortcut: bool = True):
         self.spec, self.conf, self.iou, self.max_det, self.cap = spec, conf_thres, iou_thres, max_det, cap
         self.batch, self.rank, self.world, self.group = batch, rank, world, group
         self.device = torch.device(device if device is not None else f"cuda:{torch.cuda.current_device()}")
@@ -39,6 +40,16 @@ class SlidePostprocessor:
         md = min(max_det, cap) if cap else max_det
         self.capacity = int(capacity) if capacity is not None else max((t1 - t0) * md, 1)
         self.acc = SlideAccumulator(self.capacity, self.device)
+        # Interior shortcut of the slide merge: a detection strictly inside its tile's core can only be suppressed by
+        # a survivor of its own tile, and only if rounding `box + tile origin` to fp32 lifts their IoU over the
+        # threshold.  The per-tile NMS flags exactly those pairs (gray zone, half an ulp of the largest slide
+        # coordinate per box coordinate), so everything else in the interior is KEPT without a pair test -- exactly.
+        h, w = (image_size, image_size) if isinstance(image_size, (int, float)) else (image_size[0], image_size[1])
+        top = float(max(h, w)) * 1.01 + 64.0
+        self.gray_eps = float(np.spacing(np.float32(top))) / 2.0
+        # the cell margins of the NMS binning cover a rounding of < 0.004 px (slides up to 131 072 px) -- beyond
+        # that, and for degenerate thresholds, every row takes the unconditional path
+        self.shortcut = bool(interior_shortcut) and self.gray_eps <= 0.004 and iou_thres >= 0.05
 
     def detect(self, provider: Callable[[int, int], List[torch.Tensor]]) -> None:
         """Per-tile post-processing of every own tile, appended in slide coordinates.  No host synchronisation."""
@@ -46,7 +57,8 @@ class SlidePostprocessor:
         self.acc.reset()
         for a in range(t0, t1, self.batch):
             b = min(a + self.batch, t1)
-            out = detect_postprocess(provider(a, b), self.spec, self.conf, self.iou, self.max_det, cap=self.cap)
+            out = detect_postprocess(provider(a, b), self.spec, self.conf, self.iou, self.max_det, cap=self.cap,
+                                     gray_eps=self.gray_eps if self.shortcut else 0.0)
             self.acc.append(out, self.rois_dev[a - t0:b - t0])
 
     def merge(self, ordered: bool = True) -> Dict[str, torch.Tensor]:
@@ -57,11 +69,42 @@ class SlidePostprocessor:
         boxes, scores = self.acc.boxes[:n], self.acc.scores[:n]
         info: Dict[str, object] = {}
         if self.world > 1:
-            res = hdist.merge_sharded(boxes, scores, self.conf, self.iou, group=self.group)
+            kw = {}
+            if self.shortcut:
+                # tile ids of the accumulator are local; the core table covers the whole slide
+                t0 = self.tile_range[0]
+                tl = self.acc.tile[:n]
+                tg = torch.where(tl >= 0, tl + t0, ~((~tl) + t0))
+                from .slide import dirty_tiles, tile_cores
+                if getattr(self, "_cores_all", None) is None:
+                    self._cores_all = tile_cores(self.rois).to(self.device)
+                    self._rois_all = self.rois.to(self.device).contiguous()
+                margin, far_boxes, far_tile, far_count = self.acc.overhang()
+                # far-reaching boxes of every rank can touch any rank's tiles: gather the (short) lists
+                import torch.distributed as dist
+                nf = min(int(far_count.item()), int(far_boxes.shape[0]))
+                overflow = int(far_count.item()) > int(far_boxes.shape[0])
+                cnts = [torch.empty((2,), dtype=torch.int64, device=self.device) for _ in range(self.world)]
+                dist.all_gather(cnts, torch.tensor([nf, int(overflow)], dtype=torch.int64, device=self.device),
+                                group=self.group)
+                sizes = [int(c[0]) for c in cnts]
+                pay = torch.cat([far_boxes[:nf], (far_tile[:nf] + t0).to(torch.float32)[:, None]], 1)
+                parts = hdist._pad_gather(pay, sizes, self.group)
+                allf = torch.cat(parts) if sum(sizes) else torch.zeros((0, 5), dtype=torch.float32, device=self.device)
+                cap = max(int(allf.shape[0]), 1)
+                fb = torch.zeros((cap, 4), dtype=torch.float32, device=self.device)
+                ft = torch.zeros((cap,), dtype=torch.int32, device=self.device)
+                fb[:allf.shape[0]] = allf[:, :4]
+                ft[:allf.shape[0]] = allf[:, 4].to(torch.int32)
+                total = int(allf.shape[0]) + (cap + 1 if any(int(c[1]) for c in cnts) else 0)   # > cap: all dirty
+                fc = torch.tensor([total], dtype=torch.int32, device=self.device)
+                kw = dict(tile_id=tg.contiguous(), cores=self._cores_all, margin=margin,
+                          dirty=dirty_tiles(fb, ft, fc, self._rois_all))
+            res = hdist.merge_sharded(boxes, scores, self.conf, self.iou, group=self.group, **kw)
             state, base = res['state'], res['base']
             info = {'exchanges': res['exchanges'], 'seam_rows': res['seam_rows']}
         else:
-            state, base = merge_nms(boxes, scores, self.conf, self.iou), 0
+            state, base = self.acc.verdicts(self.conf, self.iou, interior_shortcut=self.shortcut)[:n], 0
         out: Dict[str, object] = {'state': state, 'n': n, 'base': base, **info}
         if ordered:
             idx, ob, os_, ol = _kept_in_order(state, boxes, scores, self.acc.labels[:n], n)

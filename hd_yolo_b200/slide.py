@@ -114,7 +114,7 @@ def rescale_outputs(r: Dict[str, torch.Tensor], scale: float = 1.0) -> Dict[str,
 def merge_nms(boxes: torch.Tensor, scores: torch.Tensor, conf_thres: float, iou_thres: float,
               tile_id: Optional[torch.Tensor] = None, cores: Optional[torch.Tensor] = None,
               margin: Optional[torch.Tensor] = None, n_dev: Optional[torch.Tensor] = None,
-              max_rounds: int = 24) -> torch.Tensor:
+              max_rounds: int = 24, dirty: Optional[torch.Tensor] = None) -> torch.Tensor:
     """Verdict per row of the slide-level greedy NMS of Ensemble.merge (yolo.py:189-195):
     uint8 [n] of STATE_KEPT / STATE_SUPPRESSED / STATE_DROPPED (score <= conf_thres).
     tile_id + cores + margin enable the interior shortcut (see include/hd_yolo_b200.h)."""
@@ -139,7 +139,8 @@ def merge_nms(boxes: torch.Tensor, scores: torch.Tensor, conf_thres: float, iou_
     rounds = max_rounds
     while True:
         _call("hdy_merge_nms", ptr(boxes), ptr(scores), ptr(tile_id) if use_cores else None,
-              ptr(cores) if use_cores else None, ptr(margin) if use_cores else None, ptr(n_dev), n,
+              ptr(cores) if use_cores else None, ptr(dirty) if use_cores else None,
+              ptr(margin) if use_cores else None, ptr(n_dev), n,
               _conf_thr_f32(conf_thres), _iou_thr_f32(iou_thres), rounds, ptr(state), ptr(status), ptr(ws), wbytes,
               _stream(), launches=8 + rounds)
         if not int(status.item()) & _lib.HDY_STATUS_ROUNDS:
@@ -147,6 +148,16 @@ def merge_nms(boxes: torch.Tensor, scores: torch.Tensor, conf_thres: float, iou_
         if rounds >= 64:
             raise HdyError("merge NMS did not converge in 64 rounds")
         rounds, _ = min(64, rounds * 2), status.zero_()
+
+
+def dirty_tiles(far_boxes: torch.Tensor, far_tile: torch.Tensor, far_count: torch.Tensor,
+                rois: torch.Tensor) -> torch.Tensor:
+    """uint8 [n_tiles]: tiles whose window is touched by a far-reaching box of another tile (hdy_merge_dirty_tiles)."""
+    n_tiles = int(rois.shape[0])
+    dirty = torch.empty((max(n_tiles, 1),), dtype=torch.uint8, device=rois.device)
+    _call("hdy_merge_dirty_tiles", ptr(far_boxes), ptr(far_tile), ptr(far_count), int(far_boxes.shape[0]),
+          ptr(_aligned16(rois.contiguous())), n_tiles, ptr(dirty), _stream())
+    return dirty
 
 
 def sort_keys(keys: torch.Tensor, n_dev: Optional[torch.Tensor] = None) -> torch.Tensor:
@@ -215,7 +226,7 @@ def merge_outputs(r: List[Dict[str, torch.Tensor]]) -> Dict[str, torch.Tensor]:
         status = torch.zeros((1,), dtype=torch.int32, device=dev)
         for b0 in range(0, bs, 65535):
             b1 = min(bs, b0 + 65535)
-            _call("hdy_merge_append", ptr(padded[b0:b1]), None, None, ptr(counts[b0:b1]), ptr(rois[b0:b1]), b1 - b0, md,
+            _call("hdy_merge_append", ptr(padded[b0:b1]), None, None, None, ptr(counts[b0:b1]), ptr(rois[b0:b1]), b1 - b0, md,
                   b0, 1.0, n, ptr(out), None, None, None, ptr(cursor), ptr(tile_offsets[b0:]), ptr(status), _stream(),
                   launches=2)
     res = {'boxes': out, **res}
@@ -288,6 +299,7 @@ class SlideAccumulator:
         self.tile_offsets: List[torch.Tensor] = []
         self.rois: List[torch.Tensor] = []
         self.n_tiles = 0
+        self.gray_ok = True        # every batch so far came with gray-zone flags (DetectBatch.fragile) and scale 1
 
     def reset(self):
         self.cursor.zero_()
@@ -295,6 +307,7 @@ class SlideAccumulator:
         self.tile_offsets.clear()
         self.rois.clear()
         self.n_tiles = 0
+        self.gray_ok = True
 
     def append(self, batch: DetectBatch, rois: torch.Tensor, scale: float = 1.0) -> None:
         """rois [bs, 4] fp32 on the device: the windows (x0, y0, x1, y1) of the batch's tiles."""
@@ -303,8 +316,11 @@ class SlideAccumulator:
             raise HdyError("rois must be a CUDA fp32 tensor [bs, 4]")
         rois = _aligned16(rois.contiguous())
         offs = torch.empty((bs + 1,), dtype=torch.int64, device=self.device)
+        fragile = batch.fragile if scale == 1.0 else None
+        if fragile is None:
+            self.gray_ok = False
         _call("hdy_merge_append", ptr(batch.boxes), ptr(batch.scores), ptr(batch.labels) if self.labels is not None else None,
-              ptr(batch.counts), ptr(rois), bs, batch.max_det, self.n_tiles, float(scale), self.capacity,
+              ptr(fragile), ptr(batch.counts), ptr(rois), bs, batch.max_det, self.n_tiles, float(scale), self.capacity,
               ptr(self.boxes), ptr(self.scores), ptr(self.labels), ptr(self.tile), ptr(self.cursor), ptr(offs),
               ptr(self.status), _stream(), launches=2)
         self.tile_offsets.append(offs)
@@ -318,16 +334,44 @@ class SlideAccumulator:
             raise HdyError(f"slide accumulator overflow: {int(both[0])} rows, capacity {self.capacity}")
         return int(both[0])
 
+    FAR_CAP_PX = 64.0        # boxes sticking out of their tile by more than this are handled one by one
+    FAR_CAPACITY = 4096
+
+    def overhang(self):
+        """(margin [1] fp32, far_boxes [FAR_CAPACITY,4], far_tile [FAR_CAPACITY] i32, far_count [1] i32), all on the
+        device: how far the appended boxes stick out of their own tiles at most, not counting the few far-reaching ones
+        (huge false positives), which are listed instead (tile indices local to this accumulator)."""
+        rois = torch.cat(self.rois)
+        d = self.device
+        margin = torch.zeros((1,), dtype=torch.float32, device=d)
+        far_boxes = torch.empty((self.FAR_CAPACITY, 4), dtype=torch.float32, device=d)
+        far_tile = torch.empty((self.FAR_CAPACITY,), dtype=torch.int32, device=d)
+        far_count = torch.zeros((1,), dtype=torch.int32, device=d)
+        _call("hdy_merge_overhang", ptr(self.boxes), ptr(self.tile), ptr(rois), ptr(self.cursor), self.capacity,
+              float(self.FAR_CAP_PX), ptr(margin), ptr(far_boxes), ptr(far_tile), ptr(far_count), self.FAR_CAPACITY,
+              _stream())
+        return margin, far_boxes, far_tile, far_count
+
     def verdicts(self, conf_thres: float, iou_thres: float, interior_shortcut: bool = False) -> torch.Tensor:
-        """uint8 state per appended row (asynchronous except for the round-budget check)."""
+        """uint8 state per appended row (asynchronous except for the round-budget check).
+
+        interior_shortcut: rows that lie strictly inside their tile's core (the part no other tile's boxes can reach)
+        and are not flagged fragile are KEPT without any pair test.  Exact when every batch was produced with
+        gray-zone flags (detect_postprocess(gray_eps=...)) for an IoU threshold <= iou_thres: then a survivor of the
+        per-tile NMS can only be suppressed by another tile's box or by a flagged neighbour."""
         n = self.capacity
         kw = {}
         if interior_shortcut:
+            if not self.gray_ok:
+                raise HdyError("interior_shortcut needs gray-zone flags on every appended batch "
+                               "(detect_postprocess(gray_eps=...), scale 1)")
             rois = torch.cat(self.rois)
-            margin = torch.zeros((1,), dtype=torch.float32, device=self.device)
-            _call("hdy_merge_overhang", ptr(self.boxes), ptr(self.tile), ptr(rois), ptr(self.cursor), n, ptr(margin),
-                  _stream())
-            kw = dict(tile_id=self.tile, cores=tile_cores(rois).to(self.device), margin=margin)
+            if getattr(self, "_cores_key", None) != (len(self.rois), int(rois.shape[0])):
+                self._cores = tile_cores(rois).to(self.device)
+                self._cores_key = (len(self.rois), int(rois.shape[0]))
+            margin, far_boxes, far_tile, far_count = self.overhang()
+            kw = dict(tile_id=self.tile, cores=self._cores, margin=margin,
+                      dirty=dirty_tiles(far_boxes, far_tile, far_count, rois))
         return merge_nms(self.boxes, self.scores, conf_thres, iou_thres, n_dev=self.cursor, **kw)
 
     def merge(self, conf_thres: float, iou_thres: float, max_det: Optional[int] = None,

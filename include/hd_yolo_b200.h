@@ -130,12 +130,18 @@ HDY_API size_t hdy_nms_workspace_bytes(int bs, int cap);
  *   keep_box   [bs, max_det] f32x4 : un-offset box of each survivor (may be NULL)
  *   keep_score [bs, max_det] f32 : NMS score of each survivor (may be NULL)
  *   keep_cls   [bs, max_det] f32 : cand_cls of each survivor (may be NULL)
- *   keep_counts[bs] i32 */
+ *   keep_counts[bs] i32
+ * Gray zone (keep_fragile non-NULL and gray_eps > 0; used by the whole-slide pipeline): keep_fragile [bs, max_det] u8
+ * is set for every survivor that has a neighbour with IoU <= iou_thres here, but whose IoU could exceed iou_thres if
+ * every coordinate of both boxes moved by up to gray_eps -- which is what Detect.merge_outputs' `boxes + roi origin`
+ * does to them in fp32 (yolo_head.py:455) before Ensemble.merge runs NMS again (yolo.py:195).  Survivors without the
+ * flag can never be suppressed by a survivor of their own tile in slide coordinates.  Tiles with more than 4096
+ * candidates report every survivor fragile. */
 HDY_API int hdy_nms_tiles(const uint64_t* cand_keys, const float* cand_boxes, const float* cand_cls,
                   const int32_t* counts, int bs, int cap, float iou_thres, float class_offset, int max_nms,
                   int max_det, int32_t* keep_idx, int32_t* keep_slot, float* keep_box, float* keep_score,
-                  float* keep_cls, int32_t* keep_counts, void* workspace, size_t workspace_bytes,
-                  hdy_stream_t stream);
+                  float* keep_cls, int32_t* keep_counts, float gray_eps, uint8_t* keep_fragile, void* workspace,
+                  size_t workspace_bytes, hdy_stream_t stream);
 
 /* Debug: when device_buf8 (8 x u64, zeroed by the caller) is non-NULL, hdy_nms_tiles accumulates per-phase
  * SM cycles into it (0 load, 1 sort, 2 gather, 3 binning, 4 rounds, 5 output, 6 rounds run, 7 CTAs).
@@ -253,30 +259,44 @@ HDY_API int hdy_affine_boxes(float* rows, int64_t n, int row_len, float pad_x, f
  * appended, tile by tile in order, to flat slide-level arrays at *cursor (device int64, advanced by the call).
  *   boxes [bs,max_det,4] f32, scores [bs,max_det] f32, labels [bs,max_det] i64, counts [bs] i32, rois [bs,4] f32
  *   out_boxes [capacity,4], out_scores/out_labels/out_tile [capacity] (the last three may be NULL)
- *   tile_offsets [bs+1] i64: first output row of every tile, total in [bs]; out_tile[i] = tile_base + t.
+ *   tile_offsets [bs+1] i64: first output row of every tile, total in [bs]; out_tile[i] = tile_base + t, or
+ *   ~(tile_base + t) (negative) when fragile [bs,max_det] u8 (may be NULL) flags the detection: such rows never take
+ *   the interior shortcut of hdy_merge_nms.
  * Rows that do not fit set HDY_STATUS_OVERFLOW in *status. */
-HDY_API int hdy_merge_append(const float* boxes, const float* scores, const int64_t* labels, const int32_t* counts,
-                             const float* rois, int bs, int max_det, int tile_base, float scale, int64_t capacity,
+HDY_API int hdy_merge_append(const float* boxes, const float* scores, const int64_t* labels, const uint8_t* fragile,
+                             const int32_t* counts, const float* rois, int bs, int max_det, int tile_base, float scale,
+                             int64_t capacity,
                              float* out_boxes, float* out_scores, int64_t* out_labels, int32_t* out_tile,
                              int64_t* cursor, int64_t* tile_offsets, int32_t* status, hdy_stream_t stream);
 
-/* Largest distance by which any box sticks out of its own tile (atomic max into *margin, which the caller zeroes).
- * n_dev (device int64, may be NULL) holds the live row count; n_max bounds it. */
+/* Largest distance by which a box sticks out of its own tile (atomic max into *margin, which the caller zeroes).
+ * n_dev (device int64, may be NULL) holds the live row count; n_max bounds it.  tile_id may hold ~tile for fragile
+ * rows.  With far_count non-NULL (device int32, zeroed by the caller), boxes sticking out by more than far_cap are
+ * not folded into the margin but listed (far_boxes [far_capacity,4], far_tile [far_capacity]; *far_count may exceed
+ * far_capacity: overflow): one huge false positive would otherwise shrink every tile's core. */
 HDY_API int hdy_merge_overhang(const float* boxes, const int32_t* tile_id, const float* tile_rois,
-                               const int64_t* n_dev, int64_t n_max, float* margin, hdy_stream_t stream);
+                               const int64_t* n_dev, int64_t n_max, float far_cap, float* margin, float* far_boxes,
+                               int32_t* far_tile, int32_t* far_count, int far_capacity, hdy_stream_t stream);
+/* dirty [n_tiles] u8: 1 for every tile whose window is touched by a listed far-reaching box of another tile (all
+ * tiles if the list overflowed).  Rows of dirty tiles never take the interior shortcut. */
+HDY_API int hdy_merge_dirty_tiles(const float* far_boxes, const int32_t* far_tile, const int32_t* far_count,
+                                  int far_capacity, const float* tile_rois, int n_tiles, uint8_t* dirty,
+                                  hdy_stream_t stream);
 
 /* T3: Ensemble.merge (yolo.py:165-204): keep scores > conf_thres, class-agnostic greedy NMS
  * (torchvision.ops.nms semantics: score-descending, ties by lower index, IoU > iou_thres in fp32) over all n rows.
  * Sparse and exact: boxes are binned by centre, verdicts are resolved as a fixed point in at most max_rounds
  * rounds (HDY_STATUS_ROUNDS in *status if the budget was too small; call again with more).
  *   state [n] u8 receives HDY_STATE_* per row.
- * Optional shortcut (tile_id, tile_cores [n_tiles,4], margin all non-NULL): a row whose box lies strictly inside
- * its tile's core shrunk by *margin is KEPT without any pair test.  That is exact only if survivors of the same
- * tile never exceed iou_thres against each other in slide coordinates; pass NULL for the
- * unconditional path. */
+ * Optional shortcut (tile_id, tile_cores [n_tiles,4], margin all non-NULL; tile_dirty [n_tiles] optional): a row
+ * with tile_id >= 0 whose box lies strictly inside its tile's core shrunk by *margin, in a tile that is not dirty, is
+ * KEPT without any pair test.  Exact when the rows that can be suppressed by a survivor of their OWN tile in slide
+ * coordinates carry a negative tile_id (hdy_nms_tiles' gray-zone flags -> hdy_merge_append) -- see DESIGN.md 3.5;
+ * pass NULL for the unconditional path. */
 HDY_API size_t hdy_merge_workspace_bytes(int64_t n_max);
 HDY_API int hdy_merge_nms(const float* boxes, const float* scores, const int32_t* tile_id, const float* tile_cores,
-                          const float* margin, const int64_t* n_dev, int64_t n_max, float conf_thres,
+                          const uint8_t* tile_dirty, const float* margin, const int64_t* n_dev, int64_t n_max,
+                          float conf_thres,
                           float iou_thres, int max_rounds, uint8_t* state, int32_t* status, void* workspace,
                           size_t workspace_bytes, hdy_stream_t stream);
 
@@ -285,7 +305,8 @@ HDY_API int hdy_merge_nms(const float* boxes, const float* scores, const int32_t
  * slide-wide concatenation, which breaks score ties exactly as the single-device call does.
  *   build -> { rounds(first_round, n_rounds) -> export_states(sel) -> [all-gather] -> import_states } ... -> finish */
 HDY_API int hdy_merge_build(const float* boxes, const float* scores, const uint32_t* gidx, uint32_t gidx_base,
-                            const int32_t* tile_id, const float* tile_cores, const float* margin,
+                            const int32_t* tile_id, const float* tile_cores, const uint8_t* tile_dirty,
+                            const float* margin,
                             const int64_t* n_dev, int64_t n_max, int64_t n_local, float conf_thres, float iou_thres,
                             uint8_t* state, void* workspace, size_t workspace_bytes, hdy_stream_t stream);
 HDY_API int hdy_merge_rounds(void* workspace, int64_t n_max, float iou_thres, int first_round, int n_rounds,

@@ -9,7 +9,7 @@ UNKNOWN, KEPT, SUPPRESSED, DROPPED, REMOTE_UNKNOWN = 0, 1, 2, 3, 4
 
 
 class TorchMergeBackend:
-    def __init__(self, boxes, scores, gidx, n_local, conf_thres, iou_thres):
+    def __init__(self, boxes, scores, gidx, n_local, conf_thres, iou_thres, **_shortcut):
         self.n, self.n_local = int(boxes.shape[0]), int(n_local)
         b = boxes.float().cpu()
         s = scores.float().cpu()

@@ -40,7 +40,8 @@ def test_argument_errors_are_detected_on_host():
     # nl = 0 is invalid; nothing is launched, so this is safe without a GPU
     rc = lib.hdy_decode_concat(None, 0, 1, 3, 9, 0, None, None)
     assert rc == -1 and len(lib.hdy_last_error()) > 0
-    rc = lib.hdy_nms_tiles(None, None, None, None, 1, 16, 0.5, 0.0, 0, 10, None, None, None, None, None, None, None, 0, None)
+    rc = lib.hdy_nms_tiles(None, None, None, None, 1, 16, 0.5, 0.0, 0, 10, None, None, None, None, None, None, 0.0, None,
+                           None, 0, None)
     assert rc == -1
 
 

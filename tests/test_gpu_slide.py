@@ -97,17 +97,10 @@ def test_slide_accumulator_vs_oracle(cuda_device, seed, H, W, roi, overlap, n, o
     assert torch.equal(out['labels'].cpu(), ref['labels'])
     # 'index' addresses the concatenated order
     assert torch.equal(ref_m['boxes'][out['index'].cpu()], ref['boxes'])
-    # the interior shortcut gives the same verdicts whenever no same-tile pair crosses the threshold
-    st_full = acc.verdicts(0.2, 0.45)[:n_rows]
-    st_fast = acc.verdicts(0.2, 0.45, interior_shortcut=True)[:n_rows]
-    same_tile_clean = True
-    for t in tiles:   # survivors of one tile must already be mutually <= thr for the shortcut's premise
-        b = t['boxes'] + torch.cat([t['roi'][:2], t['roi'][:2]])
-        keep = t['scores'] > 0.2
-        if int(keep.sum()) != len(port.nms(b[keep], t['scores'][keep], 0.45)):
-            same_tile_clean = False
-    if same_tile_clean:
-        assert torch.equal(st_full, st_fast)
+    # the interior shortcut is refused without the gray-zone flags of the per-tile NMS (these batches have none);
+    # its exactness with flags is covered by test_interior_shortcut_is_exact_far_from_the_origin
+    with pytest.raises(hdy.HdyError, match="gray-zone"):
+        acc.verdicts(0.2, 0.45, interior_shortcut=True)
 
 
 def test_merge_nms_random_dense_vs_oracle(cuda_device):
@@ -196,3 +189,83 @@ def test_merge_nms_with_large_boxes(cuda_device, n_small, n_large, seed):
     ref[kept] = 1
     got = hdy.merge_nms(boxes.to(cuda_device), scores.to(cuda_device), conf, iou).cpu()
     assert torch.equal(got, ref)
+
+
+def _near_threshold_tile(g, n_pairs, n_free, thr, tile=1024.0):
+    """Boxes of one tile (tile coordinates): pairs of equal squares shifted so that their IoU sits within ~2e-4 of thr
+    (either side), plus free nuclei-sized boxes."""
+    s = 14.0 + 16.0 * torch.rand((n_pairs, 1), generator=g)
+    dx = s * (1 - thr) / (1 + thr) + (torch.rand((n_pairs, 1), generator=g) - 0.5) * 0.006
+    c = 40.0 + (tile - 120.0) * torch.rand((n_pairs, 2), generator=g)
+    a = torch.cat([c, c + s], 1)
+    b = a + torch.cat([dx, torch.zeros_like(dx), dx, torch.zeros_like(dx)], 1)
+    cf = tile * torch.rand((n_free, 2), generator=g)
+    sf = 12.0 + 24.0 * torch.rand((n_free, 2), generator=g)
+    free = torch.cat([cf - sf / 2, cf + sf / 2], 1)
+    boxes = torch.cat([a, b, free]).float()
+    return boxes[torch.randperm(len(boxes), generator=g)].contiguous()
+
+
+@pytest.mark.parametrize("thr,seed", [(0.45, 0), (0.3, 1), (0.7, 2)])
+def test_interior_shortcut_is_exact_far_from_the_origin(cuda_device, thr, seed):
+    """At slide coordinates ~10^5 the fp32 rounding of `box + tile origin` (yolo_head.py:455) moves IoUs by ~5e-4, so
+    Ensemble.merge (yolo.py:195) suppresses pairs the per-tile NMS kept.  The gray-zone flags of hdy_nms_tiles must
+    route exactly those rows around the interior shortcut: verdicts == torchvision's dense NMS on the shifted boxes."""
+    import torchvision
+    from hd_yolo_b200 import ops, _lib
+    from hd_yolo_b200.ops import DetectBatch
+    dev = cuda_device
+    g = torch.Generator().manual_seed(seed)
+    rois_all = hs.sliding_window_scanner((100000, 100000), (1024, 1024), 64)
+    n_cols = 105
+    tiles = [r * n_cols + c for r in (100, 101, 102) for c in (100, 101, 102)]      # full tiles near (96000, 96000)
+    rois = rois_all[tiles]
+    bs, conf = len(tiles), 0.2
+    per_tile = [_near_threshold_tile(g, 150, 120, thr) for _ in range(bs)]
+    n = max(len(b) for b in per_tile)
+    eps = float(np.spacing(np.float32(101000.0))) / 2
+    cand = ops._Cand(dev, bs, n, tag="gz")
+    boxes_pad = torch.zeros((bs, n, 4))
+    scores_pad = torch.zeros((bs, n))
+    for i, b in enumerate(per_tile):
+        boxes_pad[i, :len(b)] = b
+        scores_pad[i, :len(b)] = 0.25 + 0.7 * torch.rand((len(b),), generator=g)
+    keys = torch.empty((bs, n), dtype=torch.int64, device=dev)
+    ops._call("hdy_make_keys", _lib.ptr(scores_pad.to(dev)), bs, n, _lib.ptr(keys), ops._stream())
+    cand.keys, cand.boxes = keys, boxes_pad.to(dev).contiguous()
+    cand.counts = torch.tensor([len(b) for b in per_tile] + [0], dtype=torch.int32).to(dev)
+    frag = []
+    keep_idx, _, keep_box, keep_score, _, keep_counts, md = ops._run_nms(cand, thr, n, gray_eps=eps, fragile_out=frag)
+    kc = keep_counts.cpu().tolist()
+    # per-tile NMS == torchvision in tile coordinates
+    kept_tiles, flips = [], 0
+    for i, b in enumerate(per_tile):
+        ref = torchvision.ops.nms(b, scores_pad[i, :len(b)], thr)
+        assert torch.equal(keep_idx[i, :kc[i]].cpu().long(), ref)
+        kb, ks = b[ref], scores_pad[i, :len(b)][ref]
+        shifted = kb + torch.tensor([rois[i, 0], rois[i, 1], rois[i, 0], rois[i, 1]])
+        flips += len(kb) - len(torchvision.ops.nms(shifted, ks, thr))
+        kept_tiles.append((shifted, ks))
+    assert flips > 0, "the construction must contain pairs that only the slide-level NMS suppresses"
+    allb = torch.cat([t[0] for t in kept_tiles])
+    alls = torch.cat([t[1] for t in kept_tiles])
+    keep = alls > conf
+    idx = torch.nonzero(keep).flatten()
+    kept = idx[torchvision.ops.nms(allb[idx], alls[idx], thr)]
+    ref_state = torch.full((len(alls),), 2, dtype=torch.uint8)
+    ref_state[~keep] = 3
+    ref_state[kept] = 1
+    batch = DetectBatch(keep_box, None, keep_score, torch.zeros((bs, md), dtype=torch.int64, device=dev), None, None,
+                        keep_idx, keep_counts, cand.counts, md, frag[0])
+    acc = hs.SlideAccumulator(int(sum(kc)), dev)
+    acc.append(batch, rois.to(dev))
+    n_rows = acc.count()
+    assert n_rows == len(alls)
+    assert torch.equal(acc.boxes[:n_rows].cpu(), allb)
+    fast = acc.verdicts(conf, thr, interior_shortcut=True)[:n_rows].cpu()
+    full = acc.verdicts(conf, thr, interior_shortcut=False)[:n_rows].cpu()
+    assert torch.equal(full, ref_state)
+    assert torch.equal(fast, ref_state)
+    # the shortcut really skipped most rows: fragile rows are a small minority
+    n_frag = int(sum(int(frag[0][i, :kc[i]].sum()) for i in range(bs)))
+    assert 0 < n_frag < 0.8 * n_rows
