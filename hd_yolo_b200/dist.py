@@ -57,6 +57,25 @@ def shard_tile_rows(rois: torch.Tensor, world: int) -> List[Tuple[int, int]]:
     return out
 
 
+_SCRATCH = None
+
+
+def _scratch():
+    global _SCRATCH
+    if _SCRATCH is None:
+        from .ops import _Scratch
+        _SCRATCH = _Scratch()
+    return _SCRATCH
+
+
+def _scratch_rows(dev, name: str, n: int, cols: int, dtype) -> torch.Tensor:
+    """[n, cols] (or [n]) view of a grow-only scratch buffer."""
+    esz = torch.empty((), dtype=dtype).element_size()
+    buf = _scratch().get(dev, name, max(n, 1) * max(cols, 1) * esz)
+    t = buf[:max(n, 1) * max(cols, 1) * esz].view(dtype)
+    return t.view(max(n, 1), cols) if cols > 1 else t
+
+
 # ------------------------------------------------------------------------------------------------ device backend
 class DeviceMergeBackend:
     """The C-ABI merge steps (hdy_merge_build / rounds / export_states / import_states / finish) over one rank's rows.
@@ -64,7 +83,7 @@ class DeviceMergeBackend:
     replicas."""
 
     def __init__(self, boxes, scores, gidx, n_local: int, conf_thres: float, iou_thres: float, tile_id=None,
-                 cores=None, margin=None, dirty=None):
+                 cores=None, margin=None, dirty=None, slot: int = 0):
         import ctypes as C
 
         from . import _lib
@@ -82,11 +101,13 @@ class DeviceMergeBackend:
         self.scores = scores.contiguous()
         self.gidx = gidx.contiguous()
         self.iou = _iou_thr_f32(iou_thres)
-        self.state = torch.empty((max(self.n, 1),), dtype=torch.uint8, device=dev)
         self.status = torch.zeros((1,), dtype=torch.int32, device=dev)
         lib = _lib.load()
         self.wbytes = lib.hdy_merge_workspace_bytes(max(self.n, 1))
-        self.ws = torch.empty((self.wbytes,), dtype=torch.uint8, device=dev)
+        # grow-only scratch (hundreds of MB per slide): a fresh torch.empty per merge churns the caching allocator
+        # (`slot` keeps the ranks apart when several are emulated inside one process)
+        self.state = _scratch().get(dev, f"dist_state{slot}", max(self.n, 1))[:max(self.n, 1)]
+        self.ws = _scratch().get(dev, f"dist_ws{slot}", self.wbytes)
         if cores is not None:
             # interior shortcut (see SlideAccumulator.verdicts): rows beyond n_local are replicas and never take it
             tid = torch.full((max(self.n, 1),), -1, dtype=torch.int32, device=dev)
@@ -188,9 +209,14 @@ class ShardedMerge:
         rep = torch.cat(others) if others else torch.empty((0, 6), dtype=torch.int32, device=dev)
         self.n_rep = int(rep.shape[0])
         n = self.n_local + self.n_rep
-        boxes = torch.empty((max(n, 1), 4), dtype=torch.float32, device=dev)
-        scores = torch.empty((max(n, 1),), dtype=torch.float32, device=dev)
-        gidx = torch.empty((max(n, 1),), dtype=torch.int32, device=dev)
+        if dev.type == "cuda":
+            boxes = _scratch_rows(dev, f"dist_boxes{self.rank}", n, 4, torch.float32)
+            scores = _scratch_rows(dev, f"dist_scores{self.rank}", n, 1, torch.float32)
+            gidx = _scratch_rows(dev, f"dist_gidx{self.rank}", n, 1, torch.int32)
+        else:   # CPU stand-in backend (tests)
+            boxes = torch.empty((max(n, 1), 4), dtype=torch.float32, device=dev)
+            scores = torch.empty((max(n, 1),), dtype=torch.float32, device=dev)
+            gidx = torch.empty((max(n, 1),), dtype=torch.int32, device=dev)
         boxes[:self.n_local] = self.boxes
         scores[:self.n_local] = self.scores
         g = torch.arange(self.n_local, device=dev, dtype=torch.int64) + self.base
@@ -199,9 +225,9 @@ class ShardedMerge:
             boxes[self.n_local:n] = rep[:, :4].contiguous().view(torch.float32)
             scores[self.n_local:n] = rep[:, 4].contiguous().view(torch.float32)
             gidx[self.n_local:n] = rep[:, 5]
-        kw = {}
+        kw = {'slot': self.rank}
         if self.cores is not None:
-            kw = dict(tile_id=self.tile_id, cores=self.cores, dirty=self.dirty,
+            kw = dict(tile_id=self.tile_id, cores=self.cores, dirty=self.dirty, slot=self.rank,
                       margin=torch.tensor([self.margin_all], dtype=torch.float32, device=dev))
         self.backend = self.backend_cls(boxes[:n], scores[:n], gidx[:n], self.n_local, self.conf, self.iou, **kw)
         self.round = 0
