@@ -40,7 +40,8 @@ WORKLOADS = {
     # BASELINE.json configs[2]: 1024x1024 dense-nuclei tiles, batch 128, ~3k candidates/tile
     "tiles1024": dict(tile=1024, bs=128, n_cand=3000, conf=0.25, iou=0.45, max_det=3000, nc=4, cap=4096),
     # BASELINE.json configs[3]: whole slide, 1024-px tiles, 64-px overlap, ~3k candidates/tile
-    "slide": dict(tile=1024, bs=128, n_cand=3000, conf=0.25, iou=0.45, max_det=4096, nc=4, cap=4096, overlap=64),
+    # (148 tiles per batch: the per-tile NMS runs one CTA per tile, one per SM)
+    "slide": dict(tile=1024, bs=148, n_cand=3000, conf=0.25, iou=0.45, max_det=4096, nc=4, cap=4096, overlap=64),
 }
 NM = 32            # prototypes
 L2_BYTES = 126e6
