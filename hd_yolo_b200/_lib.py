@@ -37,6 +37,12 @@ class Level(C.Structure):
     ]
 
 
+class FeatureLevel(C.Structure):
+    """hdy_feature_level_t"""
+
+    _fields_ = [("data", C.c_void_p), ("h", C.c_int32), ("w", C.c_int32), ("spatial_scale", C.c_float)]
+
+
 _vp, _i, _f, _sz, _i64 = C.c_void_p, C.c_int, C.c_float, C.c_size_t, C.c_int64
 _LP = C.POINTER(Level)
 
@@ -99,6 +105,9 @@ SIGNATURES = {
                                   _vp, _vp, _vp]),
     "hdy_regroup_kept": (_i, [_vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _vp, _vp, _vp, _vp, _vp, _vp]),
     "hdy_merge_gather": (_i, [_vp, _vp, _i64, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
+    "hdy_multiscale_roi_align": (_i, [C.POINTER(FeatureLevel), _i, _i, _i, _vp, _vp, _i64, _i, _i, _i, _vp, _vp]),
+    "hdy_match_pairs": (_i, [_vp, _vp, _vp, _i, _i, _vp, _vp, _i, _f, _i, _vp, _vp, _vp, _vp, _vp]),
+    "hdy_box_iou": (_i, [_vp, _i64, _vp, _i64, _vp, _vp]),
 }
 
 _lock = threading.Lock()

@@ -1,0 +1,105 @@
+"""RoIAlign in front of the reference's mask head: host mirror of
+``Detect.multiscale_roi_align`` (metayolo/models/yolo_head.py:279-299) and of the
+``torchvision.ops.roi_align`` call it makes per level, over ``hdy_multiscale_roi_align``.
+
+One launch covers every level (the level id routes each RoI to its feature map); the reference
+loops over levels with ``torch.where(levels == i)`` and scatters into a zero tensor.  fp32, the
+CPU op's operation order (bit-identical on finite inputs); CUDA tensors only.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from typing import List, Optional, Sequence, Union
+
+import torch
+
+from . import _lib
+from ._lib import HdyError, ptr
+from .ops import DetectBatch, _call, _need_cuda, _stream
+
+__all__ = ["multiscale_roi_align", "roi_align", "batch_rois"]
+
+
+def _levels(features: Sequence[torch.Tensor], scales: Sequence[float]):
+    if len(features) != len(scales):
+        raise HdyError("one spatial scale per feature level")
+    if not 1 <= len(features) <= _lib.HDY_MAX_LEVELS:
+        raise HdyError(f"1..{_lib.HDY_MAX_LEVELS} feature levels")
+    arr = (_lib.FeatureLevel * len(features))()
+    bs, ch = None, None
+    for i, f in enumerate(features):
+        _need_cuda(f, f"features[{i}]")
+        if f.dim() != 4 or not f.is_contiguous():
+            raise HdyError(f"features[{i}] must be a contiguous [bs, C, h, w] tensor")
+        if bs is None:
+            bs, ch = int(f.shape[0]), int(f.shape[1])
+        elif (bs, ch) != (int(f.shape[0]), int(f.shape[1])):
+            raise HdyError("feature levels disagree on batch size / channels")
+        arr[i].data = f.data_ptr()
+        arr[i].h, arr[i].w = int(f.shape[2]), int(f.shape[3])
+        arr[i].spatial_scale = float(scales[i])
+    return arr, bs, ch
+
+
+def multiscale_roi_align(features: List[torch.Tensor], boxes: torch.Tensor, levels: Optional[torch.Tensor],
+                         strides: Sequence[float], output_size: int = 14, sampling_ratio: int = 2,
+                         aligned: bool = False) -> torch.Tensor:
+    """Detect.multiscale_roi_align (yolo_head.py:279-299).
+
+    features: one [bs, C, h_i, w_i] tensor per level; boxes [K, 5] = (image index, x1, y1, x2, y2); levels [K] float
+    level ids (the 'extra'[:, 0] column of nms_per_image); strides: buffer.stride per level (spatial_scale =
+    1/stride, :295).  Returns [K, C, M, M] with M = output_size (the reference passes mask_output_size // 2); rows
+    whose level id matches no level stay zero."""
+    scales = [1.0 / float(s) for s in strides]
+    arr, bs, ch = _levels(features, scales)
+    _need_cuda(boxes, "boxes")
+    if boxes.dim() != 2 or boxes.shape[1] != 5:
+        raise HdyError("boxes must be [K, 5] (image index, x1, y1, x2, y2)")
+    K = int(boxes.shape[0])
+    M = int(output_size)
+    out = torch.empty((K, ch, M, M), dtype=torch.float32, device=boxes.device)
+    if K == 0:
+        return out
+    boxes = boxes.contiguous()
+    lv = None
+    if levels is not None:
+        _need_cuda(levels, "levels")
+        if levels.shape != (K,):
+            raise HdyError("levels must be [K]")
+        lv = levels.contiguous()
+    elif len(features) > 1:
+        raise HdyError("levels is required with more than one feature level")
+    _call("hdy_multiscale_roi_align", arr, len(features), bs, ch, ptr(boxes), ptr(lv), K, M, int(sampling_ratio),
+          int(bool(aligned)), ptr(out), _stream())
+    return out
+
+
+def roi_align(input: torch.Tensor, boxes: Union[torch.Tensor, List[torch.Tensor]], output_size, spatial_scale: float = 1.0,
+              sampling_ratio: int = 2, aligned: bool = False) -> torch.Tensor:
+    """torchvision.ops.roi_align as the reference calls it (yolo_head.py:243, :294): Tensor[K, 5] boxes or a list of
+    per-image Tensor[k_i, 4]; square output; sampling_ratio >= 1."""
+    if isinstance(output_size, (tuple, list)):
+        if len(output_size) != 2 or output_size[0] != output_size[1]:
+            raise HdyError("only square outputs are on the reference's path")
+        output_size = output_size[0]
+    if isinstance(boxes, (list, tuple)):
+        boxes = torch.cat([torch.nn.functional.pad(b, [1, 0], value=float(i)) for i, b in enumerate(boxes)])
+    return multiscale_roi_align([input], boxes, None, [1.0 / float(spatial_scale)], int(output_size), sampling_ratio,
+                                aligned)
+
+
+def batch_rois(batch: DetectBatch, counts_host: Optional[Sequence[int]] = None):
+    """The `proposals` / `levels` pair Detect.compute_outputs builds (yolo_head.py:320-328) from a DetectBatch:
+    ([K, 5] image-index-padded boxes, [K] level ids), detections of image 0 first.  One D2H read of the counts unless
+    they are given."""
+    if counts_host is None:
+        counts_host = batch.counts.cpu().tolist()
+    rows, lv = [], []
+    for i, k in enumerate(counts_host):
+        if k:
+            rows.append(torch.nn.functional.pad(batch.boxes[i, :k], [1, 0], value=float(i)))
+            lv.append(batch.levels[i, :k])
+    dev = batch.boxes.device
+    if not rows:
+        return torch.zeros((0, 5), dtype=torch.float32, device=dev), torch.zeros((0,), dtype=torch.float32, device=dev)
+    return torch.cat(rows), torch.cat(lv)

@@ -377,6 +377,41 @@ HDY_API int hdy_regroup_kept(const int32_t* keep_idx, const float* keep_box, con
                              int cap, uint64_t* cand_keys, float* cand_boxes, float* cand_cls, int32_t* counts,
                              int32_t* status, hdy_stream_t stream);
 
+/* ------------------------------------------------- next rows: RoIAlign in front of the mask head */
+
+/* One pyramid level of mask features (the `features` list of Detect.compute_outputs, yolo_head.py:301, after the
+ * `seg` convs): [bs, channels, h, w] fp32, spatial_scale = 1 / stride. */
+typedef struct {
+  const float* data;
+  int32_t h, w;
+  float spatial_scale;
+} hdy_feature_level_t;
+
+/* f1: Detect.multiscale_roi_align (yolo_head.py:279-299) = torchvision.ops.roi_align per level + scatter, in one
+ * launch.  rois [K, 5] = (batch index, x1, y1, x2, y2) in image pixels; level_of [K] = the level id column nms_per_image
+ * carries in 'extra' (float; NULL with nl == 1: plain roi_align); out [K, channels, pooled, pooled].  RoIs whose level
+ * id is not an integer in [0, nl) stay zero, as rows of the reference's zero-initialised `result` do.
+ * sampling_ratio in [1, 4] (reference: 2), pooled in [1, 16] (reference: mask_output_size // 2 = 14), aligned as in
+ * torchvision (reference: False).  fp32, torchvision's CPU operation order, no FMA contraction. */
+HDY_API int hdy_multiscale_roi_align(const hdy_feature_level_t* levels_host, int nl, int bs, int channels,
+                                     const float* rois, const float* level_of, int64_t K, int pooled,
+                                     int sampling_ratio, int aligned, float* out, hdy_stream_t stream);
+
+/* f2: the matching step of APMeter.add (metayolo/models/metrics.py:270-303) without the dense k x g matrix.
+ *   pred_boxes [bs, P, 4], pred_order [bs, P] i32 (rank in score order -> row; NULL: rows are already in order),
+ *   pred_counts [bs], gt_boxes [bs, G, 4], gt_counts [bs]; every pair with box_iou >= iou_min (utils_general.py:
+ *   247-265 arithmetic) is appended to image i's list: pair_keys [bs, cap] = ~orderable(iou) << 32 | (rank * g_i + j),
+ *   pair_boxes [bs, cap, 4] (the prediction's box), counts [bs] (zeroed by the caller; holds the needed size on
+ *   overflow, *status gets HDY_STATUS_OVERFLOW).  Sorting a list ascending (hdy_nms_tiles with iou_thres = 2) yields
+ *   `sort(ious[where(ious >= iou_min)], descending=True)` with ties in row-major order.  P * G < 2^32. */
+HDY_API int hdy_match_pairs(const float* pred_boxes, const int32_t* pred_order, const int32_t* pred_counts, int bs,
+                            int P, const float* gt_boxes, const int32_t* gt_counts, int G, float iou_min, int cap,
+                            uint64_t* pair_keys, float* pair_boxes, int32_t* counts, int32_t* status,
+                            hdy_stream_t stream);
+
+/* box_iou (metayolo/models/utils_general.py:247-265): out [n, m] fp32, 0/0 = NaN as in the reference. */
+HDY_API int hdy_box_iou(const float* box1, int64_t n, const float* box2, int64_t m, float* out, hdy_stream_t stream);
+
 /* Utility: zero n int32 words (keeps the host mirror free of extra torch launches). */
 HDY_API int hdy_zero_i32(int32_t* p, size_t n, hdy_stream_t stream);
 

@@ -172,6 +172,61 @@ def make_paste(ref, name, seed):
     _save(name, masks=_np(masks), boxes=_np(boxes), shape=np.array([H, W]), out=_np(out))
 
 
+def make_roi(ref, name, seed):
+    """Detect.multiscale_roi_align (yolo_head.py:279-299) on random features of a 3-level pyramid."""
+    g = torch.Generator().manual_seed(seed)
+    det = ref.Detect(ch=[8, 8, 8], anchors=synth.ANCHORS_3, strides=synth.STRIDES_3, nc=4, masks={}, is_scripting=True)
+    tile, C, K = 160, 6, 28
+    feats = [torch.randn((2, C, tile // s, tile // s), generator=g) for s in synth.STRIDES_3]
+    c = torch.rand((K, 2), generator=g) * tile
+    s = torch.rand((K, 2), generator=g) * 40 + 4
+    b = torch.cat([c - s / 2, c + s / 2], 1)
+    b[0] = torch.tensor([-30.0, -20.0, 12.5, 9.0])          # sticks out top-left
+    b[1] = torch.tensor([150.0, 140.0, 200.0, 190.0])       # sticks out bottom-right
+    b[2] = torch.tensor([300.0, 300.0, 340.0, 340.0])       # fully outside: every sample out of range
+    b[3] = torch.tensor([40.2, 50.1, 40.4, 50.3])           # sub-pixel box (roi size clamps to 1)
+    b[4] = torch.tensor([-5.0, -5.0, 165.0, 165.0])         # whole image and more
+    boxes = torch.cat([torch.randint(0, 2, (K, 1), generator=g).float(), b], 1)
+    levels = torch.randint(0, 3, (K,), generator=g).float()
+    levels[5] = 3.0                                          # no such level: row stays zero
+    out = det.multiscale_roi_align(feats, boxes, levels)
+    arrays = {"boxes": _np(boxes), "levels": _np(levels), "out": _np(out),
+              "strides": np.array(synth.STRIDES_3, dtype=np.float32)}
+    for i, f in enumerate(feats):
+        arrays[f"feat{i}"] = _np(f)
+    _save(name, **arrays)
+
+
+def make_match(ref, name, seed):
+    """APMeter.add (metrics.py:270-303) over three images (one without predictions, one without ground truth)."""
+    g = torch.Generator().manual_seed(seed)
+    meter = ref.APMeter()
+    arrays = {}
+    for i, (k, n_gt) in enumerate([(60, 50), (0, 7), (25, 0), (80, 90)]):
+        gc = torch.rand((n_gt, 2), generator=g) * 200
+        gs = torch.rand((n_gt, 2), generator=g) * 24 + 10
+        gt = torch.cat([gc - gs / 2, gc + gs / 2], 1)
+        m = min(k, n_gt)
+        # predictions: jittered copies of some ground-truth boxes + false positives
+        pb = torch.cat([gt[:m] + torch.randn((m, 4), generator=g) * 2.0,
+                        torch.rand((k - m, 4), generator=g) * 100 + torch.tensor([0., 0., 100., 100.])])
+        if m > 2:
+            pb[1] = gt[0]                                     # exact hit on another box's target (iou = 1)
+        pb = pb[torch.randperm(k, generator=g)] if k else pb
+        out = {'boxes': pb, 'scores': torch.rand(k, generator=g), 'labels': torch.randint(-1, 5, (k,), generator=g)}
+        tgt = {'boxes': gt, 'labels': torch.randint(1, 5, (n_gt,), generator=g)}
+        meter.add(out, tgt)
+        for key, v in out.items():
+            arrays[f"out{i}_{key}"] = _np(v)
+        for key, v in tgt.items():
+            arrays[f"tgt{i}_{key}"] = _np(v)
+    arrays["n_images"] = np.int64(4)
+    for f in ("scores", "y_pred", "y_true", "ious", "m_pred", "m_true"):
+        arrays["meter_" + f] = _np(getattr(meter, f))
+    arrays["meter_n"] = np.array([meter.n_pred, meter.n_true, meter.n_match], dtype=np.int64)
+    _save(name, **arrays)
+
+
 def main():
     os.makedirs(OUT, exist_ok=True)
     ref = ref_shim.load()
@@ -181,6 +236,8 @@ def main():
     make_hier(ref, "hier_tree", seed=4)
     make_merge(ref, "tile_merge", seed=5)
     make_paste(ref, "paste_masks", seed=6)
+    make_roi(ref, "roi_align", seed=7)
+    make_match(ref, "ap_match", seed=8)
 
 
 if __name__ == "__main__":

@@ -412,3 +412,68 @@ def roi_postprocess_detections(class_logits, box_regression, proposals, image_sh
 def maskrcnn_inference(x: torch.Tensor, labels: List[torch.Tensor]) -> List[torch.Tensor]:
     from torchvision.models.detection.roi_heads import maskrcnn_inference as f
     return f(x, labels)
+
+
+# ------------------------------------------------------------------- next rows: RoIAlign, AP matching
+def multiscale_roi_align(features: List[torch.Tensor], boxes: torch.Tensor, levels: torch.Tensor,
+                         strides: Sequence[float], output_size: int = 14, sampling_ratio: int = 2,
+                         aligned: bool = False) -> torch.Tensor:
+    """Detect.multiscale_roi_align (metayolo/models/yolo_head.py:279-299): per level, torchvision.ops.roi_align of the
+    boxes routed to it (spatial_scale = 1/stride, sampling_ratio = 2, aligned = ROI_ALIGN = False, :15), scattered
+    into a zero [K, C, M, M] tensor.  boxes [K, 5] = (image index, xyxy)."""
+    K, C, M = len(boxes), features[0].shape[1], output_size
+    result = torch.zeros((K, C, M, M), dtype=features[0].dtype)
+    for i, stride in enumerate(strides):
+        idx = torch.where(levels == i)[0]
+        fmap = torchvision.ops.roi_align(features[i], boxes[idx], (M, M), spatial_scale=1 / float(stride),
+                                         sampling_ratio=sampling_ratio, aligned=aligned)
+        result[idx] = fmap.to(result.dtype)
+    return result
+
+
+def box_iou(box1: torch.Tensor, box2: torch.Tensor) -> torch.Tensor:
+    """box_iou (metayolo/models/utils_general.py:247-265): inter = clamp(min(a2,b2) - max(a1,b1), 0).prod(2);
+    iou = inter / (area1[:, None] + area2 - inter), area = (x2-x1)*(y2-y1)."""
+    a1, a2 = box1[:, None, :2], box1[:, None, 2:]
+    b1, b2 = box2[:, :2], box2[:, 2:]
+    inter = (torch.min(a2, b2) - torch.max(a1, b1)).clamp(0).prod(2)
+    area1 = (box1[:, 2] - box1[:, 0]) * (box1[:, 3] - box1[:, 1])
+    area2 = (box2[:, 2] - box2[:, 0]) * (box2[:, 3] - box2[:, 1])
+    return inter / (area1[:, None] + area2 - inter)
+
+
+def apmeter_match(output: Dict[str, torch.Tensor], target: Dict[str, torch.Tensor], iou_min: float = 0.5):
+    """The matching half of APMeter.add (metayolo/models/metrics.py:271-284): predictions by score (descending), dense
+    box_iou against the ground truth, pairs with iou >= iouv.min() sorted by IoU (descending).  Returns o_scores,
+    o_labels, pred_idx (rank in score order), true_idx, ious.  Ties: both sorts are stable here (the reference calls
+    torch.sort without `stable`, whose CPU kernel is stable)."""
+    o_scores, order = torch.sort(output['scores'], descending=True, stable=True)
+    o_labels = output['labels'][order]
+    ious = box_iou(output['boxes'][order], target['boxes'])
+    pred_idx, true_idx = torch.where(ious >= iou_min)
+    ious, o2 = torch.sort(ious[pred_idx, true_idx], descending=True, stable=True)
+    return o_scores, o_labels, pred_idx[o2], true_idx[o2], ious
+
+
+class APMeterState:
+    """Accumulator fields of APMeter (metrics.py:250-303) filled through apmeter_match."""
+
+    def __init__(self):
+        self.n_pred = self.n_true = self.n_match = 0
+        self.scores, self.ious = torch.empty(0), torch.empty(0)
+        self.y_pred = torch.empty(0, dtype=torch.int64)
+        self.y_true = torch.empty(0, dtype=torch.int64)
+        self.m_pred = torch.empty(0, dtype=torch.int64)
+        self.m_true = torch.empty(0, dtype=torch.int64)
+
+    def add(self, output, target, iou_min: float = 0.5):
+        s, l, p, t, i = apmeter_match(output, target, iou_min)
+        self.m_pred = torch.cat([self.m_pred, p + self.n_pred])
+        self.m_true = torch.cat([self.m_true, t + self.n_true])
+        self.ious = torch.cat([self.ious, i])
+        self.n_match += len(i)
+        self.y_true = torch.cat([self.y_true, target['labels']])
+        self.n_true += len(target['boxes'])
+        self.y_pred = torch.cat([self.y_pred, l])
+        self.scores = torch.cat([self.scores, s])
+        self.n_pred += len(output['boxes'])

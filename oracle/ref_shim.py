@@ -38,6 +38,12 @@ def load():
         sys.modules["torch_scatter"] = ts
         if REF_ROOT not in sys.path:
             sys.path.insert(0, REF_ROOT)
+        try:  # metayolo/models/metrics.py:11 imports pyplot at module level (plots only)
+            import matplotlib.pyplot  # noqa: F401
+        except Exception:
+            mpl = types.ModuleType("matplotlib")
+            mpl.pyplot = types.ModuleType("matplotlib.pyplot")
+            sys.modules["matplotlib"], sys.modules["matplotlib.pyplot"] = mpl, mpl.pyplot
     import warnings
 
     warnings.filterwarnings("ignore", message="torch.meshgrid")
@@ -45,12 +51,13 @@ def load():
     from metayolo.models.yolo import Ensemble
     from metayolo.models.yolo_head import Detect
     import hnet.utils as hu
+    from metayolo.models.metrics import APMeter
     from torchvision.models.detection.roi_heads import paste_masks_in_image
 
     ns = types.SimpleNamespace(
         nms_per_image=ug.nms_per_image, non_max_suppression=ug.non_max_suppression, xywh2xyxy=ug.xywh2xyxy,
         box_iou=ug.box_iou, scale_coords=ug.scale_coords, Detect=Detect, Ensemble=Ensemble,
         sliding_window_scanner=hu.sliding_window_scanner, split_by_sizes=hu.split_by_sizes,
-        paste_masks_in_image=paste_masks_in_image,
+        paste_masks_in_image=paste_masks_in_image, APMeter=APMeter,
     )
     return ns

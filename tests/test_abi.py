@@ -89,3 +89,21 @@ def test_iou_threshold_rounding_modes():
     ops.set_iou_compare("cuda")
     assert ops._iou_thr_f32(0.3) == float(np.float32(0.3))
     ops.set_iou_compare("cpu")
+
+
+def test_next_rows_reject_cpu_tensors_and_bad_arguments():
+    with pytest.raises(hdy.HdyError):
+        hdy.multiscale_roi_align([torch.zeros(1, 4, 8, 8)], torch.zeros(1, 5), None, [8])
+    with pytest.raises(hdy.HdyError):
+        hdy.box_iou(torch.zeros(2, 4), torch.zeros(3, 4))
+    with pytest.raises(hdy.HdyError):
+        hdy.match_predictions({'boxes': torch.zeros(1, 4), 'scores': torch.zeros(1), 'labels': torch.zeros(1)},
+                              {'boxes': torch.zeros(1, 4), 'labels': torch.zeros(1)})
+    lib = _lib.load()
+    lv = (_lib.FeatureLevel * 1)()
+    # sampling_ratio <= 0 (torchvision's adaptive grid) is not on the reference's path: rejected before any launch
+    assert lib.hdy_multiscale_roi_align(lv, 1, 1, 4, None, None, 1, 14, 0, 0, None, None) == -1
+    assert b"sampling_ratio" in lib.hdy_last_error()
+    assert lib.hdy_multiscale_roi_align(lv, 1, 1, 4, None, None, 1, 17, 2, 0, None, None) == -1
+    assert lib.hdy_match_pairs(None, None, None, 1, 70000, None, None, 70000, 0.5, 16, None, None, None, None,
+                               None) == -1

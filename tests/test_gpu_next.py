@@ -1,0 +1,151 @@
+"""GPU parity tests of the rows SURVEY 8f ranks next: multi-scale RoIAlign (the gather in front of the reference's
+mask head) and the prediction/ground-truth matching of APMeter.add.  Oracle: oracle/port.py + oracle/roi_align_core.c,
+pinned on reference-generated goldens (tests/golden/roi_align.npz, ap_match.npz)."""
+import numpy as np
+import pytest
+import torch
+
+from conftest import load_golden
+import hd_yolo_b200 as hdy
+from hd_yolo_b200 import synth
+from oracle import port, roi_align_c
+
+pytestmark = pytest.mark.gpu
+
+
+# ------------------------------------------------------------------------------------------------ RoIAlign
+def test_roi_align_golden_bit_exact(cuda_device):
+    g = load_golden("roi_align")
+    feats = [torch.from_numpy(g[f"feat{i}"]).to(cuda_device) for i in range(3)]
+    boxes, levels = torch.from_numpy(g["boxes"]).to(cuda_device), torch.from_numpy(g["levels"]).to(cuda_device)
+    out = hdy.multiscale_roi_align(feats, boxes, levels, g["strides"].tolist()).cpu()
+    ref = torch.from_numpy(g["out"])
+    assert out.shape == ref.shape
+    assert torch.equal(out, ref), f"max abs diff {(out - ref).abs().max().item()}"
+    assert float(out[5].abs().max()) == 0.0          # level id 3: the zero row of the reference's `result`
+
+
+def _rois(gen, K, bs, tile, lo, hi):
+    c = torch.rand((K, 2), generator=gen) * tile
+    s = torch.rand((K, 2), generator=gen) * (hi - lo) + lo
+    return torch.cat([torch.randint(0, bs, (K, 1), generator=gen).float(), c - s / 2, c + s / 2], 1)
+
+
+@pytest.mark.parametrize("C,M,S,aligned,lo,hi", [
+    (40, 14, 2, False, 8, 48),      # the reference's call; ragged channel chunk (32 + 8)
+    (37, 14, 2, False, 8, 48),      # odd channel count: ragged pair
+    (8, 14, 2, False, 100, 500),    # windows too large to stage: in-place path
+    (33, 7, 2, True, 4, 64),
+    (16, 14, 1, False, 4, 64),
+    (6, 5, 3, False, 4, 200),
+    (5, 16, 4, True, 2, 90),
+])
+def test_roi_align_matches_oracle(cuda_device, C, M, S, aligned, lo, hi):
+    gen = torch.Generator().manual_seed(C * 100 + M)
+    tile, bs, K = 320, 3, 300
+    strides = [8, 16, 32]
+    feats = [torch.randn((bs, C, tile // s, tile // s), generator=gen) for s in strides]
+    rois = _rois(gen, K, bs, tile, lo, hi)
+    rois[0, 1:] = torch.tensor([-40., -40., -20., -20.])           # outside
+    rois[1, 1:] = torch.tensor([tile - 3., tile - 3., tile + 30., tile + 30.])
+    levels = torch.randint(0, 3, (K,), generator=gen).float()
+    levels[2], levels[3] = -1.0, 0.5                                # match no level
+    out = hdy.multiscale_roi_align([f.to(cuda_device) for f in feats], rois.to(cuda_device), levels.to(cuda_device),
+                                   strides, M, S, aligned).cpu().numpy()
+    ref = np.zeros_like(out)
+    for i, s in enumerate(strides):
+        idx = np.where(levels.numpy() == i)[0]
+        ref[idx] = roi_align_c.roi_align(feats[i].numpy(), rois.numpy()[idx], M, 1.0 / s, S, aligned)
+    assert np.array_equal(out, ref), f"max abs diff {np.abs(out - ref).max()}"
+    # and the oracle itself is torchvision's op (float tolerance as stated by north_star: 1e-5 relative)
+    tv = port.multiscale_roi_align(feats, rois, levels, strides, M, S, aligned).numpy()
+    assert np.allclose(out, tv, rtol=1e-5, atol=1e-6)
+
+
+def test_roi_align_single_level_and_list_boxes(cuda_device):
+    import torchvision
+    gen = torch.Generator().manual_seed(5)
+    f = torch.randn((2, 12, 40, 40), generator=gen)
+    per_image = [_rois(gen, 17, 1, 320, 8, 60)[:, 1:], _rois(gen, 9, 1, 320, 8, 60)[:, 1:]]
+    out = hdy.roi_align(f.to(cuda_device), [b.to(cuda_device) for b in per_image], (14, 14), 1 / 8, 2, False).cpu()
+    ref = torchvision.ops.roi_align(f, per_image, (14, 14), 1 / 8, 2, False)
+    assert torch.equal(out, ref)
+    empty = hdy.roi_align(f.to(cuda_device), torch.zeros((0, 5), device=cuda_device), 14, 1 / 8)
+    assert empty.shape == (0, 12, 14, 14)
+
+
+def test_roi_align_after_detect_postprocess(cuda_device):
+    """compute_outputs' mask front half (yolo_head.py:320-330): proposals + level ids of a DetectBatch -> features."""
+    spec = hdy.HeadSpec(synth.ANCHORS_3, synth.STRIDES_3, nc=4)
+    dets = synth.nuclei_logits(2, 320, 4, 200, seed=9, conf=0.25)
+    out = hdy.detect_postprocess([d.to(cuda_device) for d in dets], spec, 0.25, 0.45, 300)
+    rois, lv = hdy.batch_rois(out)
+    gen = torch.Generator().manual_seed(3)
+    feats = [torch.randn((2, 16, 320 // s, 320 // s), generator=gen) for s in synth.STRIDES_3]
+    got = hdy.multiscale_roi_align([f.to(cuda_device) for f in feats], rois, lv, synth.STRIDES_3).cpu()
+    ref = port.multiscale_roi_align(feats, rois.cpu(), lv.cpu(), synth.STRIDES_3)
+    assert len(rois) == int(out.counts.sum()) and len(rois) > 100
+    assert torch.equal(got, ref)
+
+
+# ------------------------------------------------------------------------------------------------ matching
+def _meter_inputs(g, i):
+    out = {k: torch.from_numpy(g[f"out{i}_{k}"]) for k in ("boxes", "scores", "labels")}
+    tgt = {k: torch.from_numpy(g[f"tgt{i}_{k}"]) for k in ("boxes", "labels")}
+    return out, tgt
+
+
+def test_apmeter_golden(cuda_device):
+    g = load_golden("ap_match")
+    meter = hdy.APMeter()
+    for i in range(int(g["n_images"])):
+        out, tgt = _meter_inputs(g, i)
+        meter.add({k: v.to(cuda_device) for k, v in out.items()}, {k: v.to(cuda_device) for k, v in tgt.items()})
+    assert [meter.n_pred, meter.n_true, meter.n_match] == g["meter_n"].tolist()
+    for f in ("scores", "y_pred", "y_true", "ious", "m_pred", "m_true"):
+        assert torch.equal(getattr(meter, f), torch.from_numpy(g["meter_" + f])), f
+
+
+def test_box_iou_matches_oracle(cuda_device):
+    gen = torch.Generator().manual_seed(2)
+    a = _rois(gen, 700, 1, 300, 5, 60)[:, 1:].contiguous()
+    b = _rois(gen, 450, 1, 300, 5, 60)[:, 1:].contiguous()
+    a[3] = torch.tensor([5., 5., 5., 5.])
+    b[7] = torch.tensor([5., 5., 5., 5.])          # 0/0 -> NaN in both
+    got = hdy.box_iou(a.to(cuda_device), b.to(cuda_device)).cpu()
+    ref = port.box_iou(a, b)
+    assert torch.equal(torch.isnan(got), torch.isnan(ref)) and bool(torch.isnan(got[3, 7]))
+    assert torch.equal(torch.nan_to_num(got, nan=-1.0), torch.nan_to_num(ref, nan=-1.0))
+    assert hdy.box_iou(a[:0].to(cuda_device), b.to(cuda_device)).shape == (0, 450)
+
+
+@pytest.mark.parametrize("k,n_gt,seed", [(1500, 1400, 1), (5000, 300, 2), (40, 4500, 3)])
+def test_match_predictions_matches_oracle(cuda_device, k, n_gt, seed):
+    gen = torch.Generator().manual_seed(seed)
+    gt = _rois(gen, n_gt, 1, 1024, 12, 36)[:, 1:].contiguous()
+    m = min(k, n_gt)
+    pb = torch.cat([gt[:m] + torch.randn((m, 4), generator=gen) * 1.5, _rois(gen, k - m, 1, 1024, 12, 36)[:, 1:]])
+    pb = pb[torch.randperm(k, generator=gen)].contiguous()
+    scores = (torch.rand(k, generator=gen) * 256).round() / 256          # score ties: lower row first
+    out = {'boxes': pb, 'scores': scores, 'labels': torch.randint(-1, 5, (k,), generator=gen)}
+    tgt = {'boxes': gt, 'labels': torch.randint(1, 5, (n_gt,), generator=gen)}
+    got = hdy.match_predictions({a: b.to(cuda_device) for a, b in out.items()},
+                                {a: b.to(cuda_device) for a, b in tgt.items()}, 0.5)
+    s, l, p, t, i = port.apmeter_match(out, tgt, 0.5)
+    assert len(i) > m // 4
+    assert torch.equal(got['scores'].cpu(), s) and torch.equal(got['labels'].cpu(), l)
+    assert torch.equal(got['ious'].cpu(), i)
+    assert torch.equal(got['pred_idx'].cpu(), p) and torch.equal(got['true_idx'].cpu(), t)
+
+
+def test_match_predictions_ties_and_capacity(cuda_device):
+    # every prediction is an exact copy of every ground-truth box: k*g pairs of iou 1, more than the default capacity
+    box = torch.tensor([[10., 10., 40., 40.]])
+    k, n_gt = 70, 60
+    out = {'boxes': box.repeat(k, 1), 'scores': torch.linspace(0.9, 0.1, k), 'labels': torch.ones(k, dtype=torch.int64)}
+    tgt = {'boxes': box.repeat(n_gt, 1), 'labels': torch.ones(n_gt, dtype=torch.int64)}
+    got = hdy.match_predictions({a: b.to(cuda_device) for a, b in out.items()},
+                                {a: b.to(cuda_device) for a, b in tgt.items()}, 0.5, cap=64)
+    assert len(got['ious']) == k * n_gt and bool((got['ious'] == 1.0).all())
+    idx = torch.arange(k * n_gt)
+    assert torch.equal(got['pred_idx'].cpu(), idx // n_gt) and torch.equal(got['true_idx'].cpu(), idx % n_gt)

@@ -178,3 +178,58 @@ def test_flatten_onehot_objects_matches_reference_formulation():
     assert torch.equal(got['boxes'], torch.repeat_interleave(x['boxes'], nc1, 0)[keep])
     assert torch.equal(got['scores'], x['scores'].flatten()[keep])
     assert torch.equal(got['masks'], torch.repeat_interleave(x['masks'], nc1, 0)[keep])
+
+
+# ------------------------------------------------------------------------ next rows: RoIAlign, AP matching
+def _roi_golden():
+    g = load_golden("roi_align")
+    feats = [torch.from_numpy(g[f"feat{i}"]) for i in range(3)]
+    return g, feats, torch.from_numpy(g["boxes"]), torch.from_numpy(g["levels"])
+
+
+def test_multiscale_roi_align_matches_reference():
+    g, feats, boxes, levels = _roi_golden()
+    mine = port.multiscale_roi_align(feats, boxes, levels, g["strides"].tolist())
+    assert torch.equal(mine, torch.from_numpy(g["out"]))
+    assert float(mine[5].abs().max()) == 0.0 and float(mine[2].abs().max()) == 0.0   # no such level / fully outside
+
+
+def test_roi_align_c_restatement_is_bit_exact():
+    """oracle/roi_align_core.c against the golden (reference output) and against torchvision on wider cases."""
+    from oracle import roi_align_c
+    g, feats, boxes, levels = _roi_golden()
+    ref = g["out"]
+    for i, s in enumerate(g["strides"].tolist()):
+        idx = np.where(g["levels"] == i)[0]
+        mine = roi_align_c.roi_align(g[f"feat{i}"], g["boxes"][idx], 14, 1.0 / s)
+        assert np.array_equal(mine, ref[idx])
+    gen = torch.Generator().manual_seed(11)
+    f = torch.randn((2, 3, 9, 13), generator=gen)
+    c = torch.rand((64, 2), generator=gen) * torch.tensor([13 * 8., 9 * 8.])
+    s = torch.rand((64, 2), generator=gen) * 70 + 1
+    rois = torch.cat([torch.randint(0, 2, (64, 1), generator=gen).float(), c - s / 2, c + s / 2], 1)
+    for M, S, aligned in [(14, 2, False), (7, 2, True), (14, 1, False), (5, 3, False), (16, 4, True)]:
+        tv = torchvision.ops.roi_align(f, rois, (M, M), 1 / 8, S, aligned)
+        mine = roi_align_c.roi_align(f.numpy(), rois.numpy(), M, 1 / 8, S, aligned)
+        assert np.array_equal(mine, tv.numpy()), (M, S, aligned)
+
+
+def test_apmeter_matches_reference():
+    g = load_golden("ap_match")
+    st = port.APMeterState()
+    for i in range(int(g["n_images"])):
+        out = {k: torch.from_numpy(g[f"out{i}_{k}"]) for k in ("boxes", "scores", "labels")}
+        tgt = {k: torch.from_numpy(g[f"tgt{i}_{k}"]) for k in ("boxes", "labels")}
+        st.add(out, tgt)
+    assert [st.n_pred, st.n_true, st.n_match] == g["meter_n"].tolist()
+    assert st.n_match > 40
+    for f in ("scores", "y_pred", "y_true", "ious", "m_pred", "m_true"):
+        assert torch.equal(getattr(st, f), torch.from_numpy(g["meter_" + f])), f
+
+
+def test_box_iou_known_answers():
+    a = torch.tensor([[0., 0., 10., 10.], [5., 5., 5., 5.]])
+    b = torch.tensor([[0., 0., 10., 5.], [20., 20., 30., 30.], [5., 5., 5., 5.]])
+    iou = port.box_iou(a, b)
+    assert iou[0, 0] == 0.5 and iou[0, 1] == 0.0
+    assert torch.isnan(iou[1, 2])                  # 0 / 0: never `>= 0.5`
