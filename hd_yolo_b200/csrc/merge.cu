@@ -34,9 +34,12 @@ constexpr int kMaxRounds = 64;
 constexpr float kMergeCellMargin = 1.01f;
 constexpr float kMergeMaxScaled = 1.0e6f;
 
+constexpr int kExtBins = 128;  // 8 bins per octave of max(w, h), 2^-2 .. 2^14 px
 struct MergeStats {
   float ext_sum;
   unsigned ext_cnt;
+  float cell_size;              // picked by merge_pick_cell_kernel
+  unsigned ext_hist[kExtBins];
   int unknown[kMaxRounds + 1];  // unknown[r] = boxes still undecided after round r
   int rounds_run;
 };
@@ -207,19 +210,62 @@ __global__ void append_tiles_kernel(const float4* __restrict__ boxes, const floa
 // ------------------------------------------------------------------------------------------------
 // overhang of boxes over their own tile (slide coordinates)
 // ------------------------------------------------------------------------------------------------
+constexpr int kOverBins = 256;  // 1-px bins of ceil(overhang); the last one also takes everything beyond
+
+__device__ __forceinline__ float box_overhang(const float4& b, const float4& r) {
+  float o = fmaxf(fmaxf(r.x - b.x, r.y - b.y), fmaxf(b.z - r.z, b.w - r.w));
+  if (!(o <= 3.0e38f)) o = 3.0e38f;  // NaN / inf coordinates: nothing is interior
+  return o;
+}
+
+__global__ void overhang_hist_kernel(const float4* __restrict__ boxes, const int32_t* __restrict__ tile_id,
+                                     const float4* __restrict__ tile_rois, const long long* __restrict__ n_dev,
+                                     long long n_max, unsigned* __restrict__ hist) {
+  __shared__ unsigned sh[kOverBins];
+  for (int i = threadIdx.x; i < kOverBins; i += blockDim.x) sh[i] = 0u;
+  __syncthreads();
+  const long long n = n_dev ? min(*n_dev, n_max) : n_max;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+    int t = tile_id[i];
+    if (t < 0) t = ~t;
+    const float o = box_overhang(boxes[i], tile_rois[t]);
+    if (o > 0.f) atomicAdd(&sh[o >= (float)(kOverBins - 1) ? kOverBins - 1 : (int)ceilf(o)], 1u);  // bin 0: inside
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < kOverBins; i += blockDim.x)
+    if (sh[i]) atomicAdd(&hist[i], sh[i]);
+}
+
+// The smallest whole-pixel cap in [min_cap, max_cap] that leaves at most max_far boxes sticking out further.  The
+// margin every core is shrunk by is the largest overhang below the cap, so a handful of big false positives must not
+// set it: at the 100k slide the largest overhang under a fixed 64 px cap is 63 px and 36 % of all rows stay active;
+// nuclei themselves stick out by at most half their size.
+__global__ void overhang_pick_kernel(const unsigned* __restrict__ hist, int max_far, float min_cap, float max_cap,
+                                     float* __restrict__ cap_out) {
+  if (threadIdx.x != 0 || blockIdx.x != 0) return;
+  int hi = (int)fminf(fmaxf(max_cap, 0.f), (float)(kOverBins - 2));
+  int lo = (int)fminf(fmaxf(ceilf(min_cap), 0.f), (float)hi);
+  unsigned long long above = 0;
+  for (int b = kOverBins - 1; b > hi; --b) above += hist[b];
+  int c = hi;
+  while (c > lo && above + hist[c] <= (unsigned long long)max_far) above += hist[c--];
+  *cap_out = (float)c;
+}
+
 __global__ void overhang_kernel(const float4* __restrict__ boxes, const int32_t* __restrict__ tile_id,
                                 const float4* __restrict__ tile_rois, const long long* __restrict__ n_dev,
-                                long long n_max, float far_cap, float* __restrict__ margin,
+                                long long n_max, float far_cap, const float* __restrict__ far_cap_dev,
+                                float* __restrict__ margin,
                                 float4* __restrict__ far_boxes, int32_t* __restrict__ far_tile,
                                 int32_t* __restrict__ far_count, int far_capacity) {
   const long long n = n_dev ? min(*n_dev, n_max) : n_max;
+  if (far_cap_dev) far_cap = *far_cap_dev;
   float m = 0.f;
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
     int t = tile_id[i];
     if (t < 0) t = ~t;  // fragile row: ~tile
     const float4 b = boxes[i], r = tile_rois[t];
-    float o = fmaxf(fmaxf(r.x - b.x, r.y - b.y), fmaxf(b.z - r.z, b.w - r.w));
-    if (!(o <= 3.0e38f)) o = 3.0e38f;  // NaN / inf coordinates: nothing is interior
+    const float o = box_overhang(b, r);
     if (far_count && o > far_cap) {
       // a box that reaches far beyond its tile (a rare, huge false positive) would shrink EVERY core through the
       // margin: list it instead, the tiles it touches lose the shortcut (dirty_tiles_kernel)
@@ -267,6 +313,9 @@ struct MergeWs {
   uint64_t* ckey;  // [n_max] order keys in cell order
   uint8_t* cstate; // [n_max]
   uint32_t* pos;   // [n_max] entry -> cell-order position (0xffffffff: not active)
+  int32_t* ctile;     // per cell-ordered entry: tile of a local, non-fragile detection when the gray-zone flags are in
+                      // force (tile_cores given), else negative
+  uint32_t* blocked;  // per cell-ordered entry: round stamp of "a large dominator is still undecided"
   size_t bytes;
   int G;
 };
@@ -299,6 +348,10 @@ static MergeWs merge_layout(void* base, long long n_max) {
   o += align256((size_t)n_max * 4);
   w.cstate = reinterpret_cast<uint8_t*>(p + o);
   o += align256((size_t)n_max);
+  w.blocked = reinterpret_cast<uint32_t*>(p + o);
+  o += align256((size_t)n_max * 4);
+  w.ctile = reinterpret_cast<int32_t*>(p + o);
+  o += align256((size_t)n_max * 4);
   w.bytes = o;
   return w;
 }
@@ -307,10 +360,15 @@ struct CellGeom {
   float cell_size, inv_cell, max_center;
 };
 
+__device__ __forceinline__ int ext_bin(float e) {
+  const int b = (int)floorf(8.0f * log2f(e)) + 16;
+  return min(max(b, 0), kExtBins - 1);
+}
+__device__ __forceinline__ float ext_bin_upper(int b) { return exp2f((float)(b - 16 + 1) * 0.125f) * 1.0001f; }
+
 __device__ __forceinline__ CellGeom cell_geom(const MergeStats* s) {
   CellGeom g;
-  const unsigned c = s->ext_cnt;
-  float cs = c ? 2.0f * (s->ext_sum / (float)c) : 1.0f;
+  float cs = s->cell_size;
   if (!(cs > 1e-20f) || !(cs < 1e30f)) cs = 1.0f;
   g.cell_size = cs;
   g.inv_cell = 1.0f / (cs * kMergeCellMargin);
@@ -338,6 +396,9 @@ __global__ void merge_stats_kernel(const float4* __restrict__ boxes, const float
                                    const long long* __restrict__ n_dev, long long n_max, float conf,
                                    MergeStats* __restrict__ stats) {
   const long long n = n_dev ? min(*n_dev, n_max) : n_max;
+  __shared__ unsigned hist[kExtBins];
+  for (int i = threadIdx.x; i < kExtBins; i += blockDim.x) hist[i] = 0u;
+  __syncthreads();
   float sum = 0.f;
   unsigned cnt = 0;
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
@@ -347,8 +408,12 @@ __global__ void merge_stats_kernel(const float4* __restrict__ boxes, const float
     if (w > 0.f && h > 0.f && w < 3.0e38f && h < 3.0e38f) {
       sum += fmaxf(w, h);
       ++cnt;
+      atomicAdd(&hist[ext_bin(fmaxf(w, h))], 1u);
     }
   }
+  __syncthreads();
+  for (int i = threadIdx.x; i < kExtBins; i += blockDim.x)
+    if (hist[i]) atomicAdd(&stats->ext_hist[i], hist[i]);
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) {
     sum += __shfl_xor_sync(0xffffffffu, sum, o);
@@ -358,6 +423,25 @@ __global__ void merge_stats_kernel(const float4* __restrict__ boxes, const float
     atomicAdd(&stats->ext_sum, sum);
     atomicAdd(&stats->ext_cnt, cnt);
   }
+}
+
+// Cell size of the spatial hash: the smallest bin edge that leaves at most max(64, 0.05 %) of the boxes in the "large"
+// bucket (one warp each), but never more than twice the mean extent.  A box is tested against the 3x3 cells around
+// its centre, so the pair tests per box grow with the square of the cell size: for nuclei (12-36 px) this picks ~38 px
+// where twice the mean is 48 px (-35 % pair tests).  Any value is exact; it only moves work between the two paths.
+__global__ void merge_pick_cell_kernel(MergeStats* __restrict__ stats) {
+  if (threadIdx.x != 0) return;
+  const unsigned c = stats->ext_cnt;
+  float cs = c ? 2.0f * (stats->ext_sum / (float)c) : 1.0f;
+  if (c) {
+    const unsigned allowed = max(64u, c / 2000u);
+    unsigned above = 0;
+    int b = kExtBins - 1;
+    // walk down while the boxes in bins above b still fit the allowance
+    while (b > 0 && above + stats->ext_hist[b] <= allowed) above += stats->ext_hist[b--];
+    if (b < kExtBins - 1) cs = fminf(cs, ext_bin_upper(b));
+  }
+  stats->cell_size = cs;
 }
 
 struct MergeIn {
@@ -412,7 +496,8 @@ __global__ void merge_classify_kernel(const MergeIn in, const MergeStats* __rest
 __global__ void merge_fill_kernel(const MergeIn in, const MergeStats* __restrict__ stats, int G,
                                   int* __restrict__ cell, const uint8_t* __restrict__ state,
                                   float4* __restrict__ cbox, uint64_t* __restrict__ ckey,
-                                  uint8_t* __restrict__ cstate, uint32_t* __restrict__ pos) {
+                                  uint8_t* __restrict__ cstate, uint32_t* __restrict__ pos,
+                                  uint32_t* __restrict__ blocked, int32_t* __restrict__ ctile) {
   const long long n = in.n_dev ? min(*in.n_dev, in.n_max) : in.n_max;
   const CellGeom g = cell_geom(stats);
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
@@ -426,6 +511,8 @@ __global__ void merge_fill_kernel(const MergeIn in, const MergeStats* __restrict
       ckey[p] = make_key(in.scores[i], in.gidx ? in.gidx[i] : in.gidx_base + (uint32_t)i);
       const bool remote = i >= in.n_local;
       cstate[p] = remote ? (uint8_t)MS_REMOTE_UNKNOWN : (cls == 0 ? (uint8_t)MS_KEPT : (uint8_t)MS_UNKNOWN);
+      blocked[p] = 0u;
+      ctile[p] = (!remote && in.tile_cores && in.tile_id) ? in.tile_id[i] : -1;
     }
     pos[i] = p;
   }
@@ -435,14 +522,15 @@ __global__ void merge_fill_kernel(const MergeIn in, const MergeStats* __restrict
 __global__ void __launch_bounds__(kMergeThreads) merge_round_kernel(const float4* __restrict__ cbox,
                                                                     const uint64_t* __restrict__ ckey,
                                                                     uint8_t* cstate, const int* __restrict__ cell,
-                                                                    MergeStats* stats, int G, float thr, int round) {
+                                                                    MergeStats* stats, int G, float thr, int round,
+                                                                    const uint32_t* __restrict__ blocked,
+                                                                    const int32_t* __restrict__ ctile) {
   if (round > 0 && stats->unknown[round - 1] == 0) {
     if (blockIdx.x == 0 && threadIdx.x == 0) stats->unknown[round] = 0;
     return;
   }
   const int NB = G * G + 1;
-  const int n_active = cell[NB - 1];
-  const int large_begin = cell[NB - 2], large_end = n_active;
+  const int large_begin = cell[NB - 2];
   const CellGeom g = cell_geom(stats);
   volatile uint8_t* vstate = cstate;
   int unknown = 0;
@@ -450,9 +538,12 @@ __global__ void __launch_bounds__(kMergeThreads) merge_round_kernel(const float4
     if (vstate[p] != MS_UNKNOWN) continue;
     const float4 bi = cbox[p];
     const uint64_t ki = ckey[p];
+    // Two survivors of the same tile's NMS that are not flagged fragile have IoU <= thr in slide coordinates too (the
+    // gray-zone bound of hdy_nms_tiles): such a pair is never tested.  Fragile rows carry ~tile (< 0).
+    const int ti = ctile[p];
     int decided = MS_KEPT;
     auto visit = [&](int q) -> bool {
-      if (ckey[q] < ki && iou_gt(cbox[q], bi, thr)) {
+      if (ckey[q] < ki && !(ti >= 0 && ctile[q] == ti) && iou_gt(cbox[q], bi, thr)) {
         const uint8_t sq = vstate[q];
         if (sq == MS_KEPT) {
           decided = MS_SUPPRESSED;
@@ -480,8 +571,11 @@ __global__ void __launch_bounds__(kMergeThreads) merge_round_kernel(const float4
             }
         }
       }
-      for (int q = large_begin; q < large_end && !done; ++q) done = visit(q);
     }
+    // boxes of the large bucket that outrank this one are not scanned here (every small box would walk the whole
+    // bucket): merge_large_push_kernel visits the small boxes under each large box instead -- it has already marked
+    // this box SUPPRESSED if such a box is KEPT, and stamped it for this round if one is still undecided
+    if (decided == MS_KEPT && blocked[p] == (uint32_t)round + 1u) decided = MS_UNKNOWN;
     if (decided != MS_UNKNOWN)
       vstate[p] = (uint8_t)decided;
     else
@@ -548,6 +642,59 @@ __global__ void __launch_bounds__(kMergeThreads) merge_round_large_kernel(const 
         vstate[p] = (uint8_t)MS_KEPT;
       else
         atomicAdd(&stats->unknown[round], 1);
+    }
+  }
+}
+
+// Large -> small direction of a round: ONE WARP per entry of the large bucket that is not SUPPRESSED walks the small
+// boxes it can intersect (same cell range as above).  A small box it outranks and overlaps (IoU > thr) is marked
+// SUPPRESSED at once if the large box is KEPT, and stamped "blocked in this round" if the large box is still
+// undecided, so merge_round_kernel never has to scan the large bucket (n_small x n_large pair tests otherwise: 7.5 of
+// the 10.8 ms of the 100k slide's merge).  Runs before merge_round_kernel of the same round.
+__global__ void __launch_bounds__(kMergeThreads) merge_large_push_kernel(const float4* __restrict__ cbox,
+                                                                         const uint64_t* __restrict__ ckey,
+                                                                         uint8_t* cstate, const int* __restrict__ cell,
+                                                                         const MergeStats* stats, int G, float thr,
+                                                                         int round, uint32_t* __restrict__ blocked) {
+  if (round > 0 && stats->unknown[round - 1] == 0) return;
+  const int NB = G * G + 1;
+  const int n_active = cell[NB - 1];
+  const int large_begin = cell[NB - 2];
+  const CellGeom g = cell_geom(stats);
+  volatile uint8_t* vstate = cstate;
+  const int lane = threadIdx.x & 31;
+  const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, n_warps = (gridDim.x * blockDim.x) >> 5;
+  const uint32_t stamp = (uint32_t)round + 1u;
+  for (int q = large_begin + warp; q < n_active; q += n_warps) {
+    const uint8_t sq = vstate[q];  // warp-uniform
+    if (sq != MS_KEPT && sq != MS_UNKNOWN && sq != MS_REMOTE_UNKNOWN) continue;
+    const float4 bq = cbox[q];
+    const uint64_t kq = ckey[q];
+    auto visit = [&](int p) {
+      if (kq < ckey[p] && vstate[p] == MS_UNKNOWN && iou_gt(bq, cbox[p], thr)) {
+        if (sq == MS_KEPT)
+          vstate[p] = (uint8_t)MS_SUPPRESSED;
+        else
+          blocked[p] = stamp;
+      }
+    };
+    const float half = 0.5f * g.cell_size;
+    const float fx0 = floorf((bq.x - half) * g.inv_cell), fx1 = floorf((bq.z + half) * g.inv_cell);
+    const float fy0 = floorf((bq.y - half) * g.inv_cell), fy1 = floorf((bq.w + half) * g.inv_cell);
+    const bool finite = fabsf(fx0) < 1.0e9f && fabsf(fx1) < 1.0e9f && fabsf(fy0) < 1.0e9f && fabsf(fy1) < 1.0e9f &&
+                        fx1 >= fx0 && fy1 >= fy0;
+    if (!finite) {
+      for (int p = lane; p < large_begin; p += 32) visit(p);
+    } else {
+      const int ix0 = (int)fx0, iy0 = (int)fy0;
+      const int nx = (int)fminf(fx1 - fx0 + 1.0f, (float)G), ny = (int)fminf(fy1 - fy0 + 1.0f, (float)G);
+      const long long cells = (long long)nx * ny;
+      for (long long c = lane; c < cells; c += 32) {
+        const int cy = (int)(c / nx), cx = (int)(c - (long long)cy * nx);
+        const int b = ((ix0 + cx) & (G - 1)) + ((iy0 + cy) & (G - 1)) * G;
+        const int beg = b ? cell[b - 1] : 0, end = cell[b];
+        for (int p = beg; p < end; ++p) visit(p);
+      }
     }
   }
 }
@@ -715,9 +862,31 @@ int hdy_merge_append(const float* boxes, const float* scores, const int64_t* lab
   return check_launch("hdy_merge_append");
 }
 
+int hdy_merge_overhang_cap(const float* boxes, const int32_t* tile_id, const float* tile_rois, const int64_t* n_dev,
+                           int64_t n_max, int max_far, float min_cap, float max_cap, uint32_t* hist, float* cap_out,
+                           hdy_stream_t stream) {
+  HDY_REQUIRE(n_max >= 0 && hist && cap_out && max_far >= 0, "hdy_merge_overhang_cap: bad arguments");
+  HDY_REQUIRE(min_cap >= 0.f && max_cap >= min_cap, "hdy_merge_overhang_cap: need 0 <= min_cap <= max_cap");
+  cudaStream_t st = (cudaStream_t)stream;
+  cudaError_t e = cudaMemsetAsync(hist, 0, kOverBins * sizeof(uint32_t), st);
+  if (e != cudaSuccess) {
+    set_error("hdy_merge_overhang_cap: cudaMemsetAsync: %s", cudaGetErrorString(e));
+    return HDY_ERR_CUDA;
+  }
+  if (n_max > 0) {
+    HDY_REQUIRE(boxes && tile_id && tile_rois && (((uintptr_t)boxes | (uintptr_t)tile_rois) & 15) == 0,
+                "hdy_merge_overhang_cap: NULL or misaligned pointer");
+    overhang_hist_kernel<<<blocks_for(n_max, 256, 148 * 8), 256, 0, st>>>(
+        reinterpret_cast<const float4*>(boxes), tile_id, reinterpret_cast<const float4*>(tile_rois),
+        reinterpret_cast<const long long*>(n_dev), n_max, hist);
+  }
+  overhang_pick_kernel<<<1, 32, 0, st>>>(hist, max_far, min_cap, max_cap, cap_out);
+  return check_launch("hdy_merge_overhang_cap");
+}
+
 int hdy_merge_overhang(const float* boxes, const int32_t* tile_id, const float* tile_rois, const int64_t* n_dev,
-                       int64_t n_max, float far_cap, float* margin, float* far_boxes, int32_t* far_tile,
-                       int32_t* far_count, int far_capacity, hdy_stream_t stream) {
+                       int64_t n_max, float far_cap, const float* far_cap_dev, float* margin, float* far_boxes,
+                       int32_t* far_tile, int32_t* far_count, int far_capacity, hdy_stream_t stream) {
   HDY_REQUIRE(n_max >= 0 && margin, "hdy_merge_overhang: bad arguments");
   HDY_REQUIRE(!far_count || (far_boxes && far_tile && far_capacity >= 0 && ((uintptr_t)far_boxes & 15) == 0),
               "hdy_merge_overhang: far_count needs far_boxes (16-byte aligned) and far_tile");
@@ -726,8 +895,8 @@ int hdy_merge_overhang(const float* boxes, const int32_t* tile_id, const float* 
               "hdy_merge_overhang: NULL or misaligned pointer");
   overhang_kernel<<<blocks_for(n_max, 256), 256, 0, (cudaStream_t)stream>>>(
       reinterpret_cast<const float4*>(boxes), tile_id, reinterpret_cast<const float4*>(tile_rois),
-      reinterpret_cast<const long long*>(n_dev), n_max, far_cap, margin, reinterpret_cast<float4*>(far_boxes), far_tile,
-      far_count, far_capacity);
+      reinterpret_cast<const long long*>(n_dev), n_max, far_cap, far_cap_dev, margin,
+      reinterpret_cast<float4*>(far_boxes), far_tile, far_count, far_capacity);
   return check_launch("hdy_merge_overhang");
 }
 
@@ -787,11 +956,12 @@ int hdy_merge_build(const float* boxes, const float* scores, const uint32_t* gid
   in.thr = iou_thres;
   const unsigned blocks = blocks_for(n_max, kMergeThreads);
   merge_stats_kernel<<<blocks, kMergeThreads, 0, st>>>(in.boxes, scores, in.n_dev, n_max, conf_thres, w.stats);
+  merge_pick_cell_kernel<<<1, 32, 0, st>>>(w.stats);
   merge_classify_kernel<<<blocks, kMergeThreads, 0, st>>>(in, w.stats, w.G, w.cell, state);
   int rc = device_exclusive_scan(w.cell, (long long)nb - 1, w.scan_tmp, nullptr, st);
   if (rc) return rc;
   merge_fill_kernel<<<blocks, kMergeThreads, 0, st>>>(in, w.stats, w.G, w.cell, state, w.cbox, w.ckey, w.cstate,
-                                                      w.pos);
+                                                      w.pos, w.blocked, w.ctile);
   return check_launch("hdy_merge_build");
 }
 
@@ -804,8 +974,10 @@ int hdy_merge_rounds(void* workspace, int64_t n_max, float iou_thres, int first_
   MergeWs w = merge_layout(workspace, n_max);
   const unsigned blocks = blocks_for(n_max, kMergeThreads, 148 * 8);
   for (int r = first_round; r < first_round + n_rounds; ++r) {
+    merge_large_push_kernel<<<148 * 2, kMergeThreads, 0, (cudaStream_t)stream>>>(w.cbox, w.ckey, w.cstate, w.cell,
+                                                                                 w.stats, w.G, iou_thres, r, w.blocked);
     merge_round_kernel<<<blocks, kMergeThreads, 0, (cudaStream_t)stream>>>(w.cbox, w.ckey, w.cstate, w.cell, w.stats,
-                                                                           w.G, iou_thres, r);
+                                                                           w.G, iou_thres, r, w.blocked, w.ctile);
     merge_round_large_kernel<<<148 * 2, kMergeThreads, 0, (cudaStream_t)stream>>>(w.cbox, w.ckey, w.cstate, w.cell,
                                                                                   w.stats, w.G, iou_thres, r);
   }

@@ -142,8 +142,14 @@ __device__ __forceinline__ void roi_rows(const RoiSmem& Sm, const float* __restr
         a0 = __fadd_rn(a0, s0[iy][ix]);
         a1 = __fadd_rn(a1, s1[iy][ix]);
       }
-    st0[pw] = __fdiv_rn(a0, count);
-    st1[pw] = __fdiv_rn(a1, count);
+    // S*S is a power of two for S = 1, 2, 4: dividing by it and multiplying by its (exact) reciprocal round alike
+    if ((S & (S - 1)) == 0) {
+      st0[pw] = __fmul_rn(a0, 1.0f / (float)(S * S));
+      st1[pw] = __fmul_rn(a1, 1.0f / (float)(S * S));
+    } else {
+      st0[pw] = __fdiv_rn(a0, count);
+      st1[pw] = __fdiv_rn(a1, count);
+    }
   }
 }
 

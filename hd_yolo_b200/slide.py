@@ -334,7 +334,8 @@ class SlideAccumulator:
             raise HdyError(f"slide accumulator overflow: {int(both[0])} rows, capacity {self.capacity}")
         return int(both[0])
 
-    FAR_CAP_PX = 64.0        # boxes sticking out of their tile by more than this are handled one by one
+    FAR_CAP_PX = 64.0        # boxes sticking out of their tile by more than this are always handled one by one
+    FAR_MIN_CAP_PX = 8.0     # ... and never those sticking out by less than this (the cap is picked in between)
     FAR_CAPACITY = 4096
 
     def overhang(self):
@@ -347,9 +348,16 @@ class SlideAccumulator:
         far_boxes = torch.empty((self.FAR_CAPACITY, 4), dtype=torch.float32, device=d)
         far_tile = torch.empty((self.FAR_CAPACITY,), dtype=torch.int32, device=d)
         far_count = torch.zeros((1,), dtype=torch.int32, device=d)
+        # the cap is picked from the data: as low as possible (every core shrinks by the largest overhang below it)
+        # while at most ~1.5 % of the tiles' worth of boxes end up on the far list (their neighbours turn dirty)
+        hist = torch.empty((256,), dtype=torch.int32, device=d)
+        cap = torch.empty((1,), dtype=torch.float32, device=d)
+        max_far = int(min(max(int(rois.shape[0]) // 64, 16), self.FAR_CAPACITY // 4))
+        _call("hdy_merge_overhang_cap", ptr(self.boxes), ptr(self.tile), ptr(rois), ptr(self.cursor), self.capacity,
+              max_far, float(self.FAR_MIN_CAP_PX), float(self.FAR_CAP_PX), ptr(hist), ptr(cap), _stream(), launches=2)
         _call("hdy_merge_overhang", ptr(self.boxes), ptr(self.tile), ptr(rois), ptr(self.cursor), self.capacity,
-              float(self.FAR_CAP_PX), ptr(margin), ptr(far_boxes), ptr(far_tile), ptr(far_count), self.FAR_CAPACITY,
-              _stream())
+              float(self.FAR_CAP_PX), ptr(cap), ptr(margin), ptr(far_boxes), ptr(far_tile), ptr(far_count),
+              self.FAR_CAPACITY, _stream())
         return margin, far_boxes, far_tile, far_count
 
     def verdicts(self, conf_thres: float, iou_thres: float, interior_shortcut: bool = False) -> torch.Tensor:

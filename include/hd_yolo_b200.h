@@ -275,8 +275,15 @@ HDY_API int hdy_merge_append(const float* boxes, const float* scores, const int6
  * not folded into the margin but listed (far_boxes [far_capacity,4], far_tile [far_capacity]; *far_count may exceed
  * far_capacity: overflow): one huge false positive would otherwise shrink every tile's core. */
 HDY_API int hdy_merge_overhang(const float* boxes, const int32_t* tile_id, const float* tile_rois,
-                               const int64_t* n_dev, int64_t n_max, float far_cap, float* margin, float* far_boxes,
-                               int32_t* far_tile, int32_t* far_count, int far_capacity, hdy_stream_t stream);
+                               const int64_t* n_dev, int64_t n_max, float far_cap, const float* far_cap_dev,
+                               float* margin, float* far_boxes, int32_t* far_tile, int32_t* far_count,
+                               int far_capacity, hdy_stream_t stream);
+/* Picks far_cap from the data: *cap_out (device float) = the smallest whole-pixel cap in [min_cap, max_cap] that
+ * leaves at most max_far boxes sticking out of their tiles by more than it (max_cap if there is none).  Pass cap_out
+ * as far_cap_dev above (it overrides far_cap).  hist: 256 device uint32 of scratch. */
+HDY_API int hdy_merge_overhang_cap(const float* boxes, const int32_t* tile_id, const float* tile_rois,
+                                   const int64_t* n_dev, int64_t n_max, int max_far, float min_cap, float max_cap,
+                                   uint32_t* hist, float* cap_out, hdy_stream_t stream);
 /* dirty [n_tiles] u8: 1 for every tile whose window is touched by a listed far-reaching box of another tile (all
  * tiles if the list overflowed).  Rows of dirty tiles never take the interior shortcut. */
 HDY_API int hdy_merge_dirty_tiles(const float* far_boxes, const int32_t* far_tile, const int32_t* far_count,

@@ -191,7 +191,7 @@ def test_merge_nms_with_large_boxes(cuda_device, n_small, n_large, seed):
     assert torch.equal(got, ref)
 
 
-def _near_threshold_tile(g, n_pairs, n_free, thr, tile=1024.0):
+def _near_threshold_tile(g, n_pairs, n_free, thr, tile=1024.0, n_big=0):
     """Boxes of one tile (tile coordinates): pairs of equal squares shifted so that their IoU sits within ~2e-4 of thr
     (either side), plus free nuclei-sized boxes."""
     s = 14.0 + 16.0 * torch.rand((n_pairs, 1), generator=g)
@@ -202,12 +202,18 @@ def _near_threshold_tile(g, n_pairs, n_free, thr, tile=1024.0):
     cf = tile * torch.rand((n_free, 2), generator=g)
     sf = 12.0 + 24.0 * torch.rand((n_free, 2), generator=g)
     free = torch.cat([cf - sf / 2, cf + sf / 2], 1)
-    boxes = torch.cat([a, b, free]).float()
+    # big false positives hugging the tile border: they stick out by 0..200 px (adaptive far cap, far list, dirty
+    # tiles) and land in the merge's large bucket (large -> small push)
+    cb = tile * torch.rand((n_big, 2), generator=g)
+    cb[:, 0] = torch.where(torch.rand((n_big,), generator=g) < 0.5, cb[:, 0] * 0.05, tile - cb[:, 0] * 0.05)
+    sb = 50.0 + 350.0 * torch.rand((n_big, 2), generator=g)
+    big = torch.cat([cb - sb / 2, cb + sb / 2], 1)
+    boxes = torch.cat([a, b, free, big]).float()
     return boxes[torch.randperm(len(boxes), generator=g)].contiguous()
 
 
-@pytest.mark.parametrize("thr,seed", [(0.45, 0), (0.3, 1), (0.7, 2)])
-def test_interior_shortcut_is_exact_far_from_the_origin(cuda_device, thr, seed):
+@pytest.mark.parametrize("thr,seed,n_big", [(0.45, 0, 0), (0.3, 1, 0), (0.7, 2, 0), (0.45, 3, 7), (0.3, 4, 3)])
+def test_interior_shortcut_is_exact_far_from_the_origin(cuda_device, thr, seed, n_big):
     """At slide coordinates ~10^5 the fp32 rounding of `box + tile origin` (yolo_head.py:455) moves IoUs by ~5e-4, so
     Ensemble.merge (yolo.py:195) suppresses pairs the per-tile NMS kept.  The gray-zone flags of hdy_nms_tiles must
     route exactly those rows around the interior shortcut: verdicts == torchvision's dense NMS on the shifted boxes."""
@@ -221,7 +227,7 @@ def test_interior_shortcut_is_exact_far_from_the_origin(cuda_device, thr, seed):
     tiles = [r * n_cols + c for r in (100, 101, 102) for c in (100, 101, 102)]      # full tiles near (96000, 96000)
     rois = rois_all[tiles]
     bs, conf = len(tiles), 0.2
-    per_tile = [_near_threshold_tile(g, 150, 120, thr) for _ in range(bs)]
+    per_tile = [_near_threshold_tile(g, 150, 120, thr, n_big=n_big) for _ in range(bs)]
     n = max(len(b) for b in per_tile)
     eps = float(np.spacing(np.float32(101000.0))) / 2
     cand = ops._Cand(dev, bs, n, tag="gz")

@@ -1,0 +1,61 @@
+"""Times hdy.multiscale_roi_align at the tiles640 scale (64 tiles, ~900 detections per tile, 256 channels, 14x14)
+against torchvision's own CUDA roi_align called the way the reference does (one call per level + scatter,
+yolo_head.py:279-299).  CUDA events, warm-up, inputs > L2.  Usage: python tools/roi_bench.py [K] [C] [bs]"""
+import json
+import sys
+
+import torch
+import torchvision
+
+sys.path.insert(0, ".")
+import hd_yolo_b200 as hdy
+
+K = int(sys.argv[1]) if len(sys.argv) > 1 else 57600
+C = int(sys.argv[2]) if len(sys.argv) > 2 else 256
+bs = int(sys.argv[3]) if len(sys.argv) > 3 else 64
+dev = torch.device("cuda:0")
+g = torch.Generator(device=dev).manual_seed(0)
+tile, strides = 640, [8, 16, 32]
+feats = [torch.randn((bs, C, tile // s, tile // s), generator=g, device=dev) for s in strides]
+c = torch.rand((K, 2), generator=g, device=dev) * tile
+sz = 12 + 24 * torch.rand((K, 2), generator=g, device=dev)               # nuclei: 12-36 px
+img = torch.randint(0, bs, (K, 1), generator=g, device=dev).float().sort(0).values
+rois = torch.cat([img, c - sz / 2, c + sz / 2], 1).contiguous()
+u = torch.rand((K,), generator=g, device=dev)
+levels = (u > 0.8).float() + (u > 0.95).float()                            # 80 / 15 / 5 % on levels 0 / 1 / 2
+
+
+def ours():
+    return hdy.multiscale_roi_align(feats, rois, levels, strides, 14, 2, False)
+
+
+def reference():
+    result = torch.zeros((K, C, 14, 14), device=dev)
+    for i, s in enumerate(strides):
+        idx = torch.where(levels == i)[0]
+        result[idx] = torchvision.ops.roi_align(feats[i], rois[idx], (14, 14), 1 / s, 2, False)
+    return result
+
+
+def timed(fn, n=10):
+    for _ in range(3):
+        fn()
+    torch.cuda.synchronize()
+    a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    a.record()
+    for _ in range(n):
+        fn()
+    b.record()
+    torch.cuda.synchronize()
+    return a.elapsed_time(b) / n
+
+
+t_ours = timed(ours)
+o = ours()
+t_ref = timed(reference, 3)
+r = reference()
+rel = ((o - r).abs() / (r.abs() + 1e-3)).max().item()
+out_bytes = o.numel() * 4
+print(json.dumps({"K": K, "C": C, "bs": bs, "ms_ours": t_ours, "ms_torchvision_per_level_loop": t_ref,
+                  "out_GB": out_bytes / 1e9, "write_GBs_ours": out_bytes / t_ours / 1e6,
+                  "write_GBs_torchvision": out_bytes / t_ref / 1e6, "max_rel_diff_vs_torchvision_cuda": rel}))
