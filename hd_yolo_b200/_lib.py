@@ -98,6 +98,8 @@ SIGNATURES = {
     "hdy_merge_select": (_i, [_vp, _vp, _vp, _i64, _vp, _vp, _vp]),
     "hdy_sort_workspace_bytes": (_sz, [_i64]),
     "hdy_sort_keys": (_i, [_vp, _vp, _vp, _i64, _vp, _sz, _vp]),
+    "hdy_sort_keys_bytes": (_i, [_vp, _vp, _vp, _i64, _i, _i, _vp, _sz, _vp]),
+    "hdy_merge_select_ordered": (_i, [_vp, _vp, _vp, _i64, _vp, _vp, _vp, _vp]),
     "hdy_rcnn_decode": (_i, [_vp, _vp, _i64, _i, _i64, _f, _f, _f, _f, _f, _vp, _vp]),
     "hdy_softmax_rows": (_i, [_vp, _i64, _i, _vp, _vp]),
     "hdy_rcnn_filter_compact": (_i, [_vp, _vp, _vp, _vp, _i, _i64, _i, _f, _f, _i, _i, _vp, _vp, _vp, _vp, _vp, _vp]),

@@ -758,6 +758,83 @@ __global__ void keep_keys_kernel(const uint8_t* __restrict__ state, const float*
   }
 }
 
+// Ordered variant: keys leave in ROW order, so that a stable sort on the score half alone (4 radix passes instead of 8)
+// already breaks ties by the lower row.  Blocks own contiguous row ranges: count -> scan of the block counts -> write.
+constexpr int kSelThreads = 256;
+constexpr int kSelMaxBlocks = 4096;
+
+__global__ void __launch_bounds__(kSelThreads) select_count_kernel(const uint8_t* __restrict__ state,
+                                                                   const long long* __restrict__ n_dev,
+                                                                   long long n_max, long long chunk,
+                                                                   int* __restrict__ block_counts) {
+  const long long n = n_dev ? min(*n_dev, n_max) : n_max;
+  const long long lo = (long long)blockIdx.x * chunk, hi = min(lo + chunk, n);
+  int c = 0;
+  for (long long i = lo + threadIdx.x; i < hi; i += kSelThreads) c += state[i] == MS_KEPT;
+  __shared__ int part[kSelThreads / 32];
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) c += __shfl_xor_sync(0xffffffffu, c, o);
+  if ((threadIdx.x & 31) == 0) part[threadIdx.x >> 5] = c;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    int t = 0;
+    for (int w = 0; w < kSelThreads / 32; ++w) t += part[w];
+    block_counts[blockIdx.x] = t;
+  }
+}
+
+__global__ void __launch_bounds__(1024) select_scan_kernel(int* __restrict__ block_counts, int nblocks,
+                                                           int* __restrict__ count_out) {
+  __shared__ int warp_tmp[33];
+  // nblocks <= kSelMaxBlocks = 4 x 1024: four consecutive entries per thread
+  int v[4], s = 0;
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    const int i = threadIdx.x * 4 + j;
+    v[j] = i < nblocks ? block_counts[i] : 0;
+    s += v[j];
+  }
+  int total;
+  int excl = block_scan_1024(s, warp_tmp, total);
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    const int i = threadIdx.x * 4 + j;
+    if (i < nblocks) block_counts[i] = excl;
+    excl += v[j];
+  }
+  if (threadIdx.x == 0) *count_out = total;
+}
+
+__global__ void __launch_bounds__(kSelThreads) select_write_kernel(const uint8_t* __restrict__ state,
+                                                                   const float* __restrict__ scores,
+                                                                   const long long* __restrict__ n_dev,
+                                                                   long long n_max, long long chunk,
+                                                                   const int* __restrict__ block_offsets,
+                                                                   uint64_t* __restrict__ keys) {
+  __shared__ int wcount[kSelThreads / 32];
+  const long long n = n_dev ? min(*n_dev, n_max) : n_max;
+  const long long lo = (long long)blockIdx.x * chunk, hi = min(lo + chunk, n);
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  long long running = block_offsets[blockIdx.x];
+  for (long long i0 = lo; i0 < hi; i0 += kSelThreads) {
+    const long long i = i0 + threadIdx.x;
+    const bool k = i < hi && state[i] == MS_KEPT;
+    const unsigned m = __ballot_sync(0xffffffffu, k);
+    if (lane == 0) wcount[warp] = __popc(m);
+    __syncthreads();
+    int before = 0, total = 0;
+#pragma unroll
+    for (int w = 0; w < kSelThreads / 32; ++w) {
+      const int c = wcount[w];
+      if (w < warp) before += c;
+      total += c;
+    }
+    if (k) keys[running + before + __popc(m & ((1u << lane) - 1u))] = make_key(scores[i], (uint32_t)i);
+    running += total;
+    __syncthreads();
+  }
+}
+
 constexpr int kSortThreads = 256;                         // 8 warps
 constexpr int kSortPerWarp = 1024;                        // keys per warp sub-tile
 constexpr int kSortWarps = kSortThreads / 32;
@@ -1038,8 +1115,49 @@ size_t hdy_sort_workspace_bytes(int64_t n_max) {
 }
 
 /* ascending LSD radix sort of 64-bit keys; result in `keys` (tmp is scratch of the same size) */
+static int sort_key_bytes(uint64_t* keys, uint64_t* tmp, const int32_t* n_dev, int64_t n_max, int first_byte,
+                          int n_bytes, void* workspace, size_t workspace_bytes, hdy_stream_t stream);
+
 int hdy_sort_keys(uint64_t* keys, uint64_t* tmp, const int32_t* n_dev, int64_t n_max, void* workspace,
                   size_t workspace_bytes, hdy_stream_t stream) {
+  return sort_key_bytes(keys, tmp, n_dev, n_max, 0, 8, workspace, workspace_bytes, stream);
+}
+
+int hdy_sort_keys_bytes(uint64_t* keys, uint64_t* tmp, const int32_t* n_dev, int64_t n_max, int first_byte,
+                        int n_bytes, void* workspace, size_t workspace_bytes, hdy_stream_t stream) {
+  HDY_REQUIRE(first_byte >= 0 && n_bytes >= 0 && first_byte + n_bytes <= 8 && (n_bytes & 1) == 0,
+              "hdy_sort_keys_bytes: bytes [%d, %d) -- an even number of bytes inside the key", first_byte,
+              first_byte + n_bytes);
+  return sort_key_bytes(keys, tmp, n_dev, n_max, first_byte, n_bytes, workspace, workspace_bytes, stream);
+}
+
+int hdy_merge_select_ordered(const uint8_t* state, const float* scores, const int64_t* n_dev, int64_t n_max,
+                             uint64_t* keys, int32_t* count, int32_t* block_scratch, hdy_stream_t stream) {
+  HDY_REQUIRE(n_max >= 0 && n_max < (1ll << 31) && count && block_scratch, "hdy_merge_select_ordered: bad arguments");
+  cudaStream_t st = (cudaStream_t)stream;
+  if (n_max == 0) {
+    cudaError_t e = cudaMemsetAsync(count, 0, 4, st);
+    if (e != cudaSuccess) {
+      set_error("hdy_merge_select_ordered: %s", cudaGetErrorString(e));
+      return HDY_ERR_CUDA;
+    }
+    return HDY_OK;
+  }
+  HDY_REQUIRE(state && scores && keys, "hdy_merge_select_ordered: NULL pointer");
+  // contiguous row ranges, a multiple of the block size, at most kSelMaxBlocks of them
+  long long chunk = (n_max + kSelMaxBlocks - 1) / kSelMaxBlocks;
+  chunk = ((chunk + kSelThreads - 1) / kSelThreads) * kSelThreads;
+  if (chunk < 4 * kSelThreads) chunk = 4 * kSelThreads;
+  const int nblocks = (int)((n_max + chunk - 1) / chunk);
+  const long long* nd = reinterpret_cast<const long long*>(n_dev);
+  select_count_kernel<<<nblocks, kSelThreads, 0, st>>>(state, nd, n_max, chunk, block_scratch);
+  select_scan_kernel<<<1, 1024, 0, st>>>(block_scratch, nblocks, count);
+  select_write_kernel<<<nblocks, kSelThreads, 0, st>>>(state, scores, nd, n_max, chunk, block_scratch, keys);
+  return check_launch("hdy_merge_select_ordered");
+}
+
+static int sort_key_bytes(uint64_t* keys, uint64_t* tmp, const int32_t* n_dev, int64_t n_max, int first_byte,
+                          int n_bytes, void* workspace, size_t workspace_bytes, hdy_stream_t stream) {
   HDY_REQUIRE(n_max >= 0 && n_max < (1ll << 31), "hdy_sort_keys: bad size");
   if (n_max == 0) return HDY_OK;
   HDY_REQUIRE(keys && tmp && workspace && workspace_bytes >= hdy_sort_workspace_bytes(n_max),
@@ -1052,7 +1170,7 @@ int hdy_sort_keys(uint64_t* keys, uint64_t* tmp, const int32_t* n_dev, int64_t n
   const unsigned blocks = (unsigned)((n_sub + kSortWarps - 1) / kSortWarps);
   uint64_t* src = keys;
   uint64_t* dst = tmp;
-  for (int pass = 0; pass < 8; ++pass) {
+  for (int pass = first_byte; pass < first_byte + n_bytes; ++pass) {
     sort_hist_kernel<<<blocks, kSortThreads, 0, st>>>(src, n_dev, (int)n_max, pass * 8, n_sub, hist);
     int rc = device_exclusive_scan(hist, hist_n, scratch, nullptr, st);
     if (rc) return rc;
@@ -1061,7 +1179,7 @@ int hdy_sort_keys(uint64_t* keys, uint64_t* tmp, const int32_t* n_dev, int64_t n
     src = dst;
     dst = t;
   }
-  return check_launch("hdy_sort_keys");  // 8 passes: the result is back in `keys`
+  return check_launch("hdy_sort_keys");  // an even number of passes: the result is back in `keys`
 }
 
 int hdy_merge_select(const uint8_t* state, const float* scores, const int64_t* n_dev, int64_t n_max, uint64_t* keys,

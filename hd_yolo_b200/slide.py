@@ -160,8 +160,10 @@ def dirty_tiles(far_boxes: torch.Tensor, far_tile: torch.Tensor, far_count: torc
     return dirty
 
 
-def sort_keys(keys: torch.Tensor, n_dev: Optional[torch.Tensor] = None) -> torch.Tensor:
-    """Ascending in-place LSD radix sort of int64-typed 64-bit keys (bit pattern treated as unsigned)."""
+def sort_keys(keys: torch.Tensor, n_dev: Optional[torch.Tensor] = None, first_byte: int = 0,
+              n_bytes: int = 8) -> torch.Tensor:
+    """Ascending in-place LSD radix sort of int64-typed 64-bit keys (bit pattern treated as unsigned); stable, and
+    restricted to the bytes [first_byte, first_byte + n_bytes) of the key when asked (n_bytes even)."""
     if not keys.is_cuda or keys.dtype != torch.int64 or not keys.is_contiguous():
         raise HdyError("keys must be a contiguous CUDA int64 tensor")
     n = keys.numel()
@@ -170,7 +172,8 @@ def sort_keys(keys: torch.Tensor, n_dev: Optional[torch.Tensor] = None) -> torch
         wbytes = lib.hdy_sort_workspace_bytes(n)
         ws = _ws.get(keys.device, "sort", wbytes)
         tmp = _ws.get(keys.device, "sort_tmp", n * 8)
-        _call("hdy_sort_keys", ptr(keys), ptr(tmp), ptr(n_dev), n, ptr(ws), wbytes, _stream(), launches=8 * 5)
+        _call("hdy_sort_keys_bytes", ptr(keys), ptr(tmp), ptr(n_dev), n, int(first_byte), int(n_bytes), ptr(ws), wbytes,
+              _stream(), launches=int(n_bytes) * 5)
     return keys
 
 
@@ -180,10 +183,14 @@ def _kept_in_order(state, boxes, scores, labels, max_det: int, n_dev=None):
     n = boxes.shape[0]
     keys = torch.empty((n,), dtype=torch.int64, device=dev)
     count = torch.empty((1,), dtype=torch.int32, device=dev)
-    _call("hdy_merge_select", ptr(state), ptr(scores), ptr(n_dev), n, ptr(keys), ptr(count), _stream())
+    # keys in row order + a stable sort of the score half only: same order as sorting the whole 64-bit key, in four
+    # radix passes instead of eight
+    blk = _ws.get(dev, "select_blocks", 4096 * 4)
+    _call("hdy_merge_select_ordered", ptr(state), ptr(scores), ptr(n_dev), n, ptr(keys), ptr(count), ptr(blk), _stream(),
+          launches=3)
     k_all = int(count.item())
     keys = keys[:k_all]
-    sort_keys(keys)
+    sort_keys(keys, first_byte=4, n_bytes=4)
     k = min(k_all, int(max_det))
     idx = torch.empty((k,), dtype=torch.int64, device=dev)
     ob = torch.empty((k, 4), dtype=torch.float32, device=dev)

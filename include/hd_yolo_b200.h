@@ -334,6 +334,13 @@ HDY_API int hdy_merge_select(const uint8_t* state, const float* scores, const in
 HDY_API size_t hdy_sort_workspace_bytes(int64_t n_max);
 HDY_API int hdy_sort_keys(uint64_t* keys, uint64_t* tmp, const int32_t* n_dev, int64_t n_max, void* workspace,
                           size_t workspace_bytes, hdy_stream_t stream);
+/* The same in fewer passes: select_ordered emits the keys in ROW order (block_scratch: 4096 device int32), so a
+ * stable sort of the score half alone (sort_keys_bytes with first_byte = 4, n_bytes = 4: four of the eight passes)
+ * leaves ties in row order -- the same result as select + sort_keys.  n_bytes must be even (result in `keys`). */
+HDY_API int hdy_merge_select_ordered(const uint8_t* state, const float* scores, const int64_t* n_dev, int64_t n_max,
+                                     uint64_t* keys, int32_t* count, int32_t* block_scratch, hdy_stream_t stream);
+HDY_API int hdy_sort_keys_bytes(uint64_t* keys, uint64_t* tmp, const int32_t* n_dev, int64_t n_max, int first_byte,
+                                int n_bytes, void* workspace, size_t workspace_bytes, hdy_stream_t stream);
 HDY_API int hdy_merge_gather(const uint64_t* keys, const int32_t* count, int64_t max_det, const float* boxes,
                              const float* scores, const int64_t* labels, int64_t* out_idx, float* out_boxes,
                              float* out_scores, int64_t* out_labels, int32_t* out_count, hdy_stream_t stream);
