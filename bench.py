@@ -59,6 +59,8 @@ def parse():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-slide", action="store_true")
+    ap.add_argument("--slide-streams", type=int, default=1,
+                    help="slide workload: tile batches alternate over this many streams (SlidePostprocessor(streams=))")
     ap.add_argument("--inflight", type=int, default=3, help="steps in flight (CUDA graphs on separate streams)")
     a = ap.parse_args()
     if a.steps is None:
@@ -487,7 +489,7 @@ def run_slide(args, wl, c, steps, warmup, want_e2e):
     S = args.slide_size
     post = SlidePostprocessor(spec, (S, S), (tile, tile), wl["overlap"], wl["conf"], wl["iou"], wl["max_det"],
                               cap=wl["cap"], batch=bs, rank=c.rank, world=c.world, device=c.dev,
-                              capacity=None)
+                              capacity=None, streams=args.slide_streams)
     t0, t1 = post.tile_range
     n_tiles = int(post.rois.shape[0])
     # this rank's head outputs for the whole slide, resident in HBM (N=1: 11 025 tiles x 2.3 MB = 25.6 GB)
@@ -530,11 +532,13 @@ def run_slide(args, wl, c, steps, warmup, want_e2e):
         # reused in rotation, bytes are counted for every copy), the slide's survivors are read back D2H
         nrot = min(4, len(store))
         host = [[t.cpu().pin_memory() for t in store[k]] for k in range(nrot)]
-        stage = [torch.empty_like(t) for t in store[0]]
+        # one staging buffer set per stream of the post-processor (batch k runs on stream k % streams)
+        stages = [[torch.empty_like(t) for t in store[0]] for _ in range(max(1, args.slide_streams))]
 
         def provider_h(a, b):
             k = ((a - t0) // bs)
             src = host[k % nrot]
+            stage = stages[k % len(stages)]
             n = b - a
             for s, h in zip(stage, src):
                 s[:n].copy_(h[:n], non_blocking=True)
@@ -561,7 +565,7 @@ def run_slide(args, wl, c, steps, warmup, want_e2e):
         d2h = sum(t.numel() * t.element_size() for t in hb.values())
         out["e2e"] = {"value": n_tiles * Ke / (ms_e * 1e-3), "unit": "tiles/s", "h2d_bytes_per_step": in_bytes,
                       "d2h_bytes_per_step": d2h, "steps": Ke, "ms_per_step": ms_e / Ke}
-        del host, stage
+        del host, stages
     del store
     torch.cuda.empty_cache()
     return out

@@ -29,9 +29,15 @@ class SlidePostprocessor:
 
     def __init__(self, spec: HeadSpec, image_size, roi_size, overlap: int, conf_thres: float, iou_thres: float,
                  max_det: int, cap: Optional[int] = None, batch: int = 128, rank: int = 0, world: int = 1,
-                 group=None, device=None, capacity: Optional[int] = None, interior_shortcut: bool = True):
+                 group=None, device=None, capacity: Optional[int] = None, interior_shortcut: bool = True,
+                 streams: int = 1):
         self.spec, self.conf, self.iou, self.max_det, self.cap = spec, conf_thres, iou_thres, max_det, cap
         self.batch, self.rank, self.world, self.group = batch, rank, world, group
+        # streams > 1: consecutive tile batches are post-processed on alternating side streams (own scratch slot
+        # each), so one batch's latency-bound per-tile NMS overlaps the next batch's HBM-bound filter; the appends stay
+        # in tile order through an event chain
+        self.n_streams = max(1, int(streams))
+        self._side: List[torch.cuda.Stream] = []
         self.device = torch.device(device if device is not None else f"cuda:{torch.cuda.current_device()}")
         self.rois = sliding_window_scanner(image_size, roi_size, overlap)            # [n_tiles, 4] host
         self.tile_range = hdist.shard_tile_rows(self.rois, world)[rank]
@@ -55,11 +61,35 @@ class SlidePostprocessor:
         """Per-tile post-processing of every own tile, appended in slide coordinates.  No host synchronisation."""
         t0, t1 = self.tile_range
         self.acc.reset()
-        for a in range(t0, t1, self.batch):
-            b = min(a + self.batch, t1)
-            out = detect_postprocess(provider(a, b), self.spec, self.conf, self.iou, self.max_det, cap=self.cap,
-                                     gray_eps=self.gray_eps if self.shortcut else 0.0)
-            self.acc.append(out, self.rois_dev[a - t0:b - t0])
+        if self.n_streams == 1:
+            for a in range(t0, t1, self.batch):
+                b = min(a + self.batch, t1)
+                out = detect_postprocess(provider(a, b), self.spec, self.conf, self.iou, self.max_det, cap=self.cap,
+                                         gray_eps=self.gray_eps if self.shortcut else 0.0)
+                self.acc.append(out, self.rois_dev[a - t0:b - t0])
+            return
+        from .ops import scratch_slot
+        with torch.cuda.device(self.device):
+            while len(self._side) < self.n_streams:
+                self._side.append(torch.cuda.Stream())
+            cur = torch.cuda.current_stream()
+            for s in self._side:
+                s.wait_stream(cur)
+            prev = None
+            for i, a in enumerate(range(t0, t1, self.batch)):
+                b = min(a + self.batch, t1)
+                s = self._side[i % self.n_streams]
+                with torch.cuda.stream(s), scratch_slot(8 + i % self.n_streams):
+                    dets = provider(a, b)
+                    out = detect_postprocess(dets, self.spec, self.conf, self.iou, self.max_det, cap=self.cap,
+                                             gray_eps=self.gray_eps if self.shortcut else 0.0)
+                    if prev is not None:
+                        s.wait_event(prev)           # appends in tile order: the accumulator's cursor is shared
+                    self.acc.append(out, self.rois_dev[a - t0:b - t0])
+                    prev = torch.cuda.Event()
+                    prev.record(s)
+            for s in self._side:
+                cur.wait_stream(s)
 
     def merge(self, ordered: bool = True) -> Dict[str, torch.Tensor]:
         """Slide-level Ensemble.merge over all ranks' detections.  Returns this rank's part: 'state' (verdict per own

@@ -12,12 +12,14 @@ from oracle import port
 pytestmark = pytest.mark.gpu
 
 
-@pytest.mark.parametrize("size,tile,overlap,batch", [((1500, 2000), 512, 64, 5), ((900, 900), 512, 32, 128)])
-def test_slide_postprocessor_matches_oracle_composition(cuda_device, size, tile, overlap, batch):
+@pytest.mark.parametrize("size,tile,overlap,batch,streams", [((1500, 2000), 512, 64, 5, 1), ((900, 900), 512, 32, 128, 1),
+                                                             ((1500, 2000), 512, 64, 3, 3), ((2100, 1100), 512, 64, 2, 2)])
+def test_slide_postprocessor_matches_oracle_composition(cuda_device, size, tile, overlap, batch, streams):
     dev = cuda_device
     conf, iou, md = 0.25, 0.45, 1500
     spec = hdy.HeadSpec(synth.ANCHORS_3, synth.STRIDES_3, nc=4)
-    post = hdy.SlidePostprocessor(spec, size, (tile, tile), overlap, conf, iou, md, cap=2048, batch=batch, device=dev)
+    post = hdy.SlidePostprocessor(spec, size, (tile, tile), overlap, conf, iou, md, cap=2048, batch=batch, device=dev,
+                                  streams=streams)
     rois = post.rois
     n_tiles = len(rois)
     assert n_tiles >= 4
@@ -29,6 +31,9 @@ def test_slide_postprocessor_matches_oracle_composition(cuda_device, size, tile,
         return store[(a, b)]
 
     res = post.run(provider, ordered=True)
+    if streams > 1:      # batches on alternating streams: a second pass over the same (now cached) inputs is identical
+        again = post.run(provider, ordered=True)
+        assert all(torch.equal(res[k], again[k]) for k in ('boxes', 'scores', 'labels', 'index', 'state'))
     # oracle on the same head outputs
     tiles = []
     for (a, b), dets in sorted(store.items()):
