@@ -62,6 +62,15 @@ __device__ __forceinline__ bool iou_gt(const float4& a, const float4& b, float t
   float inter = __fmul_rn(w, h);
   if (!(inter > 0.0f)) return false;  // 0/x is 0 or NaN: never > thr (thr >= 0)
   float uni = __fsub_rn(__fadd_rn(box_area(a), box_area(b)), inter);
+  // The verdict is fl(inter / uni) > thr.  Away from the threshold it can be read off one product: with
+  // t = fl(thr * uni), inter > t * (1 + 1e-5) implies the rounded quotient exceeds thr, inter < t * (1 - 1e-5) implies
+  // it does not (each rounding moves a value by at most 6e-8 relative); only the sliver in between pays for the IEEE
+  // division.  NaN / inf operands fail both tests and take the division, as before.
+  if (thr > 1.0e-3f) {
+    const float t = __fmul_rn(thr, uni);
+    if (inter > __fmul_rn(t, 1.00001f)) return true;
+    if (inter < __fmul_rn(t, 0.99999f)) return false;
+  }
   return __fdiv_rn(inter, uni) > thr;
 }
 
