@@ -59,7 +59,7 @@ def parse():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-slide", action="store_true")
-    ap.add_argument("--slide-streams", type=int, default=1,
+    ap.add_argument("--slide-streams", type=int, default=3,
                     help="slide workload: tile batches alternate over this many streams (SlidePostprocessor(streams=))")
     ap.add_argument("--inflight", type=int, default=3, help="steps in flight (CUDA graphs on separate streams)")
     a = ap.parse_args()
@@ -212,14 +212,39 @@ class Ctx:
     pass
 
 
+def bind_to_gpu_numa_node(index):
+    """Pin this process to the CPUs next to GPU `index` (sysfs local_cpulist of its PCI function) before any pinned
+    host buffer is allocated: first-touch then places the e2e staging buffers on the GPU's own NUMA node, which is
+    worth up to 1.4x of H2D bandwidth on a two-socket box.  Returns a short description for the JSON line."""
+    try:
+        import torch
+        pr = torch.cuda.get_device_properties(index)
+        path = f"/sys/bus/pci/devices/{pr.pci_domain_id:04x}:{pr.pci_bus_id:02x}:{pr.pci_device_id:02x}.0/local_cpulist"
+        cpus = set()
+        for part in open(path).read().strip().split(","):
+            if "-" in part:
+                a, b = part.split("-")
+                cpus.update(range(int(a), int(b) + 1))
+            elif part:
+                cpus.add(int(part))
+        cpus &= os.sched_getaffinity(0)
+        if cpus and len(cpus) < len(os.sched_getaffinity(0)):
+            os.sched_setaffinity(0, cpus)
+            return f"bound to the {len(cpus)} CPUs local to GPU {index}"
+        return "all CPUs are local to the GPU (single NUMA node)"
+    except Exception as e:  # no sysfs entry / no PCI ids: leave the affinity alone
+        return f"unchanged ({type(e).__name__})"
+
+
 def make_ctx(args):
-    import torch
-    import torch.distributed as dist
     c = Ctx()
     c.world = int(os.environ.get("WORLD_SIZE", "1"))
     c.rank = int(os.environ.get("RANK", "0"))
     c.local = int(os.environ.get("LOCAL_RANK", "0"))
+    import torch
+    import torch.distributed as dist
     torch.cuda.set_device(c.local)
+    c.affinity = bind_to_gpu_numa_node(c.local)
     c.dev = torch.device("cuda", c.local)
     if c.world > 1:
         dist.init_process_group("nccl", device_id=c.dev)
@@ -600,7 +625,9 @@ def main():
                        "tiles": s["tiles"], "detections": s["detections"], "kept": s["kept"],
                        "stages": "per-tile decode+filter+compact, nms, select; append in slide coordinates; exact "
                                  "slide-level merge NMS (seam all-gather + verdict exchange over NCCL when N>1)",
-                       "l2": f"{s['input_bytes'] / 1e9:.1f} GB of head outputs resident in HBM, each read once per step"},
+                       "l2": f"{s['input_bytes'] / 1e9:.1f} GB of head outputs resident in HBM, each read once per step",
+                       "launch": f"tile batches of {wl['bs']} alternate over {args.slide_streams} streams "
+                                 "(SlidePostprocessor(streams=)), appends chained by events"},
             "boxes_per_s": s["boxes_per_s"], "roofline": t["roofline"], "stages": t["stages"],
             "slide": s, "e2e": s.get("e2e"), "gpu_launches": s["gpu_launches"], "clocks": clocks,
         }
@@ -620,6 +647,8 @@ def main():
         cpu["value_reference_threads"] = v8
         cpu["reference_threads"] = c8
     line["cpu_baseline"] = cpu
+    if isinstance(line.get("e2e"), dict):
+        line["e2e"]["host_affinity"] = c.affinity
     if c.rank == 0:
         print(json.dumps(line))
     if c.world > 1:

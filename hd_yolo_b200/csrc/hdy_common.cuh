@@ -66,7 +66,7 @@ __device__ __forceinline__ bool iou_gt(const float4& a, const float4& b, float t
   // t = fl(thr * uni), inter > t * (1 + 1e-5) implies the rounded quotient exceeds thr, inter < t * (1 - 1e-5) implies
   // it does not (each rounding moves a value by at most 6e-8 relative); only the sliver in between pays for the IEEE
   // division.  NaN / inf operands fail both tests and take the division, as before.
-  if (thr > 1.0e-3f) {
+  if (thr > 1.0e-3f && uni > 1.0e-30f) {  // products stay normal: the relative error bounds hold
     const float t = __fmul_rn(thr, uni);
     if (inter > __fmul_rn(t, 1.00001f)) return true;
     if (inter < __fmul_rn(t, 0.99999f)) return false;
