@@ -34,6 +34,27 @@ if ROOT not in sys.path:
     sys.path.insert(0, ROOT)
 os.environ.setdefault("NCCL_DEBUG", "WARN")   # keep NCCL's version banner off stdout: rank 0 prints ONE JSON line
 
+# ... and when the environment asks for NCCL_DEBUG=VERSION/INFO anyway (or any library writes to fd 1): the JSON line
+# goes to a private duplicate of stdout, everything else that is written to fd 1 lands on stderr.
+_JSON_FD = None
+
+
+def _protect_stdout():
+    global _JSON_FD
+    if _JSON_FD is None:
+        sys.stdout.flush()
+        _JSON_FD = os.dup(1)
+        os.dup2(2, 1)
+
+
+def _emit(line):
+    data = (json.dumps(line) + "\n").encode()
+    if _JSON_FD is None:
+        sys.stdout.write(data.decode())
+        sys.stdout.flush()
+    else:
+        os.write(_JSON_FD, data)
+
 WORKLOADS = {
     # BASELINE.json configs[1]: 640x640 tiles, batch 64, 3 anchor levels, 32 prototypes, ~1k candidates/tile
     "tiles640": dict(tile=640, bs=64, n_cand=1000, conf=0.25, iou=0.45, max_det=1000, nc=4, cap=2048),
@@ -204,7 +225,7 @@ def run_reference(args, wl):
         "e2e": {"value": v, "unit": "tiles/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "boxes_per_s": v * wl["n_cand"],
     }
-    print(json.dumps(line))
+    _emit(line)
 
 
 # ------------------------------------------------------------------------------------------------ helpers
@@ -599,6 +620,7 @@ def run_slide(args, wl, c, steps, warmup, want_e2e):
 # ------------------------------------------------------------------------------------------------ main
 def main():
     args = parse()
+    _protect_stdout()
     wl = WORKLOADS[args.workload]
     if args.impl == "reference":
         return run_reference(args, wl)
@@ -650,7 +672,7 @@ def main():
     if isinstance(line.get("e2e"), dict):
         line["e2e"]["host_affinity"] = c.affinity
     if c.rank == 0:
-        print(json.dumps(line))
+        _emit(line)
     if c.world > 1:
         dist.destroy_process_group()
 
