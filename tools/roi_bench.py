@@ -54,8 +54,8 @@ t_ours = timed(ours)
 o = ours()
 t_ref = timed(reference, 3)
 r = reference()
-rel = ((o - r).abs() / (r.abs() + 1e-3)).max().item()
+rel = (o - r).abs().max().item()   # torchvision's CUDA kernel contracts the sample sums into FMAs: last-bit differences
 out_bytes = o.numel() * 4
 print(json.dumps({"K": K, "C": C, "bs": bs, "ms_ours": t_ours, "ms_torchvision_per_level_loop": t_ref,
                   "out_GB": out_bytes / 1e9, "write_GBs_ours": out_bytes / t_ours / 1e6,
-                  "write_GBs_torchvision": out_bytes / t_ref / 1e6, "max_rel_diff_vs_torchvision_cuda": rel}))
+                  "write_GBs_torchvision": out_bytes / t_ref / 1e6, "max_abs_diff_vs_torchvision_cuda": rel}))
