@@ -222,10 +222,16 @@ __global__ void __launch_bounds__(kRoiPairs* kRoiMaxM, S <= 2 ? 3 : 1) roi_align
   const float* feat = L.data[lvl] + ((size_t)b * C + cbase) * H * W;
   if (staged) {
     const int per = wh * ww;
-    for (int i = t; i < nch * per; i += blockDim.x) {
-      const int c = i / per, e = i - c * per;
-      const int y = e / ww, x = e - y * ww;
-      Sm.win[i] = __ldg(feat + (size_t)c * H * W + (size_t)(ylo + y) * W + xlo + x);
+    // lane = channel, warps stride over the window elements: the element index (and its row / column split) is
+    // warp-uniform, so no per-thread division is left in this loop
+    const int nwarp = blockDim.x >> 5;
+    if (lane < nch) {
+      const float* src = feat + (size_t)lane * H * W + (size_t)ylo * W + xlo;
+      float* dstw = Sm.win + lane * per;
+      for (int e = warp; e < per; e += nwarp) {
+        const int y = e / ww, x = e - y * ww;
+        dstw[e] = __ldg(src + (size_t)y * W + x);
+      }
     }
     // the odd channel of the last pair of a ragged chunk reads defined values
     if (nch & 1)

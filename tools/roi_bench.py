@@ -51,11 +51,19 @@ def timed(fn, n=10):
 
 
 t_ours = timed(ours)
-o = ours()
 t_ref = timed(reference, 3)
-r = reference()
-rel = (o - r).abs().max().item()   # torchvision's CUDA kernel contracts the sample sums into FMAs: last-bit differences
-out_bytes = o.numel() * 4
+# agreement on a slice: at the full size torchvision's CUDA kernel indexes its output with a 32-bit int, and level 0
+# alone holds 46 000 x 256 x 196 = 2.3e9 elements -- its result is not usable as a reference there (ours indexes with
+# size_t and is bit-identical to torchvision's CPU op, tests/test_gpu_next.py)
+n_chk = min(K, 4096)
+o = hdy.multiscale_roi_align(feats, rois[:n_chk].contiguous(), levels[:n_chk].contiguous(), strides, 14, 2, False)
+r = torch.zeros_like(o)
+for i, s in enumerate(strides):
+    idx = torch.where(levels[:n_chk] == i)[0]
+    r[idx] = torchvision.ops.roi_align(feats[i], rois[:n_chk][idx], (14, 14), 1 / s, 2, False)
+diff = (o - r).abs().max().item()
+out_bytes = K * C * 14 * 14 * 4
 print(json.dumps({"K": K, "C": C, "bs": bs, "ms_ours": t_ours, "ms_torchvision_per_level_loop": t_ref,
                   "out_GB": out_bytes / 1e9, "write_GBs_ours": out_bytes / t_ours / 1e6,
-                  "write_GBs_torchvision": out_bytes / t_ref / 1e6, "max_abs_diff_vs_torchvision_cuda": rel}))
+                  "write_GBs_torchvision": out_bytes / t_ref / 1e6,
+                  "max_abs_diff_vs_torchvision_cuda_first_4096_rois": diff}))
