@@ -609,6 +609,7 @@ int hdy_process_mask(const float* protos, const float* coef, const float* boxes,
   }
   const float rx = (float)((double)mw / (double)iw), ry = (float)((double)mh / (double)ih);
   rc = launch_process_mask_regions(protos, coef, boxes, counts, bs, max_det, nm, mh, mw, ih, iw, upsample, rx, ry, out,
+                                   nullptr,
                                    nullptr, nullptr, 0, nullptr, workspace, workspace_bytes, st);
   if (rc != 1) return rc;
   process_mask_kernel<false><<<(unsigned)((size_t)bs * max_det), kPmThreads, 0, st>>>(
@@ -641,7 +642,7 @@ int hdy_process_mask_geometry(const float* boxes, const int32_t* counts, int bs,
 }
 
 int hdy_process_mask_packed(const float* protos, const float* coef, const float* boxes, const int32_t* counts,
-                            const int64_t* offsets, int bs, int max_det, int nm, int mh, int mw, int ih, int iw,
+                            const int32_t* geom, const int64_t* offsets, int bs, int max_det, int nm, int mh, int mw, int ih, int iw,
                             int upsample, uint32_t* bits, int64_t capacity_words, int32_t* status, void* workspace,
                             size_t workspace_bytes, hdy_stream_t stream) {
   int rc = pm_args_ok(protos, coef, boxes, counts, bs, max_det, nm, mh, mw, ih, iw);
@@ -651,8 +652,10 @@ int hdy_process_mask_packed(const float* protos, const float* coef, const float*
   cudaStream_t st = (cudaStream_t)stream;
   const float rx = (float)((double)mw / (double)iw), ry = (float)((double)mh / (double)ih);
   // two-phase path: every word of every mask is written exactly once, nothing to clear
+  HDY_REQUIRE(!geom || ((uintptr_t)geom & 15) == 0, "hdy_process_mask_packed: geom must be 16-byte aligned");
   rc = launch_process_mask_regions(protos, coef, boxes, counts, bs, max_det, nm, mh, mw, ih, iw, upsample, rx, ry,
-                                   nullptr, offsets, bits, capacity_words, status, workspace, workspace_bytes, st);
+                                   nullptr, geom, offsets, bits, capacity_words, status, workspace, workspace_bytes,
+                                   st);
   if (rc != 1) return rc;
   // per-detection path: bits are OR-ed in, clear first (capacity is an upper bound the caller sized)
   cudaError_t e = cudaMemsetAsync(bits, 0, (size_t)capacity_words * 4, st);

@@ -44,6 +44,40 @@ __device__ __forceinline__ int ceil_to_int_clamped(float v, int lo, int hi) {
   return (int)ceilf(v);
 }
 
+// Source coordinate of output pixel `dst` exactly as lerp_coord (ATen) computes it.
+__device__ __forceinline__ float pm_src(int dst, float scale) {
+  const float src = __fsub_rn(__fmul_rn(scale, __fadd_rn((float)dst, 0.5f)), 0.5f);
+  return src < 0.f ? 0.f : src;
+}
+
+// Shrinks the window [o0, o1) of one axis to the output pixels whose value can exceed 0.5.  Proto pixels outside
+// [p0, p1) are cropped to zero and the kept ones are at most 1, so an output pixel left of the kept range is worth at
+// most its weight on pixel p0: with i0 = p0 - 1 that weight is l1 = src - i0, i.e. the pixel is dead while
+// src <= p0 - 0.5 (and it is exactly zero while i1 < p0).  Symmetrically on the right, where pixel p1 exists (p1 < in):
+// dead once src >= p1 - 0.5 (l0 = 1 - l1 <= 0.5).  Rounding cannot lift such a value over 0.5: every product and sum
+// in bilerp is monotone in its operands and 0.5 * (l0 + l1) rounds to 0.5.  src is monotone in the pixel index, so
+// both ends are found from an estimate and a short walk.  At 4x a nucleus' window shrinks by 6 pixels per axis
+// (36 -> 30: one 32-bit word per row instead of two).
+__device__ __forceinline__ void pm_trim(int& o0, int& o1, int p0, int p1, int in_size, float scale) {
+  if (o1 <= o0) return;
+  if (p0 > 0) {
+    const float tl = (float)p0 - 0.5f;
+    int c = (int)floorf((float)p0 / scale - 0.5f) - 1;
+    c = min(max(c, o0), o1);
+    while (c < o1 && !(pm_src(c, scale) > tl)) ++c;
+    while (c > o0 && pm_src(c - 1, scale) > tl) --c;
+    o0 = c;
+  }
+  if (p1 < in_size && o1 > o0) {
+    const float tr = (float)p1 - 0.5f;
+    int c = (int)floorf((float)p1 / scale - 0.5f) - 1;
+    c = min(max(c, o0), o1);
+    while (c < o1 && !(pm_src(c, scale) >= tr)) ++c;
+    while (c > o0 && pm_src(c - 1, scale) >= tr) --c;
+    o1 = c;
+  }
+}
+
 __device__ __forceinline__ PMGeom pm_geometry(const float4 b, int mh, int mw, int ih, int iw, int upsample,
                                               float rx, float ry) {
   PMGeom g;
@@ -74,6 +108,9 @@ __device__ __forceinline__ PMGeom pm_geometry(const float4 b, int mh, int mw, in
     oy0 = max(oy0, 0);
     ox1 = min(ox1, iw);
     oy1 = min(oy1, ih);
+    // ... trimmed to the pixels that CAN exceed 0.5 (exact, see pm_trim)
+    pm_trim(ox0, ox1, g.px0, g.px1, mw, sx);
+    pm_trim(oy0, oy1, g.py0, g.py1, mh, sy);
     g.x0 = ox0;
     g.y0 = oy0;
     g.w = max(ox1 - ox0, 0);
@@ -90,7 +127,7 @@ constexpr int kPatchPitch = 16;  // sigmoid patches of up to 16 x 16 proto pixel
 size_t process_mask_workspace_bytes(long long bs, long long max_det);
 int launch_process_mask_regions(const float* protos, const float* coef, const float* boxes, const int32_t* counts,
                                 int bs, int max_det, int nm, int mh, int mw, int ih, int iw, int upsample, float rx,
-                                float ry, float* out_dense, const int64_t* offsets, uint32_t* bits,
+                                float ry, float* out_dense, const int32_t* geom, const int64_t* offsets, uint32_t* bits,
                                 long long capacity_words, int32_t* status, void* workspace, size_t workspace_bytes,
                                 cudaStream_t stream);
 // mask.cu: the per-detection kernel over a device-side list of slots

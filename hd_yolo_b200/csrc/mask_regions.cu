@@ -258,7 +258,8 @@ template <bool PACKED, bool UPSAMPLE>
 __global__ void __launch_bounds__(kUpWarps * 32) mask_upsample_pack_kernel(
     const float* __restrict__ patches, const float4* __restrict__ boxes, const int32_t* __restrict__ counts,
     long long n_slots, int max_det, int mh, int mw, int ih, int iw, float rx, float ry, float* __restrict__ out_dense,
-    const int64_t* __restrict__ offsets, uint32_t* __restrict__ bits, long long capacity_words,
+    const int32_t* __restrict__ geom4, const int64_t* __restrict__ offsets, uint32_t* __restrict__ bits,
+    long long capacity_words,
     int32_t* __restrict__ status, int32_t* __restrict__ large_count, int32_t* __restrict__ large_list) {
   __shared__ UpSmem S;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -266,7 +267,17 @@ __global__ void __launch_bounds__(kUpWarps * 32) mask_upsample_pack_kernel(
   if (slot >= n_slots) return;
   const int tile = (int)(slot / max_det), d = (int)(slot - (long long)tile * max_det);
   if (d >= counts[tile]) return;
-  const PMGeom g = pm_geometry(boxes[slot], mh, mw, ih, iw, UPSAMPLE ? 1 : 0, rx, ry);
+  PMGeom g;
+  if (geom4) {
+    // the window was computed (and trimmed) once by the geometry kernel: only the kept proto range is redone here
+    const KeptRange k = kept_range(boxes[slot], rx, ry, mw, mh);
+    const int4 wdw = reinterpret_cast<const int4*>(geom4)[slot];
+    g.x1d = k.x1d, g.y1d = k.y1d, g.x2d = k.x2d, g.y2d = k.y2d;
+    g.px0 = k.px0, g.py0 = k.py0, g.px1 = k.px1, g.py1 = k.py1;
+    g.x0 = wdw.x, g.y0 = wdw.y, g.w = wdw.z, g.h = wdw.w;
+  } else {
+    g = pm_geometry(boxes[slot], mh, mw, ih, iw, UPSAMPLE ? 1 : 0, rx, ry);
+  }
   if (g.w <= 0 || g.h <= 0) return;
   const int wpr = (g.w + 31) >> 5;
   const int oh = UPSAMPLE ? ih : mh, ow = UPSAMPLE ? iw : mw;
@@ -426,7 +437,7 @@ static EncodeTiledFn tensor_map_encoder() {
 
 int launch_process_mask_regions(const float* protos, const float* coef, const float* boxes, const int32_t* counts,
                                 int bs, int max_det, int nm, int mh, int mw, int ih, int iw, int upsample, float rx,
-                                float ry, float* out_dense, const int64_t* offsets, uint32_t* bits,
+                                float ry, float* out_dense, const int32_t* geom, const int64_t* offsets, uint32_t* bits,
                                 long long capacity_words, int32_t* status, void* workspace, size_t workspace_bytes,
                                 cudaStream_t stream) {
   const long long slots = (long long)bs * max_det;
@@ -464,7 +475,7 @@ int launch_process_mask_regions(const float* protos, const float* coef, const fl
   const bool packed = out_dense == nullptr;
 #define HDY_UP(P, U)                                                                                              \
   mask_upsample_pack_kernel<P, U><<<g2, kUpWarps * 32, 0, stream>>>(W.patches, b4, counts, slots, max_det, mh, mw, \
-                                                                    ih, iw, rx, ry, out_dense, offsets, bits,      \
+                                                                    ih, iw, rx, ry, out_dense, geom, offsets, bits, \
                                                                     capacity_words, status, W.large_count,         \
                                                                     W.large_list)
   if (packed && upsample)

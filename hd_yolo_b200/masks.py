@@ -229,7 +229,8 @@ def process_mask_packed(protos: torch.Tensor, coef: torch.Tensor, boxes: torch.T
     if K:
         ws, wbytes = _pm_workspace(dev, bs, md)
         _call("hdy_process_mask_packed", ptr(_aligned16(protos.contiguous())), ptr(coef.contiguous()), ptr(boxes),
-              ptr(counts), ptr(offsets), bs, md, nm, mh, mw, ih, iw, int(bool(upsample)), ptr(bits), words, ptr(status),
+              ptr(counts), ptr(geom), ptr(offsets), bs, md, nm, mh, mw, ih, iw, int(bool(upsample)), ptr(bits), words,
+              ptr(status),
               ptr(ws), wbytes, _stream(), launches=3)
     oh, ow = (ih, iw) if upsample else (mh, mw)
     return PackedMasks(geom, offsets, bits[:words], oh, ow, status)

@@ -224,12 +224,13 @@ HDY_API size_t hdy_process_mask_workspace_bytes(int bs, int max_det);
 HDY_API int hdy_process_mask(const float* protos, const float* coef, const float* boxes, const int32_t* counts,
                              int bs, int max_det, int nm, int mh, int mw, int ih, int iw, int upsample, float* out,
                              void* workspace, size_t workspace_bytes, hdy_stream_t stream);
-/* Cropped bit-packed variant; geom [bs*max_det, 4], offsets [bs*max_det + 1] as above (slots >= counts are empty). */
+/* Cropped bit-packed variant; geom [bs*max_det, 4], offsets [bs*max_det + 1] as above (slots >= counts are empty).
+ * hdy_process_mask_packed takes the geom array hdy_process_mask_geometry wrote (NULL: windows are recomputed). */
 HDY_API int hdy_process_mask_geometry(const float* boxes, const int32_t* counts, int bs, int max_det, int mh, int mw,
                                       int ih, int iw, int upsample, int32_t* geom, int64_t* offsets,
                                       hdy_stream_t stream);
 HDY_API int hdy_process_mask_packed(const float* protos, const float* coef, const float* boxes,
-                                    const int32_t* counts, const int64_t* offsets, int bs, int max_det, int nm,
+                                    const int32_t* counts, const int32_t* geom, const int64_t* offsets, int bs, int max_det, int nm,
                                     int mh, int mw, int ih, int iw, int upsample, uint32_t* bits,
                                     int64_t capacity_words, int32_t* status, void* workspace, size_t workspace_bytes,
                                     hdy_stream_t stream);

@@ -230,3 +230,42 @@ def test_paste_other_mask_sizes(cuda_device, M):
     assert float((out - ref).abs().max()) < ATOL
     packed = hm.paste_masks_packed(masks.to(cuda_device), boxes.to(cuda_device), (H, W), padding=1)
     assert _agreement(packed.to_dense().cpu(), (ref[:, 0] > 0.5).to(torch.uint8)) >= AGREE
+
+
+@pytest.mark.parametrize("ih,iw,mh,mw,seed", [(640, 640, 160, 160, 0), (320, 480, 80, 120, 1), (300, 500, 100, 125, 2)])
+def test_process_mask_window_holds_every_set_pixel(cuda_device, ih, iw, mh, mw, seed):
+    """The packed window is trimmed to the pixels that can exceed 0.5 (mask_common.cuh pm_trim): no pixel the oracle
+    sets may fall outside it, including saturated masks (sigmoid == 1), boxes on the image border and non-integer
+    scales, and the bits inside must be the oracle's."""
+    g = torch.Generator().manual_seed(seed)
+    k = 240
+    protos = torch.randn((32, mh, mw), generator=g) * 3.0
+    protos[0] += 40.0                                              # with coef[:, 0] = 1: saturated everywhere
+    coef = torch.randn((k, 32), generator=g) * 0.5
+    coef[::3, 0] = 1.0
+    c = torch.rand((k, 2), generator=g) * torch.tensor([iw, ih])
+    s = torch.rand((k, 2), generator=g) * 50 + 6
+    boxes = torch.cat([c - s / 2, c + s / 2], 1)
+    boxes[:8] = torch.tensor([[-5., -5., 20., 20.], [iw - 20., ih - 20., iw + 9., ih + 9.], [0., 0., 33., 17.],
+                              [iw - 31., 0., iw, 12.], [0., ih - 9., 40., ih], [100.5, 60.25, 131.75, 91.0],
+                              [10., 10., 14., 14.], [200., 100., 203., 260.]])
+    ref = port.process_mask(protos, coef, boxes.clone(), (ih, iw), upsample=True)        # [k, ih, iw] 0/1
+    counts = torch.tensor([k], dtype=torch.int32)
+    pm = hm.process_mask_packed(protos[None].to(cuda_device), coef[None].to(cuda_device), boxes[None].to(cuda_device),
+                                counts.to(cuda_device), (ih, iw), upsample=True)
+    pm.check()
+    geom = pm.geom.cpu()
+    dense = pm.to_dense().cpu()
+    assert _agreement(dense, ref.to(torch.uint8)) >= AGREE
+    n_two_words = 0
+    for i in range(k):
+        x0, y0, w, h = geom[i].tolist()
+        nz = torch.nonzero(ref[i])
+        if len(nz):
+            assert y0 <= int(nz[:, 0].min()) and int(nz[:, 0].max()) < y0 + h, (i, geom[i].tolist())
+            assert x0 <= int(nz[:, 1].min()) and int(nz[:, 1].max()) < x0 + w, (i, geom[i].tolist())
+        n_two_words += w > 32
+    # saturated masks fill their window up to the trimmed edge: the trim is tight, not just safe
+    sat = [i for i in range(9, k, 3) if geom[i, 2] > 0 and boxes[i, 0] > 8 and boxes[i, 2] < iw - 8]
+    tight = sum(int(ref[i, :, geom[i, 0]].any()) + int(ref[i, :, geom[i, 0] + geom[i, 2] - 1].any()) for i in sat)
+    assert tight >= 1.6 * len(sat)
