@@ -137,6 +137,7 @@ class DeviceMergeBackend:
 
     def finish(self) -> Tuple[torch.Tensor, bool]:
         """-> (verdict per own row [n_local] uint8, converged)"""
+        self.status.zero_()
         self._call("hdy_merge_finish", self._ptr(self.ws), None, self.n, self._ptr(self.state), self._ptr(self.status),
                    self._stream())
         ok = not (int(self.status.item()) & 2)
@@ -254,14 +255,18 @@ class ShardedMerge:
 
     # phase 5 ------------------------------------------------------------------------------------
     def finish(self) -> torch.Tensor:
-        left = MAX_ROUNDS - self.round
-        if left > 0:
-            self.backend.rounds(self.round, left)     # rounds exit at once when nothing is undecided
-            self.round = MAX_ROUNDS
-        state, ok = self.backend.finish()
-        if not ok:
-            raise RuntimeError("sharded merge: undecided rows left after the round budget")
-        return state
+        # rows away from the seams may still be undecided: a few rounds at a time, one status read each (launching the
+        # whole remaining budget costs ~0.7 ms of no-op kernels per slide)
+        while True:
+            n = min(ROUNDS_PER_EXCHANGE, MAX_ROUNDS - self.round)
+            if n > 0:
+                self.backend.rounds(self.round, n)
+                self.round += n
+            state, ok = self.backend.finish()
+            if ok:
+                return state
+            if self.round >= MAX_ROUNDS:
+                raise RuntimeError("sharded merge: undecided rows left after the round budget")
 
 
 # ------------------------------------------------------------------------------------------------ drivers

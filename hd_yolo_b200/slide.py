@@ -114,7 +114,7 @@ def rescale_outputs(r: Dict[str, torch.Tensor], scale: float = 1.0) -> Dict[str,
 def merge_nms(boxes: torch.Tensor, scores: torch.Tensor, conf_thres: float, iou_thres: float,
               tile_id: Optional[torch.Tensor] = None, cores: Optional[torch.Tensor] = None,
               margin: Optional[torch.Tensor] = None, n_dev: Optional[torch.Tensor] = None,
-              max_rounds: int = 24, dirty: Optional[torch.Tensor] = None) -> torch.Tensor:
+              max_rounds: int = 8, dirty: Optional[torch.Tensor] = None) -> torch.Tensor:
     """Verdict per row of the slide-level greedy NMS of Ensemble.merge (yolo.py:189-195):
     uint8 [n] of STATE_KEPT / STATE_SUPPRESSED / STATE_DROPPED (score <= conf_thres).
     tile_id + cores + margin enable the interior shortcut (see include/hd_yolo_b200.h)."""

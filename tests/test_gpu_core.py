@@ -268,6 +268,37 @@ def test_extra_channels_are_carried(cuda_device):
         assert torch.equal(out.extra[i, :k].cpu(), cat[i, rows, 9:])
 
 
+@pytest.mark.parametrize("kernel", ["tma", "sparse"])
+@pytest.mark.parametrize("tile,bs,n_cand,conf", [(320, 3, 500, 0.25), (640, 2, 1000, 0.15), (160, 5, 60, 0.5)])
+def test_wide_rows_filters_equal_two_step_path(cuda_device, monkeypatch, tile, bs, n_cand, conf, kernel):
+    """no = 41 (32 mask coefficients behind the scores), through the TMA streamer and through the sector-sparse filter
+    (decode.cu, HDY_FILTER=sparse): same survivors, boxes, scores, labels and rows as decode_concat -> nms_per_image on
+    the same logits, and as the oracle on the device-decoded rows; ragged last chunks (160-px tiles: 1200 + 300 + 75
+    rows) and a level that contributes nothing included."""
+    monkeypatch.setenv("HDY_FILTER", kernel)
+    dets = synth.nuclei_logits(bs, tile, 4, n_cand, seed=tile + bs, conf=conf, extra=32)
+    dets[0][bs - 1, ..., 4] = -20.0                                # last tile: level 0 contributes nothing
+    spec = hdy.HeadSpec(synth.ANCHORS_3, synth.STRIDES_3, nc=4, no=41)
+    d0 = [d.to(cuda_device) for d in dets]
+    raw = torch.cat([d.view(d.shape[0], -1, 41) for d in dets], 1)
+    one = hdy.detect_postprocess(d0, spec, conf, 0.45, 2000)
+    cat = hdy.decode_concat(d0, spec)
+    two = hdy.nms_per_image(cat, 4, conf, 0.45, 2000)
+    ref = port.nms_per_image(cat.cpu(), 4, conf, 0.45, 2000)
+    total = 0
+    for i, (t, r) in enumerate(zip(two, ref)):
+        k = int(one.counts[i])
+        total += k
+        assert k == len(t['boxes']) == len(r['boxes'])
+        assert torch.equal(one.boxes[i, :k], t['boxes']) and torch.equal(one.boxes[i, :k].cpu(), r['boxes'])
+        s, l = port.select_scores(r['scores'].clone(), conf, port.default_descendants(4))
+        assert torch.equal(one.scores[i, :k].cpu(), s) and torch.equal(one.labels[i, :k].cpu(), l)
+        assert torch.equal(one.levels[i, :k].cpu(), r['extra'][:, -1])      # the level-id column (yolo_head.py:311)
+        rows = one.rows[i, :k].cpu().long()
+        assert torch.equal(one.extra[i, :k].cpu(), raw[i, rows, 9:])        # raw coefficients ride along
+    assert total > bs * n_cand // 3
+
+
 def test_empty_and_overflow(cuda_device):
     spec = hdy.HeadSpec(synth.ANCHORS_3, synth.STRIDES_3, nc=4)
     dets = synth.nuclei_logits(2, 160, 4, 100, seed=9, conf=0.25)
