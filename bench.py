@@ -80,6 +80,9 @@ def parse():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-slide", action="store_true")
+    ap.add_argument("--layout", type=int, default=0, choices=[0, 1],
+                    help="tiles workloads: 0 = the reference's permuted [bs,na,ny,nx,no] head tensors, 1 = the 1x1 "
+                         "conv's native [bs,na*no,ny,nx] output (the yolo_head.py:141-145 permute copy skipped)")
     ap.add_argument("--slide-streams", type=int, default=3,
                     help="slide workload: tile batches alternate over this many streams (SlidePostprocessor(streams=))")
     ap.add_argument("--inflight", type=int, default=3, help="steps in flight (CUDA graphs on separate streams)")
@@ -329,6 +332,9 @@ def run_tiles(args, wl, c):
     R = max(2, args.inflight, int(2.5 * L2_BYTES / in_bytes) + 1)   # rotate input batches so that reads miss L2
     batches = [synth.nuclei_logits(bs, tile, nc, wl["n_cand"], seed=1000 * c.rank + r, conf=wl["conf"], extra=extra,
                                    generator_device="cuda") for r in range(R)]
+    if args.layout == 1:   # the same logits as the head's 1x1 conv leaves them: [bs, na*no, ny, nx]
+        batches = [[d.permute(0, 1, 4, 2, 3).reshape(d.shape[0], -1, d.shape[2], d.shape[3]).contiguous() for d in b]
+                   for b in batches]
     protos = None
     if masks == "proto":
         g = torch.Generator(device="cuda").manual_seed(77 + c.rank)
@@ -346,7 +352,7 @@ def run_tiles(args, wl, c):
 
     def step(i, dets=None, pr=None):
         out = hdy.detect_postprocess(dets if dets is not None else batches[i % R], spec, wl["conf"], wl["iou"],
-                                     wl["max_det"], cap=wl["cap"])
+                                     wl["max_det"], cap=wl["cap"], layout=args.layout)
         pm = None
         if masks == "proto":
             pm = hmasks.process_mask_packed(pr if pr is not None else protos[i % R], out.extra, out.boxes, out.counts,
@@ -417,7 +423,9 @@ def run_tiles(args, wl, c):
     kept = float(out.counts.float().mean())
     ne = spec.no - 5 - nc
     alg = {   # algorithmic bytes per launch
-        "hdy_filter_compact_logits": bs * (4 * N * spec.no + 24 * cand),
+        # layout 1: only the objectness plane is streamed, survivors gather their four box logits
+        "hdy_filter_compact_logits": bs * (4 * N * spec.no + 24 * cand) if args.layout == 0
+        else bs * (4 * N + (16 + 24) * cand),
         "hdy_nms_tiles": bs * (24 * cand + 28 * kept),
         "hdy_gather_logits": bs * kept * (4 * (1 + nc + ne) * 2 + 4),
         "hdy_gather_select_logits": bs * kept * (4 * (1 + nc + ne) * 2 + 4 + 4 + 8),
@@ -498,6 +506,8 @@ def run_tiles(args, wl, c):
         "warmup": W, "ms_per_step": ms / K, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f32", "data": "synthetic",
         "config": {"workload": args.workload, "tile": tile, "tiles_per_step_per_gpu": bs, "levels": 3,
+                   "layout": "permuted [bs,na,ny,nx,no] (what the reference's Detect.forward hands over)"
+                   if args.layout == 0 else "conv-native [bs,na*no,ny,nx] (yolo_head.py:141-145 permute skipped)",
                    "rows_per_tile": N, "channels": spec.no, "prototypes": NM if masks == "proto" else 0,
                    "candidates_per_tile": round(cand, 1), "kept_per_tile": round(kept, 1), "conf": wl["conf"],
                    "iou": wl["iou"], "max_det": wl["max_det"], "cap": wl["cap"],

@@ -558,7 +558,21 @@ __global__ void __launch_bounds__(256) gather_select_logits_kernel(
     if (out_level) out_level[o] = (float)l;
   }
   // raw extra channels (mask coefficients): the whole warp copies one survivor's run at a time, coalesced
-  if (out_extra && ne > 0) {
+  if (out_extra && ne > 0 && ne <= 32) {
+    // all of the warp's survivors at once: SPW scattered loads per lane are in flight together (one round trip to L2 /
+    // HBM instead of SPW; in the conv-native layout every coefficient of a row lives in a different plane)
+    const unsigned long long rp_bits = (unsigned long long)(uintptr_t)rp;
+    float v[SPW];
+#pragma unroll
+    for (int j = 0; j < SPW; ++j) {
+      const float* rj = (const float*)(uintptr_t)__shfl_sync(0xffffffffu, rp_bits, j * G);
+      const int csj = __shfl_sync(0xffffffffu, cs, j * G);
+      v[j] = (d0 + j < k && lane < ne) ? __ldg(rj + (size_t)(5 + nc + lane) * csj) : 0.f;
+    }
+#pragma unroll
+    for (int j = 0; j < SPW; ++j)
+      if (d0 + j < k && lane < ne) out_extra[((size_t)tile * max_det + d0 + j) * ne + lane] = v[j];
+  } else if (out_extra && ne > 0) {
     const unsigned long long rp_bits = (unsigned long long)(uintptr_t)rp;
 #pragma unroll
     for (int j = 0; j < SPW; ++j) {

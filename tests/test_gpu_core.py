@@ -268,7 +268,7 @@ def test_extra_channels_are_carried(cuda_device):
         assert torch.equal(out.extra[i, :k].cpu(), cat[i, rows, 9:])
 
 
-@pytest.mark.parametrize("kernel", ["tma", "sparse"])
+@pytest.mark.parametrize("kernel", ["tma", "sparse", "planar", "generic"])
 @pytest.mark.parametrize("tile,bs,n_cand,conf", [(320, 3, 500, 0.25), (640, 2, 1000, 0.15), (160, 5, 60, 0.5)])
 def test_wide_rows_filters_equal_two_step_path(cuda_device, monkeypatch, tile, bs, n_cand, conf, kernel):
     """no = 41 (32 mask coefficients behind the scores), through the TMA streamer and through the sector-sparse filter
@@ -276,12 +276,15 @@ def test_wide_rows_filters_equal_two_step_path(cuda_device, monkeypatch, tile, b
     the same logits, and as the oracle on the device-decoded rows; ragged last chunks (160-px tiles: 1200 + 300 + 75
     rows) and a level that contributes nothing included."""
     monkeypatch.setenv("HDY_FILTER", kernel)
+    layout = 1 if kernel in ("planar", "generic") else 0          # conv-native [bs, na*no, ny, nx]: same logits
     dets = synth.nuclei_logits(bs, tile, 4, n_cand, seed=tile + bs, conf=conf, extra=32)
     dets[0][bs - 1, ..., 4] = -20.0                                # last tile: level 0 contributes nothing
     spec = hdy.HeadSpec(synth.ANCHORS_3, synth.STRIDES_3, nc=4, no=41)
     d0 = [d.to(cuda_device) for d in dets]
     raw = torch.cat([d.view(d.shape[0], -1, 41) for d in dets], 1)
-    one = hdy.detect_postprocess(d0, spec, conf, 0.45, 2000)
+    src = d0 if layout == 0 else [d.permute(0, 1, 4, 2, 3).reshape(d.shape[0], -1, d.shape[2], d.shape[3]).contiguous()
+                                  for d in d0]
+    one = hdy.detect_postprocess(src, spec, conf, 0.45, 2000, layout=layout)
     cat = hdy.decode_concat(d0, spec)
     two = hdy.nms_per_image(cat, 4, conf, 0.45, 2000)
     ref = port.nms_per_image(cat.cpu(), 4, conf, 0.45, 2000)
