@@ -474,14 +474,44 @@ def run_tiles(args, wl, c):
             h["offsets"] = torch.empty(tuple(pm.offsets.shape), dtype=torch.int64).pin_memory()
             h["bits"] = torch.empty((state["cap_words"],), dtype=torch.int32).pin_memory()
 
-        g_e2e = hdy.CapturedStep(lambda: step(0, stage, stage_p))
+        # Two staging sets and two graphs: the H2D copy of step i+1 runs on a copy stream while step i computes and
+        # reads back (PCIe is full duplex), as a serving loop would; every byte of every step is still copied inside
+        # the timed region.
+        stage2 = [torch.empty_like(d) for d in batches[0]]
+        stage_p2 = torch.empty_like(second[0]) if second is not None else None
+        stages_e = [(stage, stage_p), (stage2, stage_p2)]
+        graphs_e = [hdy.CapturedStep(lambda: step(0, stage, stage_p), slot=0),
+                    hdy.CapturedStep(lambda: step(0, stage2, stage_p2), slot=1)]
+        copy_stream = torch.cuda.Stream()
+        ready = [None, None]     # H2D of the set finished
+        freed = [None, None]     # the graph that read the set finished
+
+        def issue_h2d(i):
+            k = i % 2
+            st, stp = stages_e[k]
+            with torch.cuda.stream(copy_stream):
+                if freed[k] is not None:
+                    copy_stream.wait_event(freed[k])
+                for s, hh in zip(st, host[i % 2]):
+                    s.copy_(hh, non_blocking=True)
+                if stp is not None:
+                    stp.copy_(host_p[i % 2], non_blocking=True)
+                ready[k] = torch.cuda.Event()
+                ready[k].record(copy_stream)
+
+        pending = {"next": None}
 
         def e2e_step(i):
-            for s, hh in zip(stage, host[i % 2]):
-                s.copy_(hh, non_blocking=True)
-            if stage_p is not None:
-                stage_p.copy_(host_p[i % 2], non_blocking=True)
-            o, p = g_e2e()
+            if pending["next"] != i:      # first step of a run: nothing was prefetched
+                issue_h2d(i)
+            k = i % 2
+            cur = torch.cuda.current_stream()
+            cur.wait_event(ready[k])
+            o, p = graphs_e[k]()
+            freed[k] = torch.cuda.Event()
+            freed[k].record(cur)
+            issue_h2d(i + 1)              # overlaps the read-back below and the next replay's wait
+            pending["next"] = i + 1
             h["boxes"].copy_(o.boxes, non_blocking=True)
             h["scores"].copy_(o.scores, non_blocking=True)
             h["labels"].copy_(o.labels, non_blocking=True)
@@ -494,11 +524,13 @@ def run_tiles(args, wl, c):
         Ke = max(3, min(K, 50))
         for i in range(3):
             e2e_step(i)
-        ms_e = c.timed(e2e_step, Ke)
+        pending["next"] = None
+        torch.cuda.synchronize()
+        ms_e = c.timed(e2e_step, Ke, side_streams=(copy_stream,))
         d2h = sum(t.numel() * t.element_size() for k, t in h.items() if k != "bits") + (words * 4 if pm is not None else 0)
         e2e = {"value": c.world * bs * Ke / (ms_e * 1e-3), "unit": "tiles/s", "h2d_bytes_per_step": in_bytes,
                "d2h_bytes_per_step": d2h, "steps": Ke, "ms_per_step": ms_e / Ke}
-        del host, host_p, stage, stage_p, h, g_e2e
+        del host, host_p, stage, stage_p, stage2, stage_p2, stages_e, graphs_e, h
     clocks = sampler.stop()
 
     line = {
