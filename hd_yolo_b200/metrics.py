@@ -14,7 +14,6 @@ from typing import Dict, Optional
 import numpy as np
 import torch
 
-from . import _lib
 from ._lib import HdyError, ptr
 from .ops import _Cand, _aligned16, _call, _need_cuda, _run_nms, _stream
 

@@ -8,7 +8,6 @@ CPU op's operation order (bit-identical on finite inputs); CUDA tensors only.
 """
 from __future__ import annotations
 
-import ctypes as C
 from typing import List, Optional, Sequence, Union
 
 import torch
