@@ -46,7 +46,8 @@ from .slide import (  # noqa: F401,E402
     tile_cores,
 )
 
-from . import dist, hnet, metrics, pipeline, roi  # noqa: F401,E402
+from . import dist, hnet, io, metrics, pipeline, roi  # noqa: F401,E402
+from .io import load_detections, save_detections  # noqa: F401,E402
 from .metrics import APMeter, box_iou, match_predictions  # noqa: F401,E402
 from .roi import batch_rois, multiscale_roi_align, roi_align  # noqa: F401,E402
 from .pipeline import SlidePostprocessor  # noqa: F401,E402
