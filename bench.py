@@ -236,6 +236,12 @@ class Ctx:
     pass
 
 
+try:
+    _ORIG_AFFINITY = os.sched_getaffinity(0)
+except Exception:   # not on Linux
+    _ORIG_AFFINITY = set()
+
+
 def bind_to_gpu_numa_node(index):
     """Pin this process to the CPUs next to GPU `index` (sysfs local_cpulist of its PCI function) before any pinned
     host buffer is allocated: first-touch then places the e2e staging buffers on the GPU's own NUMA node, which is
@@ -702,6 +708,10 @@ def main():
             line["slide"] = run_slide(sargs, WORKLOADS["slide"], c, steps=3, warmup=2, want_e2e=False)
 
     cpu = None
+    try:   # the CPU legs use every core the process started with, not just the GPU's NUMA node
+        os.sched_setaffinity(0, _ORIG_AFFINITY)
+    except Exception:
+        pass
     if c.rank == 0 and not args.no_cpu_baseline:
         masks = args.masks if args.workload != "slide" else "none"
         v, cores, sample = time_cpu(wl, masks, budget_s=15.0, max_reps=30)
