@@ -208,6 +208,43 @@ def time_cpu(wl, masks, budget_s, max_reps, threads=None):
         f"{sample} tiles x {reps} passes of oracle/port.py ({what}; torch {torch.__version__} CPU + torchvision nms)")
 
 
+def cpu_merge_scaling(boxes, scores, tile, n_cols, conf, iou, grids=(2, 3, 4, 6, 8), budget_s=25.0):
+    """the reference's slide merge (Ensemble.merge, yolo.py:165-204 = one dense torchvision.ops.nms over
+    everything merge_outputs concatenated) is O(n^2) -- 338 s at 2e5 boxes -- so it is timed on g x g tile sub-slides
+    of the SAME detections and reported with its measured exponent instead of an extrapolated full-slide number.
+    boxes [n,4] / scores [n] / tile [n] (tile index in the slide's row-major grid of n_cols columns): CPU tensors in
+    merge_outputs' order.  Returns a dict for the JSON line."""
+    import math
+    import torch
+    from oracle import port
+    torch.set_num_threads(os.cpu_count() or 1)
+    rows, cols = tile // n_cols, tile % n_cols
+    pts, t_start = [], time.perf_counter()
+    for g in grids:
+        sel = (rows < g) & (cols < g)
+        b, sc = boxes[sel].contiguous(), scores[sel].contiguous()
+        if len(b) < 16:
+            continue
+        if pts and time.perf_counter() - t_start + pts[-1][2] * (len(b) / pts[-1][1]) ** 2 > budget_s:
+            break                                   # the next size would not fit the budget
+        labels = torch.zeros((len(b),), dtype=torch.int64)
+        t0 = time.perf_counter()
+        r = port.ensemble_merge([{'det': {'boxes': b, 'scores': sc, 'labels': labels}}],
+                                {'conf_thres': conf, 'iou_thres': iou, 'max_det': 10 ** 9})['det']
+        pts.append((g * g, int(len(b)), time.perf_counter() - t0, int(len(r['boxes']))))
+    out = {"what": "oracle port of Ensemble.merge (dense torchvision.ops.nms) on g x g tile sub-slides of the bench's "
+                   "own detections, all host threads", "cores": torch.get_num_threads(),
+           "tiles": [p[0] for p in pts], "boxes": [p[1] for p in pts], "seconds": [round(p[2], 4) for p in pts],
+           "kept": [p[3] for p in pts]}
+    if len(pts) >= 2:
+        xs = [math.log(p[1]) for p in pts]
+        ys = [math.log(max(p[2], 1e-9)) for p in pts]
+        mx, my = sum(xs) / len(xs), sum(ys) / len(ys)
+        den = sum((x - mx) ** 2 for x in xs)
+        out["exponent"] = round(sum((x - mx) * (y - my) for x, y in zip(xs, ys)) / den, 3) if den > 0 else None
+    return out
+
+
 def run_reference(args, wl):
     """--impl reference: the reference's own CPU implementation (oracle port: same torch/torchvision calls) on all
     host threads; each step is a bounded sample of the workload."""
@@ -572,7 +609,7 @@ def run_tiles(args, wl, c):
 
 
 # ------------------------------------------------------------------------------------------------ slide workload
-def run_slide(args, wl, c, steps, warmup, want_e2e):
+def run_slide(args, wl, c, steps, warmup, want_e2e, want_cpu_merge=False):
     import torch
     import hd_yolo_b200 as hdy
     from hd_yolo_b200 import ops, synth
@@ -612,6 +649,17 @@ def run_slide(args, wl, c, steps, warmup, want_e2e):
     r = res["r"]
     n_local = int(r["n"])
     kept_local = int((r["state"] == 1).sum())
+    cpu_merge = None
+    if want_cpu_merge and c.rank == 0 and c.world == 1:
+        try:   # a reported baseline must never take the GPU record down with it
+            n_cols = int((post.rois[:, 1] == post.rois[0, 1]).sum())        # tiles in the first grid row
+            tl = post.acc.tile[:n_local]
+            tl = torch.where(tl >= 0, tl, ~tl).to(torch.int64)              # fragile rows carry ~tile
+            sub = ((tl // n_cols) < 8) & ((tl % n_cols) < 8)      # the largest sub-slide cpu_merge_scaling may time
+            cpu_merge = cpu_merge_scaling(post.acc.boxes[:n_local][sub].cpu(), post.acc.scores[:n_local][sub].cpu(),
+                                          tl[sub].cpu(), n_cols, wl["conf"], wl["iou"])
+        except Exception as e:   # noqa: BLE001
+            cpu_merge = {"error": f"{type(e).__name__}: {e}"}
     tot = torch.tensor([n_local, kept_local, in_bytes], dtype=torch.float64, device=c.dev)
     if c.world > 1:
         import torch.distributed as dist
@@ -621,6 +669,8 @@ def run_slide(args, wl, c, steps, warmup, want_e2e):
            "input_bytes": int(tot[2]), "slide_px": S, "tile": tile, "overlap": wl["overlap"],
            "seam_rows": r.get("seam_rows"), "exchanges": r.get("exchanges"), "gpu_launches": launches,
            "boxes_per_s": int(tot[0]) * steps / (ms * 1e-3)}
+    if cpu_merge is not None:
+        out["cpu_merge"] = cpu_merge
     if want_e2e:
         # host-resident head outputs: every batch is copied H2D inside the timed region (4 pinned host batches are
         # reused in rotation, bytes are counted for every copy), the slide's survivors are read back D2H
@@ -681,7 +731,8 @@ def main():
     if args.workload == "slide":
         sampler = ClockSampler(c.local)
         sampler.start()
-        s = run_slide(args, wl, c, args.steps, args.warmup, want_e2e=not args.no_e2e)
+        s = run_slide(args, wl, c, args.steps, args.warmup, want_e2e=not args.no_e2e,
+                      want_cpu_merge=not args.no_cpu_baseline)
         clocks = sampler.stop()
         # roofline of the dominant kernel on this workload's tiles: measured on a tiles1024 batch in the same process
         targs = argparse.Namespace(**vars(args))
@@ -705,7 +756,8 @@ def main():
         line = run_tiles(args, wl, c)
         if not args.no_slide:
             sargs = argparse.Namespace(**vars(args))
-            line["slide"] = run_slide(sargs, WORKLOADS["slide"], c, steps=3, warmup=2, want_e2e=False)
+            line["slide"] = run_slide(sargs, WORKLOADS["slide"], c, steps=3, warmup=2, want_e2e=False,
+                                      want_cpu_merge=not args.no_cpu_baseline)
 
     cpu = None
     try:   # the CPU legs use every core the process started with, not just the GPU's NUMA node
