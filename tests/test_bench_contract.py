@@ -32,3 +32,33 @@ def test_reference_arm_prints_one_json_line():
 def test_reference_arm_other_ranks_stay_silent():
     p = _run({"RANK": "1", "WORLD_SIZE": "2", "LOCAL_RANK": "1"})
     assert p.returncode == 0 and p.stdout.strip() == ""
+
+
+def test_cpu_merge_scaling_leg():
+    """The slide bench's CPU merge baseline: sub-slides are cut by tile index, every size is an exact
+    Ensemble.merge of its boxes, the exponent is fitted over the sizes that fit the budget."""
+    import importlib.util
+
+    import torch
+    import torchvision
+
+    spec = importlib.util.spec_from_file_location("bench_mod", os.path.join(ROOT, "bench.py"))
+    bench = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(bench)
+    g = torch.Generator().manual_seed(0)
+    n_cols, per = 5, 300
+    boxes, scores, tile = [], [], []
+    for t in range(n_cols * n_cols):
+        r, cc = divmod(t, n_cols)
+        c = torch.rand((per, 2), generator=g) * 1024 + torch.tensor([cc * 960., r * 960.])
+        s = 12 + 24 * torch.rand((per, 2), generator=g)
+        boxes.append(torch.cat([c - s / 2, c + s / 2], 1))
+        scores.append(0.2 + 0.7 * torch.rand(per, generator=g))
+        tile.append(torch.full((per,), t))
+    boxes, scores, tile = torch.cat(boxes), torch.cat(scores), torch.cat(tile)
+    out = bench.cpu_merge_scaling(boxes, scores, tile, n_cols, 0.25, 0.45, grids=(2, 3, 4))
+    assert out["tiles"] == [4, 9, 16] and out["boxes"] == [4 * per, 9 * per, 16 * per] and "exponent" in out
+    sel = ((tile // n_cols) < 2) & ((tile % n_cols) < 2)
+    b, sc = boxes[sel], scores[sel]
+    keep = sc > 0.25
+    assert out["kept"][0] == len(torchvision.ops.nms(b[keep], sc[keep], 0.45))
