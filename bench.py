@@ -627,7 +627,7 @@ def run_slide(args, wl, c, steps, warmup, want_e2e, want_cpu_merge=False):
     store = []
     for a in range(t0, t1, bs):
         b = min(a + bs, t1)
-        store.append(synth.slide_tile_logits(post.rois[a:b], tile, nc, seed=a, conf=wl["conf"], device=c.dev))
+        store.append(synth.slide_tile_logits(post.rois[a:b], tile, nc, seed=1, first_tile=a, conf=wl["conf"], device=c.dev))
     in_bytes = sum(sum(t.numel() * 4 for t in dets) for dets in store)
 
     def provider(a, b):

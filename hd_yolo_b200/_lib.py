@@ -15,6 +15,8 @@ HDY_MAX_ANCHORS = 8
 HDY_MAX_SCORES = 96
 HDY_STATUS_OVERFLOW = 1
 HDY_STATUS_ROUNDS = 2
+HDY_F32, HDY_F16 = 0, 1
+HDY_SEAM_HDR_WORDS, HDY_SEAM_FAR_WORDS, HDY_SEAM_ROW_WORDS, HDY_SEAM_META_WORDS, HDY_SEAM_MAX_WORLD = 16, 8, 6, 96, 64
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libhdyolo_b200.so")
@@ -34,6 +36,7 @@ class Level(C.Structure):
         ("stride", C.c_float),
         ("anchor_w", C.c_float * HDY_MAX_ANCHORS),
         ("anchor_h", C.c_float * HDY_MAX_ANCHORS),
+        ("dtype", C.c_int32),
     ]
 
 
@@ -75,11 +78,12 @@ SIGNATURES = {
     "hdy_paste_masks_packed": (_i, [_vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _i, _vp, C.c_int64, _vp, _vp]),
     "hdy_unpack_masks": (_i, [_vp, _vp, _vp, _i, _i, _i, _vp, _vp]),
     "hdy_process_mask_workspace_bytes": (_sz, [_i, _i]),
-    "hdy_process_mask": (_i, [_vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _i, _i, _vp, _vp, _sz, _vp]),
-    "hdy_process_mask_geometry": (_i, [_vp, _vp, _i, _i, _i, _i, _i, _i, _i, _vp, _vp, _vp]),
+    "hdy_process_mask": (_i, [_vp, _i, _vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _i, _i, _vp, _vp, _sz, _vp]),
+    "hdy_process_mask_geometry": (_i, [_vp, _vp, _i, _i, _i, _i, _i, _i, _i, _vp, _vp, _vp, _vp, _vp]),
+    "hdy_process_mask_rows": (_i, [_vp, _vp, _vp, _vp, _vp, _i, _i, _vp, _i, _vp, _vp, _vp]),
     "hdy_process_mask_packed": (
         _i,
-        [_vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _i, _i, _vp, C.c_int64, _vp, _vp, _sz, _vp],
+        [_vp, _i, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _i, _i, _vp, C.c_int64, _vp, _vp, _sz, _vp],
     ),
     "hdy_affine_boxes": (_i, [_vp, _i64, _i, _f, _f, _f, _f, _f, _f, _i, _vp]),
     "hdy_merge_append": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _f, _i64, _vp, _vp, _vp, _vp, _vp, _vp, _vp,
@@ -95,6 +99,13 @@ SIGNATURES = {
     "hdy_merge_export_states": (_i, [_vp, _i64, _vp, _vp, _i64, _vp, _vp]),
     "hdy_merge_import_states": (_i, [_vp, _i64, _i64, _vp, _i64, _vp]),
     "hdy_merge_finish": (_i, [_vp, _vp, _i64, _vp, _vp, _vp]),
+    "hdy_seam_summary": (_i, [_vp, _i64, _vp, _vp, _vp, _vp, _i, _i, _i, _vp, _vp]),
+    "hdy_seam_select": (_i, [_vp, _vp, _i64, _vp, _i, _i, _i, _i, _vp, _vp, _vp, _vp]),
+    "hdy_seam_scatter": (_i, [_vp, _vp, _i, _i, _i, _i, _i64, _i64, _vp, _vp, _vp, _vp, _vp]),
+    "hdy_seam_dirty_tiles": (_i, [_vp, _i, _i, _vp, _i, _vp, _vp]),
+    "hdy_seam_build": (_i, [_vp, _vp, _vp, _vp, _vp, _i, _vp, _vp, _i64, _i64, _f, _f, _vp, _vp, _sz, _vp]),
+    "hdy_seam_export": (_i, [_vp, _i64, _vp, _vp, _vp, _i, _vp, _vp]),
+    "hdy_seam_import": (_i, [_vp, _i64, _i64, _vp, _vp, _vp, _i, _i, _i, _i, _vp]),
     "hdy_merge_select": (_i, [_vp, _vp, _vp, _i64, _vp, _vp, _vp]),
     "hdy_sort_workspace_bytes": (_sz, [_i64]),
     "hdy_sort_keys": (_i, [_vp, _vp, _vp, _i64, _vp, _sz, _vp]),

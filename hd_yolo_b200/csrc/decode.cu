@@ -490,7 +490,10 @@ __global__ void __launch_bounds__(kThreads) decode_kernel(const __grid_constant_
   const int plane = L.ny * L.nx;
   const int t = threadIdx.x;
   float* s = smem + 4;  // data region (phase-adjusted below)
-  if (T.layout == 0) {
+  if (T.layout == 0 && T.dtype == HDY_F16) {
+    const size_t e0 = ((size_t)tile * L.rows + row0) * no;
+    for (int e = t; e < rows * no; e += kThreads) s[e] = level_elem<true>(L.ptr, e0 + e);
+  } else if (T.layout == 0) {
     const float* g = L.ptr + ((size_t)tile * L.rows + row0) * no;
     s = smem + (((uintptr_t)g >> 2) & 3);
     stage_rows(g, s, rows * no);
@@ -617,6 +620,7 @@ int hdy_filter_compact_logits(const hdy_level_t* levels_host, int nl, int bs, in
   // at no = 41: 62.9 us against 58.3 us for the TMA streamer -- touching one 32-byte sector of every 164-byte row does
   // not make HBM deliver less than the whole rows, so it is not the default.
   const char* fsel = getenv("HDY_FILTER");
+  if (T.dtype == HDY_F16) fsel = nullptr;  // the experimental kernels read fp32 only
   const bool conf_ok = conf_thres > 1e-6f && conf_thres < 1.0f - 1e-6f;
   if (layout == 0 && conf_ok && fsel && fsel[0] == 's') {
     LevelTable S;
@@ -653,6 +657,8 @@ int hdy_filter_compact_logits(const hdy_level_t* levels_host, int nl, int bs, in
                                    counts, status, (cudaStream_t)stream);
     if (rc != 1) return rc;
   }
+  HDY_REQUIRE(T.dtype == HDY_F32, "fp16 logits need 16-byte aligned level tensors and 1e-6 < conf_thres < 1 - 1e-6 "
+                                  "(the TMA-staged filter is the only fp16 reader)");
   const size_t smem = layout == 0 ? stage_smem_bytes(no) : 0;
   rc = ensure_smem(filter_compact_logits_kernel, smem);
   if (rc) return rc;

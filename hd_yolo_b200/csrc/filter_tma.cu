@@ -47,19 +47,34 @@ __host__ __device__ constexpr size_t per_warp_bytes(int nbuf, int buf_bytes) {
   return (size_t)nbuf * buf_bytes + 2 * kQueueLen * 16 + 256 + 64;
 }
 
+template <bool HALF>
+struct LogitElem {
+  using type = float;
+};
+template <>
+struct LogitElem<true> {
+  using type = __half;
+};
+__device__ __forceinline__ float to_f32(float v) { return v; }
+__device__ __forceinline__ float to_f32(__half v) { return __half2float(v); }  // exact
+
 // WARPS independent streamers per CTA.  Per-warp shared memory: NBUF chunk buffers, NBUF mbarriers, one queue.
-template <int WARPS, int NBUF, int RPL>
+// HALF: the level tensors hold fp16 logits (a half() model's head, val_nuclei.py:115-116); they are widened to fp32 as
+// they are read from shared memory -- half the HBM bytes, the same arithmetic.
+template <int WARPS, int NBUF, int RPL, bool HALF>
 __global__ void __launch_bounds__(WARPS * 32) filter_compact_tma_kernel(
     const __grid_constant__ LevelTable T, const __grid_constant__ ItemTable I, int bs, int buf_bytes,
     float t_lo, float conf_thres, float min_size, int cap, uint64_t* __restrict__ cand_keys,
     float4* __restrict__ cand_boxes, int32_t* __restrict__ counts, int32_t* __restrict__ status) {
   extern __shared__ __align__(128) unsigned char smem_raw[];
+  using E = typename LogitElem<HALF>::type;
+  constexpr int kEsz = (int)sizeof(E);
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int no = T.no;
   constexpr int chunk_rows = 32 * RPL;
   const size_t per_warp = per_warp_bytes(NBUF, buf_bytes);
   unsigned char* base = smem_raw + (size_t)warp * per_warp;
-  float* bufs = reinterpret_cast<float*>(base);
+  E* bufs = reinterpret_cast<E*>(base);
   QueueA* qa = reinterpret_cast<QueueA*>(base + (size_t)NBUF * buf_bytes);
   QueueB* qb = reinterpret_cast<QueueB*>(base + (size_t)NBUF * buf_bytes + kQueueLen * 16);
   uint8_t* pick = base + (size_t)NBUF * buf_bytes + 2 * kQueueLen * 16;  // [256] chunk rows that passed phase A
@@ -77,7 +92,7 @@ __global__ void __launch_bounds__(WARPS * 32) filter_compact_tma_kernel(
   __syncwarp();
 
   struct Item {
-    const float* src;
+    const E* src;
     int rows, level, grow0;
   };
   auto item_at = [&](int j) -> Item {
@@ -89,12 +104,12 @@ __global__ void __launch_bounds__(WARPS * 32) filter_compact_tma_kernel(
     it.level = l;
     it.grow0 = (j - I.begin[l]) * chunk_rows;
     it.rows = min(chunk_rows, bs * T.lv[l].rows - it.grow0);
-    it.src = T.lv[l].ptr + (size_t)it.grow0 * no;
+    it.src = reinterpret_cast<const E*>(T.lv[l].ptr) + (size_t)it.grow0 * no;
     return it;
   };
   auto issue = [&](int k, int b) {  // lane 0 only: chunk k of this warp -> buffer b
     const Item it = item_at(gw + k * GW);
-    const uint32_t bytes = ((uint32_t)(it.rows * no) * 4u) & ~15u;
+    const uint32_t bytes = ((uint32_t)(it.rows * no) * (uint32_t)kEsz) & ~15u;
     mbar_arrive_expect_tx(&full[b], bytes);
     if (bytes) bulk_copy_g2s(reinterpret_cast<unsigned char*>(bufs) + (size_t)b * buf_bytes, it.src, bytes, &full[b]);
   };
@@ -191,13 +206,13 @@ __global__ void __launch_bounds__(WARPS * 32) filter_compact_tma_kernel(
   uint32_t parity = 0;
   for (int k = 0; k < n_my; ++k) {
     const Item w = item_at(gw + k * GW);
-    float* sm = reinterpret_cast<float*>(reinterpret_cast<unsigned char*>(bufs) + (size_t)b * buf_bytes);
+    E* sm = reinterpret_cast<E*>(reinterpret_cast<unsigned char*>(bufs) + (size_t)b * buf_bytes);
     const int nfl = w.rows * no;
-    const int avail = (nfl * 4 & ~15) >> 2;  // floats that arrive through the bulk copy
+    const int avail = (nfl * kEsz & ~15) / kEsz;  // elements that arrive through the bulk copy
     while (!mbar_try_wait(&full[b], parity)) {
     }
-    if (avail < nfl) {  // last chunk of a level whose size is not a multiple of 16 bytes: patch the <= 3 floats
-      if (lane < nfl - avail) sm[avail + lane] = __ldg(w.src + avail + lane);
+    if (avail < nfl) {  // last chunk of a level whose size is not a multiple of 16 bytes: patch the <= 3 (7) elements
+      if (lane < nfl - avail) sm[avail + lane] = w.src[avail + lane];
       __syncwarp();
     }
 
@@ -207,7 +222,7 @@ __global__ void __launch_bounds__(WARPS * 32) filter_compact_tma_kernel(
 #pragma unroll
     for (int g = 0; g < RPL; ++g) {
       const int rr = g * 32 + lane;
-      const bool pass = rr < w.rows && sm[rr * no + 4] >= t_lo;
+      const bool pass = rr < w.rows && to_f32(sm[rr * no + 4]) >= t_lo;
       const unsigned m = __ballot_sync(0xffffffffu, pass);
       if (pass) pick[total + __popc(m & lt_mask)] = (uint8_t)rr;
       total += __popc(m);
@@ -220,14 +235,14 @@ __global__ void __launch_bounds__(WARPS * 32) filter_compact_tma_kernel(
         const int j = j0 + lane;
         if (j < total) {
           const int rr = pick[j];
-          const float* r = sm + rr * no;
+          const E* r = sm + rr * no;
           QueueA A;
-          A.l0 = r[0];
-          A.l1 = r[1];
-          A.l2 = r[2];
-          A.l3 = r[3];
+          A.l0 = to_f32(r[0]);
+          A.l1 = to_f32(r[1]);
+          A.l2 = to_f32(r[2]);
+          A.l3 = to_f32(r[3]);
           QueueB B;
-          B.obj = r[4];
+          B.obj = to_f32(r[4]);
           const int grow = w.grow0 + rr;
           B.tile = grow / lrows;
           B.row = grow - B.tile * lrows;
@@ -250,12 +265,12 @@ __global__ void __launch_bounds__(WARPS * 32) filter_compact_tma_kernel(
   flush_pending();
 }
 
-template <int WARPS, int NBUF, int RPL>
-static int launch_variant(const LevelTable& T, const ItemTable& I, int bs, int buf_bytes, int ctas_per_sm,
+template <int WARPS, int NBUF, int RPL, bool HALF>
+static int launch_variant_t(const LevelTable& T, const ItemTable& I, int bs, int buf_bytes, int ctas_per_sm,
                           int sm_count, float t_lo, float conf_thres, float min_size, int cap, uint64_t* cand_keys,
                           float* cand_boxes, int32_t* counts, int32_t* status, cudaStream_t stream) {
   const size_t smem = per_warp_bytes(NBUF, buf_bytes) * WARPS;
-  cudaError_t e = cudaFuncSetAttribute(filter_compact_tma_kernel<WARPS, NBUF, RPL>,
+  cudaError_t e = cudaFuncSetAttribute(filter_compact_tma_kernel<WARPS, NBUF, RPL, HALF>,
                                        cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (e != cudaSuccess) {
     set_error("cudaFuncSetAttribute(filter_compact_tma_kernel): %s", cudaGetErrorString(e));
@@ -265,10 +280,21 @@ static int launch_variant(const LevelTable& T, const ItemTable& I, int bs, int b
   long long grid = (long long)sm_count * ctas_per_sm;
   const long long need = ((long long)total + WARPS - 1) / WARPS;
   if (grid > need) grid = need;
-  filter_compact_tma_kernel<WARPS, NBUF, RPL><<<(unsigned)grid, WARPS * 32, smem, stream>>>(
+  filter_compact_tma_kernel<WARPS, NBUF, RPL, HALF><<<(unsigned)grid, WARPS * 32, smem, stream>>>(
       T, I, bs, buf_bytes, t_lo, conf_thres, min_size, cap, cand_keys, reinterpret_cast<float4*>(cand_boxes),
       counts, status);
   return check_launch("hdy_filter_compact_logits(tma)");
+}
+
+template <int WARPS, int NBUF, int RPL>
+static int launch_variant(const LevelTable& T, const ItemTable& I, int bs, int buf_bytes, int ctas_per_sm,
+                          int sm_count, float t_lo, float conf_thres, float min_size, int cap, uint64_t* cand_keys,
+                          float* cand_boxes, int32_t* counts, int32_t* status, cudaStream_t stream) {
+  if (T.dtype == HDY_F16)
+    return launch_variant_t<WARPS, NBUF, RPL, true>(T, I, bs, buf_bytes, ctas_per_sm, sm_count, t_lo, conf_thres,
+                                                    min_size, cap, cand_keys, cand_boxes, counts, status, stream);
+  return launch_variant_t<WARPS, NBUF, RPL, false>(T, I, bs, buf_bytes, ctas_per_sm, sm_count, t_lo, conf_thres,
+                                                   min_size, cap, cand_keys, cand_boxes, counts, status, stream);
 }
 
 // Host side: returns HDY_OK, an error, or 1 when the layout does not meet the bulk-copy alignment rules
@@ -286,10 +312,11 @@ int launch_filter_compact_tma(const hdy_level_t* levels_host, int nl, int bs, in
   // rows per lane and chunk: 1, 2, 4 or 8, the largest whose chunk stays within kChunk bytes (9 KB chunks at no = 9,
   // 10.5 KB at no = 41: measured best on B200, smaller chunks pay the per-chunk handshake, larger ones leave too few
   // warps per SM)
-  int rpl = kChunk / (32 * no * 4);
+  const int esz = levels_host[0].dtype == HDY_F16 ? 2 : 4;
+  int rpl = kChunk / (32 * no * esz);
   rpl = rpl >= 8 ? 8 : (rpl >= 4 ? 4 : (rpl >= 2 ? 2 : 1));
   const int chunk_rows = 32 * rpl;
-  const int buf_bytes = (chunk_rows * no * 4 + 127) & ~127;
+  const int buf_bytes = (chunk_rows * no * esz + 127) & ~127;
   const size_t smem = per_warp_bytes(kNbuf, buf_bytes) * kWarps;
   if (smem > 227 * 1024) return 1;
   if (!(conf_thres > 1e-6f && conf_thres < 1.0f - 1e-6f)) return 1;  // logit(conf) is not finite enough

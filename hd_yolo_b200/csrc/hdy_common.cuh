@@ -1,5 +1,6 @@
 // Shared device/host helpers for the hd_yolo_b200 kernels (sm_100a only).
 #pragma once
+#include <cuda_fp16.h>
 #include <cuda_runtime.h>
 #include <stdint.h>
 #include <stdio.h>
@@ -137,7 +138,7 @@ __device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
 
 // Device-side copy of the level table (passed by value as a kernel parameter).
 struct LevelDev {
-  const float* ptr;
+  const float* ptr;  // fp16 levels (LevelTable::dtype == HDY_F16): the same address, read as __half
   int ny, nx;
   int rows;        // na*ny*nx rows per tile on this level
   int row_offset;  // first row of this level inside the concatenated [N] ordering
@@ -147,8 +148,15 @@ struct LevelDev {
 };
 struct LevelTable {
   LevelDev lv[HDY_MAX_LEVELS];
-  int nl, na, no, nc, N, chunks_per_tile, layout;
+  int nl, na, no, nc, N, chunks_per_tile, layout, dtype;
 };
+
+// element i of a level's tensor, widened to fp32 (exact)
+template <bool HALF>
+__device__ __forceinline__ float level_elem(const float* base, size_t i) {
+  if (HALF) return __half2float(reinterpret_cast<const __half*>(base)[i]);
+  return base[i];
+}
 
 // nms_smem.cu: one CTA per tile, tiles with at most 4096 candidates (others return at once)
 constexpr int kNmsSmemCap = 4096;

@@ -35,9 +35,12 @@ int build_level_table(const hdy_level_t* lv, int nl, int na, int no, int layout,
   for (int l = 0; l < nl; ++l) {
     HDY_REQUIRE(lv[l].logits != nullptr, "levels[%d].logits is NULL", l);
     HDY_REQUIRE(lv[l].ny > 0 && lv[l].nx > 0, "levels[%d] has empty grid", l);
-    HDY_REQUIRE(((uintptr_t)lv[l].logits & 3) == 0, "levels[%d].logits not 4-byte aligned", l);
+    HDY_REQUIRE(lv[l].dtype == HDY_F32 || lv[l].dtype == HDY_F16, "levels[%d].dtype must be HDY_F32 or HDY_F16", l);
+    HDY_REQUIRE(lv[l].dtype == lv[0].dtype, "levels disagree on dtype");
+    HDY_REQUIRE(lv[l].dtype == HDY_F32 || layout == 0, "fp16 logits are read in layout 0 ([bs,na,ny,nx,no]) only");
+    HDY_REQUIRE(((uintptr_t)lv[l].logits & (lv[l].dtype == HDY_F16 ? 1 : 3)) == 0, "levels[%d].logits misaligned", l);
     LevelDev& d = out->lv[l];
-    d.ptr = lv[l].logits;
+    d.ptr = static_cast<const float*>(lv[l].logits);
     d.ny = lv[l].ny;
     d.nx = lv[l].nx;
     long long rows = (long long)na * lv[l].ny * lv[l].nx;
@@ -59,6 +62,7 @@ int build_level_table(const hdy_level_t* lv, int nl, int na, int no, int layout,
   out->N = (int)row_off;
   out->chunks_per_tile = chunk;
   out->layout = layout;
+  out->dtype = lv[0].dtype;
   return HDY_OK;
 }
 

@@ -320,7 +320,8 @@ __global__ void unpack_masks_kernel(const int32_t* __restrict__ geom4, const int
   for (int e = threadIdx.x; e < g.z * g.w; e += blockDim.x) {
     const int yy = e / g.z, xx = e - yy * g.z;
     const uint32_t wd = bits[off + (long long)yy * wpr + (xx >> 5)];
-    o[(size_t)(g.y + yy) * W + g.x + xx] = (wd >> (xx & 31)) & 1u;
+    if (g.y + yy < H && g.x + xx < W && g.y + yy >= 0 && g.x + xx >= 0)   // windows are inside the canvas by
+      o[(size_t)(g.y + yy) * W + g.x + xx] = (wd >> (xx & 31)) & 1u;      // construction; never write beyond it
   }
 }
 
@@ -341,14 +342,16 @@ __global__ void pm_geometry_kernel(const float4* __restrict__ boxes, const int32
 // pm_geometry_kernel + scan_words_local_kernel in one launch (the step is a chain of small dependent kernels)
 __global__ void __launch_bounds__(kScanChunk) pm_geometry_scan_kernel(
     const float4* __restrict__ boxes, const int32_t* __restrict__ counts, long long K, int max_det, int mh, int mw,
-    int ih, int iw, int upsample, float rx, float ry, int32_t* __restrict__ geom4, int64_t* __restrict__ offsets) {
+    int ih, int iw, int upsample, float rx, float ry, const uint8_t* __restrict__ row_state,
+    const int64_t* __restrict__ tile_offsets, int32_t* __restrict__ geom4, int64_t* __restrict__ offsets) {
   __shared__ long long warp_sum[32];
   const long long i = (long long)blockIdx.x * kScanChunk + threadIdx.x;
   long long v = 0;
   if (i < K) {
     const int tile = (int)(i / max_det), d = (int)(i - (long long)tile * max_det);
     int4 out = make_int4(0, 0, 0, 0);
-    if (d < counts[tile]) {
+    // row_state: the slot is row tile_offsets[tile] + d of the slide; only rows the slide-level merge KEPT get a mask
+    if (d < counts[tile] && (!row_state || row_state[tile_offsets[tile] + d] == HDY_STATE_KEPT)) {
       const PMGeom g = pm_geometry(boxes[i], mh, mw, ih, iw, upsample, rx, ry);
       out = make_int4(g.x0, g.y0, g.w, g.h);
     }
@@ -362,6 +365,36 @@ __global__ void __launch_bounds__(kScanChunk) pm_geometry_scan_kernel(
   if (i == 0) offsets[0] = 0;
 }
 
+// Slide form of the packed layout: the batch's word offsets move behind the words of the earlier batches (device
+// cursor, ping-pong so that one launch both reads and advances it) and every live slot's window / offset is copied to
+// its slide row, the window shifted to slide pixels (x0 + roi.x0: bit positions inside the words do not change).
+__global__ void pm_rows_kernel(int32_t* __restrict__ geom4, int64_t* __restrict__ offsets,
+                               const int32_t* __restrict__ counts, const int64_t* __restrict__ tile_offsets,
+                               const float4* __restrict__ rois, long long K, int max_det,
+                               int64_t* __restrict__ cursor2, int parity, int32_t* __restrict__ geom_rows,
+                               int64_t* __restrict__ off_rows) {
+  const long long base = cursor2[parity & 1];
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i > K) return;
+  const long long o = offsets[i] + base;
+  offsets[i] = o;
+  if (i == K) {
+    cursor2[(parity + 1) & 1] = o;
+    return;
+  }
+  const int tile = (int)(i / max_det), d = (int)(i - (long long)tile * max_det);
+  if (d >= counts[tile]) return;
+  const long long row = tile_offsets[tile] + d;
+  int4 g = reinterpret_cast<const int4*>(geom4)[i];
+  if (g.z > 0 && g.w > 0) {
+    const float4 r = rois[tile];
+    g.x += (int)r.x;
+    g.y += (int)r.y;
+  }
+  reinterpret_cast<int4*>(geom_rows)[row] = g;
+  off_rows[row] = o;
+}
+
 constexpr int kPmTile = 32;               // proto pixels per staged tile side
 constexpr int kPmStage = kPmTile + 1;     // + 1 halo for the second bilinear tap
 constexpr int kPmThreads = 128;
@@ -370,11 +403,12 @@ constexpr int kPmThreads = 128;
 // cropped sigmoid(coef . proto) values are staged in shared memory (32 FFMA per pixel, channel-strided
 // coalesced reads that hit L2 after the first detection of a tile), then the output pixels whose first tap
 // falls into the block are emitted.
-template <bool PACKED>
+template <bool PACKED, bool HALF>
 __global__ void __launch_bounds__(kPmThreads) process_mask_kernel(
-    const float* __restrict__ protos, const float* __restrict__ coef, const float4* __restrict__ boxes,
+    const void* __restrict__ protos, const float* __restrict__ coef, const float4* __restrict__ boxes,
     const int32_t* __restrict__ counts, int max_det, int nm, int mh, int mw, int ih, int iw, int upsample,
-    float rx, float ry, float* __restrict__ out_dense, const int64_t* __restrict__ offsets,
+    float rx, float ry, float* __restrict__ out_dense, const int32_t* __restrict__ geom4,
+    const int64_t* __restrict__ offsets,
     uint32_t* __restrict__ bits, long long capacity_words, int32_t* __restrict__ status,
     const int32_t* __restrict__ slot_list, const int32_t* __restrict__ list_count) {
   __shared__ float stage[kPmStage * kPmStage];
@@ -387,6 +421,7 @@ __global__ void __launch_bounds__(kPmThreads) process_mask_kernel(
   const int tile = (int)(slot / max_det), d = (int)(slot - (long long)tile * max_det);
   __syncthreads();  // cf / stage of the previous item are free
   if (d >= counts[tile]) continue;
+  if (geom4 && (geom4[4 * slot + 2] <= 0 || geom4[4 * slot + 3] <= 0)) continue;  // empty, or not KEPT (slide form)
   const PMGeom g = pm_geometry(boxes[slot], mh, mw, ih, iw, upsample, rx, ry);
   if (g.w <= 0 || g.h <= 0) continue;
   const int oh = upsample ? ih : mh, ow = upsample ? iw : mw;
@@ -400,7 +435,7 @@ __global__ void __launch_bounds__(kPmThreads) process_mask_kernel(
     }
   }
   for (int c = threadIdx.x; c < nm; c += kPmThreads) cf[c] = coef[slot * nm + c];
-  const float* P = protos + (size_t)tile * nm * mh * mw;
+  const size_t P0 = (size_t)tile * nm * mh * mw;  // first element of the tile's prototypes
   const size_t plane = (size_t)mh * mw;
   const float sxs = (float)mw / (float)iw, sys = (float)mh / (float)ih;  // ATen: scale = in / out (fp32)
   // proto range that can contribute: the kept pixels, plus one pixel before (their second-tap neighbours)
@@ -414,10 +449,14 @@ __global__ void __launch_bounds__(kPmThreads) process_mask_kernel(
         float v = 0.f;
         if (yy < mh && xx < mw && (float)xx >= g.x1d && (float)xx < g.x2d && (float)yy >= g.y1d &&
             (float)yy < g.y2d) {
-          const float* p = P + (size_t)yy * mw + xx;
+          const size_t p = P0 + (size_t)yy * mw + xx;
           float acc = 0.f;
 #pragma unroll 8
-          for (int c = 0; c < nm; ++c) acc = fmaf(cf[c], __ldg(p + c * plane), acc);
+          for (int c = 0; c < nm; ++c) {
+            const float pv = HALF ? __half2float(__ldg(static_cast<const __half*>(protos) + p + c * plane))
+                                  : __ldg(static_cast<const float*>(protos) + p + c * plane);
+            acc = fmaf(cf[c], pv, acc);
+          }
           v = sigmoidf_ref(acc);
         }
         stage[e] = v;
@@ -460,20 +499,24 @@ __global__ void __launch_bounds__(kPmThreads) process_mask_kernel(
 }
 
 // used by mask_regions.cu for the detections its two-phase path leaves out
-int launch_process_mask_listed(const float* protos, const float* coef, const float* boxes, const int32_t* counts,
-                               int max_det, int nm, int mh, int mw, int ih, int iw, int upsample, float rx, float ry,
+int launch_process_mask_listed(const void* protos, int proto_dtype, const float* coef, const float* boxes,
+                               const int32_t* counts, int max_det, int nm, int mh, int mw, int ih, int iw, int upsample, float rx, float ry,
                                float* out_dense, const int64_t* offsets, uint32_t* bits, long long capacity_words,
                                int32_t* status, const int32_t* slot_list, const int32_t* list_count,
                                cudaStream_t st) {
   const unsigned grid = 148 * 4;
-  if (out_dense)
-    process_mask_kernel<false><<<grid, kPmThreads, 0, st>>>(protos, coef, reinterpret_cast<const float4*>(boxes), counts,
-                                                            max_det, nm, mh, mw, ih, iw, upsample, rx, ry, out_dense,
-                                                            nullptr, nullptr, 0, nullptr, slot_list, list_count);
-  else
-    process_mask_kernel<true><<<grid, kPmThreads, 0, st>>>(protos, coef, reinterpret_cast<const float4*>(boxes), counts,
-                                                           max_det, nm, mh, mw, ih, iw, upsample, rx, ry, nullptr,
-                                                           offsets, bits, capacity_words, status, slot_list, list_count);
+  const float4* b4 = reinterpret_cast<const float4*>(boxes);
+  const bool half = proto_dtype == HDY_F16;
+#define HDY_PM(P, H)                                                                                               \
+  process_mask_kernel<P, H><<<grid, kPmThreads, 0, st>>>(protos, coef, b4, counts, max_det, nm, mh, mw, ih, iw,    \
+                                                         upsample, rx, ry, out_dense, nullptr, offsets, bits,      \
+                                                         capacity_words, status, slot_list, list_count)
+  if (out_dense) {
+    if (half) HDY_PM(false, true); else HDY_PM(false, false);
+  } else {
+    if (half) HDY_PM(true, true); else HDY_PM(true, false);
+  }
+#undef HDY_PM
   return check_launch("hdy_process_mask(listed)");
 }
 
@@ -506,10 +549,11 @@ static int launch_paste(const float* src, const int32_t* channel, const float* b
   return check_launch("hdy_paste_masks");
 }
 
-static int pm_args_ok(const float* protos, const float* coef, const float* boxes, const int32_t* counts, int bs,
+static int pm_args_ok(const void* protos, int proto_dtype, const float* coef, const float* boxes, const int32_t* counts, int bs,
                       int max_det, int nm, int mh, int mw, int ih, int iw) {
   HDY_REQUIRE(bs >= 0 && max_det >= 1 && nm >= 1 && nm <= 64 && mh >= 1 && mw >= 1 && ih >= 1 && iw >= 1,
               "process_mask: bad sizes (nm must be <= 64)");
+  HDY_REQUIRE(proto_dtype == HDY_F32 || proto_dtype == HDY_F16, "process_mask: proto_dtype must be HDY_F32 or HDY_F16");
   if (bs > 0)
     HDY_REQUIRE(protos && coef && boxes && counts && ((uintptr_t)boxes & 15) == 0,
                 "process_mask: NULL or misaligned pointer");
@@ -593,10 +637,10 @@ size_t hdy_process_mask_workspace_bytes(int bs, int max_det) {
   return process_mask_workspace_bytes(bs > 0 ? bs : 0, max_det > 0 ? max_det : 0);
 }
 
-int hdy_process_mask(const float* protos, const float* coef, const float* boxes, const int32_t* counts, int bs,
-                     int max_det, int nm, int mh, int mw, int ih, int iw, int upsample, float* out, void* workspace,
-                     size_t workspace_bytes, hdy_stream_t stream) {
-  int rc = pm_args_ok(protos, coef, boxes, counts, bs, max_det, nm, mh, mw, ih, iw);
+int hdy_process_mask(const void* protos, int proto_dtype, const float* coef, const float* boxes,
+                     const int32_t* counts, int bs, int max_det, int nm, int mh, int mw, int ih, int iw, int upsample,
+                     float* out, void* workspace, size_t workspace_bytes, hdy_stream_t stream) {
+  int rc = pm_args_ok(protos, proto_dtype, coef, boxes, counts, bs, max_det, nm, mh, mw, ih, iw);
   if (rc) return rc;
   if (bs == 0) return HDY_OK;
   HDY_REQUIRE(out != nullptr, "hdy_process_mask: out is NULL");
@@ -608,20 +652,27 @@ int hdy_process_mask(const float* protos, const float* coef, const float* boxes,
     return HDY_ERR_CUDA;
   }
   const float rx = (float)((double)mw / (double)iw), ry = (float)((double)mh / (double)ih);
-  rc = launch_process_mask_regions(protos, coef, boxes, counts, bs, max_det, nm, mh, mw, ih, iw, upsample, rx, ry, out,
-                                   nullptr,
-                                   nullptr, nullptr, 0, nullptr, workspace, workspace_bytes, st);
+  rc = launch_process_mask_regions(protos, proto_dtype, coef, boxes, counts, bs, max_det, nm, mh, mw, ih, iw, upsample,
+                                   rx, ry, out, nullptr, nullptr, nullptr, 0, nullptr, workspace, workspace_bytes, st);
   if (rc != 1) return rc;
-  process_mask_kernel<false><<<(unsigned)((size_t)bs * max_det), kPmThreads, 0, st>>>(
-      protos, coef, reinterpret_cast<const float4*>(boxes), counts, max_det, nm, mh, mw, ih, iw, upsample, rx, ry,
-      out, nullptr, nullptr, 0, nullptr, nullptr, nullptr);
+  const float4* b4 = reinterpret_cast<const float4*>(boxes);
+  if (proto_dtype == HDY_F16)
+    process_mask_kernel<false, true><<<(unsigned)((size_t)bs * max_det), kPmThreads, 0, st>>>(
+        protos, coef, b4, counts, max_det, nm, mh, mw, ih, iw, upsample, rx, ry, out, nullptr, nullptr, nullptr, 0,
+        nullptr, nullptr, nullptr);
+  else
+    process_mask_kernel<false, false><<<(unsigned)((size_t)bs * max_det), kPmThreads, 0, st>>>(
+        protos, coef, b4, counts, max_det, nm, mh, mw, ih, iw, upsample, rx, ry, out, nullptr, nullptr, nullptr, 0,
+        nullptr, nullptr, nullptr);
   return check_launch("hdy_process_mask");
 }
 
 int hdy_process_mask_geometry(const float* boxes, const int32_t* counts, int bs, int max_det, int mh, int mw, int ih,
-                              int iw, int upsample, int32_t* geom, int64_t* offsets, hdy_stream_t stream) {
+                              int iw, int upsample, const uint8_t* row_state, const int64_t* tile_offsets,
+                              int32_t* geom, int64_t* offsets, hdy_stream_t stream) {
   HDY_REQUIRE(bs >= 0 && max_det >= 1 && mh >= 1 && mw >= 1 && ih >= 1 && iw >= 1, "process_mask_geometry: bad sizes");
   HDY_REQUIRE(offsets != nullptr, "process_mask_geometry: offsets is NULL");
+  HDY_REQUIRE(!row_state || tile_offsets, "process_mask_geometry: row_state needs tile_offsets");
   cudaStream_t st = (cudaStream_t)stream;
   const long long K = (long long)bs * max_det;
   if (K > 0) {
@@ -630,7 +681,8 @@ int hdy_process_mask_geometry(const float* boxes, const int32_t* counts, int bs,
     const float rx = (float)((double)mw / (double)iw), ry = (float)((double)mh / (double)ih);
     const unsigned nb = (unsigned)((K + kScanChunk - 1) / kScanChunk);
     pm_geometry_scan_kernel<<<nb, kScanChunk, 0, st>>>(reinterpret_cast<const float4*>(boxes), counts, K, max_det, mh,
-                                                       mw, ih, iw, upsample, rx, ry, geom, offsets);
+                                                       mw, ih, iw, upsample, rx, ry, row_state, tile_offsets, geom,
+                                                       offsets);
     if (nb > 1) {
       scan_words_bases_kernel<<<1, kScanChunk, 0, st>>>(K, offsets);
       scan_words_add_kernel<<<nb - 1, kScanChunk, 0, st>>>(K, offsets);
@@ -641,11 +693,27 @@ int hdy_process_mask_geometry(const float* boxes, const int32_t* counts, int bs,
   return check_launch("hdy_process_mask_geometry");
 }
 
-int hdy_process_mask_packed(const float* protos, const float* coef, const float* boxes, const int32_t* counts,
-                            const int32_t* geom, const int64_t* offsets, int bs, int max_det, int nm, int mh, int mw, int ih, int iw,
+int hdy_process_mask_rows(int32_t* geom, int64_t* offsets, const int32_t* counts, const int64_t* tile_offsets,
+                          const float* rois, int bs, int max_det, int64_t* cursor2, int parity, int32_t* geom_rows,
+                          int64_t* off_rows, hdy_stream_t stream) {
+  HDY_REQUIRE(bs >= 0 && max_det >= 1, "hdy_process_mask_rows: bad sizes");
+  if (bs == 0) return HDY_OK;
+  HDY_REQUIRE(geom && offsets && counts && tile_offsets && rois && cursor2 && geom_rows && off_rows,
+              "hdy_process_mask_rows: NULL pointer");
+  HDY_REQUIRE((((uintptr_t)geom | (uintptr_t)geom_rows | (uintptr_t)rois) & 15) == 0,
+              "hdy_process_mask_rows: geom / geom_rows / rois must be 16-byte aligned");
+  const long long K = (long long)bs * max_det;
+  pm_rows_kernel<<<(unsigned)((K + 1 + 255) / 256), 256, 0, (cudaStream_t)stream>>>(
+      geom, offsets, counts, tile_offsets, reinterpret_cast<const float4*>(rois), K, max_det, cursor2, parity,
+      geom_rows, off_rows);
+  return check_launch("hdy_process_mask_rows");
+}
+
+int hdy_process_mask_packed(const void* protos, int proto_dtype, const float* coef, const float* boxes,
+                            const int32_t* counts, const int32_t* geom, const int64_t* offsets, int bs, int max_det, int nm, int mh, int mw, int ih, int iw,
                             int upsample, uint32_t* bits, int64_t capacity_words, int32_t* status, void* workspace,
                             size_t workspace_bytes, hdy_stream_t stream) {
-  int rc = pm_args_ok(protos, coef, boxes, counts, bs, max_det, nm, mh, mw, ih, iw);
+  int rc = pm_args_ok(protos, proto_dtype, coef, boxes, counts, bs, max_det, nm, mh, mw, ih, iw);
   if (rc) return rc;
   if (bs == 0) return HDY_OK;
   HDY_REQUIRE(offsets && bits && status && capacity_words >= 0, "hdy_process_mask_packed: NULL pointer");
@@ -653,9 +721,9 @@ int hdy_process_mask_packed(const float* protos, const float* coef, const float*
   const float rx = (float)((double)mw / (double)iw), ry = (float)((double)mh / (double)ih);
   // two-phase path: every word of every mask is written exactly once, nothing to clear
   HDY_REQUIRE(!geom || ((uintptr_t)geom & 15) == 0, "hdy_process_mask_packed: geom must be 16-byte aligned");
-  rc = launch_process_mask_regions(protos, coef, boxes, counts, bs, max_det, nm, mh, mw, ih, iw, upsample, rx, ry,
-                                   nullptr, geom, offsets, bits, capacity_words, status, workspace, workspace_bytes,
-                                   st);
+  rc = launch_process_mask_regions(protos, proto_dtype, coef, boxes, counts, bs, max_det, nm, mh, mw, ih, iw, upsample,
+                                   rx, ry, nullptr, geom, offsets, bits, capacity_words, status, workspace,
+                                   workspace_bytes, st);
   if (rc != 1) return rc;
   // per-detection path: bits are OR-ed in, clear first (capacity is an upper bound the caller sized)
   cudaError_t e = cudaMemsetAsync(bits, 0, (size_t)capacity_words * 4, st);
@@ -663,9 +731,15 @@ int hdy_process_mask_packed(const float* protos, const float* coef, const float*
     set_error("cudaMemsetAsync: %s", cudaGetErrorString(e));
     return HDY_ERR_CUDA;
   }
-  process_mask_kernel<true><<<(unsigned)((size_t)bs * max_det), kPmThreads, 0, st>>>(
-      protos, coef, reinterpret_cast<const float4*>(boxes), counts, max_det, nm, mh, mw, ih, iw, upsample, rx, ry,
-      nullptr, offsets, bits, capacity_words, status, nullptr, nullptr);
+  const float4* b4 = reinterpret_cast<const float4*>(boxes);
+  if (proto_dtype == HDY_F16)
+    process_mask_kernel<true, true><<<(unsigned)((size_t)bs * max_det), kPmThreads, 0, st>>>(
+        protos, coef, b4, counts, max_det, nm, mh, mw, ih, iw, upsample, rx, ry, nullptr, geom, offsets, bits,
+        capacity_words, status, nullptr, nullptr);
+  else
+    process_mask_kernel<true, false><<<(unsigned)((size_t)bs * max_det), kPmThreads, 0, st>>>(
+        protos, coef, b4, counts, max_det, nm, mh, mw, ih, iw, upsample, rx, ry, nullptr, geom, offsets, bits,
+        capacity_words, status, nullptr, nullptr);
   return check_launch("hdy_process_mask_packed");
 }
 

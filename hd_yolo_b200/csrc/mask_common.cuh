@@ -125,14 +125,14 @@ __device__ __forceinline__ PMGeom pm_geometry(const float4 b, int mh, int mw, in
 // when the shapes / workspace do not meet its requirements (the caller then uses the per-detection kernel in mask.cu).
 constexpr int kPatchPitch = 16;  // sigmoid patches of up to 16 x 16 proto pixels go through the workspace
 size_t process_mask_workspace_bytes(long long bs, long long max_det);
-int launch_process_mask_regions(const float* protos, const float* coef, const float* boxes, const int32_t* counts,
-                                int bs, int max_det, int nm, int mh, int mw, int ih, int iw, int upsample, float rx,
+int launch_process_mask_regions(const void* protos, int proto_dtype, const float* coef, const float* boxes,
+                                const int32_t* counts, int bs, int max_det, int nm, int mh, int mw, int ih, int iw, int upsample, float rx,
                                 float ry, float* out_dense, const int32_t* geom, const int64_t* offsets, uint32_t* bits,
                                 long long capacity_words, int32_t* status, void* workspace, size_t workspace_bytes,
                                 cudaStream_t stream);
 // mask.cu: the per-detection kernel over a device-side list of slots
-int launch_process_mask_listed(const float* protos, const float* coef, const float* boxes, const int32_t* counts,
-                               int max_det, int nm, int mh, int mw, int ih, int iw, int upsample, float rx, float ry,
+int launch_process_mask_listed(const void* protos, int proto_dtype, const float* coef, const float* boxes,
+                               const int32_t* counts, int max_det, int nm, int mh, int mw, int ih, int iw, int upsample, float rx, float ry,
                                float* out_dense, const int64_t* offsets, uint32_t* bits, long long capacity_words,
                                int32_t* status, const int32_t* slot_list, const int32_t* list_count, cudaStream_t st);
 

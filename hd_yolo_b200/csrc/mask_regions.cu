@@ -39,14 +39,17 @@ constexpr int kRegThreads = 256;
 constexpr int kRegWarps = kRegThreads / 32;
 constexpr int kRegList = 512;  // detections examined per pass
 
-struct RegSmem {
-  float proto[kRegNm][kRegBoxY][kRegBoxX];  // TMA destination (dense, x fastest)
+template <typename E>
+struct RegSmemT {
+  E proto[kRegNm][kRegBoxY][kRegBoxX];  // TMA destination (dense, x fastest); fp32, or fp16 widened on use
   float coef[kRegWarps][kRegNm];
   uint16_t list[kRegList];
   int nlist;
   int pad;
   uint64_t bar;
 };
+__device__ __forceinline__ float proto_f32(float v) { return v; }
+__device__ __forceinline__ float proto_f32(__half v) { return __half2float(v); }  // exact
 
 // workspace: [0] large-detection counter, large list (int32 per slot), the patches, then the per-region detection
 // lists (count + kRegCap uint16 entries per (tile, region); sized for the largest proto plane, see kMaxRegions)
@@ -112,11 +115,14 @@ __device__ __forceinline__ KeptRange kept_range(const float4 b, float rx, float 
 __global__ void __launch_bounds__(256) proto_bin_kernel(const float4* __restrict__ boxes,
                                                         const int32_t* __restrict__ counts, long long n_slots,
                                                         int max_det, int mh, int mw, int rxn, int ryn, float rx,
-                                                        float ry, RegionList* __restrict__ regions) {
+                                                        float ry, const int32_t* __restrict__ geom4,
+                                                        RegionList* __restrict__ regions) {
   const long long slot = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (slot >= n_slots) return;
   const int tile = (int)(slot / max_det), d = (int)(slot - (long long)tile * max_det);
   if (d >= counts[tile]) return;
+  // packed form: a slot without an output window (empty, or not KEPT by the slide-level merge) needs no patch
+  if (geom4 && (geom4[4 * slot + 2] <= 0 || geom4[4 * slot + 3] <= 0)) return;
   const KeptRange k = kept_range(boxes[slot], rx, ry, mw, mh);
   if (k.px1 <= k.px0 || k.py1 <= k.py0) return;
   if (k.px1 - k.px0 > kPatchPitch || k.py1 - k.py0 > kPatchPitch) return;  // per-detection kernel
@@ -131,12 +137,13 @@ __global__ void __launch_bounds__(256) proto_bin_kernel(const float4* __restrict
 }
 
 // ------------------------------------------------------------------------------------------------ phase 1
+template <typename E>
 __global__ void __launch_bounds__(kRegThreads, 3) proto_patch_kernel(
     const __grid_constant__ CUtensorMap tmap, const float* __restrict__ coef, const float4* __restrict__ boxes,
     const int32_t* __restrict__ counts, int max_det, int mh, int mw, int rxn, int ryn, float rx, float ry,
     float* __restrict__ patches, const RegionList* __restrict__ regions) {
   extern __shared__ __align__(128) unsigned char smem_raw[];
-  RegSmem& S = *reinterpret_cast<RegSmem*>(smem_raw);
+  RegSmemT<E>& S = *reinterpret_cast<RegSmemT<E>*>(smem_raw);
   const int t = threadIdx.x, lane = t & 31, warp = t >> 5;
   const int per_tile = rxn * ryn;
   const int tile = blockIdx.x / per_tile, reg = blockIdx.x - tile * per_tile;
@@ -225,7 +232,7 @@ __global__ void __launch_bounds__(kRegThreads, 3) proto_patch_kernel(
           const int sy = yy - Y0;
           float acc = 0.f;
 #pragma unroll
-          for (int c = 0; c < kRegNm; ++c) acc = fmaf(cf[c], S.proto[c][sy][sx], acc);
+          for (int c = 0; c < kRegNm; ++c) acc = fmaf(cf[c], proto_f32(S.proto[c][sy][sx]), acc);
           v = sigmoidf_ref(acc);
         }
         dst[(yy - k.py0) * kPatchPitch] = v;
@@ -435,14 +442,18 @@ static EncodeTiledFn tensor_map_encoder() {
   return fn;
 }
 
-int launch_process_mask_regions(const float* protos, const float* coef, const float* boxes, const int32_t* counts,
+int launch_process_mask_regions(const void* protos, int proto_dtype, const float* coef, const float* boxes,
+                                const int32_t* counts,
                                 int bs, int max_det, int nm, int mh, int mw, int ih, int iw, int upsample, float rx,
                                 float ry, float* out_dense, const int32_t* geom, const int64_t* offsets, uint32_t* bits,
                                 long long capacity_words, int32_t* status, void* workspace, size_t workspace_bytes,
                                 cudaStream_t stream) {
   const long long slots = (long long)bs * max_det;
   if (!workspace || workspace_bytes < process_mask_workspace_bytes(bs, max_det)) return 1;
-  if (nm != kRegNm || (mw & 3) != 0 || ((uintptr_t)protos & 15) != 0 || max_det > 65535) return 1;
+  const bool half = proto_dtype == HDY_F16;
+  const int esz = half ? 2 : 4;
+  // TMA: the global address and every stride are multiples of 16 bytes; a tile origin too (24 pixels: 96 / 48 bytes)
+  if (nm != kRegNm || (mw * esz & 15) != 0 || ((uintptr_t)protos & 15) != 0 || max_det > 65535) return 1;
   if (getenv("HDY_MASK_GENERIC")) return 1;  // debugging aid: force the per-detection kernel
   const int rxn = (mw + kRegBoxX - 1) / kRegBoxX, ryn = (mh + kRegBoxY - 1) / kRegBoxY;
   if ((long long)bs * rxn * ryn >= (1ll << 31) || slots >= (1ll << 31) || rxn * ryn > kMaxRegionsPerTile) return 1;
@@ -450,10 +461,11 @@ int launch_process_mask_regions(const float* protos, const float* coef, const fl
   if (!enc) return 1;
   CUtensorMap map;
   const cuuint64_t dims[4] = {(cuuint64_t)mw, (cuuint64_t)mh, (cuuint64_t)nm, (cuuint64_t)bs};
-  const cuuint64_t strides[3] = {(cuuint64_t)mw * 4, (cuuint64_t)mw * mh * 4, (cuuint64_t)mw * mh * nm * 4};
+  const cuuint64_t strides[3] = {(cuuint64_t)mw * esz, (cuuint64_t)mw * mh * esz, (cuuint64_t)mw * mh * nm * esz};
   const cuuint32_t box[4] = {kRegBoxX, kRegBoxY, kRegNm, 1};
   const cuuint32_t estr[4] = {1, 1, 1, 1};
-  const CUresult r = enc(&map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, const_cast<float*>(protos), dims, strides, box, estr,
+  const CUresult r = enc(&map, half ? CU_TENSOR_MAP_DATA_TYPE_FLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4,
+                         const_cast<void*>(protos), dims, strides, box, estr,
                          CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
                          CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) return 1;
@@ -461,16 +473,23 @@ int launch_process_mask_regions(const float* protos, const float* coef, const fl
   cudaError_t e = cudaMemsetAsync(W.large_count, 0, 4, stream);
   if (e == cudaSuccess) e = cudaMemsetAsync(W.regions, 0, (size_t)bs * rxn * ryn * sizeof(RegionList), stream);
   if (e == cudaSuccess)
-    e = cudaFuncSetAttribute(proto_patch_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(RegSmem));
+    e = half ? cudaFuncSetAttribute(proto_patch_kernel<__half>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                    (int)sizeof(RegSmemT<__half>))
+             : cudaFuncSetAttribute(proto_patch_kernel<float>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                    (int)sizeof(RegSmemT<float>));
   if (e != cudaSuccess) {
     set_error("process_mask(regions) setup: %s", cudaGetErrorString(e));
     return HDY_ERR_CUDA;
   }
   const float4* b4 = reinterpret_cast<const float4*>(boxes);
   proto_bin_kernel<<<(unsigned)((slots + 255) / 256), 256, 0, stream>>>(b4, counts, slots, max_det, mh, mw, rxn, ryn, rx,
-                                                                        ry, W.regions);
-  proto_patch_kernel<<<(unsigned)((long long)bs * rxn * ryn), kRegThreads, sizeof(RegSmem), stream>>>(
-      map, coef, b4, counts, max_det, mh, mw, rxn, ryn, rx, ry, W.patches, W.regions);
+                                                                        ry, geom, W.regions);
+  if (half)
+    proto_patch_kernel<__half><<<(unsigned)((long long)bs * rxn * ryn), kRegThreads, sizeof(RegSmemT<__half>), stream>>>(
+        map, coef, b4, counts, max_det, mh, mw, rxn, ryn, rx, ry, W.patches, W.regions);
+  else
+    proto_patch_kernel<float><<<(unsigned)((long long)bs * rxn * ryn), kRegThreads, sizeof(RegSmemT<float>), stream>>>(
+        map, coef, b4, counts, max_det, mh, mw, rxn, ryn, rx, ry, W.patches, W.regions);
   const unsigned g2 = (unsigned)((slots + kUpWarps - 1) / kUpWarps);
   const bool packed = out_dense == nullptr;
 #define HDY_UP(P, U)                                                                                              \
@@ -489,7 +508,7 @@ int launch_process_mask_regions(const float* protos, const float* coef, const fl
 #undef HDY_UP
   int rc = check_launch("hdy_process_mask(regions)");
   if (rc) return rc;
-  return launch_process_mask_listed(protos, coef, boxes, counts, max_det, nm, mh, mw, ih, iw, upsample, rx, ry,
+  return launch_process_mask_listed(protos, proto_dtype, coef, boxes, counts, max_det, nm, mh, mw, ih, iw, upsample, rx, ry,
                                     out_dense, offsets, bits, capacity_words, status, W.large_list, W.large_count,
                                     stream);
 }

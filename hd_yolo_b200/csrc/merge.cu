@@ -451,6 +451,9 @@ struct MergeIn {
   const float4* boxes;
   const float* scores;
   const uint32_t* gidx;       // optional global index per entry (tie order); NULL: gidx_base + i
+  const uint32_t* rep_gidx;   // optional global index of the replicas (entry n_local + k -> rep_gidx[k])
+  const uint32_t* gidx_base_dev;  // optional device copy of gidx_base (overrides it)
+  int tile_base;              // tile_id[i] + tile_base indexes tile_cores / tile_dirty (ranks hold local tile ids)
   const int32_t* tile_id;     // optional
   const float4* tile_cores;   // optional [n_tiles] core rectangles (slide coordinates)
   const uint8_t* tile_dirty;  // optional [n_tiles]: tiles reached by another tile's far-reaching box (no shortcut)
@@ -481,9 +484,10 @@ __global__ void merge_classify_kernel(const MergeIn in, const MergeStats* __rest
       } else {
         bool interior = false;
         if (!remote && in.tile_cores && in.tile_id && in.tile_id[i] >= 0) {
-          const float4 c = in.tile_cores[in.tile_id[i]];
+          const int tg = in.tile_id[i] + in.tile_base;
+          const float4 c = in.tile_cores[tg];
           interior = (b.x > c.x + m) && (b.y > c.y + m) && (b.z < c.z - m) && (b.w < c.w - m) &&
-                     !(in.tile_dirty && in.tile_dirty[in.tile_id[i]]);
+                     !(in.tile_dirty && in.tile_dirty[tg]);
         }
         if (interior)
           st = MS_KEPT;
@@ -511,8 +515,15 @@ __global__ void merge_fill_kernel(const MergeIn in, const MergeStats* __restrict
       const int cls = merge_classify_box(b, g, G, bucket, ix, iy);
       p = (uint32_t)atomicAdd(&cell[bucket], 1);
       cbox[p] = b;
-      ckey[p] = make_key(in.scores[i], in.gidx ? in.gidx[i] : in.gidx_base + (uint32_t)i);
       const bool remote = i >= in.n_local;
+      uint32_t gi;
+      if (remote && in.rep_gidx)
+        gi = in.rep_gidx[i - in.n_local];
+      else if (in.gidx)
+        gi = in.gidx[i];
+      else
+        gi = (in.gidx_base_dev ? *in.gidx_base_dev : in.gidx_base) + (uint32_t)i;
+      ckey[p] = make_key(in.scores[i], gi);
       cstate[p] = remote ? (uint8_t)MS_REMOTE_UNKNOWN : (cls == 0 ? (uint8_t)MS_KEPT : (uint8_t)MS_UNKNOWN);
       blocked[p] = 0u;
       ctile[p] = (!remote && in.tile_cores && in.tile_id) ? in.tile_id[i] : -1;
@@ -911,6 +922,281 @@ static inline unsigned blocks_for(long long n, int threads, int max_blocks = 148
   return (unsigned)b;
 }
 
+// ------------------------------------------------------------------------------------------------
+// multi-GPU seam exchange: fixed-size blocks, every size stays on the device (include/hd_yolo_b200.h)
+// ------------------------------------------------------------------------------------------------
+constexpr int kSeamHdr = HDY_SEAM_HDR_WORDS, kSeamFar = HDY_SEAM_FAR_WORDS, kSeamRow = HDY_SEAM_ROW_WORDS;
+constexpr int kSeamMaxWorld = HDY_SEAM_MAX_WORLD;
+// meta words (int32): see hdy_seam_scatter in the header
+enum { SM_NTOTAL = 0, SM_MARGIN = 2, SM_GBASE = 3, SM_FLAGS = 4, SM_FAR_TOTAL = 5, SM_UNDECIDED = 8, SM_REP_OFF = 16,
+       SM_OWN_SEAM = 88 };
+
+__device__ __forceinline__ void atomic_min_float(float* addr, float v) {
+  if (v >= 0.f)
+    atomicMin(reinterpret_cast<int*>(addr), __float_as_int(v));
+  else
+    atomicMax(reinterpret_cast<unsigned*>(addr), __float_as_uint(v));
+}
+__device__ __forceinline__ void atomic_max_float(float* addr, float v) {
+  if (v >= 0.f)
+    atomicMax(reinterpret_cast<int*>(addr), __float_as_int(v));
+  else
+    atomicMin(reinterpret_cast<unsigned*>(addr), __float_as_uint(v));
+}
+
+// header + far list of this rank's summary block (the rectangle starts inverted; seam_rect_kernel folds the boxes in)
+__global__ void seam_summary_pack_kernel(long long n_local, const float* __restrict__ margin,
+                                         const float4* __restrict__ far_boxes, const int32_t* __restrict__ far_tile,
+                                         const int32_t* __restrict__ far_count, int far_list_capacity, int tile_base,
+                                         int far_cap, int32_t* __restrict__ block) {
+  const int k = blockIdx.x * blockDim.x + threadIdx.x;
+  const int nf = far_count ? *far_count : 0;
+  if (k == 0) {
+    float* f = reinterpret_cast<float*>(block);
+    const float big = 3.0e38f;
+    f[0] = big, f[1] = big, f[2] = -big, f[3] = -big;
+    f[4] = margin ? *margin : 0.f;
+    // a list that overflowed on the way here is reported as "more than far_cap": every tile turns dirty
+    block[5] = nf > far_list_capacity ? far_cap + 1 : nf;
+    *reinterpret_cast<long long*>(block + 6) = n_local;
+    for (int i = 8; i < kSeamHdr; ++i) block[i] = 0;
+  }
+  if (k < far_cap) {
+    int32_t* e = block + kSeamHdr + k * kSeamFar;
+    if (k < min(nf, far_list_capacity)) {
+      const float4 b = far_boxes[k];
+      e[0] = __float_as_int(b.x), e[1] = __float_as_int(b.y), e[2] = __float_as_int(b.z), e[3] = __float_as_int(b.w);
+      e[4] = far_tile[k] + tile_base;
+    } else {
+      e[0] = e[1] = e[2] = e[3] = 0, e[4] = -1;
+    }
+    e[5] = e[6] = e[7] = 0;
+  }
+}
+
+__global__ void seam_rect_kernel(const float4* __restrict__ boxes, long long n, float* __restrict__ rect) {
+  const float big = 3.0e38f;
+  float x1 = big, y1 = big, x2 = -big, y2 = -big;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+    const float4 b = boxes[i];  // fminf / fmaxf skip NaN coordinates: such a box intersects nothing anyway
+    x1 = fminf(x1, fmaxf(b.x, -big)), y1 = fminf(y1, fmaxf(b.y, -big));
+    x2 = fmaxf(x2, fminf(b.z, big)), y2 = fmaxf(y2, fminf(b.w, big));
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    x1 = fminf(x1, __shfl_xor_sync(0xffffffffu, x1, o)), y1 = fminf(y1, __shfl_xor_sync(0xffffffffu, y1, o));
+    x2 = fmaxf(x2, __shfl_xor_sync(0xffffffffu, x2, o)), y2 = fmaxf(y2, __shfl_xor_sync(0xffffffffu, y2, o));
+  }
+  if ((threadIdx.x & 31) == 0 && x2 >= x1) {
+    atomic_min_float(rect + 0, x1), atomic_min_float(rect + 1, y1);
+    atomic_max_float(rect + 2, x2), atomic_max_float(rect + 3, y2);
+  }
+}
+
+struct SeamRects {
+  float4 r[kSeamMaxWorld];
+  int live[kSeamMaxWorld];
+};
+__device__ __forceinline__ void seam_load_rects(SeamRects& S, const int32_t* summaries, int world, int rank, int hb) {
+  for (int q = threadIdx.x; q < world; q += blockDim.x) {
+    const int32_t* h = summaries + (size_t)q * hb;
+    S.r[q] = make_float4(__int_as_float(h[0]), __int_as_float(h[1]), __int_as_float(h[2]), __int_as_float(h[3]));
+    S.live[q] = (q != rank) && (*reinterpret_cast<const long long*>(h + 6) > 0);
+  }
+  __syncthreads();
+}
+// closed-interval test against every other rank's rectangle: a superset of "the boxes intersect", which is all
+// exactness needs (hd_yolo_b200/dist.py)
+__device__ __forceinline__ bool seam_row(const float4& b, const SeamRects& S, int world) {
+  bool s = false;
+  for (int q = 0; q < world; ++q)
+    s |= S.live[q] && (b.z >= S.r[q].x) && (b.x <= S.r[q].z) && (b.w >= S.r[q].y) && (b.y <= S.r[q].w);
+  return s;
+}
+
+__global__ void __launch_bounds__(kSelThreads) seam_count_kernel(const float4* __restrict__ boxes, long long n,
+                                                                 long long chunk, const int32_t* __restrict__ summaries,
+                                                                 int world, int rank, int hb,
+                                                                 int* __restrict__ block_counts) {
+  __shared__ SeamRects S;
+  __shared__ int part[kSelThreads / 32];
+  seam_load_rects(S, summaries, world, rank, hb);
+  const long long lo = (long long)blockIdx.x * chunk, hi = min(lo + chunk, n);
+  int c = 0;
+  for (long long i = lo + threadIdx.x; i < hi; i += kSelThreads) c += seam_row(boxes[i], S, world);
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) c += __shfl_xor_sync(0xffffffffu, c, o);
+  if ((threadIdx.x & 31) == 0) part[threadIdx.x >> 5] = c;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    int t = 0;
+    for (int w = 0; w < kSelThreads / 32; ++w) t += part[w];
+    block_counts[blockIdx.x] = t;
+  }
+}
+
+// rows leave in ascending row order: payload row k = (box bits, score bits, global index) of own row sel[k]
+__global__ void __launch_bounds__(kSelThreads) seam_write_kernel(const float4* __restrict__ boxes,
+                                                                 const float* __restrict__ scores, long long n,
+                                                                 long long chunk, const int32_t* __restrict__ summaries,
+                                                                 int world, int rank, int hb,
+                                                                 const int* __restrict__ block_offsets, int seam_cap,
+                                                                 int32_t* __restrict__ sel, int32_t* __restrict__ block) {
+  __shared__ SeamRects S;
+  __shared__ int wcount[kSelThreads / 32];
+  seam_load_rects(S, summaries, world, rank, hb);
+  long long gbase = 0;  // rows owned by lower ranks
+  for (int q = 0; q < rank; ++q) gbase += *reinterpret_cast<const long long*>(summaries + (size_t)q * hb + 6);
+  const long long lo = (long long)blockIdx.x * chunk, hi = min(lo + chunk, n);
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  long long running = block_offsets[blockIdx.x];
+  for (long long i0 = lo; i0 < hi; i0 += kSelThreads) {
+    const long long i = i0 + threadIdx.x;
+    float4 b = make_float4(0.f, 0.f, 0.f, 0.f);
+    bool k = false;
+    if (i < hi) {
+      b = boxes[i];
+      k = seam_row(b, S, world);
+    }
+    const unsigned m = __ballot_sync(0xffffffffu, k);
+    if (lane == 0) wcount[warp] = __popc(m);
+    __syncthreads();
+    int before = 0, total = 0;
+#pragma unroll
+    for (int w = 0; w < kSelThreads / 32; ++w) {
+      const int c = wcount[w];
+      if (w < warp) before += c;
+      total += c;
+    }
+    const long long slot = running + before + __popc(m & ((1u << lane) - 1u));
+    if (k && slot < seam_cap) {
+      sel[slot] = (int32_t)i;
+      int32_t* e = block + kSeamHdr + slot * kSeamRow;
+      e[0] = __float_as_int(b.x), e[1] = __float_as_int(b.y), e[2] = __float_as_int(b.z), e[3] = __float_as_int(b.w);
+      e[4] = __float_as_int(scores[i]);
+      e[5] = (int32_t)(uint32_t)(gbase + i);
+    }
+    running += total;
+    __syncthreads();
+  }
+}
+
+__global__ void seam_block_header_kernel(const int* __restrict__ count, int32_t* __restrict__ block) {
+  if (threadIdx.x == 0 && blockIdx.x == 0) {
+    block[0] = *count;
+    for (int i = 1; i < kSeamHdr; ++i) block[i] = 0;
+  }
+}
+
+// replicas: the other ranks' seam rows, rank by rank, appended behind the own rows; meta for the later steps
+__global__ void seam_scatter_kernel(const int32_t* __restrict__ payloads, const int32_t* __restrict__ summaries,
+                                    int world, int rank, int hb, int pb, int far_cap, int seam_cap, long long n_local,
+                                    long long rep_cap, float4* __restrict__ boxes, float* __restrict__ scores,
+                                    uint32_t* __restrict__ rep_gidx, int32_t* __restrict__ meta) {
+  __shared__ int off[kSeamMaxWorld + 1];
+  if (threadIdx.x == 0) {
+    int run = 0, fl = 0, far_total = 0;
+    float m = 0.f;
+    long long gbase = 0, rows_all = 0;
+    for (int q = 0; q < world; ++q) {
+      off[q] = run;
+      const int32_t* h = summaries + (size_t)q * hb;
+      const int cnt = payloads[(size_t)q * pb];
+      if (cnt > seam_cap) fl |= 1;
+      if (q != rank) run += min(max(cnt, 0), seam_cap);
+      m = fmaxf(m, __int_as_float(h[4]));
+      if (h[5] > far_cap) fl |= 4;
+      far_total += min(max(h[5], 0), far_cap);
+      if (q < rank) gbase += *reinterpret_cast<const long long*>(h + 6);
+      rows_all += *reinterpret_cast<const long long*>(h + 6);
+    }
+    off[world] = run;
+    if (run > rep_cap) fl |= 2;
+    if (rows_all >= (1ll << 32)) fl |= 8;  // global indices are 32-bit
+    if (blockIdx.x == 0 && blockIdx.y == 0) {
+      *reinterpret_cast<long long*>(meta + SM_NTOTAL) = n_local + min((long long)run, rep_cap);
+      meta[SM_MARGIN] = __float_as_int(m);
+      meta[SM_GBASE] = (int32_t)(uint32_t)gbase;
+      meta[SM_FLAGS] = fl;
+      meta[SM_FAR_TOTAL] = far_total;
+      for (int e = 0; e < 8; ++e) meta[SM_UNDECIDED + e] = 0;
+      for (int q = 0; q <= world; ++q) meta[SM_REP_OFF + q] = off[q];
+      meta[SM_OWN_SEAM] = min(max(payloads[(size_t)rank * pb], 0), seam_cap);
+    }
+  }
+  __syncthreads();
+  const int q = blockIdx.y;
+  if (q == rank) return;
+  const int cnt = min(max(payloads[(size_t)q * pb], 0), seam_cap);
+  const int32_t* src = payloads + (size_t)q * pb + kSeamHdr;
+  for (int j = blockIdx.x * blockDim.x + threadIdx.x; j < cnt; j += gridDim.x * blockDim.x) {
+    const long long r = (long long)off[q] + j;
+    if (r >= rep_cap) break;
+    const int32_t* e = src + (size_t)j * kSeamRow;
+    boxes[n_local + r] = make_float4(__int_as_float(e[0]), __int_as_float(e[1]), __int_as_float(e[2]),
+                                     __int_as_float(e[3]));
+    scores[n_local + r] = __int_as_float(e[4]);
+    rep_gidx[r] = (uint32_t)e[5];
+  }
+}
+
+// dirty tiles from every rank's far list (global tile ids); all dirty when a list overflowed
+__global__ void seam_dirty_tiles_kernel(const int32_t* __restrict__ summaries, int world, int hb, int far_cap,
+                                        const float4* __restrict__ tile_rois, int n_tiles,
+                                        uint8_t* __restrict__ dirty) {
+  const int t = blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= n_tiles) return;
+  const float4 r = tile_rois[t];
+  uint8_t d = 0;
+  for (int q = 0; q < world && !d; ++q) {
+    const int32_t* h = summaries + (size_t)q * hb;
+    const int nf = h[5];
+    if (nf > far_cap) d = 1;
+    for (int k = 0; k < min(nf, far_cap) && !d; ++k) {
+      const int32_t* e = h + kSeamHdr + k * kSeamFar;
+      if (e[4] == t) continue;
+      const float4 b = make_float4(__int_as_float(e[0]), __int_as_float(e[1]), __int_as_float(e[2]),
+                                   __int_as_float(e[3]));
+      const bool apart = (b.z < r.x) || (b.x > r.z) || (b.w < r.y) || (b.y > r.w);  // false for NaN: dirty
+      if (!apart) d = 1;
+    }
+  }
+  dirty[t] = d;
+}
+
+__global__ void seam_export_kernel(const uint32_t* __restrict__ pos, const uint8_t* __restrict__ cstate,
+                                   const uint8_t* __restrict__ state, const int32_t* __restrict__ sel,
+                                   const int32_t* __restrict__ my_block, int seam_cap, uint8_t* __restrict__ out) {
+  const int m = min(max(my_block[0], 0), seam_cap);
+  for (int k = blockIdx.x * blockDim.x + threadIdx.x; k < m; k += gridDim.x * blockDim.x) {
+    const int32_t i = sel[k];
+    const uint32_t p = pos[i];
+    out[k] = (p == 0xffffffffu) ? state[i] : cstate[p];
+  }
+}
+
+// verdicts of the replicas from their owners; undecided[exchange] != 0 while any seam row anywhere is still open
+__global__ void seam_import_kernel(const uint32_t* __restrict__ pos, uint8_t* __restrict__ cstate, long long n_local,
+                                   const uint8_t* __restrict__ states, const int32_t* __restrict__ payloads, int pb,
+                                   int32_t* __restrict__ meta, int world, int rank, int seam_cap, int exchange) {
+  const int q = blockIdx.y;
+  const int cnt = min(max(payloads[(size_t)q * pb], 0), seam_cap);
+  const long long first = n_local + meta[SM_REP_OFF + q];
+  const long long n_total = *reinterpret_cast<const long long*>(meta + SM_NTOTAL);
+  if (blockIdx.x == 0 && blockIdx.y == 0 && threadIdx.x == 0) meta[SM_UNDECIDED + ((exchange + 1) & 7)] = 0;
+  int open = 0;
+  for (int j = blockIdx.x * blockDim.x + threadIdx.x; j < cnt; j += gridDim.x * blockDim.x) {
+    const uint8_t s = states[(size_t)q * seam_cap + j];
+    const bool decided = (s == MS_KEPT || s == MS_SUPPRESSED || s == MS_DROPPED);
+    open |= !decided;
+    if (q == rank || first + j >= n_total) continue;
+    const uint32_t p = pos[first + j];
+    if (p == 0xffffffffu) continue;
+    cstate[p] = decided ? s : (uint8_t)MS_REMOTE_UNKNOWN;
+  }
+  if (__syncthreads_or(open) && threadIdx.x == 0) atomicOr(meta + SM_UNDECIDED + (exchange & 7), 1);
+}
+
 }  // namespace hdy
 
 using namespace hdy;
@@ -998,17 +1284,14 @@ size_t hdy_merge_workspace_bytes(int64_t n_max) {
   return merge_layout(nullptr, n_max).bytes;
 }
 
-int hdy_merge_build(const float* boxes, const float* scores, const uint32_t* gidx, uint32_t gidx_base,
-                    const int32_t* tile_id, const float* tile_cores, const uint8_t* tile_dirty, const float* margin,
-                    const int64_t* n_dev,
-                    int64_t n_max, int64_t n_local, float conf_thres, float iou_thres, uint8_t* state,
-                    void* workspace, size_t workspace_bytes, hdy_stream_t stream) {
+static int merge_build_common(MergeIn in, const float* tile_cores, uint8_t* state, void* workspace,
+                              size_t workspace_bytes, cudaStream_t st) {
+  const int64_t n_max = in.n_max, n_local = in.n_local;
   HDY_REQUIRE(n_max >= 0 && n_local >= 0 && n_local <= n_max, "hdy_merge_build: bad sizes");
   HDY_REQUIRE(n_max < (1ll << 31), "hdy_merge_build: at most 2^31-1 detections per call");
-  HDY_REQUIRE(iou_thres >= 0.f, "hdy_merge_build: iou_thres must be >= 0");
+  HDY_REQUIRE(in.thr >= 0.f, "hdy_merge_build: iou_thres must be >= 0");
   HDY_REQUIRE(workspace && workspace_bytes >= hdy_merge_workspace_bytes(n_max), "hdy_merge_build: workspace too small");
-  HDY_REQUIRE(!tile_cores || (tile_id && margin), "hdy_merge_build: tile_cores needs tile_id and margin");
-  cudaStream_t st = (cudaStream_t)stream;
+  HDY_REQUIRE(!tile_cores || (in.tile_id && in.margin), "hdy_merge_build: tile_cores needs tile_id and margin");
   MergeWs w = merge_layout(workspace, n_max > 0 ? n_max : 1);
   const size_t nb = (size_t)w.G * w.G + 2;
   cudaError_t e = cudaMemsetAsync(w.stats, 0, sizeof(MergeStats), st);
@@ -1018,12 +1301,31 @@ int hdy_merge_build(const float* boxes, const float* scores, const uint32_t* gid
     return HDY_ERR_CUDA;
   }
   if (n_max == 0) return HDY_OK;
-  HDY_REQUIRE(boxes && scores && state && (((uintptr_t)boxes | (uintptr_t)tile_cores) & 15) == 0,
+  HDY_REQUIRE(in.boxes && in.scores && state && (((uintptr_t)in.boxes | (uintptr_t)tile_cores) & 15) == 0,
               "hdy_merge_build: NULL or misaligned pointer");
+  const unsigned blocks = blocks_for(n_max, kMergeThreads);
+  merge_stats_kernel<<<blocks, kMergeThreads, 0, st>>>(in.boxes, in.scores, in.n_dev, n_max, in.conf, w.stats);
+  merge_pick_cell_kernel<<<1, 32, 0, st>>>(w.stats);
+  merge_classify_kernel<<<blocks, kMergeThreads, 0, st>>>(in, w.stats, w.G, w.cell, state);
+  int rc = device_exclusive_scan(w.cell, (long long)nb - 1, w.scan_tmp, nullptr, st);
+  if (rc) return rc;
+  merge_fill_kernel<<<blocks, kMergeThreads, 0, st>>>(in, w.stats, w.G, w.cell, state, w.cbox, w.ckey, w.cstate,
+                                                      w.pos, w.blocked, w.ctile);
+  return check_launch("hdy_merge_build");
+}
+
+int hdy_merge_build(const float* boxes, const float* scores, const uint32_t* gidx, uint32_t gidx_base,
+                    const int32_t* tile_id, const float* tile_cores, const uint8_t* tile_dirty, const float* margin,
+                    const int64_t* n_dev,
+                    int64_t n_max, int64_t n_local, float conf_thres, float iou_thres, uint8_t* state,
+                    void* workspace, size_t workspace_bytes, hdy_stream_t stream) {
   MergeIn in;
   in.boxes = reinterpret_cast<const float4*>(boxes);
   in.scores = scores;
   in.gidx = gidx;
+  in.rep_gidx = nullptr;
+  in.gidx_base_dev = nullptr;
+  in.tile_base = 0;
   in.tile_id = tile_id;
   in.tile_cores = reinterpret_cast<const float4*>(tile_cores);
   in.tile_dirty = tile_dirty;
@@ -1034,15 +1336,137 @@ int hdy_merge_build(const float* boxes, const float* scores, const uint32_t* gid
   in.gidx_base = gidx_base;
   in.conf = conf_thres;
   in.thr = iou_thres;
-  const unsigned blocks = blocks_for(n_max, kMergeThreads);
-  merge_stats_kernel<<<blocks, kMergeThreads, 0, st>>>(in.boxes, scores, in.n_dev, n_max, conf_thres, w.stats);
-  merge_pick_cell_kernel<<<1, 32, 0, st>>>(w.stats);
-  merge_classify_kernel<<<blocks, kMergeThreads, 0, st>>>(in, w.stats, w.G, w.cell, state);
-  int rc = device_exclusive_scan(w.cell, (long long)nb - 1, w.scan_tmp, nullptr, st);
-  if (rc) return rc;
-  merge_fill_kernel<<<blocks, kMergeThreads, 0, st>>>(in, w.stats, w.G, w.cell, state, w.cbox, w.ckey, w.cstate,
-                                                      w.pos, w.blocked, w.ctile);
-  return check_launch("hdy_merge_build");
+  return merge_build_common(in, tile_cores, state, workspace, workspace_bytes, (cudaStream_t)stream);
+}
+
+// ---- multi-GPU seam exchange -------------------------------------------------------------------
+static inline int seam_hb(int far_cap) { return kSeamHdr + far_cap * kSeamFar; }
+static inline int seam_pb(int seam_cap) { return kSeamHdr + seam_cap * kSeamRow; }
+
+int hdy_seam_summary(const float* boxes, int64_t n_local, const float* margin, const float* far_boxes,
+                     const int32_t* far_tile, const int32_t* far_count, int far_list_capacity, int tile_base,
+                     int far_cap, int32_t* block, hdy_stream_t stream) {
+  HDY_REQUIRE(n_local >= 0 && far_cap >= 0 && block, "hdy_seam_summary: bad arguments");
+  HDY_REQUIRE(!far_count || (far_boxes && far_tile && far_list_capacity >= 0 && ((uintptr_t)far_boxes & 15) == 0),
+              "hdy_seam_summary: far_count needs far_boxes (16-byte aligned) and far_tile");
+  HDY_REQUIRE(n_local == 0 || (boxes && ((uintptr_t)boxes & 15) == 0), "hdy_seam_summary: NULL or misaligned boxes");
+  cudaStream_t st = (cudaStream_t)stream;
+  seam_summary_pack_kernel<<<(unsigned)(far_cap / 256 + 1), 256, 0, st>>>(
+      n_local, margin, reinterpret_cast<const float4*>(far_boxes), far_tile, far_count, far_list_capacity, tile_base,
+      far_cap, block);
+  if (n_local > 0)
+    seam_rect_kernel<<<blocks_for(n_local, 256, 148 * 4), 256, 0, st>>>(reinterpret_cast<const float4*>(boxes),
+                                                                      n_local, reinterpret_cast<float*>(block));
+  return check_launch("hdy_seam_summary");
+}
+
+int hdy_seam_select(const float* boxes, const float* scores, int64_t n_local, const int32_t* summaries, int world,
+                    int rank, int far_cap, int seam_cap, int32_t* sel, int32_t* block, int32_t* block_scratch,
+                    hdy_stream_t stream) {
+  HDY_REQUIRE(n_local >= 0 && n_local < (1ll << 31) && world >= 1 && world <= kSeamMaxWorld && rank >= 0 &&
+                  rank < world && far_cap >= 0 && seam_cap >= 0,
+              "hdy_seam_select: bad arguments (world <= %d)", kSeamMaxWorld);
+  HDY_REQUIRE(summaries && sel && block && block_scratch, "hdy_seam_select: NULL pointer");
+  cudaStream_t st = (cudaStream_t)stream;
+  if (n_local == 0) {
+    cudaError_t e = cudaMemsetAsync(block, 0, kSeamHdr * 4, st);
+    if (e != cudaSuccess) {
+      set_error("hdy_seam_select: %s", cudaGetErrorString(e));
+      return HDY_ERR_CUDA;
+    }
+    return HDY_OK;
+  }
+  HDY_REQUIRE(boxes && scores && ((uintptr_t)boxes & 15) == 0, "hdy_seam_select: NULL or misaligned pointer");
+  long long chunk = (n_local + kSelMaxBlocks - 1) / kSelMaxBlocks;
+  chunk = ((chunk + kSelThreads - 1) / kSelThreads) * kSelThreads;
+  if (chunk < 4 * kSelThreads) chunk = 4 * kSelThreads;
+  const int nblocks = (int)((n_local + chunk - 1) / chunk);
+  const float4* b4 = reinterpret_cast<const float4*>(boxes);
+  const int hb = seam_hb(far_cap);
+  // block_scratch: [kSelMaxBlocks] block counts -> offsets, then the total
+  seam_count_kernel<<<nblocks, kSelThreads, 0, st>>>(b4, n_local, chunk, summaries, world, rank, hb, block_scratch);
+  select_scan_kernel<<<1, 1024, 0, st>>>(block_scratch, nblocks, block_scratch + kSelMaxBlocks);
+  seam_block_header_kernel<<<1, 32, 0, st>>>(block_scratch + kSelMaxBlocks, block);
+  seam_write_kernel<<<nblocks, kSelThreads, 0, st>>>(b4, scores, n_local, chunk, summaries, world, rank, hb,
+                                                     block_scratch, seam_cap, sel, block);
+  return check_launch("hdy_seam_select");
+}
+
+int hdy_seam_scatter(const int32_t* payloads, const int32_t* summaries, int world, int rank, int far_cap, int seam_cap,
+                     int64_t n_local, int64_t rep_cap, float* boxes, float* scores, uint32_t* rep_gidx, int32_t* meta,
+                     hdy_stream_t stream) {
+  HDY_REQUIRE(world >= 1 && world <= kSeamMaxWorld && rank >= 0 && rank < world && far_cap >= 0 && seam_cap >= 0 &&
+                  n_local >= 0 && rep_cap >= 0,
+              "hdy_seam_scatter: bad arguments");
+  HDY_REQUIRE(payloads && summaries && boxes && scores && rep_gidx && meta && ((uintptr_t)boxes & 15) == 0,
+              "hdy_seam_scatter: NULL or misaligned pointer");
+  dim3 grid((unsigned)(seam_cap / 1024 + 1), (unsigned)world);
+  if (grid.x > 64) grid.x = 64;
+  seam_scatter_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(payloads, summaries, world, rank, seam_hb(far_cap),
+                                                            seam_pb(seam_cap), far_cap, seam_cap, n_local, rep_cap,
+                                                            reinterpret_cast<float4*>(boxes), scores, rep_gidx, meta);
+  return check_launch("hdy_seam_scatter");
+}
+
+int hdy_seam_dirty_tiles(const int32_t* summaries, int world, int far_cap, const float* tile_rois, int n_tiles,
+                         uint8_t* dirty, hdy_stream_t stream) {
+  HDY_REQUIRE(world >= 1 && far_cap >= 0 && n_tiles >= 0, "hdy_seam_dirty_tiles: bad sizes");
+  if (n_tiles == 0) return HDY_OK;
+  HDY_REQUIRE(summaries && tile_rois && dirty && ((uintptr_t)tile_rois & 15) == 0,
+              "hdy_seam_dirty_tiles: NULL or misaligned pointer");
+  seam_dirty_tiles_kernel<<<(unsigned)((n_tiles + 127) / 128), 128, 0, (cudaStream_t)stream>>>(
+      summaries, world, seam_hb(far_cap), far_cap, reinterpret_cast<const float4*>(tile_rois), n_tiles, dirty);
+  return check_launch("hdy_seam_dirty_tiles");
+}
+
+int hdy_seam_build(const float* boxes, const float* scores, const uint32_t* rep_gidx, const int32_t* meta,
+                   const int32_t* tile_id, int tile_base, const float* tile_cores, const uint8_t* tile_dirty,
+                   int64_t n_max, int64_t n_local, float conf_thres, float iou_thres, uint8_t* state, void* workspace,
+                   size_t workspace_bytes, hdy_stream_t stream) {
+  HDY_REQUIRE(meta && rep_gidx, "hdy_seam_build: NULL pointer");
+  MergeIn in;
+  in.boxes = reinterpret_cast<const float4*>(boxes);
+  in.scores = scores;
+  in.gidx = nullptr;
+  in.rep_gidx = rep_gidx;
+  in.gidx_base_dev = reinterpret_cast<const uint32_t*>(meta + SM_GBASE);
+  in.tile_base = tile_base;
+  in.tile_id = tile_id;
+  in.tile_cores = reinterpret_cast<const float4*>(tile_cores);
+  in.tile_dirty = tile_dirty;
+  in.margin = reinterpret_cast<const float*>(meta + SM_MARGIN);
+  in.n_dev = reinterpret_cast<const long long*>(meta + SM_NTOTAL);
+  in.n_max = n_max;
+  in.n_local = n_local;
+  in.gidx_base = 0;
+  in.conf = conf_thres;
+  in.thr = iou_thres;
+  return merge_build_common(in, tile_cores, state, workspace, workspace_bytes, (cudaStream_t)stream);
+}
+
+int hdy_seam_export(void* workspace, int64_t n_max, const uint8_t* state, const int32_t* sel, const int32_t* my_block,
+                    int seam_cap, uint8_t* out, hdy_stream_t stream) {
+  HDY_REQUIRE(workspace && n_max >= 0 && seam_cap >= 0, "hdy_seam_export: bad arguments");
+  if (seam_cap == 0 || n_max == 0) return HDY_OK;
+  HDY_REQUIRE(state && sel && my_block && out, "hdy_seam_export: NULL pointer");
+  MergeWs w = merge_layout(workspace, n_max);
+  seam_export_kernel<<<blocks_for(seam_cap, 256, 148), 256, 0, (cudaStream_t)stream>>>(w.pos, w.cstate, state, sel,
+                                                                                    my_block, seam_cap, out);
+  return check_launch("hdy_seam_export");
+}
+
+int hdy_seam_import(void* workspace, int64_t n_max, int64_t n_local, const uint8_t* states, const int32_t* payloads,
+                    int32_t* meta, int world, int rank, int seam_cap, int exchange, hdy_stream_t stream) {
+  HDY_REQUIRE(workspace && n_max >= 0 && n_local >= 0 && world >= 1 && world <= kSeamMaxWorld && rank >= 0 &&
+                  rank < world && seam_cap >= 0 && exchange >= 0,
+              "hdy_seam_import: bad arguments");
+  HDY_REQUIRE(states && payloads && meta, "hdy_seam_import: NULL pointer");
+  MergeWs w = merge_layout(workspace, n_max > 0 ? n_max : 1);
+  dim3 grid((unsigned)(seam_cap / 1024 + 1), (unsigned)world);
+  if (grid.x > 64) grid.x = 64;
+  seam_import_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(w.pos, w.cstate, n_local, states, payloads,
+                                                           seam_pb(seam_cap), meta, world, rank, seam_cap, exchange);
+  return check_launch("hdy_seam_import");
 }
 
 int hdy_merge_rounds(void* workspace, int64_t n_max, float iou_thres, int first_round, int n_rounds,

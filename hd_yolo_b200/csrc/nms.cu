@@ -441,7 +441,12 @@ __global__ void gather_logits_kernel(const __grid_constant__ LevelTable T,
     const int rr = row - L.row_offset;
     const size_t o = (size_t)tile * max_det + d;
     float* os = out_scores + o * ns;
-    if (T.layout == 0) {
+    if (T.layout == 0 && T.dtype == HDY_F16) {
+      const size_t e0 = ((size_t)tile * L.rows + rr) * no;
+      for (int c = 0; c < ns; ++c) os[c] = sigmoidf_ref(level_elem<true>(L.ptr, e0 + 4 + c));
+      if (out_extra)
+        for (int c = 0; c < ne; ++c) out_extra[o * ne + c] = level_elem<true>(L.ptr, e0 + 5 + nc + c);
+    } else if (T.layout == 0) {
       const float* r = L.ptr + ((size_t)tile * L.rows + rr) * no;
       for (int c = 0; c < ns; ++c) os[c] = sigmoidf_ref(r[4 + c]);
       if (out_extra)
@@ -502,7 +507,13 @@ __global__ void select_scores_kernel(float* __restrict__ scores, const int32_t* 
 // G lanes per survivor (G = 8, 16 or 32 >= 1 + nc), 32 / G survivors per warp: one sigmoid evaluation, one round of
 // hierarchical-score shuffles and one select scan serve all of the warp's survivors, and their scattered row loads
 // are in flight together.
-template <int G>
+template <bool HALF>
+__device__ __forceinline__ float row_elem(const unsigned char* rp, size_t j) {
+  if (HALF) return __half2float(*reinterpret_cast<const __half*>(rp + j * 2));
+  return __ldg(reinterpret_cast<const float*>(rp + j * 4));
+}
+
+template <int G, bool HALF>
 __global__ void __launch_bounds__(256) gather_select_logits_kernel(
     const __grid_constant__ LevelTable T, const int32_t* __restrict__ keep_idx,
     const int32_t* __restrict__ keep_counts, int max_det, const __grid_constant__ HierOps H, float conf_thres,
@@ -524,17 +535,18 @@ __global__ void __launch_bounds__(256) gather_select_logits_kernel(
     if (row >= T.lv[i].row_offset) l = i;
   const LevelDev& L = T.lv[l];
   const int rr = row - L.row_offset;
-  const float* rp;
+  constexpr int kEsz = HALF ? 2 : 4;
+  const unsigned char* rp;  // first element of the survivor's row (fp16 rows exist in layout 0 only)
   int cs = 1;
   if (T.layout == 0) {
-    rp = L.ptr + ((size_t)tile * L.rows + rr) * no;
+    rp = reinterpret_cast<const unsigned char*>(L.ptr) + ((size_t)tile * L.rows + rr) * no * kEsz;
   } else {
     const int plane = L.ny * L.nx;
     const int a = rr / plane, p = rr - a * plane;
-    rp = L.ptr + ((size_t)(tile * T.na + a) * no) * plane + p;
+    rp = reinterpret_cast<const unsigned char*>(L.ptr + ((size_t)(tile * T.na + a) * no) * plane + p);
     cs = plane;
   }
-  float sc = g < ns ? sigmoidf_ref(rp[(size_t)(4 + g) * cs]) : 0.f;
+  float sc = g < ns ? sigmoidf_ref(row_elem<HALF>(rp, (size_t)(4 + g) * cs)) : 0.f;
   // hierarchical_scores: x[:, dst] *= x[:, src], in order
   for (int i = 0; i < H.n; ++i) {
     const float vs = __shfl_sync(0xffffffffu, sc, H.src[i], G);
@@ -565,9 +577,9 @@ __global__ void __launch_bounds__(256) gather_select_logits_kernel(
     float v[SPW];
 #pragma unroll
     for (int j = 0; j < SPW; ++j) {
-      const float* rj = (const float*)(uintptr_t)__shfl_sync(0xffffffffu, rp_bits, j * G);
+      const unsigned char* rj = (const unsigned char*)(uintptr_t)__shfl_sync(0xffffffffu, rp_bits, j * G);
       const int csj = __shfl_sync(0xffffffffu, cs, j * G);
-      v[j] = (d0 + j < k && lane < ne) ? __ldg(rj + (size_t)(5 + nc + lane) * csj) : 0.f;
+      v[j] = (d0 + j < k && lane < ne) ? row_elem<HALF>(rj, (size_t)(5 + nc + lane) * csj) : 0.f;
     }
 #pragma unroll
     for (int j = 0; j < SPW; ++j)
@@ -576,11 +588,11 @@ __global__ void __launch_bounds__(256) gather_select_logits_kernel(
     const unsigned long long rp_bits = (unsigned long long)(uintptr_t)rp;
 #pragma unroll
     for (int j = 0; j < SPW; ++j) {
-      const float* rj = (const float*)(uintptr_t)__shfl_sync(0xffffffffu, rp_bits, j * G);
+      const unsigned char* rj = (const unsigned char*)(uintptr_t)__shfl_sync(0xffffffffu, rp_bits, j * G);
       const int csj = __shfl_sync(0xffffffffu, cs, j * G);
       if (d0 + j >= k) break;  // warp-uniform
       float* oe = out_extra + ((size_t)tile * max_det + d0 + j) * ne;
-      for (int c = lane; c < ne; c += 32) oe[c] = rj[(size_t)(5 + nc + c) * csj];
+      for (int c = lane; c < ne; c += 32) oe[c] = row_elem<HALF>(rj, (size_t)(5 + nc + c) * csj);
     }
   }
 }
@@ -719,15 +731,18 @@ int hdy_gather_select_logits(const hdy_level_t* levels_host, int nl, int bs, int
   const int per_cta = 8 * (32 / G);
   dim3 grid((unsigned)((max_det + per_cta - 1) / per_cta), (unsigned)bs);
   cudaStream_t st = (cudaStream_t)stream;
-  if (G == 8)
-    gather_select_logits_kernel<8><<<grid, 256, 0, st>>>(T, keep_idx, keep_counts, max_det, H, conf_thres, out_scores,
-                                                         out_level, out_extra, out_score, out_label);
-  else if (G == 16)
-    gather_select_logits_kernel<16><<<grid, 256, 0, st>>>(T, keep_idx, keep_counts, max_det, H, conf_thres, out_scores,
-                                                          out_level, out_extra, out_score, out_label);
-  else
-    gather_select_logits_kernel<32><<<grid, 256, 0, st>>>(T, keep_idx, keep_counts, max_det, H, conf_thres, out_scores,
-                                                          out_level, out_extra, out_score, out_label);
+#define HDY_GS(GG, HH)                                                                                          \
+  gather_select_logits_kernel<GG, HH><<<grid, 256, 0, st>>>(T, keep_idx, keep_counts, max_det, H, conf_thres,     \
+                                                            out_scores, out_level, out_extra, out_score, out_label)
+  const bool half = T.dtype == HDY_F16;
+  if (G == 8) {
+    if (half) HDY_GS(8, true); else HDY_GS(8, false);
+  } else if (G == 16) {
+    if (half) HDY_GS(16, true); else HDY_GS(16, false);
+  } else {
+    if (half) HDY_GS(32, true); else HDY_GS(32, false);
+  }
+#undef HDY_GS
   return check_launch("hdy_gather_select_logits");
 }
 

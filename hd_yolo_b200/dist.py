@@ -5,36 +5,51 @@ Reference semantics: ``Ensemble.merge`` (metayolo/models/yolo.py:165-204) applie
 order (hnet/utils.py:37-62).  The reference runs this on one device; here every rank owns a contiguous range of tiles
 (bands of tile rows), so the slide-wide concatenation is rank 0's rows, then rank 1's, ...
 
-Only detections near a band boundary can interact across ranks.  The exchange is:
+Only detections near a band boundary can interact across ranks.  Everything variable-sized travels in FIXED-SIZE
+blocks whose fill counts stay on the device (include/hd_yolo_b200.h, "Multi-GPU form of T3"), so one merge is
 
-  1. all-gather of each rank's detection bounding rectangle (4 floats);
-  2. a rank's SEAM rows = rows whose box intersects another rank's rectangle; one padded all-gather of
-     (box, score, global index) of the seam rows -- ~1 % of the slide, a few MB;
-  3. every rank builds the sparse merge structure (csrc/merge.cu) over its own rows + the other ranks' seam rows
-     ("replicas": they take part in every IoU test, but their verdicts are never computed locally);
-  4. loop: a few fixed-point rounds locally -> export the verdicts of the own seam rows -> all-gather (1 byte per seam
-     row) -> import them into the replica slots; stop when no seam row is undecided anywhere;
-  5. finish: remaining local rounds, verdict per own row.
+    summary block      -> all-gather #1   (detection rectangle, overhang margin, row count, far-reaching boxes)
+    seam select + pack -> all-gather #2   (own rows touching another rank's rectangle: box, score, global index)
+    scatter replicas behind the own rows, dirty tiles, build the sparse merge structure (csrc/merge.cu)
+    { rounds -> export seam verdicts -> all-gather #3/#4 (1 byte per seam row) -> import } x 2
+    rounds -> finish -> (ordering of the survivors) -> ONE device->host read of 384 bytes
+
+with no host synchronisation between the steps: four collectives and one read where the first version needed seven
+collectives and eight blocking reads.  The read tells whether any seam row was still undecided at the last exchange
+(then the loop goes on, identically on every rank) or a payload outgrew its block (then the block is enlarged and the
+merge repeated).
 
 The result is bit-identical to the single-device merge (and hence to torchvision's dense NMS): a row's verdict depends
 only on higher-ranked rows its box intersects, all of which are local rows or replicas, and rank order uses the global
 index for ties.  No kernel waits on another rank; collectives are ordinary NCCL calls between kernel launches.
 
-``ShardedMerge`` is written as explicit phases so that the same code runs (a) under torch.distributed
-(``merge_sharded``), (b) as W emulated ranks inside one process on one GPU (``merge_emulated``; used by the GPU tests),
-and (c) on CPU tensors with a stand-in backend (the gloo tests of the host logic).
+The driver (``seam_merge``) talks to two small interfaces so that the same code runs (a) under torch.distributed
+(``TorchDistComm``), (b) as W emulated ranks inside one process on one GPU (``ThreadGroup``: one thread per rank,
+used by the GPU parity tests -- through SlidePostprocessor itself), and (c) on CPU tensors with a stand-in backend
+over gloo (tests/cpu_merge_backend.py: the host logic without a GPU).
 """
 from __future__ import annotations
 
+import threading
 from typing import Callable, Dict, List, Optional, Sequence, Tuple
 
 import torch
 
+from . import _lib
+
 STATE_UNKNOWN, STATE_KEPT, STATE_SUPPRESSED, STATE_DROPPED, STATE_REMOTE_UNKNOWN = 0, 1, 2, 3, 4
 ROUNDS_PER_EXCHANGE = 4
+EXCHANGES_PER_READ = 2
 MAX_ROUNDS = 64
+HDR, FAR_W, ROW_W, META_W = (_lib.HDY_SEAM_HDR_WORDS, _lib.HDY_SEAM_FAR_WORDS, _lib.HDY_SEAM_ROW_WORDS,
+                             _lib.HDY_SEAM_META_WORDS)
+# meta words (see hdy_seam_scatter); [6] and [7] are spare: the driver parks the finish status and the survivor count
+# there so that one copy brings everything back
+M_NTOTAL, M_MARGIN, M_GBASE, M_FLAGS, M_FAR, M_STATUS, M_KEPT, M_UNDECIDED, M_REP_OFF, M_OWN_SEAM = 0, 2, 3, 4, 5, 6, 7, 8, 16, 88
+FLAG_PAYLOAD, FLAG_REPLICA, FLAG_FAR, FLAG_TOO_MANY = 1, 2, 4, 8
 
-__all__ = ["shard_tile_rows", "ShardedMerge", "merge_sharded", "merge_emulated", "DeviceMergeBackend"]
+__all__ = ["shard_tile_rows", "seam_merge", "SeamOverflow", "merge_sharded", "merge_emulated", "DeviceSeamBackend", "TorchDistComm",
+           "ThreadGroup", "SoloComm", "run_emulated"]
 
 
 # ------------------------------------------------------------------------------------------------ tile sharding
@@ -57,281 +72,288 @@ def shard_tile_rows(rois: torch.Tensor, world: int) -> List[Tuple[int, int]]:
     return out
 
 
-_SCRATCH = None
+# ------------------------------------------------------------------------------------------------ collectives
+class SoloComm:
+    rank, world = 0, 1
+
+    def all_gather(self, t: torch.Tensor, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+        return t[None]
 
 
-def _scratch():
-    global _SCRATCH
-    if _SCRATCH is None:
-        from .ops import _Scratch
-        _SCRATCH = _Scratch()
-    return _SCRATCH
+class TorchDistComm:
+    """all_gather_into_tensor over a torch.distributed group (NCCL on the GPUs, gloo in the CPU tests)."""
+
+    def __init__(self, group=None):
+        import torch.distributed as dist
+        self.group = group
+        self.rank, self.world = dist.get_rank(group), dist.get_world_size(group)
+
+    def all_gather(self, t: torch.Tensor, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+        import torch.distributed as dist
+        t = t.contiguous()
+        if out is None or out.shape != (self.world,) + tuple(t.shape) or out.dtype != t.dtype:
+            out = torch.empty((self.world,) + tuple(t.shape), dtype=t.dtype, device=t.device)
+        if t.device.type == "cuda":
+            dist.all_gather_into_tensor(out, t, group=self.group)
+        else:   # gloo has no all_gather_into_tensor
+            dist.all_gather(list(out.unbind(0)), t, group=self.group)
+        return out
 
 
-def _scratch_rows(dev, name: str, n: int, cols: int, dtype) -> torch.Tensor:
-    """[n, cols] (or [n]) view of a grow-only scratch buffer."""
-    esz = torch.empty((), dtype=dtype).element_size()
-    buf = _scratch().get(dev, name, max(n, 1) * max(cols, 1) * esz)
-    t = buf[:max(n, 1) * max(cols, 1) * esz].view(dtype)
-    return t.view(max(n, 1), cols) if cols > 1 else t
+class ThreadGroup:
+    """W ranks emulated by W threads of one process (one device, one stream): a collective is a barrier and a stack.
+    Stream order makes it safe: every rank enqueues its producer kernels before the barrier and its copy after it."""
+
+    def __init__(self, world: int):
+        self.world = int(world)
+        self.barrier = threading.Barrier(self.world)
+        self.slots: List[Optional[torch.Tensor]] = [None] * self.world
+
+    def comm(self, rank: int) -> "ThreadComm":
+        return ThreadComm(self, rank)
+
+
+class ThreadComm:
+    def __init__(self, group: ThreadGroup, rank: int):
+        self.g, self.rank, self.world = group, int(rank), group.world
+
+    def all_gather(self, t: torch.Tensor, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+        g = self.g
+        g.slots[self.rank] = t
+        g.barrier.wait()
+        res = torch.stack(list(g.slots))
+        g.barrier.wait()   # nobody overwrites a slot before every rank has read it
+        return res
+
+
+def run_emulated(world: int, fn: Callable[[int, ThreadComm], object]) -> List[object]:
+    """fn(rank, comm) on `world` threads; returns the results in rank order, re-raises the first failure."""
+    g = ThreadGroup(world)
+    out: List[object] = [None] * world
+    err: List[Optional[BaseException]] = [None] * world
+    dev = torch.cuda.current_device() if torch.cuda.is_available() else None
+
+    def work(r):
+        try:
+            if dev is not None:
+                torch.cuda.set_device(dev)
+            out[r] = fn(r, g.comm(r))
+        except BaseException as e:   # noqa: BLE001 -- release the ranks waiting at the barrier
+            err[r] = e
+            g.barrier.abort()
+
+    th = [threading.Thread(target=work, args=(r,)) for r in range(world)]
+    for t in th:
+        t.start()
+    for t in th:
+        t.join()
+    real = [e for e in err if e is not None and not isinstance(e, threading.BrokenBarrierError)]
+    if real or any(err):
+        raise (real or [e for e in err if e is not None])[0]
+    return out
 
 
 # ------------------------------------------------------------------------------------------------ device backend
-class DeviceMergeBackend:
-    """The C-ABI merge steps (hdy_merge_build / rounds / export_states / import_states / finish) over one rank's rows.
-    boxes [n,4] fp32, scores [n] fp32, gidx [n] int32 (global index, bit pattern of a uint32); rows >= n_local are
-    replicas."""
+class DeviceSeamBackend:
+    """The C-ABI steps (hdy_seam_* + hdy_merge_rounds / finish) of one rank, with the rank's persistent buffers."""
 
-    def __init__(self, boxes, scores, gidx, n_local: int, conf_thres: float, iou_thres: float, tile_id=None,
-                 cores=None, margin=None, dirty=None, slot: int = 0):
-        import ctypes as C
+    def __init__(self, device, rank: int, world: int, conf_thres: float, iou_thres: float, seam_cap: int = 65536,
+                 far_cap: int = 1024):
+        from .ops import _Scratch, _conf_thr_f32, _iou_thr_f32
+        self.dev = torch.device(device)
+        self.rank, self.world = int(rank), int(world)
+        if self.world > _lib.HDY_SEAM_MAX_WORLD:
+            raise _lib.HdyError(f"at most {_lib.HDY_SEAM_MAX_WORLD} ranks")
+        self.conf, self.iou = _conf_thr_f32(conf_thres), _iou_thr_f32(iou_thres)
+        self.far_cap = int(far_cap)
+        self._scr = _Scratch()
+        self.meta = torch.zeros((META_W,), dtype=torch.int32, device=self.dev)
+        self.block_scratch = torch.empty((4097,), dtype=torch.int32, device=self.dev)
+        self.summary_block = torch.empty((HDR + FAR_W * self.far_cap,), dtype=torch.int32, device=self.dev)
+        self._no_far = torch.zeros((1,), dtype=torch.int32, device=self.dev)
+        self.set_seam_cap(seam_cap)
 
-        from . import _lib
-        from .ops import _Scratch, _call, _conf_thr_f32, _iou_thr_f32, _need_cuda, _stream
-        from ._lib import ptr
+    def set_seam_cap(self, seam_cap: int) -> None:
+        self.seam_cap = int(seam_cap)
+        d = self.dev
+        self.payload_block = torch.empty((HDR + ROW_W * self.seam_cap,), dtype=torch.int32, device=d)
+        self.sel = torch.empty((max(self.seam_cap, 1),), dtype=torch.int32, device=d)
+        self.rep_gidx = torch.empty((max(self.rep_cap, 1),), dtype=torch.int32, device=d)
+        self.states_out = torch.zeros((max(self.seam_cap, 1),), dtype=torch.uint8, device=d)
 
-        _need_cuda(boxes, "boxes")
-        self._call, self._ptr, self._stream = _call, ptr, _stream
-        self.n = int(boxes.shape[0])
-        self.n_local = int(n_local)
-        dev = boxes.device
-        self.boxes = boxes.contiguous()
-        if self.boxes.data_ptr() % 16:
-            self.boxes = self.boxes.clone()
-        self.scores = scores.contiguous()
-        self.gidx = gidx.contiguous()
-        self.iou = _iou_thr_f32(iou_thres)
-        self.status = torch.zeros((1,), dtype=torch.int32, device=dev)
+    @property
+    def rep_cap(self) -> int:
+        return (self.world - 1) * self.seam_cap
+
+    def _c(self, name, *args, launches=1):
+        from .ops import _call
+        _call(name, *args, launches=launches)
+
+    def _st(self):
+        from .ops import _stream
+        return _stream()
+
+    # -- steps ----------------------------------------------------------------------------------
+    def summary(self, boxes, n_local: int, overhang=None, tile_base: int = 0) -> torch.Tensor:
+        p = _lib.ptr
+        if overhang is not None:
+            margin, far_boxes, far_tile, far_count = overhang
+            self._c("hdy_seam_summary", p(boxes), n_local, p(margin), p(far_boxes), p(far_tile), p(far_count),
+                    int(far_boxes.shape[0]), int(tile_base), self.far_cap, p(self.summary_block), self._st(), launches=2)
+        else:
+            self._c("hdy_seam_summary", p(boxes), n_local, None, None, None, None, 0, 0, self.far_cap,
+                    p(self.summary_block), self._st(), launches=2)
+        return self.summary_block
+
+    def select(self, boxes, scores, n_local: int, summaries) -> torch.Tensor:
+        p = _lib.ptr
+        self.summaries = summaries
+        self._c("hdy_seam_select", p(boxes), p(scores), n_local, p(summaries), self.world, self.rank, self.far_cap,
+                self.seam_cap, p(self.sel), p(self.payload_block), p(self.block_scratch), self._st(), launches=4)
+        return self.payload_block
+
+    def build(self, payloads, boxes, scores, n_local: int, tile_id=None, tile_base: int = 0, cores=None,
+              rois_all=None) -> None:
+        """boxes / scores have room for n_local + rep_cap rows: the replicas are written behind the own rows."""
+        p = _lib.ptr
         lib = _lib.load()
-        self.wbytes = lib.hdy_merge_workspace_bytes(max(self.n, 1))
-        # grow-only scratch (hundreds of MB per slide): a fresh torch.empty per merge churns the caching allocator
-        # (`slot` keeps the ranks apart when several are emulated inside one process)
-        self.state = _scratch().get(dev, f"dist_state{slot}", max(self.n, 1))[:max(self.n, 1)]
-        self.ws = _scratch().get(dev, f"dist_ws{slot}", self.wbytes)
+        self.payloads, self.n_local = payloads, int(n_local)
+        self.n_max = self.n_local + self.rep_cap
+        if boxes.shape[0] < self.n_max or scores.shape[0] < self.n_max:
+            raise _lib.HdyError(f"seam merge: the row arrays need room for {self.n_max} rows "
+                                f"({self.n_local} own + {self.rep_cap} replicas), have {boxes.shape[0]}")
+        self._c("hdy_seam_scatter", p(payloads), p(self.summaries), self.world, self.rank, self.far_cap, self.seam_cap,
+                self.n_local, self.rep_cap, p(boxes), p(scores), p(self.rep_gidx), p(self.meta), self._st())
+        dirty = None
         if cores is not None:
-            # interior shortcut (see SlideAccumulator.verdicts): rows beyond n_local are replicas and never take it
-            tid = torch.full((max(self.n, 1),), -1, dtype=torch.int32, device=dev)
-            tid[:self.n_local] = tile_id[:self.n_local]
-            self._keep = (tid, cores.contiguous(), margin.contiguous(), dirty)
-        tile_p, cores_p, margin_p, dirty_p = (ptr(t) for t in self._keep) if cores is not None else (None,) * 4
-        _call("hdy_merge_build", ptr(self.boxes), ptr(self.scores), ptr(self.gidx), 0, tile_p, cores_p, dirty_p, margin_p,
-              None, self.n,
-              self.n_local, _conf_thr_f32(conf_thres), self.iou, ptr(self.state), ptr(self.ws), self.wbytes, _stream(),
-              launches=7)
+            n_tiles = int(rois_all.shape[0])
+            dirty = self._scr.get(self.dev, "dirty", max(n_tiles, 1))
+            self._c("hdy_seam_dirty_tiles", p(self.summaries), self.world, self.far_cap, p(rois_all), n_tiles, p(dirty),
+                    self._st())
+        self.wbytes = lib.hdy_merge_workspace_bytes(max(self.n_max, 1))
+        self.ws = self._scr.get(self.dev, "merge_ws", self.wbytes)
+        self.state = self._scr.get(self.dev, "state", max(self.n_max, 1))
+        self._c("hdy_seam_build", p(boxes), p(scores), p(self.rep_gidx), p(self.meta),
+                p(tile_id) if cores is not None else None, int(tile_base), p(cores), p(dirty), self.n_max, self.n_local,
+                self.conf, self.iou, p(self.state), p(self.ws), self.wbytes, self._st(), launches=7)
 
     def rounds(self, first: int, n: int) -> None:
-        self._call("hdy_merge_rounds", self._ptr(self.ws), self.n, self.iou, first, n, self._stream(), launches=n)
+        self._c("hdy_merge_rounds", _lib.ptr(self.ws), self.n_max, self.iou, first, n, self._st(), launches=3 * n)
 
-    def export_states(self, sel: torch.Tensor) -> torch.Tensor:
-        out = torch.empty((sel.numel(),), dtype=torch.uint8, device=sel.device)
-        if sel.numel():
-            self._call("hdy_merge_export_states", self._ptr(self.ws), self.n, self._ptr(self.state), self._ptr(sel),
-                       sel.numel(), self._ptr(out), self._stream())
-        return out
+    def export(self) -> torch.Tensor:
+        p = _lib.ptr
+        self._c("hdy_seam_export", p(self.ws), self.n_max, p(self.state), p(self.sel), p(self.payload_block),
+                self.seam_cap, p(self.states_out), self._st())
+        return self.states_out
 
-    def import_states(self, first: int, states: torch.Tensor) -> None:
-        if states.numel():
-            states = states.contiguous()
-            self._call("hdy_merge_import_states", self._ptr(self.ws), self.n, first, self._ptr(states), states.numel(),
-                       self._stream())
+    def import_(self, states_all, exchange: int) -> None:
+        p = _lib.ptr
+        self._c("hdy_seam_import", p(self.ws), self.n_max, self.n_local, p(states_all), p(self.payloads), p(self.meta),
+                self.world, self.rank, self.seam_cap, int(exchange), self._st())
 
-    def finish(self) -> Tuple[torch.Tensor, bool]:
-        """-> (verdict per own row [n_local] uint8, converged)"""
-        self.status.zero_()
-        self._call("hdy_merge_finish", self._ptr(self.ws), None, self.n, self._ptr(self.state), self._ptr(self.status),
-                   self._stream())
-        ok = not (int(self.status.item()) & 2)
-        return self.state[:self.n_local], ok
+    def finish(self) -> torch.Tensor:
+        """Verdict per own row [n_local] uint8; the status word lands in meta[M_STATUS]."""
+        p = _lib.ptr
+        self.meta[M_STATUS:M_STATUS + 1].zero_()
+        st_ptr = __import__("ctypes").c_void_p(self.meta.data_ptr() + 4 * M_STATUS)
+        self._c("hdy_merge_finish", p(self.ws), p(self.meta), self.n_max, p(self.state), st_ptr, self._st())
+        return self.state[:self.n_local]
+
+    def read_meta(self) -> List[int]:
+        return self.meta.cpu().tolist()
 
 
 # ------------------------------------------------------------------------------------------------ the protocol
-class ShardedMerge:
-    """One rank's side of the sharded Ensemble.merge.  Call the phases in order; what goes between them is a
-    collective over all ranks (see merge_sharded / merge_emulated)."""
+class SeamOverflow(RuntimeError):
+    """A rank's seam rows outgrew the payload block (or the replicas their room).  Raised identically on every rank;
+    `needed` is the block capacity (rows per rank) that would have sufficed."""
 
-    def __init__(self, rank: int, world: int, boxes: torch.Tensor, scores: torch.Tensor, conf_thres: float,
-                 iou_thres: float, backend: Callable = DeviceMergeBackend, tile_id=None, cores=None, margin=None,
-                 dirty=None):
-        self.rank, self.world = rank, world
-        self.boxes, self.scores = boxes, scores
-        self.tile_id, self.cores, self.margin, self.dirty = tile_id, cores, margin, dirty
-        self.conf, self.iou = conf_thres, iou_thres
-        self.n_local = int(boxes.shape[0])
-        self.backend_cls = backend
-        self.backend = None
-        self.round = 0
-
-    # phase 1 ------------------------------------------------------------------------------------
-    def local_summary(self) -> torch.Tensor:
-        """[5] fp32: bounding rectangle of the own detections (x1, y1, x2, y2; inverted if there are none) and the
-        largest overhang of an own box over its tile (0 without the interior shortcut)."""
-        b = self.boxes
-        m = self.margin.reshape(1).to(torch.float32) if self.margin is not None else \
-            torch.zeros((1,), dtype=torch.float32, device=b.device)
-        if self.n_local == 0:
-            big = 3.0e38
-            return torch.cat([torch.tensor([big, big, -big, -big], dtype=torch.float32, device=b.device), m])
-        return torch.cat([b[:, :2].min(0).values, b[:, 2:].max(0).values, m])
-
-    # phase 2 ------------------------------------------------------------------------------------
-    def select_seam(self, summaries: torch.Tensor, counts: Sequence[int]) -> torch.Tensor:
-        """summaries [world, 5] (all-gathered), counts: rows per rank.  Returns the padded-to-be seam payload
-        [m, 6] int32 = (box bits x4, score bits, global index) of the own seam rows."""
-        self.counts = [int(c) for c in counts]
-        self.base = sum(self.counts[:self.rank])
-        # boxes of any rank may stick out of their tiles: the shortcut needs the largest overhang anywhere
-        self.margin_all = float(summaries[:, 4].max()) if summaries.shape[1] > 4 else 0.0
-        if sum(self.counts) >= 2 ** 32:
-            raise ValueError("more than 2^32 detections in one slide")
-        b, dev = self.boxes, self.boxes.device
-        mask = torch.zeros((self.n_local,), dtype=torch.bool, device=dev)
-        for r in range(self.world):
-            if r == self.rank or self.counts[r] == 0:
-                continue
-            x1, y1, x2, y2 = [float(v) for v in summaries[r, :4]]
-            # closed-interval test: a superset of "boxes intersect", which is all exactness needs
-            mask |= (b[:, 2] >= x1) & (b[:, 0] <= x2) & (b[:, 3] >= y1) & (b[:, 1] <= y2)
-        self.sel = torch.nonzero(mask).flatten()                      # int64 rows, ascending
-        m = int(self.sel.numel())
-        pay = torch.empty((m, 6), dtype=torch.int32, device=dev)
-        if m:
-            pay[:, :4] = b[self.sel].contiguous().view(torch.int32)
-            pay[:, 4] = self.scores[self.sel].contiguous().view(torch.int32)
-            g = self.sel + self.base                                   # < 2^32: keep the low 32 bits' pattern
-            pay[:, 5] = torch.where(g >= 2 ** 31, g - 2 ** 32, g).to(torch.int32)
-        return pay
-
-    # phase 3 ------------------------------------------------------------------------------------
-    def build(self, payloads: Sequence[torch.Tensor]) -> None:
-        """payloads[r] = rank r's seam payload [m_r, 6] int32 (own entry ignored)."""
-        dev = self.boxes.device
-        others = [payloads[r] for r in range(self.world) if r != self.rank and payloads[r].numel()]
-        self.seam_sizes = [int(p.shape[0]) for p in payloads]
-        rep = torch.cat(others) if others else torch.empty((0, 6), dtype=torch.int32, device=dev)
-        self.n_rep = int(rep.shape[0])
-        n = self.n_local + self.n_rep
-        if dev.type == "cuda":
-            boxes = _scratch_rows(dev, f"dist_boxes{self.rank}", n, 4, torch.float32)
-            scores = _scratch_rows(dev, f"dist_scores{self.rank}", n, 1, torch.float32)
-            gidx = _scratch_rows(dev, f"dist_gidx{self.rank}", n, 1, torch.int32)
-        else:   # CPU stand-in backend (tests)
-            boxes = torch.empty((max(n, 1), 4), dtype=torch.float32, device=dev)
-            scores = torch.empty((max(n, 1),), dtype=torch.float32, device=dev)
-            gidx = torch.empty((max(n, 1),), dtype=torch.int32, device=dev)
-        boxes[:self.n_local] = self.boxes
-        scores[:self.n_local] = self.scores
-        g = torch.arange(self.n_local, device=dev, dtype=torch.int64) + self.base
-        gidx[:self.n_local] = torch.where(g >= 2 ** 31, g - 2 ** 32, g).to(torch.int32)
-        if self.n_rep:
-            boxes[self.n_local:n] = rep[:, :4].contiguous().view(torch.float32)
-            scores[self.n_local:n] = rep[:, 4].contiguous().view(torch.float32)
-            gidx[self.n_local:n] = rep[:, 5]
-        kw = {'slot': self.rank}
-        if self.cores is not None:
-            kw = dict(tile_id=self.tile_id, cores=self.cores, dirty=self.dirty, slot=self.rank,
-                      margin=torch.tensor([self.margin_all], dtype=torch.float32, device=dev))
-        self.backend = self.backend_cls(boxes[:n], scores[:n], gidx[:n], self.n_local, self.conf, self.iou, **kw)
-        self.round = 0
-
-    # phase 4 (repeated) -------------------------------------------------------------------------
-    def step_rounds(self) -> torch.Tensor:
-        """Runs a few local rounds; returns the verdicts of the own seam rows [m] uint8."""
-        n = min(ROUNDS_PER_EXCHANGE, MAX_ROUNDS - self.round)
-        if n <= 0:
-            raise RuntimeError("sharded merge did not converge within the round budget")
-        self.backend.rounds(self.round, n)
-        self.round += n
-        return self.backend.export_states(self.sel)
-
-    def step_import(self, states: Sequence[torch.Tensor]) -> bool:
-        """states[r] = rank r's seam verdicts [m_r].  Returns True when no seam row is undecided anywhere."""
-        others = [states[r] for r in range(self.world) if r != self.rank and states[r].numel()]
-        if others:
-            self.backend.import_states(self.n_local, torch.cat(others))
-        allst = torch.cat([s for s in states if s.numel()]) if any(s.numel() for s in states) else None
-        if allst is None:
-            return True
-        return not bool(((allst == STATE_UNKNOWN) | (allst == STATE_REMOTE_UNKNOWN)).any())
-
-    # phase 5 ------------------------------------------------------------------------------------
-    def finish(self) -> torch.Tensor:
-        # rows away from the seams may still be undecided: a few rounds at a time, one status read each (launching the
-        # whole remaining budget costs ~0.7 ms of no-op kernels per slide)
-        while True:
-            n = min(ROUNDS_PER_EXCHANGE, MAX_ROUNDS - self.round)
-            if n > 0:
-                self.backend.rounds(self.round, n)
-                self.round += n
-            state, ok = self.backend.finish()
-            if ok:
-                return state
-            if self.round >= MAX_ROUNDS:
-                raise RuntimeError("sharded merge: undecided rows left after the round budget")
+    def __init__(self, needed: int):
+        super().__init__(f"seam payload overflow: {needed} seam rows on one rank")
+        self.needed = int(needed)
 
 
-# ------------------------------------------------------------------------------------------------ drivers
-def _pad_gather(t: torch.Tensor, sizes: Sequence[int], group) -> List[torch.Tensor]:
-    """all_gather of per-rank tensors whose first dimension differs (sizes known to every rank)."""
-    import torch.distributed as dist
-
-    world = len(sizes)
-    mx = max(max(sizes), 1)
-    buf = torch.zeros((mx,) + tuple(t.shape[1:]), dtype=t.dtype, device=t.device)
-    buf[:t.shape[0]] = t
-    out = [torch.empty_like(buf) for _ in range(world)]
-    dist.all_gather(out, buf, group=group)
-    return [o[:s] for o, s in zip(out, sizes)]
-
-
-def merge_sharded(boxes: torch.Tensor, scores: torch.Tensor, conf_thres: float, iou_thres: float, group=None,
-                  backend: Callable = DeviceMergeBackend, tile_id=None, cores=None, margin=None,
-                  dirty=None) -> Dict[str, torch.Tensor]:
-    """Sharded Ensemble.merge verdicts under torch.distributed.  boxes [n_local, 4] / scores [n_local] are this rank's
-    rows of the slide-wide concatenation (rank order == tile order).  Returns {'state': uint8 [n_local],
-    'base': first global row of this rank, 'exchanges': number of verdict all-gathers, 'seam_rows': [world]}."""
-    import torch.distributed as dist
-
-    rank, world = dist.get_rank(group), dist.get_world_size(group)
-    sm = ShardedMerge(rank, world, boxes, scores, conf_thres, iou_thres, backend, tile_id, cores, margin, dirty)
-    dev = boxes.device
-    # 1. rectangles (+ overhang) + row counts
-    summ = [torch.empty((5,), dtype=torch.float32, device=dev) for _ in range(world)]
-    dist.all_gather(summ, sm.local_summary(), group=group)
-    cnt = [torch.empty((1,), dtype=torch.int64, device=dev) for _ in range(world)]
-    dist.all_gather(cnt, torch.tensor([sm.n_local], dtype=torch.int64, device=dev), group=group)
-    counts = [int(c) for c in torch.cat(cnt).tolist()]
-    # 2. seam payloads
-    pay = sm.select_seam(torch.stack(summ).cpu(), counts)
-    msz = [torch.empty((1,), dtype=torch.int64, device=dev) for _ in range(world)]
-    dist.all_gather(msz, torch.tensor([pay.shape[0]], dtype=torch.int64, device=dev), group=group)
-    sizes = [int(c) for c in torch.cat(msz).tolist()]
-    pays = _pad_gather(pay, sizes, group)
-    # 3. build, 4. rounds <-> verdict exchange
-    sm.build(pays)
-    exchanges = 0
+def seam_merge(comm, be, boxes: torch.Tensor, scores: torch.Tensor, n_local: int, overhang=None, tile_id=None,
+               tile_base: int = 0, cores=None, rois_all=None,
+               after_finish: Optional[Callable[[torch.Tensor], None]] = None) -> Dict[str, object]:
+    """One rank's side of the sharded Ensemble.merge.  boxes [>= n_local + be.rep_cap, 4] / scores: the own rows first
+    (the rest is scratch for the replicas).  after_finish(state) may enqueue more device work (ordering of the
+    survivors) before the single host read.  Returns {'state': uint8 [n_local], 'base': global index of own row 0,
+    'exchanges', 'seam_rows': [world], 'meta': the words read back}; raises SeamOverflow when be.seam_cap was too
+    small (grow it with be.set_seam_cap and call again)."""
+    summaries = comm.all_gather(be.summary(boxes, n_local, overhang, tile_base))
+    payloads = comm.all_gather(be.select(boxes, scores, n_local, summaries))
+    be.build(payloads, boxes, scores, n_local, tile_id, tile_base, cores, rois_all)
+    rnd = exchanges = 0
     while True:
-        st = sm.step_rounds()
-        sts = _pad_gather(st, sizes, group)
-        exchanges += 1
-        if sm.step_import(sts):
+        for _ in range(EXCHANGES_PER_READ):
+            be.rounds(rnd, ROUNDS_PER_EXCHANGE)
+            rnd += ROUNDS_PER_EXCHANGE
+            states = comm.all_gather(be.export())
+            be.import_(states, exchanges)
+            exchanges += 1
+        be.rounds(rnd, ROUNDS_PER_EXCHANGE)
+        rnd += ROUNDS_PER_EXCHANGE
+        state = be.finish()
+        if after_finish is not None:
+            after_finish(state)
+        meta = be.read_meta()                                   # the one device->host read
+        fl = meta[M_FLAGS]
+        if fl & FLAG_TOO_MANY:
+            raise ValueError("more than 2^32 detections in one slide")
+        if fl & (FLAG_PAYLOAD | FLAG_REPLICA):                  # the same flags on every rank
+            raise SeamOverflow(max(int(c) for c in payloads[:, 0].tolist()))
+        if not meta[M_UNDECIDED + ((exchanges - 1) & 7)]:
             break
-    return {'state': sm.finish(), 'base': sm.base, 'exchanges': exchanges, 'seam_rows': sizes}
+        if rnd + (EXCHANGES_PER_READ + 1) * ROUNDS_PER_EXCHANGE > MAX_ROUNDS:
+            raise RuntimeError("sharded merge did not converge within the round budget")
+    # every seam row is decided everywhere: what is left (if anything) is local
+    while meta[M_STATUS] & _lib.HDY_STATUS_ROUNDS:
+        if rnd >= MAX_ROUNDS:
+            raise RuntimeError("sharded merge: undecided rows left after the round budget")
+        n = min(ROUNDS_PER_EXCHANGE, MAX_ROUNDS - rnd)
+        be.rounds(rnd, n)
+        rnd += n
+        state = be.finish()
+        if after_finish is not None:
+            after_finish(state)
+        meta = be.read_meta()
+    off = meta[M_REP_OFF:M_REP_OFF + comm.world + 1]
+    seam_rows = [meta[M_OWN_SEAM] if q == comm.rank else off[q + 1] - off[q] for q in range(comm.world)]
+    return {'state': state, 'base': meta[M_GBASE] & 0xffffffff, 'exchanges': exchanges, 'seam_rows': seam_rows,
+            'meta': meta}
+
+
+# ------------------------------------------------------------------------------------------------ convenience drivers
+def merge_sharded(boxes: torch.Tensor, scores: torch.Tensor, conf_thres: float, iou_thres: float, group=None,
+                  backend: Callable = DeviceSeamBackend, comm=None, seam_cap: int = 4096, tile_id=None, tile_base=0,
+                  cores=None, rois_all=None, overhang=None) -> Dict[str, object]:
+    """Sharded Ensemble.merge verdicts for plain per-rank arrays: boxes [n_local, 4] / scores [n_local] are this rank's
+    rows of the slide-wide concatenation (rank order == tile order).  Collectives go over `comm` (default:
+    torch.distributed, `group`).  Returns seam_merge's dict."""
+    comm = comm if comm is not None else TorchDistComm(group)
+    be = backend(boxes.device, comm.rank, comm.world, conf_thres, iou_thres, seam_cap=seam_cap)
+    n_local = int(boxes.shape[0])
+    while True:
+        room = max(n_local + be.rep_cap, 1)
+        b = torch.zeros((room, 4), dtype=torch.float32, device=boxes.device)
+        s = torch.zeros((room,), dtype=torch.float32, device=boxes.device)
+        b[:n_local], s[:n_local] = boxes, scores
+        try:
+            res = seam_merge(comm, be, b, s, n_local, overhang, tile_id, tile_base, cores, rois_all)
+        except SeamOverflow as e:
+            be.set_seam_cap(int(e.needed * 1.25) + 1024)
+            continue
+        res['state'] = res['state'].clone()
+        return res
 
 
 def merge_emulated(parts: Sequence[Tuple[torch.Tensor, torch.Tensor]], conf_thres: float, iou_thres: float,
-                   backend: Callable = DeviceMergeBackend) -> List[torch.Tensor]:
-    """The same protocol with `len(parts)` ranks emulated inside one process (collectives become list passing).
-    parts[r] = (boxes, scores) of rank r.  Returns the verdicts per rank."""
-    world = len(parts)
-    sms = [ShardedMerge(r, world, b, s, conf_thres, iou_thres, backend) for r, (b, s) in enumerate(parts)]
-    summ = torch.stack([sm.local_summary().cpu() for sm in sms])
-    counts = [sm.n_local for sm in sms]
-    pays = [sm.select_seam(summ, counts) for sm in sms]
-    for sm in sms:
-        sm.build(pays)
-    while True:
-        sts = [sm.step_rounds() for sm in sms]
-        done = [sm.step_import(sts) for sm in sms]
-        if all(done):
-            break
-    return [sm.finish() for sm in sms]
+                   backend: Callable = DeviceSeamBackend, seam_cap: int = 4096) -> List[torch.Tensor]:
+    """The same protocol with `len(parts)` ranks emulated inside one process (one thread per rank, collectives through
+    a barrier).  parts[r] = (boxes, scores) of rank r.  Returns the verdicts per rank."""
+    def one(rank, comm):
+        b, s = parts[rank]
+        return merge_sharded(b, s, conf_thres, iou_thres, backend=backend, comm=comm, seam_cap=seam_cap)['state']
+
+    return run_emulated(len(parts), one)

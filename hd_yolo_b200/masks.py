@@ -21,12 +21,12 @@ import torch
 
 from . import _lib
 from ._lib import HdyError, ptr
-from .ops import _Scratch, _aligned16, _call, _need_cuda, _stream
+from .ops import _Scratch, _aligned16, _call, _need_cuda, _need_head_tensor, _stream
 
 _pm_scratch = _Scratch()
 
 __all__ = ["PackedMasks", "mask_select", "paste_masks_in_image", "paste_masks_packed", "process_mask",
-           "process_mask_batch", "process_mask_packed"]
+           "process_mask_batch", "process_mask_packed", "SlideMaskBuilder"]
 
 
 @dataclass
@@ -157,7 +157,7 @@ def paste_masks_packed(masks: torch.Tensor, boxes: torch.Tensor, img_shape, padd
 
 # ---------------------------------------------------------------------------------- process_mask (B)
 def _pm_args(protos, coef, boxes, counts):
-    _need_cuda(protos, "protos")
+    _need_head_tensor(protos, "protos")
     _need_cuda(coef, "masks_in")
     _need_cuda(boxes, "bboxes")
     if protos.dim() != 4 or coef.dim() != 3 or boxes.dim() != 3:
@@ -185,9 +185,11 @@ def process_mask_batch(protos: torch.Tensor, coef: torch.Tensor, boxes: torch.Te
     ih, iw = _hw(shape)
     oh, ow = (ih, iw) if upsample else (mh, mw)
     out = torch.empty((bs, md, oh, ow), dtype=torch.float32, device=protos.device)
+    coef = coef.float()
     if bs and md:
         ws, wbytes = _pm_workspace(protos.device, bs, md)
-        _call("hdy_process_mask", ptr(_aligned16(protos.contiguous())), ptr(coef.contiguous()),
+        _call("hdy_process_mask", ptr(_aligned16(protos.contiguous())), _need_head_tensor(protos, "protos"),
+              ptr(coef.contiguous()),
               ptr(_aligned16(boxes.contiguous())), ptr(counts), bs, md, nm, mh, mw, ih, iw, int(bool(upsample)),
               ptr(out), ptr(ws), wbytes, _stream(), launches=4)
     return out
@@ -198,22 +200,26 @@ def process_mask(protos: torch.Tensor, masks_in: torch.Tensor, bboxes: torch.Ten
     """ultralytics/yolov5 v7 ``process_mask(protos [c,mh,mw], masks_in [n,c], bboxes [n,4], shape (ih,iw),
     upsample=False)`` -> [n, mh, mw] (or [n, ih, iw] with upsample) of 0/1 floats:
     sigmoid(masks_in @ protos), crop to the box scaled into proto space, optional bilinear upsample, > 0.5."""
-    _need_cuda(protos, "protos")
+    _need_head_tensor(protos, "protos")
     if protos.dim() != 3:
         raise HdyError("protos must be [c, mh, mw]")
     n = masks_in.shape[0]
     ih, iw = _hw(shape)
     if n == 0:
         oh, ow = (ih, iw) if upsample else tuple(protos.shape[1:])
-        return protos.new_zeros((0, oh, ow))
+        return protos.new_zeros((0, oh, ow), dtype=torch.float32)
     counts = torch.full((1,), n, dtype=torch.int32, device=protos.device)
-    return process_mask_batch(protos[None], masks_in[None], bboxes[None, :, :4], counts, shape, upsample)[0]
+    return process_mask_batch(protos[None], masks_in.float()[None], bboxes.float()[None, :, :4], counts, shape,
+                              upsample)[0]
 
 
 def process_mask_packed(protos: torch.Tensor, coef: torch.Tensor, boxes: torch.Tensor, counts: torch.Tensor, shape,
-                        upsample: bool = False, capacity_words: Optional[int] = None) -> PackedMasks:
+                        upsample: bool = False, capacity_words: Optional[int] = None,
+                        row_state: Optional[torch.Tensor] = None,
+                        tile_offsets: Optional[torch.Tensor] = None) -> PackedMasks:
     """Bit-packed process_mask over a batch of tiles; mask index = tile * max_det + slot (empty for slots
-    >= counts[tile]).  Window coordinates are in output pixels ((ih,iw) with upsample, else (mh,mw))."""
+    >= counts[tile]).  Window coordinates are in output pixels ((ih,iw) with upsample, else (mh,mw)).
+    row_state [n] uint8 + tile_offsets [bs+1] int64 (slide form): only slots whose slide row was KEPT get a mask."""
     bs, nm, mh, mw, md = _pm_args(protos, coef, boxes, counts)
     ih, iw = _hw(shape)
     dev = protos.device
@@ -222,15 +228,68 @@ def process_mask_packed(protos: torch.Tensor, coef: torch.Tensor, boxes: torch.T
     geom = torch.empty((K, 4), dtype=torch.int32, device=dev)
     offsets = torch.empty((K + 1,), dtype=torch.int64, device=dev)
     status = torch.zeros((1,), dtype=torch.int32, device=dev)
-    _call("hdy_process_mask_geometry", ptr(boxes), ptr(counts), bs, md, mh, mw, ih, iw, int(bool(upsample)), ptr(geom),
-          ptr(offsets), _stream(), launches=2)
+    _call("hdy_process_mask_geometry", ptr(boxes), ptr(counts), bs, md, mh, mw, ih, iw, int(bool(upsample)),
+          ptr(row_state), ptr(tile_offsets), ptr(geom), ptr(offsets), _stream(), launches=2)
     words = int(offsets[K].item()) if capacity_words is None else int(capacity_words)
     bits = torch.empty((max(words, 1),), dtype=torch.int32, device=dev)
     if K:
         ws, wbytes = _pm_workspace(dev, bs, md)
-        _call("hdy_process_mask_packed", ptr(_aligned16(protos.contiguous())), ptr(coef.contiguous()), ptr(boxes),
+        _call("hdy_process_mask_packed", ptr(_aligned16(protos.contiguous())), _need_head_tensor(protos, "protos"),
+              ptr(coef.contiguous()), ptr(boxes),
               ptr(counts), ptr(geom), ptr(offsets), bs, md, nm, mh, mw, ih, iw, int(bool(upsample)), ptr(bits), words,
               ptr(status),
               ptr(ws), wbytes, _stream(), launches=3)
     oh, ow = (ih, iw) if upsample else (mh, mw)
     return PackedMasks(geom, offsets, bits[:words], oh, ow, status)
+
+
+class SlideMaskBuilder:
+    """Masks of a whole slide, computed AFTER the slide-level verdicts and only for the rows Ensemble.merge keeps
+    (yolo.py:197-202 gathers masks[keep]; the masks of suppressed duplicates are never materialised).  One
+    PackedMasks over the slide's rows: geom[r] is the window of row r in SLIDE pixels, offsets[r] its first word in the
+    slide-wide `bits`; rows that were not kept have empty windows.  Everything stays on the device; `check()` reads
+    the overflow flag."""
+
+    def __init__(self, n_rows: int, capacity_words: int, image_size, device):
+        d = torch.device(device)
+        self.n = int(n_rows)
+        self.capacity_words = int(capacity_words)
+        self.geom = torch.zeros((max(self.n, 1), 4), dtype=torch.int32, device=d)
+        self.offsets = torch.zeros((self.n + 1,), dtype=torch.int64, device=d)
+        self.bits = torch.empty((max(self.capacity_words, 1),), dtype=torch.int32, device=d)
+        self.cursor2 = torch.zeros((2,), dtype=torch.int64, device=d)
+        self.status = torch.zeros((1,), dtype=torch.int32, device=d)
+        self.batches = 0
+        self.H, self.W = _hw(image_size)
+
+    def add_batch(self, protos: torch.Tensor, coef: torch.Tensor, boxes: torch.Tensor, counts: torch.Tensor,
+                  tile_offsets: torch.Tensor, rois: torch.Tensor, row_state: torch.Tensor, shape,
+                  upsample: bool = True) -> None:
+        """protos [bs,nm,mh,mw] of the batch's tiles; coef / boxes / counts as DetectBatch holds them (tile
+        coordinates); tile_offsets [bs+1] from the append; rois [bs,4]; row_state: verdict per slide row."""
+        bs, nm, mh, mw, md = _pm_args(protos, coef, boxes, counts)
+        ih, iw = _hw(shape)
+        dev = protos.device
+        K = bs * md
+        if K == 0:
+            return
+        boxes = _aligned16(boxes.contiguous())
+        geom = _pm_scratch.get(dev, "slide_geom", K * 16).view(torch.int32)[:K * 4]
+        offsets = _pm_scratch.get(dev, "slide_offsets", (K + 1) * 8).view(torch.int64)[:K + 1]
+        _call("hdy_process_mask_geometry", ptr(boxes), ptr(counts), bs, md, mh, mw, ih, iw, int(bool(upsample)),
+              ptr(row_state), ptr(tile_offsets), ptr(geom), ptr(offsets), _stream(), launches=2)
+        _call("hdy_process_mask_rows", ptr(geom), ptr(offsets), ptr(counts), ptr(tile_offsets),
+              ptr(_aligned16(rois.contiguous())), bs, md, ptr(self.cursor2), self.batches & 1, ptr(self.geom),
+              ptr(self.offsets), _stream())
+        ws, wbytes = _pm_workspace(dev, bs, md)
+        _call("hdy_process_mask_packed", ptr(_aligned16(protos.contiguous())), _need_head_tensor(protos, "protos"),
+              ptr(coef.contiguous()), ptr(boxes),
+              ptr(counts), ptr(geom), ptr(offsets), bs, md, nm, mh, mw, ih, iw, int(bool(upsample)), ptr(self.bits),
+              self.capacity_words, ptr(self.status), ptr(ws), wbytes, _stream(), launches=3)
+        self.batches += 1
+
+    def finish(self) -> PackedMasks:
+        """offsets[n] = total words.  Rows that were never live keep offset 0 / an empty window: consumers address a
+        mask through geom[r] and offsets[r] only."""
+        self.offsets[self.n:self.n + 1].copy_(self.cursor2[self.batches & 1:(self.batches & 1) + 1])
+        return PackedMasks(self.geom[:self.n], self.offsets, self.bits, self.H, self.W, self.status)

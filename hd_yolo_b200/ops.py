@@ -9,6 +9,7 @@ rejected: there is no fallback path.
 from __future__ import annotations
 
 import ctypes as C
+import threading
 from dataclasses import dataclass
 from typing import Dict, List, Optional, Sequence, Tuple
 
@@ -117,13 +118,24 @@ class CapturedStep:
     capacities given, no ``to_list()``): its ~10 kernel launches and ~25 small allocations cost more host time than the
     kernels take on a B200 at 640-px batches, so a serving loop replays the graph instead.  ``fn`` must read its inputs
     from buffers that stay in place (write the next batch into them before calling); the returned object of the capture
-    is handed back by every replay and is overwritten in place."""
+    is handed back by every replay and is overwritten in place.
 
-    def __init__(self, fn, warmup: int = 3, slot: int = 0):
+    The graph bakes in the addresses of the scratch buffers of its (slot, capture stream), which stay PINNED while the
+    object lives: a call that would have to grow one of them raises instead of freeing memory the graph still writes
+    to.  Scratch is keyed by stream, so eager work on other streams never touches them.  slot=None (default) takes a
+    private slot nobody else uses."""
+
+    _next_private = 1 << 20
+
+    def __init__(self, fn, warmup: int = 3, slot: Optional[int] = None):
+        if slot is None:
+            slot = CapturedStep._next_private
+            CapturedStep._next_private += 1
+        self.slot = int(slot)
         cur = torch.cuda.current_stream()
         self.stream = torch.cuda.Stream()
         self.stream.wait_stream(cur)
-        with scratch_slot(slot):
+        with scratch_slot(self.slot):
             with torch.cuda.stream(self.stream):
                 for _ in range(max(warmup, 1)):      # grows every scratch buffer and sets kernel attributes
                     fn()
@@ -135,6 +147,14 @@ class CapturedStep:
                 self.out = fn()
         self.launches = profile.launches - before
         profile.launches = before
+        self._pin = (self.slot, self.stream.cuda_stream)
+        _pin_slot(self._pin, +1)
+
+    def __del__(self):
+        try:
+            _pin_slot(self._pin, -1)
+        except Exception:   # interpreter shutdown
+            pass
 
     def __call__(self, stream: Optional[torch.cuda.Stream] = None):
         """Replay on the current stream (or `stream`).  Graphs captured with different `slot`s may be in flight at the
@@ -153,41 +173,84 @@ def _need_cuda(t: torch.Tensor, name: str) -> None:
         raise HdyError(f"{name} must be a CUDA tensor: hd_yolo_b200 has no CPU fallback")
     if t.dtype != torch.float32:
         raise HdyError(f"{name} must be float32 (got {t.dtype}); the hot path is fp32 by contract")
+    _same_device(t, name)
+
+
+def _need_head_tensor(t: torch.Tensor, name: str) -> int:
+    """Raw head outputs (logits, prototypes) may be fp32 or fp16 (a half() model, val_nuclei.py:115-116); returns the
+    C-ABI dtype code.  fp16 values are widened on load: all arithmetic stays fp32."""
+    if not isinstance(t, torch.Tensor) or not t.is_cuda:
+        raise HdyError(f"{name} must be a CUDA tensor: hd_yolo_b200 has no CPU fallback")
+    if t.dtype not in (torch.float32, torch.float16):
+        raise HdyError(f"{name} must be float32 or float16 (got {t.dtype})")
+    _same_device(t, name)
+    return _lib.HDY_F16 if t.dtype == torch.float16 else _lib.HDY_F32
+
+
+def _same_device(t: torch.Tensor, name: str) -> None:
+    """Kernels are launched on the CURRENT device's current stream: a tensor of another GPU would be dereferenced
+    there.  Enter ``torch.cuda.device(t.device)`` first."""
+    if t.device.index is not None and t.device.index != torch.cuda.current_device():
+        raise HdyError(f"{name} lives on {t.device} but the current device is cuda:{torch.cuda.current_device()}: "
+                       "wrap the call in `with torch.cuda.device(tensor.device):`")
 
 
 def _aligned16(t: torch.Tensor) -> torch.Tensor:
     return t if t.data_ptr() % 16 == 0 else t.clone()
 
 
-_SLOT = 0
+_TLS = threading.local()          # the scratch slot is per thread (emulated ranks run on threads)
+_PINNED: Dict[Tuple[int, int], int] = {}   # (slot, capture stream) -> live CUDA graphs that baked its buffers in
+_PIN_LOCK = threading.Lock()
+
+
+def _slot() -> int:
+    return getattr(_TLS, "slot", 0)
+
+
+def _pin_slot(slot, delta: int) -> None:
+    with _PIN_LOCK:
+        v = _PINNED.get(slot, 0) + delta
+        if v > 0:
+            _PINNED[slot] = v
+        else:
+            _PINNED.pop(slot, None)
 
 
 class scratch_slot:
-    """Context manager: work issued inside uses scratch buffer set `k`.  Steps that run concurrently on different
-    streams (two CapturedStep graphs in flight) must use different slots; the default slot is 0."""
+    """Context manager: work issued inside (by this thread) uses scratch buffer set `k`.  Steps that run concurrently
+    (two CapturedStep graphs in flight, emulated ranks on threads) must use different slots; the default slot is 0."""
 
     def __init__(self, k: int):
         self.k = int(k)
 
     def __enter__(self):
-        global _SLOT
-        self.prev, _SLOT = _SLOT, self.k
+        self.prev = _slot()
+        _TLS.slot = self.k
 
     def __exit__(self, *exc):
-        global _SLOT
-        _SLOT = self.prev
+        _TLS.slot = self.prev
 
 
 class _Scratch:
-    """Grow-only per-device scratch buffers (candidate lists, NMS workspace), one set per scratch slot."""
+    """Grow-only scratch buffers (candidate lists, NMS workspace), one set per (device, scratch slot, stream): work on
+    two streams never shares a buffer by accident.  A (slot, stream) whose buffers a live CUDA graph has baked in
+    (CapturedStep captures on a stream of its own) refuses to grow -- the old buffer would be freed under the graph."""
 
     def __init__(self):
-        self._buf: Dict[Tuple[int, int, str], torch.Tensor] = {}
+        self._buf: Dict[Tuple[int, int, int, str], torch.Tensor] = {}
 
     def get(self, device: torch.device, name: str, nbytes: int) -> torch.Tensor:
-        key = (device.index if device.index is not None else torch.cuda.current_device(), _SLOT, name)
+        slot = _slot()
+        dev = device.index if device.index is not None else torch.cuda.current_device()
+        stream = torch.cuda.current_stream(dev).cuda_stream
+        key = (dev, slot, stream, name)
         b = self._buf.get(key)
         if b is None or b.numel() < nbytes:
+            if b is not None and (slot, stream) in _PINNED:
+                raise HdyError(f"scratch buffer '{name}' of slot {slot} would have to grow from {b.numel()} to {nbytes} "
+                               "bytes, but a live CUDA graph (CapturedStep) has its address baked in: run this call "
+                               "under another `scratch_slot`, or capture the graph for the larger shape")
             b = torch.empty(max(nbytes, 256), dtype=torch.uint8, device=device)
             self._buf[key] = b
         return b
@@ -235,8 +298,15 @@ class HeadSpec:
         arr = (Level * self.nl)()
         bs = None
         shapes = []
+        dtype = None
         for i, d in enumerate(dets):
-            _need_cuda(d, f"dets[{i}]")
+            code = _need_head_tensor(d, f"dets[{i}]")
+            if dtype is None:
+                dtype = code
+            elif dtype != code:
+                raise HdyError("levels disagree on dtype")
+            if code == _lib.HDY_F16 and layout != 0:
+                raise HdyError("fp16 logits are read in layout 0 ([bs,na,ny,nx,no]) only")
             if not d.is_contiguous():
                 raise HdyError(f"dets[{i}] must be contiguous")
             if layout == 0:
@@ -252,6 +322,7 @@ class HeadSpec:
             elif bs != b:
                 raise HdyError("levels disagree on batch size")
             arr[i].logits = d.data_ptr()
+            arr[i].dtype = code
             arr[i].ny, arr[i].nx = ny, nx
             arr[i].stride = float(self.strides[i])
             for a in range(self.na):
@@ -267,7 +338,7 @@ def compute_proposals(dets: List[torch.Tensor], spec: HeadSpec) -> List[torch.Te
     of every level, same shapes out ([bs,na,ny,nx,no])."""
     lib = _lib.load()
     levels, bs, _ = spec.levels(dets, 0)
-    outs = [torch.empty_like(d) for d in dets]
+    outs = [torch.empty_like(d, dtype=torch.float32) for d in dets]
     out_ptrs = (C.c_void_p * spec.nl)(*[o.data_ptr() for o in outs])
     _call("hdy_decode_levels", levels, spec.nl, bs, spec.na, spec.no, out_ptrs, _stream(), launches=spec.nl)
     return outs
@@ -507,6 +578,8 @@ class DetectBatch:
     cand_counts: torch.Tensor  # [bs+1] int32: candidates per tile after the filter, then status word
     max_det: int
     fragile: Optional[torch.Tensor] = None  # [bs, max_det] uint8: gray-zone flags (detect_postprocess(gray_eps=...))
+    gray_eps: float = 0.0      # the perturbation the flags cover, and the IoU threshold they were produced for
+    iou_thres: float = 0.0
 
     def to_list(self, multi_label: bool = False, conf_thres: float = 0.0) -> List[Dict[str, torch.Tensor]]:
         """The reference's List[Dict] (yolo_head.py:335-355); synchronises once."""
@@ -583,7 +656,7 @@ def detect_postprocess(dets: List[torch.Tensor], spec: HeadSpec, conf_thres: flo
         _call("hdy_select_scores", ptr(scores_full), ptr(keep_counts), bs, md, nc, flat, len(ops), cthr, ptr(score),
               ptr(label), _stream())
     return DetectBatch(keep_box, scores_full, score, label, lvl, extra, keep_idx, keep_counts, cand.counts, md,
-                       frag[0] if frag else None)
+                       frag[0] if frag else None, float(gray_eps) if frag else 0.0, float(iou_thres))
 
 
 def flatten_onehot_objects(x: Dict[str, torch.Tensor]) -> Dict[str, torch.Tensor]:

@@ -23,7 +23,8 @@ from ._lib import HdyError, ptr
 from .ops import DetectBatch, _Scratch, _aligned16, _call, _conf_thr_f32, _iou_thr_f32, _need_cuda, _stream
 
 __all__ = ["sliding_window_scanner", "tile_cores", "merge_outputs", "rescale_outputs", "scale_coords", "clip_coords",
-           "merge_nms", "ensemble_merge", "Ensemble", "SlideAccumulator", "sort_keys",
+           "merge_nms", "ensemble_merge", "Ensemble", "SlideAccumulator", "sort_keys", "kept_digest", "fold_digest",
+           "mask_digest",
            "STATE_KEPT", "STATE_SUPPRESSED", "STATE_DROPPED"]
 
 STATE_UNKNOWN, STATE_KEPT, STATE_SUPPRESSED, STATE_DROPPED = 0, 1, 2, 3
@@ -177,21 +178,26 @@ def sort_keys(keys: torch.Tensor, n_dev: Optional[torch.Tensor] = None, first_by
     return keys
 
 
-def _kept_in_order(state, boxes, scores, labels, max_det: int, n_dev=None):
-    """`keep = nms(...)[:max_det]; boxes[keep] ...` (yolo.py:195-196) from the verdicts."""
-    dev = boxes.device
-    n = boxes.shape[0]
-    keys = torch.empty((n,), dtype=torch.int64, device=dev)
-    count = torch.empty((1,), dtype=torch.int32, device=dev)
+def _order_keys(state, scores, n: int, count: torch.Tensor) -> torch.Tensor:
+    """Enqueues select + sort: one order key per KEPT row of state[:n], ascending (== score-descending, ties by the
+    lower row); their number lands in `count` (device int32 [1]).  Returns the key buffer [n] (valid up to *count)."""
+    dev = scores.device
+    keys = torch.empty((max(n, 1),), dtype=torch.int64, device=dev)
+    if n == 0:
+        count.zero_()
+        return keys
     # keys in row order + a stable sort of the score half only: same order as sorting the whole 64-bit key, in four
     # radix passes instead of eight
     blk = _ws.get(dev, "select_blocks", 4096 * 4)
-    _call("hdy_merge_select_ordered", ptr(state), ptr(scores), ptr(n_dev), n, ptr(keys), ptr(count), ptr(blk), _stream(),
+    _call("hdy_merge_select_ordered", ptr(state), ptr(scores), None, n, ptr(keys), ptr(count), ptr(blk), _stream(),
           launches=3)
-    k_all = int(count.item())
-    keys = keys[:k_all]
-    sort_keys(keys, first_byte=4, n_bytes=4)
-    k = min(k_all, int(max_det))
+    sort_keys(keys, n_dev=count, first_byte=4, n_bytes=4)
+    return keys
+
+
+def _gather_ordered(keys, count, k_all: int, max_det: int, boxes, scores, labels):
+    dev = boxes.device
+    k = min(int(k_all), int(max_det))
     idx = torch.empty((k,), dtype=torch.int64, device=dev)
     ob = torch.empty((k, 4), dtype=torch.float32, device=dev)
     os_ = torch.empty((k,), dtype=torch.float32, device=dev)
@@ -201,6 +207,62 @@ def _kept_in_order(state, boxes, scores, labels, max_det: int, n_dev=None):
         _call("hdy_merge_gather", ptr(keys), ptr(count), k, ptr(boxes), ptr(scores), ptr(labels), ptr(idx), ptr(ob),
               ptr(os_), ptr(ol), ptr(oc), _stream())
     return idx, ob, os_, ol
+
+
+def _kept_in_order(state, boxes, scores, labels, max_det: int, n_dev=None):
+    """`keep = nms(...)[:max_det]; boxes[keep] ...` (yolo.py:195-196) from the verdicts."""
+    n = boxes.shape[0]
+    count = torch.empty((1,), dtype=torch.int32, device=boxes.device)
+    keys = _order_keys(state, scores, n, count)
+    return _gather_ordered(keys, count, int(count.item()), max_det, boxes, scores, labels)
+
+
+def kept_digest(state: torch.Tensor, base: int = 0) -> torch.Tensor:
+    """Order-independent digest of the KEPT global row indices: int64 [3] = (count, low 32 bits of the sum of a 64-bit
+    mix of every index, high 32 bits of it), each a plain sum -- add the tensors of all ranks (all_reduce) and fold with
+    ``fold_digest``.  Two runs kept the same rows iff (up to hash collisions) their digests agree, whatever the number
+    of ranks.  Diagnostics: not part of the timed path."""
+    idx = torch.nonzero(state == STATE_KEPT).flatten().to(torch.int64) + int(base)
+    h = idx * -7046029254386353131            # 0x9E3779B97F4A7C15 (wraps: int64 arithmetic is mod 2^64)
+    h = h ^ (h >> 31)
+    h = h * -4658895280553007687              # 0xBF58476D1CE4E5B9
+    h = h ^ (h >> 29)
+    lo = (h & 0xffffffff).sum()
+    hi = ((h >> 32) & 0xffffffff).sum()
+    return torch.stack([torch.tensor(idx.numel(), dtype=torch.int64, device=state.device), lo, hi])
+
+
+def fold_digest(t: torch.Tensor) -> Dict[str, object]:
+    c, lo, hi = [int(v) for v in t.tolist()]
+    return {"kept": c, "hash": f"{(lo + (hi << 32)) & 0xffffffffffffffff:016x}"}
+
+
+def mask_digest(masks, state: torch.Tensor, base: int = 0, chunk_rows: int = 1 << 19) -> torch.Tensor:
+    """The same for the mask bits of the KEPT rows: every mask word is mixed with (global row, word position inside
+    the mask), so the digest does not depend on where a rank's words sit in its buffer.  int64 [3] like kept_digest,
+    the count being the number of set mask pixels.  Diagnostics (chunked torch ops), not part of the timed path."""
+    dev = state.device
+    all_rows = torch.nonzero(state == STATE_KEPT).flatten()
+    acc = torch.zeros((3,), dtype=torch.int64, device=dev)
+    for c0 in range(0, int(all_rows.numel()), chunk_rows):
+        rows = all_rows[c0:c0 + chunk_rows]
+        g = masks.geom[rows].to(torch.int64)
+        words = ((g[:, 2] + 31) >> 5) * g[:, 3]
+        total = int(words.sum())
+        if total == 0:
+            continue
+        owner = torch.repeat_interleave(torch.arange(rows.numel(), device=dev), words)
+        start = torch.cumsum(words, 0) - words
+        j = torch.arange(total, device=dev) - start[owner]
+        w = masks.bits[masks.offsets[rows][owner] + j].to(torch.int64) & 0xffffffff
+        h = ((rows[owner] + int(base)) * 1000003 + j) * -7046029254386353131
+        h = (h ^ (h >> 31)) + w * -4658895280553007687
+        h = h ^ (h >> 29)
+        pop = w - ((w >> 1) & 0x55555555)
+        pop = (pop & 0x33333333) + ((pop >> 2) & 0x33333333)
+        pop = ((((pop + (pop >> 4)) & 0x0f0f0f0f) * 0x01010101) >> 24) & 0xff
+        acc += torch.stack([pop.sum(), (h & 0xffffffff).sum(), ((h >> 32) & 0xffffffff).sum()])
+    return acc
 
 
 # ------------------------------------------------------------------------------------------------ T2 / T3 drop-ins
@@ -307,6 +369,11 @@ class SlideAccumulator:
         self.rois: List[torch.Tensor] = []
         self.n_tiles = 0
         self.gray_ok = True        # every batch so far came with gray-zone flags (DetectBatch.fragile) and scale 1
+        self.gray_eps = float("inf")   # smallest gray_eps / largest tile IoU threshold the flags were produced with
+        self.gray_iou = 0.0
+        self._cores = self._cores_rois = self._cores_key = None
+        self._top = 0.0
+        self._rois_key: Optional[List[bytes]] = []   # host bytes of the appended windows (None: not all were given)
 
     def reset(self):
         self.cursor.zero_()
@@ -315,10 +382,17 @@ class SlideAccumulator:
         self.rois.clear()
         self.n_tiles = 0
         self.gray_ok = True
+        self.gray_eps, self.gray_iou = float("inf"), 0.0
+        self._rois_key = []          # the core rectangles stay cached: they are keyed on the windows' contents
 
-    def append(self, batch: DetectBatch, rois: torch.Tensor, scale: float = 1.0) -> None:
-        """rois [bs, 4] fp32 on the device: the windows (x0, y0, x1, y1) of the batch's tiles."""
+    def append(self, batch: DetectBatch, rois: torch.Tensor, scale: float = 1.0,
+               rois_host: Optional[torch.Tensor] = None) -> None:
+        """rois [bs, 4] fp32 on the device: the windows (x0, y0, x1, y1) of the batch's tiles.  rois_host: the same
+        windows on the host, if the caller has them (keys the core-rectangle cache without a device read)."""
         bs = batch.counts.shape[0]
+        if self._rois_key is not None:
+            self._rois_key = self._rois_key + [rois_host.contiguous().numpy().tobytes()] if rois_host is not None \
+                else None
         if rois.shape != (bs, 4) or not rois.is_cuda or rois.dtype != torch.float32:
             raise HdyError("rois must be a CUDA fp32 tensor [bs, 4]")
         rois = _aligned16(rois.contiguous())
@@ -326,6 +400,9 @@ class SlideAccumulator:
         fragile = batch.fragile if scale == 1.0 else None
         if fragile is None:
             self.gray_ok = False
+        else:
+            self.gray_eps = min(self.gray_eps, float(batch.gray_eps))
+            self.gray_iou = max(self.gray_iou, float(batch.iou_thres))
         _call("hdy_merge_append", ptr(batch.boxes), ptr(batch.scores), ptr(batch.labels) if self.labels is not None else None,
               ptr(fragile), ptr(batch.counts), ptr(rois), bs, batch.max_det, self.n_tiles, float(scale), self.capacity,
               ptr(self.boxes), ptr(self.scores), ptr(self.labels), ptr(self.tile), ptr(self.cursor), ptr(offs),
@@ -367,6 +444,26 @@ class SlideAccumulator:
               self.FAR_CAPACITY, _stream())
         return margin, far_boxes, far_tile, far_count
 
+    def check_shortcut(self, iou_thres: float) -> None:
+        """The preconditions under which skipping the interior is exact; raises when one fails."""
+        import numpy as np
+        if not self.gray_ok:
+            raise HdyError("interior_shortcut needs gray-zone flags on every appended batch "
+                           "(detect_postprocess(gray_eps=...), scale 1)")
+        if iou_thres < 0.05:
+            raise HdyError("interior_shortcut: iou_thres < 0.05 is not covered by the gray-zone bound")
+        if self.gray_iou and iou_thres < self.gray_iou:
+            raise HdyError(f"interior_shortcut: merge iou_thres {iou_thres} is below the per-tile NMS threshold "
+                           f"{self.gray_iou} the gray-zone flags were produced for (same-tile survivors may overlap more)")
+        if self.rois:
+            top = self._top
+            need = float(np.spacing(np.float32(max(top, 1.0)))) / 2.0
+            if self.gray_eps < need:
+                raise HdyError(f"interior_shortcut: the gray-zone flags cover a rounding of {self.gray_eps:g} px per "
+                               f"coordinate, slide coordinates up to {top:g} round by up to {need:g}")
+        if self.gray_eps > 0.004:
+            raise HdyError("interior_shortcut: gray_eps above 0.004 px exceeds the binning margins of the per-tile NMS")
+
     def verdicts(self, conf_thres: float, iou_thres: float, interior_shortcut: bool = False) -> torch.Tensor:
         """uint8 state per appended row (asynchronous except for the round-budget check).
 
@@ -377,13 +474,18 @@ class SlideAccumulator:
         n = self.capacity
         kw = {}
         if interior_shortcut:
-            if not self.gray_ok:
-                raise HdyError("interior_shortcut needs gray-zone flags on every appended batch "
-                               "(detect_postprocess(gray_eps=...), scale 1)")
             rois = torch.cat(self.rois)
-            if getattr(self, "_cores_key", None) != (len(self.rois), int(rois.shape[0])):
+            # the core rectangles are cached on the CONTENTS of the windows (host bytes when the caller supplied them,
+            # else a device comparison)
+            key = b"".join(self._rois_key) if self._rois_key is not None else None
+            same = self._cores is not None and (
+                (key is not None and key == self._cores_key) or
+                (key is None and self._cores_rois.shape == rois.shape and torch.equal(self._cores_rois, rois)))
+            if not same:
                 self._cores = tile_cores(rois).to(self.device)
-                self._cores_key = (len(self.rois), int(rois.shape[0]))
+                self._cores_rois, self._cores_key = rois, key
+                self._top = float(rois.abs().max()) if rois.numel() else 0.0
+            self.check_shortcut(iou_thres)
             margin, far_boxes, far_tile, far_count = self.overhang()
             kw = dict(tile_id=self.tile, cores=self._cores, margin=margin,
                       dirty=dirty_tiles(far_boxes, far_tile, far_count, rois))

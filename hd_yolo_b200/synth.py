@@ -47,34 +47,46 @@ def nuclei_logits(bs: int, tile: int, nc: int, n_cand: int, seed: int, anchors=A
 
 
 # ------------------------------------------------------------------------------------------------ whole slide
+def _tile_seed(seed: int, tile_index: int) -> int:
+    return (int(seed) * 1000003 + int(tile_index) * 7919 + 12345) & 0x7fffffffffff
+
+
 def slide_tile_logits(rois: torch.Tensor, tile: int, nc: int, seed: int, pitch: float = 18.7, extra: int = 0,
                       conf: float = 0.25, size_range=(12.0, 30.0), strides=STRIDES_3, anchors=ANCHORS_3,
-                      device="cuda", background_mu: float = -6.0):
+                      device="cuda", background_mu: float = -6.0, first_tile: int = 0, dtype=torch.float32):
     """Raw head logits for a batch of slide tiles (rois [bs,4] = x0,y0,x1,y1 from sliding_window_scanner) cut from
     ONE global nuclei field (cfg 4): nuclei sit on a jittered grid of `pitch` px over the whole slide
     (~3 000 per 1024^2 tile); a nucleus is a pure function of its grid index, so the tiles that share an overlap band
     report the same nucleus with the same box (up to fp32 rounding of the tile-local decode) and a tile-dependent
     score jitter -- consistent duplicates for the merge NMS.  Every nucleus is written into the stride-8 level at the
     cell holding its centre, anchor chosen by size; all other rows are background (objectness logit ~ N(mu,1), far
-    below the threshold).  Edge tiles (clipped windows) simply contain fewer nuclei.  Returns the level tensors
-    [bs,na,ny,nx,5+nc+extra]."""
+    below the threshold).  Edge tiles (clipped windows) simply contain fewer nuclei.
+
+    DETERMINISTIC AND RANK-INDEPENDENT: tile b of the batch is global tile `first_tile + b`, and everything random about
+    it (background noise, score jitter, the `extra` coefficient channels) comes from a generator seeded with
+    (seed, global tile index) alone -- however the tiles are batched or sharded over ranks, a tile's logits are the
+    same bytes.  Two nuclei landing in the same (anchor, cell) are resolved by a fixed rule (the first in grid order
+    wins), never by the order in which a scatter happens to commit duplicates.
+    Returns the level tensors [bs,na,ny,nx,5+nc+extra] (`dtype`: float32, or float16 = what a half() model emits)."""
     bs = rois.shape[0]
     dev = torch.device(device)
-    g = torch.Generator(device=dev).manual_seed(seed)
+    g = torch.Generator(device=dev)
     na = len(anchors[0]) // 2
     no = 5 + nc + extra
     shapes = level_shapes(tile, strides)
-    dets = []
-    for (ny, nx) in shapes:
-        d = torch.randn((bs, na, ny, nx, no), generator=g, device=dev)
-        d[..., 4] += background_mu
-        dets.append(d)
+    dets = [torch.empty((bs, na, ny, nx, no), dtype=torch.float32, device=dev) for (ny, nx) in shapes]
     rois = rois.to(dev, torch.float32)
+    rois_h = rois.cpu().tolist()
     s0 = float(strides[0])
     a0 = torch.tensor(anchors[0], dtype=torch.float32, device=dev).view(na, 2)
     ncell = int(math.ceil(tile / pitch)) + 1
+    ny0, nx0 = shapes[0]
     for b in range(bs):
-        x0, y0, x1, y1 = [float(v) for v in rois[b]]
+        g.manual_seed(_tile_seed(seed, first_tile + b))
+        for d in dets:
+            d[b] = torch.randn(tuple(d.shape[1:]), generator=g, device=dev)
+            d[b, ..., 4] += background_mu
+        x0, y0, x1, y1 = rois_h[b]
         i0, j0 = int(math.floor(x0 / pitch)), int(math.floor(y0 / pitch))
         ii = torch.arange(i0, i0 + ncell, device=dev, dtype=torch.int64)
         jj = torch.arange(j0, j0 + ncell, device=dev, dtype=torch.int64)
@@ -92,16 +104,40 @@ def slide_tile_logits(rois: torch.Tensor, tile: int, nc: int, seed: int, pitch: 
         score = 0.3 + 0.65 * u(3)
         inside = (cx >= x0) & (cx < x1) & (cy >= y0) & (cy < y1)
         cx, cy, side, score = cx[inside] - x0, cy[inside] - y0, side[inside], score[inside]
+        jitter = torch.rand((ncell * ncell,), generator=g, device=dev)[:score.numel()]   # fixed draw count per tile
         if cx.numel() == 0:
             continue
-        gx = torch.clamp((cx / s0).floor().long(), 0, shapes[0][1] - 1)
-        gy = torch.clamp((cy / s0).floor().long(), 0, shapes[0][0] - 1)
+        gx = torch.clamp((cx / s0).floor().long(), 0, nx0 - 1)
+        gy = torch.clamp((cy / s0).floor().long(), 0, ny0 - 1)
         a = torch.where(side < 14.0, 0, torch.where(side < 23.0, 1, 2)).long()
         sx = ((cx / s0 - gx.float()) + 0.5) / 2.0
         sy = ((cy / s0 - gy.float()) + 0.5) / 2.0
         sw = (side / a0[a, 0]).sqrt() / 2.0
         sh = (side / a0[a, 1]).sqrt() / 2.0
-        sc = (score + 0.04 * (torch.rand(score.shape, generator=g, device=dev) - 0.5)).clamp(conf + 0.02, 0.99)
+        sc = (score + 0.04 * (jitter - 0.5)).clamp(conf + 0.02, 0.99)
         sig = torch.stack([sx, sy, sw, sh, sc], 1).clamp(0.02, 0.98)
-        dets[0][b, a, gy, gx, :5] = torch.log(sig / (1 - sig))
+        # one nucleus per (anchor, cell): the first in grid order wins (stable sort + first of every run)
+        lin = (a * ny0 + gy) * nx0 + gx
+        order = torch.argsort(lin, stable=True)
+        ls = lin[order]
+        first = torch.ones_like(ls, dtype=torch.bool)
+        first[1:] = ls[1:] != ls[:-1]
+        win = order[first]
+        dets[0][b, a[win], gy[win], gx[win], :5] = torch.log(sig[win] / (1 - sig[win]))
+    if dtype != torch.float32:
+        dets = [d.to(dtype) for d in dets]
     return [d.contiguous() for d in dets]
+
+
+def slide_tile_protos(n: int, tile: int, seed: int, first_tile: int = 0, nm: int = 32, device="cuda",
+                      dtype=torch.float32) -> torch.Tensor:
+    """Prototype maps [n, nm, tile/4, tile/4] of the global tiles [first_tile, first_tile + n): N(0,1), seeded per
+    global tile index like slide_tile_logits (the same bytes however the tiles are batched or sharded)."""
+    dev = torch.device(device)
+    g = torch.Generator(device=dev)
+    mh = tile // 4
+    out = torch.empty((n, nm, mh, mh), dtype=dtype, device=dev)
+    for b in range(n):
+        g.manual_seed(_tile_seed(seed + 77, first_tile + b))
+        out[b] = torch.randn((nm, mh, mh), generator=g, device=dev).to(dtype)
+    return out

@@ -51,14 +51,21 @@ typedef void* hdy_stream_t;    /* a cudaStream_t */
 #define HDY_API
 #endif
 
+/* Element type of the head's raw outputs (logits, prototypes).  The reference's GPU default is a half() model
+ * (val_nuclei.py:109, 115-116): HDY_F16 inputs are widened to fp32 on load -- every fp16 value is an fp32 value, so
+ * the result is exactly that of the fp32 path fed the same (fp16-rounded) numbers; all arithmetic stays fp32. */
+#define HDY_F32 0
+#define HDY_F16 1
+
 /* One pyramid level of raw head output (Detect.forward, yolo_head.py:141-145). */
 typedef struct {
-  const float* logits;  /* layout 0: [bs, na, ny, nx, no]   (the permuted tensor the reference decodes)
-                           layout 1: [bs, na*no, ny, nx]     (the 1x1 conv's native output, D0 skipped)   */
+  const void* logits;   /* layout 0: [bs, na, ny, nx, no]   (the permuted tensor the reference decodes)
+                           layout 1: [bs, na*no, ny, nx]     (the 1x1 conv's native output, D0 skipped; fp32 only) */
   int32_t ny, nx;
   float stride;                      /* buffer.stride            yolo_head.py:61   */
   float anchor_w[HDY_MAX_ANCHORS];   /* anchor_grid = anchor*stride, pixels  yolo_head.py:427 */
   float anchor_h[HDY_MAX_ANCHORS];
+  int32_t dtype;                     /* HDY_F32 / HDY_F16, the same on every level */
 } hdy_level_t;
 
 /* Library / build information. */
@@ -215,21 +222,33 @@ HDY_API int hdy_unpack_masks(const int32_t* geom, const int64_t* offsets, const 
 /* North-star process_mask (ultralytics/yolov5 v7 utils/segment/general.py::process_mask + crop_mask; the
  * reference itself has no such function): mask = sigmoid(coef . protos), zero outside the box scaled by
  * (mw/iw, mh/ih), optional bilinear upsample (align_corners=False) to (ih, iw), > 0.5.  Batched over tiles:
- *   protos [bs, nm, mh, mw], coef [bs, max_det, nm], boxes [bs, max_det, 4] (image pixels), counts [bs]
+ *   protos [bs, nm, mh, mw] (proto_dtype: HDY_F32 or HDY_F16), coef [bs, max_det, nm] f32, boxes [bs, max_det, 4]
+ *   (image pixels), counts [bs]
  *   dense out [bs, max_det, oh, ow] f32 in {0,1} with (oh,ow) = upsample ? (ih,iw) : (mh,mw).
  * workspace (hdy_process_mask_workspace_bytes(bs, max_det) bytes, may be NULL) enables the two-phase path
  * (csrc/mask_regions.cu: TMA-staged prototypes -> sigmoid patches -> upsample + pack) when nm == 32, mw % 4 == 0 and
  * protos is 16-byte aligned; otherwise, and for boxes wider than 16 proto pixels, the per-detection kernel runs. */
 HDY_API size_t hdy_process_mask_workspace_bytes(int bs, int max_det);
-HDY_API int hdy_process_mask(const float* protos, const float* coef, const float* boxes, const int32_t* counts,
-                             int bs, int max_det, int nm, int mh, int mw, int ih, int iw, int upsample, float* out,
-                             void* workspace, size_t workspace_bytes, hdy_stream_t stream);
+HDY_API int hdy_process_mask(const void* protos, int proto_dtype, const float* coef, const float* boxes,
+                             const int32_t* counts, int bs, int max_det, int nm, int mh, int mw, int ih, int iw,
+                             int upsample, float* out, void* workspace, size_t workspace_bytes, hdy_stream_t stream);
 /* Cropped bit-packed variant; geom [bs*max_det, 4], offsets [bs*max_det + 1] as above (slots >= counts are empty).
- * hdy_process_mask_packed takes the geom array hdy_process_mask_geometry wrote (NULL: windows are recomputed). */
+ * hdy_process_mask_packed takes the geom array hdy_process_mask_geometry wrote (NULL: windows are recomputed).
+ * Slide form (row_state / tile_offsets non-NULL): slot d of tile t is row tile_offsets[t] + d of the slide-level
+ * arrays (hdy_merge_append); only rows whose verdict row_state[row] is HDY_STATE_KEPT get a window -- Ensemble.merge
+ * returns masks[keep] (yolo.py:197-202), so the masks of suppressed duplicates are never computed. */
 HDY_API int hdy_process_mask_geometry(const float* boxes, const int32_t* counts, int bs, int max_det, int mh, int mw,
-                                      int ih, int iw, int upsample, int32_t* geom, int64_t* offsets,
+                                      int ih, int iw, int upsample, const uint8_t* row_state,
+                                      const int64_t* tile_offsets, int32_t* geom, int64_t* offsets,
                                       hdy_stream_t stream);
-HDY_API int hdy_process_mask_packed(const float* protos, const float* coef, const float* boxes,
+/* Slide form, second step: the batch's offsets are moved behind the words of the earlier batches (cursor2: two device
+ * int64, read at [parity & 1], the advanced value written to [(parity + 1) & 1]) and every live slot's window and
+ * offset are copied to its slide row: geom_rows [n, 4] (window origin shifted by the tile origin rois[t] to slide
+ * pixels), off_rows [n].  Run hdy_process_mask_packed afterwards with `bits` = the slide-wide word buffer. */
+HDY_API int hdy_process_mask_rows(int32_t* geom, int64_t* offsets, const int32_t* counts, const int64_t* tile_offsets,
+                                  const float* rois, int bs, int max_det, int64_t* cursor2, int parity,
+                                  int32_t* geom_rows, int64_t* off_rows, hdy_stream_t stream);
+HDY_API int hdy_process_mask_packed(const void* protos, int proto_dtype, const float* coef, const float* boxes,
                                     const int32_t* counts, const int32_t* geom, const int64_t* offsets, int bs, int max_det, int nm,
                                     int mh, int mw, int ih, int iw, int upsample, uint32_t* bits,
                                     int64_t capacity_words, int32_t* status, void* workspace, size_t workspace_bytes,
@@ -325,6 +344,65 @@ HDY_API int hdy_merge_import_states(void* workspace, int64_t n_max, int64_t firs
                                     hdy_stream_t stream);
 HDY_API int hdy_merge_finish(void* workspace, const int64_t* n_dev, int64_t n_max, uint8_t* state, int32_t* status,
                              hdy_stream_t stream);
+
+/* Multi-GPU form of T3 (the reference runs Ensemble.merge, yolo.py:165-204, on one device; here every rank owns a band
+ * of tile rows and only detections near a band boundary are exchanged).  Everything variable-sized travels in
+ * FIXED-SIZE blocks whose fill counts stay on the device, so the host issues
+ *     summary -> [all-gather] -> select -> [all-gather] -> scatter, dirty_tiles, build
+ *     -> { rounds -> export -> [all-gather] -> import } x 2 -> rounds -> finish
+ * without reading anything back in between (hd_yolo_b200/dist.py).  Blocks are arrays of 32-bit words:
+ *   summary block  [HDY_SEAM_HDR_WORDS + far_cap * HDY_SEAM_FAR_WORDS]:
+ *       [0..3] bounding rectangle of the rank's detections (f32 x1,y1,x2,y2; inverted when there are none)
+ *       [4] largest overhang of a non-far box over its tile (f32)   [5] far-list length (> far_cap: overflowed)
+ *       [6..7] number of own rows (i64)   then per far-reaching box: f32 box x4, i32 GLOBAL tile, 3 pad words
+ *   payload block  [HDY_SEAM_HDR_WORDS + seam_cap * HDY_SEAM_ROW_WORDS]:
+ *       [0] number of seam rows (> seam_cap: overflowed)   then per seam row (ascending own row): box bits x4, score
+ *       bits, index in the slide-wide concatenation (low 32 bits)
+ *   meta [HDY_SEAM_META_WORDS] i32, written by hdy_seam_scatter: [0..1] own rows + replicas (i64), [2] largest margin of
+ *       any rank (f32), [3] global index of own row 0, [4] flags (1: a payload overflowed, 2: replicas did not fit,
+ *       4: a far list overflowed -- all tiles dirty, 8: 2^32 rows or more), [5] far boxes listed, [6..7] spare (the
+ *       host mirror parks hdy_merge_finish's status and the survivor count there), [8..15] "a seam row is still
+ *       undecided" per exchange (index mod 8), [16..16+world] first replica slot of every rank, [88] own seam rows. */
+#define HDY_SEAM_HDR_WORDS 16
+#define HDY_SEAM_FAR_WORDS 8
+#define HDY_SEAM_ROW_WORDS 6
+#define HDY_SEAM_META_WORDS 96
+#define HDY_SEAM_MAX_WORLD 64
+#define HDY_SEAM_FLAG_PAYLOAD_OVERFLOW 1
+#define HDY_SEAM_FLAG_REPLICA_OVERFLOW 2
+#define HDY_SEAM_FLAG_FAR_OVERFLOW 4
+#define HDY_SEAM_FLAG_TOO_MANY_ROWS 8
+/* This rank's summary block.  margin / far_* are what hdy_merge_overhang wrote (far_tile local: tile_base is added). */
+HDY_API int hdy_seam_summary(const float* boxes, int64_t n_local, const float* margin, const float* far_boxes,
+                             const int32_t* far_tile, const int32_t* far_count, int far_list_capacity, int tile_base,
+                             int far_cap, int32_t* block, hdy_stream_t stream);
+/* Own rows whose box touches (closed intervals) the rectangle of another rank that has rows: sel [seam_cap] i32 (own
+ * row of payload row k) and this rank's payload block.  summaries = the all-gathered summary blocks [world][..];
+ * block_scratch: 4097 device int32. */
+HDY_API int hdy_seam_select(const float* boxes, const float* scores, int64_t n_local, const int32_t* summaries,
+                            int world, int rank, int far_cap, int seam_cap, int32_t* sel, int32_t* block,
+                            int32_t* block_scratch, hdy_stream_t stream);
+/* The other ranks' seam rows become replicas behind the own rows: boxes / scores rows [n_local, n_local + R) (R <=
+ * rep_cap), rep_gidx [rep_cap]; fills meta.  payloads = the all-gathered payload blocks. */
+HDY_API int hdy_seam_scatter(const int32_t* payloads, const int32_t* summaries, int world, int rank, int far_cap,
+                             int seam_cap, int64_t n_local, int64_t rep_cap, float* boxes, float* scores,
+                             uint32_t* rep_gidx, int32_t* meta, hdy_stream_t stream);
+/* hdy_merge_dirty_tiles over every rank's far list (global tile ids, tile_rois of the whole slide). */
+HDY_API int hdy_seam_dirty_tiles(const int32_t* summaries, int world, int far_cap, const float* tile_rois, int n_tiles,
+                                 uint8_t* dirty, hdy_stream_t stream);
+/* hdy_merge_build over own rows + replicas: row count, margin and global index base are read from meta; tile_id
+ * [n_local] holds LOCAL tile ids (tile_id + tile_base indexes tile_cores / tile_dirty, which cover the whole slide). */
+HDY_API int hdy_seam_build(const float* boxes, const float* scores, const uint32_t* rep_gidx, const int32_t* meta,
+                           const int32_t* tile_id, int tile_base, const float* tile_cores, const uint8_t* tile_dirty,
+                           int64_t n_max, int64_t n_local, float conf_thres, float iou_thres, uint8_t* state,
+                           void* workspace, size_t workspace_bytes, hdy_stream_t stream);
+/* Verdicts of the own seam rows (out [seam_cap] u8, payload order) / of the replicas from the all-gathered verdicts
+ * (states [world][seam_cap]); import also raises meta[8 + exchange % 8] while any rank's seam row is undecided. */
+HDY_API int hdy_seam_export(void* workspace, int64_t n_max, const uint8_t* state, const int32_t* sel,
+                            const int32_t* my_block, int seam_cap, uint8_t* out, hdy_stream_t stream);
+HDY_API int hdy_seam_import(void* workspace, int64_t n_max, int64_t n_local, const uint8_t* states,
+                            const int32_t* payloads, int32_t* meta, int world, int rank, int seam_cap, int exchange,
+                            hdy_stream_t stream);
 
 /* Survivors in the reference's order (`nms(...)[:max_det]`, yolo.py:195): select writes one 64-bit order key per
  * KEPT row (unordered) and their number, sort_keys sorts them ascending (== score-descending, ties by lower row),

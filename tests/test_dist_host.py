@@ -1,7 +1,8 @@
-"""CPU tests of the sharded whole-slide merge's host logic (hd_yolo_b200/dist.py): tile sharding, seam selection,
-padded all-gathers over gloo (world_size 2 and 3), verdict exchange and termination.  The kernels are replaced by the
-dense stand-in in tests/cpu_merge_backend.py; the checker is torchvision.ops.nms on the slide-wide concatenation,
-which is what the reference's Ensemble.merge calls (metayolo/models/yolo.py:189-195)."""
+"""CPU tests of the sharded whole-slide merge's host logic (hd_yolo_b200/dist.py): tile sharding, the fixed-size
+seam blocks and their four all-gathers over gloo (world_size 2 and 3) and over thread-emulated ranks, verdict
+exchange, termination, and block growth after an overflow.  The kernels are replaced by the dense stand-in in
+tests/cpu_merge_backend.py; the checker is torchvision.ops.nms on the slide-wide concatenation, which is what the
+reference's Ensemble.merge calls (metayolo/models/yolo.py:189-195)."""
 import os
 import sys
 
@@ -11,7 +12,7 @@ import torch.multiprocessing as mp
 import torchvision
 
 sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
-from cpu_merge_backend import TorchMergeBackend  # noqa: E402
+from cpu_merge_backend import TorchSeamBackend  # noqa: E402
 from slide_synth import banded_detections  # noqa: E402
 
 from hd_yolo_b200 import dist as hdist  # noqa: E402
@@ -58,7 +59,7 @@ def test_shard_tile_rows_full_slide_config():
 def test_emulated_ranks_match_dense_nms(world):
     parts = banded_detections(world, seed=world, n_nuclei=300 * world)
     ref = reference_states(parts)
-    got = hdist.merge_emulated(parts, CONF, IOU, backend=TorchMergeBackend)
+    got = hdist.merge_emulated(parts, CONF, IOU, backend=TorchSeamBackend)
     assert torch.equal(torch.cat(got), ref)
     # the exchange really carried something: some detection was suppressed by another rank's box
     alone = torch.cat([reference_states([p]) for p in parts])
@@ -68,10 +69,27 @@ def test_emulated_ranks_match_dense_nms(world):
 def test_emulated_empty_and_single_rank():
     parts = banded_detections(3, seed=9, n_nuclei=200)
     parts[1] = (torch.zeros((0, 4)), torch.zeros((0,)))
-    got = hdist.merge_emulated(parts, CONF, IOU, backend=TorchMergeBackend)
+    got = hdist.merge_emulated(parts, CONF, IOU, backend=TorchSeamBackend)
     assert torch.equal(torch.cat(got), reference_states(parts))
-    one = hdist.merge_emulated(parts[:1], CONF, IOU, backend=TorchMergeBackend)
+    one = hdist.merge_emulated(parts[:1], CONF, IOU, backend=TorchSeamBackend)
     assert torch.equal(one[0], reference_states(parts[:1]))
+
+
+def test_payload_overflow_grows_the_blocks():
+    """seam_cap far too small: every rank sees the overflow flag in the same read, grows and repeats."""
+    parts = banded_detections(3, seed=4, n_nuclei=900)
+    ref = reference_states(parts)
+    got = hdist.merge_emulated(parts, CONF, IOU, backend=TorchSeamBackend, seam_cap=8)
+    assert torch.equal(torch.cat(got), ref)
+
+
+def test_emulated_failure_does_not_deadlock():
+    def boom(rank, comm):
+        if rank == 1:
+            raise ValueError("rank 1 fails")
+        comm.all_gather(torch.zeros(1))
+    with pytest.raises(ValueError):
+        hdist.run_emulated(3, boom)
 
 
 def _gloo_worker(rank, world, port, out):
@@ -82,7 +100,7 @@ def _gloo_worker(rank, world, port, out):
     try:
         parts = banded_detections(world, seed=11, n_nuclei=250 * world)
         b, s = parts[rank]
-        res = hdist.merge_sharded(b, s, CONF, IOU, backend=TorchMergeBackend)
+        res = hdist.merge_sharded(b, s, CONF, IOU, backend=TorchSeamBackend, seam_cap=64 if world == 3 else 4096)
         out[rank] = (res['state'].clone(), res['base'], res['exchanges'], res['seam_rows'])
     finally:
         dist.destroy_process_group()

@@ -13,7 +13,7 @@ short = (sys.argv[2] != "0") if len(sys.argv) > 2 else True
 spec = hdy.HeadSpec(synth.ANCHORS_3, synth.STRIDES_3, nc=4)
 post = SlidePostprocessor(spec, (S, S), (1024, 1024), 64, 0.25, 0.45, 4096, cap=4096, batch=128, rank=rank, world=world, device=dev, interior_shortcut=short)
 t0, t1 = post.tile_range
-store = [synth.slide_tile_logits(post.rois[a:min(a + 128, t1)], 1024, 4, seed=a, device=dev) for a in range(t0, t1, 128)]
+store = [synth.slide_tile_logits(post.rois[a:min(a + 128, t1)], 1024, 4, seed=1, first_tile=a, device=dev) for a in range(t0, t1, 128)]
 prov = lambda a, b: store[(a - t0) // 128]
 for rep in range(4):
     dist.barrier(); torch.cuda.synchronize(); t = time.perf_counter()

@@ -12,7 +12,7 @@ dev = torch.device("cuda:0")
 spec = hdy.HeadSpec(synth.ANCHORS_3, synth.STRIDES_3, nc=4)
 post = SlidePostprocessor(spec, (S, S), (1024, 1024), 64, 0.25, 0.45, 4096, cap=4096, batch=148, device=dev)
 t0, t1 = post.tile_range
-store = [synth.slide_tile_logits(post.rois[a:min(a + 148, t1)], 1024, 4, seed=a, device=dev) for a in range(t0, t1, 148)]
+store = [synth.slide_tile_logits(post.rois[a:min(a + 148, t1)], 1024, 4, seed=1, first_tile=a, device=dev) for a in range(t0, t1, 148)]
 post.detect(lambda a, b: store[(a - t0) // 148])
 acc = post.acc
 n = acc.count()
