@@ -1,26 +1,30 @@
 #!/usr/bin/env python
 """Benchmark of the post-processing hot path (BASELINE.json metric: post-proc tiles/s & boxes/s).
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--workload tiles640|tiles1024|slide] [--masks proto|none]
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--workload slide|tiles640|tiles1024|hnet] [--masks proto|none]
+                    [--dtype f32|f16]
     python bench.py --impl reference ...      # the reference's CPU path (oracle port) on host cores
 
-tiles640 / tiles1024 (BASELINE.json configs[1] / configs[2]): one "step" = one pass of the hot path over one batch of
-synthetic head outputs: fused decode+filter+compact -> per-tile NMS -> score/label select -> proto masks
-(32-prototype contraction, sigmoid, crop, bilinear upsample, threshold, bit-packed).  Weak scaling over GPUs (every
-rank processes its own batches; the path has no cross-tile dependency).
+slide (default; BASELINE.json configs[3], the configuration the north-star target is quoted on): one "step" = a whole
+synthetic 100k x 100k px slide (11 025 tiles of 1024 px, 64 px overlap, ~3 000 nuclei per tile) cut from one global
+nuclei field: per-tile decode+filter+compact -> NMS -> score/label select of this rank's tile rows, append in slide
+coordinates, exact slide-level merge NMS (seam exchange over NCCL when N > 1), then process_mask (32-prototype
+contraction, sigmoid, crop, bilinear upsample, > 0.5, bit-packed) for the rows the merge KEPT.  Strong scaling.
+Short runs of tiles640 / tiles1024 (configs[1] / configs[2]) are attached as sub-records unless --no-sub.
 
-slide (configs[3]): one "step" = a whole synthetic 100k x 100k px slide (11 025 tiles of 1024 px, 64 px overlap) cut
-from one global nuclei field: per-tile post-processing of this rank's tile rows, append in slide coordinates, exact
-slide-level merge NMS with the seam exchange over NCCL.  Strong scaling.  Unless --no-slide, a short slide run is also
-attached to the tiles line as "slide".
+tiles640 / tiles1024: one "step" = one pass of the per-tile path over one batch of synthetic head outputs (masks
+included).  Weak scaling (every rank processes its own batches; the path has no cross-tile dependency).
 
 Prints ONE JSON line on rank 0:
   value     : whole-job tiles/s with inputs resident in HBM (CUDA events, max over ranks)
   e2e       : the same through the public API with HOST (pinned) inputs: H2D of the step's inputs and D2H of its
               results inside the timed region
-  roofline  : the dominant HBM-bound kernel: algorithmic bytes per launch / its CUDA-event time (measured live)
+  roofline  : the dominant HBM-bound call: algorithmic bytes per launch / its CUDA-event time (measured live)
   stages    : every C-ABI call of the step with its time, algorithmic bytes and achieved GB/s
+  pipeline  : the whole step's algorithmic bytes / its time, against the HBM peak (the north star's "% of roofline")
   cpu_baseline : oracle port (the reference's torch/torchvision CPU path) on a bounded sample
+  torch_cuda   : diagnostic, not product: the same port on CUDA tensors (ATen / torchvision CUDA kernels) -- the
+                 library GPU path SURVEY 2b names as the bar
 """
 import argparse
 import json
@@ -62,7 +66,10 @@ WORKLOADS = {
     "tiles1024": dict(tile=1024, bs=128, n_cand=3000, conf=0.25, iou=0.45, max_det=3000, nc=4, cap=4096),
     # BASELINE.json configs[3]: whole slide, 1024-px tiles, 64-px overlap, ~3k candidates/tile
     # (148 tiles per batch: the per-tile NMS runs one CTA per tile, one per SM)
-    "slide": dict(tile=1024, bs=148, n_cand=3000, conf=0.25, iou=0.45, max_det=4096, nc=4, cap=4096, overlap=64),
+    # (max_det 3328 = 26 x 128: the field holds at most 55 x 55 = 3 025 nuclei per tile, so the cap never binds)
+    "slide": dict(tile=1024, bs=148, n_cand=3000, conf=0.25, iou=0.45, max_det=3328, nc=4, cap=4096, overlap=64),
+    # BASELINE.json configs[4]: hnet multi-level heads (RCNN-style 10x structures + 40x nuclei), cross-level merge
+    "hnet": dict(tile=1024, bs=16, n_cand=3000, conf=0.25, iou=0.45, max_det=4096, nc=4, cap=4096, overlap=64),
 }
 NM = 32            # prototypes
 L2_BYTES = 126e6
@@ -74,12 +81,20 @@ def parse():
     ap.add_argument("--steps", type=int, default=None)
     ap.add_argument("--warmup", type=int, default=None)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--workload", default="tiles640", choices=list(WORKLOADS))
-    ap.add_argument("--masks", default="proto", choices=["proto", "paste", "none"])
+    ap.add_argument("--workload", default="slide", choices=list(WORKLOADS))
+    ap.add_argument("--masks", default=None, choices=["proto", "paste", "none"],
+                    help="mask stage (default: proto; --impl reference: paste, the reference's own mask path)")
+    ap.add_argument("--dtype", default="f32", choices=["f32", "f16"],
+                    help="element type of the head outputs (logits, prototypes) as they arrive; f16 = a half() model, "
+                         "the reference's GPU default (val_nuclei.py:109,115-116).  Arithmetic is fp32 either way.")
     ap.add_argument("--slide-size", type=int, default=100000)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
-    ap.add_argument("--no-slide", action="store_true")
+    ap.add_argument("--no-sub", "--no-slide", dest="no_sub", action="store_true",
+                    help="no sub-records (slide: tiles640/tiles1024 runs; tiles: the short slide run)")
+    ap.add_argument("--no-torch-cuda", action="store_true")
+    ap.add_argument("--proto-pool", type=int, default=592,
+                    help="slide: distinct prototype maps (tile t reads map t mod pool; 592 x 8.4 MB = 5 GB, 40x L2)")
     ap.add_argument("--layout", type=int, default=0, choices=[0, 1],
                     help="tiles workloads: 0 = the reference's permuted [bs,na,ny,nx,no] head tensors, 1 = the 1x1 "
                          "conv's native [bs,na*no,ny,nx] output (the yolo_head.py:141-145 permute copy skipped)")
@@ -87,10 +102,12 @@ def parse():
                     help="slide workload: tile batches alternate over this many streams (SlidePostprocessor(streams=))")
     ap.add_argument("--inflight", type=int, default=3, help="steps in flight (CUDA graphs on separate streams)")
     a = ap.parse_args()
+    if a.masks is None:
+        a.masks = "paste" if a.impl == "reference" else "proto"
     if a.steps is None:
-        a.steps = 5 if a.workload == "slide" else 200
+        a.steps = 5 if a.workload in ("slide", "hnet") else 200
     if a.warmup is None:
-        a.warmup = 3 if a.workload == "slide" else 10
+        a.warmup = 3 if a.workload in ("slide", "hnet") else 10
     return a
 
 
@@ -145,67 +162,128 @@ class ClockSampler(threading.Thread):
 
 
 # ------------------------------------------------------------------------------------------------ CPU reference arm
-def cpu_reference_pass(dets_cpu, protos_cpu, wl, spec_args, masks):
-    """The reference's CPU path for one batch: compute_proposals -> pad/cat -> nms_per_image -> select
-    (-> process_mask with upsample per tile)."""
-    from oracle import port
-    anchors, strides = spec_args
-    nc = wl["nc"]
-    preds = port.compute_proposals(dets_cpu, anchors, strides)
-    params = {'conf_thres': wl["conf"], 'iou_thres': wl["iou"], 'max_det': wl["max_det"]}
-    if masks == "none":
-        return port.compute_outputs(preds, nc, params)
+MASK_CHUNK = 300    # detections per paste / process_mask call on the CPU: the dense [k,1,H,W] fp32 canvases the
+                    # reference allocates are 4 MB each at 1024 px (12.6 GB for one tile's 3 000 detections)
+
+
+def _cpu_tile_pass(dets, second, wl, masks, tile_px, device=None):
+    """The reference's per-tile path for a batch of tiles (oracle port, torch/torchvision ops on `device`):
+    compute_proposals -> level pad/cat -> nms_per_image -> hierarchical scores + select
+      -> masks == "paste": mask select (yolo_head.py:346-353) + paste_masks_in_image (val_nuclei.py:169-176) > 0.5
+         masks == "proto": upstream process_mask (contraction, sigmoid, crop, upsample, > 0.5)
+    Returns [(boxes, scores, labels, n_mask_pixels)] per tile."""
     import torch
+    from oracle import port
+    from hd_yolo_b200 import synth
+    nc = wl["nc"]
+    preds = port.compute_proposals(dets, synth.ANCHORS_3, synth.STRIDES_3)
     cat = port.concat_levels(preds)
     res = port.nms_per_image(cat, nc, wl["conf"], wl["iou"], wl["max_det"])
     out = []
     for i, r in enumerate(res):
         s, l = port.select_scores(r['scores'][:, :1 + nc].clone(), wl["conf"], port.default_descendants(nc))
-        if masks == "proto":
-            coef = r['extra'][:, :NM]      # extra = raw coefficient channels + level id; the coefficients come first
-            m = port.process_mask(protos_cpu[i], coef, r['boxes'], (wl["tile"], wl["tile"]), upsample=True)
-        else:                              # reference variant A: mask select + paste_masks_in_image, > 0.5
-            k = len(r['boxes'])
-            sel = port.mask_select(protos_cpu[i][:k], l, torch.tensor([-1, 0, 0, 1, 1]))
-            m = port.paste_masks_in_image(sel, r['boxes'], (wl["tile"], wl["tile"]), padding=1) > 0.5
-        out.append((r['boxes'], s, l, m))
+        k, px = len(r['boxes']), 0
+        for c0 in range(0, k if masks != "none" else 0, MASK_CHUNK):
+            c1 = min(c0 + MASK_CHUNK, k)
+            if masks == "proto":
+                coef = r['extra'][c0:c1, :NM]   # extra = raw coefficient channels + level id; coefficients first
+                m = port.process_mask(second[i].float(), coef.float(), r['boxes'][c0:c1].clone(), (tile_px, tile_px),
+                                      upsample=True)
+            else:
+                sel = port.mask_select(second[i][c0:c1].float(), l[c0:c1],
+                                       torch.tensor([-1, 0, 0, 1, 1], device=l.device))
+                m = port.paste_masks_in_image(sel, r['boxes'][c0:c1], (tile_px, tile_px), padding=1) > 0.5
+            px += int(m.sum())
+        out.append((r['boxes'], s, l, px))
     return out
 
 
-def cpu_sample_inputs(wl, masks, sample, seed=1):
+def cpu_sample(workload, wl, masks, n_tiles, dtype="f32", device="cpu", slide_size=100000):
+    """A bounded sample of the workload as CPU (or `device`) tensors + a function running the reference path on it.
+    slide: the first n_tiles tiles of the slide's first tile row (adjacent: their overlap bands hold duplicates), the
+    per-tile path, then merge_outputs + Ensemble.merge over them."""
     import torch
+    from oracle import port
     from hd_yolo_b200 import synth
+    from hd_yolo_b200.slide import sliding_window_scanner
+    tile, nc = wl["tile"], wl["nc"]
     extra = NM if masks == "proto" else 0
-    dets = synth.nuclei_logits(sample, wl["tile"], wl["nc"], wl["n_cand"], seed=seed, conf=wl["conf"], extra=extra)
-    protos = None
+    td = torch.float16 if (dtype == "f16" and device != "cpu") else torch.float32   # CPU NMS/sigmoid: fp32 only
+    rois = None
+    if workload == "slide":
+        rois = sliding_window_scanner((slide_size, slide_size), (tile, tile), wl["overlap"])[:n_tiles]
+        dets = synth.slide_tile_logits(rois, tile, nc, seed=1, first_tile=0, conf=wl["conf"], extra=extra,
+                                       device=device)
+    else:
+        dets = [d.to(device) for d in synth.nuclei_logits(n_tiles, tile, nc, wl["n_cand"], seed=1, conf=wl["conf"],
+                                                          extra=extra)]
+    if dtype == "f16":       # the same fp16-rounded numbers the GPU arm reads
+        dets = [d.half().to(td) for d in dets]
+    g = torch.Generator().manual_seed(8)
+    second = None
     if masks == "proto":
-        g = torch.Generator().manual_seed(seed + 7)
-        protos = torch.randn((sample, NM, wl["tile"] // 4, wl["tile"] // 4), generator=g)
+        second = synth.slide_tile_protos(n_tiles, tile, seed=1, first_tile=0, nm=NM, device=device)
+        if dtype == "f16":
+            second = second.half().to(td)
     elif masks == "paste":
-        g = torch.Generator().manual_seed(seed + 8)
-        protos = torch.randn((sample, min(wl["max_det"], wl["cap"]), 2, 28, 28), generator=g)
-    return dets, protos
+        second = torch.randn((n_tiles, min(wl["max_det"], wl["cap"]), 2, 28, 28), generator=g).to(device)
+
+    def run():
+        res = _cpu_tile_pass([d.float() for d in dets], second, wl, masks, tile)
+        if workload == "slide":
+            tiles = [{'boxes': b, 'scores': sc, 'labels': l, 'roi': rois[i].to(b.device)}
+                     for i, (b, sc, l, _) in enumerate(res)]
+            port.ensemble_merge([{'det': port.merge_outputs(tiles)}],
+                                {'conf_thres': wl["conf"], 'iou_thres': wl["iou"], 'max_det': 10 ** 9})
+        return res
+
+    what = "compute_proposals + level cat + nms_per_image + score select" + \
+        {"proto": " + process_mask(upsample) > 0.5", "paste": " + mask_select + paste_masks_in_image > 0.5",
+         "none": ""}[masks] + (" + merge_outputs + Ensemble.merge over the sample's tiles" if workload == "slide" else "")
+    return run, what
 
 
-def time_cpu(wl, masks, budget_s, max_reps, threads=None):
-    """Bounded CPU timing of the oracle port on `threads` host threads (default: all).  Returns (tiles/s, threads,
-    sample text)."""
+def time_cpu(workload, wl, masks, budget_s, max_passes, threads=None, dtype="f32", n_tiles=None, slide_size=100000):
+    """Bounded CPU timing of the oracle port on `threads` host threads (default: all).  Every pass is a whole sample;
+    nothing is extrapolated.  Returns a dict for the JSON line."""
     import torch
-    from hd_yolo_b200 import synth
     torch.set_num_threads(threads or os.cpu_count() or 1)
-    sample = 8 if masks == "none" else 2
-    dets, protos = cpu_sample_inputs(wl, masks, sample)
-    spec_args = (synth.ANCHORS_3, synth.STRIDES_3)
-    cpu_reference_pass(dets, protos, wl, spec_args, masks)          # warm-up
-    reps, t0 = 0, time.perf_counter()
-    while reps < 2 or (time.perf_counter() - t0 < budget_s and reps < max_reps):
-        cpu_reference_pass(dets, protos, wl, spec_args, masks)
-        reps += 1
+    if n_tiles is None:
+        n_tiles = 2 if (masks != "none" and wl["tile"] >= 1024) else (4 if masks != "none" else 8)
+    run, what = cpu_sample(workload, wl, masks, n_tiles, dtype, "cpu", slide_size)
+    global MASK_CHUNK
+    keep, MASK_CHUNK = MASK_CHUNK, 64
+    try:                                    # warm the allocator / thread pools on a cheaper configuration of the same
+        wrun, _ = cpu_sample(workload, dict(wl, max_det=64), masks, 1, dtype, "cpu", slide_size)
+        wrun()
+    finally:
+        MASK_CHUNK = keep
+    passes, t0 = 0, time.perf_counter()
+    while passes < 1 or (passes < max_passes and (time.perf_counter() - t0) * (passes + 1) / passes < budget_s):
+        run()
+        passes += 1
     dt = time.perf_counter() - t0
-    what = "compute_proposals + nms_per_image + score select" + \
-        {"proto": " + process_mask(upsample)", "paste": " + mask_select + paste_masks_in_image", "none": ""}[masks]
-    return sample * reps / dt, torch.get_num_threads(), (
-        f"{sample} tiles x {reps} passes of oracle/port.py ({what}; torch {torch.__version__} CPU + torchvision nms)")
+    return {"value": n_tiles * passes / dt, "unit": "tiles/s", "cores": torch.get_num_threads(), "kind": "port",
+            "ms_per_pass": 1e3 * dt / passes, "tiles_per_pass": n_tiles, "passes": passes,
+            "sample": f"{n_tiles} tiles x {passes} timed passes of oracle/port.py ({what}; torch {torch.__version__} CPU "
+                      f"+ torchvision; mask canvases in chunks of {MASK_CHUNK} detections; one process)"}
+
+
+def time_torch_cuda(workload, wl, masks, dtype, device, n_tiles=4, passes=3, slide_size=100000):
+    """DIAGNOSTIC, not the product and not the reference arm: the same oracle port on CUDA tensors (ATen's and
+    torchvision's CUDA kernels) on this GPU -- the library GPU path SURVEY 2b names as the bar to beat."""
+    import torch
+    run, what = cpu_sample(workload, wl, masks, n_tiles, dtype, device, slide_size)
+    run()
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    for _ in range(passes):
+        run()
+    torch.cuda.synchronize()
+    dt = time.perf_counter() - t0
+    return {"value": n_tiles * passes / dt, "unit": "tiles/s", "ms_per_pass": 1e3 * dt / passes,
+            "tiles_per_pass": n_tiles, "passes": passes,
+            "what": f"oracle/port.py on CUDA tensors ({what}); wall clock around synchronised passes, one GPU"}
 
 
 def cpu_merge_scaling(boxes, scores, tile, n_cols, conf, iou, grids=(2, 3, 4, 6, 8), budget_s=25.0):
@@ -245,25 +323,46 @@ def cpu_merge_scaling(boxes, scores, tile, n_cols, conf, iou, grids=(2, 3, 4, 6,
     return out
 
 
+def common_config(args, wl, masks):
+    """The keys both arms print under "config" (same keys, same workload parameters)."""
+    cfg = {"workload": args.workload, "tile": wl["tile"], "candidates_per_tile": wl["n_cand"], "conf": wl["conf"],
+           "iou": wl["iou"], "max_det": wl["max_det"], "masks": masks, "dtype_in": args.dtype}
+    if args.workload == "slide":
+        cfg.update({"slide_px": args.slide_size, "overlap": wl["overlap"]})
+    return cfg
+
+
 def run_reference(args, wl):
     """--impl reference: the reference's own CPU implementation (oracle port: same torch/torchvision calls) on all
-    host threads; each step is a bounded sample of the workload."""
+    host threads of ONE process; each step is a bounded sample of the workload, timed whole -- ms_per_step is the
+    measured time of one sample pass, `steps` the passes actually run."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    masks = args.masks if args.workload != "slide" else "none"
-    v, cores, sample = time_cpu(wl, masks, budget_s=20.0, max_reps=max(2, min(args.steps, 50)))
+    masks = args.masks
+    wk = args.workload if args.workload != "hnet" else "tiles1024"
+    r = time_cpu(wk, wl, masks, budget_s=60.0, max_passes=max(1, min(args.steps, 50)), dtype=args.dtype,
+                 slide_size=args.slide_size)
+    other = None
+    if masks in ("paste", "proto"):      # the other mask variant beside it (one pass)
+        om = "proto" if masks == "paste" else "paste"
+        o = time_cpu(wk, wl, om, budget_s=1.0, max_passes=1, dtype=args.dtype, n_tiles=1, slide_size=args.slide_size)
+        other = {"masks": om, "value": o["value"], "unit": "tiles/s", "ms_per_pass": o["ms_per_pass"],
+                 "tiles_per_pass": o["tiles_per_pass"]}
+    v = r["value"]
+    cfg = common_config(args, wl, masks)
+    cfg["note"] = ("masks=paste is the reference's own mask path (yolo_head.py:346-353 + torchvision "
+                   "paste_masks_in_image, val_nuclei.py:169-176); masks=proto is upstream yolov5's process_mask, "
+                   "which the reference does not contain.  One CPU process whatever --gpus says.")
     line = {
         "impl": "reference", "metric": "postproc_tiles_per_s", "value": v, "unit": "tiles/s", "n_gpus": args.gpus,
-        "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * wl["bs"] / v, "higher_is_better": True,
+        "steps": r["passes"], "steps_requested": args.steps, "warmup": 1, "ms_per_step": r["ms_per_pass"],
+        "tiles_per_step": r["tiles_per_pass"], "higher_is_better": True,
         "scaling": "strong" if args.workload == "slide" else "weak", "vs_baseline": None, "dtype": "f32",
-        "data": "synthetic",
-        "config": {"workload": args.workload, "tile": wl["tile"], "candidates_per_tile": wl["n_cand"],
-                   "conf": wl["conf"], "iou": wl["iou"], "max_det": wl["max_det"], "masks": masks,
-                   "note": "ms_per_step is the CPU time for one full batch of the workload, extrapolated from the sample"},
-        "cpu_baseline": {"value": v, "unit": "tiles/s", "cores": cores, "kind": "port", "sample": sample},
+        "data": "synthetic", "config": cfg,
+        "cpu_baseline": {"value": v, "unit": "tiles/s", "cores": r["cores"], "kind": "port", "sample": r["sample"]},
         "e2e": {"value": v, "unit": "tiles/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
-        "boxes_per_s": v * wl["n_cand"],
+        "boxes_per_s": v * wl["n_cand"], "other_mask_variant": other,
     }
     _emit(line)
 
@@ -370,18 +469,23 @@ def run_tiles(args, wl, c):
     shapes = synth.level_shapes(tile, synth.STRIDES_3)
     N = spec.rows_per_tile(shapes)
     mh = mw = tile // 4
-    in_bytes = bs * N * spec.no * 4 + (bs * NM * mh * mw * 4 if masks == "proto" else 0) + \
+    td = torch.float16 if args.dtype == "f16" else torch.float32
+    esz = 2 if args.dtype == "f16" else 4
+    if args.dtype == "f16" and args.layout == 1:
+        raise SystemExit("--dtype f16 reads layout 0 only")
+    in_bytes = bs * N * spec.no * esz + (bs * NM * mh * mw * esz if masks == "proto" else 0) + \
         (bs * min(wl["max_det"], wl["cap"]) * 2 * 28 * 28 * 4 if masks == "paste" else 0)
     R = max(2, args.inflight, int(2.5 * L2_BYTES / in_bytes) + 1)   # rotate input batches so that reads miss L2
-    batches = [synth.nuclei_logits(bs, tile, nc, wl["n_cand"], seed=1000 * c.rank + r, conf=wl["conf"], extra=extra,
-                                   generator_device="cuda") for r in range(R)]
+    batches = [[d.to(td) for d in synth.nuclei_logits(bs, tile, nc, wl["n_cand"], seed=1000 * c.rank + r,
+                                                      conf=wl["conf"], extra=extra, generator_device="cuda")]
+               for r in range(R)]
     if args.layout == 1:   # the same logits as the head's 1x1 conv leaves them: [bs, na*no, ny, nx]
         batches = [[d.permute(0, 1, 4, 2, 3).reshape(d.shape[0], -1, d.shape[2], d.shape[3]).contiguous() for d in b]
                    for b in batches]
     protos = None
     if masks == "proto":
         g = torch.Generator(device="cuda").manual_seed(77 + c.rank)
-        protos = [torch.randn((bs, NM, mh, mw), generator=g, device=c.dev) for _ in range(R)]
+        protos = [torch.randn((bs, NM, mh, mw), generator=g, device=c.dev).to(td) for _ in range(R)]
     md_slots = min(wl["max_det"], wl["cap"])
     mlogits = None
     if masks == "paste":
@@ -467,14 +571,14 @@ def run_tiles(args, wl, c):
     ne = spec.no - 5 - nc
     alg = {   # algorithmic bytes per launch
         # layout 1: only the objectness plane is streamed, survivors gather their four box logits
-        "hdy_filter_compact_logits": bs * (4 * N * spec.no + 24 * cand) if args.layout == 0
+        "hdy_filter_compact_logits": bs * (esz * N * spec.no + 24 * cand) if args.layout == 0
         else bs * (4 * N + (16 + 24) * cand),
         "hdy_nms_tiles": bs * (24 * cand + 28 * kept),
-        "hdy_gather_logits": bs * kept * (4 * (1 + nc + ne) * 2 + 4),
-        "hdy_gather_select_logits": bs * kept * (4 * (1 + nc + ne) * 2 + 4 + 4 + 8),
+        "hdy_gather_logits": bs * kept * ((4 + esz) * (1 + nc + ne) + 4),
+        "hdy_gather_select_logits": bs * kept * ((4 + esz) * (1 + nc + ne) + 4 + 4 + 8),
         "hdy_select_scores": bs * kept * (4 * (1 + nc) * 2 + 4 + 8),
         "hdy_process_mask_geometry": bs * min(wl["max_det"], wl["cap"]) * (16 + 16 + 8),
-        "hdy_process_mask_packed": bs * (4 * NM * mh * mw + kept * (4 * NM + 16 + 8)) + 4 * words,
+        "hdy_process_mask_packed": bs * (esz * NM * mh * mw + kept * (4 * NM + 16 + 8)) + 4 * words,
         "hdy_zero_i32": 4 * (bs + 1),
         "hdy_paste_geometry": bs * md_slots * (16 + 16 + 8 + 4),
         "hdy_paste_masks_packed": bs * kept * (28 * 28 * 4 + 16 + 8) + 4 * words,
@@ -493,9 +597,12 @@ def run_tiles(args, wl, c):
     step_bytes = sum(v["alg_bytes"] for v in stages.values() if v["alg_bytes"])
     traffic = None
     try:   # DRAM bytes per launch of the dominant call, from the committed ncu --set full capture of this workload
-        traffic = json.load(open(os.path.join(ROOT, "profiles", "r01_traffic.json")))[args.workload][dom]["bytes"]
-        if masks != "proto" and dom == "hdy_filter_compact_logits":
-            traffic = None if args.workload != "tiles1024" else traffic
+        tr = "r02_traffic.json" if os.path.exists(os.path.join(ROOT, "profiles", "r02_traffic.json")) else \
+            "r01_traffic.json"
+        traffic = json.load(open(os.path.join(ROOT, "profiles", tr)))[args.workload][dom]["bytes"]
+        if args.dtype != "f32" or (masks != "proto" and dom == "hdy_filter_compact_logits" and
+                                   args.workload != "tiles1024"):
+            traffic = None
     except Exception:
         pass
 
@@ -580,7 +687,7 @@ def run_tiles(args, wl, c):
         "metric": "postproc_tiles_per_s", "value": tiles_per_s, "unit": "tiles/s", "n_gpus": c.world, "steps": K,
         "warmup": W, "ms_per_step": ms / K, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": args.workload, "tile": tile, "tiles_per_step_per_gpu": bs, "levels": 3,
+        "config": {**common_config(args, wl, masks), "tiles_per_step_per_gpu": bs, "levels": 3,
                    "layout": "permuted [bs,na,ny,nx,no] (what the reference's Detect.forward hands over)"
                    if args.layout == 0 else "conv-native [bs,na*no,ny,nx] (yolo_head.py:141-145 permute skipped)",
                    "rows_per_tile": N, "channels": spec.no, "prototypes": NM if masks == "proto" else 0,
@@ -609,46 +716,95 @@ def run_tiles(args, wl, c):
 
 
 # ------------------------------------------------------------------------------------------------ slide workload
-def run_slide(args, wl, c, steps, warmup, want_e2e, want_cpu_merge=False):
+def _timed_phase(c, fn, reps):
+    """max-over-ranks CUDA-event time of `reps` calls of fn (ms per call)."""
+    return c.timed(lambda i: fn(), reps) / reps
+
+
+def run_slide(args, wl, c, steps, warmup, want_e2e, want_cpu_merge=False, masks="proto", want_stages=True):
     import torch
     import hd_yolo_b200 as hdy
     from hd_yolo_b200 import ops, synth
     from hd_yolo_b200.pipeline import SlidePostprocessor
+    from hd_yolo_b200.slide import fold_digest, kept_digest, mask_digest
 
     nc, tile, bs = wl["nc"], wl["tile"], wl["bs"]
-    spec = hdy.HeadSpec(synth.ANCHORS_3, synth.STRIDES_3, nc=nc)
+    with_masks = masks == "proto"
+    extra = NM if with_masks else 0
+    td = torch.float16 if args.dtype == "f16" else torch.float32
+    esz = 2 if args.dtype == "f16" else 4
+    spec = hdy.HeadSpec(synth.ANCHORS_3, synth.STRIDES_3, nc=nc, no=5 + nc + extra)
     S = args.slide_size
     post = SlidePostprocessor(spec, (S, S), (tile, tile), wl["overlap"], wl["conf"], wl["iou"], wl["max_det"],
                               cap=wl["cap"], batch=bs, rank=c.rank, world=c.world, device=c.dev,
                               capacity=None, streams=args.slide_streams)
     t0, t1 = post.tile_range
     n_tiles = int(post.rois.shape[0])
-    # this rank's head outputs for the whole slide, resident in HBM (N=1: 11 025 tiles x 2.3 MB = 25.6 GB)
+    mh = tile // 4
+    # this rank's head outputs for the whole slide, resident in HBM (N=1, fp32, 41 channels: 11 025 tiles x 10.6 MB =
+    # 117 GB); every tile's bytes are a function of its global index alone, however the slide is sharded
     store = []
     for a in range(t0, t1, bs):
         b = min(a + bs, t1)
-        store.append(synth.slide_tile_logits(post.rois[a:b], tile, nc, seed=1, first_tile=a, conf=wl["conf"], device=c.dev))
-    in_bytes = sum(sum(t.numel() * 4 for t in dets) for dets in store)
+        store.append(synth.slide_tile_logits(post.rois[a:b], tile, nc, seed=1, first_tile=a, conf=wl["conf"],
+                                             extra=extra, device=c.dev, dtype=td))
+    in_bytes = sum(sum(t.numel() * t.element_size() for t in dets) for dets in store)
+    pool, P = None, 0
+    if with_masks:
+        # prototype maps: tile t reads map (t mod P) of a pool P x 8.4 MB (fp32) >> L2, rows [P, P + bs) repeat rows
+        # [0, bs) so that a batch is always one contiguous slice.  (The unique maps of 11 025 tiles would take 92 GB
+        # next to 117 GB of logits.)  The mapping is by GLOBAL tile index: the same for every number of ranks.
+        P = max(bs, min(args.proto_pool, n_tiles))
+        pool = torch.empty((P + bs, NM, mh, mh), dtype=td, device=c.dev)
+        for p0 in range(0, P, 64):
+            p1 = min(p0 + 64, P)
+            pool[p0:p1] = synth.slide_tile_protos(p1 - p0, tile, seed=1, first_tile=p0, nm=NM, device=c.dev, dtype=td)
+        pool[P:] = pool[:bs]
+        in_bytes += (t1 - t0) * NM * mh * mh * esz
 
     def provider(a, b):
         return store[(a - t0) // bs]
 
+    def protos(a, b):
+        return pool[a % P:a % P + (b - a)]
+
     res = {}
 
     def step(i):
-        res["r"] = post.run(provider, ordered=True)
+        res.pop("r", None)              # the previous slide's results are released before the next ones are allocated
+        res["r"] = post.run(provider, ordered=True, proto_provider=protos if with_masks else None,
+                            mask_words_per_row=40.0)
 
-    for i in range(max(warmup, 4)):     # the slide-sized temporaries settle in the caching allocator after ~3 passes
+    for i in range(max(warmup, 3)):     # the slide-sized temporaries settle in the caching allocator after ~3 passes
         step(i)
+    if with_masks:
+        res["r"]["masks"].check()
     ops.profile.reset()
     ms = c.timed(step, steps)
     launches = ops.profile.launches
-    # merge alone (detections already appended by the last step)
-    ms_merge = c.timed(lambda i: post.merge(ordered=True), max(2, min(steps, 5)))
-    ms_merge /= max(2, min(steps, 5))
+    # phases (each timed alone, max over ranks)
+    reps = max(2, min(steps, 3))
+    ms_detect = _timed_phase(c, lambda: post.detect(provider, keep_batches=with_masks), reps)
+    ms_merge = _timed_phase(c, lambda: res.__setitem__("m", post.merge(ordered=True)), reps)
+    ms_masks = _timed_phase(c, lambda: post.masks(protos, res["m"]["state"], words_per_row=40.0), reps) \
+        if with_masks else 0.0
+    res.pop("m", None)
     r = res["r"]
     n_local = int(r["n"])
-    kept_local = int((r["state"] == 1).sum())
+    dg = kept_digest(r["state"], r["base"])
+    cand_local = 0
+    stages = None
+    words_local = int(r["masks"].offsets[n_local]) if with_masks else 0
+    md = mask_digest(r["masks"], r["state"], r["base"]) if with_masks else torch.zeros_like(dg)
+    if want_stages:
+        # per-call CUDA-event times of one more (untimed) pass: every C-ABI call bracketed by events on its stream
+        ops.profile.enabled = True
+        ops.profile.reset()
+        step(0)
+        prof = ops.profile.summary()
+        ops.profile.enabled = False
+        stages = {k: {"calls": n, "ms_total": t} for k, (n, t) in prof.items()}
+        cand_local = int(sum(int(b[2].cand_counts[:-1].sum()) for b in post._batches)) if post._batches else 0
     cpu_merge = None
     if want_cpu_merge and c.rank == 0 and c.world == 1:
         try:   # a reported baseline must never take the GPU record down with it
@@ -657,60 +813,130 @@ def run_slide(args, wl, c, steps, warmup, want_e2e, want_cpu_merge=False):
             tl = torch.where(tl >= 0, tl, ~tl).to(torch.int64)              # fragile rows carry ~tile
             sub = ((tl // n_cols) < 8) & ((tl % n_cols) < 8)      # the largest sub-slide cpu_merge_scaling may time
             cpu_merge = cpu_merge_scaling(post.acc.boxes[:n_local][sub].cpu(), post.acc.scores[:n_local][sub].cpu(),
-                                          tl[sub].cpu(), n_cols, wl["conf"], wl["iou"])
+                                          tl[sub].cpu(), n_cols, wl["conf"], wl["iou"], budget_s=12.0)
         except Exception as e:   # noqa: BLE001
             cpu_merge = {"error": f"{type(e).__name__}: {e}"}
-    tot = torch.tensor([n_local, kept_local, in_bytes], dtype=torch.float64, device=c.dev)
+    tot = torch.cat([torch.tensor([n_local, in_bytes, cand_local, words_local], dtype=torch.int64, device=c.dev), dg, md])
     if c.world > 1:
         import torch.distributed as dist
         dist.all_reduce(tot)
+    n_all, in_all, cand_all, words_all = [int(v) for v in tot[:4].tolist()]
+    digest, mdigest = fold_digest(tot[4:7]), fold_digest(tot[7:10])
+    kept_all = digest["kept"]
+    N_rows = spec.rows_per_tile(synth.level_shapes(tile, synth.STRIDES_3))
+    alg = {   # algorithmic bytes of ONE slide, all ranks together: totals over all launches of a call
+        "hdy_filter_compact_logits": n_tiles * esz * N_rows * spec.no + 24 * cand_all,
+        "hdy_nms_tiles": 24 * cand_all + 29 * n_all,
+        "hdy_gather_select_logits": n_all * ((esz + 4) * (1 + nc + extra) + 4 + 4 + 8),
+        "hdy_merge_append": n_all * (29 + 32),
+        "hdy_merge_nms": n_all * (28 + 1),
+        "hdy_seam_build": n_all * (28 + 1),
+        "hdy_merge_select_ordered": n_all + 8 * kept_all,
+        "hdy_sort_keys_bytes": kept_all * 8 * 2 * 4,
+        "hdy_merge_gather": kept_all * (8 + 28 + 36),
+        "hdy_process_mask_geometry": n_all * (16 + 1) + n_tiles * wl["cap"] * 24,
+        "hdy_process_mask_rows": n_all * (24 + 24),
+        "hdy_process_mask_packed": n_tiles * esz * NM * mh * mh + kept_all * (4 * NM + 16 + 24) + 4 * words_all,
+    }
+    step_bytes = sum(v for k, v in alg.items() if stages is None or k in stages)
+    peak, peak_src = load_peak()
     out = {"tiles": n_tiles, "tiles_per_s": n_tiles * steps / (ms * 1e-3), "ms_per_slide": ms / steps,
-           "merge_ms": ms_merge, "detections": int(tot[0]), "kept": int(tot[1]),
-           "input_bytes": int(tot[2]), "slide_px": S, "tile": tile, "overlap": wl["overlap"],
+           "detect_ms": ms_detect, "merge_ms": ms_merge, "masks_ms": ms_masks, "detections": n_all, "kept": kept_all,
+           "candidates": cand_all, "mask_words": words_all, "digest": digest, "mask_digest": mdigest,
+           "input_bytes": in_all, "slide_px": S, "tile": tile, "overlap": wl["overlap"], "dtype_in": args.dtype,
+           "masks": masks, "proto_pool": P,
            "seam_rows": r.get("seam_rows"), "exchanges": r.get("exchanges"), "gpu_launches": launches,
-           "boxes_per_s": int(tot[0]) * steps / (ms * 1e-3)}
+           "boxes_per_s": cand_all * steps / (ms * 1e-3) if cand_all else n_all * steps / (ms * 1e-3),
+           "pipeline": {"algorithmic_bytes_per_step": step_bytes,
+                        "achieved_gbs": step_bytes / (ms / steps * 1e-3) / 1e9 / c.world,
+                        "frac_of_peak": step_bytes / (ms / steps * 1e-3) / 1e9 / c.world / peak,
+                        "note": "per GPU: the slide's algorithmic bytes / ranks / time, against one GPU's HBM peak"}}
+    if stages is not None:
+        for k, v in stages.items():     # rank 0's calls process 1/world of the slide's bytes
+            a_b = alg.get(k)
+            v["alg_bytes_total"] = (a_b / c.world) if a_b else None
+            v["gbs"] = (a_b / c.world / (v["ms_total"] * 1e-3) / 1e9) if a_b and v["ms_total"] > 0 else None
+            v["ms"] = v["ms_total"] / max(v["calls"], 1)
+        out["stages"] = stages
+        hbm = [k for k in stages if k in ("hdy_filter_compact_logits", "hdy_process_mask_packed")]
+        if hbm:
+            dom = max(hbm, key=lambda k: stages[k]["ms_total"])
+            calls, t_tot = stages[dom]["calls"], stages[dom]["ms_total"]
+            per_launch = alg[dom] / c.world / calls
+            ach = per_launch / (t_tot / calls * 1e-3) / 1e9
+            traffic = None
+            try:   # DRAM bytes per launch of the dominant call, from the committed ncu --set full capture
+                traffic = json.load(open(os.path.join(ROOT, "profiles", "r02_traffic.json")))["slide"][dom]["bytes"]
+            except Exception:
+                pass
+            out["roofline"] = {"bound": "hbm", "kernel": dom, "achieved": ach, "peak": peak, "unit": "GB/s",
+                               "frac": ach / peak, "frac_of_nominal_8000": ach / 8000.0, "traffic": traffic,
+                               "peak_source": peak_src, "algorithmic_bytes_per_launch": per_launch,
+                               "kernel_ms": t_tot / calls, "launches_per_step": calls}
     if cpu_merge is not None:
         out["cpu_merge"] = cpu_merge
     if want_e2e:
         # host-resident head outputs: every batch is copied H2D inside the timed region (4 pinned host batches are
-        # reused in rotation, bytes are counted for every copy), the slide's survivors are read back D2H
+        # reused in rotation, bytes are counted for every copy), the slide's survivors and their masks are read back
         nrot = min(4, len(store))
         host = [[t.cpu().pin_memory() for t in store[k]] for k in range(nrot)]
-        # one staging buffer set per stream of the post-processor (batch k runs on stream k % streams)
-        stages = [[torch.empty_like(t) for t in store[0]] for _ in range(max(1, args.slide_streams))]
+        nst = max(1, args.slide_streams)
+        stg = [[torch.empty_like(t) for t in store[0]] for _ in range(nst)]
+        host_p = [pool[k * bs:(k + 1) * bs].cpu().pin_memory() for k in range(min(4, P // bs))] if with_masks else None
+        stg_p = torch.empty_like(pool[:bs]) if with_masks else None
 
         def provider_h(a, b):
             k = ((a - t0) // bs)
             src = host[k % nrot]
-            stage = stages[k % len(stages)]
+            stage = stg[k % nst]
             n = b - a
-            for s, h in zip(stage, src):
-                s[:n].copy_(h[:n], non_blocking=True)
-            return [s[:n] for s in stage] if n < bs else stage
+            for s_, h in zip(stage, src):
+                s_[:n].copy_(h[:n], non_blocking=True)
+            return [s_[:n] for s_ in stage] if n < bs else stage
+
+        def protos_h(a, b):
+            k = ((a - t0) // bs)
+            n = b - a
+            stg_p[:n].copy_(host_p[k % len(host_p)][:n], non_blocking=True)
+            return stg_p[:n]
 
         hb, pinned = {}, {}
 
+        def back(k, t):
+            # results are read back into pinned host buffers that persist across slides (a pageable .cpu() of
+            # ~1 GB costs more than the whole H2D stream: fresh pages + a staged copy)
+            buf = pinned.get(k)
+            if buf is None or buf.shape[0] < t.shape[0]:
+                buf = torch.empty((int(t.shape[0] * 1.05) + 1,) + tuple(t.shape[1:]), dtype=t.dtype).pin_memory()
+                pinned[k] = buf
+            buf[:t.shape[0]].copy_(t, non_blocking=True)
+            hb[k] = buf[:t.shape[0]]
+
         def e2e_step(i):
-            # survivors are read back into pinned host buffers that persist across slides (a pageable .cpu() of
-            # 0.8 GB costs more than the whole H2D stream: fresh pages + a staged copy)
-            rr = post.run(provider_h, ordered=True)
-            for k in ("boxes", "scores", "labels"):
-                t = rr[k]
-                buf = pinned.get(k)
-                if buf is None or buf.shape[0] < t.shape[0]:
-                    buf = torch.empty((int(t.shape[0] * 1.05) + 1,) + tuple(t.shape[1:]), dtype=t.dtype).pin_memory()
-                    pinned[k] = buf
-                buf[:t.shape[0]].copy_(t, non_blocking=True)
-                hb[k] = buf[:t.shape[0]]
+            rr = post.run(provider_h, ordered=True, proto_provider=protos_h if with_masks else None,
+                          mask_words_per_row=40.0)
+            for k in ("boxes", "scores", "labels", "index"):
+                back(k, rr[k])
+            if with_masks:
+                pm = rr["masks"]
+                back("mask_geom", pm.geom)
+                back("mask_offsets", pm.offsets)
+                back("mask_bits", pm.bits[:words_local + 1])
 
         e2e_step(0)
-        Ke = max(1, min(steps, 3))
+        Ke = max(1, min(steps, 2))
         ms_e = c.timed(e2e_step, Ke)
-        d2h = sum(t.numel() * t.element_size() for t in hb.values())
-        out["e2e"] = {"value": n_tiles * Ke / (ms_e * 1e-3), "unit": "tiles/s", "h2d_bytes_per_step": in_bytes,
-                      "d2h_bytes_per_step": d2h, "steps": Ke, "ms_per_step": ms_e / Ke}
-        del host, stages
-    del store
+        d2h = torch.tensor([sum(t.numel() * t.element_size() for t in hb.values()), in_bytes], dtype=torch.int64,
+                           device=c.dev)
+        if c.world > 1:
+            import torch.distributed as dist
+            dist.all_reduce(d2h)
+        out["e2e"] = {"value": n_tiles * Ke / (ms_e * 1e-3), "unit": "tiles/s", "h2d_bytes_per_step": int(d2h[1]),
+                      "d2h_bytes_per_step": int(d2h[0]), "steps": Ke, "ms_per_step": ms_e / Ke}
+        del host, stg, host_p, stg_p, pinned, hb
+    del store, pool
+    post._batches = []
+    res.clear()
     torch.cuda.empty_cache()
     return out
 
@@ -727,51 +953,81 @@ def main():
     import torch.distributed as dist
     c = make_ctx(args)
     peak, peak_src = load_peak()
+    masks = args.masks
 
     if args.workload == "slide":
+        if masks == "paste":
+            raise SystemExit("--workload slide takes --masks proto or none")
         sampler = ClockSampler(c.local)
         sampler.start()
         s = run_slide(args, wl, c, args.steps, args.warmup, want_e2e=not args.no_e2e,
-                      want_cpu_merge=not args.no_cpu_baseline)
+                      want_cpu_merge=not args.no_cpu_baseline, masks=masks)
         clocks = sampler.stop()
-        # roofline of the dominant kernel on this workload's tiles: measured on a tiles1024 batch in the same process
-        targs = argparse.Namespace(**vars(args))
-        targs.workload, targs.masks, targs.steps, targs.warmup, targs.no_e2e = "tiles1024", "none", 50, 5, True
-        t = run_tiles(targs, WORKLOADS["tiles1024"], c)
+        cfg = common_config(args, wl, masks)
+        cfg.update({"tiles": s["tiles"], "tiles_per_step_per_gpu": s["tiles"] / c.world, "detections": s["detections"],
+                    "kept": s["kept"], "digest": s["digest"], "mask_digest": s["mask_digest"],
+                    "stages": "per tile: decode+filter+compact, nms, score/label select; append in slide coordinates; "
+                              "exact slide-level merge NMS (4 all-gathers of fixed-size seam blocks over NCCL when "
+                              "N>1)" + ("; process_mask (proto contraction, sigmoid, crop, upsample, >0.5, bit-packed) "
+                                        "for the KEPT rows" if masks == "proto" else ""),
+                    "l2": f"{s['input_bytes'] / 1e9:.1f} GB of head outputs resident in HBM, each read once per step" +
+                          (f" (prototype maps: tile t reads map t mod {s['proto_pool']})" if masks == "proto" else ""),
+                    "launch": f"tile batches of {wl['bs']} alternate over {args.slide_streams} streams "
+                              "(SlidePostprocessor(streams=)), appends chained by events"})
         line = {
             "metric": "postproc_tiles_per_s", "value": s["tiles_per_s"], "unit": "tiles/s", "n_gpus": c.world,
-            "steps": args.steps, "warmup": args.warmup, "ms_per_step": s["ms_per_slide"], "higher_is_better": True,
-            "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": "slide", "slide_px": s["slide_px"], "tile": s["tile"], "overlap": s["overlap"],
-                       "tiles": s["tiles"], "detections": s["detections"], "kept": s["kept"],
-                       "stages": "per-tile decode+filter+compact, nms, select; append in slide coordinates; exact "
-                                 "slide-level merge NMS (seam all-gather + verdict exchange over NCCL when N>1)",
-                       "l2": f"{s['input_bytes'] / 1e9:.1f} GB of head outputs resident in HBM, each read once per step",
-                       "launch": f"tile batches of {wl['bs']} alternate over {args.slide_streams} streams "
-                                 "(SlidePostprocessor(streams=)), appends chained by events"},
-            "boxes_per_s": s["boxes_per_s"], "roofline": t["roofline"], "stages": t["stages"],
-            "slide": s, "e2e": s.get("e2e"), "gpu_launches": s["gpu_launches"], "clocks": clocks,
+            "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": s["ms_per_slide"],
+            "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": cfg, "boxes_per_s": s["boxes_per_s"], "roofline": s.get("roofline"), "stages": s.get("stages"),
+            "pipeline": s["pipeline"], "slide": {k: v for k, v in s.items() if k not in ("stages", "roofline", "e2e")},
+            "e2e": s.get("e2e"), "gpu_launches": s["gpu_launches"], "clocks": clocks,
         }
+        if not args.no_sub:
+            for name, st, wu in (("tiles640", 100, 10), ("tiles1024", 40, 5)):
+                targs = argparse.Namespace(**vars(args))
+                targs.workload, targs.steps, targs.warmup, targs.no_e2e, targs.no_sub = name, st, wu, True, True
+                t = run_tiles(targs, WORKLOADS[name], c)
+                line[name] = {k: t[k] for k in ("value", "unit", "ms_per_step", "boxes_per_s", "roofline", "stages",
+                                                "pipeline", "gpu_launches", "config")}
+    elif args.workload == "hnet":
+        from tools.hnet_bench import run_hnet     # configs[4]: kept in its own file
+        line = run_hnet(args, wl, c, common_config, load_peak, ClockSampler)
     else:
         line = run_tiles(args, wl, c)
-        if not args.no_slide:
+        if not args.no_sub:
             sargs = argparse.Namespace(**vars(args))
             line["slide"] = run_slide(sargs, WORKLOADS["slide"], c, steps=3, warmup=2, want_e2e=False,
-                                      want_cpu_merge=not args.no_cpu_baseline)
+                                      want_cpu_merge=False, masks="proto" if masks == "proto" else "none",
+                                      want_stages=False)
 
-    cpu = None
     try:   # the CPU legs use every core the process started with, not just the GPU's NUMA node
         os.sched_setaffinity(0, _ORIG_AFFINITY)
     except Exception:
         pass
+    wk = args.workload if args.workload != "hnet" else "tiles1024"
+    if c.rank == 0 and not args.no_torch_cuda:
+        try:   # diagnostics must never take the record down
+            line["torch_cuda"] = time_torch_cuda(wk, wl, masks, args.dtype, c.dev,
+                                                 n_tiles=2 if wl["tile"] >= 1024 else 8, slide_size=args.slide_size)
+        except Exception as e:   # noqa: BLE001
+            line["torch_cuda"] = {"error": f"{type(e).__name__}: {e}"}
+        torch.cuda.empty_cache()
+    cpu = None
     if c.rank == 0 and not args.no_cpu_baseline:
-        masks = args.masks if args.workload != "slide" else "none"
-        v, cores, sample = time_cpu(wl, masks, budget_s=15.0, max_reps=30)
-        cpu = {"value": v, "unit": "tiles/s", "cores": cores, "kind": "port", "sample": sample}
-        # the reference caps its own thread pool at min(8, ncpu - 1) (metayolo/__init__.py:21,31): second data point
-        v8, c8, _ = time_cpu(wl, masks, budget_s=6.0, max_reps=10, threads=min(8, max(1, (os.cpu_count() or 2) - 1)))
-        cpu["value_reference_threads"] = v8
-        cpu["reference_threads"] = c8
+        try:
+            cpu = time_cpu(wk, wl, masks, budget_s=25.0, max_passes=20, dtype=args.dtype, slide_size=args.slide_size)
+            # the reference's own mask path (variant A) beside it, and its own thread cap: min(8, ncpu - 1)
+            # (metayolo/__init__.py:21,31)
+            if masks == "proto":
+                p = time_cpu(wk, wl, "paste", budget_s=1.0, max_passes=1, dtype=args.dtype, n_tiles=1,
+                             slide_size=args.slide_size)
+                cpu["paste_variant"] = {"value": p["value"], "ms_per_pass": p["ms_per_pass"], "tiles_per_pass": 1}
+            t8 = min(8, max(1, (os.cpu_count() or 2) - 1))
+            p8 = time_cpu(wk, wl, "none", budget_s=3.0, max_passes=3, threads=t8, dtype=args.dtype,
+                          slide_size=args.slide_size)
+            cpu["no_masks_reference_threads"] = {"value": p8["value"], "threads": p8["cores"]}
+        except Exception as e:   # noqa: BLE001
+            cpu = {"error": f"{type(e).__name__}: {e}", "kind": "port"}
     line["cpu_baseline"] = cpu
     if isinstance(line.get("e2e"), dict):
         line["e2e"]["host_affinity"] = c.affinity

@@ -642,15 +642,18 @@ int hdy_nms_tiles(const uint64_t* cand_keys, const float* cand_boxes, const floa
                                  reinterpret_cast<float4*>(keep_box), keep_score, keep_cls, keep_counts, gray_eps,
                                  keep_fragile, g_phase_host, (cudaStream_t)stream);
   if (rc || cap <= kNmsSmemCap) return rc;
-  static bool attr_set = false;
-  if (!attr_set) {
+  // the attribute is per DEVICE: a process-wide flag would leave every GPU but the first without the opt-in
+  static bool attr_set[64] = {};
+  int dev_i = 0;
+  cudaGetDevice(&dev_i);
+  if (dev_i < 0 || dev_i >= 64 || !attr_set[dev_i]) {
     cudaError_t e = cudaFuncSetAttribute(nms_tiles_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                          (int)kSmemBytes);
     if (e != cudaSuccess) {
       set_error("cudaFuncSetAttribute(nms_tiles_kernel): %s", cudaGetErrorString(e));
       return HDY_ERR_CUDA;
     }
-    attr_set = true;
+    if (dev_i >= 0 && dev_i < 64) attr_set[dev_i] = true;
   }
   nms_tiles_kernel<<<(unsigned)bs, kNmsThreads, kSmemBytes, (cudaStream_t)stream>>>(
       cand_keys, reinterpret_cast<const float4*>(cand_boxes), cand_cls, counts, cap, iou_thres, class_offset,

@@ -786,15 +786,18 @@ int launch_nms_tiles_smem(const uint64_t* cand_keys, const float4* cand_boxes, c
                           int max_det, int32_t* keep_idx, int32_t* keep_slot, float4* keep_box, float* keep_score,
                           float* keep_cls, int32_t* keep_counts, float gray_eps, uint8_t* keep_fragile,
                           unsigned long long* phase_cycles, cudaStream_t stream) {
-  static bool attr_set = false;
-  if (!attr_set) {
+  // the attribute is per DEVICE: a process-wide flag would leave every GPU but the first without the opt-in
+  static bool attr_set[64] = {};
+  int dev_i = 0;
+  cudaGetDevice(&dev_i);
+  if (dev_i < 0 || dev_i >= 64 || !attr_set[dev_i]) {
     cudaError_t e = cudaFuncSetAttribute(nms_tiles_smem_kernel<kFastThreads>,
                                          cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(FastSmem));
     if (e != cudaSuccess) {
       set_error("cudaFuncSetAttribute(nms_tiles_smem_kernel): %s", cudaGetErrorString(e));
       return HDY_ERR_CUDA;
     }
-    attr_set = true;
+    if (dev_i >= 0 && dev_i < 64) attr_set[dev_i] = true;
   }
   static const int sort_mode = [] {  // HDY_NMS_SORT=bitonic selects the sorting network (A/B runs); default: radix
     const char* v = getenv("HDY_NMS_SORT");

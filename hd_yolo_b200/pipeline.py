@@ -91,8 +91,10 @@ class SlidePostprocessor:
     def _append(self, out: DetectBatch, a: int, b: int) -> None:
         t0 = self.tile_range[0]
         self.acc.append(out, self.rois_dev[a - t0:b - t0], rois_host=self.rois[a:b])
-        if self.keep_batches:       # the mask pass needs the tile-local boxes and the coefficients again
-            self._batches.append((a, b, out, self.acc.tile_offsets[-1]))
+        if self.keep_batches:       # the mask pass needs the tile-local boxes and the coefficients again (only those)
+            keep = DetectBatch(out.boxes, None, None, None, None, out.extra, None, out.counts, out.cand_counts,
+                               out.max_det)
+            self._batches.append((a, b, keep, self.acc.tile_offsets[-1]))
 
     def detect(self, provider: Callable[[int, int], List[torch.Tensor]], keep_batches: bool = False) -> None:
         """Per-tile post-processing of every own tile, appended in slide coordinates.  No host synchronisation.
@@ -198,9 +200,10 @@ class SlidePostprocessor:
                           state, self.roi_size, upsample=upsample)
         return bld.finish()
 
-    def run(self, provider, ordered: bool = True, proto_provider=None) -> Dict[str, torch.Tensor]:
+    def run(self, provider, ordered: bool = True, proto_provider=None,
+            mask_words_per_row: float = 56.0) -> Dict[str, torch.Tensor]:
         self.detect(provider, keep_batches=proto_provider is not None)
         res = self.merge(ordered)
         if proto_provider is not None:
-            res['masks'] = self.masks(proto_provider, res['state'])
+            res['masks'] = self.masks(proto_provider, res['state'], words_per_row=mask_words_per_row)
         return res

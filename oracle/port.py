@@ -53,8 +53,8 @@ def compute_proposals(dets: List[torch.Tensor], anchors, strides) -> List[torch.
     for i, det in enumerate(dets):
         y = det.sigmoid()
         bs, na, ny, nx, no = y.shape
-        grid = make_grid(nx, ny).expand(1, na, ny, nx, 2)
-        anchor_grid = ag[i].view(1, na, 1, 1, 2).expand(1, na, ny, nx, 2)
+        grid = make_grid(nx, ny).to(det.device).expand(1, na, ny, nx, 2)      # buffers live on the model's device
+        anchor_grid = ag[i].to(det.device).view(1, na, 1, 1, 2).expand(1, na, ny, nx, 2)
         xy, wh, conf = y.tensor_split((2, 4), -1)
         xy = (xy * 2. - 0.5 + grid) * s[i]
         wh = (wh * 2.) ** 2 * anchor_grid

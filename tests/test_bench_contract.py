@@ -24,7 +24,10 @@ def test_reference_arm_prints_one_json_line():
     d = json.loads(lines[0])
     assert d["impl"] == "reference" and d["metric"] == "postproc_tiles_per_s" and d["unit"] == "tiles/s"
     assert d["higher_is_better"] is True and d["value"] > 0 and d["n_gpus"] == 1
-    assert d["config"]["workload"] == "tiles640"
+    assert d["config"]["workload"] == "slide" and d["config"]["masks"] == "paste"    # the reference's own mask path
+    # nothing is extrapolated: ms_per_step is the measured time of one sample pass, value follows from it
+    assert abs(d["value"] - d["tiles_per_step"] / (d["ms_per_step"] * 1e-3)) < 1e-6 * d["value"] + 1e-9
+    assert d["steps"] >= 1 and d["other_mask_variant"]["masks"] == "proto"
     assert d["cpu_baseline"]["kind"] == "port" and d["cpu_baseline"]["cores"] >= 1 and d["cpu_baseline"]["sample"]
     assert d["e2e"] == {"value": d["value"], "unit": "tiles/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
 

@@ -424,3 +424,104 @@ def test_detect_postprocess_many_classes_and_extras(cuda_device, nc, extra, layo
         if extra:
             rows = out.rows[i, :k].cpu().long()
             assert torch.equal(out.extra[i, :k].cpu(), rawcat[i, rows, 5 + nc:])
+
+
+# ------------------------------------------------------------------------------------------ fp16 ingestion
+@pytest.mark.parametrize("tile,bs,n_cand,extra", [(320, 3, 400, 0), (640, 4, 1000, 32), (1024, 2, 3000, 0)])
+def test_fp16_logits_equal_fp32_path_on_rounded_inputs(cuda_device, tile, bs, n_cand, extra):
+    """val_nuclei.py:115-116: on CUDA the reference runs a half() model, so the head hands over fp16 logits.  They are
+    widened on load (exact), all arithmetic stays fp32: every output must be BIT-identical to the fp32 path fed the
+    fp16-rounded numbers -- and the oracle, fed those numbers as fp32, keeps the same rows."""
+    dets = synth.nuclei_logits(bs, tile, 4, n_cand, seed=tile + extra, conf=0.25, extra=extra,
+                               generator_device="cuda")
+    d16 = [d.half() for d in dets]
+    d32 = [d.float() for d in d16]
+    spec = hdy.HeadSpec(synth.ANCHORS_3, synth.STRIDES_3, nc=4, no=9 + extra)
+    a = hdy.detect_postprocess(d16, spec, 0.25, 0.45, 3000, cap=4096)
+    b = hdy.detect_postprocess(d32, spec, 0.25, 0.45, 3000, cap=4096)
+    assert torch.equal(a.counts, b.counts) and torch.equal(a.cand_counts, b.cand_counts)
+    kc = a.counts.cpu().tolist()
+    assert min(kc) > 0.5 * n_cand
+    for i, k in enumerate(kc):
+        for f in ("boxes", "scores_full", "scores", "labels", "levels", "rows") + (("extra",) if extra else ()):
+            assert torch.equal(getattr(a, f)[i, :k], getattr(b, f)[i, :k]), f
+    assert torch.equal(hdy.decode_concat(d16, spec), hdy.decode_concat(d32, spec))
+    ref = _oracle_on_device_decode(hdy.decode_concat(d32, spec)[:1], 4, 0.25, 0.45, 3000)[0]
+    assert torch.equal(a.boxes[0, :kc[0]].cpu(), ref['boxes']) and torch.equal(a.labels[0, :kc[0]].cpu(), ref['labels'])
+
+
+def test_fp16_logits_golden_rows_and_unaligned_levels(cuda_device):
+    """Reference golden logits rounded to fp16: same kept rows as the oracle on the rounded numbers; a level tensor that
+    is not 16-byte aligned (a view at an odd offset) is refused loudly -- there is no slow fp16 path to fall into."""
+    g = load_golden("detect_640_l3")
+    dets, _ = _dets(g)
+    spec = _spec(g)
+    conf, iou, md = float(g["conf_thres"]), float(g["iou_thres"]), int(g["max_det"])
+    d16 = [d.to(cuda_device).half() for d in dets]
+    out = hdy.detect_postprocess(d16, spec, conf, iou, md).to_list()
+    ref = _oracle_on_device_decode(hdy.decode_concat([d.float() for d in d16], spec), spec.nc, conf, iou, md)
+    for a, b in zip(out, ref):
+        assert torch.equal(a['boxes'].cpu(), b['boxes']) and torch.equal(a['labels'].cpu(), b['labels'])
+    flat = torch.zeros((d16[0].numel() + 8,), dtype=torch.float16, device=cuda_device)
+    odd = flat[1:1 + d16[0].numel()].view(d16[0].shape)
+    odd.copy_(d16[0])
+    with pytest.raises(hdy.HdyError):
+        hdy.detect_postprocess([odd] + d16[1:], spec, conf, iou, md)
+
+
+# ------------------------------------------------------------------------------------------ every tile, full size
+@pytest.mark.parametrize("tile,bs,n_cand,md", [(640, 64, 1000, 1000), (1024, 128, 3000, 3000)])
+def test_full_size_every_tile_against_the_oracle(cuda_device, tile, bs, n_cand, md):
+    """BASELINE.json configs[1] (64 tiles of 640 px) and configs[2] (128 tiles of 1024 px) at their FULL sizes: every
+    tile's kept boxes / scores / labels against the oracle (nms_per_image + score select on the device-decoded rows)."""
+    spec = hdy.HeadSpec(synth.ANCHORS_3, synth.STRIDES_3, nc=4)
+    dets = synth.nuclei_logits(bs, tile, 4, n_cand, seed=7 * tile, conf=0.25, generator_device="cuda")
+    out = hdy.detect_postprocess(dets, spec, 0.25, 0.45, md, cap=4096)
+    counts = out.counts.cpu().tolist()
+    assert int(out.cand_counts[bs]) == 0
+    boxes, scores, labels = out.boxes.cpu(), out.scores.cpu(), out.labels.cpu()
+    for t0 in range(0, bs, 16):
+        cat = hdy.decode_concat([d[t0:t0 + 16].contiguous() for d in dets], spec)
+        ref = _oracle_on_device_decode(cat, 4, 0.25, 0.45, md)
+        for j, r in enumerate(ref):
+            i, k = t0 + j, counts[t0 + j]
+            assert k == len(r['boxes']), f"tile {i}"
+            assert torch.equal(boxes[i, :k], r['boxes']) and torch.equal(scores[i, :k], r['scores']) and \
+                torch.equal(labels[i, :k], r['labels']), f"tile {i}"
+
+
+# ------------------------------------------------------------------------------------------ the library GPU path
+def test_kept_indices_from_raw_logits_match_torch_cuda_reference(cuda_device):
+    """The north star's own wording: kept-detection index lists bit-exact against the reference's PyTorch/torchvision
+    path -- here run on the SAME B200 (oracle/port.py on CUDA tensors: ATen's CUDA sigmoid, torchvision's CUDA nms,
+    `set_iou_compare("cuda")`), from RAW logits, on >= 1 000 tiles.  Row lists and labels must be identical on every
+    tile; a tile where they are not is reported with the margin of the row that flipped."""
+    import torchvision  # noqa: F401
+    spec = hdy.HeadSpec(synth.ANCHORS_3, synth.STRIDES_3, nc=4)
+    hdy.set_iou_compare("cuda")
+    try:
+        n_tiles, bad = 0, []
+        for rep in range(8):
+            bs = 128
+            dets = synth.nuclei_logits(bs, 320, 4, 350, seed=9000 + rep, conf=0.25, generator_device="cuda")
+            out = hdy.detect_postprocess(dets, spec, 0.25, 0.45, 1000)
+            counts = out.counts.cpu().tolist()
+            preds = port.compute_proposals(dets, synth.ANCHORS_3, synth.STRIDES_3)      # ATen CUDA kernels
+            cat = port.concat_levels(preds)
+            ref = port.nms_per_image(cat, 4, 0.25, 0.45, 1000)                          # torchvision CUDA nms
+            for i, r in enumerate(ref):
+                k = counts[i]
+                s, l = port.select_scores(r['scores'].clone(), 0.25, port.default_descendants(4))
+                if k != len(r['boxes']) or not torch.equal(out.labels[i, :k], l):
+                    bad.append((rep, i, k, len(r['boxes'])))
+                    continue
+                b = out.boxes[i, :k]
+                if not bool(((b - r['boxes']).abs() <= 1e-5 * r['boxes'].abs() + 1e-4).all()):
+                    bad.append((rep, i, "boxes"))
+                if not bool(((out.scores[i, :k] - s).abs() <= 1e-5 * s.abs()).all()):
+                    bad.append((rep, i, "scores"))
+            n_tiles += bs
+        assert n_tiles >= 1000
+        assert not bad, f"{len(bad)} of {n_tiles} tiles differ from the torch/torchvision CUDA path: {bad[:5]}"
+    finally:
+        hdy.set_iou_compare("cpu")

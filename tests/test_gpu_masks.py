@@ -269,3 +269,57 @@ def test_process_mask_window_holds_every_set_pixel(cuda_device, ih, iw, mh, mw, 
     sat = [i for i in range(9, k, 3) if geom[i, 2] > 0 and boxes[i, 0] > 8 and boxes[i, 2] < iw - 8]
     tight = sum(int(ref[i, :, geom[i, 0]].any()) + int(ref[i, :, geom[i, 0] + geom[i, 2] - 1].any()) for i in sat)
     assert tight >= 1.6 * len(sat)
+
+
+# ------------------------------------------------------------------------------- fp16 prototypes / full-size masks
+@pytest.mark.parametrize("upsample", [False, True])
+def test_process_mask_fp16_prototypes_equal_fp32_path_on_rounded_inputs(cuda_device, upsample):
+    """A half() model hands over fp16 prototypes (val_nuclei.py:115-116).  They are widened on load and every fp16
+    value is an fp32 value, so the result must be BIT-identical to the fp32 path fed the rounded numbers."""
+    g = torch.Generator().manual_seed(21)
+    bs, md, mh, mw, ih, iw = 2, 150, 96, 120, 384, 480
+    protos = torch.randn((bs, 32, mh, mw), generator=g).half()
+    coef = (torch.randn((bs, md, 32), generator=g) * 0.5).to(cuda_device)
+    boxes = torch.stack([_rand_boxes(g, md, ih, iw, 6, 90) for _ in range(bs)]).to(cuda_device)
+    counts = torch.tensor([150, 97], dtype=torch.int32, device=cuda_device)
+    a = hm.process_mask_packed(protos.to(cuda_device), coef, boxes, counts, (ih, iw), upsample=upsample)
+    b = hm.process_mask_packed(protos.float().to(cuda_device), coef, boxes, counts, (ih, iw), upsample=upsample)
+    a.check()
+    assert torch.equal(a.geom, b.geom) and torch.equal(a.offsets, b.offsets) and torch.equal(a.bits, b.bits)
+    assert int(a.offsets[-1]) > 0
+    d16 = hm.process_mask_batch(protos.to(cuda_device), coef, boxes, counts, (ih, iw), upsample=upsample)
+    d32 = hm.process_mask_batch(protos.float().to(cuda_device), coef, boxes, counts, (ih, iw), upsample=upsample)
+    assert torch.equal(d16, d32)
+    # and against the oracle on the rounded prototypes
+    ref = port.process_mask(protos[1].float(), coef[1, :97].cpu(), boxes[1, :97].cpu().clone(), (ih, iw),
+                            upsample=upsample)
+    assert _agreement(d16[1, :97].cpu(), ref) >= AGREE
+
+
+def test_process_mask_full_size_config2(cuda_device):
+    """BASELINE configs[2] scale: 256 x 256 prototypes x ~2 650 nuclei-sized detections of a 1024-px tile (two tiles,
+    one of them crowded into a corner), bit planes vs the oracle's process_mask(upsample) > 0.5."""
+    g = torch.Generator().manual_seed(33)
+    bs, md, mh, ih = 2, 2650, 256, 1024
+    protos = torch.randn((bs, 32, mh, mh), generator=g)
+    coef = torch.randn((bs, md, 32), generator=g) * 0.4
+    boxes = torch.stack([_rand_boxes(g, md, ih, ih, 12, 36), _rand_boxes(g, md, 300, 300, 12, 36)])
+    counts = torch.tensor([md, md - 650], dtype=torch.int32)
+    pk = hm.process_mask_packed(protos.to(cuda_device), coef.to(cuda_device), boxes.to(cuda_device),
+                                counts.to(cuda_device), (ih, ih), upsample=True)
+    pk.check()
+    geom, offs, bits = pk.geom.cpu(), pk.offsets.cpu(), pk.bits.cpu()
+    agree = total = 0
+    for t in range(bs):
+        k = int(counts[t])
+        for c0 in range(0, k, 250):                      # the oracle's dense canvases: 250 x 4 MB at a time
+            c1 = min(c0 + 250, k)
+            ref = port.process_mask(protos[t], coef[t, c0:c1], boxes[t, c0:c1].clone(), (ih, ih), upsample=True)
+            sub = hm.PackedMasks(pk.geom[t * md + c0:t * md + c1], pk.offsets[t * md + c0:t * md + c1 + 1], pk.bits,
+                                 ih, ih, pk.status)
+            got = sub.to_dense().cpu()
+            agree += int((got.float() == ref).sum())
+            total += ref.numel()
+        assert int((geom[t * md + k:(t + 1) * md, 2:] != 0).sum()) == 0      # slots beyond counts are empty
+    assert agree / total >= AGREE, f"agreement {agree / total}"
+    assert int(offs[-1]) <= bits.numel() and int(offs[-1]) > 30 * 2000
