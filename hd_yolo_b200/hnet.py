@@ -11,9 +11,14 @@ delegates to torchvision, over csrc/rcnn.cu +
                                      composition is a TODO in the reference, hnet/hnet_new.py:275)
 
 torchvision.ops.batched_nms has two arithmetically different forms: the coordinate trick (boxes + class * (max + 1),
-one NMS) below 4000 box coordinates on CPU / 100000 on CUDA, and the class-separated "vanilla" form above.  ``mode``
-selects: "vanilla" (default: one batched launch, class-separated candidate lists), "trick", or "torchvision-cpu" /
-"torchvision-cuda" (torchvision's own size rule per image; needs the candidate counts on the host).
+one NMS) up to a size limit (box coordinates: 4000 on CPU, 100000 on CUDA in torchvision 0.26; read from the
+INSTALLED torchvision at import, ``BATCHED_NMS_LIMITS``) and the class-separated "vanilla" form above it.  The two
+round differently, so ``mode`` selects which arithmetic runs:
+  "torchvision-cuda" (default) / "torchvision-cpu": torchvision's own size rule per image for that device -- what the
+      reference executes (it runs on CUDA; at hnet's sizes, 1000 pre-NMS boxes per level, that is the trick).  Needs
+      the candidate counts on the host.
+  "vanilla": one batched launch over class-separated candidate lists (the throughput form; bit-parity with
+      torchvision only where torchvision itself takes the vanilla form), "trick": the coordinate trick always.
 """
 from __future__ import annotations
 
@@ -34,6 +39,25 @@ __all__ = ["box_decode", "rpn_filter_proposals", "roi_postprocess_detections", "
 
 XFORM_CLIP = math.log(1000.0 / 16)
 _MODES = ("vanilla", "trick", "torchvision-cpu", "torchvision-cuda")
+
+
+def _torchvision_limits() -> Dict[str, int]:
+    """(cpu, cuda) element-count limits of torchvision.ops.batched_nms' coordinate trick, from the installed source."""
+    lim = {"cpu": 4000, "cuda": 100000}
+    try:
+        import inspect
+        import re
+        from torchvision.ops import boxes as _b
+        m = re.search(r"numel\(\)\s*>\s*\(\s*([\d_]+)\s*if[^)]*?cpu[^)]*?else\s*([\d_]+)\s*\)",
+                      inspect.getsource(_b.batched_nms))
+        if m:
+            lim = {"cpu": int(m.group(1).replace("_", "")), "cuda": int(m.group(2).replace("_", ""))}
+    except Exception:   # no torchvision / source not available: the documented 0.26 values
+        pass
+    return lim
+
+
+BATCHED_NMS_LIMITS = _torchvision_limits()
 
 
 def _a16(t: torch.Tensor) -> torch.Tensor:
@@ -93,7 +117,8 @@ def _class_separated(cand: _Cand, n_img: int, group: int, iou: float, top_n: int
 def _per_image_rule(cand: _Cand, n_img: int, iou: float, top_n: int, mode: str):
     """torchvision's own batched_nms per image (size rule: coordinate trick up to 4000 / 100000 box coordinates,
     class-separated above).  cand holds one list per image with classes."""
-    limit = {"torchvision-cpu": 4000, "torchvision-cuda": 100000, "trick": 1 << 62, "vanilla": -1}[mode]
+    limit = {"torchvision-cpu": BATCHED_NMS_LIMITS["cpu"], "torchvision-cuda": BATCHED_NMS_LIMITS["cuda"],
+             "trick": 1 << 62, "vanilla": -1}[mode]
     counts = cand.counts[:n_img].cpu().tolist()
     dev = cand.counts.device
     keys = cand.keys.view(torch.int64)[:n_img * cand.cap].view(n_img, cand.cap)
@@ -127,7 +152,7 @@ def _per_image_rule(cand: _Cand, n_img: int, iou: float, top_n: int, mode: str):
 def rpn_filter_proposals(proposals: torch.Tensor, objectness: torch.Tensor, image_shapes: Sequence[Tuple[int, int]],
                          num_anchors_per_level: Sequence[int], pre_nms_top_n: int = 1000, post_nms_top_n: int = 1000,
                          nms_thresh: float = 0.7, score_thresh: float = 0.0, min_size: float = 1e-3,
-                         mode: str = "vanilla") -> Tuple[List[torch.Tensor], List[torch.Tensor]]:
+                         mode: str = "torchvision-cuda") -> Tuple[List[torch.Tensor], List[torch.Tensor]]:
     """RegionProposalNetwork.filter_proposals (torchvision models/detection/rpn.py): proposals [N, A, 4] (decoded
     anchors), objectness [N, A] (or [N*A, 1]) logits -> (boxes per image, scores per image), best first."""
     if mode not in _MODES:
@@ -164,7 +189,7 @@ def roi_postprocess_detections(class_logits: torch.Tensor, box_regression: torch
                                proposals: List[torch.Tensor], image_shapes: Sequence[Tuple[int, int]],
                                box_weights=(10.0, 10.0, 5.0, 5.0), score_thresh: float = 0.05,
                                nms_thresh: float = 0.5, detections_per_img: int = 100, min_size: float = 1e-2,
-                               mode: str = "vanilla"):
+                               mode: str = "torchvision-cuda"):
     """RoIHeads.postprocess_detections (torchvision models/detection/roi_heads.py): class_logits [R, C],
     box_regression [R, C*4], proposals = per-image [r_i, 4] -> (boxes, scores, labels) per image, best first."""
     if mode not in _MODES:

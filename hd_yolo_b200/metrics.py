@@ -53,16 +53,15 @@ def match_predictions(output: Dict[str, torch.Tensor], target: Dict[str, torch.T
     if k == 0:
         return {'order': torch.empty(0, **i64), 'scores': scores.reshape(0), 'labels': output['labels'].reshape(0), **empty}
     boxes = _aligned16(boxes.contiguous())
-    # 1. predictions by score: one ascending sort of (~score, row) keys (hdy_nms_tiles with iou_thres = 2 sorts only)
+    # 1. predictions by score: one ascending radix sort of the (~score, row) keys (hdy_sort_keys), row = low word
+    from .slide import sort_keys
+    scores = scores.contiguous()
     keys = torch.empty(k, dtype=torch.int64, device=dev)
-    _call("hdy_make_keys", ptr(scores.contiguous()), 1, k, ptr(keys), _stream())
-    cand = _Cand.__new__(_Cand)
-    cand.bs, cand.cap, cand.keys, cand.boxes, cand.cls = 1, k, keys, boxes, None
-    cand.counts = torch.tensor([k, 0], dtype=torch.int32).to(dev)
-    order32, _, _, o_scores, _, _, _ = _run_nms(cand, 2.0, k)
-    order32 = order32[0].contiguous()
-    order = order32.to(torch.int64)
-    res = {'order': order, 'scores': o_scores[0], 'labels': output['labels'][order]}
+    _call("hdy_make_keys", ptr(scores), 1, k, ptr(keys), _stream())
+    sort_keys(keys)
+    order = keys & 0xffffffff
+    order32 = order.to(torch.int32).contiguous()
+    res = {'order': order, 'scores': scores[order], 'labels': output['labels'][order]}
     if g == 0:
         return {**res, **empty}
     gts = _aligned16(gts.contiguous())
@@ -83,12 +82,20 @@ def match_predictions(output: Dict[str, torch.Tensor], target: Dict[str, torch.T
         cap = n_match                                 # a crowded image: retry with the size the kernel reported
     if n_match == 0:
         return {**res, **empty}
-    # 3. IoU-descending order of the pairs
-    pc.counts[1] = 0
-    pidx, _, _, pious, _, _, _ = _run_nms(pc, 2.0, n_match)
-    pidx = pidx[0, :n_match].to(torch.int64)
-    res.update({'pred_idx': pidx // g, 'true_idx': pidx % g, 'ious': pious[0, :n_match]})
+    # 3. IoU-descending order of the pairs: a key sort (pairs of one prediction share a box -- as an "NMS that only
+    #    sorts" they would all land in one spatial-hash cell); index and IoU are read back out of the key
+    pk = pk[:n_match].contiguous()
+    sort_keys(pk)
+    pidx = pk & 0xffffffff
+    res.update({'pred_idx': pidx // g, 'true_idx': pidx % g, 'ious': _key_scores(pk)})
     return res
+
+
+def _key_scores(keys: torch.Tensor) -> torch.Tensor:
+    """fp32 value stored in the high word of order keys ((~orderable(v) << 32) | index, csrc/hdy_common.cuh)."""
+    o = (~(keys >> 32)) & 0xffffffff                                    # orderable(v)
+    bits = torch.where(o >= 0x80000000, o & 0x7fffffff, (~o) & 0xffffffff)
+    return torch.where(bits >= 0x80000000, bits - (1 << 32), bits).to(torch.int32).view(torch.float32)
 
 
 class APMeter(object):

@@ -146,9 +146,6 @@ class SlidePostprocessor:
                 if self._cores_all is None:     # tile ids of the accumulator are local; the tables cover the slide
                     self._cores_all = tile_cores(self.rois).to(self.device)
                     self._rois_all = self.rois.to(self.device).contiguous()
-                over = acc.overhang() if acc.rois else None
-                kw = dict(tile_id=acc.tile, tile_base=self.tile_range[0], cores=self._cores_all,
-                          rois_all=self._rois_all)
             hook, box = None, {}
             if ordered:
                 cnt = be.meta[hdist.M_KEPT:hdist.M_KEPT + 1]
@@ -156,15 +153,17 @@ class SlidePostprocessor:
                 def hook(state):            # enqueued in front of the single host read of the merge
                     box['keys'] = _order_keys(state, acc.scores, n, cnt)
             while True:
-                if n + be.rep_cap > acc.capacity:
-                    raise HdyError(f"slide accumulator: {n} rows + {be.rep_cap} replica slots exceed the capacity "
-                                   f"{acc.capacity}; pass a larger `capacity`")
+                acc.reserve(n + be.rep_cap)         # (no-op unless the seam blocks had to grow)
+                if self.shortcut:
+                    kw = dict(tile_id=acc.tile, tile_base=self.tile_range[0], cores=self._cores_all,
+                              rois_all=self._rois_all)
+                    over = acc.overhang() if acc.rois else None
                 try:
                     res = hdist.seam_merge(self.comm, be, acc.boxes, acc.scores, n, over, after_finish=hook, **kw)
                     break
                 except hdist.SeamOverflow as e:     # raised on every rank alike: grow the blocks and repeat
                     be.set_seam_cap(int(e.needed * 1.25) + 1024)
-            state, base = res['state'], res['base']
+            state, base = res['state'].clone(), res['base']       # (the backend's buffer is reused by the next merge)
             info = {'exchanges': res['exchanges'], 'seam_rows': res['seam_rows']}
             out: Dict[str, object] = {'state': state, 'n': n, 'base': base, **info}
             if ordered:

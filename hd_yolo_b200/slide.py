@@ -411,6 +411,22 @@ class SlideAccumulator:
         self.rois.append(rois)
         self.n_tiles += bs
 
+    def reserve(self, capacity: int) -> None:
+        """Grow the row arrays to `capacity` rows, keeping what was appended (the sharded merge parks the other ranks'
+        seam rows behind the own rows and may find that it needs more room than was planned)."""
+        capacity = int(capacity)
+        if capacity <= self.capacity:
+            return
+        n = min(int(self.cursor.item()), self.capacity)
+        for name in ("boxes", "scores", "labels", "tile"):
+            old = getattr(self, name)
+            if old is None:
+                continue
+            new = torch.empty((capacity,) + tuple(old.shape[1:]), dtype=old.dtype, device=old.device)
+            new[:n] = old[:n]
+            setattr(self, name, new)
+        self.capacity = capacity
+
     def count(self) -> int:
         """Rows appended so far (synchronises); raises on capacity overflow."""
         both = torch.cat([self.cursor, self.status.long()]).cpu()

@@ -243,8 +243,8 @@ def crop_mask(masks: torch.Tensor, boxes: torch.Tensor) -> torch.Tensor:
     zero everything outside x1 <= col < x2, y1 <= row < y2."""
     n, h, w = masks.shape
     x1, y1, x2, y2 = torch.chunk(boxes[:, :, None], 4, 1)
-    r = torch.arange(w, dtype=x1.dtype)[None, None, :]
-    c = torch.arange(h, dtype=x1.dtype)[None, :, None]
+    r = torch.arange(w, device=masks.device, dtype=x1.dtype)[None, None, :]   # upstream: device=masks.device
+    c = torch.arange(h, device=masks.device, dtype=x1.dtype)[None, :, None]
     return masks * ((r >= x1) * (r < x2) * (c >= y1) * (c < y2))
 
 
