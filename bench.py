@@ -782,27 +782,38 @@ def run_slide(args, wl, c, steps, warmup, want_e2e, want_cpu_merge=False, masks=
     ops.profile.reset()
     ms = c.timed(step, steps)
     launches = ops.profile.launches
+    r = res["r"]
+    n_local = int(r["n"])
+    seam_rows, exchanges = r.get("seam_rows"), r.get("exchanges")
+    dg = kept_digest(r["state"], r["base"])
+    words_local = int(r["masks"].offsets[n_local]) if with_masks else 0
+    md = mask_digest(r["masks"], r["state"], r["base"]) if with_masks else torch.zeros_like(dg)
+    del r
+    res.clear()                         # the phases below allocate their own results: release the slide's first
     # phases (each timed alone, max over ranks)
     reps = max(2, min(steps, 3))
     ms_detect = _timed_phase(c, lambda: post.detect(provider, keep_batches=with_masks), reps)
-    ms_merge = _timed_phase(c, lambda: res.__setitem__("m", post.merge(ordered=True)), reps)
+
+    def merge_only():
+        res.pop("m", None)
+        res["m"] = post.merge(ordered=True)
+
+    ms_merge = _timed_phase(c, merge_only, reps)
     ms_masks = _timed_phase(c, lambda: post.masks(protos, res["m"]["state"], words_per_row=40.0), reps) \
         if with_masks else 0.0
-    res.pop("m", None)
-    r = res["r"]
-    n_local = int(r["n"])
-    dg = kept_digest(r["state"], r["base"])
+    res.clear()
     cand_local = 0
     stages = None
-    words_local = int(r["masks"].offsets[n_local]) if with_masks else 0
-    md = mask_digest(r["masks"], r["state"], r["base"]) if with_masks else torch.zeros_like(dg)
     if want_stages:
         # per-call CUDA-event times of one more (untimed) pass: every C-ABI call bracketed by events on its stream
+        ns, post.n_streams = post.n_streams, 1       # one stream: a call's events then bracket its own kernels only
         ops.profile.enabled = True
         ops.profile.reset()
         step(0)
         prof = ops.profile.summary()
         ops.profile.enabled = False
+        post.n_streams = ns
+        res.clear()
         stages = {k: {"calls": n, "ms_total": t} for k, (n, t) in prof.items()}
         cand_local = int(sum(int(b[2].cand_counts[:-1].sum()) for b in post._batches)) if post._batches else 0
     cpu_merge = None
@@ -845,7 +856,7 @@ def run_slide(args, wl, c, steps, warmup, want_e2e, want_cpu_merge=False, masks=
            "candidates": cand_all, "mask_words": words_all, "digest": digest, "mask_digest": mdigest,
            "input_bytes": in_all, "slide_px": S, "tile": tile, "overlap": wl["overlap"], "dtype_in": args.dtype,
            "masks": masks, "proto_pool": P,
-           "seam_rows": r.get("seam_rows"), "exchanges": r.get("exchanges"), "gpu_launches": launches,
+           "seam_rows": seam_rows, "exchanges": exchanges, "gpu_launches": launches,
            "boxes_per_s": cand_all * steps / (ms * 1e-3) if cand_all else n_all * steps / (ms * 1e-3),
            "pipeline": {"algorithmic_bytes_per_step": step_bytes,
                         "achieved_gbs": step_bytes / (ms / steps * 1e-3) / 1e9 / c.world,

@@ -61,25 +61,32 @@ struct RegionList {
 };
 static_assert(sizeof(RegionList) == 512, "one region list is 512 bytes");
 struct PmWorkspace {
-  int32_t* large_count;
+  int32_t* large_count;   // [0]: detections left to the per-detection kernel
+  int32_t* work_counter;  // [1]: next (tile, region) item of the fused kernel
   int32_t* large_list;
   float* patches;
   RegionList* regions;
+  int32_t* done;          // per slot: pieces of the patch written so far (fused kernel)
 };
 static inline size_t align256(size_t v) { return (v + 255) & ~(size_t)255; }
 size_t process_mask_workspace_bytes(long long bs, long long max_det) {
   const long long slots = bs * max_det;
-  return 256 + align256((size_t)slots * 4) + (size_t)slots * kPatchPitch * kPatchPitch * 4 +
+  return 256 + 2 * align256((size_t)slots * 4) + (size_t)slots * kPatchPitch * kPatchPitch * 4 +
          (size_t)bs * kMaxRegionsPerTile * sizeof(RegionList);
 }
 static PmWorkspace pm_workspace(void* base, long long slots) {
   PmWorkspace w;
   unsigned char* p = static_cast<unsigned char*>(base);
   w.large_count = reinterpret_cast<int32_t*>(p);
-  w.large_list = reinterpret_cast<int32_t*>(p + 256);
-  w.patches = reinterpret_cast<float*>(p + 256 + align256((size_t)slots * 4));
-  w.regions = reinterpret_cast<RegionList*>(p + 256 + align256((size_t)slots * 4) +
-                                            (size_t)slots * kPatchPitch * kPatchPitch * 4);
+  w.work_counter = reinterpret_cast<int32_t*>(p) + 1;
+  p += 256;
+  w.large_list = reinterpret_cast<int32_t*>(p);
+  p += align256((size_t)slots * 4);
+  w.done = reinterpret_cast<int32_t*>(p);
+  p += align256((size_t)slots * 4);
+  w.patches = reinterpret_cast<float*>(p);
+  p += (size_t)slots * kPatchPitch * kPatchPitch * 4;
+  w.regions = reinterpret_cast<RegionList*>(p);
   return w;
 }
 
@@ -424,6 +431,293 @@ __global__ void __launch_bounds__(kUpWarps * 32) mask_upsample_pack_kernel(
   }
 }
 
+// ------------------------------------------------------------------------------------------------ fused path
+// Phases 1 and 2 in ONE persistent kernel (bit-packed + upsampled masks, the throughput form).  The two phases want
+// different resources -- phase 1 waits on HBM (TMA regions), phase 2 on issue slots (~500 instructions per detection)
+// -- and as two kernels they ran back to back: 1.13 ms per 148-tile batch of the slide, 5.5x the HBM floor.  Here
+//   * two CTAs per SM (8 warps, one 72 KB region buffer each) walk the (tile, region) items handed out by a global
+//     counter: while one CTA waits for its region (TMA) and for the dependent loads of its first pieces, the other
+//     computes; the ticket of the next item is drawn at the start of an item and looked at only at its end;
+//   * a warp takes the next piece of the item (dynamic, shared-memory counter), contracts it and writes it into the
+//     detection's patch in the L2-resident workspace, then bumps the detection's `done` counter; the warp that writes
+//     the LAST piece of a detection upsamples and packs it at once (patch read back through L2), so the issue-bound
+//     half of the work fills the cycles the other warps of the SM spend waiting for their region;
+//   * the upsample keeps the ringed patch rows in registers (one predicated, coalesced load per source row) and takes
+//     the two x taps by shuffle: no patch staging, no ring building, no per-detection geometry recomputation.
+// Detections whose kept range exceeds 16 x 16 proto pixels, or that met an overfull region list, are listed by the
+// binning kernel and go to the per-detection kernel of mask.cu (their words are cleared first: it ORs bits in).
+constexpr int kFuWarps = 8;
+constexpr int kFuThreads = kFuWarps * 32;
+constexpr int kFuRows = kPatchPitch + 2;  // ringed source rows
+
+template <typename E>
+struct FuSmem {
+  E proto[kRegNm][kRegBoxY][kRegBoxX];  // TMA destination
+  float coef[kFuWarps][kRegNm];
+  float col[kFuWarps][kFuRows][32];  // x-interpolated values of the lanes' columns, per source row
+  RowTab rows[kFuWarps][kRowChunk];
+  uint64_t full;
+  int item;
+  int next_piece;
+};
+
+// binning for the fused path: region lists as proto_bin_kernel, plus the per-slot piece counters (zeroed here) and
+// the list of detections the fused kernel does not take
+__global__ void __launch_bounds__(256) proto_bin_fused_kernel(const float4* __restrict__ boxes,
+                                                              const int32_t* __restrict__ counts, long long n_slots,
+                                                              int max_det, int mh, int mw, int rxn, int ryn, float rx,
+                                                              float ry, const int32_t* __restrict__ geom4,
+                                                              RegionList* __restrict__ regions,
+                                                              int32_t* __restrict__ done,
+                                                              int32_t* __restrict__ large_count,
+                                                              int32_t* __restrict__ large_list) {
+  const long long slot = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (slot >= n_slots) return;
+  done[slot] = 0;
+  const int tile = (int)(slot / max_det), d = (int)(slot - (long long)tile * max_det);
+  if (d >= counts[tile]) return;
+  if (geom4[4 * slot + 2] <= 0 || geom4[4 * slot + 3] <= 0) return;  // empty window, or not KEPT (slide form)
+  const KeptRange k = kept_range(boxes[slot], rx, ry, mw, mh);
+  if (k.px1 <= k.px0 || k.py1 <= k.py0) return;
+  bool leave = k.px1 - k.px0 > kPatchPitch || k.py1 - k.py0 > kPatchPitch;
+  if (!leave) {
+    const int rx0 = k.px0 / kRegBoxX, rx1 = (k.px1 - 1) / kRegBoxX;
+    const int ry0 = k.py0 / kRegBoxY, ry1 = (k.py1 - 1) / kRegBoxY;
+    for (int ryy = ry0; ryy <= ry1; ++ryy)
+      for (int rxx = rx0; rxx <= rx1; ++rxx) {
+        RegionList& R = regions[(size_t)tile * (rxn * ryn) + ryy * rxn + rxx];
+        const int pos = atomicAdd(&R.count, 1);
+        if (pos < kRegCap)
+          R.det[pos] = (uint16_t)d;
+        else
+          leave = true;  // overfull region: its piece is never written, so the patch never completes -- hand it over
+      }
+  }
+  if (leave) large_list[atomicAdd(large_count, 1)] = (int32_t)slot;
+}
+
+// the words of the listed detections are cleared: the per-detection kernel ORs its bits in
+__global__ void pm_clear_listed_kernel(const int32_t* __restrict__ geom4, const int64_t* __restrict__ offsets,
+                                       uint32_t* __restrict__ bits, long long capacity_words,
+                                       const int32_t* __restrict__ list, const int32_t* __restrict__ list_count) {
+  const int n = *list_count;
+  for (int item = blockIdx.x; item < n; item += gridDim.x) {
+    const long long slot = list[item];
+    const int4 g = reinterpret_cast<const int4*>(geom4)[slot];
+    const long long words = (long long)((g.z + 31) >> 5) * g.w, off = offsets[slot];
+    if (off + words > capacity_words) continue;  // reported by the kernel that would have filled them
+    for (long long i = threadIdx.x; i < words; i += blockDim.x) bits[off + i] = 0u;
+  }
+}
+
+// One warp: upsample (ATen bilinear, align_corners=False, operation by operation) + threshold + pack of one detection
+// whose sigmoid patch (<= 16 x 16, pitch 16) is complete in the workspace.
+__device__ __forceinline__ void upsample_pack_warp(const float* __restrict__ patch, const KeptRange& k, const int4 wdw,
+                                                   long long off, uint32_t* __restrict__ bits, int mh, int mw, int ih,
+                                                   int iw, float (*col)[32], RowTab* rowtab, int lane) {
+  const int pw = k.px1 - k.px0, ph = k.py1 - k.py0;
+  const int gx0 = wdw.x, gy0 = wdw.y, gw = wdw.z, gh = wdw.w;
+  const int wpr = (gw + 31) >> 5;
+  const int src_rows = ph + 2;
+  // ringed patch: lane j holds ring column j of every ring row s (zero outside the kept pixels: the crop)
+  float prow[kFuRows];
+  const bool lane_in = lane >= 1 && lane <= pw;
+#pragma unroll
+  for (int s = 0; s < kFuRows; ++s)
+    prow[s] = (lane_in && s >= 1 && s <= ph) ? __ldcg(patch + (s - 1) * kPatchPitch + lane - 1) : 0.f;
+  const float sxs = (float)mw / (float)iw, sys = (float)mh / (float)ih;  // ATen: scale = in / out (fp32)
+  for (int r0 = 0; r0 < gh; r0 += kRowChunk) {
+    const int nr = min(kRowChunk, gh - r0);
+    __syncwarp();
+    for (int r = lane; r < nr; r += 32) {
+      const Lerp Y = lerp_coord(gy0 + r0 + r, sys, mh);
+      RowTab T;
+      // taps outside [py0 - 1, py1] contribute nothing (cropped): clamp them onto the ring of zeros
+      T.i0 = min(max(Y.i0 - k.py0 + 1, 0), ph + 1);
+      T.i1 = min(max(Y.i1 - k.py0 + 1, 0), ph + 1);
+      T.l0 = Y.l0;
+      T.l1 = Y.l1;
+      rowtab[r] = T;
+    }
+    for (int w = 0; w < wpr; ++w) {
+      const int vw = min(32, gw - (w << 5));  // valid columns of this word
+      const bool narrow = vw <= 16;
+      // x pass (lane = column of the word): top/bot of ATen's formula for every source row, taps by shuffle
+      const int c = (w << 5) + lane;
+      const bool valid = c < gw;
+      const Lerp X = lerp_coord(gx0 + (valid ? c : 0), sxs, mw);
+      const int xi0 = min(max(X.i0 - k.px0 + 1, 0), pw + 1), xi1 = min(max(X.i1 - k.px0 + 1, 0), pw + 1);
+      __syncwarp();
+#pragma unroll
+      for (int s = 0; s < kFuRows; ++s) {
+        if (s < src_rows) {  // warp-uniform
+          const float a = __shfl_sync(0xffffffffu, prow[s], xi0), b = __shfl_sync(0xffffffffu, prow[s], xi1);
+          col[s][lane] = __fadd_rn(__fmul_rn(X.l0, a), __fmul_rn(X.l1, b));
+        }
+      }
+      __syncwarp();
+      uint32_t* dst = bits + off + (long long)r0 * wpr + w;
+      if (narrow) {
+        // narrow word (the tail of a 36-px window is 4 columns): lanes cover floor(32 / vw) output rows at a time
+        const int rows_per = 32 / vw;
+        const int lr = lane / vw, lc = lane - lr * vw;
+        const bool active = lr < rows_per;
+        const unsigned row_mask = (1u << vw) - 1u;
+        for (int rb = 0; rb < nr; rb += rows_per) {
+          const int r = rb + lr;
+          bool bit = false;
+          if (active && r < nr) {
+            const float4 rt = *reinterpret_cast<const float4*>(&rowtab[r]);
+            const float v = __fadd_rn(__fmul_rn(rt.z, col[__float_as_int(rt.x)][lc]),
+                                      __fmul_rn(rt.w, col[__float_as_int(rt.y)][lc]));
+            bit = v > 0.5f;
+          }
+          const unsigned m = __ballot_sync(0xffffffffu, bit);
+          if (active && lc == 0 && r < nr) dst[(long long)r * wpr] = (m >> (lr * vw)) & row_mask;
+        }
+        continue;
+      }
+      unsigned myword = 0;
+#pragma unroll 4
+      for (int r = 0; r < nr; ++r) {
+        const float4 rt = *reinterpret_cast<const float4*>(&rowtab[r]);
+        const float v = __fadd_rn(__fmul_rn(rt.z, col[__float_as_int(rt.x)][lane]),
+                                  __fmul_rn(rt.w, col[__float_as_int(rt.y)][lane]));
+        const unsigned word = __ballot_sync(0xffffffffu, valid && v > 0.5f);
+        if ((r & 31) == lane) myword = word;
+        if ((r & 31) == 31 || r == nr - 1) {  // lanes store the words of up to 32 rows at once
+          const int rr = (r & ~31) + lane;
+          if (rr <= r) dst[(long long)rr * wpr] = myword;
+        }
+      }
+    }
+  }
+}
+
+template <typename E>
+__global__ void __launch_bounds__(kFuThreads, 2) mask_fused_kernel(
+    const __grid_constant__ CUtensorMap tmap, const float* __restrict__ coef, const float4* __restrict__ boxes,
+    int max_det, int mh, int mw, int ih, int iw, int rxn, int ryn, long long n_items, float rx, float ry,
+    float* __restrict__ patches, const RegionList* __restrict__ regions, int32_t* __restrict__ done,
+    int32_t* __restrict__ work_counter, const int32_t* __restrict__ geom4, const int64_t* __restrict__ offsets,
+    uint32_t* __restrict__ bits, long long capacity_words, int32_t* __restrict__ status) {
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  FuSmem<E>& S = *reinterpret_cast<FuSmem<E>*>(smem_raw);
+  const int t = threadIdx.x, lane = t & 31, warp = t >> 5;
+  const int per_tile = rxn * ryn;
+  long long ticket = 0;  // thread 0: the next item's ticket, drawn one item ahead
+  if (t == 0) {
+    mbar_init(&S.full, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    ticket = (long long)atomicAdd(work_counter, 1);
+  }
+  uint32_t parity = 0u;
+  for (;;) {
+    if (t == 0) {
+      // resolve the ticket drawn an item ago (regions nobody reaches into are skipped: they load nothing)
+      while (ticket < n_items && regions[ticket].count <= 0) ticket = (long long)atomicAdd(work_counter, 1);
+      const int item = ticket < n_items ? (int)ticket : -1;
+      if (item >= 0) {
+        const int tile = item / per_tile, reg = item - tile * per_tile;
+        const int RY = reg / rxn, RX = reg - RY * rxn;
+        mbar_arrive_expect_tx(&S.full, (uint32_t)sizeof(S.proto));
+        tma_load_4d(&S.proto[0][0][0], &tmap, RX * kRegBoxX, RY * kRegBoxY, 0, tile, &S.full);
+        ticket = (long long)atomicAdd(work_counter, 1);  // used at the top of the next iteration only
+      }
+      S.item = item;
+      S.next_piece = 0;
+    }
+    __syncthreads();
+    const int cur = S.item;
+    if (cur < 0) break;
+    const int tile = cur / per_tile, reg = cur - tile * per_tile;
+    const int RY = reg / rxn, RX = reg - RY * rxn;
+    const int X0 = RX * kRegBoxX, Y0 = RY * kRegBoxY;
+    const RegionList& RL = regions[cur];
+    const int nl = min(RL.count, kRegCap);
+    // first piece of this warp: its box and coefficient are requested before the wait for the region
+    int e = 0;
+    if (lane == 0) e = atomicAdd(&S.next_piece, 1);
+    e = __shfl_sync(0xffffffffu, e, 0);
+    size_t nslot = 0;
+    float4 nbox = make_float4(0.f, 0.f, 0.f, 0.f);
+    float ncoef = 0.f;
+    auto fetch = [&](int ee) {
+      nslot = (size_t)tile * max_det + RL.det[ee];
+      nbox = boxes[nslot];
+      ncoef = coef[nslot * kRegNm + lane];
+    };
+    if (e < nl) fetch(e);
+    while (!mbar_try_wait(&S.full, parity)) {
+    }
+    parity ^= 1u;
+    while (e < nl) {
+      const size_t slot = nslot;
+      const float4 box = nbox;
+      const KeptRange k = kept_range(box, rx, ry, mw, mh);
+      __syncwarp();
+      S.coef[warp][lane] = ncoef;
+      __syncwarp();
+      int en = 0;
+      if (lane == 0) en = atomicAdd(&S.next_piece, 1);
+      en = __shfl_sync(0xffffffffu, en, 0);
+      if (en < nl) fetch(en);  // the next piece's loads fly while this one is computed
+      float cf[kRegNm];
+#pragma unroll
+      for (int c = 0; c < kRegNm; c += 4) {
+        const float4 v = *reinterpret_cast<const float4*>(&S.coef[warp][c]);
+        cf[c] = v.x;
+        cf[c + 1] = v.y;
+        cf[c + 2] = v.z;
+        cf[c + 3] = v.w;
+      }
+      // the piece: kept pixels inside this region; lanes cover floor(32 / pw) rows at a time
+      const int qx0 = max(k.px0, X0), qx1 = min(k.px1, X0 + kRegBoxX);
+      const int qy0 = max(k.py0, Y0), qy1 = min(k.py1, Y0 + kRegBoxY);
+      const int pw = qx1 - qx0;  // 1..16
+      const int rows_per = 32 / pw;
+      const int ly = lane / pw, lx = lane - ly * pw;
+      float* pbase = patches + slot * (kPatchPitch * kPatchPitch);
+      if (ly < rows_per) {
+        const int xx = qx0 + lx, sx = xx - X0;
+        const bool x_in = (float)xx >= k.x1d && (float)xx < k.x2d;
+        float* dstp = pbase + (xx - k.px0);
+        for (int yy = qy0 + ly; yy < qy1; yy += rows_per) {
+          float v = 0.f;
+          if (x_in && (float)yy >= k.y1d && (float)yy < k.y2d) {
+            const int sy = yy - Y0;
+            float acc = 0.f;
+#pragma unroll
+            for (int c = 0; c < kRegNm; ++c) acc = fmaf(cf[c], proto_f32(S.proto[c][sy][sx]), acc);
+            v = sigmoidf_ref(acc);
+          }
+          __stcg(dstp + (yy - k.py0) * kPatchPitch, v);
+        }
+      }
+      // this piece is in L2; the warp that completes the detection's patch upsamples it
+      __threadfence();
+      __syncwarp();
+      const int npieces = ((k.px1 - 1) / kRegBoxX - k.px0 / kRegBoxX + 1) * ((k.py1 - 1) / kRegBoxY - k.py0 / kRegBoxY + 1);
+      int last = 0;
+      if (lane == 0) last = (atomicAdd(&done[slot], 1) == npieces - 1) ? 1 : 0;
+      last = __shfl_sync(0xffffffffu, last, 0);
+      if (last) {
+        __threadfence();
+        const int4 wdw = reinterpret_cast<const int4*>(geom4)[slot];
+        const long long off = offsets[slot];
+        const long long words = (long long)((wdw.z + 31) >> 5) * wdw.w;
+        if (off + words > capacity_words) {
+          if (lane == 0) atomicOr(status, HDY_STATUS_OVERFLOW);
+        } else {
+          upsample_pack_warp(pbase, k, wdw, off, bits, mh, mw, ih, iw, S.col[warp], S.rows[warp], lane);
+        }
+      }
+      e = en;
+    }
+    __syncthreads();  // every warp is done with the region buffer (and with S.item / S.next_piece)
+  }
+}
+
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
                                   const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
                                   CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
@@ -482,6 +776,48 @@ int launch_process_mask_regions(const void* protos, int proto_dtype, const float
     return HDY_ERR_CUDA;
   }
   const float4* b4 = reinterpret_cast<const float4*>(boxes);
+  // bit-packed + upsampled (the throughput form): ONE persistent kernel does both phases (HDY_MASK_PATH=2phase keeps
+  // the two-kernel form for A/B runs)
+  static const bool two_phase = [] {
+    const char* v = getenv("HDY_MASK_PATH");
+    return v && v[0] == '2';
+  }();
+  if (out_dense == nullptr && upsample && geom && !two_phase) {
+    static int sm_count = 0;
+    if (!sm_count) {
+      int dev = 0;
+      cudaGetDevice(&dev);
+      cudaDeviceGetAttribute(&sm_count, cudaDevAttrMultiProcessorCount, dev);
+      if (sm_count <= 0) sm_count = 148;
+    }
+    e = cudaMemsetAsync(W.work_counter, 0, 4, stream);
+    const size_t smem = half ? sizeof(FuSmem<__half>) : sizeof(FuSmem<float>);
+    if (e == cudaSuccess)
+      e = half ? cudaFuncSetAttribute(mask_fused_kernel<__half>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)
+               : cudaFuncSetAttribute(mask_fused_kernel<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) {
+      set_error("process_mask(fused) setup: %s", cudaGetErrorString(e));
+      return HDY_ERR_CUDA;
+    }
+    proto_bin_fused_kernel<<<(unsigned)((slots + 255) / 256), 256, 0, stream>>>(
+        b4, counts, slots, max_det, mh, mw, rxn, ryn, rx, ry, geom, W.regions, W.done, W.large_count, W.large_list);
+    const long long n_items = (long long)bs * rxn * ryn;
+    const unsigned grid = (unsigned)(n_items < 2ll * sm_count ? n_items : 2ll * sm_count);   // two CTAs per SM
+    if (half)
+      mask_fused_kernel<__half><<<grid, kFuThreads, smem, stream>>>(
+          map, coef, b4, max_det, mh, mw, ih, iw, rxn, ryn, n_items, rx, ry, W.patches, W.regions, W.done,
+          W.work_counter, geom, offsets, bits, capacity_words, status);
+    else
+      mask_fused_kernel<float><<<grid, kFuThreads, smem, stream>>>(
+          map, coef, b4, max_det, mh, mw, ih, iw, rxn, ryn, n_items, rx, ry, W.patches, W.regions, W.done,
+          W.work_counter, geom, offsets, bits, capacity_words, status);
+    pm_clear_listed_kernel<<<148, 256, 0, stream>>>(geom, offsets, bits, capacity_words, W.large_list, W.large_count);
+    int rcf = check_launch("hdy_process_mask(fused)");
+    if (rcf) return rcf;
+    return launch_process_mask_listed(protos, proto_dtype, coef, boxes, counts, max_det, nm, mh, mw, ih, iw, upsample,
+                                      rx, ry, nullptr, offsets, bits, capacity_words, status, W.large_list,
+                                      W.large_count, stream);
+  }
   proto_bin_kernel<<<(unsigned)((slots + 255) / 256), 256, 0, stream>>>(b4, counts, slots, max_det, mh, mw, rxn, ryn, rx,
                                                                         ry, geom, W.regions);
   if (half)
