@@ -178,6 +178,9 @@ def _cpu_tile_pass(dets, second, wl, masks, tile_px, device=None):
     nc = wl["nc"]
     preds = port.compute_proposals(dets, synth.ANCHORS_3, synth.STRIDES_3)
     cat = port.concat_levels(preds)
+    if masks == "proto":    # mask coefficients travel raw (no sigmoid), as in the device path
+        raw = torch.cat([d.reshape(d.shape[0], -1, d.shape[-1]) for d in dets], 1)
+        cat[..., 5 + nc:5 + nc + NM] = raw[..., 5 + nc:5 + nc + NM]
     res = port.nms_per_image(cat, nc, wl["conf"], wl["iou"], wl["max_det"])
     out = []
     for i, r in enumerate(res):

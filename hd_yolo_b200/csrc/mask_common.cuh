@@ -90,6 +90,9 @@ __device__ __forceinline__ PMGeom pm_geometry(const float4 b, int mh, int mw, in
   g.px1 = ceil_to_int_clamped(g.x2d, 0, mw);
   g.py0 = ceil_to_int_clamped(g.y1d, 0, mh);
   g.py1 = ceil_to_int_clamped(g.y2d, 0, mh);
+  // a NaN coordinate fails every crop comparison of the reference (r >= x1 ...): the mask is empty
+  const bool nan = !(g.x1d == g.x1d) || !(g.x2d == g.x2d) || !(g.y1d == g.y1d) || !(g.y2d == g.y2d);
+  if (nan) g.px1 = g.px0, g.py1 = g.py0;
   if (g.px1 <= g.px0 || g.py1 <= g.py0) {
     g.x0 = g.y0 = g.w = g.h = 0;
     return g;

@@ -26,6 +26,9 @@
 #include <cuda.h>  // CUtensorMap types only; the encoder is fetched through cudaGetDriverEntryPoint
 #include "mask_common.cuh"
 
+#ifndef HDY_MASK_DEFAULT_PATH
+#define HDY_MASK_DEFAULT_PATH 1  // 1: two kernels (regions -> patches, upsample_pack_v2); 2: fused persistent kernel
+#endif
 #ifndef HDY_REG_BOX_X
 #define HDY_REG_BOX_X 24
 #define HDY_REG_BOX_Y 24
@@ -67,12 +70,13 @@ struct PmWorkspace {
   float* patches;
   RegionList* regions;
   int32_t* done;          // per slot: pieces of the patch written so far (fused kernel)
+  int4* kr;               // per slot: kept proto range (px0, py0, px1, py1), written by the binning kernel
 };
 static inline size_t align256(size_t v) { return (v + 255) & ~(size_t)255; }
 size_t process_mask_workspace_bytes(long long bs, long long max_det) {
   const long long slots = bs * max_det;
-  return 256 + 2 * align256((size_t)slots * 4) + (size_t)slots * kPatchPitch * kPatchPitch * 4 +
-         (size_t)bs * kMaxRegionsPerTile * sizeof(RegionList);
+  return 256 + 2 * align256((size_t)slots * 4) + align256((size_t)slots * 16) +
+         (size_t)slots * kPatchPitch * kPatchPitch * 4 + (size_t)bs * kMaxRegionsPerTile * sizeof(RegionList);
 }
 static PmWorkspace pm_workspace(void* base, long long slots) {
   PmWorkspace w;
@@ -84,6 +88,8 @@ static PmWorkspace pm_workspace(void* base, long long slots) {
   p += align256((size_t)slots * 4);
   w.done = reinterpret_cast<int32_t*>(p);
   p += align256((size_t)slots * 4);
+  w.kr = reinterpret_cast<int4*>(p);
+  p += align256((size_t)slots * 16);
   w.patches = reinterpret_cast<float*>(p);
   p += (size_t)slots * kPatchPitch * kPatchPitch * 4;
   w.regions = reinterpret_cast<RegionList*>(p);
@@ -113,8 +119,17 @@ __device__ __forceinline__ KeptRange kept_range(const float4 b, float rx, float 
   k.px1 = ceil_to_int_clamped(k.x2d, 0, mw);
   k.py0 = ceil_to_int_clamped(k.y1d, 0, mh);
   k.py1 = ceil_to_int_clamped(k.y2d, 0, mh);
+  // a NaN coordinate fails every crop comparison of the reference: nothing is kept.  For finite coordinates the crop
+  // test x1d <= col < x2d over integer columns IS col in [px0, px1) (px = ceil, clamped), so the kernels below walk the
+  // integer range and never compare against the floats again.
+  if (!(k.x1d == k.x1d) || !(k.x2d == k.x2d) || !(k.y1d == k.y1d) || !(k.y2d == k.y2d)) k.px1 = k.px0, k.py1 = k.py0;
   return k;
 }
+
+// floor(v / pw) for 0 <= v < 64 and 1 <= pw <= 16 as (v * ceil(2^16 / pw)) >> 16 (exact while v * pw < 2^16): the
+// piece loops split the 32 lanes into floor(32 / pw) rows of pw pixels, and an integer division costs ~20 instructions
+__constant__ int c_inv16[17] = {0,     65536, 32768, 21846, 16384, 13108, 10923, 9363, 8192,
+                                7282,  6554,  5958,  5462,  5042,  4682,  4370,  4096};
 
 // ------------------------------------------------------------------------------------------------ phase 0
 // One thread per detection: append it to the list of every region its kept range touches (1-4 for a nucleus), so that
@@ -123,14 +138,17 @@ __global__ void __launch_bounds__(256) proto_bin_kernel(const float4* __restrict
                                                         const int32_t* __restrict__ counts, long long n_slots,
                                                         int max_det, int mh, int mw, int rxn, int ryn, float rx,
                                                         float ry, const int32_t* __restrict__ geom4,
-                                                        RegionList* __restrict__ regions) {
+                                                        RegionList* __restrict__ regions, int4* __restrict__ kr) {
   const long long slot = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (slot >= n_slots) return;
   const int tile = (int)(slot / max_det), d = (int)(slot - (long long)tile * max_det);
-  if (d >= counts[tile]) return;
-  // packed form: a slot without an output window (empty, or not KEPT by the slide-level merge) needs no patch
-  if (geom4 && (geom4[4 * slot + 2] <= 0 || geom4[4 * slot + 3] <= 0)) return;
-  const KeptRange k = kept_range(boxes[slot], rx, ry, mw, mh);
+  // a slot beyond counts, or (packed form) without an output window -- empty, or not KEPT by the slide-level merge --
+  // needs no patch: its kept range is recorded as empty
+  const bool live = d < counts[tile] && !(geom4 && (geom4[4 * slot + 2] <= 0 || geom4[4 * slot + 3] <= 0));
+  KeptRange k;
+  k.px0 = k.py0 = k.px1 = k.py1 = 0;
+  if (live) k = kept_range(boxes[slot], rx, ry, mw, mh);
+  kr[slot] = make_int4(k.px0, k.py0, k.px1, k.py1);
   if (k.px1 <= k.px0 || k.py1 <= k.py0) return;
   if (k.px1 - k.px0 > kPatchPitch || k.py1 - k.py0 > kPatchPitch) return;  // per-detection kernel
   const int rx0 = k.px0 / kRegBoxX, rx1 = (k.px1 - 1) / kRegBoxX;
@@ -144,11 +162,42 @@ __global__ void __launch_bounds__(256) proto_bin_kernel(const float4* __restrict
 }
 
 // ------------------------------------------------------------------------------------------------ phase 1
+// One piece: the kept pixels of a detection inside one region, contracted against the region's 32 prototype planes in
+// shared memory.  Lanes cover floor(32 / pw) rows of pw pixels at a time.  emit(x - px0, y - py0, value).
+template <typename E, typename Emit>
+__device__ __forceinline__ void contract_piece(const E (*proto)[kRegBoxY][kRegBoxX], const float* __restrict__ coef_smem,
+                                               const int4 kr, int X0, int Y0, int lane, Emit emit) {
+  float cf[kRegNm];
+#pragma unroll
+  for (int c = 0; c < kRegNm; c += 4) {
+    const float4 v = *reinterpret_cast<const float4*>(coef_smem + c);
+    cf[c] = v.x;
+    cf[c + 1] = v.y;
+    cf[c + 2] = v.z;
+    cf[c + 3] = v.w;
+  }
+  const int qx0 = max(kr.x, X0), qx1 = min(kr.z, X0 + kRegBoxX);
+  const int qy0 = max(kr.y, Y0), qy1 = min(kr.w, Y0 + kRegBoxY);
+  const int pw = qx1 - qx0;  // 1..16
+  const int inv = c_inv16[pw];
+  const int rows_per = (32 * inv) >> 16;
+  const int ly = (lane * inv) >> 16, lx = lane - ly * pw;
+  if (ly >= rows_per) return;
+  const int xx = qx0 + lx, sx = xx - X0;
+  for (int yy = qy0 + ly; yy < qy1; yy += rows_per) {
+    const int sy = yy - Y0;
+    float acc = 0.f;
+#pragma unroll
+    for (int c = 0; c < kRegNm; ++c) acc = fmaf(cf[c], proto_f32(proto[c][sy][sx]), acc);
+    emit(xx - kr.x, yy - kr.y, sigmoidf_ref(acc));
+  }
+}
+
 template <typename E>
 __global__ void __launch_bounds__(kRegThreads, 3) proto_patch_kernel(
-    const __grid_constant__ CUtensorMap tmap, const float* __restrict__ coef, const float4* __restrict__ boxes,
-    const int32_t* __restrict__ counts, int max_det, int mh, int mw, int rxn, int ryn, float rx, float ry,
-    float* __restrict__ patches, const RegionList* __restrict__ regions) {
+    const __grid_constant__ CUtensorMap tmap, const float* __restrict__ coef, const int4* __restrict__ krs,
+    const int32_t* __restrict__ counts, int max_det, int rxn, int ryn, float* __restrict__ patches,
+    const RegionList* __restrict__ regions) {
   extern __shared__ __align__(128) unsigned char smem_raw[];
   RegSmemT<E>& S = *reinterpret_cast<RegSmemT<E>*>(smem_raw);
   const int t = threadIdx.x, lane = t & 31, warp = t >> 5;
@@ -179,26 +228,28 @@ __global__ void __launch_bounds__(kRegThreads, 3) proto_patch_kernel(
       for (int i = base + t; i < lim; i += kRegThreads) S.list[i - base] = RL.det[i];
       if (t == 0) S.nlist = lim - base;
     } else {
-      // overfull list (more than kRegCap detections in one region): scan the tile
+      // overfull list (more than kRegCap detections in one region): scan the tile (slots the binning pass skipped --
+      // beyond counts, empty, not KEPT -- carry no kept range of this launch: they are filtered by counts / geometry
+      // in the binning pass only, so the scan re-checks the range itself)
       for (int d = base + t; d < lim; d += kRegThreads) {
-        const KeptRange k = kept_range(boxes[(size_t)tile * max_det + d], rx, ry, mw, mh);
-        if (k.px1 <= k.px0 || k.py1 <= k.py0) continue;
-        if (k.px1 - k.px0 > kPatchPitch || k.py1 - k.py0 > kPatchPitch) continue;  // per-detection kernel
-        if (k.px1 <= X0 || k.px0 >= X0 + kRegBoxX || k.py1 <= Y0 || k.py0 >= Y0 + kRegBoxY) continue;
+        const int4 k = krs[(size_t)tile * max_det + d];
+        if (k.z <= k.x || k.w <= k.y) continue;
+        if (k.z - k.x > kPatchPitch || k.w - k.y > kPatchPitch) continue;  // per-detection kernel
+        if (k.z <= X0 || k.x >= X0 + kRegBoxX || k.w <= Y0 || k.y >= Y0 + kRegBoxY) continue;
         S.list[atomicAdd(&S.nlist, 1)] = (uint16_t)(d - base);
       }
     }
     __syncthreads();
     const int nl = S.nlist;
-    // software pipeline over this warp's pieces: the box and the coefficients of the NEXT piece are requested before
-    // the current one is computed (and those of the first piece before waiting for the TMA load)
+    // software pipeline over this warp's pieces: the kept range and the coefficients of the NEXT piece are requested
+    // before the current one is computed (and those of the first piece before waiting for the TMA load)
     int e = warp;
     size_t nslot = 0;
-    float4 nbox = make_float4(0.f, 0.f, 0.f, 0.f);
+    int4 nkr = make_int4(0, 0, 0, 0);
     float ncoef = 0.f;
     auto fetch = [&](int ee) {
       nslot = (size_t)tile * max_det + (use_list ? 0 : base) + S.list[ee];
-      nbox = boxes[nslot];
+      nkr = krs[nslot];
       ncoef = coef[nslot * kRegNm + lane];
     };
     if (e < nl) fetch(e);
@@ -209,41 +260,14 @@ __global__ void __launch_bounds__(kRegThreads, 3) proto_patch_kernel(
     }
     for (; e < nl; e += kRegWarps) {
       const size_t slot = nslot;
-      const KeptRange k = kept_range(nbox, rx, ry, mw, mh);
+      const int4 k = nkr;
       __syncwarp();
       S.coef[warp][lane] = ncoef;
       __syncwarp();
       if (e + kRegWarps < nl) fetch(e + kRegWarps);
-      float cf[kRegNm];
-#pragma unroll
-      for (int c = 0; c < kRegNm; c += 4) {
-        const float4 v = *reinterpret_cast<const float4*>(&S.coef[warp][c]);
-        cf[c] = v.x;
-        cf[c + 1] = v.y;
-        cf[c + 2] = v.z;
-        cf[c + 3] = v.w;
-      }
-      // the piece: kept pixels inside this region; lanes cover floor(32 / pw) rows at a time
-      const int qx0 = max(k.px0, X0), qx1 = min(k.px1, X0 + kRegBoxX);
-      const int qy0 = max(k.py0, Y0), qy1 = min(k.py1, Y0 + kRegBoxY);
-      const int pw = qx1 - qx0;  // 1..16
-      const int rows_per = 32 / pw;
-      const int ly = lane / pw, lx = lane - ly * pw;
-      if (ly >= rows_per) continue;  // lane-level: the rest of the loop body has no warp-wide operation
-      const int xx = qx0 + lx, sx = xx - X0;
-      const bool x_in = (float)xx >= k.x1d && (float)xx < k.x2d;
-      float* dst = patches + slot * (kPatchPitch * kPatchPitch) + (xx - k.px0);
-      for (int yy = qy0 + ly; yy < qy1; yy += rows_per) {
-        float v = 0.f;
-        if (x_in && (float)yy >= k.y1d && (float)yy < k.y2d) {
-          const int sy = yy - Y0;
-          float acc = 0.f;
-#pragma unroll
-          for (int c = 0; c < kRegNm; ++c) acc = fmaf(cf[c], proto_f32(S.proto[c][sy][sx]), acc);
-          v = sigmoidf_ref(acc);
-        }
-        dst[(yy - k.py0) * kPatchPitch] = v;
-      }
+      float* dst = patches + slot * (kPatchPitch * kPatchPitch);
+      contract_piece<E>(S.proto, S.coef[warp], k, X0, Y0, lane,
+                        [&](int px, int py, float v) { dst[py * kPatchPitch + px] = v; });
     }
   }
   if (!loaded) {  // never leave with the bulk copy still in flight
@@ -431,43 +455,85 @@ __global__ void __launch_bounds__(kUpWarps * 32) mask_upsample_pack_kernel(
   }
 }
 
-// ------------------------------------------------------------------------------------------------ fused path
-// Phases 1 and 2 in ONE persistent kernel (bit-packed + upsampled masks, the throughput form).  The two phases want
-// different resources -- phase 1 waits on HBM (TMA regions), phase 2 on issue slots (~500 instructions per detection)
-// -- and as two kernels they ran back to back: 1.13 ms per 148-tile batch of the slide, 5.5x the HBM floor.  Here
-//   * two CTAs per SM (8 warps, one 72 KB region buffer each) walk the (tile, region) items handed out by a global
-//     counter: while one CTA waits for its region (TMA) and for the dependent loads of its first pieces, the other
-//     computes; the ticket of the next item is drawn at the start of an item and looked at only at its end;
-//   * a warp takes the next piece of the item (dynamic, shared-memory counter), contracts it and writes it into the
-//     detection's patch in the L2-resident workspace, then bumps the detection's `done` counter; the warp that writes
-//     the LAST piece of a detection upsamples and packs it at once (patch read back through L2), so the issue-bound
-//     half of the work fills the cycles the other warps of the SM spend waiting for their region;
-//   * the upsample keeps the ringed patch rows in registers (one predicated, coalesced load per source row) and takes
-//     the two x taps by shuffle: no patch staging, no ring building, no per-detection geometry recomputation.
-// Detections whose kept range exceeds 16 x 16 proto pixels, or that met an overfull region list, are listed by the
-// binning kernel and go to the per-detection kernel of mask.cu (their words are cleared first: it ORs bits in).
+// ------------------------------------------------------------------------------------------------ packed + upsampled
+// The throughput form (bit planes of the upsampled masks) has kernels of its own.  What they share:
+//   * the binning kernel records every slot's kept proto range (so nobody recomputes it from the box), zeroes the
+//     per-slot piece counters and lists the detections that do not fit the patch path (kept range over 16 x 16 proto
+//     pixels, or an overfull region list): those go to the per-detection kernel of mask.cu afterwards;
+//   * upsample_pack_v2: one warp per detection.  The sigmoid patch sits in shared memory with a ring of zeros (the
+//     crop).  x pass with lane = output column (two taps per source row), results stored TRANSPOSED; y pass with lane =
+//     output ROW: every lane walks the columns of its row, blends two of the stored values per pixel and sets the bit
+//     in a register -- 7 instructions per column for 32 rows at once, no ballots, no row tables, one coalesced store
+//     of the row words.  (The first version ran lane = column with a ballot per row: ~13 instructions per row and a
+//     special case for narrow tail words; 1 000 warp instructions per detection, 70 % of the issue slots.)
 constexpr int kFuWarps = 8;
 constexpr int kFuThreads = kFuWarps * 32;
-constexpr int kFuRows = kPatchPitch + 2;  // ringed source rows
+constexpr int kFuRows = kPatchPitch + 2;   // ringed source rows / columns
+constexpr int kColPitch = kFuRows + 1;     // odd: lanes = columns write, lanes = rows read, both conflict-free
 
-template <typename E>
-struct FuSmem {
-  E proto[kRegNm][kRegBoxY][kRegBoxX];  // TMA destination
-  float coef[kFuWarps][kRegNm];
-  float col[kFuWarps][kFuRows][32];  // x-interpolated values of the lanes' columns, per source row
-  RowTab rows[kFuWarps][kRowChunk];
-  uint64_t full;
-  int item;
-  int next_piece;
+struct UpWarpSmem {
+  float patch[kFuRows * kFuRows];   // ringed sigmoid patch, 81 float4
+  float colT[32 * kColPitch];       // x-pass results of the current 32 output columns: [column][source row]
 };
 
-// binning for the fused path: region lists as proto_bin_kernel, plus the per-slot piece counters (zeroed here) and
-// the list of detections the fused kernel does not take
+__device__ __forceinline__ void up_zero_patch(float* P, int lane) {
+  float4* p4 = reinterpret_cast<float4*>(P);
+  for (int i = lane; i < kFuRows * kFuRows / 4; i += 32) p4[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+}
+
+// ATen bilinear (align_corners=False), operation by operation, + threshold + pack of one detection.
+// P: ringed patch (element (y, x) of the kept range at [(y + 1) * 18 + x + 1], zeros elsewhere).
+__device__ __forceinline__ void upsample_pack_v2(const float* __restrict__ P, float* __restrict__ colT, const int4 kr,
+                                                 const int4 wdw, long long off, uint32_t* __restrict__ bits, int mh,
+                                                 int mw, int ih, int iw, int lane) {
+  const int pw = kr.z - kr.x, ph = kr.w - kr.y;
+  const int gx0 = wdw.x, gy0 = wdw.y, gw = wdw.z, gh = wdw.w;
+  const int wpr = (gw + 31) >> 5;
+  const int src_rows = ph + 2;
+  const float sxs = (float)mw / (float)iw, sys = (float)mh / (float)ih;  // ATen: scale = in / out (fp32)
+  for (int w = 0; w < wpr; ++w) {
+    const int vw = min(32, gw - (w << 5));  // valid columns of this word
+    // x pass (lane = column): top / bot of ATen's formula for every source row
+    const int c = (w << 5) + lane;
+    const Lerp X = lerp_coord(gx0 + (c < gw ? c : 0), sxs, mw);
+    // taps outside [px0 - 1, px1] contribute nothing (cropped): clamp them onto the ring of zeros
+    const int xi0 = min(max(X.i0 - kr.x + 1, 0), pw + 1), xi1 = min(max(X.i1 - kr.x + 1, 0), pw + 1);
+    __syncwarp();  // the previous word's y pass is done with colT
+    float* ct = colT + lane * kColPitch;
+#pragma unroll 2
+    for (int s = 0; s < src_rows; ++s)
+      ct[s] = __fadd_rn(__fmul_rn(X.l0, P[s * kFuRows + xi0]), __fmul_rn(X.l1, P[s * kFuRows + xi1]));
+    __syncwarp();
+    // y pass (lane = row)
+    for (int r0 = 0; r0 < gh; r0 += 32) {
+      const int r = r0 + lane;
+      const bool act = r < gh;
+      const Lerp Y = lerp_coord(gy0 + (act ? r : 0), sys, mh);
+      const float* c0 = colT + min(max(Y.i0 - kr.y + 1, 0), ph + 1);
+      const float* c1 = colT + min(max(Y.i1 - kr.y + 1, 0), ph + 1);
+      uint32_t word = 0u;
+#pragma unroll
+      for (int xg = 0; xg < 32; xg += 4) {
+        if (xg >= vw) break;  // warp-uniform
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          const int x = xg + j;
+          const float v = __fadd_rn(__fmul_rn(Y.l0, c0[x * kColPitch]), __fmul_rn(Y.l1, c1[x * kColPitch]));
+          if (v > 0.5f) word |= 1u << x;
+        }
+      }
+      if (vw < 32) word &= (1u << vw) - 1u;  // columns past the window were computed from clamped taps
+      if (act) bits[off + (long long)r * wpr + w] = word;
+    }
+  }
+}
+
+// binning for the packed + upsampled kernels (see above)
 __global__ void __launch_bounds__(256) proto_bin_fused_kernel(const float4* __restrict__ boxes,
                                                               const int32_t* __restrict__ counts, long long n_slots,
                                                               int max_det, int mh, int mw, int rxn, int ryn, float rx,
                                                               float ry, const int32_t* __restrict__ geom4,
-                                                              RegionList* __restrict__ regions,
+                                                              RegionList* __restrict__ regions, int4* __restrict__ kr,
                                                               int32_t* __restrict__ done,
                                                               int32_t* __restrict__ large_count,
                                                               int32_t* __restrict__ large_list) {
@@ -475,25 +541,30 @@ __global__ void __launch_bounds__(256) proto_bin_fused_kernel(const float4* __re
   if (slot >= n_slots) return;
   done[slot] = 0;
   const int tile = (int)(slot / max_det), d = (int)(slot - (long long)tile * max_det);
-  if (d >= counts[tile]) return;
-  if (geom4[4 * slot + 2] <= 0 || geom4[4 * slot + 3] <= 0) return;  // empty window, or not KEPT (slide form)
-  const KeptRange k = kept_range(boxes[slot], rx, ry, mw, mh);
-  if (k.px1 <= k.px0 || k.py1 <= k.py0) return;
-  bool leave = k.px1 - k.px0 > kPatchPitch || k.py1 - k.py0 > kPatchPitch;
-  if (!leave) {
-    const int rx0 = k.px0 / kRegBoxX, rx1 = (k.px1 - 1) / kRegBoxX;
-    const int ry0 = k.py0 / kRegBoxY, ry1 = (k.py1 - 1) / kRegBoxY;
-    for (int ryy = ry0; ryy <= ry1; ++ryy)
-      for (int rxx = rx0; rxx <= rx1; ++rxx) {
-        RegionList& R = regions[(size_t)tile * (rxn * ryn) + ryy * rxn + rxx];
-        const int pos = atomicAdd(&R.count, 1);
-        if (pos < kRegCap)
-          R.det[pos] = (uint16_t)d;
-        else
-          leave = true;  // overfull region: its piece is never written, so the patch never completes -- hand it over
-      }
+  // empty window, not KEPT (slide form) or beyond counts: no patch, an empty kept range
+  const bool live = d < counts[tile] && geom4[4 * slot + 2] > 0 && geom4[4 * slot + 3] > 0;
+  KeptRange k;
+  k.px0 = k.py0 = k.px1 = k.py1 = 0;
+  if (live) k = kept_range(boxes[slot], rx, ry, mw, mh);
+  bool leave = false;
+  if (k.px1 > k.px0 && k.py1 > k.py0) {
+    leave = k.px1 - k.px0 > kPatchPitch || k.py1 - k.py0 > kPatchPitch;
+    if (!leave) {
+      const int rx0 = k.px0 / kRegBoxX, rx1 = (k.px1 - 1) / kRegBoxX;
+      const int ry0 = k.py0 / kRegBoxY, ry1 = (k.py1 - 1) / kRegBoxY;
+      for (int ryy = ry0; ryy <= ry1; ++ryy)
+        for (int rxx = rx0; rxx <= rx1; ++rxx) {
+          RegionList& R = regions[(size_t)tile * (rxn * ryn) + ryy * rxn + rxx];
+          const int pos = atomicAdd(&R.count, 1);
+          if (pos < kRegCap)
+            R.det[pos] = (uint16_t)d;
+          else
+            leave = true;  // overfull region: hand the detection over (its other pieces are skipped: empty range)
+        }
+    }
+    if (leave) large_list[atomicAdd(large_count, 1)] = (int32_t)slot;
   }
-  if (leave) large_list[atomicAdd(large_count, 1)] = (int32_t)slot;
+  kr[slot] = leave ? make_int4(0, 0, 0, 0) : make_int4(k.px0, k.py0, k.px1, k.py1);
 }
 
 // the words of the listed detections are cleared: the per-detection kernel ORs its bits in
@@ -510,97 +581,66 @@ __global__ void pm_clear_listed_kernel(const int32_t* __restrict__ geom4, const 
   }
 }
 
-// One warp: upsample (ATen bilinear, align_corners=False, operation by operation) + threshold + pack of one detection
-// whose sigmoid patch (<= 16 x 16, pitch 16) is complete in the workspace.
-__device__ __forceinline__ void upsample_pack_warp(const float* __restrict__ patch, const KeptRange& k, const int4 wdw,
-                                                   long long off, uint32_t* __restrict__ bits, int mh, int mw, int ih,
-                                                   int iw, float (*col)[32], RowTab* rowtab, int lane) {
-  const int pw = k.px1 - k.px0, ph = k.py1 - k.py0;
-  const int gx0 = wdw.x, gy0 = wdw.y, gw = wdw.z, gh = wdw.w;
-  const int wpr = (gw + 31) >> 5;
-  const int src_rows = ph + 2;
-  // ringed patch: lane j holds ring column j of every ring row s (zero outside the kept pixels: the crop)
-  float prow[kFuRows];
-  const bool lane_in = lane >= 1 && lane <= pw;
-#pragma unroll
-  for (int s = 0; s < kFuRows; ++s)
-    prow[s] = (lane_in && s >= 1 && s <= ph) ? __ldcg(patch + (s - 1) * kPatchPitch + lane - 1) : 0.f;
-  const float sxs = (float)mw / (float)iw, sys = (float)mh / (float)ih;  // ATen: scale = in / out (fp32)
-  for (int r0 = 0; r0 < gh; r0 += kRowChunk) {
-    const int nr = min(kRowChunk, gh - r0);
-    __syncwarp();
-    for (int r = lane; r < nr; r += 32) {
-      const Lerp Y = lerp_coord(gy0 + r0 + r, sys, mh);
-      RowTab T;
-      // taps outside [py0 - 1, py1] contribute nothing (cropped): clamp them onto the ring of zeros
-      T.i0 = min(max(Y.i0 - k.py0 + 1, 0), ph + 1);
-      T.i1 = min(max(Y.i1 - k.py0 + 1, 0), ph + 1);
-      T.l0 = Y.l0;
-      T.l1 = Y.l1;
-      rowtab[r] = T;
-    }
-    for (int w = 0; w < wpr; ++w) {
-      const int vw = min(32, gw - (w << 5));  // valid columns of this word
-      const bool narrow = vw <= 16;
-      // x pass (lane = column of the word): top/bot of ATen's formula for every source row, taps by shuffle
-      const int c = (w << 5) + lane;
-      const bool valid = c < gw;
-      const Lerp X = lerp_coord(gx0 + (valid ? c : 0), sxs, mw);
-      const int xi0 = min(max(X.i0 - k.px0 + 1, 0), pw + 1), xi1 = min(max(X.i1 - k.px0 + 1, 0), pw + 1);
-      __syncwarp();
-#pragma unroll
-      for (int s = 0; s < kFuRows; ++s) {
-        if (s < src_rows) {  // warp-uniform
-          const float a = __shfl_sync(0xffffffffu, prow[s], xi0), b = __shfl_sync(0xffffffffu, prow[s], xi1);
-          col[s][lane] = __fadd_rn(__fmul_rn(X.l0, a), __fmul_rn(X.l1, b));
-        }
-      }
-      __syncwarp();
-      uint32_t* dst = bits + off + (long long)r0 * wpr + w;
-      if (narrow) {
-        // narrow word (the tail of a 36-px window is 4 columns): lanes cover floor(32 / vw) output rows at a time
-        const int rows_per = 32 / vw;
-        const int lr = lane / vw, lc = lane - lr * vw;
-        const bool active = lr < rows_per;
-        const unsigned row_mask = (1u << vw) - 1u;
-        for (int rb = 0; rb < nr; rb += rows_per) {
-          const int r = rb + lr;
-          bool bit = false;
-          if (active && r < nr) {
-            const float4 rt = *reinterpret_cast<const float4*>(&rowtab[r]);
-            const float v = __fadd_rn(__fmul_rn(rt.z, col[__float_as_int(rt.x)][lc]),
-                                      __fmul_rn(rt.w, col[__float_as_int(rt.y)][lc]));
-            bit = v > 0.5f;
-          }
-          const unsigned m = __ballot_sync(0xffffffffu, bit);
-          if (active && lc == 0 && r < nr) dst[(long long)r * wpr] = (m >> (lr * vw)) & row_mask;
-        }
-        continue;
-      }
-      unsigned myword = 0;
-#pragma unroll 4
-      for (int r = 0; r < nr; ++r) {
-        const float4 rt = *reinterpret_cast<const float4*>(&rowtab[r]);
-        const float v = __fadd_rn(__fmul_rn(rt.z, col[__float_as_int(rt.x)][lane]),
-                                  __fmul_rn(rt.w, col[__float_as_int(rt.y)][lane]));
-        const unsigned word = __ballot_sync(0xffffffffu, valid && v > 0.5f);
-        if ((r & 31) == lane) myword = word;
-        if ((r & 31) == 31 || r == nr - 1) {  // lanes store the words of up to 32 rows at once
-          const int rr = (r & ~31) + lane;
-          if (rr <= r) dst[(long long)rr * wpr] = myword;
-        }
-      }
-    }
+// phase 2 of the two-kernel form: one warp per detection, patch from the workspace
+__global__ void __launch_bounds__(kFuThreads) mask_upsample_pack2_kernel(
+    const float* __restrict__ patches, const int4* __restrict__ krs, const int32_t* __restrict__ geom4,
+    const int64_t* __restrict__ offsets, long long n_slots, int mh, int mw, int ih, int iw, uint32_t* __restrict__ bits,
+    long long capacity_words, int32_t* __restrict__ status) {
+  __shared__ __align__(16) UpWarpSmem S[kFuWarps];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const long long slot = (long long)blockIdx.x * kFuWarps + warp;
+  if (slot >= n_slots) return;
+  const int4 kr = krs[slot];
+  const int pw = kr.z - kr.x, ph = kr.w - kr.y;
+  if (pw <= 0 || ph <= 0) return;  // dead / empty / handed to the per-detection kernel
+  const int4 wdw = reinterpret_cast<const int4*>(geom4)[slot];
+  const long long off = offsets[slot];
+  if (off + (long long)((wdw.z + 31) >> 5) * wdw.w > capacity_words) {
+    if (lane == 0) atomicOr(status, HDY_STATUS_OVERFLOW);
+    return;
   }
+  float* P = S[warp].patch;
+  up_zero_patch(P, lane);
+  __syncwarp();
+  {  // interior: rows of 16 floats, two rows per step (entries beyond pw are stale: not copied)
+    const float* src = patches + slot * (kPatchPitch * kPatchPitch);
+    const int x = lane & 15;
+    if (x < pw)
+      for (int y = lane >> 4; y < ph; y += 2) P[(y + 1) * kFuRows + x + 1] = src[y * kPatchPitch + x];
+  }
+  __syncwarp();
+  upsample_pack_v2(P, S[warp].colT, kr, wdw, off, bits, mh, mw, ih, iw, lane);
 }
+
+// ------------------------------------------------------------------------------------------------ fused path
+// Phases 1 and 2 in ONE persistent kernel.  The two phases want different resources -- phase 1 waits on HBM (TMA
+// regions), phase 2 on issue slots -- and as two kernels they run back to back.  Here
+//   * two CTAs per SM (8 warps, one 72 KB region buffer each) walk the (tile, region) items handed out by a global
+//     counter: while one CTA waits for its region (TMA) and for the dependent loads of its first pieces, the other
+//     computes; the ticket of the next item is drawn at the start of an item and looked at only at its end;
+//   * a warp takes the next piece of the item (dynamic, shared-memory counter) and contracts it.  A detection that
+//     lies inside ONE region (about half of them) goes straight from the contraction into the warp's shared-memory
+//     patch and is upsampled and packed on the spot: no workspace, no fence, no atomic.  A piece of a detection that
+//     straddles regions is written to the detection's patch in the L2-resident workspace and counted; the warp that
+//     writes the LAST piece fetches the patch back and upsamples it.  The issue-bound half of the work thus fills
+//     the cycles the other warps of the SM spend waiting for their region.
+template <typename E>
+struct FuSmem {
+  E proto[kRegNm][kRegBoxY][kRegBoxX];  // TMA destination
+  float coef[kFuWarps][kRegNm];
+  UpWarpSmem up[kFuWarps];
+  uint64_t full;
+  int item;
+  int next_piece;
+};
 
 template <typename E>
 __global__ void __launch_bounds__(kFuThreads, 2) mask_fused_kernel(
-    const __grid_constant__ CUtensorMap tmap, const float* __restrict__ coef, const float4* __restrict__ boxes,
-    int max_det, int mh, int mw, int ih, int iw, int rxn, int ryn, long long n_items, float rx, float ry,
-    float* __restrict__ patches, const RegionList* __restrict__ regions, int32_t* __restrict__ done,
-    int32_t* __restrict__ work_counter, const int32_t* __restrict__ geom4, const int64_t* __restrict__ offsets,
-    uint32_t* __restrict__ bits, long long capacity_words, int32_t* __restrict__ status) {
+    const __grid_constant__ CUtensorMap tmap, const float* __restrict__ coef, const int4* __restrict__ krs, int max_det,
+    int mh, int mw, int ih, int iw, int rxn, int ryn, long long n_items, float* __restrict__ patches,
+    const RegionList* __restrict__ regions, int32_t* __restrict__ done, int32_t* __restrict__ work_counter,
+    const int32_t* __restrict__ geom4, const int64_t* __restrict__ offsets, uint32_t* __restrict__ bits,
+    long long capacity_words, int32_t* __restrict__ status) {
   extern __shared__ __align__(128) unsigned char smem_raw[];
   FuSmem<E>& S = *reinterpret_cast<FuSmem<E>*>(smem_raw);
   const int t = threadIdx.x, lane = t & 31, warp = t >> 5;
@@ -612,6 +652,7 @@ __global__ void __launch_bounds__(kFuThreads, 2) mask_fused_kernel(
     ticket = (long long)atomicAdd(work_counter, 1);
   }
   uint32_t parity = 0u;
+  float* P = S.up[warp].patch;
   for (;;) {
     if (t == 0) {
       // resolve the ticket drawn an item ago (regions nobody reaches into are skipped: they load nothing)
@@ -635,16 +676,16 @@ __global__ void __launch_bounds__(kFuThreads, 2) mask_fused_kernel(
     const int X0 = RX * kRegBoxX, Y0 = RY * kRegBoxY;
     const RegionList& RL = regions[cur];
     const int nl = min(RL.count, kRegCap);
-    // first piece of this warp: its box and coefficient are requested before the wait for the region
+    // first piece of this warp: its kept range and coefficient are requested before the wait for the region
     int e = 0;
     if (lane == 0) e = atomicAdd(&S.next_piece, 1);
     e = __shfl_sync(0xffffffffu, e, 0);
     size_t nslot = 0;
-    float4 nbox = make_float4(0.f, 0.f, 0.f, 0.f);
+    int4 nkr = make_int4(0, 0, 0, 0);
     float ncoef = 0.f;
     auto fetch = [&](int ee) {
       nslot = (size_t)tile * max_det + RL.det[ee];
-      nbox = boxes[nslot];
+      nkr = krs[nslot];
       ncoef = coef[nslot * kRegNm + lane];
     };
     if (e < nl) fetch(e);
@@ -653,8 +694,7 @@ __global__ void __launch_bounds__(kFuThreads, 2) mask_fused_kernel(
     parity ^= 1u;
     while (e < nl) {
       const size_t slot = nslot;
-      const float4 box = nbox;
-      const KeptRange k = kept_range(box, rx, ry, mw, mh);
+      const int4 k = nkr;
       __syncwarp();
       S.coef[warp][lane] = ncoef;
       __syncwarp();
@@ -662,57 +702,47 @@ __global__ void __launch_bounds__(kFuThreads, 2) mask_fused_kernel(
       if (lane == 0) en = atomicAdd(&S.next_piece, 1);
       en = __shfl_sync(0xffffffffu, en, 0);
       if (en < nl) fetch(en);  // the next piece's loads fly while this one is computed
-      float cf[kRegNm];
-#pragma unroll
-      for (int c = 0; c < kRegNm; c += 4) {
-        const float4 v = *reinterpret_cast<const float4*>(&S.coef[warp][c]);
-        cf[c] = v.x;
-        cf[c + 1] = v.y;
-        cf[c + 2] = v.z;
-        cf[c + 3] = v.w;
-      }
-      // the piece: kept pixels inside this region; lanes cover floor(32 / pw) rows at a time
-      const int qx0 = max(k.px0, X0), qx1 = min(k.px1, X0 + kRegBoxX);
-      const int qy0 = max(k.py0, Y0), qy1 = min(k.py1, Y0 + kRegBoxY);
-      const int pw = qx1 - qx0;  // 1..16
-      const int rows_per = 32 / pw;
-      const int ly = lane / pw, lx = lane - ly * pw;
+      e = en;
+      if (k.z <= k.x) continue;  // handed to the per-detection kernel by the binning pass (overfull region)
+      const bool single = k.x >= X0 && k.z <= X0 + kRegBoxX && k.y >= Y0 && k.w <= Y0 + kRegBoxY;
+      bool upsample = single;
       float* pbase = patches + slot * (kPatchPitch * kPatchPitch);
-      if (ly < rows_per) {
-        const int xx = qx0 + lx, sx = xx - X0;
-        const bool x_in = (float)xx >= k.x1d && (float)xx < k.x2d;
-        float* dstp = pbase + (xx - k.px0);
-        for (int yy = qy0 + ly; yy < qy1; yy += rows_per) {
-          float v = 0.f;
-          if (x_in && (float)yy >= k.y1d && (float)yy < k.y2d) {
-            const int sy = yy - Y0;
-            float acc = 0.f;
-#pragma unroll
-            for (int c = 0; c < kRegNm; ++c) acc = fmaf(cf[c], proto_f32(S.proto[c][sy][sx]), acc);
-            v = sigmoidf_ref(acc);
-          }
-          __stcg(dstp + (yy - k.py0) * kPatchPitch, v);
+      if (single) {
+        // the whole kept range lies in this region: contraction -> shared-memory patch, nothing leaves the SM
+        up_zero_patch(P, lane);
+        __syncwarp();
+        contract_piece<E>(S.proto, S.coef[warp], k, X0, Y0, lane,
+                          [&](int px, int py, float v) { P[(py + 1) * kFuRows + px + 1] = v; });
+      } else {
+        contract_piece<E>(S.proto, S.coef[warp], k, X0, Y0, lane,
+                          [&](int px, int py, float v) { __stcg(pbase + py * kPatchPitch + px, v); });
+        // this piece is on its way to L2; the warp that completes the detection's patch upsamples it
+        const int npieces = ((k.z - 1) / kRegBoxX - k.x / kRegBoxX + 1) * ((k.w - 1) / kRegBoxY - k.y / kRegBoxY + 1);
+        asm volatile("fence.acq_rel.gpu;" ::: "memory");
+        __syncwarp();
+        int last = 0;
+        if (lane == 0) last = (atomicAdd(&done[slot], 1) == npieces - 1) ? 1 : 0;
+        last = __shfl_sync(0xffffffffu, last, 0);
+        if (last) {
+          asm volatile("fence.acq_rel.gpu;" ::: "memory");
+          up_zero_patch(P, lane);
+          __syncwarp();
+          const int pw = k.z - k.x, ph = k.w - k.y, x = lane & 15;
+          if (x < pw)
+            for (int y = lane >> 4; y < ph; y += 2) P[(y + 1) * kFuRows + x + 1] = __ldcg(pbase + y * kPatchPitch + x);
+          upsample = true;
         }
       }
-      // this piece is in L2; the warp that completes the detection's patch upsamples it
-      __threadfence();
-      __syncwarp();
-      const int npieces = ((k.px1 - 1) / kRegBoxX - k.px0 / kRegBoxX + 1) * ((k.py1 - 1) / kRegBoxY - k.py0 / kRegBoxY + 1);
-      int last = 0;
-      if (lane == 0) last = (atomicAdd(&done[slot], 1) == npieces - 1) ? 1 : 0;
-      last = __shfl_sync(0xffffffffu, last, 0);
-      if (last) {
-        __threadfence();
+      if (upsample) {
+        __syncwarp();
         const int4 wdw = reinterpret_cast<const int4*>(geom4)[slot];
         const long long off = offsets[slot];
-        const long long words = (long long)((wdw.z + 31) >> 5) * wdw.w;
-        if (off + words > capacity_words) {
+        if (off + (long long)((wdw.z + 31) >> 5) * wdw.w > capacity_words) {
           if (lane == 0) atomicOr(status, HDY_STATUS_OVERFLOW);
         } else {
-          upsample_pack_warp(pbase, k, wdw, off, bits, mh, mw, ih, iw, S.col[warp], S.rows[warp], lane);
+          upsample_pack_v2(P, S.up[warp].colT, k, wdw, off, bits, mh, mw, ih, iw, lane);
         }
       }
-      e = en;
     }
     __syncthreads();  // every warp is done with the region buffer (and with S.item / S.next_piece)
   }
@@ -776,13 +806,15 @@ int launch_process_mask_regions(const void* protos, int proto_dtype, const float
     return HDY_ERR_CUDA;
   }
   const float4* b4 = reinterpret_cast<const float4*>(boxes);
-  // bit-packed + upsampled (the throughput form): ONE persistent kernel does both phases (HDY_MASK_PATH=2phase keeps
-  // the two-kernel form for A/B runs)
-  static const bool two_phase = [] {
+  // bit-packed + upsampled (the throughput form) has kernels of its own: HDY_MASK_PATH = "fused" (one persistent
+  // kernel for both phases), "2" (two kernels: regions -> patches, then upsample_pack_v2), "1" (the first version's
+  // kernels, kept for A/B runs); read per call
+  int path = 0;
+  if (out_dense == nullptr && upsample && geom) {
     const char* v = getenv("HDY_MASK_PATH");
-    return v && v[0] == '2';
-  }();
-  if (out_dense == nullptr && upsample && geom && !two_phase) {
+    path = !v ? HDY_MASK_DEFAULT_PATH : (v[0] == 'f' ? 2 : (v[0] == '1' ? 0 : 1));
+  }
+  if (path != 0) {
     static int sm_count = 0;
     if (!sm_count) {
       int dev = 0;
@@ -792,40 +824,52 @@ int launch_process_mask_regions(const void* protos, int proto_dtype, const float
     }
     e = cudaMemsetAsync(W.work_counter, 0, 4, stream);
     const size_t smem = half ? sizeof(FuSmem<__half>) : sizeof(FuSmem<float>);
-    if (e == cudaSuccess)
+    if (e == cudaSuccess && path == 2)
       e = half ? cudaFuncSetAttribute(mask_fused_kernel<__half>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)
                : cudaFuncSetAttribute(mask_fused_kernel<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) {
-      set_error("process_mask(fused) setup: %s", cudaGetErrorString(e));
+      set_error("process_mask(packed) setup: %s", cudaGetErrorString(e));
       return HDY_ERR_CUDA;
     }
     proto_bin_fused_kernel<<<(unsigned)((slots + 255) / 256), 256, 0, stream>>>(
-        b4, counts, slots, max_det, mh, mw, rxn, ryn, rx, ry, geom, W.regions, W.done, W.large_count, W.large_list);
+        b4, counts, slots, max_det, mh, mw, rxn, ryn, rx, ry, geom, W.regions, W.kr, W.done, W.large_count,
+        W.large_list);
     const long long n_items = (long long)bs * rxn * ryn;
-    const unsigned grid = (unsigned)(n_items < 2ll * sm_count ? n_items : 2ll * sm_count);   // two CTAs per SM
-    if (half)
-      mask_fused_kernel<__half><<<grid, kFuThreads, smem, stream>>>(
-          map, coef, b4, max_det, mh, mw, ih, iw, rxn, ryn, n_items, rx, ry, W.patches, W.regions, W.done,
-          W.work_counter, geom, offsets, bits, capacity_words, status);
-    else
-      mask_fused_kernel<float><<<grid, kFuThreads, smem, stream>>>(
-          map, coef, b4, max_det, mh, mw, ih, iw, rxn, ryn, n_items, rx, ry, W.patches, W.regions, W.done,
-          W.work_counter, geom, offsets, bits, capacity_words, status);
+    if (path == 2) {
+      const unsigned grid = (unsigned)(n_items < 2ll * sm_count ? n_items : 2ll * sm_count);   // two CTAs per SM
+      if (half)
+        mask_fused_kernel<__half><<<grid, kFuThreads, smem, stream>>>(
+            map, coef, W.kr, max_det, mh, mw, ih, iw, rxn, ryn, n_items, W.patches, W.regions, W.done, W.work_counter,
+            geom, offsets, bits, capacity_words, status);
+      else
+        mask_fused_kernel<float><<<grid, kFuThreads, smem, stream>>>(
+            map, coef, W.kr, max_det, mh, mw, ih, iw, rxn, ryn, n_items, W.patches, W.regions, W.done, W.work_counter,
+            geom, offsets, bits, capacity_words, status);
+    } else {
+      if (half)
+        proto_patch_kernel<__half><<<(unsigned)n_items, kRegThreads, sizeof(RegSmemT<__half>), stream>>>(
+            map, coef, W.kr, counts, max_det, rxn, ryn, W.patches, W.regions);
+      else
+        proto_patch_kernel<float><<<(unsigned)n_items, kRegThreads, sizeof(RegSmemT<float>), stream>>>(
+            map, coef, W.kr, counts, max_det, rxn, ryn, W.patches, W.regions);
+      mask_upsample_pack2_kernel<<<(unsigned)((slots + kFuWarps - 1) / kFuWarps), kFuThreads, 0, stream>>>(
+          W.patches, W.kr, geom, offsets, slots, mh, mw, ih, iw, bits, capacity_words, status);
+    }
     pm_clear_listed_kernel<<<148, 256, 0, stream>>>(geom, offsets, bits, capacity_words, W.large_list, W.large_count);
-    int rcf = check_launch("hdy_process_mask(fused)");
+    int rcf = check_launch("hdy_process_mask(packed)");
     if (rcf) return rcf;
     return launch_process_mask_listed(protos, proto_dtype, coef, boxes, counts, max_det, nm, mh, mw, ih, iw, upsample,
                                       rx, ry, nullptr, offsets, bits, capacity_words, status, W.large_list,
                                       W.large_count, stream);
   }
   proto_bin_kernel<<<(unsigned)((slots + 255) / 256), 256, 0, stream>>>(b4, counts, slots, max_det, mh, mw, rxn, ryn, rx,
-                                                                        ry, geom, W.regions);
+                                                                        ry, geom, W.regions, W.kr);
   if (half)
     proto_patch_kernel<__half><<<(unsigned)((long long)bs * rxn * ryn), kRegThreads, sizeof(RegSmemT<__half>), stream>>>(
-        map, coef, b4, counts, max_det, mh, mw, rxn, ryn, rx, ry, W.patches, W.regions);
+        map, coef, W.kr, counts, max_det, rxn, ryn, W.patches, W.regions);
   else
     proto_patch_kernel<float><<<(unsigned)((long long)bs * rxn * ryn), kRegThreads, sizeof(RegSmemT<float>), stream>>>(
-        map, coef, b4, counts, max_det, mh, mw, rxn, ryn, rx, ry, W.patches, W.regions);
+        map, coef, W.kr, counts, max_det, rxn, ryn, W.patches, W.regions);
   const unsigned g2 = (unsigned)((slots + kUpWarps - 1) / kUpWarps);
   const bool packed = out_dense == nullptr;
 #define HDY_UP(P, U)                                                                                              \

@@ -323,3 +323,52 @@ def test_process_mask_full_size_config2(cuda_device):
         assert int((geom[t * md + k:(t + 1) * md, 2:] != 0).sum()) == 0      # slots beyond counts are empty
     assert agree / total >= AGREE, f"agreement {agree / total}"
     assert int(offs[-1]) <= bits.numel() and int(offs[-1]) > 30 * 2000
+
+
+@pytest.mark.parametrize("mh,mw,ih,iw,md,lo,hi,half", [(160, 160, 640, 640, 900, 12, 36, False),
+                                                       (256, 256, 1024, 1024, 2650, 12, 36, False),
+                                                       (64, 80, 250, 333, 300, 4, 120, False),
+                                                       (128, 128, 512, 512, 700, 10, 70, True)])
+def test_packed_mask_kernel_paths_agree_bit_for_bit(cuda_device, monkeypatch, mh, mw, ih, iw, md, lo, hi, half):
+    """The bit-packed, upsampled form has three kernel paths (HDY_MASK_PATH: "1" = the first version's two kernels,
+    "2" = regions -> patches + upsample_pack_v2, "fused" = one persistent kernel): same geometry, same offsets, the
+    same bits -- including boxes too large for the patch path, crowded regions whose lists overflow, empty tiles and
+    non-integer scales."""
+    g = torch.Generator().manual_seed(mh + md)
+    bs = 3
+    protos = torch.randn((bs, 32, mh, mw), generator=g)
+    if half:
+        protos = protos.half()
+    coef = torch.randn((bs, md, 32), generator=g) * 0.5
+    boxes = torch.stack([_rand_boxes(g, md, ih, iw, lo, hi),
+                         _rand_boxes(g, md, ih // 6, iw // 6, lo, min(hi, 30)),        # > 254 boxes in one region
+                         _rand_boxes(g, md, ih, iw, lo, hi)])
+    boxes[0, 3] = torch.tensor([5.0, 7.0, iw - 20.0, ih * 0.6])                       # huge: per-detection kernel
+    counts = torch.tensor([md, md - 7, 0], dtype=torch.int32)
+    args = (protos.to(cuda_device), coef.to(cuda_device), boxes.to(cuda_device), counts.to(cuda_device), (ih, iw))
+    out = {}
+    for path in ("1", "2", "fused"):
+        monkeypatch.setenv("HDY_MASK_PATH", path)
+        pk = hm.process_mask_packed(*args, upsample=True)
+        pk.check()
+        out[path] = (pk.geom.clone(), pk.offsets.clone(), pk.bits.clone())
+    monkeypatch.delenv("HDY_MASK_PATH")
+    for path in ("2", "fused"):
+        for a, b, what in zip(out["1"], out[path], ("geom", "offsets", "bits")):
+            assert torch.equal(a, b), f"path {path}: {what} differ ({int((a != b).sum())} entries)"
+    assert int(out["1"][1][-1]) > 20 * (md - 7)
+
+
+def test_mask_agreement_is_tight_inside_the_windows(cuda_device):
+    """The 99.99 % bar of the north star is over whole canvases, where a nucleus covers < 1 % of the pixels.  The
+    stricter statement: mismatching pixels are fewer than 1e-4 of the pixels the oracle SETS (differences can only
+    come from values within an ulp of 0.5)."""
+    g = torch.Generator().manual_seed(77)
+    n, mh, ih = 600, 160, 640
+    protos = torch.randn((32, mh, mh), generator=g)
+    coef = torch.randn((n, 32), generator=g) * 0.5
+    boxes = _rand_boxes(g, n, ih, ih, 10, 50)
+    ref = port.process_mask(protos, coef, boxes.clone(), (ih, ih), upsample=True)
+    out = hm.process_mask(protos.to(cuda_device), coef.to(cuda_device), boxes.to(cuda_device), (ih, ih), upsample=True).cpu()
+    diff = int((out != ref).sum())
+    assert float(ref.sum()) > 1e5 and diff <= 1e-4 * float(ref.sum()), f"{diff} of {int(ref.sum())} set pixels differ"

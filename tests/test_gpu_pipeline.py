@@ -22,6 +22,10 @@ def _oracle_merge(spec, rois, store, md):
     tiles = []
     for (a, b), dets in sorted(store.items()):
         cat = hdy.decode_concat(dets, spec).cpu()
+        ne = spec.no - 5 - spec.nc
+        if ne:      # mask coefficients travel RAW (the decode's sigmoid over the whole row is not applied to them)
+            raw = torch.cat([d.reshape(d.shape[0], -1, spec.no) for d in dets], 1).cpu()
+            cat[..., 5 + spec.nc:5 + spec.nc + ne] = raw[..., 5 + spec.nc:]
         outs = port.nms_per_image(cat, spec.nc, CONF, IOU, md)
         for j, o in enumerate(outs):
             s, l = port.select_scores(o['scores'][:, :1 + spec.nc].clone(), CONF, port.default_descendants(spec.nc))
@@ -192,6 +196,8 @@ def test_slide_masks_of_kept_rows_match_oracle(cuda_device):
         row += k
     assert row == n and total > 0
     assert agree / total >= 0.9999, f"mask agreement {agree / total}"
+    set_px = int(dense[state == 1].sum())
+    assert set_px > 1e5 and total - agree <= 1e-4 * set_px, f"{total - agree} of {set_px} set pixels differ"
     d1 = fold_digest(mask_digest(pm, res['state'], 0))
 
     def rank_run(rank, comm):
