@@ -897,7 +897,7 @@ def run_slide(args, wl, c, steps, warmup, want_e2e, want_cpu_merge=False, masks=
         nst = max(1, args.slide_streams)
         stg = [[torch.empty_like(t) for t in store[0]] for _ in range(nst)]
         host_p = [pool[k * bs:(k + 1) * bs].cpu().pin_memory() for k in range(min(4, P // bs))] if with_masks else None
-        stg_p = torch.empty_like(pool[:bs]) if with_masks else None
+        stg_p = [torch.empty_like(pool[:bs]) for _ in range(nst)] if with_masks else None   # one per stream
 
         def provider_h(a, b):
             k = ((a - t0) // bs)
@@ -911,8 +911,9 @@ def run_slide(args, wl, c, steps, warmup, want_e2e, want_cpu_merge=False, masks=
         def protos_h(a, b):
             k = ((a - t0) // bs)
             n = b - a
-            stg_p[:n].copy_(host_p[k % len(host_p)][:n], non_blocking=True)
-            return stg_p[:n]
+            sp = stg_p[k % nst]               # batch k runs on stream k % streams (SlidePostprocessor.masks)
+            sp[:n].copy_(host_p[k % len(host_p)][:n], non_blocking=True)
+            return sp[:n]
 
         hb, pinned = {}, {}
 

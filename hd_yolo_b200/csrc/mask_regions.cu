@@ -468,41 +468,73 @@ __global__ void __launch_bounds__(kUpWarps * 32) mask_upsample_pack_kernel(
 //     special case for narrow tail words; 1 000 warp instructions per detection, 70 % of the issue slots.)
 constexpr int kFuWarps = 8;
 constexpr int kFuThreads = kFuWarps * 32;
-constexpr int kFuRows = kPatchPitch + 2;   // ringed source rows / columns
+constexpr int kFuRows = kPatchPitch + 2;   // ringed source rows
 constexpr int kColPitch = kFuRows + 1;     // odd: lanes = columns write, lanes = rows read, both conflict-free
+// ringed patch in shared memory: ring row s at P[s * kUpPitch ...], element (y, x) of the kept range at
+// [(y + 1) * kUpPitch + kUpX0 + x] (rows 16-byte aligned, so a row of the workspace patch is one float4 per 4 pixels),
+// ring column xi (0 = left zero column, pw + 1 = right zero column) at [.. + kUpX0 - 1 + xi]
+constexpr int kUpPitch = 24;
+constexpr int kUpX0 = 4;
 
 struct UpWarpSmem {
-  float patch[kFuRows * kFuRows];   // ringed sigmoid patch, 81 float4
+  float patch[kFuRows * kUpPitch];  // 432 floats
   float colT[32 * kColPitch];       // x-pass results of the current 32 output columns: [column][source row]
 };
 
-__device__ __forceinline__ void up_zero_patch(float* P, int lane) {
-  float4* p4 = reinterpret_cast<float4*>(P);
-  for (int i = lane; i < kFuRows * kFuRows / 4; i += 32) p4[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+// Only what the taps can reach has to be zero: ring rows 0 and ph + 1 (columns 0 .. pw + 1) and the two ring columns
+// of the rows in between.  Entries past the kept range that a float4 copy of a workspace row drags in are never read.
+__device__ __forceinline__ void up_zero_ring(float* P, int pw, int ph, int lane) {
+  if (lane < kFuRows) {
+    P[kUpX0 - 1 + lane] = 0.f;                              // ring row 0
+    P[(ph + 1) * kUpPitch + kUpX0 - 1 + lane] = 0.f;        // ring row ph + 1
+    if (lane < ph) {
+      P[(lane + 1) * kUpPitch + kUpX0 - 1] = 0.f;           // left ring column
+      P[(lane + 1) * kUpPitch + kUpX0 + pw] = 0.f;          // right ring column
+    }
+  }
+}
+
+// workspace patch (pitch 16, [ph][pw] valid) -> ringed shared-memory patch: one float4 per lane and 8 rows
+template <bool CG>
+__device__ __forceinline__ void up_load_patch(float* P, const float* __restrict__ src, int pw, int ph, int lane) {
+  const int row = lane >> 2, quad = lane & 3;
+  const float4* s4 = reinterpret_cast<const float4*>(src);
+  float4 a = make_float4(0.f, 0.f, 0.f, 0.f), b = a;
+  const bool ra = row < ph, rb = row + 8 < ph;
+  if (ra) a = CG ? __ldcg(s4 + row * 4 + quad) : s4[row * 4 + quad];
+  if (rb) b = CG ? __ldcg(s4 + (row + 8) * 4 + quad) : s4[(row + 8) * 4 + quad];
+  if (ra) *reinterpret_cast<float4*>(P + (row + 1) * kUpPitch + kUpX0 + quad * 4) = a;
+  if (rb) *reinterpret_cast<float4*>(P + (row + 9) * kUpPitch + kUpX0 + quad * 4) = b;
+  __syncwarp();
+  up_zero_ring(P, pw, ph, lane);   // after the copy: the right ring column lies inside the copied floats
 }
 
 // ATen bilinear (align_corners=False), operation by operation, + threshold + pack of one detection.
-// P: ringed patch (element (y, x) of the kept range at [(y + 1) * 18 + x + 1], zeros elsewhere).
+// P: ringed patch (layout above).  sxs / sys: ATen's scale = in / out, computed in fp32 on the host.
 __device__ __forceinline__ void upsample_pack_v2(const float* __restrict__ P, float* __restrict__ colT, const int4 kr,
                                                  const int4 wdw, long long off, uint32_t* __restrict__ bits, int mh,
-                                                 int mw, int ih, int iw, int lane) {
+                                                 int mw, float sxs, float sys, int lane) {
   const int pw = kr.z - kr.x, ph = kr.w - kr.y;
   const int gx0 = wdw.x, gy0 = wdw.y, gw = wdw.z, gh = wdw.w;
   const int wpr = (gw + 31) >> 5;
   const int src_rows = ph + 2;
-  const float sxs = (float)mw / (float)iw, sys = (float)mh / (float)ih;  // ATen: scale = in / out (fp32)
   for (int w = 0; w < wpr; ++w) {
     const int vw = min(32, gw - (w << 5));  // valid columns of this word
     // x pass (lane = column): top / bot of ATen's formula for every source row
     const int c = (w << 5) + lane;
     const Lerp X = lerp_coord(gx0 + (c < gw ? c : 0), sxs, mw);
     // taps outside [px0 - 1, px1] contribute nothing (cropped): clamp them onto the ring of zeros
-    const int xi0 = min(max(X.i0 - kr.x + 1, 0), pw + 1), xi1 = min(max(X.i1 - kr.x + 1, 0), pw + 1);
+    const float* p0 = P + kUpX0 - 1 + min(max(X.i0 - kr.x + 1, 0), pw + 1);
+    const float* p1 = P + kUpX0 - 1 + min(max(X.i1 - kr.x + 1, 0), pw + 1);
     __syncwarp();  // the previous word's y pass is done with colT
     float* ct = colT + lane * kColPitch;
-#pragma unroll 2
-    for (int s = 0; s < src_rows; ++s)
-      ct[s] = __fadd_rn(__fmul_rn(X.l0, P[s * kFuRows + xi0]), __fmul_rn(X.l1, P[s * kFuRows + xi1]));
+    int s = 0;
+    for (; s + 4 <= src_rows; s += 4) {
+#pragma unroll
+      for (int j = 0; j < 4; ++j)
+        ct[s + j] = __fadd_rn(__fmul_rn(X.l0, p0[(s + j) * kUpPitch]), __fmul_rn(X.l1, p1[(s + j) * kUpPitch]));
+    }
+    for (; s < src_rows; ++s) ct[s] = __fadd_rn(__fmul_rn(X.l0, p0[s * kUpPitch]), __fmul_rn(X.l1, p1[s * kUpPitch]));
     __syncwarp();
     // y pass (lane = row)
     for (int r0 = 0; r0 < gh; r0 += 32) {
@@ -512,16 +544,40 @@ __device__ __forceinline__ void upsample_pack_v2(const float* __restrict__ P, fl
       const float* c0 = colT + min(max(Y.i0 - kr.y + 1, 0), ph + 1);
       const float* c1 = colT + min(max(Y.i1 - kr.y + 1, 0), ph + 1);
       uint32_t word = 0u;
-#pragma unroll
-      for (int xg = 0; xg < 32; xg += 4) {
-        if (xg >= vw) break;  // warp-uniform
-#pragma unroll
-        for (int j = 0; j < 4; ++j) {
-          const int x = xg + j;
-          const float v = __fadd_rn(__fmul_rn(Y.l0, c0[x * kColPitch]), __fmul_rn(Y.l1, c1[x * kColPitch]));
-          if (v > 0.5f) word |= 1u << x;
+      // one pixel: two-tap blend, compare, predicated OR of an immediate bit (word |= (v > 0.5f) << x)
+#define HDY_PX(x)                                                                                                  \
+  {                                                                                                                \
+    const float v = __fadd_rn(__fmul_rn(Y.l0, c0[(x) * kColPitch]), __fmul_rn(Y.l1, c1[(x) * kColPitch]));         \
+    asm("{\n\t.reg .pred p;\n\tsetp.gt.f32 p, %1, 0f3F000000;\n\t@p or.b32 %0, %0, %2;\n\t}"                   \
+        : "+r"(word)                                                                                               \
+        : "f"(v), "n"(1u << (x)));                                                                                 \
+  }
+#define HDY_G4(g) HDY_PX(g) HDY_PX((g) + 1) HDY_PX((g) + 2) HDY_PX((g) + 3)
+      // groups of four columns, nested so that the warp-uniform exit costs one branch per group
+      HDY_G4(0)
+      if (vw > 4) {
+        HDY_G4(4)
+        if (vw > 8) {
+          HDY_G4(8)
+          if (vw > 12) {
+            HDY_G4(12)
+            if (vw > 16) {
+              HDY_G4(16)
+              if (vw > 20) {
+                HDY_G4(20)
+                if (vw > 24) {
+                  HDY_G4(24)
+                  if (vw > 28) {
+                    HDY_G4(28)
+                  }
+                }
+              }
+            }
+          }
         }
       }
+#undef HDY_G4
+#undef HDY_PX
       if (vw < 32) word &= (1u << vw) - 1u;  // columns past the window were computed from clamped taps
       if (act) bits[off + (long long)r * wpr + w] = word;
     }
@@ -584,8 +640,8 @@ __global__ void pm_clear_listed_kernel(const int32_t* __restrict__ geom4, const 
 // phase 2 of the two-kernel form: one warp per detection, patch from the workspace
 __global__ void __launch_bounds__(kFuThreads) mask_upsample_pack2_kernel(
     const float* __restrict__ patches, const int4* __restrict__ krs, const int32_t* __restrict__ geom4,
-    const int64_t* __restrict__ offsets, long long n_slots, int mh, int mw, int ih, int iw, uint32_t* __restrict__ bits,
-    long long capacity_words, int32_t* __restrict__ status) {
+    const int64_t* __restrict__ offsets, long long n_slots, int mh, int mw, float sxs, float sys,
+    uint32_t* __restrict__ bits, long long capacity_words, int32_t* __restrict__ status) {
   __shared__ __align__(16) UpWarpSmem S[kFuWarps];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const long long slot = (long long)blockIdx.x * kFuWarps + warp;
@@ -600,16 +656,9 @@ __global__ void __launch_bounds__(kFuThreads) mask_upsample_pack2_kernel(
     return;
   }
   float* P = S[warp].patch;
-  up_zero_patch(P, lane);
+  up_load_patch<false>(P, patches + slot * (kPatchPitch * kPatchPitch), pw, ph, lane);
   __syncwarp();
-  {  // interior: rows of 16 floats, two rows per step (entries beyond pw are stale: not copied)
-    const float* src = patches + slot * (kPatchPitch * kPatchPitch);
-    const int x = lane & 15;
-    if (x < pw)
-      for (int y = lane >> 4; y < ph; y += 2) P[(y + 1) * kFuRows + x + 1] = src[y * kPatchPitch + x];
-  }
-  __syncwarp();
-  upsample_pack_v2(P, S[warp].colT, kr, wdw, off, bits, mh, mw, ih, iw, lane);
+  upsample_pack_v2(P, S[warp].colT, kr, wdw, off, bits, mh, mw, sxs, sys, lane);
 }
 
 // ------------------------------------------------------------------------------------------------ fused path
@@ -637,7 +686,7 @@ struct FuSmem {
 template <typename E>
 __global__ void __launch_bounds__(kFuThreads, 2) mask_fused_kernel(
     const __grid_constant__ CUtensorMap tmap, const float* __restrict__ coef, const int4* __restrict__ krs, int max_det,
-    int mh, int mw, int ih, int iw, int rxn, int ryn, long long n_items, float* __restrict__ patches,
+    int mh, int mw, float sxs, float sys, int rxn, int ryn, long long n_items, float* __restrict__ patches,
     const RegionList* __restrict__ regions, int32_t* __restrict__ done, int32_t* __restrict__ work_counter,
     const int32_t* __restrict__ geom4, const int64_t* __restrict__ offsets, uint32_t* __restrict__ bits,
     long long capacity_words, int32_t* __restrict__ status) {
@@ -709,10 +758,9 @@ __global__ void __launch_bounds__(kFuThreads, 2) mask_fused_kernel(
       float* pbase = patches + slot * (kPatchPitch * kPatchPitch);
       if (single) {
         // the whole kept range lies in this region: contraction -> shared-memory patch, nothing leaves the SM
-        up_zero_patch(P, lane);
-        __syncwarp();
+        up_zero_ring(P, k.z - k.x, k.w - k.y, lane);
         contract_piece<E>(S.proto, S.coef[warp], k, X0, Y0, lane,
-                          [&](int px, int py, float v) { P[(py + 1) * kFuRows + px + 1] = v; });
+                          [&](int px, int py, float v) { P[(py + 1) * kUpPitch + kUpX0 + px] = v; });
       } else {
         contract_piece<E>(S.proto, S.coef[warp], k, X0, Y0, lane,
                           [&](int px, int py, float v) { __stcg(pbase + py * kPatchPitch + px, v); });
@@ -725,11 +773,7 @@ __global__ void __launch_bounds__(kFuThreads, 2) mask_fused_kernel(
         last = __shfl_sync(0xffffffffu, last, 0);
         if (last) {
           asm volatile("fence.acq_rel.gpu;" ::: "memory");
-          up_zero_patch(P, lane);
-          __syncwarp();
-          const int pw = k.z - k.x, ph = k.w - k.y, x = lane & 15;
-          if (x < pw)
-            for (int y = lane >> 4; y < ph; y += 2) P[(y + 1) * kFuRows + x + 1] = __ldcg(pbase + y * kPatchPitch + x);
+          up_load_patch<true>(P, pbase, k.z - k.x, k.w - k.y, lane);
           upsample = true;
         }
       }
@@ -740,7 +784,7 @@ __global__ void __launch_bounds__(kFuThreads, 2) mask_fused_kernel(
         if (off + (long long)((wdw.z + 31) >> 5) * wdw.w > capacity_words) {
           if (lane == 0) atomicOr(status, HDY_STATUS_OVERFLOW);
         } else {
-          upsample_pack_v2(P, S.up[warp].colT, k, wdw, off, bits, mh, mw, ih, iw, lane);
+          upsample_pack_v2(P, S.up[warp].colT, k, wdw, off, bits, mh, mw, sxs, sys, lane);
         }
       }
     }
@@ -815,6 +859,7 @@ int launch_process_mask_regions(const void* protos, int proto_dtype, const float
     path = !v ? HDY_MASK_DEFAULT_PATH : (v[0] == 'f' ? 2 : (v[0] == '1' ? 0 : 1));
   }
   if (path != 0) {
+    const float sxs = (float)mw / (float)iw, sys = (float)mh / (float)ih;  // ATen: scale = in / out (fp32)
     static int sm_count = 0;
     if (!sm_count) {
       int dev = 0;
@@ -839,12 +884,12 @@ int launch_process_mask_regions(const void* protos, int proto_dtype, const float
       const unsigned grid = (unsigned)(n_items < 2ll * sm_count ? n_items : 2ll * sm_count);   // two CTAs per SM
       if (half)
         mask_fused_kernel<__half><<<grid, kFuThreads, smem, stream>>>(
-            map, coef, W.kr, max_det, mh, mw, ih, iw, rxn, ryn, n_items, W.patches, W.regions, W.done, W.work_counter,
-            geom, offsets, bits, capacity_words, status);
+            map, coef, W.kr, max_det, mh, mw, sxs, sys, rxn, ryn, n_items, W.patches, W.regions, W.done,
+            W.work_counter, geom, offsets, bits, capacity_words, status);
       else
         mask_fused_kernel<float><<<grid, kFuThreads, smem, stream>>>(
-            map, coef, W.kr, max_det, mh, mw, ih, iw, rxn, ryn, n_items, W.patches, W.regions, W.done, W.work_counter,
-            geom, offsets, bits, capacity_words, status);
+            map, coef, W.kr, max_det, mh, mw, sxs, sys, rxn, ryn, n_items, W.patches, W.regions, W.done,
+            W.work_counter, geom, offsets, bits, capacity_words, status);
     } else {
       if (half)
         proto_patch_kernel<__half><<<(unsigned)n_items, kRegThreads, sizeof(RegSmemT<__half>), stream>>>(
@@ -853,7 +898,7 @@ int launch_process_mask_regions(const void* protos, int proto_dtype, const float
         proto_patch_kernel<float><<<(unsigned)n_items, kRegThreads, sizeof(RegSmemT<float>), stream>>>(
             map, coef, W.kr, counts, max_det, rxn, ryn, W.patches, W.regions);
       mask_upsample_pack2_kernel<<<(unsigned)((slots + kFuWarps - 1) / kFuWarps), kFuThreads, 0, stream>>>(
-          W.patches, W.kr, geom, offsets, slots, mh, mw, ih, iw, bits, capacity_words, status);
+          W.patches, W.kr, geom, offsets, slots, mh, mw, sxs, sys, bits, capacity_words, status);
     }
     pm_clear_listed_kernel<<<148, 256, 0, stream>>>(geom, offsets, bits, capacity_words, W.large_list, W.large_count);
     int rcf = check_launch("hdy_process_mask(packed)");

@@ -262,31 +262,52 @@ class SlideMaskBuilder:
         self.batches = 0
         self.H, self.W = _hw(image_size)
 
-    def add_batch(self, protos: torch.Tensor, coef: torch.Tensor, boxes: torch.Tensor, counts: torch.Tensor,
-                  tile_offsets: torch.Tensor, rois: torch.Tensor, row_state: torch.Tensor, shape,
-                  upsample: bool = True) -> None:
-        """protos [bs,nm,mh,mw] of the batch's tiles; coef / boxes / counts as DetectBatch holds them (tile
-        coordinates); tile_offsets [bs+1] from the append; rois [bs,4]; row_state: verdict per slide row."""
-        bs, nm, mh, mw, md = _pm_args(protos, coef, boxes, counts)
+    def prepare(self, boxes: torch.Tensor, counts: torch.Tensor, tile_offsets: torch.Tensor, rois: torch.Tensor,
+                row_state: torch.Tensor, proto_hw, shape, upsample: bool = True, lane: int = 0):
+        """Windows and word offsets of the next batch (in batch order: the slide-wide word cursor advances), scattered
+        to the slide rows.  Returns (geom, offsets) for ``run``; `lane` picks the scratch pair, so that the kernels of
+        batch i can still read theirs while batch i + 1 is prepared (mask kernels on alternating streams)."""
+        bs, md = int(boxes.shape[0]), int(boxes.shape[1])
+        mh, mw = proto_hw
         ih, iw = _hw(shape)
-        dev = protos.device
+        dev = boxes.device
         K = bs * md
         if K == 0:
-            return
+            return None
         boxes = _aligned16(boxes.contiguous())
-        geom = _pm_scratch.get(dev, "slide_geom", K * 16).view(torch.int32)[:K * 4]
-        offsets = _pm_scratch.get(dev, "slide_offsets", (K + 1) * 8).view(torch.int64)[:K + 1]
+        geom = _pm_scratch.get(dev, f"slide_geom{lane}", K * 16).view(torch.int32)[:K * 4]
+        offsets = _pm_scratch.get(dev, f"slide_offsets{lane}", (K + 1) * 8).view(torch.int64)[:K + 1]
         _call("hdy_process_mask_geometry", ptr(boxes), ptr(counts), bs, md, mh, mw, ih, iw, int(bool(upsample)),
               ptr(row_state), ptr(tile_offsets), ptr(geom), ptr(offsets), _stream(), launches=2)
         _call("hdy_process_mask_rows", ptr(geom), ptr(offsets), ptr(counts), ptr(tile_offsets),
               ptr(_aligned16(rois.contiguous())), bs, md, ptr(self.cursor2), self.batches & 1, ptr(self.geom),
               ptr(self.offsets), _stream())
+        self.batches += 1
+        return geom, offsets
+
+    def run(self, prepared, protos: torch.Tensor, coef: torch.Tensor, boxes: torch.Tensor, counts: torch.Tensor,
+            shape, upsample: bool = True) -> None:
+        """The mask kernels of a prepared batch (any stream ordered after its ``prepare``)."""
+        if prepared is None:
+            return
+        geom, offsets = prepared
+        bs, nm, mh, mw, md = _pm_args(protos, coef, boxes, counts)
+        ih, iw = _hw(shape)
+        dev = protos.device
+        boxes = _aligned16(boxes.contiguous())
         ws, wbytes = _pm_workspace(dev, bs, md)
         _call("hdy_process_mask_packed", ptr(_aligned16(protos.contiguous())), _need_head_tensor(protos, "protos"),
               ptr(coef.contiguous()), ptr(boxes),
               ptr(counts), ptr(geom), ptr(offsets), bs, md, nm, mh, mw, ih, iw, int(bool(upsample)), ptr(self.bits),
               self.capacity_words, ptr(self.status), ptr(ws), wbytes, _stream(), launches=3)
-        self.batches += 1
+
+    def add_batch(self, protos: torch.Tensor, coef: torch.Tensor, boxes: torch.Tensor, counts: torch.Tensor,
+                  tile_offsets: torch.Tensor, rois: torch.Tensor, row_state: torch.Tensor, shape,
+                  upsample: bool = True) -> None:
+        """protos [bs,nm,mh,mw] of the batch's tiles; coef / boxes / counts as DetectBatch holds them (tile
+        coordinates); tile_offsets [bs+1] from the append; rois [bs,4]; row_state: verdict per slide row."""
+        prep = self.prepare(boxes, counts, tile_offsets, rois, row_state, tuple(protos.shape[2:]), shape, upsample)
+        self.run(prep, protos, coef, boxes, counts, shape, upsample)
 
     def finish(self) -> PackedMasks:
         """offsets[n] = total words.  Rows that were never live keep offset 0 / an empty window: consumers address a

@@ -194,9 +194,40 @@ class SlidePostprocessor:
         canvas = (int(self.rois[:, 1].max()) + int(self.roi_size[0]), int(self.rois[:, 0].max()) + int(self.roi_size[1]))
         bld = SlideMaskBuilder(n, int(n * words_per_row) + 4096, canvas, self.device)
         t0 = self.tile_range[0]
-        for a, b, out, offs in self._batches:
-            bld.add_batch(proto_provider(a, b), out.extra, out.boxes, out.counts, offs, self.rois_dev[a - t0:b - t0],
-                          state, self.roi_size, upsample=upsample)
+        if self.n_streams == 1:
+            for a, b, out, offs in self._batches:
+                bld.add_batch(proto_provider(a, b), out.extra, out.boxes, out.counts, offs,
+                              self.rois_dev[a - t0:b - t0], state, self.roi_size, upsample=upsample)
+            return bld.finish()
+        # The region kernel waits on HBM, the upsample kernel on issue slots: batches alternate over the side streams,
+        # so one batch's upsample overlaps the next batch's regions.  Windows / offsets are prepared on the calling
+        # stream in batch order (the word cursor is shared); a scratch pair is re-used only after its kernels finished.
+        from .ops import scratch_slot, _slot
+        base_slot = _slot()
+        with torch.cuda.device(self.device):
+            while len(self._side) < self.n_streams:
+                self._side.append(torch.cuda.Stream())
+            cur = torch.cuda.current_stream()
+            done: List[Optional[torch.cuda.Event]] = [None] * self.n_streams
+            for i, (a, b, out, offs) in enumerate(self._batches):
+                lane = i % self.n_streams
+                side = self._side[lane]
+                if done[lane] is not None:
+                    cur.wait_event(done[lane])
+                ready = torch.cuda.Event()
+                with torch.cuda.stream(side), scratch_slot(base_slot * 16 + 8 + lane):
+                    protos = proto_provider(a, b)            # (a host-resident provider copies on this stream)
+                pshape = tuple(protos.shape[2:])
+                prep = bld.prepare(out.boxes, out.counts, offs, self.rois_dev[a - t0:b - t0], state, pshape,
+                                   self.roi_size, upsample, lane=lane)
+                ready.record(cur)
+                with torch.cuda.stream(side), scratch_slot(base_slot * 16 + 8 + lane):
+                    side.wait_event(ready)
+                    bld.run(prep, protos, out.extra, out.boxes, out.counts, self.roi_size, upsample)
+                    done[lane] = torch.cuda.Event()
+                    done[lane].record(side)
+            for s_ in self._side:
+                cur.wait_stream(s_)
         return bld.finish()
 
     def run(self, provider, ordered: bool = True, proto_provider=None,

@@ -262,7 +262,7 @@ def test_interior_shortcut_is_exact_far_from_the_origin(cuda_device, thr, seed, 
     ref_state[~keep] = 3
     ref_state[kept] = 1
     batch = DetectBatch(keep_box, None, keep_score, torch.zeros((bs, md), dtype=torch.int64, device=dev), None, None,
-                        keep_idx, keep_counts, cand.counts, md, frag[0])
+                        keep_idx, keep_counts, cand.counts, md, frag[0], eps, thr)
     acc = hs.SlideAccumulator(int(sum(kc)), dev)
     acc.append(batch, rois.to(dev))
     n_rows = acc.count()
@@ -275,3 +275,74 @@ def test_interior_shortcut_is_exact_far_from_the_origin(cuda_device, thr, seed, 
     # the shortcut really skipped most rows: fragile rows are a small minority
     n_frag = int(sum(int(frag[0][i, :kc[i]].sum()) for i in range(bs)))
     assert 0 < n_frag < 0.8 * n_rows
+
+
+def test_interior_shortcut_preconditions_are_enforced(cuda_device):
+    """The shortcut is exact only under the conditions its gray-zone flags were produced for: a merge threshold below
+    the per-tile NMS threshold, flags for a smaller coordinate range than the slide's, or a re-used accumulator whose
+    tiling changed while the tile counts stayed the same must not silently keep interior rows."""
+    from hd_yolo_b200 import synth
+    dev = cuda_device
+    spec = hdy.HeadSpec(synth.ANCHORS_3, synth.STRIDES_3, nc=4)
+    tile = 320
+
+    def fill(acc, rois, eps, seed=3):
+        dets = synth.slide_tile_logits(rois, tile, 4, seed=seed, device=dev, pitch=20.0)
+        out = hdy.detect_postprocess(dets, spec, 0.25, 0.45, 600, gray_eps=eps)
+        acc.append(out, rois.to(dev), rois_host=rois)
+        return out
+
+    rois_a = hs.sliding_window_scanner((600, 900), (tile, tile), 40)
+    acc = hs.SlideAccumulator(6000, dev)
+    eps = float(np.spacing(np.float32(1000.0))) / 2
+    fill(acc, rois_a, eps)
+    n = acc.count()
+    fast = acc.verdicts(0.25, 0.45, interior_shortcut=True)[:n].clone()
+    full = acc.verdicts(0.25, 0.45, interior_shortcut=False)[:n].clone()
+    assert torch.equal(fast, full) and int((full == 2).sum()) > 0
+    with pytest.raises(hdy.HdyError, match="below the per-tile NMS threshold"):
+        acc.verdicts(0.25, 0.3, interior_shortcut=True)            # same-tile survivors may overlap more than 0.3
+    # the same accumulator, a different tiling with the same number of batches and tiles: the cores are recomputed
+    rois_b = rois_a.clone()
+    rois_b[:, [0, 2]] += 5000.0
+    acc.reset()
+    fill(acc, rois_b, eps)
+    n = acc.count()
+    with pytest.raises(hdy.HdyError, match="round by up to"):       # flags made for coordinates up to ~1000 px
+        acc.verdicts(0.25, 0.45, interior_shortcut=True)
+    acc.reset()
+    fill(acc, rois_b, float(np.spacing(np.float32(8000.0))) / 2)
+    n = acc.count()
+    fast = acc.verdicts(0.25, 0.45, interior_shortcut=True)[:n].clone()
+    full = acc.verdicts(0.25, 0.45, interior_shortcut=False)[:n].clone()
+    assert torch.equal(fast, full)
+
+
+def test_captured_step_pins_its_scratch(cuda_device):
+    """A CUDA graph bakes the addresses of its scratch buffers in: growing one of them under a live graph must raise,
+    never free the memory the graph still writes to; eager work on another stream gets buffers of its own."""
+    from hd_yolo_b200 import synth
+    from hd_yolo_b200.ops import scratch_slot
+    spec = hdy.HeadSpec(synth.ANCHORS_3, synth.STRIDES_3, nc=4)
+    small = [d.to(cuda_device) for d in synth.nuclei_logits(2, 160, 4, 100, seed=1, conf=0.25)]
+    big = [d.to(cuda_device) for d in synth.nuclei_logits(8, 320, 4, 400, seed=2, conf=0.25)]
+    step = hdy.CapturedStep(lambda: hdy.detect_postprocess(small, spec, 0.25, 0.45, 300, cap=512), slot=77)
+    ref = [a['boxes'].clone() for a in step().to_list()]
+    # the same slot, eagerly, on the default stream: its scratch is keyed by stream, the graph's buffers stay put
+    with scratch_slot(77):
+        hdy.detect_postprocess(big, spec, 0.25, 0.45, 300).to_list()
+    again = [a['boxes'] for a in step().to_list()]
+    assert all(torch.equal(a, b) for a, b in zip(ref, again))
+    # on the graph's own stream a larger call would have to regrow the pinned buffers: refused
+    with scratch_slot(77), torch.cuda.stream(step.stream):
+        with pytest.raises(hdy.HdyError, match="CUDA graph"):
+            hdy.detect_postprocess(big, spec, 0.25, 0.45, 300)
+    torch.cuda.synchronize()
+
+
+def test_tensors_of_another_device_are_refused(cuda_device):
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs two GPUs")
+    b = torch.zeros((4, 4), device="cuda:1")
+    with pytest.raises(hdy.HdyError, match="current device"):
+        hdy.nms(b, torch.zeros((4,), device="cuda:1"), 0.5)
