@@ -469,7 +469,12 @@ __global__ void __launch_bounds__(kUpWarps * 32) mask_upsample_pack_kernel(
 constexpr int kFuWarps = 8;
 constexpr int kFuThreads = kFuWarps * 32;
 constexpr int kFuRows = kPatchPitch + 2;   // ringed source rows
-constexpr int kColPitch = kFuRows + 1;     // odd: lanes = columns write, lanes = rows read, both conflict-free
+constexpr int kXRows = 20;                 // source rows the x pass may compute (src_rows rounded up to a multiple of 4)
+// x-pass results of the current 32 output columns, stored for the y pass as PAIRS of adjacent columns:
+// [column >> 1][source row][column & 1], kPairPitch floats per column pair.  The y pass (lane = output row) reads
+// the two columns of a pair with one 64-bit load and multiplies them with one packed FMUL2 (sm_100 f32x2: two IEEE
+// roundings in one instruction); kPairPitch = 42 keeps the x pass's stores (lane = column) conflict-free.
+constexpr int kPairPitch = 2 * (kXRows + 1);
 // ringed patch in shared memory: ring row s at P[s * kUpPitch ...], element (y, x) of the kept range at
 // [(y + 1) * kUpPitch + kUpX0 + x] (rows 16-byte aligned, so a row of the workspace patch is one float4 per 4 pixels),
 // ring column xi (0 = left zero column, pw + 1 = right zero column) at [.. + kUpX0 - 1 + xi]
@@ -477,9 +482,22 @@ constexpr int kUpPitch = 24;
 constexpr int kUpX0 = 4;
 
 struct UpWarpSmem {
-  float patch[kFuRows * kUpPitch];  // 432 floats
-  float colT[32 * kColPitch];       // x-pass results of the current 32 output columns: [column][source row]
+  float patch[kXRows * kUpPitch];   // ringed patch (rows beyond ph + 1 are never used, only read by the x pass)
+  float colT[16 * kPairPitch];      // x-pass results, see kPairPitch
 };
+
+__device__ __forceinline__ unsigned long long f32x2_pack(float lo, float hi) {
+  unsigned long long r;
+  asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi));
+  return r;
+}
+// two IEEE fp32 products in one instruction (FMUL2); the sums stay scalar FADDs: ptxas contracts mul.f32x2 + add.f32x2
+// into FFMA2 even under -fmad=false, which would round once where ATen rounds twice
+__device__ __forceinline__ void f32x2_mul(unsigned long long a, unsigned long long b, float& lo, float& hi) {
+  unsigned long long r;
+  asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
+  asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(r));
+}
 
 // Only what the taps can reach has to be zero: ring rows 0 and ph + 1 (columns 0 .. pw + 1) and the two ring columns
 // of the rows in between.  Entries past the kept range that a float4 copy of a workspace row drags in are never read.
@@ -527,32 +545,38 @@ __device__ __forceinline__ void upsample_pack_v2(const float* __restrict__ P, fl
     const float* p0 = P + kUpX0 - 1 + min(max(X.i0 - kr.x + 1, 0), pw + 1);
     const float* p1 = P + kUpX0 - 1 + min(max(X.i1 - kr.x + 1, 0), pw + 1);
     __syncwarp();  // the previous word's y pass is done with colT
-    float* ct = colT + lane * kColPitch;
-    int s = 0;
-    for (; s + 4 <= src_rows; s += 4) {
+    float* ct = colT + (lane >> 1) * kPairPitch + (lane & 1);
+    // (source rows in fours: the rows past src_rows hold stale values nobody reads back)
+    for (int s = 0; s < src_rows; s += 4) {
 #pragma unroll
       for (int j = 0; j < 4; ++j)
-        ct[s + j] = __fadd_rn(__fmul_rn(X.l0, p0[(s + j) * kUpPitch]), __fmul_rn(X.l1, p1[(s + j) * kUpPitch]));
+        ct[(s + j) * 2] = __fadd_rn(__fmul_rn(X.l0, p0[(s + j) * kUpPitch]), __fmul_rn(X.l1, p1[(s + j) * kUpPitch]));
     }
-    for (; s < src_rows; ++s) ct[s] = __fadd_rn(__fmul_rn(X.l0, p0[s * kUpPitch]), __fmul_rn(X.l1, p1[s * kUpPitch]));
     __syncwarp();
     // y pass (lane = row)
     for (int r0 = 0; r0 < gh; r0 += 32) {
       const int r = r0 + lane;
       const bool act = r < gh;
       const Lerp Y = lerp_coord(gy0 + (act ? r : 0), sys, mh);
-      const float* c0 = colT + min(max(Y.i0 - kr.y + 1, 0), ph + 1);
-      const float* c1 = colT + min(max(Y.i1 - kr.y + 1, 0), ph + 1);
+      const float* c0 = colT + 2 * min(max(Y.i0 - kr.y + 1, 0), ph + 1);
+      const float* c1 = colT + 2 * min(max(Y.i1 - kr.y + 1, 0), ph + 1);
+      const unsigned long long W0 = f32x2_pack(Y.l0, Y.l0), W1 = f32x2_pack(Y.l1, Y.l1);
       uint32_t word = 0u;
-      // one pixel: two-tap blend, compare, predicated OR of an immediate bit (word |= (v > 0.5f) << x)
-#define HDY_PX(x)                                                                                                  \
-  {                                                                                                                \
-    const float v = __fadd_rn(__fmul_rn(Y.l0, c0[(x) * kColPitch]), __fmul_rn(Y.l1, c1[(x) * kColPitch]));         \
-    asm("{\n\t.reg .pred p;\n\tsetp.gt.f32 p, %1, 0f3F000000;\n\t@p or.b32 %0, %0, %2;\n\t}"                   \
-        : "+r"(word)                                                                                               \
-        : "f"(v), "n"(1u << (x)));                                                                                 \
+      // two pixels: one 64-bit load per tap row, two FMUL2, two FADDs, two compares, two predicated ORs of an
+      // immediate bit (word |= (v > 0.5f) << x)
+#define HDY_SETBIT(v, x)                                                                                          \
+  asm("{\n\t.reg .pred p;\n\tsetp.gt.f32 p, %1, 0f3F000000;\n\t@p or.b32 %0, %0, %2;\n\t}" : "+r"(word) : "f"(v), \
+      "n"(1u << (x)));
+#define HDY_PX2(x)                                                                                                \
+  {                                                                                                               \
+    float a0, a1, b0, b1;                                                                                         \
+    f32x2_mul(W0, *reinterpret_cast<const unsigned long long*>(c0 + ((x) >> 1) * kPairPitch), a0, a1);            \
+    f32x2_mul(W1, *reinterpret_cast<const unsigned long long*>(c1 + ((x) >> 1) * kPairPitch), b0, b1);            \
+    const float v0 = __fadd_rn(a0, b0), v1 = __fadd_rn(a1, b1);                                                   \
+    HDY_SETBIT(v0, (x))                                                                                           \
+    HDY_SETBIT(v1, (x) + 1)                                                                                       \
   }
-#define HDY_G4(g) HDY_PX(g) HDY_PX((g) + 1) HDY_PX((g) + 2) HDY_PX((g) + 3)
+#define HDY_G4(g) HDY_PX2(g) HDY_PX2((g) + 2)
       // groups of four columns, nested so that the warp-uniform exit costs one branch per group
       HDY_G4(0)
       if (vw > 4) {
@@ -577,7 +601,8 @@ __device__ __forceinline__ void upsample_pack_v2(const float* __restrict__ P, fl
         }
       }
 #undef HDY_G4
-#undef HDY_PX
+#undef HDY_PX2
+#undef HDY_SETBIT
       if (vw < 32) word &= (1u << vw) - 1u;  // columns past the window were computed from clamped taps
       if (act) bits[off + (long long)r * wpr + w] = word;
     }
