@@ -395,6 +395,18 @@ __global__ void pm_rows_kernel(int32_t* __restrict__ geom4, int64_t* __restrict_
   off_rows[row] = o;
 }
 
+// smallest dst in [lo, hi) whose first tap lerp_coord(dst).i0 is >= target (hi if there is none)
+__device__ __forceinline__ int first_dst_i0_ge(int target, int lo, int hi, float scale, int in_size) {
+  while (lo < hi) {
+    const int mid = (lo + hi) >> 1;
+    if (lerp_coord(mid, scale, in_size).i0 >= target)
+      hi = mid;
+    else
+      lo = mid + 1;
+  }
+  return lo;
+}
+
 constexpr int kPmTile = 32;               // proto pixels per staged tile side
 constexpr int kPmStage = kPmTile + 1;     // + 1 halo for the second bilinear tap
 constexpr int kPmThreads = 128;
@@ -413,10 +425,14 @@ __global__ void __launch_bounds__(kPmThreads) process_mask_kernel(
     const int32_t* __restrict__ slot_list, const int32_t* __restrict__ list_count) {
   __shared__ float stage[kPmStage * kPmStage];
   __shared__ float cf[64];
-  // slot_list == NULL: CTA b handles slot b.  Otherwise the CTAs share the listed slots (the detections too large for
-  // the two-phase path of mask_regions.cu).
+  // slot_list == NULL: CTA b handles slot b, all of its proto tiles.  Otherwise (2-D grid) the CTAs share the listed
+  // slots -- the detections too large for the patch path of mask_regions.cu -- AND the proto tiles of every slot:
+  // blockIdx.y strides the list, blockIdx.x the 32 x 32 proto tiles of a detection.  A 1 000-px false positive is 60
+  // tiles; walked by one CTA it took longer than the whole patch path of its batch.
   const long long n_items = slot_list ? (long long)*list_count : (long long)gridDim.x;
-  for (long long item = blockIdx.x; item < n_items; item += gridDim.x) {
+  const long long item_first = slot_list ? blockIdx.y : blockIdx.x, item_step = slot_list ? gridDim.y : gridDim.x;
+  const int tile_first = slot_list ? (int)blockIdx.x : 0, tile_step = slot_list ? (int)gridDim.x : 1;
+  for (long long item = item_first; item < n_items; item += item_step) {
   const long long slot = slot_list ? (long long)slot_list[item] : item;
   const int tile = (int)(slot / max_det), d = (int)(slot - (long long)tile * max_det);
   __syncthreads();  // cf / stage of the previous item are free
@@ -440,8 +456,10 @@ __global__ void __launch_bounds__(kPmThreads) process_mask_kernel(
   const float sxs = (float)mw / (float)iw, sys = (float)mh / (float)ih;  // ATen: scale = in / out (fp32)
   // proto range that can contribute: the kept pixels, plus one pixel before (their second-tap neighbours)
   const int ty_begin = upsample ? max(g.py0 - 1, 0) : g.py0, tx_begin = upsample ? max(g.px0 - 1, 0) : g.px0;
-  for (int ty = ty_begin; ty < g.py1; ty += kPmTile) {
-    for (int tx = tx_begin; tx < g.px1; tx += kPmTile) {
+  const int nty = (g.py1 - ty_begin + kPmTile - 1) / kPmTile, ntx = (g.px1 - tx_begin + kPmTile - 1) / kPmTile;
+  for (int tt = tile_first; tt < nty * ntx; tt += tile_step) {
+    {
+      const int ty = ty_begin + (tt / ntx) * kPmTile, tx = tx_begin + (tt % ntx) * kPmTile;
       __syncthreads();
       // ---- stage cropped sigmoid values for proto pixels [ty, ty+33) x [tx, tx+33)
       for (int e = threadIdx.x; e < kPmStage * kPmStage; e += kPmThreads) {
@@ -477,11 +495,17 @@ __global__ void __launch_bounds__(kPmThreads) process_mask_kernel(
           }
         }
       } else {
-        // output pixels of the window whose first taps (i0) fall into [ty, ty+32) x [tx, tx+32)
-        for (int e = threadIdx.x; e < g.w * g.h; e += kPmThreads) {
-          const int oy = g.y0 + e / g.w, ox = g.x0 + e % g.w;
+        // output pixels of the window whose first taps (i0) fall into [ty, ty+32) x [tx, tx+32): i0 is monotone in the
+        // output coordinate, so they form a rectangle whose edges are found by bisection (scanning the whole window
+        // for every tile made a large box quadratic in its tile count)
+        const int oy_lo = first_dst_i0_ge(ty, g.y0, g.y0 + g.h, sys, mh);
+        const int oy_hi = first_dst_i0_ge(ty + kPmTile, oy_lo, g.y0 + g.h, sys, mh);
+        const int ox_lo = first_dst_i0_ge(tx, g.x0, g.x0 + g.w, sxs, mw);
+        const int ox_hi = first_dst_i0_ge(tx + kPmTile, ox_lo, g.x0 + g.w, sxs, mw);
+        const int tw = ox_hi - ox_lo, th = oy_hi - oy_lo;
+        for (int e = threadIdx.x; e < tw * th; e += kPmThreads) {
+          const int oy = oy_lo + e / tw, ox = ox_lo + e % tw;
           const Lerp Y = lerp_coord(oy, sys, mh), X = lerp_coord(ox, sxs, mw);
-          if (Y.i0 < ty || Y.i0 >= ty + kPmTile || X.i0 < tx || X.i0 >= tx + kPmTile) continue;
           const int sy0 = Y.i0 - ty, sx0 = X.i0 - tx, sy1 = Y.i1 - ty, sx1 = X.i1 - tx;
           const float v = bilerp(stage[sy0 * kPmStage + sx0], stage[sy0 * kPmStage + sx1],
                                  stage[sy1 * kPmStage + sx0], stage[sy1 * kPmStage + sx1], X, Y);
@@ -504,7 +528,7 @@ int launch_process_mask_listed(const void* protos, int proto_dtype, const float*
                                float* out_dense, const int64_t* offsets, uint32_t* bits, long long capacity_words,
                                int32_t* status, const int32_t* slot_list, const int32_t* list_count,
                                cudaStream_t st) {
-  const unsigned grid = 148 * 4;
+  const dim3 grid(16, 37);   // x: proto tiles of a detection, y: listed detections (592 CTAs = 4 per SM)
   const float4* b4 = reinterpret_cast<const float4*>(boxes);
   const bool half = proto_dtype == HDY_F16;
 #define HDY_PM(P, H)                                                                                               \
