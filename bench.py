@@ -66,8 +66,9 @@ WORKLOADS = {
     "tiles1024": dict(tile=1024, bs=128, n_cand=3000, conf=0.25, iou=0.45, max_det=3000, nc=4, cap=4096),
     # BASELINE.json configs[3]: whole slide, 1024-px tiles, 64-px overlap, ~3k candidates/tile
     # (148 tiles per batch: the per-tile NMS runs one CTA per tile, one per SM)
-    # (max_det 3328 = 26 x 128: the field holds at most 55 x 55 = 3 025 nuclei per tile, so the cap never binds)
-    "slide": dict(tile=1024, bs=148, n_cand=3000, conf=0.25, iou=0.45, max_det=3328, nc=4, cap=4096, overlap=64),
+    # (the field holds at most 55 x 55 = 3 025 nuclei per tile, so max_det = cap = 3072 never binds)
+    # (cap 3072: the per-tile NMS instance that shares an SM with the filter of the next batch; an overflow raises)
+    "slide": dict(tile=1024, bs=148, n_cand=3000, conf=0.25, iou=0.45, max_det=3072, nc=4, cap=3072, overlap=64),
     # BASELINE.json configs[4]: hnet multi-level heads (RCNN-style 10x structures + 40x nuclei), cross-level merge
     "hnet": dict(tile=1024, bs=16, n_cand=3000, conf=0.25, iou=0.45, max_det=4096, nc=4, cap=4096, overlap=64),
 }

@@ -20,12 +20,17 @@
 //   5. emit      rank-ordered compaction of KEPT boxes, first max_det.
 // Binning only prunes pairs that cannot intersect; every pair that can is tested with hdy_common.cuh's iou_gt
 // (fp32, torchvision's operation order), so cell size and bucket choice never change a verdict.
+#include <stddef.h>
 #include <stdlib.h>
 #include "hdy_common.cuh"
 
 namespace hdy {
 
-constexpr int kFastCap = 4096;
+constexpr int kFastCap = 4096;       // candidates per tile of the full-size instance (168 KB: one CTA per SM)
+constexpr int kFastCapSmall = 3072;  // ... and of the instance that shares an SM: 126 KB leave room for a 93 KB
+                                     // filter CTA, so the HBM-bound filter of the next tile batch (another stream) runs
+                                     // WHILE this latency-bound kernel works -- with the 168 KB instance the two
+                                     // alternate, and the slide's per-tile part was filter + NMS instead of the filter
 constexpr int kFastG = 32;  // torus grid side
 constexpr int kFastNB = kFastG * kFastG + 1;
 constexpr int kMaxDom = 4;
@@ -35,21 +40,29 @@ constexpr float kFastMaxScaled = 16384.0f;
 
 enum : uint8_t { FS_UNKNOWN = 0, FS_KEPT = 1, FS_SUPPRESSED = 2 };
 
-struct FastSmem {
-  uint64_t skey[kFastCap];       // sorted keys (rank order)
-  float4 cbox[kFastCap];         // boxes in cell order (class offset applied)
-  uint16_t crank[kFastCap];      // rank of the box at a cell-order position
-  uint16_t pos[kFastCap];        // rank -> cell-order position (0xffff: degenerate box, KEPT)
-  uint16_t slot[kFastCap];       // rank -> candidate slot (index into the tile's cand_* arrays)
-  uint16_t dom[kFastCap * kMaxDom];
-  uint8_t ndom[kFastCap];
-  uint8_t state[kFastCap];
-  uint8_t frag[kFastCap];        // cell-order position -> has a neighbour whose IoU could cross thr after the shift
+template <int CAP>
+struct FastSmemT {
+  uint64_t skey[CAP];       // sorted keys (rank order)
+  float4 cbox[CAP];         // boxes in cell order (class offset applied)
+  uint16_t crank[CAP];      // rank of the box at a cell-order position
+  uint16_t pos[CAP];        // rank -> cell-order position (0xffff: degenerate box, KEPT)
+  uint16_t slot[CAP];       // rank -> candidate slot (index into the tile's cand_* arrays)
+  uint16_t dom[CAP * kMaxDom];
+  uint8_t ndom[CAP];
+  uint8_t state[CAP];
+  uint8_t frag[CAP];        // cell-order position -> has a neighbour whose IoU could cross thr after the shift
   int cell[kFastNB + 3];
   int warp_i[33];
   float warp_f[2][32];
-  int flags[4];                  // 0: all small cells rank-sorted
+  int flags[4];             // 0: all small cells rank-sorted
 };
+// the radix sort keeps two [32][256] uint16 count buffers in dom (+ the three byte arrays behind it, all unused until
+// the sort is over): 32 KB
+static_assert(sizeof(FastSmemT<kFastCapSmall>::dom) + 3 * kFastCapSmall >= 2 * 32 * 256 * 2 &&
+                  offsetof(FastSmemT<kFastCapSmall>, ndom) ==
+                      offsetof(FastSmemT<kFastCapSmall>, dom) + sizeof(FastSmemT<kFastCapSmall>::dom) &&
+                  offsetof(FastSmemT<kFastCapSmall>, cell) >= offsetof(FastSmemT<kFastCapSmall>, dom) + 2 * 32 * 256 * 2,
+              "radix count buffers must fit behind dom");
 
 template <int THREADS>
 __device__ __forceinline__ int block_excl_scan_cells(int* a, int len, int* warp_tmp) {
@@ -209,8 +222,8 @@ __device__ __forceinline__ void load_sort_store(const uint64_t* __restrict__ gke
 // ballots (stable: item e of lane l is element w*EPW + e*32 + l), leaving per-warp digit counts in `whist`; a column
 // scan over the 32 warps and a 256-entry scan give every (warp, digit) its base; keys and slots are scattered to the
 // other buffer.  ~2.6 k cycles per pass at 4096 keys against ~72 k cycles for the 78-step bitonic network.
-template <int THREADS>
-__device__ __forceinline__ void radix_sort_store(const uint64_t* __restrict__ gkeys, int n_in, FastSmem& S) {
+template <int THREADS, int CAP>
+__device__ __forceinline__ void radix_sort_store(const uint64_t* __restrict__ gkeys, int n_in, FastSmemT<CAP>& S) {
   static_assert(THREADS == 1024, "32 warps, 4 threads per digit in the column scan");
   const int t = threadIdx.x, lane = t & 31, w = t >> 5;
   const int items = (n_in + THREADS - 1) / THREADS;  // 1..4 keys per thread
@@ -221,7 +234,7 @@ __device__ __forceinline__ void radix_sort_store(const uint64_t* __restrict__ gk
   uint16_t* slotA = S.slot;
   uint16_t* slotB = S.crank;
   uint16_t* whist = S.dom;  // [32][256]
-  int* dbase = reinterpret_cast<int*>(S.cbox + kFastCap / 2);  // [256] exclusive digit offsets
+  int* dbase = reinterpret_cast<int*>(S.cbox + CAP / 2);  // [256] exclusive digit offsets
   int* dflag = dbase + 256;   // [128], start-up only
   int* gpart = dbase + 256;   // [4][256] group sums of the column scan
 
@@ -400,7 +413,7 @@ __device__ __forceinline__ int fast_classify(const float4& b, const FastGeom& g,
   return 2;  // also NaN / inf coordinates
 }
 
-template <int THREADS>
+template <int THREADS, int CAP>
 __global__ void __launch_bounds__(THREADS, 1) nms_tiles_smem_kernel(
     const uint64_t* __restrict__ cand_keys, const float4* __restrict__ cand_boxes,
     const float* __restrict__ cand_cls, const int32_t* __restrict__ counts, int cap, float thr, float class_offset,
@@ -409,17 +422,17 @@ __global__ void __launch_bounds__(THREADS, 1) nms_tiles_smem_kernel(
     int32_t* __restrict__ keep_counts, float gray_eps, uint8_t* __restrict__ keep_fragile,
     unsigned long long* __restrict__ phase_cycles, int sort_mode) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
-  FastSmem& S = *reinterpret_cast<FastSmem*>(smem_raw);
+  FastSmemT<CAP>& S = *reinterpret_cast<FastSmemT<CAP>*>(smem_raw);
   // gray zone: pairs that this NMS leaves alone (IoU <= thr in tile coordinates) but whose IoU may exceed thr once both
   // boxes are shifted to slide coordinates and rounded.  Both boxes of such a pair are reported FRAGILE: the slide-level
   // merge must look at them even if they sit in the interior of their tile (interior shortcut).
   const bool gray = keep_fragile != nullptr && gray_eps > 0.f;
   uint8_t* o_frag = keep_fragile ? keep_fragile + (size_t)blockIdx.x * max_det : nullptr;
-  constexpr int MAXR = kFastCap / THREADS;  // ranks owned by one thread
+  constexpr int MAXR = CAP / THREADS;  // ranks owned by one thread
   const int tile = blockIdx.x;
   const int t = threadIdx.x;
   const int n_in = min(counts[tile], cap);
-  if (n_in > kFastCap) return;  // handled by the workspace kernel
+  if (n_in > CAP) return;  // handled by the workspace kernel (the launcher picks CAP >= cap when cap fits an instance)
   int32_t* o_idx = keep_idx + (size_t)tile * max_det;
   int32_t* o_slot = keep_slot + (size_t)tile * max_det;
   float4* o_box = keep_box ? keep_box + (size_t)tile * max_det : nullptr;
@@ -445,9 +458,10 @@ __global__ void __launch_bounds__(THREADS, 1) nms_tiles_smem_kernel(
   mark(-1);
 
   // ---- 1. sort ----------------------------------------------------------------------------------------------
-  static_assert(MAXR == 4, "the sort dispatch below assumes 4 ranks per thread at full capacity");
-  if (sort_mode == 0 && n_in > THREADS)  // the sorting network wins up to 1024 keys (20.7 k vs 22.7 k cycles)
-    radix_sort_store<THREADS>(gkeys, n_in, S);
+  static_assert(MAXR == 4 || MAXR == 3, "the sort dispatch below assumes 3 or 4 ranks per thread at full capacity");
+  // the sorting network wins up to 1024 keys (20.7 k vs 22.7 k cycles); its 4-keys-per-thread form needs 4096 slots
+  if ((sort_mode == 0 && n_in > THREADS) || (MAXR < 4 && n_in > 2 * THREADS))
+    radix_sort_store<THREADS, CAP>(gkeys, n_in, S);
   else if (n_in <= THREADS)
     load_sort_store<THREADS, 1>(gkeys, n_in, S.skey, S.slot);
   else if (n_in <= 2 * THREADS)
@@ -497,7 +511,7 @@ __global__ void __launch_bounds__(THREADS, 1) nms_tiles_smem_kernel(
   }
   for (int i = t; i < kFastNB + 3; i += THREADS) S.cell[i] = 0;
   if (gray)
-    for (int i = t; i < kFastCap; i += THREADS) S.frag[i] = 0;
+    for (int i = t; i < CAP; i += THREADS) S.frag[i] = 0;
   if (t == 0) S.flags[0] = 1;
   __syncthreads();
   FastGeom g;
@@ -781,32 +795,48 @@ __global__ void __launch_bounds__(THREADS, 1) nms_tiles_smem_kernel(
 
 constexpr int kFastThreads = 1024;
 
-int launch_nms_tiles_smem(const uint64_t* cand_keys, const float4* cand_boxes, const float* cand_cls,
-                          const int32_t* counts, int bs, int cap, float thr, float class_offset, int max_nms,
-                          int max_det, int32_t* keep_idx, int32_t* keep_slot, float4* keep_box, float* keep_score,
-                          float* keep_cls, int32_t* keep_counts, float gray_eps, uint8_t* keep_fragile,
-                          unsigned long long* phase_cycles, cudaStream_t stream) {
+template <int CAP>
+static int launch_nms_instance(const uint64_t* cand_keys, const float4* cand_boxes, const float* cand_cls,
+                               const int32_t* counts, int bs, int cap, float thr, float class_offset, int max_nms,
+                               int max_det, int32_t* keep_idx, int32_t* keep_slot, float4* keep_box, float* keep_score,
+                               float* keep_cls, int32_t* keep_counts, float gray_eps, uint8_t* keep_fragile,
+                               unsigned long long* phase_cycles, int sort_mode, cudaStream_t stream) {
   // the attribute is per DEVICE: a process-wide flag would leave every GPU but the first without the opt-in
   static bool attr_set[64] = {};
   int dev_i = 0;
   cudaGetDevice(&dev_i);
   if (dev_i < 0 || dev_i >= 64 || !attr_set[dev_i]) {
-    cudaError_t e = cudaFuncSetAttribute(nms_tiles_smem_kernel<kFastThreads>,
-                                         cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(FastSmem));
+    cudaError_t e = cudaFuncSetAttribute(nms_tiles_smem_kernel<kFastThreads, CAP>,
+                                         cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(FastSmemT<CAP>));
     if (e != cudaSuccess) {
       set_error("cudaFuncSetAttribute(nms_tiles_smem_kernel): %s", cudaGetErrorString(e));
       return HDY_ERR_CUDA;
     }
     if (dev_i >= 0 && dev_i < 64) attr_set[dev_i] = true;
   }
+  nms_tiles_smem_kernel<kFastThreads, CAP><<<(unsigned)bs, kFastThreads, sizeof(FastSmemT<CAP>), stream>>>(
+      cand_keys, cand_boxes, cand_cls, counts, cap, thr, class_offset, max_nms, max_det, keep_idx, keep_slot,
+      keep_box, keep_score, keep_cls, keep_counts, gray_eps, keep_fragile, phase_cycles, sort_mode);
+  return check_launch("hdy_nms_tiles(smem)");
+}
+
+int launch_nms_tiles_smem(const uint64_t* cand_keys, const float4* cand_boxes, const float* cand_cls,
+                          const int32_t* counts, int bs, int cap, float thr, float class_offset, int max_nms,
+                          int max_det, int32_t* keep_idx, int32_t* keep_slot, float4* keep_box, float* keep_score,
+                          float* keep_cls, int32_t* keep_counts, float gray_eps, uint8_t* keep_fragile,
+                          unsigned long long* phase_cycles, cudaStream_t stream) {
   static const int sort_mode = [] {  // HDY_NMS_SORT=bitonic selects the sorting network (A/B runs); default: radix
     const char* v = getenv("HDY_NMS_SORT");
     return (v && v[0] == 'b') ? 1 : 0;
   }();
-  nms_tiles_smem_kernel<kFastThreads><<<(unsigned)bs, kFastThreads, sizeof(FastSmem), stream>>>(
-      cand_keys, cand_boxes, cand_cls, counts, cap, thr, class_offset, max_nms, max_det, keep_idx, keep_slot,
-      keep_box, keep_score, keep_cls, keep_counts, gray_eps, keep_fragile, phase_cycles, sort_mode);
-  return check_launch("hdy_nms_tiles(smem)");
+  // candidate lists of at most 3072 entries take the instance that leaves room for a filter CTA on the same SM
+  if (cap <= kFastCapSmall && !getenv("HDY_NMS_FULL"))
+    return launch_nms_instance<kFastCapSmall>(cand_keys, cand_boxes, cand_cls, counts, bs, cap, thr, class_offset,
+                                              max_nms, max_det, keep_idx, keep_slot, keep_box, keep_score, keep_cls,
+                                              keep_counts, gray_eps, keep_fragile, phase_cycles, sort_mode, stream);
+  return launch_nms_instance<kFastCap>(cand_keys, cand_boxes, cand_cls, counts, bs, cap, thr, class_offset, max_nms,
+                                       max_det, keep_idx, keep_slot, keep_box, keep_score, keep_cls, keep_counts,
+                                       gray_eps, keep_fragile, phase_cycles, sort_mode, stream);
 }
 
 }  // namespace hdy

@@ -91,6 +91,9 @@ class SlidePostprocessor:
     def _append(self, out: DetectBatch, a: int, b: int) -> None:
         t0 = self.tile_range[0]
         self.acc.append(out, self.rois_dev[a - t0:b - t0], rois_host=self.rois[a:b])
+        # a candidate list that outgrew `cap` truncated its tile: carried into the accumulator's status word, which
+        # merge() reads (nobody calls to_list() on the batches of a slide)
+        self.acc.status.bitwise_or_(out.cand_counts[-1:])
         if self.keep_batches:       # the mask pass needs the tile-local boxes and the coefficients again (only those)
             keep = DetectBatch(out.boxes, None, None, None, None, out.extra, None, out.counts, out.cand_counts,
                                out.max_det)

@@ -431,7 +431,8 @@ class SlideAccumulator:
         """Rows appended so far (synchronises); raises on capacity overflow."""
         both = torch.cat([self.cursor, self.status.long()]).cpu()
         if int(both[1]) & _lib.HDY_STATUS_OVERFLOW:
-            raise HdyError(f"slide accumulator overflow: {int(both[0])} rows, capacity {self.capacity}")
+            raise HdyError(f"slide accumulator overflow ({int(both[0])} rows, capacity {self.capacity}), or a tile's "
+                           "candidate list outgrew `cap` (detect_postprocess(cap=...))")
         return int(both[0])
 
     FAR_CAP_PX = 64.0        # boxes sticking out of their tile by more than this are always handled one by one

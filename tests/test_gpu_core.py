@@ -525,3 +525,30 @@ def test_kept_indices_from_raw_logits_match_torch_cuda_reference(cuda_device):
         assert not bad, f"{len(bad)} of {n_tiles} tiles differ from the torch/torchvision CUDA path: {bad[:5]}"
     finally:
         hdy.set_iou_compare("cpu")
+
+
+def test_nms_instances_agree(cuda_device, monkeypatch):
+    """hdy_nms_tiles has two shared-memory instances (3072 candidates: 126 KB, shares an SM with a filter CTA; 4096:
+    168 KB).  The same candidate lists through both give identical survivors, and what the oracle keeps."""
+    spec = hdy.HeadSpec(synth.ANCHORS_3, synth.STRIDES_3, nc=4)
+    dets = synth.nuclei_logits(6, 1024, 4, 2900, seed=31, conf=0.25, generator_device="cuda")
+    ref = None
+    for full in (False, True):
+        if full:
+            monkeypatch.setenv("HDY_NMS_FULL", "1")
+        else:
+            monkeypatch.delenv("HDY_NMS_FULL", raising=False)
+        out = hdy.detect_postprocess(dets, spec, 0.25, 0.45, 3072, cap=3072)
+        assert int(out.cand_counts[-1]) == 0 and int(out.cand_counts[:-1].max()) > 2900
+        got = (out.counts.clone(), out.rows.clone(), out.boxes.clone(), out.scores.clone())
+        kc = got[0].cpu().tolist()
+        if ref is None:
+            ref = got
+            o = _oracle_on_device_decode(hdy.decode_concat([d[:1].contiguous() for d in dets], spec), 4, 0.25, 0.45,
+                                         3072)[0]
+            assert torch.equal(out.boxes[0, :kc[0]].cpu(), o['boxes'])
+        else:
+            assert torch.equal(got[0], ref[0])
+            for i, k in enumerate(kc):
+                assert torch.equal(got[1][i, :k], ref[1][i, :k]) and torch.equal(got[2][i, :k], ref[2][i, :k])
+    monkeypatch.delenv("HDY_NMS_FULL", raising=False)
