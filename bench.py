@@ -998,6 +998,16 @@ def main():
             "pipeline": s["pipeline"], "slide": {k: v for k, v in s.items() if k not in ("stages", "roofline", "e2e")},
             "e2e": s.get("e2e"), "gpu_launches": s["gpu_launches"], "clocks": clocks,
         }
+        if not args.no_sub and args.dtype == "f32":
+            # the same slide with fp16 head outputs -- what the reference's GPU path hands over (half=True,
+            # val_nuclei.py:109,115-116); widened on load, fp32 arithmetic: half the HBM and PCIe bytes
+            hargs = argparse.Namespace(**vars(args))
+            hargs.dtype = "f16"
+            h = run_slide(hargs, wl, c, 2, 2, want_e2e=not args.no_e2e, want_cpu_merge=False, masks=masks,
+                          want_stages=False)
+            line["slide_f16"] = {k: h[k] for k in ("tiles_per_s", "ms_per_slide", "detect_ms", "merge_ms", "masks_ms",
+                                                   "kept", "digest", "mask_digest", "input_bytes", "pipeline", "e2e")
+                                 if k in h}
         if not args.no_sub:
             for name, st, wu in (("tiles640", 100, 10), ("tiles1024", 40, 5)):
                 targs = argparse.Namespace(**vars(args))

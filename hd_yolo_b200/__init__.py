@@ -17,6 +17,7 @@ from .ops import (  # noqa: F401
     nms,
     nms_per_image,
     non_max_suppression,
+    scratch_slot,
     set_iou_compare,
 )
 
@@ -29,6 +30,7 @@ from .masks import (  # noqa: F401,E402
     process_mask,
     process_mask_batch,
     process_mask_packed,
+    SlideMaskBuilder,
 )
 
 from . import slide  # noqa: F401,E402

@@ -227,6 +227,22 @@ def make_match(ref, name, seed):
     _save(name, **arrays)
 
 
+def make_scale_coords(ref, name, seed):
+    """C1: scale_coords + clip_coords of the reference (utils_general.py:161-190), with and without ratio_pad."""
+    g = torch.Generator().manual_seed(seed)
+    arrays = {}
+    cases = [((640, 640), (480, 720), None), ((640, 512), (1080, 810), None), ((320, 320), (100, 333), None),
+             ((640, 640), (500, 375), ((1.28, 1.28), (80.0, 0.0)))]
+    for i, (img1, img0, rp) in enumerate(cases):
+        c = torch.rand((200, 4), generator=g) * torch.tensor([img1[1], img1[0], img1[1], img1[0]]) * 1.2 - 30.0
+        out = ref.scale_coords(img1, c.clone(), img0, rp)
+        arrays[f"in{i}"], arrays[f"out{i}"] = _np(c), _np(out)
+        arrays[f"img1_{i}"], arrays[f"img0_{i}"] = np.array(img1, dtype=np.int64), np.array(img0, dtype=np.int64)
+        arrays[f"rp{i}"] = np.array([rp[0][0], rp[1][0], rp[1][1]] if rp else [0, 0, 0], dtype=np.float64)
+    arrays["n"] = np.int64(len(cases))
+    _save(name, **arrays)
+
+
 def main():
     os.makedirs(OUT, exist_ok=True)
     ref = ref_shim.load()
@@ -238,6 +254,7 @@ def main():
     make_paste(ref, "paste_masks", seed=6)
     make_roi(ref, "roi_align", seed=7)
     make_match(ref, "ap_match", seed=8)
+    make_scale_coords(ref, "scale_coords", seed=9)
 
 
 if __name__ == "__main__":

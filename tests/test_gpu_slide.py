@@ -277,6 +277,18 @@ def test_interior_shortcut_is_exact_far_from_the_origin(cuda_device, thr, seed, 
     assert 0 < n_frag < 0.8 * n_rows
 
 
+def test_scale_coords_vs_reference_golden(cuda_device):
+    """C1 against what the reference's own scale_coords / clip_coords returned (tests/golden/scale_coords.npz)."""
+    g = load_golden("scale_coords")
+    for i in range(int(g["n"])):
+        rp = g[f"rp{i}"].tolist()
+        ratio_pad = ((rp[0], rp[0]), (rp[1], rp[2])) if rp[0] else None
+        c = torch.from_numpy(g[f"in{i}"]).to(cuda_device)
+        out = hs.scale_coords(tuple(g[f"img1_{i}"].tolist()), c, tuple(g[f"img0_{i}"].tolist()), ratio_pad)
+        assert out.data_ptr() == c.data_ptr()                       # in place, like the reference
+        assert torch.equal(out.cpu(), torch.from_numpy(g[f"out{i}"]))
+
+
 def test_interior_shortcut_preconditions_are_enforced(cuda_device):
     """The shortcut is exact only under the conditions its gray-zone flags were produced for: a merge threshold below
     the per-tile NMS threshold, flags for a smaller coordinate range than the slide's, or a re-used accumulator whose

@@ -233,3 +233,62 @@ def test_box_iou_known_answers():
     iou = port.box_iou(a, b)
     assert iou[0, 0] == 0.5 and iou[0, 1] == 0.0
     assert torch.isnan(iou[1, 2])                  # 0 / 0: never `>= 0.5`
+
+
+# ------------------------------------------------------------------------------------------ scale_coords golden
+def _scale_cases():
+    g = load_golden("scale_coords")
+    for i in range(int(g["n"])):
+        rp = g[f"rp{i}"].tolist()
+        ratio_pad = ((rp[0], rp[0]), (rp[1], rp[2])) if rp[0] else None
+        yield (tuple(g[f"img1_{i}"].tolist()), torch.from_numpy(g[f"in{i}"]), tuple(g[f"img0_{i}"].tolist()), ratio_pad,
+               torch.from_numpy(g[f"out{i}"]))
+
+
+def test_scale_coords_port_vs_reference_golden():
+    """C1 (utils_general.py:161-190): the port gives what the reference itself returned (bit for bit)."""
+    n = 0
+    for img1, c, img0, rp, want in _scale_cases():
+        assert torch.equal(port.scale_coords(img1, c.clone(), img0, rp), want)
+        n += 1
+    assert n == 4
+
+
+# ------------------------------------------------------------------------------------------ process_mask known answers
+def test_process_mask_known_answers():
+    """process_mask / crop_mask are upstream ultralytics/yolov5 v7.0 (utils/segment/general.py), which the reference
+    does not contain and this container cannot fetch (no network): the port is a restatement of the published
+    algorithm, PARITY UNPINNED.  What can be pinned are hand-computable consequences of that algorithm:
+      * sigmoid(coef . protos) > 0.5  <=>  coef . protos > 0: with one-hot coefficients the mask is `proto_c > 0`;
+      * crop_mask keeps x1 <= col < x2, y1 <= row < y2 on the box scaled by (mw / iw, mh / ih), fractional edges
+        included exactly as float comparisons against arange (a box edge at 2.5 keeps column 3, not column 2);
+      * upsample: bilinear, align_corners=False, thresholded AFTER the interpolation: a single proto pixel of value 1
+        (sigmoid(+large)) among zeros stays > 0.5 only where its weight exceeds 0.5."""
+    mh = mw = 8
+    protos = torch.full((2, mh, mw), -20.0)
+    protos[0, 2:6, 1:7] = 20.0                  # channel 0: a 4 x 6 blob
+    protos[1, 4, 4] = 20.0                      # channel 1: one pixel
+    coef = torch.tensor([[1.0, 0.0], [0.0, 1.0]])
+    full = torch.tensor([[0.0, 0.0, 32.0, 32.0], [0.0, 0.0, 32.0, 32.0]])
+    m = port.process_mask(protos, coef, full.clone(), (32, 32), upsample=False)
+    assert torch.equal(m[0], (protos[0] > 0).float()) and torch.equal(m[1], (protos[1] > 0).float())
+    # crop: box [10, 6, 22, 18] px at 1/4 scale = [2.5, 1.5, 5.5, 4.5] -> columns 3..5, rows 2..4
+    box = torch.tensor([[10.0, 6.0, 22.0, 18.0]])
+    c = port.process_mask(protos, coef[:1], box.clone(), (32, 32), upsample=False)[0]
+    want = torch.zeros((mh, mw))
+    want[2:5, 3:6] = 1.0
+    assert torch.equal(c, want)
+    # upsample of the single pixel (channel 1, proto (4, 4)): at 4x, output pixel o has src = 0.25 * (o + 0.5) - 0.5; the
+    # weight of proto pixel 4 is 1 - |src - 4| -> > 0.5 for o in 17..18 and exactly 0.5 (not kept) at o = 15.5/19.5: none
+    u = port.process_mask(protos, coef[1:], full[1:].clone(), (32, 32), upsample=True)[0]
+    rows = torch.nonzero(u.sum(1)).flatten().tolist()
+    cols = torch.nonzero(u.sum(0)).flatten().tolist()
+    # weight_y * weight_x > 0.5 (sigmoid(20) ~ 1, sigmoid(-20) ~ 0): per-axis weights are 0.625, 0.875, 0.875, 0.625
+    # for o = 16..19, so the product exceeds 0.5 for the pairs with both weights 0.875 and the mixed 0.875 * 0.625 ones
+    w = {16: 0.625, 17: 0.875, 18: 0.875, 19: 0.625}
+    expect = torch.zeros((32, 32))
+    for y, wy in w.items():
+        for x, wx in w.items():
+            if wy * wx > 0.5:
+                expect[y, x] = 1.0
+    assert torch.equal(u, expect) and rows == [16, 17, 18, 19] and cols == [16, 17, 18, 19]
