@@ -533,14 +533,14 @@ __global__ void merge_fill_kernel(const MergeIn in, const MergeStats* __restrict
 }
 
 // one round of the fixed point over cell-ordered positions
-__global__ void __launch_bounds__(kMergeThreads) merge_round_kernel(const float4* __restrict__ cbox,
+__device__ __forceinline__ void merge_round_body(int bid, int nblk, const float4* __restrict__ cbox,
                                                                     const uint64_t* __restrict__ ckey,
                                                                     uint8_t* cstate, const int* __restrict__ cell,
                                                                     MergeStats* stats, int G, float thr, int round,
                                                                     const uint32_t* __restrict__ blocked,
                                                                     const int32_t* __restrict__ ctile) {
   if (round > 0 && stats->unknown[round - 1] == 0) {
-    if (blockIdx.x == 0 && threadIdx.x == 0) stats->unknown[round] = 0;
+    if (bid == 0 && threadIdx.x == 0) stats->unknown[round] = 0;
     return;
   }
   const int NB = G * G + 1;
@@ -548,7 +548,7 @@ __global__ void __launch_bounds__(kMergeThreads) merge_round_kernel(const float4
   const CellGeom g = cell_geom(stats);
   volatile uint8_t* vstate = cstate;
   int unknown = 0;
-  for (int p = blockIdx.x * blockDim.x + threadIdx.x; p < large_begin; p += gridDim.x * blockDim.x) {
+  for (int p = bid * blockDim.x + threadIdx.x; p < large_begin; p += nblk * blockDim.x) {
     if (vstate[p] != MS_UNKNOWN) continue;
     const float4 bi = cbox[p];
     const uint64_t ki = ckey[p];
@@ -603,7 +603,7 @@ __global__ void __launch_bounds__(kMergeThreads) merge_round_kernel(const float4
 // per entry.  A large box can intersect small boxes whose centre lies within half a cell of it, i.e. the cells
 // [floor((x1 - c/2) / cell), floor((x2 + c/2) / cell)] x [same in y]; the lanes share those cells (the whole grid if
 // the range wraps around the torus, the whole array if the coordinates are not finite) and the large bucket.
-__global__ void __launch_bounds__(kMergeThreads) merge_round_large_kernel(const float4* __restrict__ cbox,
+__device__ __forceinline__ void merge_round_large_body(int bid, int nblk, const float4* __restrict__ cbox,
                                                                           const uint64_t* __restrict__ ckey,
                                                                           uint8_t* cstate, const int* __restrict__ cell,
                                                                           MergeStats* stats, int G, float thr,
@@ -615,7 +615,7 @@ __global__ void __launch_bounds__(kMergeThreads) merge_round_large_kernel(const 
   const CellGeom g = cell_geom(stats);
   volatile uint8_t* vstate = cstate;
   const int lane = threadIdx.x & 31;
-  const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, n_warps = (gridDim.x * blockDim.x) >> 5;
+  const int warp = (bid * blockDim.x + threadIdx.x) >> 5, n_warps = (nblk * blockDim.x) >> 5;
   for (int p = large_begin + warp; p < n_active; p += n_warps) {
     if (vstate[p] != MS_UNKNOWN) continue;  // warp-uniform
     const float4 bi = cbox[p];
@@ -658,6 +658,24 @@ __global__ void __launch_bounds__(kMergeThreads) merge_round_large_kernel(const 
         atomicAdd(&stats->unknown[round], 1);
     }
   }
+}
+
+// One launch per round for both directions that only READ other entries' verdicts: the first nb_small blocks run the
+// small-box round, the rest the large-bucket round (any interleaving is valid: a verdict is only ever taken from a
+// dominator that is already decided, and decided verdicts are final).  Three launches per round were ~25 us each of
+// dependent launch latency -- more than the kernels themselves on a rank's share of an 8-GPU slide.
+__global__ void __launch_bounds__(kMergeThreads) merge_round_both_kernel(const float4* __restrict__ cbox,
+                                                                         const uint64_t* __restrict__ ckey,
+                                                                         uint8_t* cstate, const int* __restrict__ cell,
+                                                                         MergeStats* stats, int G, float thr, int round,
+                                                                         const uint32_t* __restrict__ blocked,
+                                                                         const int32_t* __restrict__ ctile,
+                                                                         int nb_small) {
+  if ((int)blockIdx.x < nb_small)
+    merge_round_body((int)blockIdx.x, nb_small, cbox, ckey, cstate, cell, stats, G, thr, round, blocked, ctile);
+  else
+    merge_round_large_body((int)blockIdx.x - nb_small, (int)gridDim.x - nb_small, cbox, ckey, cstate, cell, stats, G, thr,
+                           round);
 }
 
 // Large -> small direction of a round: ONE WARP per entry of the large bucket that is not SUPPRESSED walks the small
@@ -1480,10 +1498,8 @@ int hdy_merge_rounds(void* workspace, int64_t n_max, float iou_thres, int first_
   for (int r = first_round; r < first_round + n_rounds; ++r) {
     merge_large_push_kernel<<<148 * 2, kMergeThreads, 0, (cudaStream_t)stream>>>(w.cbox, w.ckey, w.cstate, w.cell,
                                                                                  w.stats, w.G, iou_thres, r, w.blocked);
-    merge_round_kernel<<<blocks, kMergeThreads, 0, (cudaStream_t)stream>>>(w.cbox, w.ckey, w.cstate, w.cell, w.stats,
-                                                                           w.G, iou_thres, r, w.blocked, w.ctile);
-    merge_round_large_kernel<<<148 * 2, kMergeThreads, 0, (cudaStream_t)stream>>>(w.cbox, w.ckey, w.cstate, w.cell,
-                                                                                  w.stats, w.G, iou_thres, r);
+    merge_round_both_kernel<<<blocks + 148 * 2, kMergeThreads, 0, (cudaStream_t)stream>>>(
+        w.cbox, w.ckey, w.cstate, w.cell, w.stats, w.G, iou_thres, r, w.blocked, w.ctile, (int)blocks);
   }
   return check_launch("hdy_merge_rounds");
 }
