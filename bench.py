@@ -36,10 +36,9 @@ import time
 ROOT = os.path.dirname(os.path.abspath(__file__))
 if ROOT not in sys.path:
     sys.path.insert(0, ROOT)
-os.environ.setdefault("NCCL_DEBUG", "WARN")   # keep NCCL's version banner off stdout: rank 0 prints ONE JSON line
 
-# ... and when the environment asks for NCCL_DEBUG=VERSION/INFO anyway (or any library writes to fd 1): the JSON line
-# goes to a private duplicate of stdout, everything else that is written to fd 1 lands on stderr.
+# NCCL (NCCL_DEBUG=VERSION/INFO) or any library may write to fd 1: the JSON line goes to a private duplicate of stdout,
+# everything else that is written to fd 1 lands on stderr -- rank 0 prints ONE JSON line whatever the environment asks.
 _JSON_FD = None
 
 
