@@ -51,7 +51,7 @@ from .slide import (  # noqa: F401,E402
 from . import dist, hnet, io, metrics, pipeline, roi  # noqa: F401,E402
 from .io import load_detections, save_detections  # noqa: F401,E402
 from .metrics import APMeter, box_iou, match_predictions  # noqa: F401,E402
-from .roi import batch_rois, multiscale_roi_align, roi_align  # noqa: F401,E402
+from .roi import batch_rois, compute_outputs, multiscale_roi_align, roi_align  # noqa: F401,E402
 from .pipeline import SlidePostprocessor  # noqa: F401,E402
 
 __version__ = "0.1.0"

@@ -916,11 +916,28 @@ int launch_process_mask_regions(const void* protos, int proto_dtype, const float
             map, coef, W.kr, max_det, mh, mw, sxs, sys, rxn, ryn, n_items, W.patches, W.regions, W.done,
             W.work_counter, geom, offsets, bits, capacity_words, status);
     } else {
+      // HDY_PATCH_SMEM=<bytes>: pad the region kernel's shared memory (e.g. 92160: two CTAs per SM instead of three,
+      // which leaves room for an upsample CTA of the previous batch on the same SM -- an A/B knob)
+      size_t psmem = half ? sizeof(RegSmemT<__half>) : sizeof(RegSmemT<float>);
+      if (const char* v = getenv("HDY_PATCH_SMEM")) {
+        const size_t want = (size_t)atol(v);
+        if (want > psmem && want <= 227 * 1024) {
+          psmem = want;
+          e = half ? cudaFuncSetAttribute(proto_patch_kernel<__half>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                          (int)psmem)
+                   : cudaFuncSetAttribute(proto_patch_kernel<float>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                          (int)psmem);
+          if (e != cudaSuccess) {
+            set_error("process_mask(packed) setup: %s", cudaGetErrorString(e));
+            return HDY_ERR_CUDA;
+          }
+        }
+      }
       if (half)
-        proto_patch_kernel<__half><<<(unsigned)n_items, kRegThreads, sizeof(RegSmemT<__half>), stream>>>(
+        proto_patch_kernel<__half><<<(unsigned)n_items, kRegThreads, psmem, stream>>>(
             map, coef, W.kr, counts, max_det, rxn, ryn, W.patches, W.regions);
       else
-        proto_patch_kernel<float><<<(unsigned)n_items, kRegThreads, sizeof(RegSmemT<float>), stream>>>(
+        proto_patch_kernel<float><<<(unsigned)n_items, kRegThreads, psmem, stream>>>(
             map, coef, W.kr, counts, max_det, rxn, ryn, W.patches, W.regions);
       mask_upsample_pack2_kernel<<<(unsigned)((slots + kFuWarps - 1) / kFuWarps), kFuThreads, 0, stream>>>(
           W.patches, W.kr, geom, offsets, slots, mh, mw, sxs, sys, bits, capacity_words, status);

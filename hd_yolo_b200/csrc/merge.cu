@@ -660,22 +660,23 @@ __device__ __forceinline__ void merge_round_large_body(int bid, int nblk, const 
   }
 }
 
-// One launch per round for both directions that only READ other entries' verdicts: the first nb_small blocks run the
-// small-box round, the rest the large-bucket round (any interleaving is valid: a verdict is only ever taken from a
-// dominator that is already decided, and decided verdicts are final).  Three launches per round were ~25 us each of
-// dependent launch latency -- more than the kernels themselves on a rank's share of an 8-GPU slide.
-__global__ void __launch_bounds__(kMergeThreads) merge_round_both_kernel(const float4* __restrict__ cbox,
-                                                                         const uint64_t* __restrict__ ckey,
-                                                                         uint8_t* cstate, const int* __restrict__ cell,
-                                                                         MergeStats* stats, int G, float thr, int round,
-                                                                         const uint32_t* __restrict__ blocked,
-                                                                         const int32_t* __restrict__ ctile,
-                                                                         int nb_small) {
-  if ((int)blockIdx.x < nb_small)
-    merge_round_body((int)blockIdx.x, nb_small, cbox, ckey, cstate, cell, stats, G, thr, round, blocked, ctile);
-  else
-    merge_round_large_body((int)blockIdx.x - nb_small, (int)gridDim.x - nb_small, cbox, ckey, cstate, cell, stats, G, thr,
-                           round);
+// The two read-only directions of a round as kernels of their own.  (Round 2 tried them as ONE launch -- block ranges
+// of a fused kernel -- to save a dependent launch per round at small per-rank sizes: no gain at N = 8, rounds 1.06 ms
+// either way, and 5.8 -> 7.7 ms on one GPU, the small-box part inheriting the large part's register count.)
+__global__ void __launch_bounds__(kMergeThreads) merge_round_kernel(const float4* __restrict__ cbox,
+                                                                    const uint64_t* __restrict__ ckey, uint8_t* cstate,
+                                                                    const int* __restrict__ cell, MergeStats* stats,
+                                                                    int G, float thr, int round,
+                                                                    const uint32_t* __restrict__ blocked,
+                                                                    const int32_t* __restrict__ ctile) {
+  merge_round_body((int)blockIdx.x, (int)gridDim.x, cbox, ckey, cstate, cell, stats, G, thr, round, blocked, ctile);
+}
+__global__ void __launch_bounds__(kMergeThreads) merge_round_large_kernel(const float4* __restrict__ cbox,
+                                                                          const uint64_t* __restrict__ ckey,
+                                                                          uint8_t* cstate, const int* __restrict__ cell,
+                                                                          MergeStats* stats, int G, float thr,
+                                                                          int round) {
+  merge_round_large_body((int)blockIdx.x, (int)gridDim.x, cbox, ckey, cstate, cell, stats, G, thr, round);
 }
 
 // Large -> small direction of a round: ONE WARP per entry of the large bucket that is not SUPPRESSED walks the small
@@ -1498,8 +1499,10 @@ int hdy_merge_rounds(void* workspace, int64_t n_max, float iou_thres, int first_
   for (int r = first_round; r < first_round + n_rounds; ++r) {
     merge_large_push_kernel<<<148 * 2, kMergeThreads, 0, (cudaStream_t)stream>>>(w.cbox, w.ckey, w.cstate, w.cell,
                                                                                  w.stats, w.G, iou_thres, r, w.blocked);
-    merge_round_both_kernel<<<blocks + 148 * 2, kMergeThreads, 0, (cudaStream_t)stream>>>(
-        w.cbox, w.ckey, w.cstate, w.cell, w.stats, w.G, iou_thres, r, w.blocked, w.ctile, (int)blocks);
+    merge_round_kernel<<<blocks, kMergeThreads, 0, (cudaStream_t)stream>>>(w.cbox, w.ckey, w.cstate, w.cell, w.stats,
+                                                                           w.G, iou_thres, r, w.blocked, w.ctile);
+    merge_round_large_kernel<<<148 * 2, kMergeThreads, 0, (cudaStream_t)stream>>>(w.cbox, w.ckey, w.cstate, w.cell,
+                                                                                  w.stats, w.G, iou_thres, r);
   }
   return check_launch("hdy_merge_rounds");
 }

@@ -38,7 +38,7 @@ import torch
 from . import _lib
 
 STATE_UNKNOWN, STATE_KEPT, STATE_SUPPRESSED, STATE_DROPPED, STATE_REMOTE_UNKNOWN = 0, 1, 2, 3, 4
-ROUNDS_PER_EXCHANGE = 2      # two launches per round; nuclei settle in ~3 rounds, a seam row needs its owner's verdict first
+ROUNDS_PER_EXCHANGE = 2      # nuclei settle in ~3 rounds; a seam row needs its owner's verdict first
 EXCHANGES_PER_READ = 2
 MAX_ROUNDS = 64
 HDR, FAR_W, ROW_W, META_W = (_lib.HDY_SEAM_HDR_WORDS, _lib.HDY_SEAM_FAR_WORDS, _lib.HDY_SEAM_ROW_WORDS,
@@ -238,7 +238,7 @@ class DeviceSeamBackend:
                 self.conf, self.iou, p(self.state), p(self.ws), self.wbytes, self._st(), launches=7)
 
     def rounds(self, first: int, n: int) -> None:
-        self._c("hdy_merge_rounds", _lib.ptr(self.ws), self.n_max, self.iou, first, n, self._st(), launches=2 * n)
+        self._c("hdy_merge_rounds", _lib.ptr(self.ws), self.n_max, self.iou, first, n, self._st(), launches=3 * n)
 
     def export(self) -> torch.Tensor:
         p = _lib.ptr

@@ -16,7 +16,7 @@ from . import _lib
 from ._lib import HdyError, ptr
 from .ops import DetectBatch, _call, _need_cuda, _stream
 
-__all__ = ["multiscale_roi_align", "roi_align", "batch_rois"]
+__all__ = ["multiscale_roi_align", "roi_align", "batch_rois", "compute_outputs"]
 
 
 def _levels(features: Sequence[torch.Tensor], scales: Sequence[float]):
@@ -102,3 +102,41 @@ def batch_rois(batch: DetectBatch, counts_host: Optional[Sequence[int]] = None):
     if not rows:
         return torch.zeros((0, 5), dtype=torch.float32, device=dev), torch.zeros((0,), dtype=torch.float32, device=dev)
     return torch.cat(rows), torch.cat(lv)
+
+
+def compute_outputs(dets: List[torch.Tensor], spec, features: Optional[List[torch.Tensor]] = None,
+                    compute_masks: bool = True, seg_h=None, mask_indices: Optional[torch.Tensor] = None,
+                    nms_params: Optional[dict] = None, mask_output_size: int = 28, aligned: bool = False,
+                    multi_label: bool = False, hier_ops=None, layout: int = 0):
+    """Detect.compute_outputs (yolo_head.py:301-355), composed: level concat + nms_per_image (:311-318), the
+    `proposals` / `levels` pair (:320-328), multiscale_roi_align (:329), the mask head (:330, `seg_h`: the reference's
+    own PyTorch module -- convolutions are not part of this package), sigmoid + per-label channel select (:331, 346-353),
+    hierarchical scores + score / label select (:335-345).
+
+    dets: the head's RAW level tensors ([bs,na,ny,nx,no] logits -- the decode of compute_proposals is fused in);
+    features: the `seg` feature maps, one [bs, C, h_i, w_i] per level (needed with compute_masks); mask_indices:
+    Detect.mask_indices ([1+nc] int64: channel of the mask head per label, < 0 = no mask); nms_params as
+    Detect.get_nms_params returns them.  Returns the reference's List[Dict{'boxes','scores','labels'[, 'masks' [k,1,M,M]]}].
+    The reference's `r['labels'].clamp(min=0.)` (:348) raises on torch >= 2 (a float clamp of an int64 tensor cannot
+    index); the integer clamp it means is what runs here."""
+    from .masks import mask_select
+    from .ops import detect_postprocess
+    p = {'conf_thres': 0.15, 'iou_thres': 0.45, 'max_det': 300}
+    p.update(nms_params or {})
+    batch = detect_postprocess(dets, spec, p['conf_thres'], p['iou_thres'], int(p['max_det']), layout=layout,
+                               hier_ops=hier_ops)
+    counts = batch.counts.cpu().tolist()       # the reference synchronises here too (n_obj_per_image, :318)
+    results = batch.to_list(multi_label=multi_label, conf_thres=p['conf_thres'])
+    if not compute_masks or multi_label or sum(counts) == 0:
+        return results
+    if features is None or seg_h is None or mask_indices is None:
+        raise HdyError("compute_masks=True needs the seg feature maps, the seg_h module and mask_indices")
+    proposals, levels = batch_rois(batch, counts)
+    mask_features = multiscale_roi_align(features, proposals, levels, spec.strides, mask_output_size // 2, 2, aligned)
+    mask_logits = seg_h(mask_features)                                   # the reference's mask head, PyTorch
+    labels = torch.cat([r['labels'] for r in results])
+    masks = mask_select(mask_logits.float().contiguous(), labels, mask_indices)   # sigmoid + channel pick + zeroing
+    for r, m in zip(results, masks.split(counts, 0)):
+        if len(r['boxes']):
+            r['masks'] = m
+    return results

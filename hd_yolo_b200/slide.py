@@ -143,7 +143,7 @@ def merge_nms(boxes: torch.Tensor, scores: torch.Tensor, conf_thres: float, iou_
               ptr(cores) if use_cores else None, ptr(dirty) if use_cores else None,
               ptr(margin) if use_cores else None, ptr(n_dev), n,
               _conf_thr_f32(conf_thres), _iou_thr_f32(iou_thres), rounds, ptr(state), ptr(status), ptr(ws), wbytes,
-              _stream(), launches=8 + 2 * rounds)
+              _stream(), launches=8 + 3 * rounds)
         if not int(status.item()) & _lib.HDY_STATUS_ROUNDS:
             return state
         if rounds >= 64:

@@ -149,3 +149,46 @@ def test_match_predictions_ties_and_capacity(cuda_device):
     assert len(got['ious']) == k * n_gt and bool((got['ious'] == 1.0).all())
     idx = torch.arange(k * n_gt)
     assert torch.equal(got['pred_idx'].cpu(), idx // n_gt) and torch.equal(got['true_idx'].cpu(), idx % n_gt)
+
+
+def test_compute_outputs_with_masks_composed(cuda_device):
+    """Detect.compute_outputs(compute_masks=True) (yolo_head.py:301-355) end to end: fused decode + nms_per_image, the
+    proposals / levels pair, multiscale RoIAlign, the reference's own mask head (a PyTorch module, here two small
+    convolutions), sigmoid + per-label channel select.  Checker: the oracle composition on the device-decoded rows
+    (the reference's own :348 raises on torch >= 2; the port restates it with the integer clamp it means)."""
+    import torch.nn as nn
+    from hd_yolo_b200 import synth
+    torch.manual_seed(11)
+    torch.backends.cudnn.allow_tf32 = False
+    dev = cuda_device
+    nc, C = 4, 8
+    spec = hdy.HeadSpec(synth.ANCHORS_3, synth.STRIDES_3, nc=nc)
+    dets = synth.nuclei_logits(2, 320, nc, 250, seed=4, conf=0.25)
+    feats = [torch.randn((2, C, 320 // s, 320 // s)) for s in synth.STRIDES_3]
+    seg_h = nn.Sequential(nn.Conv2d(C, C, 3, padding=1), nn.ReLU(), nn.ConvTranspose2d(C, C, 2, 2), nn.ReLU(),
+                          nn.Conv2d(C, 2, 1)).eval()
+    mask_indices = torch.tensor([-1, 0, 0, 1, 1])
+    params = {'conf_thres': 0.25, 'iou_thres': 0.45, 'max_det': 300}
+    with torch.no_grad():
+        got = hdy.compute_outputs([d.to(dev) for d in dets], spec, [f.to(dev) for f in feats], True,
+                                  seg_h=seg_h.to(dev), mask_indices=mask_indices.to(dev), nms_params=params)
+        seg_h = seg_h.cpu()
+        cat = hdy.decode_concat([d.to(dev) for d in dets], spec).cpu()
+        outs = port.nms_per_image(cat, nc, 0.25, 0.45, 300)
+        n_masks = 0
+        for i, (g, o) in enumerate(zip(got, outs)):
+            s, l = port.select_scores(o['scores'].clone(), 0.25, port.default_descendants(nc))
+            assert torch.equal(g['boxes'].cpu(), o['boxes']) and torch.equal(g['labels'].cpu(), l)
+            assert torch.equal(g['scores'].cpu(), s)
+            k = len(o['boxes'])
+            assert k > 50
+            rois = torch.nn.functional.pad(o['boxes'], [1, 0], value=float(i))
+            mf = port.multiscale_roi_align(feats, rois, o['extra'][:, 0], synth.STRIDES_3)
+            ref = port.mask_select(seg_h(mf), l, mask_indices)
+            assert g['masks'].shape == (k, 1, 28, 28)
+            assert float((g['masks'].cpu() - ref).abs().max()) < 2e-5
+            assert float(g['masks'].cpu()[l < 0].abs().sum()) == 0.0      # unclassified (-100 -> index -1): no mask
+            n_masks += k
+    assert n_masks > 100
+    no_masks = hdy.compute_outputs([d.to(dev) for d in dets], spec, compute_masks=False, nms_params=params)
+    assert all('masks' not in r for r in no_masks) and len(no_masks) == 2
