@@ -78,7 +78,7 @@ def _plant_far_boxes(dets, where):
         big[b, 2, gy, gx, :5] = torch.log(sig / (1 - sig))
 
 
-@pytest.mark.parametrize("world,far", [(2, False), (3, True), (4, True)])
+@pytest.mark.parametrize("world,far", [(2, False), (3, True), (4, True), (8, True)])   # 8 ranks, 6 tile rows: two idle
 def test_sharded_ranks_match_single_rank_with_shortcut(cuda_device, world, far):
     """SlidePostprocessor(world=W, rank=r) for every r -- through pipeline.merge's multi-rank branch with the interior
     shortcut, seam blocks, far lists and dirty tiles -- gives, row for row, the verdicts of the world=1 run and of the
@@ -124,6 +124,7 @@ def test_sharded_ranks_match_single_rank_with_shortcut(cuda_device, world, far):
     assert torch.equal(state, ref1['state'])
     assert fold_digest(sum(p['digest'] for p in parts)) == fold_digest(kept_digest(ref1['state'], 0))
     assert sum(sum(p['seam_rows']) for p in parts) > 0 and all(p['exchanges'] >= 2 for p in parts)
+    assert world < 8 or sum(int(p['n']) == 0 for p in parts) == 2
     # survivors: every rank's list is score-descending; their union is the single-rank list
     for p in parts:
         assert bool((p['scores'][1:] <= p['scores'][:-1]).all())
