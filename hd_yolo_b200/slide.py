@@ -478,7 +478,7 @@ class SlideAccumulator:
             if self.gray_eps < need:
                 raise HdyError(f"interior_shortcut: the gray-zone flags cover a rounding of {self.gray_eps:g} px per "
                                f"coordinate, slide coordinates up to {top:g} round by up to {need:g}")
-        if self.gray_eps > 0.004:
+        if self.rois and self.gray_eps > 0.004:        # (a rank without tiles has appended nothing: nothing to check)
             raise HdyError("interior_shortcut: gray_eps above 0.004 px exceeds the binning margins of the per-tile NMS")
 
     def verdicts(self, conf_thres: float, iou_thres: float, interior_shortcut: bool = False) -> torch.Tensor:
