@@ -528,7 +528,10 @@ int launch_process_mask_listed(const void* protos, int proto_dtype, const float*
                                float* out_dense, const int64_t* offsets, uint32_t* bits, long long capacity_words,
                                int32_t* status, const int32_t* slot_list, const int32_t* list_count,
                                cudaStream_t st) {
-  const dim3 grid(16, 37);   // x: proto tiles of a detection, y: listed detections (592 CTAs = 4 per SM)
+  // x: proto tiles of a detection, y: listed detections.  The list is short (a few background false positives per
+  // batch of 148 tiles) and each item large (up to 64 proto tiles): the call's duration is the longest item's walk, so
+  // one CTA per tile of the largest box (64 x 9 = 576 CTAs; those without a tile leave after reading the geometry)
+  const dim3 grid(64, 9);
   const float4* b4 = reinterpret_cast<const float4*>(boxes);
   const bool half = proto_dtype == HDY_F16;
 #define HDY_PM(P, H)                                                                                               \

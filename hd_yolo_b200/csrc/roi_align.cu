@@ -24,27 +24,13 @@
 //   * results go through a shared staging tile and leave as coalesced 128-bit stores (the chunk's 32 x M x M floats
 //     are contiguous in the output).
 #include <limits.h>
-#include "hdy_common.cuh"
+#include "roi_align_common.cuh"
 
 namespace hdy {
 
 constexpr int kRoiChunk = 32;        // channels per CTA
 constexpr int kRoiPairs = kRoiChunk / 2;
-constexpr int kRoiMaxM = 16;         // pooled size
-constexpr int kRoiMaxS = 4;          // sampling ratio
 constexpr int kWinMax = 168;         // staged window floats per channel (e.g. 12 x 14)
-
-struct RoiLevels {
-  const float* data[HDY_MAX_LEVELS];
-  int h[HDY_MAX_LEVELS], w[HDY_MAX_LEVELS];
-  float scale[HDY_MAX_LEVELS];
-  int nl;
-};
-
-struct SampleTab {
-  int low, high;
-  float l, h;
-};
 
 struct RoiSmem {
   SampleTab ytab[kRoiMaxM * kRoiMaxS];
@@ -53,33 +39,6 @@ struct RoiSmem {
   float win[kRoiChunk * kWinMax];
   float stage[kRoiChunk * kRoiMaxM * kRoiMaxM];
 };
-
-// One axis of torchvision's pre_calc_for_bilinear_interpolate (roi_align_common.h): sample `i` of bin `p`.
-__device__ __forceinline__ SampleTab roi_sample(float start, float bin, int p, int i, int grid, int size) {
-  float v = __fadd_rn(__fadd_rn(start, __fmul_rn((float)p, bin)),
-                      __fdiv_rn(__fmul_rn(__fadd_rn((float)i, 0.5f), bin), (float)grid));
-  SampleTab t;
-  if (!(v >= -1.0f && v <= (float)size)) {  // also NaN: the reference's `v < -1 || v > size` is false for NaN, but a
-    t.low = -1;                             // NaN coordinate is outside the contract (finite boxes)
-    t.high = -1;
-    t.l = 0.f;
-    t.h = 0.f;
-    return t;
-  }
-  if (v <= 0.f) v = 0.f;
-  int low = (int)v, high;
-  if (low >= size - 1) {
-    high = low = size - 1;
-    v = (float)low;
-  } else {
-    high = low + 1;
-  }
-  t.low = low;
-  t.high = high;
-  t.l = __fsub_rn(v, (float)low);
-  t.h = __fsub_rn(1.0f, t.l);
-  return t;
-}
 
 template <int S, bool STAGED>
 __device__ __forceinline__ void roi_rows(const RoiSmem& Sm, const float* __restrict__ base, int plane, int pitch,
@@ -153,15 +112,12 @@ __device__ __forceinline__ void roi_rows(const RoiSmem& Sm, const float* __restr
   }
 }
 
+// one (RoI, 32-channel chunk); every thread of the CTA calls it
 template <int S>
-__global__ void __launch_bounds__(kRoiPairs* kRoiMaxM, S <= 2 ? 3 : 1) roi_align_levels_kernel(
-    const RoiLevels L, int bs, int C, const float* __restrict__ rois, const float* __restrict__ level_of, int M,
-    int aligned, float* __restrict__ out) {
-  extern __shared__ __align__(16) unsigned char roi_smem_raw[];
-  RoiSmem& Sm = *reinterpret_cast<RoiSmem*>(roi_smem_raw);
+__device__ __forceinline__ void roi_align_one(RoiSmem& Sm, const RoiLevels& L, int bs, int C,
+                                              const float* __restrict__ rois, const float* __restrict__ level_of,
+                                              int M, int aligned, float* __restrict__ out, long long n, int cbase) {
   const int t = threadIdx.x, lane = t & 31, warp = t >> 5;
-  const long long n = blockIdx.x;
-  const int cbase = blockIdx.y * kRoiChunk;
   const int nch = min(kRoiChunk, C - cbase);
   const int MM = M * M;
   float* o = out + ((size_t)n * C + cbase) * MM;
@@ -260,24 +216,31 @@ __global__ void __launch_bounds__(kRoiPairs* kRoiMaxM, S <= 2 ? 3 : 1) roi_align
   }
 }
 
-}  // namespace hdy
+// only == NULL: CTA x = RoI.  Otherwise only[0] RoIs listed in only[1..] (what the tensor-core path of
+// roi_align_tc.cu left: windows over 6 x 6 taps), strided by the CTAs.
+template <int S>
+__global__ void __launch_bounds__(kRoiPairs* kRoiMaxM, S <= 2 ? 3 : 1) roi_align_levels_kernel(
+    const RoiLevels L, int bs, int C, const float* __restrict__ rois, const float* __restrict__ level_of, int M,
+    int aligned, float* __restrict__ out, const int32_t* __restrict__ only) {
+  extern __shared__ __align__(16) unsigned char roi_smem_raw[];
+  RoiSmem& Sm = *reinterpret_cast<RoiSmem*>(roi_smem_raw);
+  const int cbase = blockIdx.y * kRoiChunk;
+  if (!only) {
+    roi_align_one<S>(Sm, L, bs, C, rois, level_of, M, aligned, out, (long long)blockIdx.x, cbase);
+    return;
+  }
+  const int count = only[0];
+  for (int i = blockIdx.x; i < count; i += gridDim.x) {
+    roi_align_one<S>(Sm, L, bs, C, rois, level_of, M, aligned, out, (long long)only[1 + i], cbase);
+    __syncthreads();  // the tables and staging tiles are re-used
+  }
+}
 
-extern "C" int hdy_multiscale_roi_align(const hdy_feature_level_t* levels_host, int nl, int bs, int channels,
-                                        const float* rois, const float* level_of, int64_t K, int pooled,
-                                        int sampling_ratio, int aligned, float* out, hdy_stream_t stream) {
-  using namespace hdy;
+
+int roi_levels_from_host(const hdy_feature_level_t* levels_host, int nl, RoiLevels* Lp) {
   HDY_REQUIRE(levels_host != nullptr, "roi_align: levels is NULL");
   HDY_REQUIRE(nl >= 1 && nl <= HDY_MAX_LEVELS, "roi_align: nl=%d out of range [1,%d]", nl, HDY_MAX_LEVELS);
-  HDY_REQUIRE(bs >= 1 && channels >= 1, "roi_align: bs=%d channels=%d", bs, channels);
-  HDY_REQUIRE(pooled >= 1 && pooled <= kRoiMaxM, "roi_align: output size %d out of range [1,%d]", pooled, kRoiMaxM);
-  HDY_REQUIRE(sampling_ratio >= 1 && sampling_ratio <= kRoiMaxS,
-              "roi_align: sampling_ratio=%d out of range [1,%d] (the adaptive grid of sampling_ratio<=0 is not on the "
-              "reference's path)", sampling_ratio, kRoiMaxS);
-  HDY_REQUIRE(K >= 0 && K < (1ll << 31), "roi_align: K out of range");
-  if (K == 0) return HDY_OK;
-  HDY_REQUIRE(rois != nullptr && out != nullptr, "roi_align: NULL pointer");
-  HDY_REQUIRE(nl == 1 || level_of != nullptr, "roi_align: level ids required with more than one level");
-  RoiLevels L;
+  RoiLevels& L = *Lp;
   memset(&L, 0, sizeof(L));
   L.nl = nl;
   for (int i = 0; i < nl; ++i) {
@@ -289,12 +252,32 @@ extern "C" int hdy_multiscale_roi_align(const hdy_feature_level_t* levels_host, 
     L.w[i] = levels_host[i].w;
     L.scale[i] = levels_host[i].spatial_scale;
   }
+  return HDY_OK;
+}
+
+int roi_align_args_ok(int bs, int channels, const float* rois, const float* level_of, int nl, int64_t K, int pooled,
+                      int sampling_ratio, const float* out) {
+  HDY_REQUIRE(bs >= 1 && channels >= 1, "roi_align: bs=%d channels=%d", bs, channels);
+  HDY_REQUIRE(pooled >= 1 && pooled <= kRoiMaxM, "roi_align: output size %d out of range [1,%d]", pooled, kRoiMaxM);
+  HDY_REQUIRE(sampling_ratio >= 1 && sampling_ratio <= kRoiMaxS,
+              "roi_align: sampling_ratio=%d out of range [1,%d] (the adaptive grid of sampling_ratio<=0 is not on the "
+              "reference's path)", sampling_ratio, kRoiMaxS);
+  HDY_REQUIRE(K >= 0 && K < (1ll << 31), "roi_align: K out of range");
+  if (K == 0) return HDY_OK;
+  HDY_REQUIRE(rois != nullptr && out != nullptr, "roi_align: NULL pointer");
+  HDY_REQUIRE(nl == 1 || level_of != nullptr, "roi_align: level ids required with more than one level");
+  return HDY_OK;
+}
+
+// the exact-order kernel over all RoIs (only == NULL) or over those with only[n] != 0
+int launch_roi_align_exact(const RoiLevels& L, int bs, int channels, const float* rois, const float* level_of,
+                           int64_t K, int pooled, int sampling_ratio, int aligned, float* out, const int32_t* only,
+                           cudaStream_t st) {
   const int chunks = (channels + kRoiChunk - 1) / kRoiChunk;
   HDY_REQUIRE(chunks <= 65535, "roi_align: too many channels");
   const int threads = ((kRoiPairs * pooled + 31) / 32) * 32;
-  const dim3 grid((unsigned)K, (unsigned)chunks);
+  const dim3 grid((unsigned)(only ? (K < 1184 ? K : 1184) : K), (unsigned)chunks);
   const size_t smem = sizeof(RoiSmem);
-  cudaStream_t st = (cudaStream_t)stream;
 #define HDY_ROI(SS)                                                                                                  \
   do {                                                                                                               \
     cudaError_t e = cudaFuncSetAttribute(roi_align_levels_kernel<SS>, cudaFuncAttributeMaxDynamicSharedMemorySize,   \
@@ -303,7 +286,8 @@ extern "C" int hdy_multiscale_roi_align(const hdy_feature_level_t* levels_host, 
       set_error("roi_align setup: %s", cudaGetErrorString(e));                                                       \
       return HDY_ERR_CUDA;                                                                                           \
     }                                                                                                                \
-    roi_align_levels_kernel<SS><<<grid, threads, smem, st>>>(L, bs, channels, rois, level_of, pooled, aligned, out); \
+    roi_align_levels_kernel<SS><<<grid, threads, smem, st>>>(L, bs, channels, rois, level_of, pooled, aligned, out,  \
+                                                             only);                                                  \
   } while (0)
   switch (sampling_ratio) {
     case 1: HDY_ROI(1); break;
@@ -313,4 +297,19 @@ extern "C" int hdy_multiscale_roi_align(const hdy_feature_level_t* levels_host, 
   }
 #undef HDY_ROI
   return check_launch("hdy_multiscale_roi_align");
+}
+
+}  // namespace hdy
+
+extern "C" int hdy_multiscale_roi_align(const hdy_feature_level_t* levels_host, int nl, int bs, int channels,
+                                        const float* rois, const float* level_of, int64_t K, int pooled,
+                                        int sampling_ratio, int aligned, float* out, hdy_stream_t stream) {
+  using namespace hdy;
+  RoiLevels L;
+  int rc = roi_levels_from_host(levels_host, nl, &L);
+  if (rc) return rc;
+  rc = roi_align_args_ok(bs, channels, rois, level_of, nl, K, pooled, sampling_ratio, out);
+  if (rc || K == 0) return rc;
+  return launch_roi_align_exact(L, bs, channels, rois, level_of, K, pooled, sampling_ratio, aligned, out, nullptr,
+                                (cudaStream_t)stream);
 }

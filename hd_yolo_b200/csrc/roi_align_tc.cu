@@ -1,0 +1,386 @@
+// Multi-scale RoIAlign on the 5th-generation tensor cores (tcgen05, accumulators in TMEM): the selectable fast form of
+// roi_align.cu for callers that accept the north star's 1e-5 relative tolerance instead of torchvision's exact
+// operation order.
+//
+// Reference: Detect.multiscale_roi_align, metayolo/models/yolo_head.py:279-299 (torchvision.ops.roi_align per level,
+// sampling_ratio = 2, aligned = False, output 14 x 14, 256 channels).
+//
+// Why tensor cores here (and not in the mask kernels): per RoI the op writes C*M*M*4 = 200 KB and reads a ~6 x 6 window
+// of every channel, so the bound is the HBM write -- but the exact-order kernel needs 77 warp instructions per output
+// (ncu: issue slots 73 % busy, DRAM 15 %, profiles/r01_i_roi_align.md).  Bilinear sampling + averaging is linear in the
+// window: out[bin][c] = sum_k W[bin][k] * F[k][c] with W = (mean over the S samples of the y weights) x (the same for
+// x), a [M*M x 36] matrix per RoI that all 256 channels share.  That is a 196 x 36 x 256 GEMM per RoI.
+//
+// Arithmetic: 3xTF32.  Both operands are split  v = hi + lo  (hi = cvt.rna.tf32(v), lo = cvt.rna.tf32(v - hi), both
+// exactly representable, so the tensor core's own input conversion changes nothing) and D = Alo*Bhi + Ahi*Blo + Ahi*Bhi
+// accumulates in fp32: the dropped lo*lo term and the rounding of lo are each <= 2^-22 relative per product.
+//
+// B200 mapping, one CTA per RoI at a time (persistent grid, 2 CTAs per SM so one CTA's operand build overlaps the
+// other's MMAs and epilogue):
+//   * sample tables exactly as the exact kernel builds them (roi_align_common.cuh), reduced to per-axis weights
+//     wy[M][6], wx[M][6] over the RoI's tap window (<= 6 x 6 feature pixels: nuclei; larger windows are appended to a
+//     list and done by the exact kernel afterwards);
+//   * A = W [196 (-> 2 x M128) x 40] and, per half of the channels, B = F [128 x 40], both hi and lo, written by the
+//     threads straight into the no-swizzle K-major core-matrix layout the shared-memory descriptors describe
+//     (8 rows x 16 B core matrices; SBO = 128 B between row groups, LBO = the K-chunk pitch);
+//   * one thread issues 3 terms x 2 M tiles x 5 K steps of tcgen05.mma.kind::tf32 (128 x 128 x 8) and commits to an
+//     mbarrier;
+//   * epilogue: tcgen05.ld 32x32b.x32 (lane = output bin, column = channel) and coalesced streaming stores -- the bins
+//     of a channel are contiguous in the output, so a warp writes 128 B per register.
+#include <limits.h>
+#include "roi_align_common.cuh"
+
+namespace hdy {
+
+int roi_align_args_ok(int bs, int channels, const float* rois, const float* level_of, int nl, int64_t K, int pooled,
+                      int sampling_ratio, const float* out);
+int launch_roi_align_exact(const RoiLevels& L, int bs, int channels, const float* rois, const float* level_of,
+                           int64_t K, int pooled, int sampling_ratio, int aligned, float* out, const int32_t* only,
+                           cudaStream_t st);
+
+constexpr int kTcThreads = 256;
+constexpr int kTcSpan = 6;                      // tap window per axis on the tensor-core path
+constexpr int kTcK = 40;                        // 36 window pixels, padded to whole K steps of 8
+constexpr int kTcKc = kTcK / 4;                 // 16-byte K chunks
+constexpr int kTcKSteps = kTcK / 8;
+constexpr int kTcRows = 200;                    // A rows held (bins <= 196 in 25 groups of 8); see the over-read note
+constexpr int kTcN = 64;                        // channels per MMA (N): one slice of the RoI's channels
+constexpr int kTcALbo = kTcRows * 16;           // bytes between the K chunks of A
+constexpr int kTcBLbo = kTcN * 16 + 16;         // ... of B; +16: a channel's consecutive k land in consecutive banks
+constexpr int kTcABytes = kTcKc * kTcALbo;      // 32 000
+constexpr int kTcBBytes = kTcKc * kTcBLbo;      // 10 400
+constexpr int kTcCols = 256;                    // TMEM columns: 2 accumulator buffers x 2 M tiles x 64 channels (fp32)
+// Over-read: the second M tile's descriptor covers rows 128..255 but only rows < bins are written.  What the MMA reads
+// past row 199 of a chunk is the next chunk / the next buffer (A_hi -> A_lo -> B_hi, all inside this CTA's shared
+// memory): finite or not, it only reaches accumulator rows >= bins, which nobody loads.
+static_assert(kTcKc * kTcALbo + 56 * 16 <= kTcABytes + kTcBBytes, "over-read of the last A chunk stays inside smem");
+
+struct TcTables {
+  SampleTab ytab[kRoiMaxM * kRoiMaxS];
+  SampleTab xtab[kRoiMaxM * kRoiMaxS];
+  float wy[kRoiMaxM][8];
+  float wx[kRoiMaxM][8];
+  unsigned long long mbar;
+  int ylo, yhi, xlo, xhi;
+  uint32_t tmem_base;
+};
+constexpr size_t kTcSmem = 2 * kTcABytes + 2 * kTcBBytes + sizeof(TcTables);
+static_assert(kTcSmem <= 113 * 1024, "two CTAs per SM");
+
+// round to nearest tf32 (10 mantissa bits; ties away from zero, like cvt.rna.tf32.f32) with two integer-pipe
+// instructions: the cvt runs on the quarter-rate conversion pipe and was 16 % of the kernel's stall samples
+__device__ __forceinline__ float tf32_rna(float v) {
+  return __uint_as_float((__float_as_uint(v) + 0x1000u) & 0xFFFFE000u);
+}
+
+// shared-memory matrix descriptor: K-major, no swizzle, version 1 (sm_100)
+__device__ __forceinline__ uint64_t tc_desc(uint32_t smem_addr, uint32_t lbo, uint32_t sbo) {
+  return (uint64_t)((smem_addr & 0x3FFFFu) >> 4) | ((uint64_t)(lbo >> 4) << 16) | ((uint64_t)(sbo >> 4) << 32) |
+         (1ull << 46);
+}
+
+// instruction descriptor: D fp32 (bits 4-5 = 1), A and B tf32 (bits 7-9, 10-12 = 2), both K-major, N >> 3 at bit 17,
+// M >> 4 at bit 24
+constexpr uint32_t kTcIdesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(kTcN >> 3) << 17) | ((128u >> 4) << 24);
+
+__device__ __forceinline__ void tc_mma(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t"
+      "}\n" ::"r"(d_tmem),
+      "l"(adesc), "l"(bdesc), "r"(kTcIdesc), "r"(accumulate)
+      : "memory");
+}
+
+__device__ __forceinline__ void tc_ld32(uint32_t taddr, uint32_t (&v)[32]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];\n"
+      : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]),
+        "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]), "=r"(v[16]),
+        "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]), "=r"(v[24]),
+        "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
+      : "r"(taddr)
+      : "memory");
+}
+
+// MC: the pooled size when it is the reference's 14 (compile-time: the epilogue's 128 stores per warp then take
+// immediate offsets -- with a run-time row pitch the address arithmetic was 8 of every 9 instructions of the kernel's
+// hottest line), else 0 (run-time M)
+template <int MC>
+__global__ void __launch_bounds__(kTcThreads, 2) roi_align_tc_kernel(
+    const RoiLevels L, int bs, int C, const float* __restrict__ rois, const float* __restrict__ level_of, long long K,
+    int M_rt, int S, int aligned, float* __restrict__ out, int32_t* __restrict__ fallback) {
+  const int M = MC ? MC : M_rt;
+  extern __shared__ __align__(128) unsigned char tc_smem[];
+  unsigned char* const A_hi = tc_smem;
+  unsigned char* const A_lo = A_hi + kTcABytes;
+  unsigned char* const B_hi = A_lo + kTcABytes;
+  unsigned char* const B_lo = B_hi + kTcBBytes;
+  TcTables& T = *reinterpret_cast<TcTables*>(B_lo + kTcBBytes);
+  const int t = threadIdx.x, lane = t & 31, warp = t >> 5;
+  const int bins = MC ? MC * MC : M * M, n_mt = (bins + 127) >> 7, slices = C / kTcN;
+
+  if (warp == 0) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&T.tmem_base)),
+                 "r"(kTcCols)
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  if (t == 0) {
+    mbar_init(reinterpret_cast<uint64_t*>(&T.mbar), 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  // the padding columns k = 36..39 of B are never written again: zero (their A weights are zero, but 0 * garbage
+  // could be NaN)
+  for (int i = t; i < kTcN; i += kTcThreads) {
+    *reinterpret_cast<float4*>(B_hi + (kTcKc - 1) * kTcBLbo + i * 16) = make_float4(0.f, 0.f, 0.f, 0.f);
+    *reinterpret_cast<float4*>(B_lo + (kTcKc - 1) * kTcBLbo + i * 16) = make_float4(0.f, 0.f, 0.f, 0.f);
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+  const uint32_t tmem = T.tmem_base;
+  uint32_t phase = 0;
+  const float inv_s = 1.0f / (float)S;
+
+  for (long long n = blockIdx.x; n < K; n += gridDim.x) {
+    const float* r = rois + n * 5;
+    const int lvl = level_of ? (int)level_of[n] : 0;
+    const bool lvl_ok = level_of ? (level_of[n] == (float)lvl && lvl >= 0 && lvl < L.nl) : true;
+    const int b = (int)r[0];
+    const bool live = lvl_ok && b >= 0 && b < bs;
+    const int H = live ? L.h[lvl] : 1, W = live ? L.w[lvl] : 1;
+    __syncthreads();  // everybody is done with the previous RoI's window bounds (also on the fallback `continue`)
+    if (t == 0) {
+      T.ylo = INT_MAX;
+      T.xlo = INT_MAX;
+      T.yhi = -1;
+      T.xhi = -1;
+    }
+    __syncthreads();
+    // ---- sample tables: threads [0, M*S) the y axis, [128, 128 + M*S) the x axis
+    if (live && (t & 127) < M * S) {
+      const float scale = L.scale[lvl], off = aligned ? 0.5f : 0.0f;
+      const bool isx = t >= 128;
+      const float s0 = __fsub_rn(__fmul_rn(isx ? r[1] : r[2], scale), off);
+      const float e0 = __fsub_rn(__fmul_rn(isx ? r[3] : r[4], scale), off);
+      float len = __fsub_rn(e0, s0);
+      if (!aligned) len = fmaxf(len, 1.0f);
+      const float bin = __fdiv_rn(len, (float)M);
+      const int i = t & 127;
+      const SampleTab Sa = roi_sample(s0, bin, i / S, i % S, S, isx ? W : H);
+      (isx ? T.xtab : T.ytab)[i] = Sa;
+      if (Sa.low >= 0) {
+        atomicMin(isx ? &T.xlo : &T.ylo, Sa.low);
+        atomicMax(isx ? &T.xhi : &T.yhi, Sa.high);
+      }
+    }
+    __syncthreads();
+    const int ylo = T.ylo, xlo = T.xlo;
+    const int span_h = T.yhi - ylo + 1, span_w = T.xhi - xlo + 1;
+    // dead rows (zero-filled by the reference), all-zero weights and windows over 6 x 6 go to the exact kernel
+    if (!(live && T.yhi >= 0 && T.xhi >= 0 && span_h <= kTcSpan && span_w <= kTcSpan)) {
+      if (t == 0) fallback[1 + atomicAdd(fallback, 1)] = (int32_t)n;
+      continue;
+    }
+    // ---- per-axis weights over the window: the mean over the bin's S samples of the bilinear tap weights
+    {
+      const bool isx = t >= 128;
+      const int p = (t & 127) >> 3, j = t & 7;
+      if (p < M) {
+        const SampleTab* tab = isx ? T.xtab : T.ytab;
+        const int lo0 = isx ? xlo : ylo;
+        float w = 0.f;
+        for (int i = 0; i < S; ++i) {
+          const SampleTab Sa = tab[p * S + i];
+          if (Sa.low >= 0) {
+            if (Sa.low - lo0 == j) w += Sa.h;
+            if (Sa.high - lo0 == j) w += Sa.l;
+          }
+        }
+        (isx ? T.wx : T.wy)[p][j] = w * inv_s;
+      }
+    }
+    __syncthreads();
+    // ---- B, software-pipelined through registers: the window of slice sl + 1 is loaded while slice sl is in the tensor
+    // cores and the epilogue.  Thread t < 252 owns window pixel k = t % 36 (= jy * 6 + jx) of channels t / 36 + 7 i:
+    // its tap validity, feature offset and shared-memory slot are fixed for the RoI and step by constants per channel,
+    // and a warp's 32 loads touch the rows of one or two channels (~7 cache lines; with lane = channel it was 32 lines
+    // per load and the L1 tag stage, not HBM, set the pace).
+    const size_t plane = (size_t)H * W;
+    constexpr int kKK = kTcSpan * kTcSpan, kCg = kTcThreads / kKK, kEl = (kTcN + kCg - 1) / kCg;   // 36, 7, 10
+    const int bk = t % kKK, bc = t / kKK;
+    const int bjy = bk / kTcSpan, bjx = bk - bjy * kTcSpan;
+    const bool b_on = bc < kCg, b_tap = b_on && bjy < span_h && bjx < span_w;
+    const float* feat = L.data[lvl] + ((size_t)b * C + bc) * plane + (size_t)(ylo + (b_tap ? bjy : 0)) * W + xlo +
+                        (b_tap ? bjx : 0);
+    const int b_slot = (bk >> 2) * kTcBLbo + bc * 16 + (bk & 3) * 4;
+    float pv[kEl];
+#define HDY_TC_PREFETCH(sl)                                                                              \
+  _Pragma("unroll") for (int i = 0; i < kEl; ++i) {                                                      \
+    pv[i] = (b_tap && bc + kCg * i < kTcN) ? __ldg(feat + ((size_t)(sl) * kTcN + kCg * i) * plane) : 0.f; \
+  }
+    HDY_TC_PREFETCH(0)
+    // ---- A: thread = output bin, k = jy * 6 + jx
+    if (t < bins) {
+      const int py = t / M, px = t - py * M;
+      float wyv[kTcSpan], wxv[kTcSpan];
+#pragma unroll
+      for (int j = 0; j < kTcSpan; ++j) {
+        wyv[j] = T.wy[py][j];
+        wxv[j] = T.wx[px][j];
+      }
+#pragma unroll
+      for (int kc = 0; kc < kTcKc; ++kc) {
+        float hi[4], lo[4];
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+          const int k = kc * 4 + e;
+          const float v = k < kTcSpan * kTcSpan ? wyv[k / kTcSpan] * wxv[k % kTcSpan] : 0.f;
+          hi[e] = tf32_rna(v);
+          lo[e] = tf32_rna(v - hi[e]);
+        }
+        *reinterpret_cast<float4*>(A_hi + kc * kTcALbo + t * 16) = make_float4(hi[0], hi[1], hi[2], hi[3]);
+        *reinterpret_cast<float4*>(A_lo + kc * kTcALbo + t * 16) = make_float4(lo[0], lo[1], lo[2], lo[3]);
+      }
+    }
+    // split: registers -> B (hi, lo) in the core-matrix layout
+#define HDY_TC_SPLIT()                                                                         \
+  if (b_on) {                                                                                  \
+    _Pragma("unroll") for (int i = 0; i < kEl; ++i) {                                          \
+      if (bc + kCg * i < kTcN) {                                                               \
+        const float hi = tf32_rna(pv[i]), lo = tf32_rna(pv[i] - hi);                           \
+        *reinterpret_cast<float*>(B_hi + b_slot + i * (kCg * 16)) = hi;                        \
+        *reinterpret_cast<float*>(B_lo + b_slot + i * (kCg * 16)) = lo;                        \
+      }                                                                                        \
+    }                                                                                          \
+  }
+    // one thread: 3 terms x M tiles x 5 K steps into accumulator buffer `buf`, then commit to the mbarrier
+#define HDY_TC_ISSUE(buf)                                                                                         \
+  if (t == 0) {                                                                                                   \
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");                                               \
+    const uint32_t a_hi = smem_u32(A_hi), a_lo = smem_u32(A_lo), b_hi = smem_u32(B_hi), b_lo = smem_u32(B_lo);    \
+    for (int mt = 0; mt < n_mt; ++mt) {                                                                           \
+      const uint32_t d = tmem + (uint32_t)((buf) * 2 * kTcN + mt * kTcN);                                         \
+      uint32_t acc = 0;                                                                                           \
+      _Pragma("unroll") for (int term = 0; term < 3; ++term) { /* the small terms first */                       \
+        const uint32_t a0 = (term == 0 ? a_lo : a_hi) + (uint32_t)(mt * 128 * 16);                                \
+        const uint32_t b0 = term == 1 ? b_lo : b_hi;                                                              \
+        _Pragma("unroll") for (int ks = 0; ks < kTcKSteps; ++ks) {                                                \
+          tc_mma(d, tc_desc(a0 + ks * 2 * kTcALbo, kTcALbo, 128), tc_desc(b0 + ks * 2 * kTcBLbo, kTcBLbo, 128),   \
+                 acc);                                                                                            \
+          acc = 1;                                                                                                \
+        }                                                                                                         \
+      }                                                                                                           \
+    }                                                                                                             \
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(             \
+                     smem_u32(&T.mbar))                                                                           \
+                 : "memory");                                                                                     \
+  }
+    // Pipeline over the slices: the MMAs of slice sl + 1 (other accumulator buffer) run while the epilogue of slice sl
+    // stores, and the loads of slice sl + 2 are in flight behind both.  B is single-buffered: it is rewritten only after
+    // the mbarrier said the MMAs reading it are done.
+    HDY_TC_SPLIT()
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // generic-proxy writes -> visible to the MMA
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();  // (every warp is past the previous RoI's epilogue: both accumulator buffers are free)
+    HDY_TC_ISSUE(0)
+    if (1 < slices) {
+      HDY_TC_PREFETCH(1)
+    }
+    for (int sl = 0; sl < slices; ++sl) {
+      while (!mbar_try_wait(reinterpret_cast<uint64_t*>(&T.mbar), phase)) {
+      }
+      phase ^= 1;
+      if (sl + 1 < slices) {
+        HDY_TC_SPLIT()
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+        asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+        __syncthreads();  // (every warp is past the epilogue of slice sl - 1, which read the buffer written next)
+        HDY_TC_ISSUE((sl + 1) & 1)
+        if (sl + 2 < slices) {
+          HDY_TC_PREFETCH(sl + 2)
+        }
+      }
+      asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+      // ---- epilogue: warp -> (M tile, lane quarter); lane = bin, registers = 32 consecutive channels
+      {
+        const int mt = warp >> 2, q = warp & 3;
+        const int bin0 = mt * 128 + q * 32, bin = bin0 + lane;
+        const bool mine = mt < n_mt && bin0 < bins;
+        float* o = out + ((size_t)n * C + (size_t)sl * kTcN) * bins;
+        if (mine) {
+#pragma unroll 1
+          for (int cc = 0; cc < kTcN / 32; ++cc) {
+            uint32_t v[32];
+            tc_ld32(tmem + ((uint32_t)(q * 32) << 16) + (uint32_t)((sl & 1) * 2 * kTcN + mt * kTcN + cc * 32), v);
+            asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+            if (bin < bins) {
+#pragma unroll
+              for (int j = 0; j < 32; ++j) __stcs(o + (size_t)(cc * 32 + j) * bins + bin, __uint_as_float(v[j]));
+            }
+          }
+        }
+      }
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+#undef HDY_TC_SPLIT
+#undef HDY_TC_ISSUE
+#undef HDY_TC_PREFETCH
+  }
+  __syncthreads();
+  if (warp == 0)
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(kTcCols) : "memory");
+}
+
+}  // namespace hdy
+
+extern "C" int hdy_multiscale_roi_align_tf32x3(const hdy_feature_level_t* levels_host, int nl, int bs, int channels,
+                                               const float* rois, const float* level_of, int64_t K, int pooled,
+                                               int sampling_ratio, int aligned, float* out, int32_t* fallback,
+                                               hdy_stream_t stream) {
+  using namespace hdy;
+  RoiLevels L;
+  int rc = roi_levels_from_host(levels_host, nl, &L);
+  if (rc) return rc;
+  rc = roi_align_args_ok(bs, channels, rois, level_of, nl, K, pooled, sampling_ratio, out);
+  if (rc || K == 0) return rc;
+  HDY_REQUIRE(channels % kTcN == 0, "roi_align (tf32x3): channels=%d must be a multiple of %d", channels, kTcN);
+  HDY_REQUIRE(fallback != nullptr, "roi_align (tf32x3): fallback scratch is NULL");
+  cudaStream_t st = (cudaStream_t)stream;
+  if (pooled * pooled > kTcRows)  // (the A operand holds 200 rows: pooled <= 14; 15 and 16 take the exact kernel)
+    return launch_roi_align_exact(L, bs, channels, rois, level_of, K, pooled, sampling_ratio, aligned, out, nullptr, st);
+  int dev = 0, sms = 148;
+  cudaGetDevice(&dev);
+  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  static bool attr_set[64] = {};
+  if (dev < 0 || dev >= 64 || !attr_set[dev]) {
+    cudaError_t e = cudaFuncSetAttribute(roi_align_tc_kernel<14>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kTcSmem);
+    if (e == cudaSuccess)
+      e = cudaFuncSetAttribute(roi_align_tc_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kTcSmem);
+    if (e != cudaSuccess) {
+      set_error("roi_align (tf32x3) setup: %s", cudaGetErrorString(e));
+      return HDY_ERR_CUDA;
+    }
+    if (dev >= 0 && dev < 64) attr_set[dev] = true;
+  }
+  cudaError_t e = cudaMemsetAsync(fallback, 0, sizeof(int32_t), st);
+  if (e != cudaSuccess) {
+    set_error("cudaMemsetAsync: %s", cudaGetErrorString(e));
+    return HDY_ERR_CUDA;
+  }
+  const unsigned grid = (unsigned)(K < 2ll * sms ? K : 2ll * sms);
+  if (pooled == 14)
+    roi_align_tc_kernel<14><<<grid, kTcThreads, kTcSmem, st>>>(L, bs, channels, rois, level_of, (long long)K, pooled,
+                                                               sampling_ratio, aligned, out, fallback);
+  else
+    roi_align_tc_kernel<0><<<grid, kTcThreads, kTcSmem, st>>>(L, bs, channels, rois, level_of, (long long)K, pooled,
+                                                              sampling_ratio, aligned, out, fallback);
+  rc = check_launch("hdy_multiscale_roi_align_tf32x3");
+  if (rc) return rc;
+  // the RoIs the tensor-core path left (windows over 6 x 6 taps, dead rows): exact kernel over the list
+  return launch_roi_align_exact(L, bs, channels, rois, level_of, K, pooled, sampling_ratio, aligned, out, fallback, st);
+}

@@ -42,8 +42,13 @@ def _levels(features: Sequence[torch.Tensor], scales: Sequence[float]):
 
 def multiscale_roi_align(features: List[torch.Tensor], boxes: torch.Tensor, levels: Optional[torch.Tensor],
                          strides: Sequence[float], output_size: int = 14, sampling_ratio: int = 2,
-                         aligned: bool = False) -> torch.Tensor:
+                         aligned: bool = False, mode: str = "exact") -> torch.Tensor:
     """Detect.multiscale_roi_align (yolo_head.py:279-299).
+
+    mode "exact" (default): torchvision's operation order, bit-identical to its CPU op.  mode "tf32x3": the per-RoI
+    [M*M x 36] x [36 x C] product on the tensor cores (tcgen05, 3xTF32 split, fp32 accumulation): ~1e-6 relative to
+    the window's magnitude, several times faster; C must be a multiple of 64.  RoIs with tap windows over 6 x 6
+    feature pixels are computed by the exact kernel in either mode.
 
     features: one [bs, C, h_i, w_i] tensor per level; boxes [K, 5] = (image index, x1, y1, x2, y2); levels [K] float
     level ids (the 'extra'[:, 0] column of nms_per_image); strides: buffer.stride per level (spatial_scale =
@@ -68,13 +73,22 @@ def multiscale_roi_align(features: List[torch.Tensor], boxes: torch.Tensor, leve
         lv = levels.contiguous()
     elif len(features) > 1:
         raise HdyError("levels is required with more than one feature level")
+    if mode == "tf32x3":
+        if ch % 64:
+            raise HdyError(f"mode 'tf32x3' needs a multiple of 64 channels, got {ch}")
+        fallback = torch.empty((K + 1,), dtype=torch.int32, device=boxes.device)
+        _call("hdy_multiscale_roi_align_tf32x3", arr, len(features), bs, ch, ptr(boxes), ptr(lv), K, M,
+              int(sampling_ratio), int(bool(aligned)), ptr(out), ptr(fallback), _stream(), launches=2)
+        return out
+    if mode != "exact":
+        raise HdyError(f"unknown roi_align mode {mode!r} ('exact' or 'tf32x3')")
     _call("hdy_multiscale_roi_align", arr, len(features), bs, ch, ptr(boxes), ptr(lv), K, M, int(sampling_ratio),
           int(bool(aligned)), ptr(out), _stream())
     return out
 
 
 def roi_align(input: torch.Tensor, boxes: Union[torch.Tensor, List[torch.Tensor]], output_size, spatial_scale: float = 1.0,
-              sampling_ratio: int = 2, aligned: bool = False) -> torch.Tensor:
+              sampling_ratio: int = 2, aligned: bool = False, mode: str = "exact") -> torch.Tensor:
     """torchvision.ops.roi_align as the reference calls it (yolo_head.py:243, :294): Tensor[K, 5] boxes or a list of
     per-image Tensor[k_i, 4]; square output; sampling_ratio >= 1."""
     if isinstance(output_size, (tuple, list)):
@@ -84,7 +98,7 @@ def roi_align(input: torch.Tensor, boxes: Union[torch.Tensor, List[torch.Tensor]
     if isinstance(boxes, (list, tuple)):
         boxes = torch.cat([torch.nn.functional.pad(b, [1, 0], value=float(i)) for i, b in enumerate(boxes)])
     return multiscale_roi_align([input], boxes, None, [1.0 / float(spatial_scale)], int(output_size), sampling_ratio,
-                                aligned)
+                                aligned, mode=mode)
 
 
 def batch_rois(batch: DetectBatch, counts_host: Optional[Sequence[int]] = None):

@@ -490,6 +490,18 @@ HDY_API int hdy_multiscale_roi_align(const hdy_feature_level_t* levels_host, int
                                      const float* rois, const float* level_of, int64_t K, int pooled,
                                      int sampling_ratio, int aligned, float* out, hdy_stream_t stream);
 
+/* f1 on the tensor cores (tcgen05.mma.kind::tf32, accumulators in TMEM): same arguments and result layout, but the
+ * bilinear sampling + averaging of a RoI is evaluated as the [pooled^2 x 36] x [36 x channels] product of its tap
+ * weights with its <= 6 x 6 feature window, in 3xTF32 (split operands, fp32 accumulation): results agree with
+ * hdy_multiscale_roi_align to ~1e-6 relative to the window's magnitude instead of bit for bit (the north star's
+ * tolerance for box-derived quantities is 1e-5).  RoIs whose taps span more than 6 x 6 feature pixels, and rows the
+ * reference leaves zero, are listed in `fallback` and computed by the exact kernel in the same call.
+ *   channels must be a multiple of 64; pooled <= 14 (larger outputs run the exact kernel); fallback [K + 1] int32 scratch ([0] = number of listed RoIs afterwards). */
+HDY_API int hdy_multiscale_roi_align_tf32x3(const hdy_feature_level_t* levels_host, int nl, int bs, int channels,
+                                            const float* rois, const float* level_of, int64_t K, int pooled,
+                                            int sampling_ratio, int aligned, float* out, int32_t* fallback,
+                                            hdy_stream_t stream);
+
 /* f2: the matching step of APMeter.add (metayolo/models/metrics.py:270-303) without the dense k x g matrix.
  *   pred_boxes [bs, P, 4], pred_order [bs, P] i32 (rank in score order -> row; NULL: rows are already in order),
  *   pred_counts [bs], gt_boxes [bs, G, 4], gt_counts [bs]; every pair with box_iou >= iou_min (utils_general.py:

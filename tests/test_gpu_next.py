@@ -25,6 +25,58 @@ def test_roi_align_golden_bit_exact(cuda_device):
     assert float(out[5].abs().max()) == 0.0          # level id 3: the zero row of the reference's `result`
 
 
+@pytest.mark.parametrize("C,M,S,aligned,lo,hi", [
+    (256, 14, 2, False, 12, 36),    # the reference's call on nuclei: all on the tensor-core path but a few 7-tap windows
+    (128, 14, 2, False, 8, 120),    # mixed: the large RoIs go to the exact kernel
+    (128, 7, 2, True, 4, 40),       # one M tile (49 bins)
+    (256, 16, 3, False, 6, 30),     # 256 bins: over the 200 rows of the A operand, the exact kernel does them all
+    (128, 13, 3, False, 6, 30),     # S = 3 (weights are thirds)
+    (128, 11, 1, True, 6, 30),
+])
+def test_roi_align_tf32x3_within_tolerance(cuda_device, C, M, S, aligned, lo, hi):
+    """mode='tf32x3' (tcgen05 3xTF32, roi_align_tc.cu) against the exact-order kernel on the same inputs: the north
+    star's 1e-5 relative tolerance, measured against the magnitude of the taps (|w| . |f|, which bounds every partial
+    sum); rows the reference leaves zero stay exactly zero; RoIs over 6 x 6 taps are bit-identical (exact kernel)."""
+    gen = torch.Generator().manual_seed(C + 7 * M + S)
+    tile, bs, K = 320, 3, 700
+    strides = [8, 16, 32]
+    feats = [torch.randn((bs, C, tile // s, tile // s), generator=gen).to(cuda_device) for s in strides]
+    rois = _rois(gen, K, bs, tile, lo, hi)
+    rois[0, 1:] = torch.tensor([-40., -40., -20., -20.])           # outside: all weights zero
+    rois[1, 1:] = torch.tensor([tile - 3., tile - 3., tile + 30., tile + 30.])
+    rois[4, 1:] = torch.tensor([100., 100., 100., 100.])           # empty box (aligned=False clamps to 1 px)
+    levels = torch.randint(0, 3, (K,), generator=gen).float()
+    levels[2], levels[3] = -1.0, 0.5                                # match no level
+    levels[0] = 0.0                                                 # (on a coarse level the far box is in range again)
+    rois, levels = rois.to(cuda_device), levels.to(cuda_device)
+    exact = hdy.multiscale_roi_align(feats, rois, levels, strides, M, S, aligned)
+    fast = hdy.multiscale_roi_align(feats, rois, levels, strides, M, S, aligned, mode="tf32x3")
+    absf = hdy.multiscale_roi_align([f.abs() for f in feats], rois, levels, strides, M, S, aligned)   # sum |w| |f|
+    err = (fast - exact).abs()
+    assert bool((err <= 1e-5 * absf + 1e-30).all()), \
+        f"max err {err.max().item():.3g}, worst ratio {(err / absf.clamp_min(1e-30)).max().item():.3g}"
+    assert float(fast[2].abs().max()) == 0.0 and float(fast[3].abs().max()) == 0.0 and float(fast[0].abs().max()) == 0.0
+    same = (fast == exact).flatten(1).all(1)
+    assert 0 < int(same.sum()) and (int(same.sum()) < K or M * M > 200)   # some rows took the exact kernel
+    if M * M > 200:
+        assert torch.equal(fast, exact)
+    else:
+        assert float(err.max()) > 0.0                 # ... so the tensor-core path did run
+
+
+def test_roi_align_tf32x3_golden(cuda_device):
+    g = load_golden("roi_align")
+    feats = [torch.from_numpy(g[f"feat{i}"]).to(cuda_device) for i in range(3)]
+    feats = [f.repeat(1, 64 // f.shape[1] + 1, 1, 1)[:, :64].contiguous() for f in feats]
+    boxes, levels = torch.from_numpy(g["boxes"]).to(cuda_device), torch.from_numpy(g["levels"]).to(cuda_device)
+    exact = hdy.multiscale_roi_align(feats, boxes, levels, g["strides"].tolist())
+    fast = hdy.multiscale_roi_align(feats, boxes, levels, g["strides"].tolist(), mode="tf32x3")
+    assert torch.allclose(fast, exact, rtol=1e-5, atol=1e-5)
+    with pytest.raises(hdy.HdyError):
+        hdy.multiscale_roi_align([f[:, :40].contiguous() for f in feats], boxes, levels, g["strides"].tolist(),
+                                 mode="tf32x3")
+
+
 def _rois(gen, K, bs, tile, lo, hi):
     c = torch.rand((K, 2), generator=gen) * tile
     s = torch.rand((K, 2), generator=gen) * (hi - lo) + lo

@@ -221,3 +221,47 @@ def test_slide_masks_of_kept_rows_match_oracle(cuda_device):
     parts = hdist.run_emulated(2, rank_run)
     assert fold_digest(parts[0][0] + parts[1][0]) == d1
     assert fold_digest(parts[0][1] + parts[1][1]) == fold_digest(kept_digest(res['state'], 0))
+
+
+@pytest.mark.parametrize("world", [1, 2])
+def test_run_orders_survivors_beside_the_mask_pass(cuda_device, world):
+    """run(ordered=True, proto_provider=...) with side streams sorts / gathers the survivors on their own stream while
+    the mask pass runs: same survivors in the same order, same mask bits as the one-stream sequence."""
+    dev = cuda_device
+    size, tile, overlap, md, nm = (1500, 1100), 512, 64, 1200, 32
+    spec = hdy.HeadSpec(synth.ANCHORS_3, synth.STRIDES_3, nc=4, no=9 + nm)
+    rois = hdy.sliding_window_scanner(size, (tile, tile), overlap)
+    lg = [synth.slide_tile_logits(rois[t:t + 1], tile, 4, seed=13, first_tile=t, device=dev, pitch=30.0, extra=nm)
+          for t in range(len(rois))]
+    pr = [synth.slide_tile_protos(1, tile, seed=13, first_tile=t, nm=nm, device=dev) for t in range(len(rois))]
+
+    def prov(a, b):
+        return [torch.cat([lg[t][l] for t in range(a, b)]) for l in range(3)]
+
+    def prot(a, b):
+        return torch.cat(pr[a:b])
+
+    def rank_run(rank, comm, streams):
+        with scratch_slot(300 + 10 * streams + rank):
+            p = hdy.SlidePostprocessor(spec, size, (tile, tile), overlap, CONF, IOU, md, cap=2048, batch=2, device=dev,
+                                       rank=rank, world=world, comm=comm, seam_cap=512, streams=streams)
+            outs = []
+            for _ in range(2):          # twice: the second run re-uses the streams and scratch of the first
+                r = p.run(prov, ordered=True, proto_provider=prot)
+                r['masks'].check()
+                outs.append((r['index'].clone(), r['boxes'].clone(), r['scores'].clone(), r['labels'].clone(),
+                             mask_digest(r['masks'], r['state'], r['base']), r['state'].clone()))
+            for a, b in zip(outs[0], outs[1]):
+                assert torch.equal(a, b)
+            return outs[1]
+
+    if world == 1:
+        one, three = rank_run(0, None, 1), rank_run(0, None, 3)
+        parts1, parts3 = [one], [three]
+    else:
+        parts1 = hdist.run_emulated(world, lambda r, c: rank_run(r, c, 1))
+        parts3 = hdist.run_emulated(world, lambda r, c: rank_run(r, c, 3))
+    for a, b in zip(parts1, parts3):
+        assert a[0].numel() > 100
+        for x, y in zip(a, b):
+            assert torch.equal(x, y)

@@ -29,6 +29,10 @@ def ours():
     return hdy.multiscale_roi_align(feats, rois, levels, strides, 14, 2, False)
 
 
+def ours_tc():
+    return hdy.multiscale_roi_align(feats, rois, levels, strides, 14, 2, False, mode="tf32x3")
+
+
 def reference():
     result = torch.zeros((K, C, 14, 14), device=dev)
     for i, s in enumerate(strides):
@@ -51,6 +55,7 @@ def timed(fn, n=10):
 
 
 t_ours = timed(ours)
+t_tc = timed(ours_tc)
 t_ref = timed(reference, 3)
 # agreement on a slice: at the full size torchvision's CUDA kernel indexes its output with a 32-bit int, and level 0
 # alone holds 46 000 x 256 x 196 = 2.3e9 elements -- its result is not usable as a reference there (ours indexes with
@@ -63,7 +68,16 @@ for i, s in enumerate(strides):
     r[idx] = torchvision.ops.roi_align(feats[i], rois[:n_chk][idx], (14, 14), 1 / s, 2, False)
 diff = (o - r).abs().max().item()
 out_bytes = K * C * 14 * 14 * 4
-print(json.dumps({"K": K, "C": C, "bs": bs, "ms_ours": t_ours, "ms_torchvision_per_level_loop": t_ref,
+o_tc = hdy.multiscale_roi_align(feats, rois[:n_chk].contiguous(), levels[:n_chk].contiguous(), strides, 14, 2, False,
+                                mode="tf32x3")
+mag = hdy.multiscale_roi_align([f.abs() for f in feats], rois[:n_chk].contiguous(), levels[:n_chk].contiguous(),
+                               strides, 14, 2, False)
+err_tc = ((o_tc - o).abs() / mag.clamp_min(1e-30)).max().item()
+n_exact = int((o_tc == o).flatten(1).all(1).sum())
+print(json.dumps({"K": K, "C": C, "bs": bs, "ms_ours": t_ours, "ms_ours_tf32x3": t_tc,
+                  "write_GBs_ours_tf32x3": out_bytes / t_tc / 1e6,
+                  "tf32x3_max_err_over_tap_magnitude_first_4096_rois": err_tc,
+                  "tf32x3_rows_bit_identical_to_exact_first_4096_rois": n_exact, "ms_torchvision_per_level_loop": t_ref,
                   "out_GB": out_bytes / 1e9, "write_GBs_ours": out_bytes / t_ours / 1e6,
                   "write_GBs_torchvision": out_bytes / t_ref / 1e6,
                   "max_abs_diff_vs_torchvision_cuda_first_4096_rois": diff}))
