@@ -23,7 +23,7 @@
 //   Detections whose kept range exceeds 16x16 proto pixels (64 px boxes at the usual 4x) are listed by phase 2 and
 //   handled by the per-detection kernel of mask.cu.
 #include <stdlib.h>
-#include <cuda.h>  // CUtensorMap types only; the encoder is fetched through cudaGetDriverEntryPoint
+#include "tma_common.cuh"
 #include "mask_common.cuh"
 
 #ifndef HDY_MASK_DEFAULT_PATH
@@ -94,15 +94,6 @@ static PmWorkspace pm_workspace(void* base, long long slots) {
   p += (size_t)slots * kPatchPitch * kPatchPitch * 4;
   w.regions = reinterpret_cast<RegionList*>(p);
   return w;
-}
-
-__device__ __forceinline__ void tma_load_4d(void* dst, const CUtensorMap* map, int c0, int c1, int c2, int c3,
-                                            uint64_t* bar) {
-  asm volatile(
-      "cp.async.bulk.tensor.4d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4, %5}], "
-      "[%6];" ::"r"(smem_u32(dst)),
-      "l"(map), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "r"(smem_u32(bar))
-      : "memory");
 }
 
 struct KeptRange {
@@ -815,24 +806,6 @@ __global__ void __launch_bounds__(kFuThreads, 2) mask_fused_kernel(
     }
     __syncthreads();  // every warp is done with the region buffer (and with S.item / S.next_piece)
   }
-}
-
-typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
-                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
-                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
-
-static EncodeTiledFn tensor_map_encoder() {
-  static EncodeTiledFn fn = nullptr;
-  static bool tried = false;
-  if (!tried) {
-    tried = true;
-    void* p = nullptr;
-    cudaDriverEntryPointQueryResult q;
-    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess &&
-        q == cudaDriverEntryPointSuccess)
-      fn = reinterpret_cast<EncodeTiledFn>(p);
-  }
-  return fn;
 }
 
 int launch_process_mask_regions(const void* protos, int proto_dtype, const float* coef, const float* boxes,

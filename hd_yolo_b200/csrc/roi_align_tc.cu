@@ -29,6 +29,7 @@
 //     of a channel are contiguous in the output, so a warp writes 128 B per register.
 #include <limits.h>
 #include "roi_align_common.cuh"
+#include "tma_common.cuh"
 
 namespace hdy {
 
@@ -51,9 +52,17 @@ constexpr int kTcABytes = kTcKc * kTcALbo;      // 32 000
 constexpr int kTcBBytes = kTcKc * kTcBLbo;      // 10 400
 constexpr int kTcCols = 256;                    // TMEM columns: 2 accumulator buffers x 2 M tiles x 64 channels (fp32)
 // Over-read: the second M tile's descriptor covers rows 128..255 but only rows < bins are written.  What the MMA reads
-// past row 199 of a chunk is the next chunk / the next buffer (A_hi -> A_lo -> B_hi, all inside this CTA's shared
+// past row 199 of a chunk is the next chunk / the next buffer (A_hi -> A_lo -> the TMA ring, all inside this CTA's shared
 // memory): finite or not, it only reaches accumulator rows >= bins, which nobody loads.
-static_assert(kTcKc * kTcALbo + 56 * 16 <= kTcABytes + kTcBBytes, "over-read of the last A chunk stays inside smem");
+
+// The TMA box: its global origin must be 16-byte aligned (an unaligned x origin is an illegal-instruction fault, probed
+// with tools/probe/tma_box_probe.cu), so the load starts at xlo & ~3 and is 12 pixels wide: 3 + 6 window columns, 48 B.
+constexpr int kTcRawX = 12;
+constexpr int kTcRawBytes = kTcN * kTcSpan * kTcRawX * 4;   // one slice's window, [channel][6][12] fp32: 18 432
+
+struct TcMaps {
+  CUtensorMap m[HDY_MAX_LEVELS];   // per level: [bs][C][H][W] fp32, box {12, 6, 64, 1}
+};
 
 struct TcTables {
   SampleTab ytab[kRoiMaxM * kRoiMaxS];
@@ -61,11 +70,15 @@ struct TcTables {
   float wy[kRoiMaxM][8];
   float wx[kRoiMaxM][8];
   unsigned long long mbar;
+  unsigned long long ring_bar;
   int ylo, yhi, xlo, xhi;
   uint32_t tmem_base;
 };
-constexpr size_t kTcSmem = 2 * kTcABytes + 2 * kTcBBytes + sizeof(TcTables);
+constexpr size_t kTcSmem = 2 * kTcABytes + 2 * kTcBBytes + kTcRawBytes + sizeof(TcTables);
 static_assert(kTcSmem <= 113 * 1024, "two CTAs per SM");
+static_assert(56 * 16 <= kTcRawBytes, "over-read of the last A chunk stays inside smem");
+static_assert((2 * kTcABytes) % 128 == 0 && kTcRawBytes % 128 == 0, "TMA destinations are 128-byte aligned");
+
 
 // round to nearest tf32 (10 mantissa bits; ties away from zero, like cvt.rna.tf32.f32) with two integer-pipe
 // instructions: the cvt runs on the quarter-rate conversion pipe and was 16 % of the kernel's stall samples
@@ -111,13 +124,14 @@ __device__ __forceinline__ void tc_ld32(uint32_t taddr, uint32_t (&v)[32]) {
 // hottest line), else 0 (run-time M)
 template <int MC>
 __global__ void __launch_bounds__(kTcThreads, 2) roi_align_tc_kernel(
-    const RoiLevels L, int bs, int C, const float* __restrict__ rois, const float* __restrict__ level_of, long long K,
-    int M_rt, int S, int aligned, float* __restrict__ out, int32_t* __restrict__ fallback) {
+    const __grid_constant__ TcMaps maps, const RoiLevels L, int bs, int C, const float* __restrict__ rois, const float* __restrict__ level_of, long long K,
+    int M_rt, int S, int aligned, float* __restrict__ out, int32_t* __restrict__ fallback, uint32_t level_mask) {
   const int M = MC ? MC : M_rt;
   extern __shared__ __align__(128) unsigned char tc_smem[];
   unsigned char* const A_hi = tc_smem;
   unsigned char* const A_lo = A_hi + kTcABytes;
-  unsigned char* const B_hi = A_lo + kTcABytes;
+  unsigned char* const raw = A_lo + kTcABytes;   // the next slice's window, filled by TMA (128-byte aligned: 64 000)
+  unsigned char* const B_hi = raw + kTcRawBytes;
   unsigned char* const B_lo = B_hi + kTcBBytes;
   TcTables& T = *reinterpret_cast<TcTables*>(B_lo + kTcBBytes);
   const int t = threadIdx.x, lane = t & 31, warp = t >> 5;
@@ -131,6 +145,7 @@ __global__ void __launch_bounds__(kTcThreads, 2) roi_align_tc_kernel(
   }
   if (t == 0) {
     mbar_init(reinterpret_cast<uint64_t*>(&T.mbar), 1);
+    mbar_init(reinterpret_cast<uint64_t*>(&T.ring_bar), 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   // the padding columns k = 36..39 of B are never written again: zero (their A weights are zero, but 0 * garbage
@@ -143,7 +158,7 @@ __global__ void __launch_bounds__(kTcThreads, 2) roi_align_tc_kernel(
   __syncthreads();
   asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
   const uint32_t tmem = T.tmem_base;
-  uint32_t phase = 0;
+  uint32_t phase = 0, ring_phase = 0;
   const float inv_s = 1.0f / (float)S;
 
   for (long long n = blockIdx.x; n < K; n += gridDim.x) {
@@ -182,7 +197,8 @@ __global__ void __launch_bounds__(kTcThreads, 2) roi_align_tc_kernel(
     const int ylo = T.ylo, xlo = T.xlo;
     const int span_h = T.yhi - ylo + 1, span_w = T.xhi - xlo + 1;
     // dead rows (zero-filled by the reference), all-zero weights and windows over 6 x 6 go to the exact kernel
-    if (!(live && T.yhi >= 0 && T.xhi >= 0 && span_h <= kTcSpan && span_w <= kTcSpan)) {
+    // ... and so do the levels without a tensor map (row pitch not a multiple of 16 bytes)
+    if (!(live && T.yhi >= 0 && T.xhi >= 0 && span_h <= kTcSpan && span_w <= kTcSpan && ((level_mask >> lvl) & 1))) {
       if (t == 0) fallback[1 + atomicAdd(fallback, 1)] = (int32_t)n;
       continue;
     }
@@ -205,25 +221,24 @@ __global__ void __launch_bounds__(kTcThreads, 2) roi_align_tc_kernel(
       }
     }
     __syncthreads();
-    // ---- B, software-pipelined through registers: the window of slice sl + 1 is loaded while slice sl is in the tensor
-    // cores and the epilogue.  Thread t < 252 owns window pixel k = t % 36 (= jy * 6 + jx) of channels t / 36 + 7 i:
-    // its tap validity, feature offset and shared-memory slot are fixed for the RoI and step by constants per channel,
-    // and a warp's 32 loads touch the rows of one or two channels (~7 cache lines; with lane = channel it was 32 lines
-    // per load and the L1 tag stage, not HBM, set the pace).
-    const size_t plane = (size_t)H * W;
+    // ---- B: the window of a 64-channel slice ([64][6][12] fp32, out-of-range zero-filled) comes by ONE TMA tensor load,
+    // one slice ahead of the tensor cores -- no LDG, no L1: with per-thread loads the 24-byte rows cost ~7 cache lines
+    // per warp instruction and the LSU, shared with the epilogue's stores, set the pace.
+    // Thread t < 252 then moves window pixel k = t % 36 (= jy * 6 + jx) of channels t / 36 + 7 i from the TMA buffer into
+    // the (hi, lo) core-matrix layout: its tap validity and both shared-memory offsets are fixed for the RoI.
     constexpr int kKK = kTcSpan * kTcSpan, kCg = kTcThreads / kKK, kEl = (kTcN + kCg - 1) / kCg;   // 36, 7, 10
     const int bk = t % kKK, bc = t / kKK;
     const int bjy = bk / kTcSpan, bjx = bk - bjy * kTcSpan;
     const bool b_on = bc < kCg, b_tap = b_on && bjy < span_h && bjx < span_w;
-    const float* feat = L.data[lvl] + ((size_t)b * C + bc) * plane + (size_t)(ylo + (b_tap ? bjy : 0)) * W + xlo +
-                        (b_tap ? bjx : 0);
     const int b_slot = (bk >> 2) * kTcBLbo + bc * 16 + (bk & 3) * 4;
-    float pv[kEl];
-#define HDY_TC_PREFETCH(sl)                                                                              \
-  _Pragma("unroll") for (int i = 0; i < kEl; ++i) {                                                      \
-    pv[i] = (b_tap && bc + kCg * i < kTcN) ? __ldg(feat + ((size_t)(sl) * kTcN + kCg * i) * plane) : 0.f; \
+    const int b_raw = ((bc * kTcSpan + bjy) * kTcRawX + (xlo & 3) + bjx) * 4;
+#define HDY_TC_LOAD(sl)                                                                                          \
+  if (t == 0) {                                                                                                  \
+    uint64_t* bar = reinterpret_cast<uint64_t*>(&T.ring_bar);                                                    \
+    mbar_arrive_expect_tx(bar, kTcRawBytes);                                                                     \
+    tma_load_4d(raw, &maps.m[lvl], xlo & ~3, ylo, (sl) * kTcN, b, bar);                                          \
   }
-    HDY_TC_PREFETCH(0)
+    HDY_TC_LOAD(0)
     // ---- A: thread = output bin, k = jy * 6 + jx
     if (t < bins) {
       const int py = t / M, px = t - py * M;
@@ -248,15 +263,22 @@ __global__ void __launch_bounds__(kTcThreads, 2) roi_align_tc_kernel(
       }
     }
     // split: registers -> B (hi, lo) in the core-matrix layout
-#define HDY_TC_SPLIT()                                                                         \
-  if (b_on) {                                                                                  \
-    _Pragma("unroll") for (int i = 0; i < kEl; ++i) {                                          \
-      if (bc + kCg * i < kTcN) {                                                               \
-        const float hi = tf32_rna(pv[i]), lo = tf32_rna(pv[i] - hi);                           \
-        *reinterpret_cast<float*>(B_hi + b_slot + i * (kCg * 16)) = hi;                        \
-        *reinterpret_cast<float*>(B_lo + b_slot + i * (kCg * 16)) = lo;                        \
-      }                                                                                        \
-    }                                                                                          \
+#define HDY_TC_SPLIT()                                                                                   \
+  {                                                                                                      \
+    while (!mbar_try_wait(reinterpret_cast<uint64_t*>(&T.ring_bar), ring_phase)) {                       \
+    }                                                                                                    \
+    ring_phase ^= 1u;                                                                                    \
+    if (b_on) {                                                                                          \
+      const unsigned char* rp = raw + b_raw;                                                             \
+      _Pragma("unroll") for (int i = 0; i < kEl; ++i) {                                                  \
+        if (bc + kCg * i < kTcN) {                                                                       \
+          const float v = b_tap ? *reinterpret_cast<const float*>(rp + i * (kCg * kTcSpan * kTcRawX * 4)) : 0.f; \
+          const float hi = tf32_rna(v), lo = tf32_rna(v - hi);                                           \
+          *reinterpret_cast<float*>(B_hi + b_slot + i * (kCg * 16)) = hi;                                \
+          *reinterpret_cast<float*>(B_lo + b_slot + i * (kCg * 16)) = lo;                                \
+        }                                                                                                \
+      }                                                                                                  \
+    }                                                                                                    \
   }
     // one thread: 3 terms x M tiles x 5 K steps into accumulator buffer `buf`, then commit to the mbarrier
 #define HDY_TC_ISSUE(buf)                                                                                         \
@@ -289,47 +311,51 @@ __global__ void __launch_bounds__(kTcThreads, 2) roi_align_tc_kernel(
     __syncthreads();  // (every warp is past the previous RoI's epilogue: both accumulator buffers are free)
     HDY_TC_ISSUE(0)
     if (1 < slices) {
-      HDY_TC_PREFETCH(1)
+      HDY_TC_LOAD(1)   // (the TMA buffer was read out before the barrier)
     }
-    for (int sl = 0; sl < slices; ++sl) {
-      while (!mbar_try_wait(reinterpret_cast<uint64_t*>(&T.mbar), phase)) {
-      }
-      phase ^= 1;
-      if (sl + 1 < slices) {
-        HDY_TC_SPLIT()
-        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-        asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
-        __syncthreads();  // (every warp is past the epilogue of slice sl - 1, which read the buffer written next)
-        HDY_TC_ISSUE((sl + 1) & 1)
-        if (sl + 2 < slices) {
-          HDY_TC_PREFETCH(sl + 2)
-        }
-      }
-      asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-      // ---- epilogue: warp -> (M tile, lane quarter); lane = bin, registers = 32 consecutive channels
-      {
-        const int mt = warp >> 2, q = warp & 3;
-        const int bin0 = mt * 128 + q * 32, bin = bin0 + lane;
-        const bool mine = mt < n_mt && bin0 < bins;
-        float* o = out + ((size_t)n * C + (size_t)sl * kTcN) * bins;
-        if (mine) {
-#pragma unroll 1
-          for (int cc = 0; cc < kTcN / 32; ++cc) {
-            uint32_t v[32];
-            tc_ld32(tmem + ((uint32_t)(q * 32) << 16) + (uint32_t)((sl & 1) * 2 * kTcN + mt * kTcN + cc * 32), v);
-            asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-            if (bin < bins) {
-#pragma unroll
-              for (int j = 0; j < 32; ++j) __stcs(o + (size_t)(cc * 32 + j) * bins + bin, __uint_as_float(v[j]));
-            }
-          }
-        }
-      }
+    // one slice: wait for its MMAs; hand slice sl + 1 to the tensor cores; start the load of slice sl + 2; then store
+    // slice sl from accumulator buffer P
+#define HDY_TC_STEP(sl, P)                                                                                    \
+  {                                                                                                                \
+    while (!mbar_try_wait(reinterpret_cast<uint64_t*>(&T.mbar), phase)) {                                          \
+    }                                                                                                              \
+    phase ^= 1;                                                                                                    \
+    if ((sl) + 1 < slices) {                                                                                       \
+      HDY_TC_SPLIT()                                                                                               \
+      asm volatile("fence.proxy.async.shared::cta;" ::: "memory");                                                 \
+      asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");                                             \
+      __syncthreads(); /* every warp is past the epilogue of slice sl - 1, which read the buffer written next */   \
+      HDY_TC_ISSUE(1 - (P))                                                                                        \
+      if ((sl) + 2 < slices) {                                                                                     \
+        HDY_TC_LOAD((sl) + 2)                                                                                      \
+      }                                                                                                            \
+    }                                                                                                              \
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");                                                \
+    /* epilogue: warp -> (M tile, lane quarter); lane = bin, registers = 32 consecutive channels */                \
+    const int mt = warp >> 2, q = warp & 3;                                                                        \
+    const int bin0 = mt * 128 + q * 32, bin = bin0 + lane;                                                         \
+    float* o = out + ((size_t)n * C + (size_t)(sl) * kTcN) * bins;                                                 \
+    if (mt < n_mt && bin0 < bins) {                                                                                \
+      _Pragma("unroll 1") for (int cc = 0; cc < kTcN / 32; ++cc) {                                                 \
+        uint32_t v[32];                                                                                            \
+        tc_ld32(tmem + ((uint32_t)(q * 32) << 16) + (uint32_t)((P) * 2 * kTcN + mt * kTcN + cc * 32), v);          \
+        asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");                                               \
+        if (bin < bins) {                                                                                          \
+          _Pragma("unroll") for (int j = 0; j < 32; ++j)                                                           \
+              __stcs(o + (size_t)(cc * 32 + j) * bins + bin, __uint_as_float(v[j]));                               \
+        }                                                                                                          \
+      }                                                                                                            \
+    }                                                                                                              \
+  }
+    for (int sl = 0; sl < slices; sl += 2) {
+      HDY_TC_STEP(sl, 0)
+      if (sl + 1 < slices) HDY_TC_STEP(sl + 1, 1)
     }
+#undef HDY_TC_STEP
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
 #undef HDY_TC_SPLIT
 #undef HDY_TC_ISSUE
-#undef HDY_TC_PREFETCH
+#undef HDY_TC_LOAD
   }
   __syncthreads();
   if (warp == 0)
@@ -353,6 +379,25 @@ extern "C" int hdy_multiscale_roi_align_tf32x3(const hdy_feature_level_t* levels
   cudaStream_t st = (cudaStream_t)stream;
   if (pooled * pooled > kTcRows)  // (the A operand holds 200 rows: pooled <= 14; 15 and 16 take the exact kernel)
     return launch_roi_align_exact(L, bs, channels, rois, level_of, K, pooled, sampling_ratio, aligned, out, nullptr, st);
+  // one tensor map per level: [bs][C][H][W] fp32, box {12, 6, 64, 1}; TMA wants the base and every stride 16-byte granular
+  TcMaps maps;
+  memset(&maps, 0, sizeof(maps));
+  uint32_t level_mask = 0;
+  EncodeTiledFn enc = tensor_map_encoder();
+  for (int i = 0; enc && i < nl; ++i) {
+    const cuuint64_t w = (cuuint64_t)L.w[i], h = (cuuint64_t)L.h[i];
+    if ((w * 4 & 15) != 0 || ((uintptr_t)L.data[i] & 15) != 0) continue;
+    const cuuint64_t dims[4] = {w, h, (cuuint64_t)channels, (cuuint64_t)bs};
+    const cuuint64_t strides[3] = {w * 4, w * h * 4, w * h * (cuuint64_t)channels * 4};
+    const cuuint32_t box[4] = {kTcRawX, kTcSpan, kTcN, 1};
+    const cuuint32_t estr[4] = {1, 1, 1, 1};
+    if (enc(&maps.m[i], CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, const_cast<float*>(L.data[i]), dims, strides, box, estr,
+            CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+            CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS)
+      level_mask |= 1u << i;
+  }
+  if (!level_mask)
+    return launch_roi_align_exact(L, bs, channels, rois, level_of, K, pooled, sampling_ratio, aligned, out, nullptr, st);
   int dev = 0, sms = 148;
   cudaGetDevice(&dev);
   cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
@@ -374,11 +419,11 @@ extern "C" int hdy_multiscale_roi_align_tf32x3(const hdy_feature_level_t* levels
   }
   const unsigned grid = (unsigned)(K < 2ll * sms ? K : 2ll * sms);
   if (pooled == 14)
-    roi_align_tc_kernel<14><<<grid, kTcThreads, kTcSmem, st>>>(L, bs, channels, rois, level_of, (long long)K, pooled,
-                                                               sampling_ratio, aligned, out, fallback);
+    roi_align_tc_kernel<14><<<grid, kTcThreads, kTcSmem, st>>>(maps, L, bs, channels, rois, level_of, (long long)K, pooled,
+                                                               sampling_ratio, aligned, out, fallback, level_mask);
   else
-    roi_align_tc_kernel<0><<<grid, kTcThreads, kTcSmem, st>>>(L, bs, channels, rois, level_of, (long long)K, pooled,
-                                                              sampling_ratio, aligned, out, fallback);
+    roi_align_tc_kernel<0><<<grid, kTcThreads, kTcSmem, st>>>(maps, L, bs, channels, rois, level_of, (long long)K, pooled,
+                                                              sampling_ratio, aligned, out, fallback, level_mask);
   rc = check_launch("hdy_multiscale_roi_align_tf32x3");
   if (rc) return rc;
   // the RoIs the tensor-core path left (windows over 6 x 6 taps, dead rows): exact kernel over the list
