@@ -71,7 +71,7 @@ struct TcTables {
   float wx[kRoiMaxM][8];
   unsigned long long mbar;
   unsigned long long ring_bar;
-  int ylo, yhi, xlo, xhi;
+  int bnd[2][4];   // window of all taps (ylo, yhi, xlo, xhi), ping-pong over consecutive RoIs
   uint32_t tmem_base;
 };
 constexpr size_t kTcSmem = 2 * kTcABytes + 2 * kTcBBytes + kTcRawBytes + sizeof(TcTables);
@@ -143,6 +143,7 @@ __global__ void __launch_bounds__(kTcThreads, 2) roi_align_tc_kernel(
                  : "memory");
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
   }
+  if (t < 8) T.bnd[t >> 2][t & 3] = (t & 1) ? -1 : INT_MAX;
   if (t == 0) {
     mbar_init(reinterpret_cast<uint64_t*>(&T.mbar), 1);
     mbar_init(reinterpret_cast<uint64_t*>(&T.ring_bar), 1);
@@ -161,21 +162,29 @@ __global__ void __launch_bounds__(kTcThreads, 2) roi_align_tc_kernel(
   uint32_t phase = 0, ring_phase = 0;
   const float inv_s = 1.0f / (float)S;
 
+  // the RoI row (image, box) and its level id are read one RoI ahead: their global-load latency sat at the head of every
+  // RoI's dependency chain
+  float nr[5] = {0.f, 0.f, 0.f, 0.f, 0.f}, nlv = 0.f;
+  if ((long long)blockIdx.x < K) {
+#pragma unroll
+    for (int i = 0; i < 5; ++i) nr[i] = __ldg(rois + (long long)blockIdx.x * 5 + i);
+    nlv = level_of ? __ldg(level_of + blockIdx.x) : 0.f;
+  }
+  int it = 0;
   for (long long n = blockIdx.x; n < K; n += gridDim.x) {
-    const float* r = rois + n * 5;
-    const int lvl = level_of ? (int)level_of[n] : 0;
-    const bool lvl_ok = level_of ? (level_of[n] == (float)lvl && lvl >= 0 && lvl < L.nl) : true;
+    const float r[5] = {nr[0], nr[1], nr[2], nr[3], nr[4]};
+    const float lv_f = nlv;
+    if (n + gridDim.x < K) {
+#pragma unroll
+      for (int i = 0; i < 5; ++i) nr[i] = __ldg(rois + (n + gridDim.x) * 5 + i);
+      nlv = level_of ? __ldg(level_of + n + gridDim.x) : 0.f;
+    }
+    const int lvl = level_of ? (int)lv_f : 0;
+    const bool lvl_ok = level_of ? (lv_f == (float)lvl && lvl >= 0 && lvl < L.nl) : true;
     const int b = (int)r[0];
     const bool live = lvl_ok && b >= 0 && b < bs;
     const int H = live ? L.h[lvl] : 1, W = live ? L.w[lvl] : 1;
-    __syncthreads();  // everybody is done with the previous RoI's window bounds (also on the fallback `continue`)
-    if (t == 0) {
-      T.ylo = INT_MAX;
-      T.xlo = INT_MAX;
-      T.yhi = -1;
-      T.xhi = -1;
-    }
-    __syncthreads();
+    int* const bnd = T.bnd[it & 1];   // (reset one RoI ago, after everybody had read it for the last time)
     // ---- sample tables: threads [0, M*S) the y axis, [128, 128 + M*S) the x axis
     if (live && (t & 127) < M * S) {
       const float scale = L.scale[lvl], off = aligned ? 0.5f : 0.0f;
@@ -189,17 +198,26 @@ __global__ void __launch_bounds__(kTcThreads, 2) roi_align_tc_kernel(
       const SampleTab Sa = roi_sample(s0, bin, i / S, i % S, S, isx ? W : H);
       (isx ? T.xtab : T.ytab)[i] = Sa;
       if (Sa.low >= 0) {
-        atomicMin(isx ? &T.xlo : &T.ylo, Sa.low);
-        atomicMax(isx ? &T.xhi : &T.yhi, Sa.high);
+        atomicMin(&bnd[isx ? 2 : 0], Sa.low);
+        atomicMax(&bnd[isx ? 3 : 1], Sa.high);
       }
     }
     __syncthreads();
-    const int ylo = T.ylo, xlo = T.xlo;
-    const int span_h = T.yhi - ylo + 1, span_w = T.xhi - xlo + 1;
+    const int ylo = bnd[0], xlo = bnd[2], yhi = bnd[1], xhi = bnd[3];
+    const int span_h = yhi - ylo + 1, span_w = xhi - xlo + 1;
+    if (t == 0) {   // the other slot, for the next RoI: its readers are all past the barrier above
+      int* const o = T.bnd[(it & 1) ^ 1];
+      o[0] = INT_MAX;
+      o[1] = -1;
+      o[2] = INT_MAX;
+      o[3] = -1;
+    }
+    ++it;
     // dead rows (zero-filled by the reference), all-zero weights and windows over 6 x 6 go to the exact kernel
     // ... and so do the levels without a tensor map (row pitch not a multiple of 16 bytes)
-    if (!(live && T.yhi >= 0 && T.xhi >= 0 && span_h <= kTcSpan && span_w <= kTcSpan && ((level_mask >> lvl) & 1))) {
+    if (!(live && yhi >= 0 && xhi >= 0 && span_h <= kTcSpan && span_w <= kTcSpan && ((level_mask >> lvl) & 1))) {
       if (t == 0) fallback[1 + atomicAdd(fallback, 1)] = (int32_t)n;
+      __syncthreads();  // (the reset of the other slot lands before the next RoI's atomics)
       continue;
     }
     // ---- per-axis weights over the window: the mean over the bin's S samples of the bilinear tap weights
@@ -336,14 +354,15 @@ __global__ void __launch_bounds__(kTcThreads, 2) roi_align_tc_kernel(
     const int bin0 = mt * 128 + q * 32, bin = bin0 + lane;                                                         \
     float* o = out + ((size_t)n * C + (size_t)(sl) * kTcN) * bins;                                                 \
     if (mt < n_mt && bin0 < bins) {                                                                                \
-      _Pragma("unroll 1") for (int cc = 0; cc < kTcN / 32; ++cc) {                                                 \
-        uint32_t v[32];                                                                                            \
-        tc_ld32(tmem + ((uint32_t)(q * 32) << 16) + (uint32_t)((P) * 2 * kTcN + mt * kTcN + cc * 32), v);          \
-        asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");                                               \
-        if (bin < bins) {                                                                                          \
-          _Pragma("unroll") for (int j = 0; j < 32; ++j)                                                           \
-              __stcs(o + (size_t)(cc * 32 + j) * bins + bin, __uint_as_float(v[j]));                               \
-        }                                                                                                          \
+      uint32_t v0[32], v1[32];                                                                                     \
+      const uint32_t ta = tmem + ((uint32_t)(q * 32) << 16) + (uint32_t)((P) * 2 * kTcN + mt * kTcN);              \
+      tc_ld32(ta, v0);                                                                                             \
+      tc_ld32(ta + 32, v1);                                                                                        \
+      asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");                                                 \
+      if (bin < bins) {                                                                                            \
+        _Pragma("unroll") for (int j = 0; j < 32; ++j) __stcs(o + (size_t)j * bins + bin, __uint_as_float(v0[j])); \
+        _Pragma("unroll") for (int j = 0; j < 32; ++j)                                                             \
+            __stcs(o + (size_t)(32 + j) * bins + bin, __uint_as_float(v1[j]));                                     \
       }                                                                                                            \
     }                                                                                                              \
   }
