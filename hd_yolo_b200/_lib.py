@@ -120,8 +120,8 @@ SIGNATURES = {
     "hdy_regroup_kept": (_i, [_vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _vp, _vp, _vp, _vp, _vp, _vp]),
     "hdy_merge_gather": (_i, [_vp, _vp, _i64, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
     "hdy_multiscale_roi_align": (_i, [C.POINTER(FeatureLevel), _i, _i, _i, _vp, _vp, _i64, _i, _i, _i, _vp, _vp]),
-    "hdy_multiscale_roi_align_tf32x3": (_i, [C.POINTER(FeatureLevel), _i, _i, _i, _vp, _vp, _i64, _i, _i, _i, _vp, _vp,
-                                            _vp]),
+    "hdy_multiscale_roi_align_tf32x3": (_i, [C.POINTER(FeatureLevel), _i, _i, _i, _i, _vp, _vp, _i64, _i, _i, _i, _vp,
+                                            _vp, _vp]),
     "hdy_match_pairs": (_i, [_vp, _vp, _vp, _i, _i, _vp, _vp, _i, _f, _i, _vp, _vp, _vp, _vp, _vp]),
     "hdy_box_iou": (_i, [_vp, _i64, _vp, _i64, _vp, _vp]),
 }

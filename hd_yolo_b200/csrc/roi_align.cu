@@ -42,7 +42,7 @@ struct RoiSmem {
 
 template <int S, bool STAGED>
 __device__ __forceinline__ void roi_rows(const RoiSmem& Sm, const float* __restrict__ base, int plane, int pitch,
-                                         int ylo, int xlo, int M, int ph, float count, float* __restrict__ st0,
+                                         int sx, int ylo, int xlo, int M, int ph, float count, float* __restrict__ st0,
                                          float* __restrict__ st1) {
   // this thread's 2S feature rows (two per y sample) and their weights
   int roff[2 * S];
@@ -74,10 +74,10 @@ __device__ __forceinline__ void roi_rows(const RoiSmem& Sm, const float* __restr
             v1[k][0] = base[plane + roff[k] + cl];
             v1[k][1] = base[plane + roff[k] + chh];
           } else {
-            v0[k][0] = __ldg(base + roff[k] + cl);
-            v0[k][1] = __ldg(base + roff[k] + chh);
-            v1[k][0] = __ldg(base + plane + roff[k] + cl);
-            v1[k][1] = __ldg(base + plane + roff[k] + chh);
+            v0[k][0] = __ldg(base + roff[k] + cl * sx);
+            v0[k][1] = __ldg(base + roff[k] + chh * sx);
+            v1[k][0] = __ldg(base + plane + roff[k] + cl * sx);
+            v1[k][1] = __ldg(base + plane + roff[k] + chh * sx);
           }
         }
       }
@@ -175,18 +175,20 @@ __device__ __forceinline__ void roi_align_one(RoiSmem& Sm, const RoiLevels& L, i
   const int ylo = Sm.ylo, xlo = Sm.xlo;
   const int wh = Sm.yhi - ylo + 1, ww = Sm.xhi - xlo + 1;
   const bool staged = wh * ww <= kWinMax;
-  const float* feat = L.data[lvl] + ((size_t)b * C + cbase) * H * W;
+  // element (c, y, x) of image b: NCHW  b*C*H*W + c*H*W + y*W + x;  channels-last  b*H*W*C + (y*W + x)*C + c
+  const int sc = L.nhwc ? 1 : H * W, sy = L.nhwc ? W * C : W, sx = L.nhwc ? C : 1;
+  const float* feat = L.data[lvl] + (size_t)b * C * H * W + (size_t)cbase * sc;
   if (staged) {
     const int per = wh * ww;
     // lane = channel, warps stride over the window elements: the element index (and its row / column split) is
     // warp-uniform, so no per-thread division is left in this loop
     const int nwarp = blockDim.x >> 5;
     if (lane < nch) {
-      const float* src = feat + (size_t)lane * H * W + (size_t)ylo * W + xlo;
+      const float* src = feat + (size_t)lane * sc + (size_t)ylo * sy + (size_t)xlo * sx;
       float* dstw = Sm.win + lane * per;
       for (int e = warp; e < per; e += nwarp) {
         const int y = e / ww, x = e - y * ww;
-        dstw[e] = __ldg(src + (size_t)y * W + x);
+        dstw[e] = __ldg(src + (size_t)y * sy + (size_t)x * sx);
       }
     }
     // the odd channel of the last pair of a ragged chunk reads defined values
@@ -200,9 +202,9 @@ __device__ __forceinline__ void roi_align_one(RoiSmem& Sm, const RoiLevels& L, i
     float* st0 = &Sm.stage[(2 * cp) * MM + ph * M];
     float* st1 = st0 + MM;
     if (staged)
-      roi_rows<S, true>(Sm, Sm.win + (2 * cp) * (wh * ww), wh * ww, ww, ylo, xlo, M, ph, count, st0, st1);
+      roi_rows<S, true>(Sm, Sm.win + (2 * cp) * (wh * ww), wh * ww, ww, 1, ylo, xlo, M, ph, count, st0, st1);
     else  // the odd channel of a ragged last pair re-reads the even one (its results are not written)
-      roi_rows<S, false>(Sm, feat + (size_t)(2 * cp) * H * W, (2 * cp + 1 < nch) ? H * W : 0, W, 0, 0, M, ph, count,
+      roi_rows<S, false>(Sm, feat + (size_t)(2 * cp) * sc, (2 * cp + 1 < nch) ? sc : 0, sy, sx, 0, 0, M, ph, count,
                          st0, st1);
   }
   __syncthreads();

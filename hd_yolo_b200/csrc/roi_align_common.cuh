@@ -13,6 +13,7 @@ struct RoiLevels {
   int h[HDY_MAX_LEVELS], w[HDY_MAX_LEVELS];
   float scale[HDY_MAX_LEVELS];
   int nl;
+  int nhwc;   // 0: [bs][C][h][w] (the reference's layout); 1: channels-last [bs][h][w][C] (tf32x3 entry point only)
 };
 
 struct SampleTab {

@@ -44,15 +44,15 @@ constexpr int kTcSpan = 6;                      // tap window per axis on the te
 constexpr int kTcK = 40;                        // 36 window pixels, padded to whole K steps of 8
 constexpr int kTcKc = kTcK / 4;                 // 16-byte K chunks
 constexpr int kTcKSteps = kTcK / 8;
-constexpr int kTcRows = 200;                    // A rows held (bins <= 196 in 25 groups of 8); see the over-read note
+constexpr int kTcRows = 196;                    // A rows held (pooled <= 14); see the over-read note
 constexpr int kTcN = 64;                        // channels per MMA (N): one slice of the RoI's channels
 constexpr int kTcALbo = kTcRows * 16;           // bytes between the K chunks of A
 constexpr int kTcBLbo = kTcN * 16 + 16;         // ... of B; +16: a channel's consecutive k land in consecutive banks
-constexpr int kTcABytes = kTcKc * kTcALbo;      // 32 000
+constexpr int kTcABytes = kTcKc * kTcALbo;      // 31 360
 constexpr int kTcBBytes = kTcKc * kTcBLbo;      // 10 400
 constexpr int kTcCols = 256;                    // TMEM columns: 2 accumulator buffers x 2 M tiles x 64 channels (fp32)
 // Over-read: the second M tile's descriptor covers rows 128..255 but only rows < bins are written.  What the MMA reads
-// past row 199 of a chunk is the next chunk / the next buffer (A_hi -> A_lo -> the TMA ring, all inside this CTA's shared
+// past row 195 of a chunk is the next chunk / the next buffer (A_hi -> A_lo -> the TMA ring, all inside this CTA's shared
 // memory): finite or not, it only reaches accumulator rows >= bins, which nobody loads.
 
 // The TMA box: its global origin must be 16-byte aligned (an unaligned x origin is an illegal-instruction fault, probed
@@ -61,8 +61,18 @@ constexpr int kTcRawX = 12;
 constexpr int kTcRawBytes = kTcN * kTcSpan * kTcRawX * 4;   // one slice's window, [channel][6][12] fp32: 18 432
 
 struct TcMaps {
-  CUtensorMap m[HDY_MAX_LEVELS];   // per level: [bs][C][H][W] fp32, box {12, 6, 64, 1}
+  CUtensorMap m[HDY_MAX_LEVELS];   // per level; NCHW: box {12, 6, 64, 1}; channels-last: box {32 ch, 6, 6, 1}, 128B swizzle
 };
+
+// Channels-last features ([bs][h][w][C]; torch.channels_last): a window row is 6 x C contiguous floats, so a TMA box
+// {32 channels, 6, 6} is 36 requests of 128 bytes instead of 384 of 48, and its origin needs no alignment slack.  With the
+// 128-byte swizzle it lands as [k = 36 window pixels][32 channels] rows of 128 bytes, 16-byte chunk j of row k stored at
+// chunk j ^ (k & 7) (checked with tools/probe/tma_nhwc_probe.cu); the split pass reads it back with lane = channel
+// (conflict-free) and writes the same K-major (hi, lo) operand as the NCHW path, one 16-byte K chunk per store.
+// (Feeding the swizzled rows to the MMA directly as an MN-major SWIZZLE_128B operand returned zeros; not pursued.)
+constexpr int kTcNhBlk = 40 * 128;              // one 32-channel block of a ring buffer: 36 rows, 1 024-byte aligned pitch
+constexpr int kTcNhRing = 2 * kTcNhBlk;         // one ring buffer: a slice's 64 channels
+constexpr int kTcNhA0 = (2 * kTcABytes + 1023) / 1024 * 1024;   // swizzled buffers are 1 024-byte aligned
 
 struct TcTables {
   SampleTab ytab[kRoiMaxM * kRoiMaxS];
@@ -70,15 +80,15 @@ struct TcTables {
   float wy[kRoiMaxM][8];
   float wx[kRoiMaxM][8];
   unsigned long long mbar;
-  unsigned long long ring_bar;
+  unsigned long long ring_bar[2];
   int bnd[2][4];   // window of all taps (ylo, yhi, xlo, xhi), ping-pong over consecutive RoIs
   uint32_t tmem_base;
 };
-constexpr size_t kTcSmem = 2 * kTcABytes + 2 * kTcBBytes + kTcRawBytes + sizeof(TcTables);
-static_assert(kTcSmem <= 113 * 1024, "two CTAs per SM");
-static_assert(56 * 16 <= kTcRawBytes, "over-read of the last A chunk stays inside smem");
+constexpr size_t kTcSmemNchw = 2 * kTcABytes + 2 * kTcBBytes + kTcRawBytes + sizeof(TcTables);
+constexpr size_t kTcSmemNhwc = kTcNhA0 + 2 * kTcNhRing + 2 * kTcBBytes + sizeof(TcTables);
+static_assert(kTcSmemNchw <= 113 * 1024 && kTcSmemNhwc <= 113 * 1024, "two CTAs per SM");
+static_assert(60 * 16 <= kTcRawBytes, "over-read of the last A chunk stays inside smem");
 static_assert((2 * kTcABytes) % 128 == 0 && kTcRawBytes % 128 == 0, "TMA destinations are 128-byte aligned");
-
 
 // round to nearest tf32 (10 mantissa bits; ties away from zero, like cvt.rna.tf32.f32) with two integer-pipe
 // instructions: the cvt runs on the quarter-rate conversion pipe and was 16 % of the kernel's stall samples
@@ -96,14 +106,15 @@ __device__ __forceinline__ uint64_t tc_desc(uint32_t smem_addr, uint32_t lbo, ui
 // M >> 4 at bit 24
 constexpr uint32_t kTcIdesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(kTcN >> 3) << 17) | ((128u >> 4) << 24);
 
-__device__ __forceinline__ void tc_mma(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t accumulate) {
+__device__ __forceinline__ void tc_mma(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc,
+                                       uint32_t accumulate) {
   asm volatile(
       "{\n\t"
       ".reg .pred p;\n\t"
       "setp.ne.b32 p, %4, 0;\n\t"
       "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t"
       "}\n" ::"r"(d_tmem),
-      "l"(adesc), "l"(bdesc), "r"(kTcIdesc), "r"(accumulate)
+      "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
       : "memory");
 }
 
@@ -122,16 +133,18 @@ __device__ __forceinline__ void tc_ld32(uint32_t taddr, uint32_t (&v)[32]) {
 // MC: the pooled size when it is the reference's 14 (compile-time: the epilogue's 128 stores per warp then take
 // immediate offsets -- with a run-time row pitch the address arithmetic was 8 of every 9 instructions of the kernel's
 // hottest line), else 0 (run-time M)
-template <int MC>
+template <int MC, bool NHWC>
 __global__ void __launch_bounds__(kTcThreads, 2) roi_align_tc_kernel(
     const __grid_constant__ TcMaps maps, const RoiLevels L, int bs, int C, const float* __restrict__ rois, const float* __restrict__ level_of, long long K,
     int M_rt, int S, int aligned, float* __restrict__ out, int32_t* __restrict__ fallback, uint32_t level_mask) {
   const int M = MC ? MC : M_rt;
-  extern __shared__ __align__(128) unsigned char tc_smem[];
+  extern __shared__ __align__(1024) unsigned char tc_smem[];
   unsigned char* const A_hi = tc_smem;
   unsigned char* const A_lo = A_hi + kTcABytes;
-  unsigned char* const raw = A_lo + kTcABytes;   // the next slice's window, filled by TMA (128-byte aligned: 64 000)
-  unsigned char* const B_hi = raw + kTcRawBytes;
+  // NCHW: [A_hi | A_lo | TMA window (128-byte aligned) | B_hi | B_lo | tables]
+  // NHWC: [A_hi | A_lo | pad to 1 KB | TMA ring 0 | TMA ring 1 | B_hi | B_lo | tables]
+  unsigned char* const raw = NHWC ? tc_smem + kTcNhA0 : A_lo + kTcABytes;
+  unsigned char* const B_hi = raw + (NHWC ? 2 * kTcNhRing : kTcRawBytes);
   unsigned char* const B_lo = B_hi + kTcBBytes;
   TcTables& T = *reinterpret_cast<TcTables*>(B_lo + kTcBBytes);
   const int t = threadIdx.x, lane = t & 31, warp = t >> 5;
@@ -146,7 +159,8 @@ __global__ void __launch_bounds__(kTcThreads, 2) roi_align_tc_kernel(
   if (t < 8) T.bnd[t >> 2][t & 3] = (t & 1) ? -1 : INT_MAX;
   if (t == 0) {
     mbar_init(reinterpret_cast<uint64_t*>(&T.mbar), 1);
-    mbar_init(reinterpret_cast<uint64_t*>(&T.ring_bar), 1);
+    mbar_init(reinterpret_cast<uint64_t*>(&T.ring_bar[0]), 1);
+    mbar_init(reinterpret_cast<uint64_t*>(&T.ring_bar[1]), 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   // the padding columns k = 36..39 of B are never written again: zero (their A weights are zero, but 0 * garbage
@@ -159,7 +173,7 @@ __global__ void __launch_bounds__(kTcThreads, 2) roi_align_tc_kernel(
   __syncthreads();
   asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
   const uint32_t tmem = T.tmem_base;
-  uint32_t phase = 0, ring_phase = 0;
+  uint32_t phase = 0, ring_phase = 0;   // (bit r of ring_phase: parity of TMA buffer r's next completion)
   const float inv_s = 1.0f / (float)S;
 
   // the RoI row (image, box) and its level id are read one RoI ahead: their global-load latency sat at the head of every
@@ -239,11 +253,13 @@ __global__ void __launch_bounds__(kTcThreads, 2) roi_align_tc_kernel(
       }
     }
     __syncthreads();
-    // ---- B: the window of a 64-channel slice ([64][6][12] fp32, out-of-range zero-filled) comes by ONE TMA tensor load,
-    // one slice ahead of the tensor cores -- no LDG, no L1: with per-thread loads the 24-byte rows cost ~7 cache lines
-    // per warp instruction and the LSU, shared with the epilogue's stores, set the pace.
-    // Thread t < 252 then moves window pixel k = t % 36 (= jy * 6 + jx) of channels t / 36 + 7 i from the TMA buffer into
-    // the (hi, lo) core-matrix layout: its tap validity and both shared-memory offsets are fixed for the RoI.
+    // ---- B.  NCHW: the window of a 64-channel slice ([64][6][12] fp32, out-of-range zero-filled) comes by ONE TMA tensor
+    // load, one slice ahead of the tensor cores -- no LDG, no L1: with per-thread loads the 24-byte rows cost ~7 cache
+    // lines per warp instruction and the LSU, shared with the epilogue's stores, set the pace.  Thread t < 252 then moves
+    // window pixel k = t % 36 (= jy * 6 + jx) of channels t / 36 + 7 i from the TMA buffer into the (hi, lo) core-matrix
+    // layout: its tap validity and both shared-memory offsets are fixed for the RoI.
+    // Channels-last: two TMA loads ({32 channels, 6, 6}, swizzled) per slice into a ring of two buffers, two slices
+    // ahead; the split streams float4s (see kTcNhBlk).
     constexpr int kKK = kTcSpan * kTcSpan, kCg = kTcThreads / kKK, kEl = (kTcN + kCg - 1) / kCg;   // 36, 7, 10
     const int bk = t % kKK, bc = t / kKK;
     const int bjy = bk / kTcSpan, bjx = bk - bjy * kTcSpan;
@@ -252,11 +268,24 @@ __global__ void __launch_bounds__(kTcThreads, 2) roi_align_tc_kernel(
     const int b_raw = ((bc * kTcSpan + bjy) * kTcRawX + (xlo & 3) + bjx) * 4;
 #define HDY_TC_LOAD(sl)                                                                                          \
   if (t == 0) {                                                                                                  \
-    uint64_t* bar = reinterpret_cast<uint64_t*>(&T.ring_bar);                                                    \
-    mbar_arrive_expect_tx(bar, kTcRawBytes);                                                                     \
-    tma_load_4d(raw, &maps.m[lvl], xlo & ~3, ylo, (sl) * kTcN, b, bar);                                          \
+    if constexpr (NHWC) {                                                                                        \
+      uint64_t* bar = reinterpret_cast<uint64_t*>(&T.ring_bar[(sl) & 1]);                                        \
+      unsigned char* dst = raw + ((sl) & 1) * kTcNhRing;                                                         \
+      mbar_arrive_expect_tx(bar, 2 * 36 * 128);                                                                  \
+      tma_load_4d(dst, &maps.m[lvl], (sl) * kTcN, xlo, ylo, b, bar);                                             \
+      tma_load_4d(dst + kTcNhBlk, &maps.m[lvl], (sl) * kTcN + 32, xlo, ylo, b, bar);                             \
+    } else {                                                                                                     \
+      uint64_t* bar = reinterpret_cast<uint64_t*>(&T.ring_bar[0]);                                               \
+      mbar_arrive_expect_tx(bar, kTcRawBytes);                                                                   \
+      tma_load_4d(raw, &maps.m[lvl], xlo & ~3, ylo, (sl) * kTcN, b, bar);                                        \
+    }                                                                                                            \
   }
     HDY_TC_LOAD(0)
+    if constexpr (NHWC) {
+      if (1 < slices) {
+        HDY_TC_LOAD(1)
+      }
+    }
     // ---- A: thread = output bin, k = jy * 6 + jx
     if (t < bins) {
       const int py = t / M, px = t - py * M;
@@ -281,9 +310,35 @@ __global__ void __launch_bounds__(kTcThreads, 2) roi_align_tc_kernel(
       }
     }
     // split: registers -> B (hi, lo) in the core-matrix layout
-#define HDY_TC_SPLIT()                                                                                   \
-  {                                                                                                      \
-    while (!mbar_try_wait(reinterpret_cast<uint64_t*>(&T.ring_bar), ring_phase)) {                       \
+#define HDY_TC_SPLIT(sl)                                                                                 \
+  if constexpr (NHWC) {                                                                                  \
+    const int rb = (sl) & 1;                                                                             \
+    while (!mbar_try_wait(reinterpret_cast<uint64_t*>(&T.ring_bar[rb]), (ring_phase >> rb) & 1)) {       \
+    }                                                                                                    \
+    ring_phase ^= 1u << rb;                                                                              \
+    _Pragma("unroll") for (int j = 0; j < 3; ++j) {                                                      \
+      const int idx = t + j * kTcThreads; /* item = (K chunk of 4 window pixels, channel): 9 x 64 */     \
+      if (idx < 9 * kTcN) {                                                                              \
+        const int c = idx & (kTcN - 1), kc = idx >> 6;                                                   \
+        const unsigned char* blk = raw + rb * kTcNhRing + (c >> 5) * kTcNhBlk + (c & 3) * 4;             \
+        const int cj = (c & 31) >> 2;                                                                    \
+        float v[4];                                                                                      \
+        _Pragma("unroll") for (int e = 0; e < 4; ++e) {                                                  \
+          const int k = kc * 4 + e, jy = k / kTcSpan, jx = k - jy * kTcSpan;                             \
+          v[e] = (jy < span_h && jx < span_w)                                                            \
+                     ? *reinterpret_cast<const float*>(blk + k * 128 + ((cj ^ (k & 7)) << 4))            \
+                     : 0.f;                                                                              \
+        }                                                                                                \
+        float4 hi, lo;                                                                                   \
+        hi.x = tf32_rna(v[0]), hi.y = tf32_rna(v[1]), hi.z = tf32_rna(v[2]), hi.w = tf32_rna(v[3]);      \
+        lo.x = tf32_rna(v[0] - hi.x), lo.y = tf32_rna(v[1] - hi.y);                                      \
+        lo.z = tf32_rna(v[2] - hi.z), lo.w = tf32_rna(v[3] - hi.w);                                      \
+        *reinterpret_cast<float4*>(B_hi + kc * kTcBLbo + c * 16) = hi;                                   \
+        *reinterpret_cast<float4*>(B_lo + kc * kTcBLbo + c * 16) = lo;                                   \
+      }                                                                                                  \
+    }                                                                                                    \
+  } else {                                                                                               \
+    while (!mbar_try_wait(reinterpret_cast<uint64_t*>(&T.ring_bar[0]), ring_phase & 1)) {                \
     }                                                                                                    \
     ring_phase ^= 1u;                                                                                    \
     if (b_on) {                                                                                          \
@@ -311,7 +366,7 @@ __global__ void __launch_bounds__(kTcThreads, 2) roi_align_tc_kernel(
         const uint32_t b0 = term == 1 ? b_lo : b_hi;                                                              \
         _Pragma("unroll") for (int ks = 0; ks < kTcKSteps; ++ks) {                                                \
           tc_mma(d, tc_desc(a0 + ks * 2 * kTcALbo, kTcALbo, 128), tc_desc(b0 + ks * 2 * kTcBLbo, kTcBLbo, 128),   \
-                 acc);                                                                                            \
+                 kTcIdesc, acc);                                                                                  \
           acc = 1;                                                                                                \
         }                                                                                                         \
       }                                                                                                           \
@@ -323,13 +378,13 @@ __global__ void __launch_bounds__(kTcThreads, 2) roi_align_tc_kernel(
     // Pipeline over the slices: the MMAs of slice sl + 1 (other accumulator buffer) run while the epilogue of slice sl
     // stores, and the loads of slice sl + 2 are in flight behind both.  B is single-buffered: it is rewritten only after
     // the mbarrier said the MMAs reading it are done.
-    HDY_TC_SPLIT()
+    HDY_TC_SPLIT(0)
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // generic-proxy writes -> visible to the MMA
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
     __syncthreads();  // (every warp is past the previous RoI's epilogue: both accumulator buffers are free)
     HDY_TC_ISSUE(0)
-    if (1 < slices) {
-      HDY_TC_LOAD(1)   // (the TMA buffer was read out before the barrier)
+    if ((NHWC ? 2 : 1) < slices) {
+      HDY_TC_LOAD(NHWC ? 2 : 1)   // (the TMA buffer was read out before the barrier)
     }
     // one slice: wait for its MMAs; hand slice sl + 1 to the tensor cores; start the load of slice sl + 2; then store
     // slice sl from accumulator buffer P
@@ -339,13 +394,13 @@ __global__ void __launch_bounds__(kTcThreads, 2) roi_align_tc_kernel(
     }                                                                                                              \
     phase ^= 1;                                                                                                    \
     if ((sl) + 1 < slices) {                                                                                       \
-      HDY_TC_SPLIT()                                                                                               \
+      HDY_TC_SPLIT((sl) + 1)                                                                                       \
       asm volatile("fence.proxy.async.shared::cta;" ::: "memory");                                                 \
       asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");                                             \
       __syncthreads(); /* every warp is past the epilogue of slice sl - 1, which read the buffer written next */   \
       HDY_TC_ISSUE(1 - (P))                                                                                        \
-      if ((sl) + 2 < slices) {                                                                                     \
-        HDY_TC_LOAD((sl) + 2)                                                                                      \
+      if ((sl) + (NHWC ? 3 : 2) < slices) {                                                                        \
+        HDY_TC_LOAD((sl) + (NHWC ? 3 : 2))                                                                         \
       }                                                                                                            \
     }                                                                                                              \
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");                                                \
@@ -384,36 +439,50 @@ __global__ void __launch_bounds__(kTcThreads, 2) roi_align_tc_kernel(
 }  // namespace hdy
 
 extern "C" int hdy_multiscale_roi_align_tf32x3(const hdy_feature_level_t* levels_host, int nl, int bs, int channels,
-                                               const float* rois, const float* level_of, int64_t K, int pooled,
-                                               int sampling_ratio, int aligned, float* out, int32_t* fallback,
-                                               hdy_stream_t stream) {
+                                               int channels_last, const float* rois, const float* level_of, int64_t K,
+                                               int pooled, int sampling_ratio, int aligned, float* out,
+                                               int32_t* fallback, hdy_stream_t stream) {
   using namespace hdy;
   RoiLevels L;
   int rc = roi_levels_from_host(levels_host, nl, &L);
   if (rc) return rc;
+  L.nhwc = channels_last ? 1 : 0;
   rc = roi_align_args_ok(bs, channels, rois, level_of, nl, K, pooled, sampling_ratio, out);
   if (rc || K == 0) return rc;
   HDY_REQUIRE(channels % kTcN == 0, "roi_align (tf32x3): channels=%d must be a multiple of %d", channels, kTcN);
   HDY_REQUIRE(fallback != nullptr, "roi_align (tf32x3): fallback scratch is NULL");
   cudaStream_t st = (cudaStream_t)stream;
-  if (pooled * pooled > kTcRows)  // (the A operand holds 200 rows: pooled <= 14; 15 and 16 take the exact kernel)
+  if (pooled * pooled > kTcRows)  // (the A operand holds 196 rows: pooled <= 14; 15 and 16 take the exact kernel)
     return launch_roi_align_exact(L, bs, channels, rois, level_of, K, pooled, sampling_ratio, aligned, out, nullptr, st);
-  // one tensor map per level: [bs][C][H][W] fp32, box {12, 6, 64, 1}; TMA wants the base and every stride 16-byte granular
+  // One tensor map per level; TMA wants the base and every stride 16-byte granular.
+  //   NCHW  [bs][C][H][W]: dims {W, H, C, bs}, box {12, 6, 64, 1}
+  //   NHWC  [bs][H][W][C]: dims {C, W, H, bs}, box {32, 6, 6, 1}, SWIZZLE_128B (32 channels = one 128-byte row)
   TcMaps maps;
   memset(&maps, 0, sizeof(maps));
   uint32_t level_mask = 0;
   EncodeTiledFn enc = tensor_map_encoder();
   for (int i = 0; enc && i < nl; ++i) {
-    const cuuint64_t w = (cuuint64_t)L.w[i], h = (cuuint64_t)L.h[i];
-    if ((w * 4 & 15) != 0 || ((uintptr_t)L.data[i] & 15) != 0) continue;
-    const cuuint64_t dims[4] = {w, h, (cuuint64_t)channels, (cuuint64_t)bs};
-    const cuuint64_t strides[3] = {w * 4, w * h * 4, w * h * (cuuint64_t)channels * 4};
-    const cuuint32_t box[4] = {kTcRawX, kTcSpan, kTcN, 1};
+    const cuuint64_t w = (cuuint64_t)L.w[i], h = (cuuint64_t)L.h[i], c = (cuuint64_t)channels, n = (cuuint64_t)bs;
+    if (((uintptr_t)L.data[i] & 15) != 0) continue;
     const cuuint32_t estr[4] = {1, 1, 1, 1};
-    if (enc(&maps.m[i], CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, const_cast<float*>(L.data[i]), dims, strides, box, estr,
-            CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
-            CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS)
-      level_mask |= 1u << i;
+    CUresult r;
+    if (L.nhwc) {
+      const cuuint64_t dims[4] = {c, w, h, n};
+      const cuuint64_t strides[3] = {c * 4, w * c * 4, h * w * c * 4};
+      const cuuint32_t box[4] = {32, kTcSpan, kTcSpan, 1};
+      r = enc(&maps.m[i], CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, const_cast<float*>(L.data[i]), dims, strides, box, estr,
+              CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+              CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    } else {
+      if ((w * 4 & 15) != 0) continue;
+      const cuuint64_t dims[4] = {w, h, c, n};
+      const cuuint64_t strides[3] = {w * 4, w * h * 4, w * h * c * 4};
+      const cuuint32_t box[4] = {kTcRawX, kTcSpan, kTcN, 1};
+      r = enc(&maps.m[i], CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, const_cast<float*>(L.data[i]), dims, strides, box, estr,
+              CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+              CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    }
+    if (r == CUDA_SUCCESS) level_mask |= 1u << i;
   }
   if (!level_mask)
     return launch_roi_align_exact(L, bs, channels, rois, level_of, K, pooled, sampling_ratio, aligned, out, nullptr, st);
@@ -422,9 +491,17 @@ extern "C" int hdy_multiscale_roi_align_tf32x3(const hdy_feature_level_t* levels
   cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
   static bool attr_set[64] = {};
   if (dev < 0 || dev >= 64 || !attr_set[dev]) {
-    cudaError_t e = cudaFuncSetAttribute(roi_align_tc_kernel<14>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kTcSmem);
+    cudaError_t e = cudaFuncSetAttribute(roi_align_tc_kernel<14, false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                         (int)kTcSmemNchw);
     if (e == cudaSuccess)
-      e = cudaFuncSetAttribute(roi_align_tc_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kTcSmem);
+      e = cudaFuncSetAttribute(roi_align_tc_kernel<0, false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                               (int)kTcSmemNchw);
+    if (e == cudaSuccess)
+      e = cudaFuncSetAttribute(roi_align_tc_kernel<14, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                               (int)kTcSmemNhwc);
+    if (e == cudaSuccess)
+      e = cudaFuncSetAttribute(roi_align_tc_kernel<0, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                               (int)kTcSmemNhwc);
     if (e != cudaSuccess) {
       set_error("roi_align (tf32x3) setup: %s", cudaGetErrorString(e));
       return HDY_ERR_CUDA;
@@ -437,12 +514,15 @@ extern "C" int hdy_multiscale_roi_align_tf32x3(const hdy_feature_level_t* levels
     return HDY_ERR_CUDA;
   }
   const unsigned grid = (unsigned)(K < 2ll * sms ? K : 2ll * sms);
-  if (pooled == 14)
-    roi_align_tc_kernel<14><<<grid, kTcThreads, kTcSmem, st>>>(maps, L, bs, channels, rois, level_of, (long long)K, pooled,
-                                                               sampling_ratio, aligned, out, fallback, level_mask);
-  else
-    roi_align_tc_kernel<0><<<grid, kTcThreads, kTcSmem, st>>>(maps, L, bs, channels, rois, level_of, (long long)K, pooled,
-                                                              sampling_ratio, aligned, out, fallback, level_mask);
+#define HDY_TC_LAUNCH(MC, NH, SMEM)                                                                                 \
+  roi_align_tc_kernel<MC, NH><<<grid, kTcThreads, SMEM, st>>>(maps, L, bs, channels, rois, level_of, (long long)K,  \
+                                                              pooled, sampling_ratio, aligned, out, fallback, level_mask)
+  if (L.nhwc) {
+    if (pooled == 14) HDY_TC_LAUNCH(14, true, kTcSmemNhwc); else HDY_TC_LAUNCH(0, true, kTcSmemNhwc);
+  } else {
+    if (pooled == 14) HDY_TC_LAUNCH(14, false, kTcSmemNchw); else HDY_TC_LAUNCH(0, false, kTcSmemNchw);
+  }
+#undef HDY_TC_LAUNCH
   rc = check_launch("hdy_multiscale_roi_align_tf32x3");
   if (rc) return rc;
   // the RoIs the tensor-core path left (windows over 6 x 6 taps, dead rows): exact kernel over the list

@@ -19,17 +19,24 @@ from .ops import DetectBatch, _call, _need_cuda, _stream
 __all__ = ["multiscale_roi_align", "roi_align", "batch_rois", "compute_outputs"]
 
 
-def _levels(features: Sequence[torch.Tensor], scales: Sequence[float]):
+def _levels(features: Sequence[torch.Tensor], scales: Sequence[float], allow_channels_last: bool = False):
+    """(level table, bs, channels, channels_last).  channels_last: every level is a [bs, C, h, w] tensor laid out
+    [bs][h][w][C] in memory (torch.channels_last); only the tf32x3 mode reads that layout."""
     if len(features) != len(scales):
         raise HdyError("one spatial scale per feature level")
     if not 1 <= len(features) <= _lib.HDY_MAX_LEVELS:
         raise HdyError(f"1..{_lib.HDY_MAX_LEVELS} feature levels")
     arr = (_lib.FeatureLevel * len(features))()
     bs, ch = None, None
+    plain = all(f.dim() == 4 and f.is_contiguous() for f in features)
+    cl = (not plain) and allow_channels_last and all(
+        f.dim() == 4 and f.is_contiguous(memory_format=torch.channels_last) for f in features)
     for i, f in enumerate(features):
         _need_cuda(f, f"features[{i}]")
-        if f.dim() != 4 or not f.is_contiguous():
-            raise HdyError(f"features[{i}] must be a contiguous [bs, C, h, w] tensor")
+        if not (plain or cl):
+            raise HdyError(f"features[{i}] must be a contiguous [bs, C, h, w] tensor" +
+                           (" (or all levels torch.channels_last)" if allow_channels_last else
+                            "; channels_last is read by mode='tf32x3' only"))
         if bs is None:
             bs, ch = int(f.shape[0]), int(f.shape[1])
         elif (bs, ch) != (int(f.shape[0]), int(f.shape[1])):
@@ -37,7 +44,7 @@ def _levels(features: Sequence[torch.Tensor], scales: Sequence[float]):
         arr[i].data = f.data_ptr()
         arr[i].h, arr[i].w = int(f.shape[2]), int(f.shape[3])
         arr[i].spatial_scale = float(scales[i])
-    return arr, bs, ch
+    return arr, bs, ch, cl
 
 
 def multiscale_roi_align(features: List[torch.Tensor], boxes: torch.Tensor, levels: Optional[torch.Tensor],
@@ -48,14 +55,16 @@ def multiscale_roi_align(features: List[torch.Tensor], boxes: torch.Tensor, leve
     mode "exact" (default): torchvision's operation order, bit-identical to its CPU op.  mode "tf32x3": the per-RoI
     [M*M x 36] x [36 x C] product on the tensor cores (tcgen05, 3xTF32 split, fp32 accumulation): ~1e-6 relative to
     the window's magnitude, several times faster; C must be a multiple of 64.  RoIs with tap windows over 6 x 6
-    feature pixels are computed by the exact kernel in either mode.
+    feature pixels are computed by the exact kernel in either mode.  In tf32x3 mode the levels may be
+    torch.channels_last tensors (same shape, [bs][h][w][C] in memory): the window rows are then contiguous and the
+    TMA loads several times cheaper -- the layout to keep the mask features in on B200.
 
     features: one [bs, C, h_i, w_i] tensor per level; boxes [K, 5] = (image index, x1, y1, x2, y2); levels [K] float
     level ids (the 'extra'[:, 0] column of nms_per_image); strides: buffer.stride per level (spatial_scale =
     1/stride, :295).  Returns [K, C, M, M] with M = output_size (the reference passes mask_output_size // 2); rows
     whose level id matches no level stay zero."""
     scales = [1.0 / float(s) for s in strides]
-    arr, bs, ch = _levels(features, scales)
+    arr, bs, ch, cl = _levels(features, scales, allow_channels_last=(mode == "tf32x3"))
     _need_cuda(boxes, "boxes")
     if boxes.dim() != 2 or boxes.shape[1] != 5:
         raise HdyError("boxes must be [K, 5] (image index, x1, y1, x2, y2)")
@@ -77,7 +86,7 @@ def multiscale_roi_align(features: List[torch.Tensor], boxes: torch.Tensor, leve
         if ch % 64:
             raise HdyError(f"mode 'tf32x3' needs a multiple of 64 channels, got {ch}")
         fallback = torch.empty((K + 1,), dtype=torch.int32, device=boxes.device)
-        _call("hdy_multiscale_roi_align_tf32x3", arr, len(features), bs, ch, ptr(boxes), ptr(lv), K, M,
+        _call("hdy_multiscale_roi_align_tf32x3", arr, len(features), bs, ch, int(cl), ptr(boxes), ptr(lv), K, M,
               int(sampling_ratio), int(bool(aligned)), ptr(out), ptr(fallback), _stream(), launches=2)
         return out
     if mode != "exact":

@@ -496,10 +496,11 @@ HDY_API int hdy_multiscale_roi_align(const hdy_feature_level_t* levels_host, int
  * hdy_multiscale_roi_align to ~1e-6 relative to the window's magnitude instead of bit for bit (the north star's
  * tolerance for box-derived quantities is 1e-5).  RoIs whose taps span more than 6 x 6 feature pixels, and rows the
  * reference leaves zero, are listed in `fallback` and computed by the exact kernel in the same call.
- *   channels must be a multiple of 64; pooled <= 14 (larger outputs run the exact kernel); fallback [K + 1] int32 scratch ([0] = number of listed RoIs afterwards). */
+ *   channels_last != 0: the feature maps are [bs][h][w][channels] in memory (torch.channels_last) -- the faster form:
+ *   a window row is contiguous, one TMA request per 128 bytes.  channels must be a multiple of 64; pooled <= 14 (larger outputs run the exact kernel); fallback [K + 1] int32 scratch ([0] = number of listed RoIs afterwards). */
 HDY_API int hdy_multiscale_roi_align_tf32x3(const hdy_feature_level_t* levels_host, int nl, int bs, int channels,
-                                            const float* rois, const float* level_of, int64_t K, int pooled,
-                                            int sampling_ratio, int aligned, float* out, int32_t* fallback,
+                                            int channels_last, const float* rois, const float* level_of, int64_t K,
+                                            int pooled, int sampling_ratio, int aligned, float* out, int32_t* fallback,
                                             hdy_stream_t stream);
 
 /* f2: the matching step of APMeter.add (metayolo/models/metrics.py:270-303) without the dense k x g matrix.

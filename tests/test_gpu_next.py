@@ -33,7 +33,8 @@ def test_roi_align_golden_bit_exact(cuda_device):
     (128, 13, 3, False, 6, 30),     # S = 3 (weights are thirds)
     (128, 11, 1, True, 6, 30),
 ])
-def test_roi_align_tf32x3_within_tolerance(cuda_device, C, M, S, aligned, lo, hi):
+@pytest.mark.parametrize("channels_last", [False, True])
+def test_roi_align_tf32x3_within_tolerance(cuda_device, C, M, S, aligned, lo, hi, channels_last):
     """mode='tf32x3' (tcgen05 3xTF32, roi_align_tc.cu) against the exact-order kernel on the same inputs: the north
     star's 1e-5 relative tolerance, measured against the magnitude of the taps (|w| . |f|, which bounds every partial
     sum); rows the reference leaves zero stay exactly zero; RoIs over 6 x 6 taps are bit-identical (exact kernel)."""
@@ -50,7 +51,8 @@ def test_roi_align_tf32x3_within_tolerance(cuda_device, C, M, S, aligned, lo, hi
     levels[0] = 0.0                                                 # (on a coarse level the far box is in range again)
     rois, levels = rois.to(cuda_device), levels.to(cuda_device)
     exact = hdy.multiscale_roi_align(feats, rois, levels, strides, M, S, aligned)
-    fast = hdy.multiscale_roi_align(feats, rois, levels, strides, M, S, aligned, mode="tf32x3")
+    feats_in = [f.contiguous(memory_format=torch.channels_last) for f in feats] if channels_last else feats
+    fast = hdy.multiscale_roi_align(feats_in, rois, levels, strides, M, S, aligned, mode="tf32x3")
     absf = hdy.multiscale_roi_align([f.abs() for f in feats], rois, levels, strides, M, S, aligned)   # sum |w| |f|
     err = (fast - exact).abs()
     assert bool((err <= 1e-5 * absf + 1e-30).all()), \
@@ -72,9 +74,15 @@ def test_roi_align_tf32x3_golden(cuda_device):
     exact = hdy.multiscale_roi_align(feats, boxes, levels, g["strides"].tolist())
     fast = hdy.multiscale_roi_align(feats, boxes, levels, g["strides"].tolist(), mode="tf32x3")
     assert torch.allclose(fast, exact, rtol=1e-5, atol=1e-5)
+    fast_cl = hdy.multiscale_roi_align([f.contiguous(memory_format=torch.channels_last) for f in feats], boxes, levels,
+                                       g["strides"].tolist(), mode="tf32x3")
+    assert torch.allclose(fast_cl, exact, rtol=1e-5, atol=1e-5)
     with pytest.raises(hdy.HdyError):
         hdy.multiscale_roi_align([f[:, :40].contiguous() for f in feats], boxes, levels, g["strides"].tolist(),
                                  mode="tf32x3")
+    with pytest.raises(hdy.HdyError):       # the exact kernel reads the reference's layout only
+        hdy.multiscale_roi_align([f.contiguous(memory_format=torch.channels_last) for f in feats], boxes, levels,
+                                 g["strides"].tolist())
 
 
 def _rois(gen, K, bs, tile, lo, hi):

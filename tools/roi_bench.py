@@ -33,6 +33,13 @@ def ours_tc():
     return hdy.multiscale_roi_align(feats, rois, levels, strides, 14, 2, False, mode="tf32x3")
 
 
+feats_cl = [f.contiguous(memory_format=torch.channels_last) for f in feats]
+
+
+def ours_tc_cl():
+    return hdy.multiscale_roi_align(feats_cl, rois, levels, strides, 14, 2, False, mode="tf32x3")
+
+
 def reference():
     result = torch.zeros((K, C, 14, 14), device=dev)
     for i, s in enumerate(strides):
@@ -56,6 +63,7 @@ def timed(fn, n=10):
 
 t_ours = timed(ours)
 t_tc = timed(ours_tc)
+t_tc_cl = timed(ours_tc_cl)
 t_ref = timed(reference, 3)
 # agreement on a slice: at the full size torchvision's CUDA kernel indexes its output with a 32-bit int, and level 0
 # alone holds 46 000 x 256 x 196 = 2.3e9 elements -- its result is not usable as a reference there (ours indexes with
@@ -74,8 +82,14 @@ mag = hdy.multiscale_roi_align([f.abs() for f in feats], rois[:n_chk].contiguous
                                strides, 14, 2, False)
 err_tc = ((o_tc - o).abs() / mag.clamp_min(1e-30)).max().item()
 n_exact = int((o_tc == o).flatten(1).all(1).sum())
+o_cl = hdy.multiscale_roi_align(feats_cl, rois[:n_chk].contiguous(), levels[:n_chk].contiguous(), strides, 14, 2, False,
+                                mode="tf32x3")
+err_cl = ((o_cl - o).abs() / mag.clamp_min(1e-30)).max().item()
 print(json.dumps({"K": K, "C": C, "bs": bs, "ms_ours": t_ours, "ms_ours_tf32x3": t_tc,
                   "write_GBs_ours_tf32x3": out_bytes / t_tc / 1e6,
+                  "ms_ours_tf32x3_channels_last": t_tc_cl,
+                  "write_GBs_ours_tf32x3_channels_last": out_bytes / t_tc_cl / 1e6,
+                  "tf32x3_channels_last_max_err_over_tap_magnitude_first_4096_rois": err_cl,
                   "tf32x3_max_err_over_tap_magnitude_first_4096_rois": err_tc,
                   "tf32x3_rows_bit_identical_to_exact_first_4096_rois": n_exact, "ms_torchvision_per_level_loop": t_ref,
                   "out_GB": out_bytes / 1e9, "write_GBs_ours": out_bytes / t_ours / 1e6,
