@@ -82,6 +82,7 @@ struct TcTables {
   unsigned long long mbar;
   unsigned long long ring_bar[2];
   int bnd[2][4];   // window of all taps (ylo, yhi, xlo, xhi), ping-pong over consecutive RoIs
+  int nxt[5];      // the next RoI, worked out one RoI ahead by the idle warp: (fits, xlo, ylo, level, image)
   uint32_t tmem_base;
 };
 constexpr size_t kTcSmemNchw = 2 * kTcABytes + 2 * kTcBBytes + kTcRawBytes + sizeof(TcTables);
@@ -185,6 +186,7 @@ __global__ void __launch_bounds__(kTcThreads, 2) roi_align_tc_kernel(
     nlv = level_of ? __ldg(level_of + blockIdx.x) : 0.f;
   }
   int it = 0;
+  uint32_t pre = 0;   // (thread 0) slices of the coming RoI whose loads were started during the previous one
   for (long long n = blockIdx.x; n < K; n += gridDim.x) {
     const float r[5] = {nr[0], nr[1], nr[2], nr[3], nr[4]};
     const float lv_f = nlv;
@@ -266,24 +268,85 @@ __global__ void __launch_bounds__(kTcThreads, 2) roi_align_tc_kernel(
     const bool b_on = bc < kCg, b_tap = b_on && bjy < span_h && bjx < span_w;
     const int b_slot = (bk >> 2) * kTcBLbo + bc * 16 + (bk & 3) * 4;
     const int b_raw = ((bc * kTcSpan + bjy) * kTcRawX + (xlo & 3) + bjx) * 4;
-#define HDY_TC_LOAD(sl)                                                                                          \
-  if (t == 0) {                                                                                                  \
+    // slice `sl` of the RoI (LV, X, Y, IMG) into TMA buffer sl mod depth
+#define HDY_TC_LOAD_AT(sl, LV, X, Y, IMG)                                                                        \
+  {                                                                                                              \
     if constexpr (NHWC) {                                                                                        \
       uint64_t* bar = reinterpret_cast<uint64_t*>(&T.ring_bar[(sl) & 1]);                                        \
       unsigned char* dst = raw + ((sl) & 1) * kTcNhRing;                                                         \
       mbar_arrive_expect_tx(bar, 2 * 36 * 128);                                                                  \
-      tma_load_4d(dst, &maps.m[lvl], (sl) * kTcN, xlo, ylo, b, bar);                                             \
-      tma_load_4d(dst + kTcNhBlk, &maps.m[lvl], (sl) * kTcN + 32, xlo, ylo, b, bar);                             \
+      tma_load_4d(dst, &maps.m[LV], (sl) * kTcN, X, Y, IMG, bar);                                                \
+      tma_load_4d(dst + kTcNhBlk, &maps.m[LV], (sl) * kTcN + 32, X, Y, IMG, bar);                                \
     } else {                                                                                                     \
       uint64_t* bar = reinterpret_cast<uint64_t*>(&T.ring_bar[0]);                                               \
       mbar_arrive_expect_tx(bar, kTcRawBytes);                                                                   \
-      tma_load_4d(raw, &maps.m[lvl], xlo & ~3, ylo, (sl) * kTcN, b, bar);                                        \
+      tma_load_4d(raw, &maps.m[LV], (X) & ~3, Y, (sl) * kTcN, IMG, bar);                                         \
     }                                                                                                            \
   }
-    HDY_TC_LOAD(0)
-    if constexpr (NHWC) {
-      if (1 < slices) {
-        HDY_TC_LOAD(1)
+    // TMA buffer freed: it takes virtual slice v -- slice v of this RoI, or, past its last slice, slice v - slices of the
+    // NEXT RoI (whose window the idle warp worked out during the A build), so that a RoI's first windows are already
+    // in flight while the previous RoI's last slices are stored.  (Buffer parity carries over when depth divides slices.
+    // Channels-last only: with the NCHW boxes -- 384 requests of 48 bytes each -- starting them earlier measured slower.)
+#define HDY_TC_LOAD(v)                                                                                           \
+  if (t == 0) {                                                                                                  \
+    if ((v) < slices) {                                                                                          \
+      HDY_TC_LOAD_AT(v, lvl, xlo, ylo, b)                                                                        \
+    } else if (NHWC && (v) - slices < kDepth && slices % kDepth == 0 && T.nxt[0]) {                              \
+      HDY_TC_LOAD_AT((v) - slices, T.nxt[3], T.nxt[1], T.nxt[2], T.nxt[4])                                       \
+      pre |= 1u << ((v) - slices);                                                                               \
+    }                                                                                                            \
+  }
+    constexpr int kDepth = NHWC ? 2 : 1;
+    if (t == 0) {   // what the previous RoI did not start already
+      for (int j = 0; j < kDepth && j < slices; ++j)
+        if (!((pre >> j) & 1)) HDY_TC_LOAD_AT(j, lvl, xlo, ylo, b)
+      pre = 0;
+    }
+    // ---- the next RoI's window, by warp 7 (bins 224..255: no A row, no epilogue work): same samples, same decision
+    if (NHWC && warp == 7) {
+      int fit2 = 0, x2 = 0, y2 = 0, l2 = 0, b2 = 0;
+      if (n + gridDim.x < K) {
+        l2 = level_of ? (int)nlv : 0;
+        const bool ok2 = level_of ? (nlv == (float)l2 && l2 >= 0 && l2 < L.nl) : true;
+        b2 = (int)nr[0];
+        if (ok2 && b2 >= 0 && b2 < bs && ((level_mask >> l2) & 1)) {
+          const float scale = L.scale[l2], off = aligned ? 0.5f : 0.0f;
+          const float sw = __fsub_rn(__fmul_rn(nr[1], scale), off), sh = __fsub_rn(__fmul_rn(nr[2], scale), off);
+          const float ew = __fsub_rn(__fmul_rn(nr[3], scale), off), eh = __fsub_rn(__fmul_rn(nr[4], scale), off);
+          float rw = __fsub_rn(ew, sw), rh = __fsub_rn(eh, sh);
+          if (!aligned) {
+            rw = fmaxf(rw, 1.0f);
+            rh = fmaxf(rh, 1.0f);
+          }
+          const float bin_h = __fdiv_rn(rh, (float)M), bin_w = __fdiv_rn(rw, (float)M);
+          int ylo2 = INT_MAX, yhi2 = -1, xlo2 = INT_MAX, xhi2 = -1;
+          for (int i = lane; i < M * S; i += 32) {
+            const SampleTab Y = roi_sample(sh, bin_h, i / S, i % S, S, L.h[l2]);
+            const SampleTab X = roi_sample(sw, bin_w, i / S, i % S, S, L.w[l2]);
+            if (Y.low >= 0) {
+              ylo2 = min(ylo2, Y.low);
+              yhi2 = max(yhi2, Y.high);
+            }
+            if (X.low >= 0) {
+              xlo2 = min(xlo2, X.low);
+              xhi2 = max(xhi2, X.high);
+            }
+          }
+          ylo2 = __reduce_min_sync(0xffffffffu, ylo2);
+          xlo2 = __reduce_min_sync(0xffffffffu, xlo2);
+          yhi2 = __reduce_max_sync(0xffffffffu, yhi2);
+          xhi2 = __reduce_max_sync(0xffffffffu, xhi2);
+          fit2 = yhi2 >= 0 && xhi2 >= 0 && yhi2 - ylo2 + 1 <= kTcSpan && xhi2 - xlo2 + 1 <= kTcSpan;
+          x2 = xlo2;
+          y2 = ylo2;
+        }
+      }
+      if (lane == 0) {
+        T.nxt[0] = fit2;
+        T.nxt[1] = x2;
+        T.nxt[2] = y2;
+        T.nxt[3] = l2;
+        T.nxt[4] = b2;
       }
     }
     // ---- A: thread = output bin, k = jy * 6 + jx
@@ -383,9 +446,7 @@ __global__ void __launch_bounds__(kTcThreads, 2) roi_align_tc_kernel(
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
     __syncthreads();  // (every warp is past the previous RoI's epilogue: both accumulator buffers are free)
     HDY_TC_ISSUE(0)
-    if ((NHWC ? 2 : 1) < slices) {
-      HDY_TC_LOAD(NHWC ? 2 : 1)   // (the TMA buffer was read out before the barrier)
-    }
+    HDY_TC_LOAD(kDepth)   // (TMA buffer 0 was read out before the barrier)
     // one slice: wait for its MMAs; hand slice sl + 1 to the tensor cores; start the load of slice sl + 2; then store
     // slice sl from accumulator buffer P
 #define HDY_TC_STEP(sl, P)                                                                                    \
@@ -399,9 +460,7 @@ __global__ void __launch_bounds__(kTcThreads, 2) roi_align_tc_kernel(
       asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");                                             \
       __syncthreads(); /* every warp is past the epilogue of slice sl - 1, which read the buffer written next */   \
       HDY_TC_ISSUE(1 - (P))                                                                                        \
-      if ((sl) + (NHWC ? 3 : 2) < slices) {                                                                        \
-        HDY_TC_LOAD((sl) + (NHWC ? 3 : 2))                                                                         \
-      }                                                                                                            \
+      HDY_TC_LOAD((sl) + 1 + kDepth)                                                                               \
     }                                                                                                              \
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");                                                \
     /* epilogue: warp -> (M tile, lane quarter); lane = bin, registers = 32 consecutive channels */                \
@@ -430,6 +489,7 @@ __global__ void __launch_bounds__(kTcThreads, 2) roi_align_tc_kernel(
 #undef HDY_TC_SPLIT
 #undef HDY_TC_ISSUE
 #undef HDY_TC_LOAD
+#undef HDY_TC_LOAD_AT
   }
   __syncthreads();
   if (warp == 0)

@@ -1,2 +1,4 @@
 #!/usr/bin/env bash
-timeout 120 python tools/probe/roi_cl_diag.py 2>&1 | tail -14
+mkdir -p gpurun_out
+timeout 600 ncu --set full --clock-control none --import-source on --kernel-name-base demangled -k 'regex:tc_kernel<\(int\)14, \(bool\)1>' -s 3 -c 1 -o gpurun_out/z_roi_cl python tools/roi_bench.py 8192 > gpurun_out/z_ncu.log 2>&1
+tail -3 gpurun_out/z_ncu.log
