@@ -307,11 +307,13 @@ extern "C" int hdy_multiscale_roi_align(const hdy_feature_level_t* levels_host, 
                                         const float* rois, const float* level_of, int64_t K, int pooled,
                                         int sampling_ratio, int aligned, float* out, hdy_stream_t stream) {
   using namespace hdy;
-  RoiLevels L;
-  int rc = roi_levels_from_host(levels_host, nl, &L);
-  if (rc) return rc;
-  rc = roi_align_args_ok(bs, channels, rois, level_of, nl, K, pooled, sampling_ratio, out);
+  HDY_REQUIRE(levels_host != nullptr, "roi_align: levels is NULL");
+  HDY_REQUIRE(nl >= 1 && nl <= HDY_MAX_LEVELS, "roi_align: nl=%d out of range [1,%d]", nl, HDY_MAX_LEVELS);
+  int rc = roi_align_args_ok(bs, channels, rois, level_of, nl, K, pooled, sampling_ratio, out);
   if (rc || K == 0) return rc;
+  RoiLevels L;
+  rc = roi_levels_from_host(levels_host, nl, &L);
+  if (rc) return rc;
   return launch_roi_align_exact(L, bs, channels, rois, level_of, K, pooled, sampling_ratio, aligned, out, nullptr,
                                 (cudaStream_t)stream);
 }

@@ -503,12 +503,14 @@ extern "C" int hdy_multiscale_roi_align_tf32x3(const hdy_feature_level_t* levels
                                                int pooled, int sampling_ratio, int aligned, float* out,
                                                int32_t* fallback, hdy_stream_t stream) {
   using namespace hdy;
+  HDY_REQUIRE(levels_host != nullptr, "roi_align: levels is NULL");
+  HDY_REQUIRE(nl >= 1 && nl <= HDY_MAX_LEVELS, "roi_align: nl=%d out of range [1,%d]", nl, HDY_MAX_LEVELS);
+  int rc = roi_align_args_ok(bs, channels, rois, level_of, nl, K, pooled, sampling_ratio, out);
+  if (rc || K == 0) return rc;
   RoiLevels L;
-  int rc = roi_levels_from_host(levels_host, nl, &L);
+  rc = roi_levels_from_host(levels_host, nl, &L);
   if (rc) return rc;
   L.nhwc = channels_last ? 1 : 0;
-  rc = roi_align_args_ok(bs, channels, rois, level_of, nl, K, pooled, sampling_ratio, out);
-  if (rc || K == 0) return rc;
   HDY_REQUIRE(channels % kTcN == 0, "roi_align (tf32x3): channels=%d must be a multiple of %d", channels, kTcN);
   HDY_REQUIRE(fallback != nullptr, "roi_align (tf32x3): fallback scratch is NULL");
   cudaStream_t st = (cudaStream_t)stream;
