@@ -10,7 +10,8 @@ synthetic 100k x 100k px slide (11 025 tiles of 1024 px, 64 px overlap, ~3 000 n
 nuclei field: per-tile decode+filter+compact -> NMS -> score/label select of this rank's tile rows, append in slide
 coordinates, exact slide-level merge NMS (seam exchange over NCCL when N > 1), then process_mask (32-prototype
 contraction, sigmoid, crop, bilinear upsample, > 0.5, bit-packed) for the rows the merge KEPT.  Strong scaling.
-Short runs of tiles640 / tiles1024 (configs[1] / configs[2]) are attached as sub-records unless --no-sub.
+Short runs of tiles640 / tiles1024 (configs[1] / configs[2]) and of the multi-scale RoIAlign are attached as
+sub-records unless --no-sub.
 
 tiles640 / tiles1024: one "step" = one pass of the per-tile path over one batch of synthetic head outputs (masks
 included).  Weak scaling (every rank processes its own batches; the path has no cross-tile dependency).
@@ -1014,6 +1015,14 @@ def main():
                 t = run_tiles(targs, WORKLOADS[name], c)
                 line[name] = {k: t[k] for k in ("value", "unit", "ms_per_step", "boxes_per_s", "roofline", "stages",
                                                 "pipeline", "gpu_launches", "config")}
+            if c.rank == 0:
+                try:   # the gather in front of the mask head, exact order vs tensor cores
+                    from tools.roi_bench import run_roi
+                    torch.cuda.empty_cache()
+                    line["roi_align"] = run_roi(dev=c.dev, with_torchvision=False)
+                except Exception as e:   # noqa: BLE001  (a sub-record must never take the line down)
+                    line["roi_align"] = {"error": f"{type(e).__name__}: {e}"}
+                torch.cuda.empty_cache()
     elif args.workload == "hnet":
         from tools.hnet_bench import run_hnet     # configs[4]: kept in its own file
         line = run_hnet(args, wl, c, common_config, load_peak, ClockSampler)
