@@ -468,9 +468,20 @@ __global__ void __launch_bounds__(kPmThreads) process_mask_kernel(
         if (yy < mh && xx < mw && (float)xx >= g.x1d && (float)xx < g.x2d && (float)yy >= g.y1d &&
             (float)yy < g.y2d) {
           const size_t p = P0 + (size_t)yy * mw + xx;
+          // (the listed form runs a handful of CTAs: its duration is this latency chain, so all the channel loads of a
+          // pixel are issued before the first FMA -- with 8 in flight the kernel took 4 DRAM round trips per pixel)
           float acc = 0.f;
-#pragma unroll 8
-          for (int c = 0; c < nm; ++c) {
+          int c = 0;
+          for (; c + 32 <= nm; c += 32) {
+            float pv[32];
+#pragma unroll
+            for (int j = 0; j < 32; ++j)
+              pv[j] = HALF ? __half2float(__ldg(static_cast<const __half*>(protos) + p + (c + j) * plane))
+                           : __ldg(static_cast<const float*>(protos) + p + (c + j) * plane);
+#pragma unroll
+            for (int j = 0; j < 32; ++j) acc = fmaf(cf[c + j], pv[j], acc);
+          }
+          for (; c < nm; ++c) {
             const float pv = HALF ? __half2float(__ldg(static_cast<const __half*>(protos) + p + c * plane))
                                   : __ldg(static_cast<const float*>(protos) + p + c * plane);
             acc = fmaf(cf[c], pv, acc);

@@ -48,7 +48,6 @@ class SlidePostprocessor:
         # in tile order through an event chain
         self.n_streams = max(1, int(streams))
         self._side: List[torch.cuda.Stream] = []
-        self._order_stream: Optional[torch.cuda.Stream] = None
         self.device = torch.device(device if device is not None else f"cuda:{torch.cuda.current_device()}")
         self.image_size = (image_size, image_size) if isinstance(image_size, (int, float)) else \
             (image_size[0], image_size[1])
@@ -236,35 +235,10 @@ class SlidePostprocessor:
 
     def run(self, provider, ordered: bool = True, proto_provider=None,
             mask_words_per_row: float = 56.0) -> Dict[str, torch.Tensor]:
-        """detect -> merge -> masks.  With masks AND ordered survivors asked for, the ordering (select, radix sort,
-        gather: scatter-bound work that leaves most of HBM idle) runs on its own stream beside the mask pass, which only
-        needs the verdicts; results are the ones merge(ordered=True) + masks() give."""
+        """detect -> merge -> masks.  (Ordering the survivors on a side stream beside the mask pass was measured: the
+        sort fills the SMs whenever it runs, 72.6 -> 73.3 ms per slide; the phases stay in sequence.)"""
         self.detect(provider, keep_batches=proto_provider is not None)
-        if proto_provider is None or not ordered or self.n_streams == 1:
-            res = self.merge(ordered)
-            if proto_provider is not None:
-                res['masks'] = self.masks(proto_provider, res['state'], words_per_row=mask_words_per_row)
-            return res
-        from .ops import scratch_slot, _slot
-        res = self.merge(ordered=False)
-        n, acc, slot = int(res['n']), self.acc, _slot() * 16 + 7
-        with torch.cuda.device(self.device):
-            cur = torch.cuda.current_stream()
-            if self._order_stream is None:
-                self._order_stream = torch.cuda.Stream()
-            so = self._order_stream
-            so.wait_stream(cur)
-            with torch.cuda.stream(so), scratch_slot(slot):
-                cnt = torch.empty((1,), dtype=torch.int32, device=self.device)
-                keys = _order_keys(res['state'], acc.scores, n, cnt)
+        res = self.merge(ordered)
+        if proto_provider is not None:
             res['masks'] = self.masks(proto_provider, res['state'], words_per_row=mask_words_per_row)
-            with torch.cuda.stream(so), scratch_slot(slot):
-                k = int(cnt.item())          # waits for the sort only; the mask pass is enqueued already
-                idx, ob, os_, ol = _gather_ordered(keys, cnt, k, n, acc.boxes, acc.scores, acc.labels)
-                idx = idx + int(res['base'])
-            cur.wait_stream(so)
-            for t in (idx, ob, os_, ol):
-                if t is not None:
-                    t.record_stream(cur)     # allocated on the ordering stream, consumed on the caller's
-        res.update({'boxes': ob, 'scores': os_, 'labels': ol, 'index': idx})
         return res

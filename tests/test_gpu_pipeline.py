@@ -224,9 +224,9 @@ def test_slide_masks_of_kept_rows_match_oracle(cuda_device):
 
 
 @pytest.mark.parametrize("world", [1, 2])
-def test_run_orders_survivors_beside_the_mask_pass(cuda_device, world):
-    """run(ordered=True, proto_provider=...) with side streams sorts / gathers the survivors on their own stream while
-    the mask pass runs: same survivors in the same order, same mask bits as the one-stream sequence."""
+def test_run_with_side_streams_equals_one_stream(cuda_device, world):
+    """run(ordered=True, proto_provider=...) with three side streams (tile batches and mask batches alternate over
+    them) gives the survivors in the same order and the same mask bits as the one-stream sequence, twice in a row."""
     dev = cuda_device
     size, tile, overlap, md, nm = (1500, 1100), 512, 64, 1200, 32
     spec = hdy.HeadSpec(synth.ANCHORS_3, synth.STRIDES_3, nc=4, no=9 + nm)

@@ -1,4 +1,10 @@
 #!/usr/bin/env bash
 mkdir -p gpurun_out
-timeout 600 ncu --set full --clock-control none --import-source on --kernel-name-base demangled -k 'regex:tc_kernel<\(int\)14, \(bool\)1>' -s 3 -c 1 -o gpurun_out/z_roi_cl python tools/roi_bench.py 8192 > gpurun_out/z_ncu.log 2>&1
-tail -3 gpurun_out/z_ncu.log
+timeout 300 python -m pytest tests/test_gpu_masks.py tests/test_gpu_pipeline.py -q -m gpu 2>&1 | tail -3
+timeout 300 ncu --metrics gpu__time_duration.sum --clock-control none -k regex:process_mask_kernel -s 3 -c 3 python tools/mask_batch_probe.py 3072 2>&1 | grep -i "gpu__time_duration\|process_mask_packed (geom" | head
+python bench.py --steps 5 --warmup 3 --no-sub --no-cpu-baseline --no-torch-cuda --no-e2e > gpurun_out/l_slide.json 2> gpurun_out/l_slide.err
+python - <<'PY'
+import json
+d=json.loads(open('gpurun_out/l_slide.json').read().strip().splitlines()[-1])
+print(d['ms_per_step'], d['roofline']['frac'], d['roofline']['kernel_ms'], {k:d['slide'][k] for k in ('detect_ms','merge_ms','masks_ms')}, d['slide']['digest'], d['slide']['mask_digest'])
+PY

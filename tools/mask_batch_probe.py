@@ -29,3 +29,13 @@ e1.record()
 torch.cuda.synchronize()
 pm.check()
 print("process_mask_packed (geometry + masks) ms per batch:", e0.elapsed_time(e1) / 5, "words", int(pm.offsets[-1]))
+# how many detections the region path handed to the per-detection kernel (first word of the workspace), and their sizes
+ws, _ = hm._pm_workspace(dev, bs, md)
+n_listed = int(ws.view(torch.int32)[0])
+w = (out.boxes[..., 2] - out.boxes[..., 0])
+h = (out.boxes[..., 3] - out.boxes[..., 1])
+valid = torch.arange(md, device=dev)[None, :] < out.counts[:, None]
+big = valid & ((w > 64) | (h > 64))
+print("listed detections in the batch:", n_listed, "| boxes over 64 px:", int(big.sum()),
+      "| largest box side:", float(torch.maximum(w, h)[valid].max()),
+      "| sizes of the big ones:", torch.maximum(w, h)[big].sort(descending=True).values[:12].tolist())
