@@ -1,10 +1,5 @@
 #!/usr/bin/env bash
 mkdir -p gpurun_out
-timeout 300 python -m pytest tests/test_gpu_masks.py tests/test_gpu_pipeline.py -q -m gpu 2>&1 | tail -3
-timeout 300 ncu --metrics gpu__time_duration.sum --clock-control none -k regex:process_mask_kernel -s 3 -c 3 python tools/mask_batch_probe.py 3072 2>&1 | grep -i "gpu__time_duration\|process_mask_packed (geom" | head
-python bench.py --steps 5 --warmup 3 --no-sub --no-cpu-baseline --no-torch-cuda --no-e2e > gpurun_out/l_slide.json 2> gpurun_out/l_slide.err
-python - <<'PY'
-import json
-d=json.loads(open('gpurun_out/l_slide.json').read().strip().splitlines()[-1])
-print(d['ms_per_step'], d['roofline']['frac'], d['roofline']['kernel_ms'], {k:d['slide'][k] for k in ('detect_ms','merge_ms','masks_ms')}, d['slide']['digest'], d['slide']['mask_digest'])
-PY
+python -m pytest tests -x -q -m gpu 2>&1 | tail -3 > gpurun_out/final_pytest.txt; cat gpurun_out/final_pytest.txt
+python __graft_entry__.py smoke 2>&1 | tail -2 > gpurun_out/final_smoke.txt; cat gpurun_out/final_smoke.txt
+python bench.py > gpurun_out/final_bench_default.json 2> gpurun_out/final_bench_default.err; tail -2 gpurun_out/final_bench_default.err
