@@ -124,6 +124,140 @@ __device__ __forceinline__ PMGeom pm_geometry(const float4 b, int mh, int mw, in
 }
 
 
+// smallest dst in [lo, hi) whose first tap lerp_coord(dst).i0 is >= target (hi if there is none)
+__device__ __forceinline__ int first_dst_i0_ge(int target, int lo, int hi, float scale, int in_size) {
+  while (lo < hi) {
+    const int mid = (lo + hi) >> 1;
+    if (lerp_coord(mid, scale, in_size).i0 >= target)
+      hi = mid;
+    else
+      lo = mid + 1;
+  }
+  return lo;
+}
+
+constexpr int kPmTile = 32;               // proto pixels per staged tile side
+constexpr int kPmStage = kPmTile + 1;     // + 1 halo for the second bilinear tap
+
+// One CTA per detection slot.  For every kPmTile^2 block of proto pixels touching the mask's window the
+// cropped sigmoid(coef . proto) values are staged in shared memory (32 FFMA per pixel, channel-strided
+// coalesced reads that hit L2 after the first detection of a tile), then the output pixels whose first tap
+// falls into the block are emitted.
+// `stage` [kPmStage^2] and `cf` [64] floats of shared memory are the caller's (static in process_mask_kernel, a corner of
+// the region buffer when the listed detections ride in proto_patch_kernel's launch); every thread of the CTA calls it.
+// Items item_first, item_first + item_step, ... < n_items; of each item the proto tiles tile_first, + tile_step, ...
+template <bool PACKED, bool HALF>
+__device__ __forceinline__ void process_mask_body(
+    const void* __restrict__ protos, const float* __restrict__ coef, const float4* __restrict__ boxes,
+    const int32_t* __restrict__ counts, int max_det, int nm, int mh, int mw, int ih, int iw, int upsample,
+    float rx, float ry, float* __restrict__ out_dense, const int32_t* __restrict__ geom4,
+    const int64_t* __restrict__ offsets,
+    uint32_t* __restrict__ bits, long long capacity_words, int32_t* __restrict__ status,
+    const int32_t* __restrict__ slot_list, long long n_items, long long item_first, long long item_step,
+    int tile_first, int tile_step, float* __restrict__ stage, float* __restrict__ cf) {
+  const int nthreads = blockDim.x;
+  for (long long item = item_first; item < n_items; item += item_step) {
+  const long long slot = slot_list ? (long long)slot_list[item] : item;
+  const int tile = (int)(slot / max_det), d = (int)(slot - (long long)tile * max_det);
+  __syncthreads();  // cf / stage of the previous item are free
+  if (d >= counts[tile]) continue;
+  if (geom4 && (geom4[4 * slot + 2] <= 0 || geom4[4 * slot + 3] <= 0)) continue;  // empty, or not KEPT (slide form)
+  const PMGeom g = pm_geometry(boxes[slot], mh, mw, ih, iw, upsample, rx, ry);
+  if (g.w <= 0 || g.h <= 0) continue;
+  const int oh = upsample ? ih : mh, ow = upsample ? iw : mw;
+  const int wpr = (g.w + 31) >> 5;
+  long long off = 0;
+  if (PACKED) {
+    off = offsets[slot];
+    if (off + (long long)wpr * g.h > capacity_words) {
+      if (threadIdx.x == 0) atomicOr(status, HDY_STATUS_OVERFLOW);
+      continue;
+    }
+  }
+  for (int c = threadIdx.x; c < nm; c += nthreads) cf[c] = coef[slot * nm + c];
+  const size_t P0 = (size_t)tile * nm * mh * mw;  // first element of the tile's prototypes
+  const size_t plane = (size_t)mh * mw;
+  const float sxs = (float)mw / (float)iw, sys = (float)mh / (float)ih;  // ATen: scale = in / out (fp32)
+  // proto range that can contribute: the kept pixels, plus one pixel before (their second-tap neighbours)
+  const int ty_begin = upsample ? max(g.py0 - 1, 0) : g.py0, tx_begin = upsample ? max(g.px0 - 1, 0) : g.px0;
+  const int nty = (g.py1 - ty_begin + kPmTile - 1) / kPmTile, ntx = (g.px1 - tx_begin + kPmTile - 1) / kPmTile;
+  for (int tt = tile_first; tt < nty * ntx; tt += tile_step) {
+    {
+      const int ty = ty_begin + (tt / ntx) * kPmTile, tx = tx_begin + (tt % ntx) * kPmTile;
+      __syncthreads();
+      // ---- stage cropped sigmoid values for proto pixels [ty, ty+33) x [tx, tx+33)
+      for (int e = threadIdx.x; e < kPmStage * kPmStage; e += nthreads) {
+        const int yy = ty + e / kPmStage, xx = tx + e % kPmStage;
+        float v = 0.f;
+        if (yy < mh && xx < mw && (float)xx >= g.x1d && (float)xx < g.x2d && (float)yy >= g.y1d &&
+            (float)yy < g.y2d) {
+          const size_t p = P0 + (size_t)yy * mw + xx;
+          // (the listed form runs a handful of CTAs: its duration is this latency chain, so all the channel loads of a
+          // pixel are issued before the first FMA -- with 8 in flight the kernel took 4 DRAM round trips per pixel)
+          float acc = 0.f;
+          int c = 0;
+          for (; c + 32 <= nm; c += 32) {
+            float pv[32];
+#pragma unroll
+            for (int j = 0; j < 32; ++j)
+              pv[j] = HALF ? __half2float(__ldg(static_cast<const __half*>(protos) + p + (c + j) * plane))
+                           : __ldg(static_cast<const float*>(protos) + p + (c + j) * plane);
+#pragma unroll
+            for (int j = 0; j < 32; ++j) acc = fmaf(cf[c + j], pv[j], acc);
+          }
+          for (; c < nm; ++c) {
+            const float pv = HALF ? __half2float(__ldg(static_cast<const __half*>(protos) + p + c * plane))
+                                  : __ldg(static_cast<const float*>(protos) + p + c * plane);
+            acc = fmaf(cf[c], pv, acc);
+          }
+          v = sigmoidf_ref(acc);
+        }
+        stage[e] = v;
+      }
+      __syncthreads();
+      if (!upsample) {
+        // output pixel == proto pixel
+        const int y_lo = max(ty, g.y0), y_hi = min(ty + kPmTile, g.y0 + g.h);
+        const int x_lo = max(tx, g.x0), x_hi = min(tx + kPmTile, g.x0 + g.w);
+        const int tw = x_hi - x_lo, th = y_hi - y_lo;
+        for (int e = threadIdx.x; e < tw * th; e += nthreads) {
+          const int yy = y_lo + e / tw, xx = x_lo + e % tw;
+          const bool bit = stage[(yy - ty) * kPmStage + (xx - tx)] > 0.5f;
+          if (PACKED) {
+            if (bit) atomicOr(&bits[off + (long long)(yy - g.y0) * wpr + ((xx - g.x0) >> 5)], 1u << ((xx - g.x0) & 31));
+          } else {
+            out_dense[(size_t)slot * oh * ow + (size_t)yy * ow + xx] = bit ? 1.f : 0.f;
+          }
+        }
+      } else {
+        // output pixels of the window whose first taps (i0) fall into [ty, ty+32) x [tx, tx+32): i0 is monotone in the
+        // output coordinate, so they form a rectangle whose edges are found by bisection (scanning the whole window
+        // for every tile made a large box quadratic in its tile count)
+        const int oy_lo = first_dst_i0_ge(ty, g.y0, g.y0 + g.h, sys, mh);
+        const int oy_hi = first_dst_i0_ge(ty + kPmTile, oy_lo, g.y0 + g.h, sys, mh);
+        const int ox_lo = first_dst_i0_ge(tx, g.x0, g.x0 + g.w, sxs, mw);
+        const int ox_hi = first_dst_i0_ge(tx + kPmTile, ox_lo, g.x0 + g.w, sxs, mw);
+        const int tw = ox_hi - ox_lo, th = oy_hi - oy_lo;
+        for (int e = threadIdx.x; e < tw * th; e += nthreads) {
+          const int oy = oy_lo + e / tw, ox = ox_lo + e % tw;
+          const Lerp Y = lerp_coord(oy, sys, mh), X = lerp_coord(ox, sxs, mw);
+          const int sy0 = Y.i0 - ty, sx0 = X.i0 - tx, sy1 = Y.i1 - ty, sx1 = X.i1 - tx;
+          const float v = bilerp(stage[sy0 * kPmStage + sx0], stage[sy0 * kPmStage + sx1],
+                                 stage[sy1 * kPmStage + sx0], stage[sy1 * kPmStage + sx1], X, Y);
+          const bool bit = v > 0.5f;
+          if (PACKED) {
+            if (bit) atomicOr(&bits[off + (long long)(oy - g.y0) * wpr + ((ox - g.x0) >> 5)], 1u << ((ox - g.x0) & 31));
+          } else {
+            out_dense[(size_t)slot * oh * ow + (size_t)oy * ow + ox] = bit ? 1.f : 0.f;
+          }
+        }
+      }
+    }
+  }
+  }
+}
+
+
 // mask_regions.cu: two-phase process_mask (TMA-staged prototypes -> sigmoid patches -> upsample + pack).  Returns 1
 // when the shapes / workspace do not meet its requirements (the caller then uses the per-detection kernel in mask.cu).
 constexpr int kPatchPitch = 16;  // sigmoid patches of up to 16 x 16 proto pixels go through the workspace

@@ -184,19 +184,49 @@ __device__ __forceinline__ void contract_piece(const E (*proto)[kRegBoxY][kRegBo
   }
 }
 
+// The detections the patch path leaves out (listed by the binning kernel: windows over 16 x 16 proto pixels, overfull
+// regions) ride in the same launch: the first `ctas` CTAs run the per-detection body of mask.cu on them (64 proto tiles
+// x ctas / 64 list strides), in a corner of the region buffer, while the others stream the regions.  As a kernel of its
+// own behind the upsample that work was a 27-70 us latency chain in a handful of CTAs at the end of every mask call.
+struct ListedRide {
+  const void* protos;
+  const float4* boxes;
+  const int64_t* offsets;
+  uint32_t* bits;
+  int32_t* status;
+  const int32_t* list;
+  const int32_t* list_count;
+  long long capacity_words;
+  float rx, ry;
+  int nm, mh, mw, ih, iw;
+  int ctas;   // 0: nothing rides (dense / not upsampled forms keep the separate launch)
+};
+constexpr int kListedTiles = 64;
+
 template <typename E>
 __global__ void __launch_bounds__(kRegThreads, 3) proto_patch_kernel(
     const __grid_constant__ CUtensorMap tmap, const float* __restrict__ coef, const int4* __restrict__ krs,
     const int32_t* __restrict__ counts, int max_det, int rxn, int ryn, float* __restrict__ patches,
-    const RegionList* __restrict__ regions) {
+    const RegionList* __restrict__ regions, const ListedRide LR) {
   extern __shared__ __align__(128) unsigned char smem_raw[];
+  if ((int)blockIdx.x < LR.ctas) {
+    float* stage = reinterpret_cast<float*>(smem_raw);
+    process_mask_body<true, sizeof(E) == 2>(LR.protos, coef, LR.boxes, counts, max_det, LR.nm, LR.mh, LR.mw, LR.ih, LR.iw,
+                                            1, LR.rx, LR.ry, nullptr, nullptr, LR.offsets, LR.bits, LR.capacity_words,
+                                            LR.status, LR.list, (long long)*LR.list_count,
+                                            (long long)(blockIdx.x / kListedTiles), (long long)(LR.ctas / kListedTiles),
+                                            (int)(blockIdx.x % kListedTiles), kListedTiles, stage,
+                                            stage + kPmStage * kPmStage);
+    return;
+  }
+  const int bid = (int)blockIdx.x - LR.ctas;
   RegSmemT<E>& S = *reinterpret_cast<RegSmemT<E>*>(smem_raw);
   const int t = threadIdx.x, lane = t & 31, warp = t >> 5;
   const int per_tile = rxn * ryn;
-  const int tile = blockIdx.x / per_tile, reg = blockIdx.x - tile * per_tile;
+  const int tile = bid / per_tile, reg = bid - tile * per_tile;
   const int RY = reg / rxn, RX = reg - RY * rxn;
   const int X0 = RX * kRegBoxX, Y0 = RY * kRegBoxY;
-  const RegionList& RL = regions[blockIdx.x];
+  const RegionList& RL = regions[bid];
   const int listed = RL.count;
   if (listed <= 0) return;  // nothing reaches into this region: no load at all
   const bool use_list = listed <= kRegCap;
@@ -906,14 +936,22 @@ int launch_process_mask_regions(const void* protos, int proto_dtype, const float
           }
         }
       }
+      // the listed detections' words are cleared first (their tiles OR into them), then they ride in the region launch
+      pm_clear_listed_kernel<<<148, 256, 0, stream>>>(geom, offsets, bits, capacity_words, W.large_list, W.large_count);
+      ListedRide LR;
+      LR.protos = protos, LR.boxes = b4, LR.offsets = offsets, LR.bits = bits, LR.status = status;
+      LR.list = W.large_list, LR.list_count = W.large_count, LR.capacity_words = capacity_words;
+      LR.rx = rx, LR.ry = ry, LR.nm = nm, LR.mh = mh, LR.mw = mw, LR.ih = ih, LR.iw = iw;
+      LR.ctas = kListedTiles * 9;
       if (half)
-        proto_patch_kernel<__half><<<(unsigned)n_items, kRegThreads, psmem, stream>>>(
-            map, coef, W.kr, counts, max_det, rxn, ryn, W.patches, W.regions);
+        proto_patch_kernel<__half><<<(unsigned)(n_items + LR.ctas), kRegThreads, psmem, stream>>>(
+            map, coef, W.kr, counts, max_det, rxn, ryn, W.patches, W.regions, LR);
       else
-        proto_patch_kernel<float><<<(unsigned)n_items, kRegThreads, psmem, stream>>>(
-            map, coef, W.kr, counts, max_det, rxn, ryn, W.patches, W.regions);
+        proto_patch_kernel<float><<<(unsigned)(n_items + LR.ctas), kRegThreads, psmem, stream>>>(
+            map, coef, W.kr, counts, max_det, rxn, ryn, W.patches, W.regions, LR);
       mask_upsample_pack2_kernel<<<(unsigned)((slots + kFuWarps - 1) / kFuWarps), kFuThreads, 0, stream>>>(
           W.patches, W.kr, geom, offsets, slots, mh, mw, sxs, sys, bits, capacity_words, status);
+      return check_launch("hdy_process_mask(packed)");
     }
     pm_clear_listed_kernel<<<148, 256, 0, stream>>>(geom, offsets, bits, capacity_words, W.large_list, W.large_count);
     int rcf = check_launch("hdy_process_mask(packed)");
@@ -922,14 +960,16 @@ int launch_process_mask_regions(const void* protos, int proto_dtype, const float
                                       rx, ry, nullptr, offsets, bits, capacity_words, status, W.large_list,
                                       W.large_count, stream);
   }
+  ListedRide no_ride;
+  memset(&no_ride, 0, sizeof(no_ride));
   proto_bin_kernel<<<(unsigned)((slots + 255) / 256), 256, 0, stream>>>(b4, counts, slots, max_det, mh, mw, rxn, ryn, rx,
                                                                         ry, geom, W.regions, W.kr);
   if (half)
     proto_patch_kernel<__half><<<(unsigned)((long long)bs * rxn * ryn), kRegThreads, sizeof(RegSmemT<__half>), stream>>>(
-        map, coef, W.kr, counts, max_det, rxn, ryn, W.patches, W.regions);
+        map, coef, W.kr, counts, max_det, rxn, ryn, W.patches, W.regions, no_ride);
   else
     proto_patch_kernel<float><<<(unsigned)((long long)bs * rxn * ryn), kRegThreads, sizeof(RegSmemT<float>), stream>>>(
-        map, coef, W.kr, counts, max_det, rxn, ryn, W.patches, W.regions);
+        map, coef, W.kr, counts, max_det, rxn, ryn, W.patches, W.regions, no_ride);
   const unsigned g2 = (unsigned)((slots + kUpWarps - 1) / kUpWarps);
   const bool packed = out_dense == nullptr;
 #define HDY_UP(P, U)                                                                                              \
