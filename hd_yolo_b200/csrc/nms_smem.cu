@@ -414,7 +414,7 @@ __device__ __forceinline__ int fast_classify(const float4& b, const FastGeom& g,
 }
 
 template <int THREADS, int CAP>
-__global__ void __launch_bounds__(THREADS, 1) nms_tiles_smem_kernel(
+__global__ void __maxnreg__(CAP <= 3072 ? 56 : 64) nms_tiles_smem_kernel(
     const uint64_t* __restrict__ cand_keys, const float4* __restrict__ cand_boxes,
     const float* __restrict__ cand_cls, const int32_t* __restrict__ counts, int cap, float thr, float class_offset,
     int max_nms, int max_det, int32_t* __restrict__ keep_idx, int32_t* __restrict__ keep_slot,
